@@ -1,0 +1,1995 @@
+// The scheduling program of the B200-native HiveD hot path (device code; see hived_prims.h for
+// the execution model).  It implements, over the flat HBM-resident arrays of hived_dev.h, the
+// behaviour of the reference's pkg/algorithm (HivedAlgorithm.Schedule -> intra-VC topology-aware
+// search -> buddy-cell virtual->physical mapping -> commit) — each function cites the reference
+// lines whose observable behaviour it reproduces.  This is a re-design, not a translation:
+//   * cells are ids into SoA arrays; children / leaves of a cell are contiguous id ranges;
+//   * per-priority used-leaf maps are not stored: used[q](cell) == #leaves below it with priority q,
+//     so a cluster-view node's sort key is recomputed from its leaf priorities with coalesced loads;
+//   * free / bad-free / doomed lists keep the reference's order semantics (append, swap-remove) but
+//     carry a position index per cell, so contains/remove are O(1) instead of linear scans;
+//   * findPhysicalLeafCell's scan over all leaves is a (node, chain) -> leaves table lookup;
+//   * the cluster-view pass (key computation, stable sort, greedy first-fit) is data-parallel over
+//     the whole CTA; everything else is warp-uniform control flow on the leader warp.
+#pragma once
+#include "../../include/hived.h"
+#include "hived_dev.h"
+#include "hived_prims.h"
+
+namespace hived {
+
+#ifndef HIVED_MAXL_DEFINED
+#define HIVED_MAXL_DEFINED
+#ifndef HIVED_TOPO_CONSTS
+constexpr int MAXL = 16;
+constexpr int MAX_NODE_LEAVES = 64;
+constexpr int MAX_FANOUT = 64;
+#endif
+#endif
+
+constexpr int MAX_BINS = 4 * (MAX_NODE_LEAVES + 1);
+constexpr int MAX_WARPS = 32;
+constexpr int FREE_PRIO = HIVED_FREE_PRIORITY;
+constexpr int OPP_PRIO = HIVED_OPPORTUNISTIC_PRIORITY;
+
+// shared-memory block of the CTA
+struct Sm {
+  int cmd;        // 0 idle, 1 view pass, 2 exit
+  // ---- view-pass arguments
+  int a_sched, a_prio, a_ignore, a_npods;
+  const uint32_t* a_sugg;
+  // ---- view-pass results
+  int r_ok, r_reason, r_cell;
+  // ---- scratch
+  int best;
+  int nbins;
+  int cnt[MAX_BINS * MAX_WARPS];
+  int part[1024 + 64];
+  // ---- event-scoped state (leader)
+  int panic;        // sticky platform-error code of the current event
+  long long pool_off;
+};
+
+enum { CMD_IDLE = 0, CMD_VIEW = 1, CMD_EXIT = 2 };
+
+struct Core {
+  const Dev& d;
+  Sm* sm;
+  const uint32_t* sugg;  // suggested-node bitmap of the current event (nullptr = every node)
+  int32_t* pool;
+  long long pool_cap;
+  HIVED_DEV Core(const Dev& dev, Sm* s, int32_t* pool_, long long cap) : d(dev), sm(s), sugg(nullptr), pool(pool_), pool_cap(cap) {}
+
+  // ======================================================================================
+  // small helpers
+  // ======================================================================================
+  HIVED_DEV void panic(int code) { if (sm->panic == 0) HV_ST(&sm->panic, code); }
+  HIVED_DEV bool node_suggested(int node) const {
+    if (sugg == nullptr) return true;
+    if (node < 0) return false;
+    return (sugg[node >> 5] >> (node & 31)) & 1u;
+  }
+  HIVED_DEV void stat_add(int which, long long v) { HV_ST(&d.stats[which], d.stats[which] + v); }
+  HIVED_DEV int cl(int chain, int level) const { return chain * MAXL + level; }
+  HIVED_DEV int vcl(int vc, int chain, int level) const { return (vc * d.S.nChains + chain) * MAXL + level; }
+
+  // ---- free list of the physical cluster: order semantics of types.go:78-95 (swap-remove) and append
+  HIVED_DEV void fl_append(int chain, int level, int cell) {
+    int k = cl(chain, level);
+    int n = d.fl_len[k];
+    HV_ST(&d.fl_data[d.fl_base[k] + n], cell);
+    HV_ST(&d.p_flpos[cell], n);
+    HV_ST(&d.fl_len[k], n + 1);
+  }
+  HIVED_DEV void fl_remove(int chain, int level, int cell) {
+    int k = cl(chain, level);
+    int pos = d.p_flpos[cell];
+    if (pos < 0) { panic(HIVED_ERR_PLATFORM); return; }  // "Cell not not found in list when removing"
+    int n = d.fl_len[k];
+    int last = d.fl_data[d.fl_base[k] + n - 1];
+    HV_ST(&d.fl_data[d.fl_base[k] + pos], last);
+    HV_ST(&d.p_flpos[last], pos);
+    HV_ST(&d.p_flpos[cell], -1);
+    HV_ST(&d.fl_len[k], n - 1);
+  }
+  HIVED_DEV bool fl_contains(int cell) const { return d.p_flpos[cell] >= 0; }
+  // ---- bad free cells (badFreeCells, hived_algorithm.go:78)
+  HIVED_DEV void bf_append(int chain, int level, int cell) {
+    int k = cl(chain, level);
+    int n = d.bf_len[k];
+    HV_ST(&d.bf_data[d.fl_base[k] + n], cell);
+    HV_ST(&d.p_bfpos[cell], n);
+    HV_ST(&d.bf_len[k], n + 1);
+  }
+  HIVED_DEV void bf_remove(int chain, int level, int cell) {
+    int k = cl(chain, level);
+    int pos = d.p_bfpos[cell];
+    if (pos < 0) { panic(HIVED_ERR_PLATFORM); return; }
+    int n = d.bf_len[k];
+    int last = d.bf_data[d.fl_base[k] + n - 1];
+    HV_ST(&d.bf_data[d.fl_base[k] + pos], last);
+    HV_ST(&d.p_bfpos[last], pos);
+    HV_ST(&d.p_bfpos[cell], -1);
+    HV_ST(&d.bf_len[k], n - 1);
+  }
+  // ---- doomed bad cells of a VC (vcDoomedBadCells, hived_algorithm.go:80)
+  HIVED_DEV void dm_append(int vc, int chain, int level, int cell) {
+    int k = vcl(vc, chain, level);
+    int n = d.dm_len[k];
+    if (n >= d.dm_cap[k]) { panic(HIVED_ERR_PLATFORM); return; }
+    HV_ST(&d.dm_data[d.dm_base[k] + n], cell);
+    HV_ST(&d.p_dmpos[cell], n);
+    HV_ST(&d.p_dmvc[cell], vc);
+    HV_ST(&d.dm_len[k], n + 1);
+  }
+  HIVED_DEV void dm_remove(int vc, int chain, int level, int cell) {
+    int k = vcl(vc, chain, level);
+    int pos = d.p_dmpos[cell];
+    if (pos < 0 || d.p_dmvc[cell] != vc) { panic(HIVED_ERR_PLATFORM); return; }
+    int n = d.dm_len[k];
+    int last = d.dm_data[d.dm_base[k] + n - 1];
+    HV_ST(&d.dm_data[d.dm_base[k] + pos], last);
+    HV_ST(&d.p_dmpos[last], pos);
+    HV_ST(&d.p_dmpos[cell], -1);
+    HV_ST(&d.p_dmvc[cell], -1);
+    HV_ST(&d.dm_len[k], n - 1);
+  }
+  HIVED_DEV bool dm_contains(int vc, int cell) const { return d.p_dmpos[cell] >= 0 && d.p_dmvc[cell] == vc; }
+
+  // ======================================================================================
+  // cell primitives
+  // ======================================================================================
+  // utils.go:381-391
+  HIVED_DEV bool inFreeCellList(int c) const {
+    while (true) {
+      if (d.p_vcell[c] >= 0 || d.p_split[c]) return false;
+      int par = d.p_parent[c];
+      if (par < 0 || d.p_split[par]) return true;
+      c = par;
+    }
+  }
+  // cell.go:195-204 + utils.go:397-415
+  HIVED_DEV void setCellState(int c, int s) {
+    while (true) {
+      HV_ST(&d.p_state[c], s);
+      int vc = d.p_vcell[c];
+      if (vc >= 0) HV_ST(&d.v_state[vc], s);
+      int par = d.p_parent[c];
+      if (par < 0) return;
+      if (s != HIVED_CELL_USED) {
+        bool all = true;
+        int c0 = d.p_child0[par], n = d.p_nchild[par];
+        for (int i = 0; i < n; i++)
+          if (d.p_state[c0 + i] != s) { all = false; break; }
+        if (!all) return;
+      }
+      c = par;
+    }
+  }
+  // cell_allocation.go:422-441, physical tree
+  HIVED_DEV void setPriorityP(int c, int p) {
+    while (true) {
+      int orig = d.p_prio[c];
+      HV_ST(&d.p_prio[c], p);
+      int par = d.p_parent[c];
+      if (par < 0) return;
+      int pp = d.p_prio[par];
+      if (p > pp) { c = par; continue; }
+      if (orig == pp && p < orig) {
+        int mx = FREE_PRIO;
+        int c0 = d.p_child0[par], n = d.p_nchild[par];
+        for (int i = 0; i < n; i++) { int q = d.p_prio[c0 + i]; if (q > mx) mx = q; }
+        c = par; p = mx; continue;
+      }
+      return;
+    }
+  }
+  HIVED_DEV void setPriorityV(int c, int p) {
+    while (true) {
+      int orig = d.v_prio[c];
+      HV_ST(&d.v_prio[c], p);
+      int par = d.v_parent[c];
+      if (par < 0) return;
+      int pp = d.v_prio[par];
+      if (p > pp) { c = par; continue; }
+      if (orig == pp && p < orig) {
+        int mx = FREE_PRIO;
+        int c0 = d.v_child0[par], n = d.v_nchild[par];
+        for (int i = 0; i < n; i++) { int q = d.v_prio[c0 + i]; if (q > mx) mx = q; }
+        c = par; p = mx; continue;
+      }
+      return;
+    }
+  }
+  // cell_allocation.go:443-454 — only the opportunistic count of physical cells is ever read back
+  // (getUsablePhysicalCells :238-241); every other used[] value is recomputed from leaf priorities.
+  HIVED_DEV void updateUsedOpp(int c, int delta) {
+    while (c >= 0) { HV_ST(&d.p_usedopp[c], d.p_usedopp[c] + delta); c = d.p_parent[c]; }
+  }
+  // cell.go:264-277, 401-419
+  HIVED_DEV void bindPair(int pc, int vc) {
+    HV_ST(&d.p_vcell[pc], vc);
+    HV_ST(&d.v_pcell[vc], pc);
+    HV_ST(&d.v_healthy[vc], d.p_healthy[pc]);
+  }
+  HIVED_DEV void unbindPair(int pc, int vc) {
+    HV_ST(&d.p_vcell[pc], -1);
+    HV_ST(&d.v_pcell[vc], -1);
+    HV_ST(&d.v_state[vc], HIVED_CELL_FREE);
+    HV_ST(&d.v_healthy[vc], 1);
+  }
+  // cell_allocation.go:384-397
+  HIVED_DEV void bindCell(int pc, int vc) {
+    while (d.v_pcell[vc] < 0) {
+      bindPair(pc, vc);
+      if (d.v_parent[vc] < 0) break;
+      vc = d.v_parent[vc];
+      pc = d.p_parent[pc];
+    }
+  }
+  // cell_allocation.go:399-420
+  HIVED_DEV void unbindCell(int c) {
+    int bv = d.p_vcell[c];
+    while (!(d.p_flags[d.v_pcell[bv]] & PF_PINNED_BIT)) {
+      int bp = d.v_pcell[bv];
+      unbindPair(bp, bv);
+      int par = d.v_parent[bv];
+      if (par < 0) return;
+      int c0 = d.v_child0[par], n = d.v_nchild[par];
+      for (int i = 0; i < n; i++)
+        if (d.v_pcell[c0 + i] >= 0) return;
+      bv = par;
+    }
+  }
+  static constexpr int PF_AT_OR_ABOVE_NODE_BIT = 1, PF_NODE_LEVEL_BIT = 2, PF_PINNED_BIT = 4;
+
+  // cell_allocation.go:374-382 over a contiguous child range
+  HIVED_DEV int unboundChild(int vparent) const {
+    int c0 = d.v_child0[vparent], n = d.v_nchild[vparent];
+    for (int i = 0; i < n; i++)
+      if (d.v_pcell[c0 + i] < 0) return c0 + i;
+    return -1;
+  }
+
+  // ======================================================================================
+  // bad cells, doomed bad cells, preassigned cell (de)allocation  (hived_algorithm.go:466-653, 1354-1565)
+  // ======================================================================================
+  // hived_algorithm.go:1502-1527
+  HIVED_DEV int removeCellFromFreeList(int c) {
+    int chain = d.p_chain[c];
+    while (true) {
+      int l = d.p_level[c];
+      int par = d.p_parent[c];
+      bool terminate = false;
+      if (par >= 0) {
+        if (d.p_split[par]) {
+          terminate = true;
+        } else {
+          int c0 = d.p_child0[par], n = d.p_nchild[par];
+          for (int i = 0; i < n; i++) fl_append(chain, l, c0 + i);
+          HV_ST(&d.p_split[par], 1);
+        }
+      } else {
+        terminate = true;
+      }
+      fl_remove(chain, l, c);
+      if (terminate) return l;
+      c = par;
+    }
+  }
+  // hived_algorithm.go:1529-1565
+  HIVED_DEV int addCellToFreeList(int c) {
+    int chain = d.p_chain[c];
+    while (true) {
+      int l = d.p_level[c];
+      int par = d.p_parent[c];
+      bool terminate = false;
+      if (par >= 0) {
+        bool allBuddyFree = true;
+        int c0 = d.p_child0[par], n = d.p_nchild[par];
+        for (int i = 0; i < n; i++)
+          if (c0 + i != c && !fl_contains(c0 + i)) { allBuddyFree = false; break; }
+        if (!allBuddyFree) {
+          terminate = true;
+        } else {
+          for (int i = 0; i < n; i++)
+            if (c0 + i != c) fl_remove(chain, l, c0 + i);
+          HV_ST(&d.p_split[par], 0);
+        }
+      } else {
+        terminate = true;
+      }
+      if (terminate) { fl_append(chain, l, c); return l; }
+      c = par;
+    }
+  }
+
+  // hived_algorithm.go:602-628 (VCs in ascending id order)
+  HIVED_DEV_NOINLINE void tryBindDoomedBadCell(int chain, int l) {
+    int k = cl(chain, l);
+    for (int vc = 0; vc < d.S.nVCs; vc++) {
+      if (!d.vc_chain_counter[vc * d.S.nChains + chain]) continue;
+      int kv = vcl(vc, chain, l);
+      int guard = 0;
+      while (d.vcFree[kv] > d.totalLeft[k] - d.bf_len[k]) {
+        if (d.bf_len[k] <= 0 || ++guard > d.S.NP) { panic(HIVED_ERR_PLATFORM); return; }
+        int pc = d.bf_data[d.fl_base[k] + 0];
+        int vcell = -1;
+        for (int i = 0; i < d.pre_cnt[kv]; i++) {
+          int cand = d.pre_list[d.pre_off[kv] + i];
+          if (d.v_pcell[cand] < 0) { vcell = cand; break; }
+        }
+        if (vcell < 0) { panic(HIVED_ERR_PLATFORM); return; }
+        bindPair(pc, vcell);
+        dm_append(vc, chain, l, pc);
+        HV_ST(&d.allVCDoomed[k], d.allVCDoomed[k] + 1);
+        allocatePreassignedCell(pc, vc, true);
+        if (sm->panic) return;
+      }
+    }
+  }
+  // hived_algorithm.go:630-653
+  HIVED_DEV_NOINLINE void tryUnbindDoomedBadCell(int chain, int l) {
+    int k = cl(chain, l);
+    for (int vc = 0; vc < d.S.nVCs; vc++) {
+      if (!d.vc_chain_counter[vc * d.S.nChains + chain]) continue;
+      int kv = vcl(vc, chain, l);
+      int guard = 0;
+      while (d.dm_len[kv] != 0 && d.vcFree[kv] < d.totalLeft[k] - d.bf_len[k]) {
+        if (++guard > d.S.NP) { panic(HIVED_ERR_PLATFORM); return; }
+        int pc = d.dm_data[d.dm_base[kv] + 0];
+        unbindPair(pc, d.p_vcell[pc]);
+        dm_remove(vc, chain, l, pc);
+        HV_ST(&d.allVCDoomed[k], d.allVCDoomed[k] - 1);
+        releasePreassignedCell(pc, vc, true);
+        if (sm->panic) return;
+      }
+    }
+  }
+  // hived_algorithm.go:1429-1447
+  HIVED_DEV_NOINLINE void allocateBadCell(int c) {
+    if (d.p_bfpos[c] >= 0) bf_remove(d.p_chain[c], d.p_level[c], c);
+    if (d.p_vcell[c] < 0) {
+      int par = d.p_parent[c];
+      int pv = par >= 0 ? d.p_vcell[par] : -1;
+      int vc = pv >= 0 ? unboundChild(pv) : -1;
+      if (vc < 0) { panic(HIVED_ERR_PLATFORM); return; }
+      bindPair(c, vc);
+    }
+    int c0 = d.p_child0[c], n = d.p_nchild[c];
+    for (int i = 0; i < n; i++)
+      if (!d.p_healthy[c0 + i]) allocateBadCell(c0 + i);
+  }
+  // hived_algorithm.go:1487-1500
+  HIVED_DEV_NOINLINE void releaseBadCell(int c) {
+    bf_append(d.p_chain[c], d.p_level[c], c);
+    int vc = d.p_vcell[c];
+    if (vc >= 0) unbindPair(c, vc);
+    int c0 = d.p_child0[c], n = d.p_nchild[c];
+    for (int i = 0; i < n; i++)
+      if (!d.p_healthy[c0 + i]) releaseBadCell(c0 + i);
+  }
+  // hived_algorithm.go:1354-1427
+  HIVED_DEV_NOINLINE bool allocatePreassignedCell(int c, int vc, bool doomedBad) {
+    bool safetyOk = true;
+    int chain = d.p_chain[c], level = d.p_level[c];
+    int kv = vcl(vc, chain, level), k = cl(chain, level);
+    HV_ST(&d.vcFree[kv], d.vcFree[kv] - 1);
+    HV_ST(&d.allVCFree[k], d.allVCFree[k] - 1);
+    HV_ST(&d.totalLeft[k], d.totalLeft[k] - 1);
+    int splitLevelUpTo = removeCellFromFreeList(c);
+    int parent = d.p_parent[c];
+    for (int l = level + 1; l <= splitLevelUpTo; l++) {
+      int kl = cl(chain, l);
+      HV_ST(&d.totalLeft[kl], d.totalLeft[kl] - 1);
+      if (d.totalLeft[kl] < d.allVCFree[kl]) safetyOk = false;
+      if (!d.p_healthy[parent]) {
+        bf_remove(chain, l, parent);
+      } else {
+        tryBindDoomedBadCell(chain, l);
+      }
+      parent = d.p_parent[parent];
+    }
+    if (!d.p_healthy[c]) {
+      allocateBadCell(c);
+      if (!doomedBad) tryUnbindDoomedBadCell(chain, level);
+    } else {
+      tryBindDoomedBadCell(chain, level);
+    }
+    int numToReduce = d.p_nchild[c];
+    for (int l = level - 1; l >= 1; l--) {
+      int kl = cl(chain, l);
+      HV_ST(&d.totalLeft[kl], d.totalLeft[kl] - numToReduce);
+      if (d.totalLeft[kl] < d.allVCFree[kl]) safetyOk = false;
+      if (!doomedBad) tryBindDoomedBadCell(chain, l);
+      numToReduce *= d.chain_lvl_nchild[kl];
+    }
+    return safetyOk;
+  }
+  // hived_algorithm.go:1449-1485
+  HIVED_DEV_NOINLINE void releasePreassignedCell(int c, int vc, bool doomedBad) {
+    int chain = d.p_chain[c], level = d.p_level[c];
+    int kv = vcl(vc, chain, level), k = cl(chain, level);
+    HV_ST(&d.vcFree[kv], d.vcFree[kv] + 1);
+    HV_ST(&d.allVCFree[k], d.allVCFree[k] + 1);
+    HV_ST(&d.totalLeft[k], d.totalLeft[k] + 1);
+    int mergeLevelUpTo = addCellToFreeList(c);
+    int parent = d.p_parent[c];
+    for (int l = level + 1; l <= mergeLevelUpTo; l++) {
+      int kl = cl(chain, l);
+      HV_ST(&d.totalLeft[kl], d.totalLeft[kl] + 1);
+      if (!d.p_healthy[parent]) {
+        bf_append(chain, l, parent);
+      } else {
+        tryUnbindDoomedBadCell(chain, l);
+      }
+      parent = d.p_parent[parent];
+    }
+    if (!d.p_healthy[c]) {
+      releaseBadCell(c);
+      if (!doomedBad) tryBindDoomedBadCell(chain, level);
+    } else {
+      tryUnbindDoomedBadCell(chain, level);
+    }
+    int numToAdd = d.p_nchild[c];
+    for (int l = level - 1; l >= 1; l--) {
+      int kl = cl(chain, l);
+      HV_ST(&d.totalLeft[kl], d.totalLeft[kl] + numToAdd);
+      if (!doomedBad) tryUnbindDoomedBadCell(chain, l);
+      numToAdd *= d.chain_lvl_nchild[kl];
+    }
+  }
+  // cell.go:302-312
+  HIVED_DEV void setHealthiness(int c, int healthy) {
+    HV_ST(&d.p_healthy[c], healthy);
+    int vc = d.p_vcell[c];
+    if (vc >= 0) HV_ST(&d.v_healthy[vc], healthy);
+  }
+  // hived_algorithm.go:562-581
+  HIVED_DEV void addBadFreeCell(int c) {
+    int chain = d.p_chain[c], level = d.p_level[c];
+    if (!d.chain_in_vc[chain]) { panic(HIVED_ERR_PLATFORM); return; }  // nil-map write in the reference
+    bf_append(chain, level, c);
+    int k = cl(chain, level);
+    if (d.allVCFree[k] > d.totalLeft[k] - d.bf_len[k]) tryBindDoomedBadCell(chain, level);
+  }
+  // hived_algorithm.go:500-522
+  HIVED_DEV_NOINLINE void setBadCell(int c) {
+    if (!d.p_healthy[c]) return;
+    setHealthiness(c, 0);
+    int par = d.p_parent[c];
+    if (par >= 0) setBadCell(par);
+    if (inFreeCellList(c)) {
+      addBadFreeCell(c);
+    } else if (d.p_vcell[c] < 0 && !d.p_split[c]) {
+      int pv = par >= 0 ? d.p_vcell[par] : -1;
+      int vc = pv >= 0 ? unboundChild(pv) : -1;
+      if (vc < 0) { panic(HIVED_ERR_PLATFORM); return; }
+      bindPair(c, vc);
+    }
+  }
+  // hived_algorithm.go:524-560
+  HIVED_DEV_NOINLINE void setHealthyCell(int c) {
+    while (true) {
+      if (d.p_healthy[c]) return;
+      setHealthiness(c, 1);
+      if (inFreeCellList(c)) {
+        // removeBadFreeCell :583-600
+        bf_remove(d.p_chain[c], d.p_level[c], c);
+        tryUnbindDoomedBadCell(d.p_chain[c], d.p_level[c]);
+      } else {
+        int vc = d.p_vcell[c];
+        if (vc >= 0 && !(d.p_flags[c] & PF_PINNED_BIT) && d.p_prio[c] < 0) {
+          int vcid = d.v_vc[vc];
+          bool preassigned = d.v_parent[vc] < 0;
+          unbindPair(c, vc);
+          if (preassigned) {
+            dm_remove(vcid, d.p_chain[c], d.p_level[c], c);
+            int k = cl(d.p_chain[c], d.p_level[c]);
+            HV_ST(&d.allVCDoomed[k], d.allVCDoomed[k] - 1);
+            releasePreassignedCell(c, vcid, true);
+          }
+        }
+      }
+      int par = d.p_parent[c];
+      if (par < 0) return;
+      int c0 = d.p_child0[par], n = d.p_nchild[par];
+      for (int i = 0; i < n; i++)
+        if (!d.p_healthy[c0 + i]) return;
+      c = par;
+    }
+  }
+  // hived_algorithm.go:466-498: the leaves of a node, chain by chain, in level-1 list order
+  HIVED_DEV void setNodeHealth(int node, bool healthy) {
+    if (node < 0 || node >= d.S.nNodes) return;
+    if (healthy) {
+      if (!d.node_bad[node]) return;
+      HV_ST(&d.node_bad[node], 0);
+    } else {
+      if (d.node_bad[node]) return;
+      HV_ST(&d.node_bad[node], 1);
+    }
+    for (int chain = 0; chain < d.S.nChains; chain++) {
+      int k = node * d.S.nChains + chain;
+      for (int i = 0; i < d.ncl_cnt[k]; i++) {
+        int leaf = d.ncl_list[d.ncl_off[k] + i];
+        if (healthy) setHealthyCell(leaf); else setBadCell(leaf);
+        if (sm->panic) return;
+      }
+    }
+  }
+
+  // ======================================================================================
+  // leaf cell allocation / release (hived_algorithm.go:1292-1352)
+  // ======================================================================================
+  HIVED_DEV bool allocateLeafCell(int pLeaf, int vLeaf, int p, int vc) {
+    bool safetyOk = true;
+    stat_add(ST_LEAVES, 1);
+    if (vLeaf >= 0) {
+      setPriorityV(vLeaf, p);
+      setPriorityP(pLeaf, p);
+      if (p == OPP_PRIO) updateUsedOpp(pLeaf, 1);
+      int pac = d.v_pre[vLeaf];
+      bool newlyBound = d.v_pcell[pac] < 0;
+      if (d.p_vcell[pLeaf] < 0) bindCell(pLeaf, vLeaf);
+      if (newlyBound) safetyOk = allocatePreassignedCell(d.v_pcell[pac], vc, false);
+    } else {
+      setPriorityP(pLeaf, OPP_PRIO);
+      updateUsedOpp(pLeaf, 1);
+    }
+    return safetyOk;
+  }
+  HIVED_DEV void releaseLeafCell(int pLeaf, int vc) {
+    stat_add(ST_LEAVES, 1);
+    int vLeaf = d.p_vcell[pLeaf];
+    if (vLeaf >= 0) {
+      setPriorityV(vLeaf, FREE_PRIO);
+      int pre = d.v_pre[vLeaf];
+      int preassignedPhysical = d.v_pcell[pre];
+      if (d.p_healthy[pLeaf]) unbindCell(pLeaf);
+      if (!(d.p_flags[preassignedPhysical] & PF_PINNED_BIT) && d.v_prio[pre] < 0 && !dm_contains(vc, preassignedPhysical))
+        releasePreassignedCell(preassignedPhysical, vc, false);
+    }
+    if (d.p_prio[pLeaf] == OPP_PRIO) updateUsedOpp(pLeaf, -1);
+    setPriorityP(pLeaf, FREE_PRIO);
+  }
+
+  // ======================================================================================
+  // cluster-view pass: data-parallel over the CTA
+  //   updateClusterView + sort.Stable + findNodesForPods (topology_aware_scheduler.go:231-306)
+  // ======================================================================================
+  // info word of a view node: free(8b) | usedSame(8b)<<8 | usedHigher(8b)<<16 | healthy<<24 | suggested<<25
+  HIVED_DEV int viewNodeInfo(int cell, bool isVirtual, bool cross, int p, bool ignoreSuggested) const {
+    int leaf0, nleaf, healthy = 1, suggested = 1;
+    const int32_t* prio;
+    if (isVirtual) {
+      leaf0 = d.v_leaf0[cell]; nleaf = d.v_nleaf[cell]; prio = d.v_prio;
+      int pc = d.v_pcell[cell];
+      if (pc >= 0) { healthy = d.p_healthy[pc]; suggested = ignoreSuggested || node_suggested(d.p_node[pc]); }
+    } else {
+      leaf0 = d.p_leaf0[cell]; nleaf = d.p_nleaf[cell]; prio = d.p_prio;
+      healthy = d.p_healthy[cell]; suggested = ignoreSuggested || node_suggested(d.p_node[cell]);
+    }
+    int same = 0, higher = 0, ge = 0;
+    for (int i = 0; i < nleaf; i++) {
+      int q = prio[leaf0 + i];
+      if (q < OPP_PRIO) continue;  // free leaf
+      if (q == p) same++;
+      else if (cross) same++;
+      else if (q > p) higher++;
+      if (q >= p) ge++;
+    }
+    int free = nleaf - ge;
+    return (free & 255) | (same << 8) | (higher << 16) | (healthy << 24) | (suggested << 25);
+  }
+  HIVED_DEV static int infoFree(int w) { return w & 255; }
+  HIVED_DEV static int infoSame(int w) { return (w >> 8) & 255; }
+  HIVED_DEV static int infoHigher(int w) { return (w >> 16) & 255; }
+  HIVED_DEV static int infoHealthy(int w) { return (w >> 24) & 1; }
+  HIVED_DEV static int infoSuggested(int w) { return (w >> 25) & 1; }
+
+  // CTA-wide exclusive prefix sum of sm->cnt[0..n) (row-major: bin-major, warp-minor)
+  HIVED_DEV void ctaExclusiveScan(int n) {
+    int nth = hv_nth(), tid = hv_tid(), lane = hv_lane(), w = hv_warp(), W = hv_nwarps();
+    int per = (n + nth - 1) / nth;
+    int lo = tid * per, hi = lo + per < n ? lo + per : n;
+    int s = 0;
+    for (int i = lo; i < hi; i++) s += sm->cnt[i];
+    int incl = s;
+    for (int o = 1; o < HIVED_WARPSZ; o <<= 1) { int t = hv_shfl_up(incl, o); if (lane >= o) incl += t; }
+    if (lane == HIVED_WARPSZ - 1) sm->part[w] = incl;
+    hv_cta_sync();
+    if (w == 0) {
+      int v = lane < W ? sm->part[lane] : 0;
+      int inc = v;
+      for (int o = 1; o < HIVED_WARPSZ; o <<= 1) { int t = hv_shfl_up(inc, o); if (lane >= o) inc += t; }
+      if (lane < W) sm->part[lane] = inc - v;
+    }
+    hv_cta_sync();
+    int run = sm->part[w] + incl - s;
+    for (int i = lo; i < hi; i++) { int v = sm->cnt[i]; sm->cnt[i] = run; run += v; }
+    hv_cta_sync();
+  }
+
+  // one stable counting pass: out[rank] = in[i] ordered by bin(info[in[i]]), ties by position
+  template <typename BinFn>
+  HIVED_DEV void stablePass(const int32_t* in, int32_t* out, int n, int nbins, BinFn binOf) {
+    int W = hv_nwarps(), w = hv_warp(), lane = hv_lane();
+    for (int i = hv_tid(); i < nbins * W; i += hv_nth()) sm->cnt[i] = 0;
+    hv_cta_sync();
+    int chunk = (n + W - 1) / W;
+    chunk = (chunk + HIVED_WARPSZ - 1) / HIVED_WARPSZ * HIVED_WARPSZ;
+    int lo = w * chunk, hi = lo + chunk < n ? lo + chunk : n;
+    for (int base = lo; base < hi; base += HIVED_WARPSZ) {
+      int i = base + lane;
+      int b = i < hi ? binOf(d.vw_info[in[i]]) : -1 - lane;  // inactive lanes get unique dummies
+      unsigned peers = hv_match(b);
+      if (i < hi && (peers & hv_lanemask_lt()) == 0) sm->cnt[b * W + w] += hv_popc(peers);
+      hv_warp_sync();
+    }
+    hv_cta_sync();
+    ctaExclusiveScan(nbins * W);
+    for (int base = lo; base < hi; base += HIVED_WARPSZ) {
+      int i = base + lane;
+      int b = i < hi ? binOf(d.vw_info[in[i]]) : -1 - lane;
+      unsigned peers = hv_match(b);
+      if (i < hi) {
+        int rank = sm->cnt[b * W + w] + hv_popc(peers & hv_lanemask_lt());
+        out[rank] = in[i];
+      }
+      hv_warp_sync();
+      if (i < hi && (peers & hv_lanemask_lt()) == 0) sm->cnt[b * W + w] += hv_popc(peers);
+      hv_warp_sync();
+    }
+    hv_cta_sync();
+  }
+
+  // all threads of the CTA
+  HIVED_DEV void viewOp() {
+    const int sched = sm->a_sched, p = sm->a_prio, npods = sm->a_npods;
+    const bool ignoreSuggested = sm->a_ignore != 0;
+    const int off = d.s_off[sched], n = d.s_n[sched];
+    const bool cross = d.s_cross[sched] != 0, isVirtual = d.s_virtual[sched] != 0;
+    const int L = d.s_maxleaf[sched];
+    const int tid = hv_tid(), nth = hv_nth();
+    // 1. per-node keys from leaf priorities (coalesced int32 loads of contiguous leaf ranges)
+    for (int i = tid; i < n; i += nth) {
+      int cell = d.cv[off + i];
+      d.vw_cell[i] = cell;
+      d.vw_info[i] = viewNodeInfo(cell, isVirtual, cross, p, ignoreSuggested);
+      d.vw_ordA[i] = i;
+    }
+    hv_cta_sync();
+    // 2. stable sort by (healthy desc, suggested desc, usedSame desc, usedHigher asc): LSD passes
+    int32_t* cur = d.vw_ordA;
+    int32_t* nxt = d.vw_ordB;
+    if (!cross) {
+      stablePass(cur, nxt, n, L + 1, [](int w) { return infoHigher(w); });
+      int32_t* t = cur; cur = nxt; nxt = t;
+    }
+    stablePass(cur, nxt, n, 4 * (L + 1), [L](int w) {
+      return ((1 - infoHealthy(w)) * 2 + (1 - infoSuggested(w))) * (L + 1) + (L - infoSame(w));
+    });
+    { int32_t* t = cur; cur = nxt; nxt = t; }
+    // 3. persist the new order (the reference sorts its slice in place) and lay the infos out in order
+    for (int i = tid; i < n; i += nth) {
+      int src = cur[i];
+      d.cv[off + i] = d.vw_cell[src];
+      nxt[i] = d.vw_info[src];
+    }
+    hv_cta_sync();
+    const int32_t* sinfo = nxt;
+    // 4. greedy first-fit (findNodesForPods :278-305); every thread tracks the same scalar state
+    int nodeIndex = 0, picked = 0, ok = 1, reason = 0, rcell = -1;
+    for (int k = 0; k < npods && ok; k++) {
+      int need = d.pod_need[k];
+      int found = -1;
+      if (nodeIndex < n && infoFree(sinfo[nodeIndex]) - picked >= need) {
+        found = nodeIndex;
+      } else {
+        if (tid == 0) sm->best = n;
+        hv_cta_sync();
+        int mine = n;
+        for (int j = nodeIndex + 1 + tid; j < n; j += nth)
+          if (infoFree(sinfo[j]) >= need) { mine = j; break; }
+        // warp-level min, then one shared atomic per warp
+        for (int o = HIVED_WARPSZ / 2; o > 0; o >>= 1) { int other = hv_shfl_xor(mine, o); if (other < mine) mine = other; }
+        if (hv_lane() == 0 && mine < n) hv_atomic_min(&sm->best, mine);
+        hv_cta_sync();
+        int b = sm->best;
+        hv_cta_sync();
+        if (b < n) { found = b; picked = 0; }
+      }
+      if (found < 0) { ok = 0; reason = HIVED_WAIT_INSUFFICIENT; rcell = -1; break; }
+      int w = sinfo[found];
+      if (!infoHealthy(w) || !infoSuggested(w)) {
+        ok = 0;
+        reason = !infoHealthy(w) ? HIVED_WAIT_BAD_NODE : HIVED_WAIT_NON_SUGGESTED_NODE;
+        int cell = d.cv[off + found];
+        rcell = isVirtual ? d.v_pcell[cell] : cell;
+        break;
+      }
+      nodeIndex = found;
+      picked += need;
+      if (tid == 0) { d.pod_pos[k] = found; d.pod_cell[k] = d.cv[off + found]; }
+    }
+    if (tid == 0) { sm->r_ok = ok; sm->r_reason = reason; sm->r_cell = rcell; }
+    hv_cta_sync();
+  }
+
+  // leader: post the view pass to the CTA and take part in it
+  HIVED_DEV bool runViewPass(int sched, int p, bool ignoreSuggested, int npods, int& reason, int& rcell) {
+    HV_ST(&sm->a_sched, sched);
+    HV_ST(&sm->a_prio, p);
+    HV_ST(&sm->a_ignore, ignoreSuggested ? 1 : 0);
+    HV_ST(&sm->a_npods, npods);
+    HV_ST(&sm->a_sugg, sugg);
+    HV_ST(&sm->cmd, CMD_VIEW);
+    hv_cta_sync();
+    viewOp();
+    HV_ST(&sm->cmd, CMD_IDLE);
+    stat_add(ST_VIEW_NODES, d.s_n[sched]);
+    reason = sm->r_reason;
+    rcell = sm->r_cell;
+    return sm->r_ok != 0;
+  }
+
+  // ======================================================================================
+  // intra-node leaf search (topology_aware_scheduler.go:308-476)
+  // ======================================================================================
+  template <bool V>
+  HIVED_DEV int tparent(int c) const { return V ? d.v_parent[c] : d.p_parent[c]; }
+  template <bool V>
+  HIVED_DEV int tlevel(int c) const { return V ? d.v_level[c] : d.p_level[c]; }
+  // :443-462
+  template <bool V>
+  HIVED_DEV int findLCA(int lower, int higher) const {
+    while (tlevel<V>(lower) < tlevel<V>(higher)) {
+      if (tparent<V>(lower) < 0) return -1;
+      lower = tparent<V>(lower);
+    }
+    if (lower == higher) return lower;
+    while (tparent<V>(lower) != tparent<V>(higher)) {
+      if (tparent<V>(lower) < 0 || tparent<V>(higher) < 0) return -1;
+      lower = tparent<V>(lower);
+      higher = tparent<V>(higher);
+    }
+    return tparent<V>(lower);
+  }
+  // :389-399
+  HIVED_DEV int optimalAffinity(int chain, int leafNum) const {
+    for (int l = 1; l <= d.chain_top[chain]; l++)
+      if (d.chain_lvl_leafnum[cl(chain, l)] >= leafNum) return l;
+    return -1;
+  }
+  // :308-387.  slot = index of this node's candidate list (nodeAvailableLeafCells); out = leaf ids
+  template <bool V>
+  HIVED_DEV_NOINLINE void findLeafCellsInNode(int node, int k, int p, int slot, bool fresh, int chain, int32_t* out) {
+    int32_t* avail = d.cand + slot * MAX_NODE_LEAVES;
+    int navail;
+    if (fresh) {
+      // getLeafCellsFromNode :464-476: free leaves in DFS order, then preemptible ones
+      int leaf0 = V ? d.v_leaf0[node] : d.p_leaf0[node];
+      int nleaf = V ? d.v_nleaf[node] : d.p_nleaf[node];
+      const int32_t* prio = V ? d.v_prio : d.p_prio;
+      int n = 0;
+      for (int i = 0; i < nleaf; i++)
+        if (prio[leaf0 + i] == FREE_PRIO) { HV_ST(&avail[n], leaf0 + i); n++; }
+      for (int i = 0; i < nleaf; i++) {
+        int q = prio[leaf0 + i];
+        if (q != FREE_PRIO && q < p) { HV_ST(&avail[n], leaf0 + i); n++; }
+      }
+      navail = n;
+    } else {
+      navail = d.cand_len[slot];
+    }
+    int curIdx[MAX_NODE_LEAVES], curAff[MAX_NODE_LEAVES], bestIdx[MAX_NODE_LEAVES];
+    const int HIGHEST = 0x7fffffff;
+    int bestAffinity = HIGHEST;
+    int optimal = optimalAffinity(chain, k);
+    if (optimal < 0 || k > MAX_NODE_LEAVES) { panic(HIVED_ERR_PLATFORM); return; }
+    int ai = 0, si = 0;
+    bool done = false;
+    while (!done) {
+      while (ai < navail) {
+        int leaf = avail[ai];
+        curIdx[si] = ai;
+        if (si == 0) {
+          curAff[si] = leaf;
+        } else {
+          curAff[si] = findLCA<V>(leaf, curAff[si - 1]);
+          if ((curAff[si] < 0 && bestAffinity < HIGHEST) || (curAff[si] >= 0 && tlevel<V>(curAff[si]) > bestAffinity)) {
+            ai++;
+            continue;
+          }
+        }
+        if (si == k - 1) {
+          if (curAff[k - 1] < 0) { panic(HIVED_ERR_PLATFORM); return; }
+          int affinity = tlevel<V>(curAff[k - 1]);
+          bool foundOptimal = false;
+          if (affinity < bestAffinity) {
+            for (int i = 0; i < k; i++) bestIdx[i] = curIdx[i];
+            bestAffinity = affinity;
+            foundOptimal = affinity == optimal;
+          }
+          if (foundOptimal) { done = true; break; }
+        } else {
+          si++;
+        }
+        ai++;
+      }
+      if (done) break;
+      si--;
+      if (si < 0) {
+        if (bestAffinity == HIGHEST) { panic(HIVED_ERR_PLATFORM); return; }  // "Assert Failure"
+        break;
+      }
+      ai = curIdx[si] + 1;
+    }
+    for (int i = 0; i < k; i++) HV_ST(&out[i], avail[bestIdx[i]]);
+    // removePickedLeafCells :425-441 (order preserving)
+    int w = 0, b = 0;
+    for (int i = 0; i < navail; i++) {
+      if (b < k && bestIdx[b] == i) { b++; continue; }
+      int v = avail[i];
+      HV_ST(&avail[w], v);
+      w++;
+    }
+    HV_ST(&d.cand_len[slot], w);
+  }
+
+  // ======================================================================================
+  // topologyAwareScheduler.Schedule (topology_aware_scheduler.go:65-116)
+  //   members: ascending leaf numbers (merged); placement written to `outLeaves` in
+  //   (member, pod, leaf) order.  Returns false + reason on failure.
+  // ======================================================================================
+  HIVED_DEV_NOINLINE bool tasSchedule(int sched, int nmem, const int* memLeaf, const int* memPods, int p,
+                                      bool ignoreSuggested, int32_t* outLeaves, int& reason, int& rcell) {
+    int npods = 0;
+    for (int m = 0; m < nmem; m++)
+      for (int i = 0; i < memPods[m]; i++) { HV_ST(&d.pod_need[npods], memLeaf[m]); npods++; }
+    int priority = OPP_PRIO;
+    bool ok = runViewPass(sched, priority, ignoreSuggested, npods, reason, rcell);
+    if (!ok && p > OPP_PRIO) {
+      priority = p;
+      ok = runViewPass(sched, priority, ignoreSuggested, npods, reason, rcell);
+    }
+    if (!ok) return false;
+    stat_add(ST_PODS, npods);
+    const bool isVirtual = d.s_virtual[sched] != 0;
+    const int chain = d.s_chain[sched];
+    int nslots = 0, outOff = 0;
+    for (int k = 0; k < npods; k++) {
+      int node = d.pod_cell[k];
+      int slot = -1;
+      for (int j = 0; j < nslots; j++)
+        if (d.cand_node[j] == node) { slot = j; break; }
+      bool fresh = slot < 0;
+      if (fresh) { slot = nslots++; HV_ST(&d.cand_node[slot], node); }
+      int need = d.pod_need[k];
+      if (isVirtual) findLeafCellsInNode<true>(node, need, priority, slot, fresh, chain, outLeaves + outOff);
+      else findLeafCellsInNode<false>(node, need, priority, slot, fresh, chain, outLeaves + outOff);
+      if (sm->panic) return false;
+      outOff += need;
+    }
+    reason = 0;
+    rcell = -1;
+    return true;
+  }
+
+  // ======================================================================================
+  // virtual -> physical mapping (types.go:282-340, cell_allocation.go:34-315)
+  // ======================================================================================
+  int vxCount;   // vertices in use
+  int paCount;   // preassigned roots
+  int npCount;   // non-preassigned buddy groups
+  HIVED_DEV int newVertex(int vcell) {
+    int v = vxCount++;
+    if (v >= d.S.VX) { panic(HIVED_ERR_CAPACITY); return 0; }
+    HV_ST(&d.vx_cell[v], vcell);
+    HV_ST(&d.vx_child[v], -1);
+    HV_ST(&d.vx_last[v], -1);
+    HV_ST(&d.vx_next[v], -1);
+    HV_ST(&d.vx_nch[v], 0);
+    HV_ST(&d.vx_of[vcell], v);
+    HV_ST(&d.vx_stamp[vcell], *d.epoch);
+    return v;
+  }
+  HIVED_DEV int vertexOf(int vcell) const { return d.vx_stamp[vcell] == *d.epoch ? d.vx_of[vcell] : -1; }
+  HIVED_DEV void addChildVertex(int parentV, int childV) {
+    int last = d.vx_last[parentV];
+    if (last < 0) HV_ST(&d.vx_child[parentV], childV); else HV_ST(&d.vx_next[last], childV);
+    HV_ST(&d.vx_last[parentV], childV);
+    HV_ST(&d.vx_nch[parentV], d.vx_nch[parentV] + 1);
+  }
+  // types.go:282-340
+  HIVED_DEV_NOINLINE void toBindingPaths(const int32_t* vleaves, int nleaves) {
+    HV_ST(d.epoch, *d.epoch + 1);
+    vxCount = 0; paCount = 0; npCount = 0;
+    int path[MAXL];
+    for (int i = 0; i < nleaves; i++) {
+      int leaf = vleaves[i];
+      int pl = d.v_pcell[leaf];
+      if (pl >= 0) { HV_ST(&d.binding[leaf], pl); continue; }
+      int np = 0;
+      for (int c = leaf; c >= 0; c = d.v_parent[c]) {
+        if (d.v_pcell[c] >= 0 || vertexOf(c) >= 0) break;
+        path[np++] = c;
+      }
+      int root = path[np - 1];
+      int n = newVertex(root);
+      int par = d.v_parent[root];
+      if (par < 0) {
+        HV_ST(&d.pa_list[paCount], n); paCount++;
+      } else if (d.v_pcell[par] >= 0) {
+        bool buddy = false;
+        for (int g = 0; g < npCount; g++) {
+          if (d.v_parent[d.vx_cell[d.np_head[g]]] == par) {
+            // append to the group's chain (roots are linked through vx_next)
+            int t = d.np_head[g];
+            while (d.vx_next[t] >= 0) t = d.vx_next[t];
+            HV_ST(&d.vx_next[t], n);
+            HV_ST(&d.np_cnt[g], d.np_cnt[g] + 1);
+            buddy = true;
+            break;
+          }
+        }
+        if (!buddy) { HV_ST(&d.np_head[npCount], n); HV_ST(&d.np_cnt[npCount], 1); npCount++; }
+      } else {
+        addChildVertex(vertexOf(par), n);
+      }
+      for (int j = np - 2; j >= 0; j--) {
+        int c = path[j];
+        int nn = newVertex(c);
+        addChildVertex(vertexOf(d.v_parent[c]), nn);
+      }
+      if (sm->panic) return;
+    }
+  }
+
+  // cell_allocation.go:199-243.  candidates: in[i] or (in == nullptr) the id range base+i.
+  // out: usable ones, stably sorted ascending by used[opportunistic].  returns -1 for nil.
+  HIVED_DEV bool cellUsable(int c, bool ignoreSuggested) const {
+    if (d.p_vcell[c] >= 0) return false;
+    int nn = d.p_nodes_cnt[c];
+    if (nn == 1 && !d.p_healthy[c]) return false;
+    if (!ignoreSuggested) {
+      int o = d.p_nodes_off[c];
+      for (int j = 0; j < nn; j++)
+        if (node_suggested(d.nodes_flat[o + j])) return true;
+      return false;
+    }
+    return true;
+  }
+  HIVED_DEV int getUsablePhysicalCells(const int32_t* in, int base, int nin, int numNeeded, bool ignoreSuggested, int32_t* out) {
+    stat_add(ST_FREE_CELLS, nin);
+    // order-preserving filter, one warp-wide ballot per 32 candidates
+    int n = 0;
+    const int lane = hv_lane();
+    for (int b0 = 0; b0 < nin; b0 += HIVED_WARPSZ) {
+      int i = b0 + lane;
+      int c = i < nin ? (in ? in[i] : base + i) : -1;
+      bool ok = c >= 0 && cellUsable(c, ignoreSuggested);
+      unsigned m = hv_ballot(ok);
+      if (ok) out[n + hv_popc(m & hv_lanemask_lt())] = c;
+      n += hv_popc(m);
+    }
+    hv_warp_sync();
+    if (n < numNeeded) return -1;
+    // sort.SliceStable by used[opportunistic]: only when some neighbour pair is out of order
+    bool unsorted = false;
+    for (int b0 = 1; b0 < n; b0 += HIVED_WARPSZ) {
+      int i = b0 + lane;
+      bool bad = i < n && d.p_usedopp[out[i - 1]] > d.p_usedopp[out[i]];
+      if (hv_ballot(bad)) { unsorted = true; break; }
+    }
+    if (unsorted) {
+      for (int i = 1; i < n; i++) {
+        int c = out[i], key = d.p_usedopp[c];
+        int j = i - 1;
+        if (d.p_usedopp[out[j]] <= key) continue;
+        while (j >= 0 && d.p_usedopp[out[j]] > key) { HV_ST(&out[j + 1], out[j]); j--; }
+        HV_ST(&out[j + 1], c);
+      }
+    }
+    return n;
+  }
+
+  // cell_allocation.go:245-315.  cells: ncells vertices linked through vx_next from firstV.
+  HIVED_DEV_NOINLINE bool mapVirtualCellsToPhysical(int firstV, int ncells, const int32_t* candIn, int candBase, int ncand,
+                                                    bool ignoreSuggested, int depth, int32_t* pickedOut) {
+    if (depth >= MAXL || ncells > MAX_FANOUT || (depth > 0 && ncand > MAX_FANOUT)) { panic(HIVED_ERR_CAPACITY); return false; }
+    int32_t* cands = depth == 0 ? d.mc0 : d.mcbuf + depth * MAX_FANOUT;
+    int n = getUsablePhysicalCells(candIn, candBase, ncand, ncells, ignoreSuggested, cands);
+    if (n < 0) return false;
+    int32_t* pickedIdx = d.mcpick + depth * MAX_FANOUT;
+    int32_t* cellV = d.mccells + depth * MAX_FANOUT;
+    {
+      int v = firstV;
+      for (int i = 0; i < ncells; i++) { HV_ST(&cellV[i], v); HV_ST(&pickedIdx[i], 0); v = d.vx_next[v]; }
+    }
+    int cellIndex = 0;
+    while (cellIndex >= 0) {
+      int candidateIndex;
+      for (candidateIndex = pickedIdx[cellIndex]; candidateIndex < n; candidateIndex++) {
+        bool used = false;  // pickedIndexSet == picks of the cells before cellIndex
+        for (int j = 0; j < cellIndex; j++)
+          if (pickedIdx[j] == candidateIndex) { used = true; break; }
+        if (used) continue;
+        int candidate = cands[candidateIndex];
+        int vtx = cellV[cellIndex];
+        bool picked;
+        if (d.p_level[candidate] == 1) {
+          picked = true;
+          HV_ST(&d.binding[d.vx_cell[vtx]], candidate);
+        } else {
+          picked = mapVirtualCellsToPhysical(d.vx_child[vtx], d.vx_nch[vtx], nullptr, d.p_child0[candidate], d.p_nchild[candidate],
+                                             ignoreSuggested, depth + 1, nullptr);
+          if (sm->panic) return false;
+        }
+        if (picked) {
+          HV_ST(&pickedIdx[cellIndex], candidateIndex);
+          if (cellIndex == ncells - 1) {
+            if (pickedOut)
+              for (int i = 0; i < ncells; i++) HV_ST(&pickedOut[i], cands[pickedIdx[i]]);
+            return true;
+          }
+          break;
+        }
+      }
+      if (candidateIndex == n) {
+        cellIndex--;
+        if (cellIndex >= 0) HV_ST(&pickedIdx[cellIndex], pickedIdx[cellIndex] + 1);
+      } else {
+        cellIndex++;
+      }
+    }
+    return false;
+  }
+
+  // ---- the Schedule-time copy of the chain's free list (types.go:123-130, hived_algorithm.go:917-929)
+  int sflChain;
+  HIVED_DEV int32_t* sfl(int level) const { return d.sfl_data + d.fl_base[cl(sflChain, level)]; }
+  HIVED_DEV void sflCopy(int chain) {
+    sflChain = chain;
+    const int lane = hv_lane();
+    for (int l = 1; l < MAXL; l++) {
+      int k = cl(chain, l);
+      int n = l <= d.chain_top[chain] ? d.fl_len[k] : 0;
+      HV_ST(&d.sfl_len[l], n);
+      for (int i = lane; i < n; i += HIVED_WARPSZ) d.sfl_data[d.fl_base[k] + i] = d.fl_data[d.fl_base[k] + i];
+    }
+    hv_warp_sync();
+  }
+  HIVED_DEV void sflRemove(int level, int cell) {  // types.go:78-95 on the copy
+    int32_t* a = sfl(level);
+    int n = d.sfl_len[level], idx = -1;
+    const int lane = hv_lane();
+    for (int b0 = 0; b0 < n && idx < 0; b0 += HIVED_WARPSZ) {
+      int i = b0 + lane;
+      unsigned m = hv_ballot(i < n && a[i] == cell);
+      if (m) idx = b0 + hv_ffs(m) - 1;
+    }
+    if (idx < 0) { panic(HIVED_ERR_PLATFORM); return; }
+    HV_ST(&a[idx], a[n - 1]);
+    HV_ST(&d.sfl_len[level], n - 1);
+  }
+
+  // cell_allocation.go:34-80
+  HIVED_DEV_NOINLINE bool buddyAlloc(int vtx, int currentLevel, bool ignoreSuggested) {
+    int cellLevel = d.v_level[d.vx_cell[vtx]];
+    if (currentLevel == cellLevel) {
+      int32_t picked[1];
+      HV_ST(&d.vx_next[vtx], -1);
+      bool ok = mapVirtualCellsToPhysical(vtx, 1, sfl(currentLevel), 0, d.sfl_len[currentLevel], ignoreSuggested, 0, d.tmp_list);
+      if (ok) { picked[0] = d.tmp_list[0]; sflRemove(currentLevel, picked[0]); return true; }
+      return false;
+    }
+    int32_t* freeCells = d.ba_buf + (int64_t)currentLevel * d.S.maxLevelCount;
+    int nfree = getUsablePhysicalCells(sfl(currentLevel), 0, d.sfl_len[currentLevel], 1, ignoreSuggested, freeCells);
+    if (nfree < 0) return false;
+    for (int i = 0; i < nfree; i++) {
+      int c = freeCells[i];
+      int32_t* lower = sfl(currentLevel - 1);
+      int nl = d.sfl_len[currentLevel - 1];
+      for (int j = 0; j < d.p_nchild[c]; j++) HV_ST(&lower[nl + j], d.p_child0[c] + j);
+      HV_ST(&d.sfl_len[currentLevel - 1], nl + d.p_nchild[c]);
+      if (buddyAlloc(vtx, currentLevel - 1, ignoreSuggested)) {
+        sflRemove(currentLevel, c);
+        return true;
+      }
+      if (sm->panic) return false;
+      HV_ST(&d.sfl_len[currentLevel - 1], 0);  // = nil
+    }
+    return false;
+  }
+
+  // cell_allocation.go:82-150
+  HIVED_DEV_NOINLINE bool safeRelaxedBuddyAlloc(int vtx, int* freeCellNum, int currentLevel, bool ignoreSuggested) {
+    int top = sflChain >= 0 ? d.chain_top[sflChain] : 0;
+    int splittableNum[MAXL];
+    for (int i = 0; i < MAXL; i++) splittableNum[i] = 0;
+    int splittableCell = -1;
+    for (int i = top; i > currentLevel; i--) {
+      splittableNum[i] = d.sfl_len[i] - freeCellNum[i];
+      if (i < top && splittableCell >= 0) splittableNum[i] += splittableNum[i + 1] * d.p_nchild[splittableCell];
+      if (splittableCell < 0 && d.sfl_len[i] > 0) splittableCell = sfl(i)[0];
+      else if (splittableCell >= 0) splittableCell = d.p_child0[splittableCell];
+      if (splittableNum[i] < 0) { panic(HIVED_ERR_PLATFORM); return false; }  // "VC Safety Broken"
+    }
+    for (int l = currentLevel + 1; l <= top; l++) {
+      int cellNum = d.sfl_len[l];
+      if (cellNum > splittableNum[l]) cellNum = splittableNum[l];
+      if (cellNum > 0) {
+        int32_t* split = d.ba_buf;  // level 0 row is otherwise unused
+        int ns = 0;
+        for (int i = 0; i < cellNum; i++) {
+          int first = sfl(l)[0];
+          HV_ST(&split[ns], first); ns++;
+          sflRemove(l, first);
+        }
+        splittableNum[l] -= cellNum;
+        for (int sl = l; sl > currentLevel; sl--) {
+          // expand every cell of the split list into its children (in place, back to front)
+          int total = 0;
+          for (int i = 0; i < ns; i++) total += d.p_nchild[split[i]];
+          if (total > d.S.maxLevelCount) { panic(HIVED_ERR_CAPACITY); return false; }
+          int w = total;
+          for (int i = ns - 1; i >= 0; i--) {
+            int c = split[i], nc = d.p_nchild[c];
+            for (int j = nc - 1; j >= 0; j--) { w--; HV_ST(&split[w], d.p_child0[c] + j); }
+          }
+          ns = total;
+        }
+        // freeList[currentLevel] = append(splitList, freeList[currentLevel]...)
+        int32_t* cur = sfl(currentLevel);
+        int nc = d.sfl_len[currentLevel];
+        for (int i = nc - 1; i >= 0; i--) HV_ST(&cur[i + ns], cur[i]);
+        for (int i = 0; i < ns; i++) HV_ST(&cur[i], split[i]);
+        HV_ST(&d.sfl_len[currentLevel], nc + ns);
+        HV_ST(&d.vx_next[vtx], -1);
+        bool ok = mapVirtualCellsToPhysical(vtx, 1, cur, 0, nc + ns, ignoreSuggested, 0, d.tmp_list);
+        if (ok) { sflRemove(currentLevel, d.tmp_list[0]); return true; }
+        if (sm->panic) return false;
+      }
+    }
+    return false;
+  }
+
+  // cell_allocation.go:152-197
+  HIVED_DEV_NOINLINE bool mapVirtualPlacementToPhysical(int chain, bool ignoreSuggested) {
+    int freeCellNum[MAXL];
+    for (int l = 0; l < MAXL; l++) freeCellNum[l] = (chain >= 0 && d.chain_in_vc[chain]) ? d.allVCFree[cl(chain, l)] : 0;
+    if (paCount > 0) {
+      if (chain < 0) { panic(HIVED_ERR_PLATFORM); return false; }  // nil free list: "VC Safety Broken"
+      sflCopy(chain);
+    } else {
+      sflChain = chain;
+    }
+    for (int i = 0; i < paCount; i++) {
+      int vtx = d.pa_list[i];
+      int level = d.v_level[d.vx_cell[vtx]];
+      int l = level, top = d.chain_top[chain];
+      for (; l <= top; l++)
+        if (d.sfl_len[l] != 0) break;
+      if (l > top) { panic(HIVED_ERR_PLATFORM); return false; }  // getLowestFreeCellLevel: "VC Safety Broken"
+      if (!buddyAlloc(vtx, l, ignoreSuggested)) {
+        if (sm->panic) return false;
+        if (!safeRelaxedBuddyAlloc(vtx, freeCellNum, level, ignoreSuggested)) return false;
+      } else {
+        freeCellNum[level]--;
+      }
+    }
+    for (int g = 0; g < npCount; g++) {
+      int head = d.np_head[g];
+      int parentPhysical = d.v_pcell[d.v_parent[d.vx_cell[head]]];
+      bool ok = mapVirtualCellsToPhysical(head, d.np_cnt[g], nullptr, d.p_child0[parentPhysical], d.p_nchild[parentPhysical],
+                                          ignoreSuggested, 0, nullptr);
+      if (!ok) return false;
+    }
+    return true;
+  }
+
+  // ======================================================================================
+  // affinity groups (types.go:133-183; hived_algorithm.go:981-1222)
+  // ======================================================================================
+  HIVED_DEV int32_t* gphys(int g) const { return d.g_phys + (int64_t)g * d.S.LS; }
+  HIVED_DEV int32_t* gvirt(int g) const { return d.g_virt + (int64_t)g * d.S.LS; }
+  HIVED_DEV int32_t* gpods(int g) const { return d.g_pods + (int64_t)g * d.S.PS; }
+  HIVED_DEV int32_t* gpre(int g) const { return d.g_pre + (int64_t)g * d.S.PS; }
+  HIVED_DEV int groupLeaves(int g) const {
+    int n = 0;
+    for (int m = 0; m < d.g_nmem[g]; m++) n += d.g_mem_leaf[g * 8 + m] * d.g_mem_pods[g * 8 + m];
+    return n;
+  }
+  HIVED_DEV int groupPods(int g) const {
+    int n = 0;
+    for (int m = 0; m < d.g_nmem[g]; m++) n += d.g_mem_pods[g * 8 + m];
+    return n;
+  }
+  // merge + sort the spec's members (types.go:157-160, hived_algorithm.go:775-778)
+  HIVED_DEV static int mergeMembers(const hived_pod_spec_t& sp, int* leaf, int* pods) {
+    int n = 0;
+    for (int i = 0; i < sp.n_members; i++) {
+      int ln = sp.member_leaf_num[i], pn = sp.member_pod_num[i];
+      int j = 0;
+      for (; j < n; j++) if (leaf[j] == ln) break;
+      if (j < n) { pods[j] += pn; continue; }
+      j = n++;
+      while (j > 0 && leaf[j - 1] > ln) { leaf[j] = leaf[j - 1]; pods[j] = pods[j - 1]; j--; }
+      leaf[j] = ln; pods[j] = pn;
+    }
+    return n;
+  }
+  // newAlgoAffinityGroup types.go:150-183
+  HIVED_DEV void newGroup(int g, const hived_pod_spec_t& sp, int state) {
+    int leaf[HIVED_MAX_MEMBERS], pods[HIVED_MAX_MEMBERS];
+    int n = mergeMembers(sp, leaf, pods);
+    HV_ST(&d.g_state[g], state);
+    HV_ST(&d.g_vc[g], sp.vc);
+    HV_ST(&d.g_prio[g], sp.priority);
+    HV_ST(&d.g_flags[g], ((sp.flags & HIVED_SPEC_LAZY_PREEMPTION) ? GF_LAZY_ENABLE : 0) | GF_HAS_VIRTUAL);
+    HV_ST(&d.g_nmem[g], n);
+    int nl = 0, np = 0;
+    for (int m = 0; m < n; m++) {
+      HV_ST(&d.g_mem_leaf[g * 8 + m], leaf[m]);
+      HV_ST(&d.g_mem_pods[g * 8 + m], pods[m]);
+      nl += leaf[m] * pods[m]; np += pods[m];
+    }
+    for (int i = 0; i < nl; i++) { HV_ST(&gphys(g)[i], -1); HV_ST(&gvirt(g)[i], -1); }
+    for (int i = 0; i < np; i++) HV_ST(&gpods(g)[i], -1);
+    HV_ST(&d.g_npre[g], 0);
+  }
+  HIVED_DEV void eraseGroup(int g) { HV_ST(&d.g_state[g], HIVED_GROUP_NONE); }
+  // slot offsets of member m: leaves before it / pods before it
+  HIVED_DEV void memberOffsets(int g, int m, int& leafOff, int& podOff) const {
+    leafOff = 0; podOff = 0;
+    for (int i = 0; i < m; i++) { leafOff += d.g_mem_leaf[g * 8 + i] * d.g_mem_pods[g * 8 + i]; podOff += d.g_mem_pods[g * 8 + i]; }
+  }
+  HIVED_DEV int memberOf(int g, int leafNum) const {
+    for (int m = 0; m < d.g_nmem[g]; m++) if (d.g_mem_leaf[g * 8 + m] == leafNum) return m;
+    return -1;
+  }
+
+  // hived_algorithm.go:1165-1191.  save != nullptr receives the original virtual placement.
+  HIVED_DEV_NOINLINE void lazyPreemptAffinityGroup(int g, int32_t* save) {
+    int nl = groupLeaves(g);
+    bool had = (d.g_flags[g] & GF_HAS_VIRTUAL) != 0;
+    if (had) {
+      for (int i = 0; i < nl; i++) {
+        int vLeaf = gvirt(g)[i];
+        if (vLeaf >= 0) {
+          int pLeaf = d.v_pcell[vLeaf];
+          if (pLeaf < 0) { panic(HIVED_ERR_PLATFORM); return; }
+          releaseLeafCell(pLeaf, d.g_vc[g]);
+          allocateLeafCell(pLeaf, -1, OPP_PRIO, d.g_vc[g]);
+        }
+      }
+    }
+    if (save) {
+      HV_ST(&save[0], had ? 1 : 0);  // word 0: non-nil marker
+      for (int i = 0; i < nl; i++) HV_ST(&save[1 + i], had ? gvirt(g)[i] : -1);
+    }
+    HV_ST(&d.g_flags[g], (d.g_flags[g] & ~GF_HAS_VIRTUAL) | GF_LAZY_PREEMPTED);
+  }
+  // hived_algorithm.go:1193-1201
+  HIVED_DEV_NOINLINE void lazyPreemptCell(int vcell) {
+    if (d.v_level[vcell] == 1 && d.v_state[vcell] == HIVED_CELL_USED) {
+      int pc = d.v_pcell[vcell];
+      int g = pc >= 0 ? d.p_using[pc] : -1;
+      if (g < 0) { panic(HIVED_ERR_PLATFORM); return; }
+      lazyPreemptAffinityGroup(g, nullptr);
+    }
+    int c0 = d.v_child0[vcell], n = d.v_nchild[vcell];
+    for (int i = 0; i < n; i++) lazyPreemptCell(c0 + i);
+  }
+  // hived_algorithm.go:1203-1222
+  HIVED_DEV void revertLazyPreempt(int g, const int32_t* save) {
+    if (!save[0]) { panic(HIVED_ERR_PLATFORM); return; }  // nil placement indexed in the reference
+    int nl = groupLeaves(g);
+    for (int i = 0; i < nl; i++) {
+      int pLeaf = gphys(g)[i];
+      if (pLeaf < 0) continue;
+      int vLeaf = save[1 + i];
+      releaseLeafCell(pLeaf, d.g_vc[g]);
+      allocateLeafCell(pLeaf, vLeaf, d.g_prio[g], d.g_vc[g]);
+    }
+    for (int i = 0; i < nl; i++) HV_ST(&gvirt(g)[i], save[1 + i]);
+    HV_ST(&d.g_flags[g], (d.g_flags[g] | GF_HAS_VIRTUAL) & ~GF_LAZY_PREEMPTED);
+  }
+
+  // hived_algorithm.go:1043-1070
+  HIVED_DEV void deleteAllocatedAffinityGroup(int g) {
+    int nl = groupLeaves(g);
+    for (int i = 0; i < nl; i++) {
+      int pLeaf = gphys(g)[i];
+      if (pLeaf < 0) continue;
+      HV_ST(&d.p_using[pLeaf], -1);
+      if (d.p_state[pLeaf] == HIVED_CELL_USED) {
+        releaseLeafCell(pLeaf, d.g_vc[g]);
+        setCellState(pLeaf, HIVED_CELL_FREE);
+      } else {
+        setCellState(pLeaf, HIVED_CELL_RESERVED);
+      }
+    }
+    eraseGroup(g);
+  }
+  // utils.go:267-283
+  HIVED_DEV int retrieveVirtualCell(int g, int pLeaf) const {
+    int nl = groupLeaves(g);
+    for (int i = 0; i < nl; i++)
+      if (gphys(g)[i] == pLeaf) return gvirt(g)[i];
+    return -1;
+  }
+  // hived_algorithm.go:1114-1145
+  HIVED_DEV_NOINLINE void deletePreemptingAffinityGroup(int g) {
+    int nl = groupLeaves(g);
+    for (int i = 0; i < nl; i++) {
+      int pLeaf = gphys(g)[i];
+      releaseLeafCell(pLeaf, d.g_vc[g]);
+      HV_ST(&d.p_resv[pLeaf], -1);
+      if (d.p_state[pLeaf] == HIVED_CELL_RESERVING) {
+        setCellState(pLeaf, HIVED_CELL_USED);
+        int bg = d.p_using[pLeaf];
+        int bv = -1;
+        if (d.g_flags[bg] & GF_HAS_VIRTUAL) bv = retrieveVirtualCell(bg, pLeaf);
+        allocateLeafCell(pLeaf, bv, d.g_prio[bg], d.g_vc[bg]);
+      } else {
+        setCellState(pLeaf, HIVED_CELL_FREE);
+      }
+    }
+    eraseGroup(g);
+  }
+  // hived_algorithm.go:1147-1163
+  HIVED_DEV void allocatePreemptingAffinityGroup(int g) {
+    int nl = groupLeaves(g);
+    for (int i = 0; i < nl; i++) {
+      int pLeaf = gphys(g)[i];
+      HV_ST(&d.p_resv[pLeaf], -1);
+      HV_ST(&d.p_using[pLeaf], g);
+      setCellState(pLeaf, HIVED_CELL_USED);
+    }
+    HV_ST(&d.g_state[g], HIVED_GROUP_ALLOCATED);
+    HV_ST(&d.g_npre[g], 0);
+  }
+  // hived_algorithm.go:1072-1112
+  HIVED_DEV_NOINLINE void createPreemptingAffinityGroup(int g, const hived_pod_spec_t& sp, const int32_t* phys, const int32_t* virt) {
+    newGroup(g, sp, HIVED_GROUP_PREEMPTING);
+    int nl = groupLeaves(g);
+    for (int i = 0; i < nl; i++) { HV_ST(&gphys(g)[i], phys[i]); HV_ST(&gvirt(g)[i], virt[i]); }
+    for (int i = 0; i < nl; i++) {
+      int pLeaf = phys[i], vLeaf = virt[i];
+      if (d.p_state[pLeaf] == HIVED_CELL_USED) {
+        int ug = d.p_using[pLeaf];
+        releaseLeafCell(pLeaf, d.g_vc[ug]);
+        HV_ST(&d.g_state[ug], HIVED_GROUP_BEING_PREEMPTED);
+      }
+      allocateLeafCell(pLeaf, vLeaf, sp.priority, sp.vc);
+      HV_ST(&d.p_resv[pLeaf], g);
+      if (d.p_state[pLeaf] == HIVED_CELL_USED) setCellState(pLeaf, HIVED_CELL_RESERVING);
+      else setCellState(pLeaf, HIVED_CELL_RESERVED);
+    }
+    HV_ST(&gpre(g)[0], sp.pod);
+    HV_ST(&d.g_npre[g], 1);
+  }
+  HIVED_DEV void addPreemptingPod(int g, int pod) {  // g.preemptingPods[pod.UID] = pod
+    int n = d.g_npre[g];
+    for (int i = 0; i < n; i++) if (gpre(g)[i] == pod) return;
+    if (n >= d.S.PS) { panic(HIVED_ERR_CAPACITY); return; }
+    HV_ST(&gpre(g)[n], pod);
+    HV_ST(&d.g_npre[g], n + 1);
+  }
+
+  // ======================================================================================
+  // Schedule of a NEW affinity group (hived_algorithm.go:754-979)
+  // ======================================================================================
+  struct Req {
+    int vc, pinned, chain, priority, group;
+    bool ignoreSuggested;
+    int nmem;
+    int memLeaf[HIVED_MAX_MEMBERS], memPods[HIVED_MAX_MEMBERS];
+    int nleaves;
+  };
+  int lzCount;
+
+  // hived_algorithm.go:944-965
+  HIVED_DEV void tryLazyPreempt(const int32_t* vleaves, int nleaves) {
+    lzCount = 0;
+    for (int i = 0; i < nleaves; i++) {
+      int pLeaf = d.v_pcell[vleaves[i]];
+      if (pLeaf < 0) continue;
+      if (d.p_state[pLeaf] == HIVED_CELL_USED) {
+        int victim = d.p_using[pLeaf];
+        if (victim >= 0 && (d.g_flags[victim] & GF_LAZY_ENABLE)) {
+          int slot = -1;
+          for (int j = 0; j < lzCount; j++) if (d.lz_group[j] == victim) { slot = j; break; }
+          if (slot < 0) {
+            if (lzCount >= d.S.LZ) { panic(HIVED_ERR_CAPACITY); return; }
+            slot = lzCount++;
+            HV_ST(&d.lz_group[slot], victim);
+          }
+          lazyPreemptAffinityGroup(victim, d.lz_save + (int64_t)slot * (d.S.LS + 1));
+          if (sm->panic) return;
+        }
+      }
+    }
+  }
+
+  // hived_algorithm.go:898-942; intra_vc_scheduler.go:92-117
+  HIVED_DEV_NOINLINE bool scheduleGuaranteedAffinityGroup(const Req& r, int& reason, int& rcell) {
+    int vset = r.pinned >= 0 ? d.vc_pinned_vset[r.vc * d.S.nPinned + r.pinned] : (r.chain >= 0 ? d.vc_chain_vset[r.vc * d.S.nChains + r.chain] : -1);
+    int sched = vset >= 0 ? d.vset_sched[vset] : -1;
+    if (sched < 0) { reason = HIVED_WAIT_NO_SCHEDULER | HIVED_WAIT_SCOPE_VC; rcell = -1; return false; }
+    if (!tasSchedule(sched, r.nmem, r.memLeaf, r.memPods, r.priority, r.ignoreSuggested, d.pl_v, reason, rcell)) {
+      reason |= HIVED_WAIT_SCOPE_VC;
+      return false;
+    }
+    tryLazyPreempt(d.pl_v, r.nleaves);
+    if (sm->panic) return false;
+    toBindingPaths(d.pl_v, r.nleaves);
+    if (sm->panic) return false;
+    if (mapVirtualPlacementToPhysical(r.chain, r.ignoreSuggested)) {
+      for (int i = 0; i < r.nleaves; i++) HV_ST(&d.pl_p[i], d.binding[d.pl_v[i]]);  // toPhysicalPlacement types.go:260-280
+      reason = 0; rcell = -1;
+      return true;
+    }
+    if (sm->panic) return false;
+    for (int j = 0; j < lzCount; j++) revertLazyPreempt(d.lz_group[j], d.lz_save + (int64_t)j * (d.S.LS + 1));
+    reason = HIVED_WAIT_MAPPING; rcell = -1;
+    return false;
+  }
+  // hived_algorithm.go:967-979
+  HIVED_DEV bool scheduleOpportunisticAffinityGroup(const Req& r, int& reason, int& rcell) {
+    int sched = d.opp_sched[r.chain];
+    if (!tasSchedule(sched, r.nmem, r.memLeaf, r.memPods, OPP_PRIO, r.ignoreSuggested, d.pl_p, reason, rcell)) {
+      reason |= HIVED_WAIT_SCOPE_PHYSICAL;
+      return false;
+    }
+    reason = 0; rcell = -1;
+    return true;
+  }
+  // hived_algorithm.go:872-896; hasVirtual tells whether pl_v is meaningful
+  HIVED_DEV bool handleSchedulingRequest(const Req& r, bool& hasVirtual, int& reason, int& rcell) {
+    if (r.priority >= 0) { hasVirtual = true; return scheduleGuaranteedAffinityGroup(r, reason, rcell); }
+    hasVirtual = false;
+    return scheduleOpportunisticAffinityGroup(r, reason, rcell);
+  }
+  // hived_algorithm.go:798-829.  returns 1 placed, 0 not placed, <0 = -(user error code)
+  HIVED_DEV int scheduleForLeafCellType(Req& r, int leafType, bool typeSpecified, bool& hasVirtual, int& reason, int& rcell) {
+    bool vcHasType = false;
+    reason = 0; rcell = -1;
+    for (int i = 0; i < d.lt_cnt[leafType]; i++) {
+      int chain = d.lt_chains[d.lt_off[leafType] + i];
+      if (r.priority < 0 || d.vc_chain_vset[r.vc * d.S.nChains + chain] >= 0) {
+        vcHasType = true;
+        r.chain = chain;
+        if (handleSchedulingRequest(r, hasVirtual, reason, rcell)) { reason = 0; return 1; }
+        if (sm->panic) return 0;
+      }
+    }
+    if (typeSpecified && r.priority >= 0 && !vcHasType) return -HIVED_ERR_LEAF_TYPE_NOT_IN_VC;
+    return 0;
+  }
+  // hived_algorithm.go:754-796 (+ validateSchedulingRequest :855-870)
+  HIVED_DEV_NOINLINE int scheduleNewAffinityGroup(const hived_pod_spec_t& sp, Req& r, bool& hasVirtual, int& reason, int& rcell) {
+    r.vc = sp.vc; r.pinned = sp.pinned; r.chain = -1; r.priority = sp.priority; r.group = sp.group;
+    r.ignoreSuggested = (sp.flags & HIVED_SPEC_IGNORE_SUGGESTED) != 0;
+    r.nmem = mergeMembers(sp, r.memLeaf, r.memPods);
+    r.nleaves = 0;
+    for (int m = 0; m < r.nmem; m++) r.nleaves += r.memLeaf[m] * r.memPods[m];
+    reason = 0; rcell = -1; hasVirtual = false;
+    if (sp.vc < 0 || sp.vc >= d.S.nVCs) return -HIVED_ERR_UNKNOWN_VC;
+    if (sp.pinned != -1) {
+      if (sp.pinned < 0 || sp.pinned >= d.S.nPinned || d.vc_pinned_vset[sp.vc * d.S.nPinned + sp.pinned] < 0) return -HIVED_ERR_UNKNOWN_PINNED_CELL;
+      if (sp.priority == OPP_PRIO) return -HIVED_ERR_OPPORTUNISTIC_PINNED;
+      return handleSchedulingRequest(r, hasVirtual, reason, rcell) ? 1 : 0;
+    }
+    if (sp.leaf_type != -1) {
+      if (sp.leaf_type < 0 || sp.leaf_type >= d.S.nLeafTypes || d.lt_cnt[sp.leaf_type] == 0) return -HIVED_ERR_LEAF_TYPE_NOT_IN_CLUSTER;
+      return scheduleForLeafCellType(r, sp.leaf_type, true, hasVirtual, reason, rcell);
+    }
+    // any leaf cell type (:831-853): leaf types that own a chain, ascending
+    int lastReason = 0, lastCell = -1;
+    for (int lt = 0; lt < d.S.nLeafTypes; lt++) {
+      if (d.lt_cnt[lt] == 0) continue;
+      int tr, tc;
+      int rc = scheduleForLeafCellType(r, lt, false, hasVirtual, tr, tc);
+      if (rc != 0) { reason = 0; rcell = -1; return rc; }
+      if (sm->panic) return 0;
+      if (tr != 0) { lastReason = tr; lastCell = tc; }
+    }
+    reason = lastReason; rcell = lastCell;
+    return 0;
+  }
+
+  // ======================================================================================
+  // results
+  // ======================================================================================
+  HIVED_DEV void poolPut(int32_t v) {
+    if (sm->pool_off >= pool_cap) { panic(HIVED_ERR_CAPACITY); return; }
+    HV_ST(&pool[sm->pool_off], v);
+    HV_ST(&sm->pool_off, sm->pool_off + 1);
+  }
+  // utils.go:202-235.  victims written to the pool (pod id, node id) sorted by pod id; overlapping
+  // preemptor groups (sorted by id) to d.tmp_list, count returned through nOverlap.
+  HIVED_DEV_NOINLINE void collectPreemptionVictims(const int32_t* phys, int nleaves, hived_result_t* res, int& nOverlap) {
+    int32_t* groups = d.tmp_list;  // using groups (first half) — tmp_list has >= MAX_FANOUT + maxLevelCount entries
+    int ng = 0;
+    nOverlap = 0;
+    int32_t* overlap = d.lz_group;  // reuse: lazy-preempt bookkeeping is dead by now
+    long long start = sm->pool_off;
+    for (int i = 0; i < nleaves; i++) {
+      int c = phys[i];
+      if (c < 0) continue;
+      int st = d.p_state[c];
+      if (st == HIVED_CELL_USED || st == HIVED_CELL_RESERVING) {
+        int g = d.p_using[c];
+        bool seen = false;
+        for (int j = 0; j < ng; j++) if (groups[j] == g) { seen = true; break; }
+        if (!seen && g >= 0) {
+          if (ng >= d.S.maxLevelCount + MAX_FANOUT) { panic(HIVED_ERR_CAPACITY); return; }
+          HV_ST(&groups[ng], g); ng++;
+        }
+      }
+      if (st == HIVED_CELL_RESERVING || st == HIVED_CELL_RESERVED) {
+        int g = d.p_resv[c];
+        bool seen = false;
+        for (int j = 0; j < nOverlap; j++) if (overlap[j] == g) { seen = true; break; }
+        if (!seen && g >= 0) {
+          if (nOverlap >= d.S.LS) { panic(HIVED_ERR_CAPACITY); return; }
+          HV_ST(&overlap[nOverlap], g); nOverlap++;
+        }
+      }
+    }
+    int nv = 0;
+    for (int j = 0; j < ng; j++) {
+      int g = groups[j], np = groupPods(g);
+      for (int k = 0; k < np; k++) {
+        int pod = gpods(g)[k];
+        if (pod < 0) continue;
+        // insert sorted by pod id
+        poolPut(0); poolPut(0);
+        if (sm->panic) return;
+        int pos = nv;
+        while (pos > 0 && pool[start + 2 * (pos - 1)] > pod) {
+          HV_ST(&pool[start + 2 * pos], pool[start + 2 * (pos - 1)]);
+          HV_ST(&pool[start + 2 * pos + 1], pool[start + 2 * (pos - 1) + 1]);
+          pos--;
+        }
+        HV_ST(&pool[start + 2 * pos], pod);
+        HV_ST(&pool[start + 2 * pos + 1], d.pod_node[pod]);
+        nv++;
+      }
+    }
+    for (int i = 1; i < nOverlap; i++) {  // ascending group id
+      int g = overlap[i], j = i - 1;
+      while (j >= 0 && overlap[j] > g) { HV_ST(&overlap[j + 1], overlap[j]); j--; }
+      HV_ST(&overlap[j + 1], g);
+    }
+    HV_ST(&res->victim_off, nv ? (int)start : 0);
+    HV_ST(&res->n_victims, nv);
+    if (nv == 0) HV_ST(&sm->pool_off, start);
+  }
+
+  // generatePodScheduleResult / generateAffinityGroupBindInfo (utils.go:38-171)
+  HIVED_DEV_NOINLINE void emitBind(hived_result_t* res, int nmem, const int* memLeaf, const int* memPods, const int32_t* phys,
+                                   const int32_t* virt, bool hasVirtual, int curLeafNum, int curPodIndex) {
+    HV_ST(&res->kind, HIVED_KIND_BIND);
+    HV_ST(&res->has_virtual, hasVirtual ? 1 : 0);
+    HV_ST(&res->pod_index, curPodIndex);
+    HV_ST(&res->n_members, nmem);
+    HV_ST(&res->leaf_off, (int)sm->pool_off);
+    int k = 0;
+    for (int m = 0; m < nmem; m++) {
+      HV_ST(&res->member_leaf_num[m], memLeaf[m]);
+      HV_ST(&res->member_pod_num[m], memPods[m]);
+      for (int pi = 0; pi < memPods[m]; pi++) {
+        if (memLeaf[m] == curLeafNum && pi == curPodIndex) {
+          HV_ST(&res->this_off, (int)sm->pool_off);
+          HV_ST(&res->this_n, memLeaf[m]);
+          int first = phys[k];
+          if (first < 0) { panic(HIVED_ERR_PLATFORM); return; }
+          HV_ST(&res->node, d.p_node[first]);
+          HV_ST(&res->chain, d.p_chain[first]);
+        }
+        for (int j = 0; j < memLeaf[m]; j++, k++) {
+          int pl = phys[k];
+          if (pl < 0) { panic(HIVED_ERR_PLATFORM); return; }  // retrieveMissingPodPlacement: recovery path
+          poolPut(d.p_node[pl]);
+          poolPut(d.p_leafidx[pl]);
+          int t = -1;
+          if (hasVirtual) { int vl = virt[k]; t = d.chain_lvl_type[cl(d.v_chain[vl], d.v_level[d.v_pre[vl]])]; }
+          poolPut(t);
+          if (sm->panic) return;
+        }
+      }
+    }
+    HV_ST(&res->n_leaves, k);
+  }
+
+  // ======================================================================================
+  // AddAllocatedPod / createAllocatedAffinityGroup (hived_algorithm.go:247-270, 981-1041, 1224-1290)
+  // ======================================================================================
+  // utils.go:347-378 through the (node, chain) -> leaves table
+  HIVED_DEV int findPhysicalLeafCellInChain(int chain, int node, int leafIdx) const {
+    if (chain < 0 || node < 0) return -1;
+    int k = node * d.S.nChains + chain;
+    for (int i = 0; i < d.ncl_cnt[k]; i++) {
+      int leaf = d.ncl_list[d.ncl_off[k] + i];
+      if (leafIdx < 0 || d.p_leafidx[leaf] == leafIdx) return leaf;
+    }
+    return -1;
+  }
+  // utils.go:318-345
+  HIVED_DEV int findPhysicalLeafCell(int chain, int node, int leafIdx) const {
+    int g = findPhysicalLeafCellInChain(chain, node, leafIdx);
+    if (g >= 0) return g;
+    for (int c = 0; c < d.S.nChains; c++)
+      if (c != chain) { g = findPhysicalLeafCellInChain(c, node, leafIdx); if (g >= 0) return g; }
+    return -1;
+  }
+  // cell_allocation.go:348-372 over a list (ptr) or a contiguous range
+  HIVED_DEV int getLowestPriorityVirtualCell(const int32_t* list, int base, int n, int p) const {
+    int lowest = HIVED_MAX_GUARANTEED_PRIORITY, cell = -1;
+    for (int i = 0; i < n; i++) {
+      int vc = list ? list[i] : base + i;
+      int q = d.v_prio[vc];
+      if (q == FREE_PRIO) {
+        if (d.v_pcell[vc] < 0) return vc;
+        continue;
+      } else if (q < p && q < lowest) { lowest = q; cell = vc; }
+    }
+    return cell;
+  }
+  // cell_allocation.go:317-346.  vccl: pinned -> the vset's cells at the level; else the VC's preassigned roots
+  HIVED_DEV int mapPhysicalCellToVirtual(int c, int vc, int chain, int pinned, int preassignedLevel, int p) const {
+    int steps = 0;
+    int virt = -1;
+    while (true) {
+      if (d.p_vcell[c] >= 0) { virt = d.p_vcell[c]; break; }
+      if (d.p_level[c] == preassignedLevel) {
+        if (pinned >= 0) {
+          int vset = d.vc_pinned_vset[vc * d.S.nPinned + pinned];
+          int k = vset * MAXL + preassignedLevel;
+          virt = (preassignedLevel < MAXL) ? getLowestPriorityVirtualCell(nullptr, d.v_lvl_base[k], d.v_lvl_cnt[k], p) : -1;
+        } else {
+          int k = vcl(vc, chain, preassignedLevel);
+          virt = getLowestPriorityVirtualCell(d.pre_list + d.pre_off[k], 0, d.pre_cnt[k], p);
+        }
+        break;
+      }
+      if (d.p_parent[c] < 0) return -1;
+      c = d.p_parent[c];
+      steps++;
+    }
+    for (int i = 0; i < steps && virt >= 0; i++) virt = getLowestPriorityVirtualCell(nullptr, d.v_child0[virt], d.v_nchild[virt], p);
+    return virt;
+  }
+
+  struct BindView {  // api.PodBindInfo in ids
+    int node, first_leaf, chain, has_preassigned, n_members;
+    const int32_t* member_leaf_num;
+    const int32_t* member_pod_num;
+    const int32_t* leaves;  // triples
+  };
+
+  // utils.go:291-304
+  HIVED_DEV static int getAllocatedPodIndex(const BindView& b, int leafNum) {
+    int k = 0;
+    for (int m = 0; m < b.n_members; m++) {
+      int ln = b.member_leaf_num[m], pn = b.member_pod_num[m];
+      if (ln == leafNum) {
+        for (int pi = 0; pi < pn; pi++) {
+          if (b.leaves[3 * (k + pi * ln)] == b.node)
+            for (int j = 0; j < ln; j++)
+              if (b.leaves[3 * (k + pi * ln + j) + 1] == b.first_leaf) return pi;
+        }
+      }
+      k += ln * pn;
+    }
+    return -1;
+  }
+
+  HIVED_DEV_NOINLINE void createAllocatedAffinityGroup(const hived_pod_spec_t& sp, const BindView& b) {
+    int g = sp.group;
+    newGroup(g, sp, HIVED_GROUP_ALLOCATED);
+    bool shouldLazyPreempt = false;
+    int k = 0;
+    for (int m = 0; m < b.n_members; m++) {
+      int leafNumber = b.member_leaf_num[m];
+      int gm = memberOf(g, leafNumber);
+      int leafOff = 0, podOff = 0;
+      if (gm >= 0) memberOffsets(g, gm, leafOff, podOff);
+      for (int podIndex = 0; podIndex < b.member_pod_num[m]; podIndex++) {
+        int node = b.leaves[3 * k];
+        for (int li = 0; li < leafNumber; li++, k++) {
+          // findAllocatedLeafCell :1224-1290
+          int pLeaf = findPhysicalLeafCell(b.chain, node, b.leaves[3 * k + 1]);
+          if (pLeaf < 0) continue;  // not found in the spec: ignored
+          int vLeaf = -1;
+          int lazy = 1;  // 0 nil, 1 false, 2 true
+          if (!b.has_preassigned) {
+            lazy = 2;
+          } else if ((d.g_flags[g] & GF_HAS_VIRTUAL) && !shouldLazyPreempt) {
+            int t = b.leaves[3 * k + 2];
+            if (t != -1) {
+              int chainOfLeaf = d.p_chain[pLeaf];
+              int preLevel = -1;
+              for (int l = 1; l <= d.chain_top[chainOfLeaf]; l++)
+                if (d.chain_lvl_type[cl(chainOfLeaf, l)] == t) preLevel = l;
+              if (preLevel >= 0 && sp.vc >= 0 && sp.vc < d.S.nVCs) {
+                bool have;
+                if (sp.pinned != -1) have = sp.pinned >= 0 && sp.pinned < d.S.nPinned && d.vc_pinned_vset[sp.vc * d.S.nPinned + sp.pinned] >= 0;
+                else have = d.vc_chain_vset[sp.vc * d.S.nChains + chainOfLeaf] >= 0;
+                if (have) vLeaf = mapPhysicalCellToVirtual(pLeaf, sp.vc, chainOfLeaf, sp.pinned != -1 ? sp.pinned : -1, preLevel, sp.priority);
+              }
+              lazy = vLeaf < 0 ? 2 : 1;
+            } else {
+              lazy = 0;
+            }
+          }
+          if (gm < 0 || podIndex >= d.g_mem_pods[g * 8 + gm]) { panic(HIVED_ERR_PLATFORM); return; }  // index out of range
+          int slot = leafOff + podIndex * leafNumber + li;
+          HV_ST(&gphys(g)[slot], pLeaf);
+          if (lazy == 0) {
+            HV_ST(&d.g_flags[g], d.g_flags[g] & ~GF_HAS_VIRTUAL);
+          } else if (vLeaf >= 0) {
+            HV_ST(&gvirt(g)[slot], vLeaf);
+            if (inFreeCellList(pLeaf) && d.v_prio[d.v_pre[vLeaf]] > FREE_PRIO) lazyPreemptCell(d.v_pre[vLeaf]);
+          } else {
+            shouldLazyPreempt = shouldLazyPreempt || lazy == 2;
+          }
+          bool safetyOk = allocateLeafCell(pLeaf, vLeaf, sp.priority, sp.vc);
+          HV_ST(&d.p_using[pLeaf], g);
+          setCellState(pLeaf, HIVED_CELL_USED);
+          if (!safetyOk) shouldLazyPreempt = true;
+          if (sm->panic) return;
+        }
+      }
+    }
+    if (shouldLazyPreempt) lazyPreemptAffinityGroup(g, nullptr);
+  }
+
+  HIVED_DEV_NOINLINE int addAllocatedPod(const hived_pod_spec_t& sp, const BindView& b, int podIndexFromInfo) {
+    int g = sp.group;
+    int podIndex = 0;
+    if (d.g_state[g] != HIVED_GROUP_NONE) {
+      if (d.g_state[g] == HIVED_GROUP_PREEMPTING) allocatePreemptingAffinityGroup(g);
+      podIndex = podIndexFromInfo;
+      if (podIndex == -1) return 0;
+    } else {
+      createAllocatedAffinityGroup(sp, b);
+      if (sm->panic) return 0;
+    }
+    int m = memberOf(g, sp.leaf_num);
+    if (m < 0 || podIndex < 0 || podIndex >= d.g_mem_pods[g * 8 + m]) { panic(HIVED_ERR_PLATFORM); return 0; }
+    int leafOff, podOff;
+    memberOffsets(g, m, leafOff, podOff);
+    HV_ST(&gpods(g)[podOff + podIndex], sp.pod);
+    HV_ST(&d.pod_node[sp.pod], b.node);
+    return 0;
+  }
+
+  // hived_algorithm.go:272-296
+  HIVED_DEV void deleteAllocatedPod(int g, int leafNum, int podIndex) {
+    if (g < 0 || g >= d.S.maxGroups || d.g_state[g] == HIVED_GROUP_NONE) return;
+    if (podIndex == -1) return;
+    int m = memberOf(g, leafNum);
+    if (m < 0 || podIndex < 0 || podIndex >= d.g_mem_pods[g * 8 + m]) { panic(HIVED_ERR_PLATFORM); return; }
+    int leafOff, podOff;
+    memberOffsets(g, m, leafOff, podOff);
+    HV_ST(&gpods(g)[podOff + podIndex], -1);
+    int np = groupPods(g);
+    for (int i = 0; i < np; i++) if (gpods(g)[i] >= 0) return;
+    deleteAllocatedAffinityGroup(g);
+  }
+  // hived_algorithm.go:229-245
+  HIVED_DEV void deleteUnallocatedPod(int g, int pod) {
+    if (g < 0 || g >= d.S.maxGroups || d.g_state[g] != HIVED_GROUP_PREEMPTING) return;
+    int n = d.g_npre[g];
+    for (int i = 0; i < n; i++)
+      if (gpre(g)[i] == pod) { HV_ST(&gpre(g)[i], gpre(g)[n - 1]); n--; HV_ST(&d.g_npre[g], n); break; }
+    if (n == 0) deletePreemptingAffinityGroup(g);
+  }
+
+  // ======================================================================================
+  // Schedule (hived_algorithm.go:180-224, 655-752)
+  // ======================================================================================
+  HIVED_DEV_NOINLINE int schedule(const hived_pod_spec_t& sp, int phase, hived_result_t* res) {
+    int g = sp.group;
+    stat_add(ST_SCHEDULE, 1);
+    {
+      long long bit = (sp.priority >= -1 && sp.priority < 62) ? (1ll << (sp.priority + 1)) : (1ll << 63);
+      if (!(d.stats[ST_PRIO_MASK] & bit)) HV_ST(&d.stats[ST_PRIO_MASK], d.stats[ST_PRIO_MASK] | bit);
+    }
+    bool havePlacement = false, hasVirtual = false;
+    const int32_t* phys = nullptr;
+    const int32_t* virt = nullptr;
+    int nmem = 0, memLeaf[HIVED_MAX_MEMBERS], memPods[HIVED_MAX_MEMBERS];
+    int podIndex = 0, reason = 0, rcell = -1;
+    bool victimsCollected = false;
+    if (d.g_state[g] != HIVED_GROUP_NONE) {
+      // schedulePodFromExistingGroup :655-712
+      int nl = groupLeaves(g);
+      bool badOrNonSuggested = false;  // collectBadOrNonSuggestedNodes utils.go:175-200 (ignoreK8sSuggestedNodes is never set on a group)
+      for (int i = 0; i < nl; i++) {
+        int c = gphys(g)[i];
+        if (c < 0) continue;
+        if (!d.p_healthy[c] || !node_suggested(d.p_node[c])) { badOrNonSuggested = true; break; }
+      }
+      nmem = d.g_nmem[g];
+      for (int m = 0; m < nmem; m++) { memLeaf[m] = d.g_mem_leaf[g * 8 + m]; memPods[m] = d.g_mem_pods[g * 8 + m]; }
+      if (d.g_state[g] == HIVED_GROUP_ALLOCATED) {
+        havePlacement = true; phys = gphys(g); virt = gvirt(g); hasVirtual = (d.g_flags[g] & GF_HAS_VIRTUAL) != 0;
+        int m = memberOf(g, sp.leaf_num);
+        podIndex = -1;
+        if (m >= 0) {
+          int leafOff, podOff;
+          memberOffsets(g, m, leafOff, podOff);
+          for (int i = 0; i < d.g_mem_pods[g * 8 + m]; i++)
+            if (gpods(g)[podOff + i] < 0) { podIndex = i; break; }
+        }
+        if (podIndex == -1) return HIVED_ERR_TOO_MANY_PODS;
+      } else {
+        if (phase == HIVED_PHASE_PREEMPTING && badOrNonSuggested) {
+          deletePreemptingAffinityGroup(g);
+        } else {
+          havePlacement = true; phys = gphys(g); virt = gvirt(g); hasVirtual = (d.g_flags[g] & GF_HAS_VIRTUAL) != 0;
+          int nOverlap;
+          collectPreemptionVictims(phys, nl, res, nOverlap);
+          victimsCollected = true;
+          addPreemptingPod(g, sp.pod);
+        }
+      }
+      if (sm->panic) return sm->panic;
+    }
+    if (d.g_state[g] == HIVED_GROUP_NONE) {
+      // schedulePodFromNewGroup :714-752
+      Req r;
+      int rc = scheduleNewAffinityGroup(sp, r, hasVirtual, reason, rcell);
+      if (sm->panic) return sm->panic;
+      if (rc < 0) return -rc;
+      nmem = r.nmem;
+      for (int m = 0; m < nmem; m++) { memLeaf[m] = r.memLeaf[m]; memPods[m] = r.memPods[m]; }
+      podIndex = 0;
+      if (rc == 1) {
+        havePlacement = true; phys = d.pl_p; virt = d.pl_v;
+        int nOverlap;
+        collectPreemptionVictims(phys, r.nleaves, res, nOverlap);
+        victimsCollected = true;
+        if (sm->panic) return sm->panic;
+        if (phase == HIVED_PHASE_PREEMPTING) {
+          // copy first: cancelling preemptors never touches pl_*, but keep the order of the reference
+          for (int i = 0; i < nOverlap; i++) deletePreemptingAffinityGroup(d.lz_group[i]);
+          if (res->n_victims != 0) {
+            if (!hasVirtual) { panic(HIVED_ERR_PLATFORM); return sm->panic; }  // nil virtual placement indexed in the reference
+            for (int i = 0; i < r.nleaves; i++) { HV_ST(&d.pl_p2[i], d.pl_p[i]); HV_ST(&d.pl_v2[i], d.pl_v[i]); }
+            createPreemptingAffinityGroup(g, sp, d.pl_p2, d.pl_v2);
+          }
+        }
+        if (sm->panic) return sm->panic;
+      } else {
+        havePlacement = false;
+      }
+    }
+    // generatePodScheduleResult utils.go:38-79
+    if (!havePlacement) {
+      HV_ST(&res->kind, HIVED_KIND_WAIT);
+      HV_ST(&res->wait_code, reason);
+      HV_ST(&res->wait_cell, rcell);
+      stat_add(ST_WAIT, 1);
+      return 0;
+    }
+    if (victimsCollected && res->n_victims > 0) {
+      HV_ST(&res->kind, HIVED_KIND_PREEMPT);
+      HV_ST(&res->has_virtual, hasVirtual ? 1 : 0);
+      stat_add(ST_PREEMPT, 1);
+      return 0;
+    }
+    emitBind(res, nmem, memLeaf, memPods, phys, virt, hasVirtual, sp.leaf_num, podIndex);
+    stat_add(ST_BIND, 1);
+    return sm->panic;
+  }
+
+  // ======================================================================================
+  // one event (leader warp).  aux: hived_bind_info_t + leaf triples for the explicit AddAllocatedPod.
+  // ======================================================================================
+  HIVED_DEV_NOINLINE void processEvent(const hived_event_t& ev, hived_result_t* res, const uint32_t* suggPool, const int32_t* aux) {
+    HV_ST(&sm->panic, 0);
+    // clearResult
+    {
+      int32_t* w = reinterpret_cast<int32_t*>(res);
+      for (int i = 0; i < (int)(sizeof(hived_result_t) / 4); i++) HV_ST(&w[i], 0);
+      HV_ST(&res->wait_cell, -1); HV_ST(&res->chain, -1); HV_ST(&res->node, -1);
+    }
+    sugg = (ev.suggested_off >= 0 && suggPool) ? suggPool + ev.suggested_off : nullptr;
+    int rc = 0;
+    int type = ev.type;
+    if (type == HIVED_EV_SCHEDULE || type == EV_SCHEDULE_ONLY) {
+      const hived_pod_spec_t& sp = ev.spec;
+      rc = validateSpec(sp);
+      if (rc == 0) rc = schedule(sp, ev.phase, res);
+      if (rc == 0 && type == HIVED_EV_SCHEDULE && res->kind == HIVED_KIND_BIND) {
+        // the filterRoutine sequence: AddAllocatedPod with the PodBindInfo just produced
+        BindView b;
+        b.node = res->node; b.first_leaf = pool[res->this_off + 1]; b.chain = res->chain; b.has_preassigned = 1;
+        b.n_members = res->n_members; b.member_leaf_num = res->member_leaf_num; b.member_pod_num = res->member_pod_num;
+        b.leaves = pool + res->leaf_off;
+        sugg = nullptr;
+        addAllocatedPod(sp, b, getAllocatedPodIndex(b, sp.leaf_num));
+        rc = sm->panic;
+      }
+    } else if (type == EV_ADD_ALLOCATED) {
+      const hived_bind_info_t* bi = reinterpret_cast<const hived_bind_info_t*>(aux);
+      BindView b;
+      b.node = bi->node; b.first_leaf = bi->first_leaf; b.chain = bi->chain; b.has_preassigned = bi->has_preassigned;
+      b.n_members = bi->n_members; b.member_leaf_num = bi->member_leaf_num; b.member_pod_num = bi->member_pod_num;
+      b.leaves = aux + sizeof(hived_bind_info_t) / 4;
+      rc = validateSpec(ev.spec);
+      if (rc == 0) { addAllocatedPod(ev.spec, b, ev.arg0); rc = sm->panic; }
+    } else if (type == HIVED_EV_DELETE_ALLOCATED) {
+      deleteAllocatedPod(ev.spec.group, ev.spec.leaf_num, ev.arg0);
+      rc = sm->panic;
+    } else if (type == HIVED_EV_DELETE_UNALLOCATED) {
+      deleteUnallocatedPod(ev.spec.group, ev.spec.pod);
+      rc = sm->panic;
+    } else if (type == HIVED_EV_NODE_HEALTH) {
+      setNodeHealth(ev.arg0, ev.arg1 != 0);
+      rc = sm->panic;
+    } else {
+      rc = HIVED_ERR_PLATFORM;
+    }
+    HV_ST(&res->error, rc);
+  }
+  static constexpr int EV_SCHEDULE_ONLY = 16, EV_ADD_ALLOCATED = 17, EV_INIT = 18;
+
+  // pkg/internal/utils.go:256-287 + capacity checks (the shim validates first; this is defensive)
+  HIVED_DEV int validateSpec(const hived_pod_spec_t& sp) const {
+    if (sp.group < 0 || sp.group >= d.S.maxGroups || sp.pod < 0 || sp.pod >= d.S.maxPods) return HIVED_ERR_CAPACITY;
+    if (sp.priority < OPP_PRIO || sp.priority > HIVED_MAX_GUARANTEED_PRIORITY || sp.leaf_num <= 0) return HIVED_ERR_BAD_SPEC;
+    if (sp.n_members <= 0 || sp.n_members > HIVED_MAX_MEMBERS) return HIVED_ERR_BAD_SPEC;
+    bool in = false;
+    long long leaves = 0, pods = 0;
+    for (int i = 0; i < sp.n_members; i++) {
+      if (sp.member_pod_num[i] <= 0 || sp.member_leaf_num[i] <= 0) return HIVED_ERR_BAD_SPEC;
+      if (sp.member_leaf_num[i] == sp.leaf_num) in = true;
+      leaves += (long long)sp.member_leaf_num[i] * sp.member_pod_num[i];
+      pods += sp.member_pod_num[i];
+    }
+    if (!in) return HIVED_ERR_BAD_SPEC;
+    if (leaves > d.S.LS || pods > d.S.PS) return HIVED_ERR_CAPACITY;
+    return 0;
+  }
+
+  // NewHivedAlgorithm's dynamic part: initPinnedCells + initBadNodes (hived_algorithm.go:437-464)
+  HIVED_DEV_NOINLINE void initState(const int32_t* pinnedOrder, int nPinnedOrder, const int32_t* badOrder, int nBad) {
+    HV_ST(&sm->panic, 0);
+    sugg = nullptr;
+    for (int i = 0; i < nPinnedOrder; i++) {
+      int pi = pinnedOrder[i];
+      allocatePreassignedCell(d.pin_pcell[pi], d.pin_vc[pi], false);
+      bindCell(d.pin_pcell[pi], d.pin_vcell[pi]);
+    }
+    for (int i = 0; i < nBad; i++) setNodeHealth(badOrder[i], false);
+  }
+
+  // the CTA's main loop: leader warp walks the ordered batch, the other warps serve view passes
+  HIVED_DEV void run(const hived_event_t* events, int n, hived_result_t* results, const uint32_t* suggPool, const int32_t* aux,
+                     const int32_t* initLists, int nPinnedOrder, int nBad) {
+    if (hv_warp() == 0) {
+      if (initLists) initState(initLists, nPinnedOrder, initLists + nPinnedOrder, nBad);
+      for (int i = 0; i < n; i++) processEvent(events[i], &results[i], suggPool, aux);
+      HV_ST(&sm->cmd, CMD_EXIT);
+      hv_cta_sync();
+    } else {
+      while (true) {
+        hv_cta_sync();
+        if (sm->cmd == CMD_EXIT) break;
+        sugg = sm->a_sugg;
+        viewOp();
+      }
+    }
+  }
+};
+
+}  // namespace hived

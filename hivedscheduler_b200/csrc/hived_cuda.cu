@@ -1,0 +1,112 @@
+// libhived_cuda.so — the product: CUDA backend (sm_100a) of include/hived.h.
+//
+// One kernel, `hived_events_kernel`, runs the scheduling program of hived_core.h over an ordered
+// batch of events with ALL scheduler state resident in HBM (hived_dev.h).  It is launched as one
+// CTA: warp 0 walks the batch (the reference's contract is strictly sequential,
+// pkg/internal/types.go:64-71), the remaining warps are woken through the hardware barrier for the
+// data-parallel cluster-view pass of every scheduling decision.  There is no host implementation
+// of the algorithm in this library: if no CUDA device is usable hived_create fails with
+// HIVED_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+
+#include "hived_engine.hpp"
+
+namespace hived {
+
+constexpr int NT = 512;  // threads per CTA (16 warps); the kernel needs the full register file of one SM
+
+__global__ void __launch_bounds__(NT, 1)
+hived_events_kernel(const __grid_constant__ Dev dev, const hived_event_t* __restrict__ events, int n, hived_result_t* results,
+                    const uint32_t* suggPool, const int32_t* aux, const int32_t* initLists, int nPinnedOrder, int nBad,
+                    int32_t* pool, long long poolCap, long long* scalars) {
+  __shared__ Sm sm;
+  if (threadIdx.x == 0) {
+    sm.cmd = CMD_IDLE;
+    sm.panic = 0;
+    sm.pool_off = scalars[0];
+  }
+  __syncthreads();
+  Core core(dev, &sm, pool, poolCap);
+  core.run(events, n, results, suggPool, aux, initLists, nPinnedOrder, nBad);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    scalars[0] = sm.pool_off;
+    scalars[1] = sm.panic;
+  }
+}
+
+static bool cudaOk(cudaError_t e, std::string& err, const char* what) {
+  if (e == cudaSuccess) return true;
+  err = std::string(what) + ": " + cudaGetErrorString(e);
+  return false;
+}
+
+void* bk_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+  return p;
+}
+void bk_free(void* p) { cudaFree(p); }
+void bk_h2d(void* dst, const void* src, size_t bytes) { cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice); }
+void bk_d2h(void* dst, const void* src, size_t bytes) { cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost); }
+void bk_d2d(void* dst, const void* src, size_t bytes) { cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToDevice); }
+
+int bk_init(int device, std::string& err) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    err = std::string("no usable CUDA device (") + (e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e)) +
+          "); libhived_cuda has no CPU fallback";
+    return HIVED_ERR_NO_DEVICE;
+  }
+  if (device < 0 || device >= count) device = 0;
+  if (!cudaOk(cudaSetDevice(device), err, "cudaSetDevice")) return HIVED_ERR_NO_DEVICE;
+  // the program recurses (bad-cell propagation, buddy allocation, cell mapping): give it stack
+  size_t cur = 0;
+  cudaDeviceGetLimit(&cur, cudaLimitStackSize);
+  if (cur < 16384 && !cudaOk(cudaDeviceSetLimit(cudaLimitStackSize, 16384), err, "cudaDeviceSetLimit")) return HIVED_ERR_NO_DEVICE;
+  return 0;
+}
+
+struct CudaTimers {
+  cudaEvent_t start = nullptr, stop = nullptr;
+  cudaStream_t stream = nullptr;
+};
+
+int launchProgram(Engine& e, int n, bool withInit) {
+  if (!e.stream) {
+    CudaTimers* t = new CudaTimers();
+    if (!cudaOk(cudaStreamCreate(&t->stream), e.err, "cudaStreamCreate")) return HIVED_ERR_NO_DEVICE;
+    cudaEventCreate(&t->start);
+    cudaEventCreate(&t->stop);
+    e.stream = t;
+  }
+  CudaTimers* t = (CudaTimers*)e.stream;
+  long long scal[2] = {e.poolOff, 0};
+  cudaMemcpyAsync(e.dScalars.p, scal, sizeof scal, cudaMemcpyHostToDevice, t->stream);
+  cudaEventRecord(t->start, t->stream);
+  hived_events_kernel<<<1, NT, 0, t->stream>>>(
+      e.dev, (const hived_event_t*)e.dEvents.p, n, (hived_result_t*)e.dResults.p,
+      e.hasSugg ? (const uint32_t*)e.dSugg.p : nullptr, e.hasAux ? (const int32_t*)e.dAux.p : nullptr,
+      withInit ? (const int32_t*)e.dInit.p : nullptr, e.nPinnedOrder, e.nBad, (int32_t*)e.dPool.p,
+      withInit ? 0 : (long long)e.poolCapWords, (long long*)e.dScalars.p);
+  cudaEventRecord(t->stop, t->stream);
+  cudaMemcpyAsync(scal, e.dScalars.p, sizeof scal, cudaMemcpyDeviceToHost, t->stream);
+  cudaError_t err = cudaStreamSynchronize(t->stream);
+  if (err != cudaSuccess || (err = cudaGetLastError()) != cudaSuccess) {
+    e.err = std::string("hived_events_kernel failed: ") + cudaGetErrorString(err);
+    return HIVED_ERR_PLATFORM;
+  }
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, t->start, t->stop);
+  e.lastKernelMs = ms;
+  e.kernelMsTotal += ms;
+  e.kernelLaunches++;
+  e.poolOff = scal[0];
+  if (withInit && scal[1]) { e.err = "initialisation panicked on the device"; return (int)scal[1]; }
+  return 0;
+}
+
+}  // namespace hived
+
+extern "C" const char* hived_backend(void) { return "cuda-sm100a"; }

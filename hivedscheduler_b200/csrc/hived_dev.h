@@ -1,0 +1,80 @@
+// Device-resident state of the B200-native HiveD scheduling path: one POD struct of raw pointers
+// into HBM (flat int32 SoA, see DESIGN.md "Data layout").  Static arrays come from FlatTopo
+// (hived_topo.hpp); mutable arrays are the scheduler state that the reference keeps in its
+// pointer forest (pkg/algorithm/cell.go:58-142,315-324; hived_algorithm.go:40-105).
+#pragma once
+#include <cstdint>
+
+namespace hived {
+
+// X(name): static int32 array copied verbatim from FlatTopo::name
+#define HIVED_STATIC_ARRAYS(X)                                                                         \
+  X(p_parent) X(p_child0) X(p_nchild) X(p_level) X(p_chain) X(p_leaf0) X(p_nleaf) X(p_node)           \
+  X(p_leafidx) X(p_flags) X(p_nodes_off) X(p_nodes_cnt) X(nodes_flat)                                  \
+  X(v_parent) X(v_child0) X(v_nchild) X(v_level) X(v_chain) X(v_leaf0) X(v_nleaf) X(v_vc) X(v_pre)    \
+  X(v_vset) X(v_flags)                                                                                 \
+  X(chain_top) X(chain_leaftype) X(chain_lvl_type) X(chain_lvl_leafnum) X(chain_lvl_nchild)           \
+  X(p_lvl_base) X(p_lvl_cnt) X(chain_in_vc) X(lt_off) X(lt_cnt) X(lt_chains)                           \
+  X(vs_vc) X(vs_chain) X(vs_pinned) X(vs_top) X(v_lvl_base) X(v_lvl_cnt) X(vc_chain_vset)             \
+  X(vc_pinned_vset) X(pre_off) X(pre_cnt) X(pre_list) X(vc_chain_counter) X(pin_pcell) X(pin_vcell)   \
+  X(pin_vc) X(s_off) X(s_n) X(s_cross) X(s_chain) X(s_virtual) X(s_maxleaf) X(vset_sched) X(opp_sched) \
+  X(ncl_off) X(ncl_cnt) X(ncl_list) X(fl_base) X(fl_cap) X(dm_base) X(dm_cap)
+
+// Y(name, count, init): mutable int32 array of `count` elements filled with `init`
+// (count expressions may use the Dev size fields through `S.`)
+#define HIVED_MUTABLE_ARRAYS(Y)                                                                        \
+  Y(p_prio, S.NP, -2) Y(p_state, S.NP, 0) Y(p_healthy, S.NP, 1) Y(p_vcell, S.NP, -1) Y(p_split, S.NP, 0) \
+  Y(p_using, S.NP, -1) Y(p_resv, S.NP, -1) Y(p_usedopp, S.NP, 0) Y(p_flpos, S.NP, -1)                  \
+  Y(p_bfpos, S.NP, -1) Y(p_dmpos, S.NP, -1) Y(p_dmvc, S.NP, -1)                                        \
+  Y(v_prio, S.NV, -2) Y(v_state, S.NV, 0) Y(v_healthy, S.NV, 1) Y(v_pcell, S.NV, -1)                   \
+  Y(vcFree, S.nVCs * S.nChains * MAXL, 0) Y(allVCFree, S.nChains * MAXL, 0)                            \
+  Y(totalLeft, S.nChains * MAXL, 0) Y(allVCDoomed, S.nChains * MAXL, 0)                                \
+  Y(fl_data, S.flTotal, -1) Y(fl_len, S.nChains * MAXL, 0) Y(bf_data, S.flTotal, -1)                   \
+  Y(bf_len, S.nChains * MAXL, 0) Y(dm_data, S.dmTotal, -1) Y(dm_len, S.nVCs * S.nChains * MAXL, 0)     \
+  Y(cv, S.cvTotal, -1) Y(node_bad, S.nNodes, 0)                                                        \
+  Y(g_state, S.maxGroups, 0) Y(g_vc, S.maxGroups, -1) Y(g_prio, S.maxGroups, 0) Y(g_flags, S.maxGroups, 0) \
+  Y(g_nmem, S.maxGroups, 0) Y(g_mem_leaf, S.maxGroups * 8, 0) Y(g_mem_pods, S.maxGroups * 8, 0)        \
+  Y(g_phys, (int64_t)S.maxGroups * S.LS, -1) Y(g_virt, (int64_t)S.maxGroups * S.LS, -1)                \
+  Y(g_pods, (int64_t)S.maxGroups * S.PS, -1) Y(g_npre, S.maxGroups, 0)                                 \
+  Y(g_pre, (int64_t)S.maxGroups * S.PS, -1) Y(pod_node, S.maxPods, -1)                                 \
+  /* scratch of one scheduling decision */                                                             \
+  Y(sfl_data, S.flTotal, -1) Y(sfl_len, MAXL, 0)                                                       \
+  Y(vx_cell, S.VX, -1) Y(vx_child, S.VX, -1) Y(vx_last, S.VX, -1) Y(vx_next, S.VX, -1) Y(vx_nch, S.VX, 0) \
+  Y(vx_of, S.NV, -1) Y(vx_stamp, S.NV, 0) Y(binding, S.NV, -1)                                         \
+  Y(pa_list, S.LS, -1) Y(np_head, S.LS, -1) Y(np_cnt, S.LS, 0)                                         \
+  Y(pl_v, S.LS, -1) Y(pl_p, S.LS, -1) Y(pl_v2, S.LS, -1) Y(pl_p2, S.LS, -1)                            \
+  Y(cand, S.PS * MAX_NODE_LEAVES, -1) Y(cand_len, S.PS, 0) Y(cand_node, S.PS, -1)                      \
+  Y(pod_need, S.PS, 0) Y(pod_pos, S.PS, -1) Y(pod_cell, S.PS, -1)                                      \
+  Y(mc0, S.maxLevelCount + MAX_FANOUT, -1) Y(mcbuf, MAXL * MAX_FANOUT, -1)                             \
+  Y(mcpick, MAXL * MAX_FANOUT, 0) Y(mccells, MAXL * MAX_FANOUT, -1)                                    \
+  Y(lz_group, S.LS, -1) Y(lz_save, (int64_t)S.LZ * (S.LS + 1), -1) Y(ba_buf, (int64_t)MAXL * S.maxLevelCount, -1)                                           \
+  Y(tmp_list, S.maxLevelCount + MAX_FANOUT, -1)                                                        \
+  Y(vw_cell, S.maxViewN, -1) Y(vw_info, S.maxViewN, 0) Y(vw_ordA, S.maxViewN, 0) Y(vw_ordB, S.maxViewN, 0)
+
+struct DevSizes {
+  int32_t NP, NV, nChains, nVCs, nLeafTypes, nPinned, nNodes, nVsets, nScheds;
+  int32_t flTotal, dmTotal, cvTotal, maxGroups, maxPods, LS, PS, VX, LZ;
+  int32_t maxLevelCount, maxViewN, bitmapWords, maxLevels, maxNodeLeaves;
+};
+
+struct Dev {
+  DevSizes S;
+#define X(name) const int32_t* name;
+  HIVED_STATIC_ARRAYS(X)
+#undef X
+#define Y(name, count, init) int32_t* name;
+  HIVED_MUTABLE_ARRAYS(Y)
+#undef Y
+  long long* stats;   // [16] counters, see ST_* below
+  int32_t* epoch;     // [1] stamp for vx_stamp
+};
+
+enum {
+  ST_VIEW_NODES = 0, ST_LEAVES = 1, ST_FREE_CELLS = 2, ST_PODS = 3, ST_SCHEDULE = 4, ST_BIND = 5, ST_WAIT = 6,
+  ST_PREEMPT = 7, ST_PRIO_MASK = 8 /* bit (p+1) for small priorities, else bit 63 */, ST_COUNT = 16
+};
+
+// group flags
+enum { GF_LAZY_ENABLE = 1, GF_HAS_VIRTUAL = 2, GF_LAZY_PREEMPTED = 4 };
+
+}  // namespace hived

@@ -1,0 +1,408 @@
+// Host side of the library behind include/hived.h: owns the flattened topology, the device memory
+// and the staging buffers; every ABI call becomes an ordered batch of events executed by the device
+// program (hived_core.h).  Included by exactly one translation unit per build:
+//   hived_cuda.cu        -> libhived_cuda.so   (the product: CUDA backend, sm_100a, no host path)
+//   tests/emu/hived_emu.cpp -> test-only 1-thread emulation of the same device program (HIVED_EMU)
+// The backend supplies bk_* (memory) and launchProgram().
+#pragma once
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/hived.h"
+#include "../../include/hived_hash.h"
+#include "hived_topo.hpp"
+#define HIVED_TOPO_CONSTS
+#include "hived_core.h"
+
+namespace hived {
+
+struct Engine;
+// ---- backend hooks (defined by the including translation unit)
+void* bk_alloc(size_t bytes);
+void bk_free(void* p);
+void bk_h2d(void* dst, const void* src, size_t bytes);
+void bk_d2h(void* dst, const void* src, size_t bytes);
+void bk_d2d(void* dst, const void* src, size_t bytes);
+int bk_init(int device, std::string& err);
+// runs the program over n staged events; returns 0 or a HIVED_ERR_* code
+int launchProgram(Engine& e, int n, bool withInit);
+
+struct Buf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  void ensure(size_t need) {
+    if (need <= bytes) return;
+    if (p) bk_free(p);
+    size_t cap = need + need / 2 + 256;
+    p = bk_alloc(cap);
+    bytes = cap;
+  }
+  ~Buf() { if (p) bk_free(p); }
+};
+
+struct Engine {
+  FlatTopo T;
+  Dev dev{};
+  hived_options_t opt{};
+  std::string err;
+  std::vector<void*> allocs;
+  std::vector<std::pair<void*, size_t>> mutableRegions;  // for save/restore
+  std::vector<void*> savedRegions;
+  // staging (device side)
+  Buf dEvents, dResults, dPool, dSugg, dAux, dInit, dScalars;
+  long long poolOff = 0;
+  int nPinnedOrder = 0, nBad = 0;
+  uint64_t hash = HIVED_FNV_OFFSET;
+  float lastKernelMs = 0.f;
+  double kernelMsTotal = 0.0;
+  long long kernelLaunches = 0;
+  void* stream = nullptr;
+
+  ~Engine() {
+    for (void* p : allocs) bk_free(p);
+    for (void* p : savedRegions) bk_free(p);
+  }
+
+  template <typename TT>
+  TT* allocFill(size_t count, TT init) {
+    if (count == 0) count = 1;
+    std::vector<TT> h(count, init);
+    TT* p = (TT*)bk_alloc(count * sizeof(TT));
+    bk_h2d(p, h.data(), count * sizeof(TT));
+    allocs.push_back(p);
+    return p;
+  }
+  const int32_t* uploadStatic(const std::vector<int32_t>& v) {
+    size_t count = v.empty() ? 1 : v.size();
+    int32_t* p = (int32_t*)bk_alloc(count * sizeof(int32_t));
+    if (!v.empty()) bk_h2d(p, v.data(), v.size() * sizeof(int32_t));
+    allocs.push_back(p);
+    return p;
+  }
+
+  int create(const char* spec, const hived_options_t* o) {
+    if (o) opt = *o;
+    if (opt.max_groups <= 0) opt.max_groups = 1 << 17;
+    if (opt.max_pods <= 0) opt.max_pods = 1 << 20;
+    if (opt.max_group_leaves <= 0) opt.max_group_leaves = 64;
+    if (opt.max_group_pods <= 0) opt.max_group_pods = 8;
+    int rc = bk_init(opt.device, err);
+    if (rc) return rc;
+    try {
+      T = buildTopo(spec);
+    } catch (const TopoError& e) {
+      err = e.what();
+      return e.code;
+    } catch (const std::exception& e) {
+      err = e.what();
+      return HIVED_ERR_BAD_CONFIG;
+    }
+    DevSizes& S = dev.S;
+    S.NP = T.NP; S.NV = T.NV; S.nChains = T.nChains; S.nVCs = T.nVCs; S.nLeafTypes = T.nLeafTypes; S.nPinned = T.nPinned;
+    S.nNodes = T.nNodes; S.nVsets = T.nVsets; S.nScheds = T.nScheds;
+    S.flTotal = T.flTotal; S.dmTotal = T.dmTotal; S.cvTotal = (int32_t)T.cv_init.size();
+    S.maxGroups = opt.max_groups; S.maxPods = opt.max_pods; S.LS = opt.max_group_leaves; S.PS = opt.max_group_pods;
+    S.VX = S.LS * MAXL + 16; S.LZ = S.LS < 64 ? S.LS : 64;
+    S.maxLevelCount = T.maxLevelCount; S.maxViewN = T.maxViewN; S.bitmapWords = (T.nNodes + 31) / 32;
+    S.maxLevels = T.maxLevels; S.maxNodeLeaves = T.maxNodeLeaves;
+#define X(name) dev.name = uploadStatic(T.name);
+    HIVED_STATIC_ARRAYS(X)
+#undef X
+#define Y(name, count, init)                                                   \
+  {                                                                            \
+    size_t cnt_ = (size_t)(count);                                             \
+    dev.name = allocFill<int32_t>(cnt_, (int32_t)(init));                      \
+    mutableRegions.push_back({dev.name, (cnt_ ? cnt_ : 1) * sizeof(int32_t)}); \
+  }
+    HIVED_MUTABLE_ARRAYS(Y)
+#undef Y
+    dev.stats = allocFill<long long>(ST_COUNT, 0);
+    mutableRegions.push_back({dev.stats, ST_COUNT * sizeof(long long)});
+    dev.epoch = allocFill<int32_t>(1, 1);
+    mutableRegions.push_back({dev.epoch, sizeof(int32_t)});
+    // initial dynamic state (hived_algorithm.go:108-145, 365-409)
+    bk_h2d(dev.vcFree, T.vcFree.data(), T.vcFree.size() * 4);
+    bk_h2d(dev.allVCFree, T.allVCFree.data(), T.allVCFree.size() * 4);
+    bk_h2d(dev.totalLeft, T.totalLeft.data(), T.totalLeft.size() * 4);
+    if (!T.fl_init_data.empty()) bk_h2d(dev.fl_data, T.fl_init_data.data(), T.fl_init_data.size() * 4);
+    bk_h2d(dev.fl_len, T.fl_init_len.data(), T.fl_init_len.size() * 4);
+    {
+      std::vector<int32_t> flpos(T.NP ? T.NP : 1, -1);
+      for (int c = 0; c < T.nChains; c++)
+        for (int l = 1; l < MAXL; l++)
+          for (int i = 0; i < T.fl_init_len[c * MAXL + l]; i++) flpos[T.fl_init_data[T.fl_base[c * MAXL + l] + i]] = i;
+      bk_h2d(dev.p_flpos, flpos.data(), flpos.size() * 4);
+    }
+    if (!T.cv_init.empty()) bk_h2d(dev.cv, T.cv_init.data(), T.cv_init.size() * 4);
+    // initPinnedCells + initBadNodes run on the device
+    std::vector<int32_t> init = T.pinned_init_order;
+    nPinnedOrder = (int)T.pinned_init_order.size();
+    init.insert(init.end(), T.bad_init_order.begin(), T.bad_init_order.end());
+    nBad = (int)T.bad_init_order.size();
+    dInit.ensure((init.size() + 1) * 4);
+    if (!init.empty()) bk_h2d(dInit.p, init.data(), init.size() * 4);
+    dScalars.ensure(64);
+    dPool.ensure(4096 * 4);
+    dResults.ensure(sizeof(hived_result_t));
+    dEvents.ensure(sizeof(hived_event_t));
+    poolOff = 0;
+    rc = launchProgram(*this, 0, true);
+    if (rc) { if (err.empty()) err = "device initialisation failed"; return rc; }
+    return 0;
+  }
+
+  // stage + run a batch; host result/pool buffers are caller-owned
+  int runBatch(const hived_event_t* events, int n, const uint32_t* suggPool, int64_t suggWords, const int32_t* aux,
+               int64_t auxWords, hived_result_t* res, int32_t* pool, int64_t poolCap) {
+    if (n <= 0) return 0;
+    dEvents.ensure((size_t)n * sizeof(hived_event_t));
+    dResults.ensure((size_t)n * sizeof(hived_result_t));
+    dPool.ensure((size_t)(poolCap > 0 ? poolCap : 1) * 4);
+    bk_h2d(dEvents.p, events, (size_t)n * sizeof(hived_event_t));
+    hasSugg = suggPool != nullptr && suggWords > 0;
+    if (hasSugg) { dSugg.ensure((size_t)suggWords * 4); bk_h2d(dSugg.p, suggPool, (size_t)suggWords * 4); }
+    hasAux = aux != nullptr && auxWords > 0;
+    if (hasAux) { dAux.ensure((size_t)auxWords * 4); bk_h2d(dAux.p, aux, (size_t)auxWords * 4); }
+    poolOff = 0;
+    poolCapWords = poolCap;
+    int rc = launchProgram(*this, n, false);
+    if (rc) return rc;
+    bk_d2h(res, dResults.p, (size_t)n * sizeof(hived_result_t));
+    if (poolOff > 0) bk_d2h(pool, dPool.p, (size_t)poolOff * 4);
+    return 0;
+  }
+  bool hasSugg = false, hasAux = false;
+  int64_t poolCapWords = 0;
+
+  void readArray(const int32_t* devPtr, std::vector<int32_t>& out, size_t count) {
+    out.resize(count ? count : 1);
+    bk_d2h(out.data(), devPtr, out.size() * 4);
+  }
+  void saveState() {
+    if (savedRegions.empty())
+      for (auto& r : mutableRegions) savedRegions.push_back(bk_alloc(r.second));
+    for (size_t i = 0; i < mutableRegions.size(); i++) bk_d2d(savedRegions[i], mutableRegions[i].first, mutableRegions[i].second);
+    savedHash = hash;
+  }
+  int restoreState() {
+    if (savedRegions.empty()) return HIVED_ERR_PLATFORM;
+    for (size_t i = 0; i < mutableRegions.size(); i++) bk_d2d(mutableRegions[i].first, savedRegions[i], mutableRegions[i].second);
+    hash = savedHash;
+    return 0;
+  }
+  uint64_t savedHash = HIVED_FNV_OFFSET;
+};
+
+}  // namespace hived
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+struct hived_ctx {
+  hived::Engine e;
+};
+
+static std::string g_hived_create_error;
+
+extern "C" {
+
+const char* hived_create_error(void) { return g_hived_create_error.c_str(); }
+
+int hived_create(const char* spec_text, const hived_options_t* opt, hived_ctx** out) {
+  *out = nullptr;
+  auto ctx = std::make_unique<hived_ctx>();
+  int rc = ctx->e.create(spec_text, opt);
+  if (rc) { g_hived_create_error = ctx->e.err; return rc; }
+  *out = ctx.release();
+  return 0;
+}
+void hived_destroy(hived_ctx* ctx) { delete ctx; }
+const char* hived_last_error(hived_ctx* ctx) { return ctx->e.err.c_str(); }
+
+#define HIVED_TABLE(fn_num, fn_name, vec)                                                        \
+  int32_t fn_num(hived_ctx* ctx) { return (int32_t)ctx->e.T.vec.size(); }                         \
+  const char* fn_name(hived_ctx* ctx, int32_t id) {                                               \
+    return (id >= 0 && id < (int32_t)ctx->e.T.vec.size()) ? ctx->e.T.vec[id].c_str() : nullptr;   \
+  }
+HIVED_TABLE(hived_num_nodes, hived_node_name, nodeNames)
+HIVED_TABLE(hived_num_chains, hived_chain_name, chainNames)
+HIVED_TABLE(hived_num_vcs, hived_vc_name, vcNames)
+HIVED_TABLE(hived_num_leaf_types, hived_leaf_type_name, leafTypeNames)
+HIVED_TABLE(hived_num_pinned, hived_pinned_name, pinnedNames)
+HIVED_TABLE(hived_num_cell_types, hived_cell_type_name, cellTypeNames)
+#undef HIVED_TABLE
+int32_t hived_num_physical_cells(hived_ctx* ctx) { return ctx->e.T.NP; }
+int32_t hived_num_virtual_cells(hived_ctx* ctx) { return ctx->e.T.NV; }
+const char* hived_physical_cell_address(hived_ctx* ctx, int32_t c) { return (c >= 0 && c < ctx->e.T.NP) ? ctx->e.T.pAddr[c].c_str() : nullptr; }
+const char* hived_virtual_cell_address(hived_ctx* ctx, int32_t c) { return (c >= 0 && c < ctx->e.T.NV) ? ctx->e.T.vAddr[c].c_str() : nullptr; }
+
+int hived_vc_preassigned_cells(hived_ctx* ctx, int32_t vc, int32_t chain, int32_t level, int32_t* cells, int32_t cap, int32_t* n) {
+  const hived::FlatTopo& T = ctx->e.T;
+  *n = 0;
+  if (vc < 0 || vc >= T.nVCs || chain < 0 || chain >= T.nChains || level < 1 || level >= hived::MAXL) return HIVED_ERR_PLATFORM;
+  size_t k = ((size_t)vc * T.nChains + chain) * hived::MAXL + level;
+  for (int i = 0; i < T.pre_cnt[k]; i++) {
+    if (*n < cap) cells[*n] = T.pre_list[T.pre_off[k] + i];
+    (*n)++;
+  }
+  return 0;
+}
+
+static int hived_run_one(hived_ctx* ctx, const hived_event_t& ev, const uint32_t* sugg, const int32_t* aux, int64_t auxWords,
+                         hived_result_t* res, int32_t* pool, int64_t poolCap) {
+  hived::Engine& e = ctx->e;
+  hived_event_t copy = ev;
+  copy.suggested_off = sugg ? 0 : -1;
+  int rc = e.runBatch(&copy, 1, sugg, sugg ? e.dev.S.bitmapWords : 0, aux, auxWords, res, pool, poolCap);
+  if (rc) return rc;
+  if (res->error) {
+    char buf[96];
+    snprintf(buf, sizeof buf, "scheduler error %d (see HIVED_ERR_* in hived.h)", res->error);
+    e.err = buf;
+  }
+  return res->error;
+}
+
+int hived_set_node_health(hived_ctx* ctx, int32_t node, int32_t healthy) {
+  hived_event_t ev;
+  memset(&ev, 0, sizeof ev);
+  ev.type = HIVED_EV_NODE_HEALTH; ev.arg0 = node; ev.arg1 = healthy;
+  hived_result_t res; int32_t pool[4];
+  return hived_run_one(ctx, ev, nullptr, nullptr, 0, &res, pool, 4);
+}
+
+int hived_schedule(hived_ctx* ctx, const hived_pod_spec_t* spec, const uint32_t* suggested, int32_t phase, hived_result_t* res,
+                   int32_t* pool, int32_t pool_cap) {
+  hived_event_t ev;
+  memset(&ev, 0, sizeof ev);
+  ev.type = hived::Core::EV_SCHEDULE_ONLY; ev.phase = phase; ev.spec = *spec;
+  int rc = hived_run_one(ctx, ev, suggested, nullptr, 0, res, pool, pool_cap);
+  if (rc == 0) ctx->e.hash = hived_hash_result(ctx->e.hash, res, pool);
+  return rc;
+}
+
+int hived_add_allocated_pod(hived_ctx* ctx, const hived_pod_spec_t* spec, const hived_bind_info_t* info, const int32_t* leaves,
+                            int32_t pod_index) {
+  hived_event_t ev;
+  memset(&ev, 0, sizeof ev);
+  ev.type = hived::Core::EV_ADD_ALLOCATED; ev.arg0 = pod_index; ev.spec = *spec;
+  std::vector<int32_t> aux(sizeof(hived_bind_info_t) / 4 + 3 * (size_t)info->n_leaves);
+  memcpy(aux.data(), info, sizeof(hived_bind_info_t));
+  if (info->n_leaves > 0) memcpy(aux.data() + sizeof(hived_bind_info_t) / 4, leaves, 3 * (size_t)info->n_leaves * 4);
+  hived_result_t res; int32_t pool[4];
+  return hived_run_one(ctx, ev, nullptr, aux.data(), (int64_t)aux.size(), &res, pool, 4);
+}
+
+int hived_delete_allocated_pod(hived_ctx* ctx, int32_t group, int32_t leaf_num, int32_t pod_index) {
+  hived_event_t ev;
+  memset(&ev, 0, sizeof ev);
+  ev.type = HIVED_EV_DELETE_ALLOCATED; ev.arg0 = pod_index; ev.spec.group = group; ev.spec.leaf_num = leaf_num;
+  hived_result_t res; int32_t pool[4];
+  return hived_run_one(ctx, ev, nullptr, nullptr, 0, &res, pool, 4);
+}
+
+int hived_delete_unallocated_pod(hived_ctx* ctx, int32_t group, int32_t pod) {
+  hived_event_t ev;
+  memset(&ev, 0, sizeof ev);
+  ev.type = HIVED_EV_DELETE_UNALLOCATED; ev.spec.group = group; ev.spec.pod = pod;
+  hived_result_t res; int32_t pool[4];
+  return hived_run_one(ctx, ev, nullptr, nullptr, 0, &res, pool, 4);
+}
+
+int hived_process_events(hived_ctx* ctx, const hived_event_t* events, int32_t n, const uint32_t* suggested_pool,
+                         int64_t suggested_words, hived_result_t* res, int32_t* pool, int64_t pool_cap) {
+  hived::Engine& e = ctx->e;
+  int rc = e.runBatch(events, n, suggested_pool, suggested_words, nullptr, 0, res, pool, pool_cap);
+  if (rc) return rc;
+  for (int32_t i = 0; i < n; i++) {
+    if (events[i].type == HIVED_EV_SCHEDULE) e.hash = hived_hash_result(e.hash, &res[i], pool);
+    if (res[i].error == HIVED_ERR_CAPACITY) { e.err = "capacity exceeded (result pool or hived_options_t)"; return HIVED_ERR_CAPACITY; }
+  }
+  return 0;
+}
+
+int hived_get_group(hived_ctx* ctx, int32_t group, hived_group_info_t* out) {
+  memset(out, 0, sizeof *out);
+  hived::Engine& e = ctx->e;
+  if (group < 0 || group >= e.dev.S.maxGroups) return 0;
+  int32_t v[5];
+  hived::bk_d2h(&v[0], e.dev.g_state + group, 4);
+  if (v[0] == HIVED_GROUP_NONE) return 0;
+  hived::bk_d2h(&v[1], e.dev.g_vc + group, 4);
+  hived::bk_d2h(&v[2], e.dev.g_prio + group, 4);
+  hived::bk_d2h(&v[3], e.dev.g_flags + group, 4);
+  hived::bk_d2h(&v[4], e.dev.g_npre + group, 4);
+  out->state = v[0]; out->vc = v[1]; out->priority = v[2];
+  out->has_virtual = (v[3] & hived::GF_HAS_VIRTUAL) ? 1 : 0;
+  out->n_preempting_pods = v[0] == HIVED_GROUP_PREEMPTING ? v[4] : 0;
+  return 0;
+}
+
+int hived_snapshot_physical(hived_ctx* ctx, hived_cell_status_t* out, int32_t cap) {
+  hived::Engine& e = ctx->e;
+  int n = e.T.NP;
+  if (cap < n) return HIVED_ERR_CAPACITY;
+  std::vector<int32_t> prio, state, healthy, vcell, split, flpos;
+  e.readArray(e.dev.p_prio, prio, n); e.readArray(e.dev.p_state, state, n); e.readArray(e.dev.p_healthy, healthy, n);
+  e.readArray(e.dev.p_vcell, vcell, n); e.readArray(e.dev.p_split, split, n);
+  for (int i = 0; i < n; i++) {
+    out[i].priority = prio[i]; out[i].state = state[i]; out[i].healthy = healthy[i]; out[i].peer = vcell[i];
+    out[i].level = e.T.p_level[i]; out[i].chain = e.T.p_chain[i]; out[i].parent = e.T.p_parent[i];
+    // inFreeCellList (utils.go:381-391) on the snapshot
+    bool inFree;
+    int c = i;
+    while (true) {
+      if (vcell[c] >= 0 || split[c]) { inFree = false; break; }
+      int par = e.T.p_parent[c];
+      if (par < 0 || split[par]) { inFree = true; break; }
+      c = par;
+    }
+    out[i].flags = (split[i] ? 1 : 0) | ((e.T.p_flags[i] & hived::PF_PINNED) ? 2 : 0) | (inFree ? 4 : 0);
+  }
+  return 0;
+}
+
+int hived_snapshot_virtual(hived_ctx* ctx, hived_cell_status_t* out, int32_t cap) {
+  hived::Engine& e = ctx->e;
+  int n = e.T.NV;
+  if (cap < n) return HIVED_ERR_CAPACITY;
+  std::vector<int32_t> prio, state, healthy, pcell;
+  e.readArray(e.dev.v_prio, prio, n); e.readArray(e.dev.v_state, state, n); e.readArray(e.dev.v_healthy, healthy, n);
+  e.readArray(e.dev.v_pcell, pcell, n);
+  for (int i = 0; i < n; i++) {
+    out[i].priority = prio[i]; out[i].state = state[i]; out[i].healthy = healthy[i]; out[i].peer = pcell[i];
+    out[i].level = e.T.v_level[i]; out[i].chain = e.T.v_chain[i]; out[i].parent = e.T.v_parent[i];
+    out[i].flags = e.T.v_parent[i] < 0 ? 1 : 0;
+  }
+  return 0;
+}
+
+int hived_get_stats(hived_ctx* ctx, hived_stats_t* out) {
+  memset(out, 0, sizeof *out);
+  hived::Engine& e = ctx->e;
+  long long st[hived::ST_COUNT];
+  hived::bk_d2h(st, e.dev.stats, sizeof st);
+  out->schedule_events = st[hived::ST_SCHEDULE]; out->bind_results = st[hived::ST_BIND]; out->wait_results = st[hived::ST_WAIT];
+  out->preempt_results = st[hived::ST_PREEMPT]; out->view_nodes_scanned = st[hived::ST_VIEW_NODES];
+  out->leaves_committed = st[hived::ST_LEAVES]; out->free_cells_scanned = st[hived::ST_FREE_CELLS]; out->pods_placed = st[hived::ST_PODS];
+  long long K = __builtin_popcountll((unsigned long long)st[hived::ST_PRIO_MASK]);
+  if (K < 1) K = 1;
+  long long L = e.T.maxLevels;
+  out->algorithmic_bytes = st[hived::ST_VIEW_NODES] * (36 + 4 * K) + st[hived::ST_PODS] * 64 + st[hived::ST_FREE_CELLS] * 12 +
+                           st[hived::ST_LEAVES] * 16 * L * (1 + K);
+  return 0;
+}
+
+uint64_t hived_result_hash(hived_ctx* ctx) { return ctx->e.hash; }
+
+// ---- measurement hooks (include/hived_bench.h)
+int hived_bench_save_state(hived_ctx* ctx) { ctx->e.saveState(); return 0; }
+int hived_bench_restore_state(hived_ctx* ctx) { return ctx->e.restoreState(); }
+double hived_bench_last_kernel_ms(hived_ctx* ctx) { return ctx->e.lastKernelMs; }
+double hived_bench_total_kernel_ms(hived_ctx* ctx) { return ctx->e.kernelMsTotal; }
+int64_t hived_bench_kernel_launches(hived_ctx* ctx) { return ctx->e.kernelLaunches; }
+
+}  // extern "C"

@@ -1,0 +1,68 @@
+// Execution primitives of the device program.
+//
+// The scheduling program (hived_core.h) is written once against these primitives:
+//   * CUDA build (the product, sm_100a): one CTA; warp 0 is the "leader warp" that executes the
+//     sequential control flow warp-uniformly (all 32 lanes run the same scalar code; stores are
+//     done by lane 0 and ordered with __syncwarp), the other warps sleep in the hardware barrier
+//     until the leader posts a data-parallel operation (cluster-view pass) in shared memory.
+//   * HIVED_EMU build (tests/ only, never shipped or loaded by the package): a 1-thread, 1-lane
+//     instantiation of the same source on the host so the kernel LOGIC can be unit-tested in a
+//     container without a GPU.  It is not a fallback: the product library contains no host path.
+#pragma once
+#include <cstdint>
+
+#ifdef HIVED_EMU
+#define HIVED_DEV inline
+#define HIVED_DEV_NOINLINE
+#define HIVED_WARPSZ 1
+namespace hived {
+struct ExecShim {};
+inline int hv_lane() { return 0; }
+inline int hv_tid() { return 0; }
+inline int hv_nth() { return 1; }
+inline int hv_warp() { return 0; }
+inline int hv_nwarps() { return 1; }
+inline void hv_cta_sync() {}
+inline void hv_warp_sync() {}
+inline unsigned hv_ballot(bool p) { return p ? 1u : 0u; }
+inline unsigned hv_match(int) { return 1u; }
+inline unsigned hv_lanemask_lt() { return 0u; }
+inline int hv_popc(unsigned m) { return __builtin_popcount(m); }
+inline int hv_ffs(unsigned m) { return __builtin_ffs((int)m); }
+inline int hv_shfl(int v, int) { return v; }
+inline int hv_shfl_up(int v, int) { return v; }
+inline int hv_shfl_xor(int v, int) { return v; }
+inline int hv_atomic_min(int* a, int v) { int o = *a; if (v < o) *a = v; return o; }
+inline int hv_atomic_add(int* a, int v) { int o = *a; *a = o + v; return o; }
+}  // namespace hived
+#define HV_ST(ptr, val) (*(ptr) = (val))
+#else
+#define HIVED_DEV __device__ __forceinline__
+#define HIVED_DEV_NOINLINE __device__ __noinline__
+#define HIVED_WARPSZ 32
+namespace hived {
+__device__ __forceinline__ int hv_lane() { return threadIdx.x & 31; }
+__device__ __forceinline__ int hv_tid() { return threadIdx.x; }
+__device__ __forceinline__ int hv_nth() { return blockDim.x; }
+__device__ __forceinline__ int hv_warp() { return threadIdx.x >> 5; }
+__device__ __forceinline__ int hv_nwarps() { return blockDim.x >> 5; }
+__device__ __forceinline__ void hv_cta_sync() { __syncthreads(); }
+__device__ __forceinline__ void hv_warp_sync() { __syncwarp(); }
+__device__ __forceinline__ unsigned hv_ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
+__device__ __forceinline__ unsigned hv_match(int v) { return __match_any_sync(0xffffffffu, v); }
+__device__ __forceinline__ unsigned hv_lanemask_lt() { return (1u << (threadIdx.x & 31)) - 1u; }
+__device__ __forceinline__ int hv_popc(unsigned m) { return __popc(m); }
+__device__ __forceinline__ int hv_ffs(unsigned m) { return __ffs((int)m); }
+__device__ __forceinline__ int hv_shfl(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+__device__ __forceinline__ int hv_shfl_up(int v, int delta) { return __shfl_up_sync(0xffffffffu, v, delta); }
+__device__ __forceinline__ int hv_shfl_xor(int v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+__device__ __forceinline__ int hv_atomic_min(int* a, int v) { return atomicMin(a, v); }
+__device__ __forceinline__ int hv_atomic_add(int* a, int v) { return atomicAdd(a, v); }
+}  // namespace hived
+// leader-warp store: one lane writes, the warp is re-converged and the store ordered before later loads
+#define HV_ST(ptr, val)                      \
+  do {                                       \
+    if (hived::hv_lane() == 0) *(ptr) = (val); \
+    __syncwarp();                            \
+  } while (0)
+#endif

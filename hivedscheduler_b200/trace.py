@@ -1,0 +1,241 @@
+"""Seeded synthetic event traces of the benchmark configs and the batch driver.
+
+A trace is a numpy structured array with the exact memory layout of ``hived_event_t``
+(include/hived.h); it is generated up-front on the host and replayed identically by every
+implementation of the ABI (``hived_process_events``).  The generators are results-independent:
+the admission window only uses gang sizes, so the same trace is valid for oracle and product.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from collections import deque
+from typing import Any, Dict, List, Tuple
+
+import numpy as np
+
+from . import _cabi
+from .config import config_c1, config_c2, config_c3
+
+_SPEC_DT = np.dtype([
+    ("pod", "<i4"), ("group", "<i4"), ("vc", "<i4"), ("priority", "<i4"), ("pinned", "<i4"),
+    ("leaf_type", "<i4"), ("leaf_num", "<i4"), ("flags", "<i4"), ("n_members", "<i4"),
+    ("member_leaf_num", "<i4", (8,)), ("member_pod_num", "<i4", (8,))], align=True)
+EVENT_DT = np.dtype([("type", "<i4"), ("phase", "<i4"), ("arg0", "<i4"), ("arg1", "<i4"),
+                     ("suggested_off", "<i8"), ("spec", _SPEC_DT)], align=True)
+assert EVENT_DT.itemsize == C.sizeof(_cabi.Event), (EVENT_DT.itemsize, C.sizeof(_cabi.Event))
+
+RESULT_DT = np.dtype([
+    ("kind", "<i4"), ("error", "<i4"), ("wait_code", "<i4"), ("wait_cell", "<i4"), ("chain", "<i4"),
+    ("pod_index", "<i4"), ("node", "<i4"), ("this_off", "<i4"), ("this_n", "<i4"), ("n_members", "<i4"),
+    ("member_leaf_num", "<i4", (8,)), ("member_pod_num", "<i4", (8,)), ("leaf_off", "<i4"),
+    ("n_leaves", "<i4"), ("victim_off", "<i4"), ("n_victims", "<i4"), ("has_virtual", "<i4"),
+    ("reserved", "<i4")], align=True)
+assert RESULT_DT.itemsize == C.sizeof(_cabi.Result)
+
+MASK64 = (1 << 64) - 1
+
+
+class XorShift64Star:
+    """xorshift64* of SURVEY.md section 8d."""
+
+    def __init__(self, seed: int):
+        self.x = seed & MASK64
+        if self.x == 0:
+            self.x = 0x9E3779B97F4A7C15
+
+    def next(self) -> int:
+        x = self.x
+        x ^= x >> 12
+        x ^= (x << 25) & MASK64
+        x ^= x >> 27
+        self.x = x
+        return (x * 0x2545F4914F6CDD1D) & MASK64
+
+    def below(self, n: int) -> int:
+        return self.next() % n
+
+
+def seed_for(config_number: int) -> int:
+    return 0x9E3779B97F4A7C15 ^ config_number
+
+
+class TraceBuilder:
+    def __init__(self, capacity: int):
+        self.ev = np.zeros(capacity, dtype=EVENT_DT)
+        self.n = 0
+        self.decision = np.zeros(capacity, dtype=bool)  # True on the first pod of each gang
+        self.next_pod = 0
+
+    def _grow(self):
+        if self.n == len(self.ev):
+            self.ev = np.concatenate([self.ev, np.zeros(len(self.ev), dtype=EVENT_DT)])
+            self.decision = np.concatenate([self.decision, np.zeros(len(self.decision), dtype=bool)])
+
+    def schedule(self, group: int, vc: int, priority: int, leaf_type: int, leaf_num: int, pod_num: int,
+                 phase: int = _cabi.PHASE_PREEMPTING, flags: int = _cabi.SPEC_IGNORE_SUGGESTED,
+                 first: bool = True) -> int:
+        self._grow()
+        e = self.ev[self.n]
+        e["type"] = _cabi.EV_SCHEDULE
+        e["phase"] = phase
+        e["suggested_off"] = -1
+        s = e["spec"]
+        s["pod"] = self.next_pod
+        s["group"] = group
+        s["vc"] = vc
+        s["priority"] = priority
+        s["pinned"] = -1
+        s["leaf_type"] = leaf_type
+        s["leaf_num"] = leaf_num
+        s["flags"] = flags
+        s["n_members"] = 1
+        s["member_leaf_num"][0] = leaf_num
+        s["member_pod_num"][0] = pod_num
+        self.decision[self.n] = first
+        self.n += 1
+        self.next_pod += 1
+        return self.next_pod - 1
+
+    def delete_allocated(self, group: int, leaf_num: int, pod_index: int):
+        self._grow()
+        e = self.ev[self.n]
+        e["type"] = _cabi.EV_DELETE_ALLOCATED
+        e["arg0"] = pod_index
+        e["suggested_off"] = -1
+        e["spec"]["group"] = group
+        e["spec"]["leaf_num"] = leaf_num
+        self.n += 1
+
+    def node_health(self, node: int, healthy: bool):
+        self._grow()
+        e = self.ev[self.n]
+        e["type"] = _cabi.EV_NODE_HEALTH
+        e["arg0"] = node
+        e["arg1"] = 1 if healthy else 0
+        e["suggested_off"] = -1
+        self.n += 1
+
+    def finish(self) -> Tuple[np.ndarray, np.ndarray]:
+        return self.ev[:self.n].copy(), self.decision[:self.n].copy()
+
+
+def trace_c1() -> Dict[str, Any]:
+    """C1: 4 single-GPU pods (own group each), priority 0, typed K80; SURVEY.md section 8c."""
+    tb = TraceBuilder(8)
+    for i in range(4):
+        tb.schedule(group=i, vc=0, priority=0, leaf_type=0, leaf_num=1, pod_num=1)
+    ev, dec = tb.finish()
+    return {"name": "C1", "config": config_c1(), "events": ev, "decision": dec, "n_groups": 4, "n_pods": tb.next_pod,
+            "max_group_leaves": 8, "max_group_pods": 8}
+
+
+def trace_c2(n_pods: int = 10000) -> Dict[str, Any]:
+    """C2: 10 000 one-GPU single-pod groups, group i -> vc(i mod 4), no deletions."""
+    tb = TraceBuilder(n_pods)
+    for i in range(n_pods):
+        tb.schedule(group=i, vc=i % 4, priority=0, leaf_type=0, leaf_num=1, pod_num=1)
+    ev, dec = tb.finish()
+    return {"name": "C2", "config": config_c2(), "events": ev, "decision": dec, "n_groups": n_pods,
+            "n_pods": tb.next_pod, "max_group_leaves": 8, "max_group_pods": 8}
+
+
+def _gang_shape(r: int) -> Tuple[int, int]:
+    """40 % 1x1, 25 % 1x4, 25 % 1x8, 10 % 8x8 -> (pod_num, leaf_num); r uniform in [0,100)."""
+    if r < 40:
+        return 1, 1
+    if r < 65:
+        return 1, 4
+    if r < 90:
+        return 1, 8
+    return 8, 8
+
+
+def trace_c3(n_gangs: int = 100000, n_vcs: int = 8, vc_gpus: int = 7168, load: float = 0.9,
+             config_number: int = 3) -> Dict[str, Any]:
+    """C3: 100 000 mixed gangs on the 64k-GPU tree with the per-VC admission window."""
+    rng = XorShift64Star(seed_for(config_number))
+    tb = TraceBuilder(4 * n_gangs)
+    alive: List[deque] = [deque() for _ in range(n_vcs)]  # (group, pod_num, leaf_num)
+    alive_gpus = [0] * n_vcs
+    limit = int(load * vc_gpus)
+    for g in range(n_gangs):
+        pod_num, leaf_num = _gang_shape(rng.below(100))
+        v = rng.below(n_vcs)
+        size = pod_num * leaf_num
+        while alive_gpus[v] + size > limit and alive[v]:
+            og, opn, oln = alive[v].popleft()
+            for j in range(opn):
+                tb.delete_allocated(og, oln, j)
+            alive_gpus[v] -= opn * oln
+        for j in range(pod_num):
+            tb.schedule(group=g, vc=v, priority=0, leaf_type=0, leaf_num=leaf_num, pod_num=pod_num, first=(j == 0))
+        alive[v].append((g, pod_num, leaf_num))
+        alive_gpus[v] += size
+    ev, dec = tb.finish()
+    return {"name": "C%d" % config_number, "config": config_c3(), "events": ev, "decision": dec,
+            "n_groups": n_gangs, "n_pods": tb.next_pod, "max_group_leaves": 64, "max_group_pods": 8}
+
+
+# ------------------------------------------------------------------------------------------------
+# batch driver
+# ------------------------------------------------------------------------------------------------
+
+class BatchContext:
+    """A raw ctx of include/hived.h for the batch path (bench.py, parity tests)."""
+
+    def __init__(self, lib, config: Dict[str, Any], max_groups: int, max_pods: int, max_group_leaves: int = 64,
+                 max_group_pods: int = 8, device: int = 0):
+        from .config import to_spec_text
+        self.lib = lib
+        self.opt = _cabi.Options(max_groups=max_groups, max_pods=max_pods, max_group_leaves=max_group_leaves,
+                                 max_group_pods=max_group_pods, device=device)
+        self.ctx = C.c_void_p()
+        rc = lib.hived_create(to_spec_text(config).encode(), C.byref(self.opt), C.byref(self.ctx))
+        if rc != 0:
+            raise RuntimeError("hived_create failed (%d): %s" % (rc, (lib.hived_create_error() or b"").decode()))
+        self.n_nodes = lib.hived_num_nodes(self.ctx)
+
+    def set_all_nodes_healthy(self):
+        """Healthy nodes arrive in ascending node id (= name) order."""
+        ev = np.zeros(self.n_nodes, dtype=EVENT_DT)
+        ev["type"] = _cabi.EV_NODE_HEALTH
+        ev["arg0"] = np.arange(self.n_nodes, dtype=np.int32)
+        ev["arg1"] = 1
+        ev["suggested_off"] = -1
+        self.process(ev, pool_words=16)
+
+    def process(self, events: np.ndarray, pool_words: int = None):
+        n = len(events)
+        if pool_words is None:
+            pool_words = 3 * 64 * n // 4 + 4096
+        res = np.zeros(n, dtype=RESULT_DT)
+        pool = np.zeros(pool_words, dtype=np.int32)
+        events = np.ascontiguousarray(events)
+        rc = self.lib.hived_process_events(
+            self.ctx, events.ctypes.data_as(C.POINTER(_cabi.Event)), n, None, 0,
+            res.ctypes.data_as(C.POINTER(_cabi.Result)), pool.ctypes.data_as(C.POINTER(C.c_int32)), pool_words)
+        if rc != 0:
+            raise RuntimeError("hived_process_events failed (%d): %s" % (
+                rc, (self.lib.hived_last_error(self.ctx) or b"").decode()))
+        return res, pool
+
+    def result_hash(self) -> int:
+        return int(self.lib.hived_result_hash(self.ctx))
+
+    def stats(self) -> Dict[str, int]:
+        st = _cabi.Stats()
+        self.lib.hived_get_stats(self.ctx, C.byref(st))
+        return {f: getattr(st, f) for f, _ in _cabi.Stats._fields_}
+
+    def close(self):
+        if self.ctx:
+            self.lib.hived_destroy(self.ctx)
+            self.ctx = None
+
+
+def pool_words_for(trace: Dict[str, Any]) -> int:
+    """Upper bound of result-pool words: every SCHEDULE event may emit the whole gang placement."""
+    ev = trace["events"]
+    sched = ev[ev["type"] == _cabi.EV_SCHEDULE]["spec"]
+    leaves = (sched["member_leaf_num"][:, 0].astype(np.int64) * sched["member_pod_num"][:, 0]).sum()
+    return int(3 * leaves + 4096)

@@ -32,3 +32,38 @@ def cuda_lib():
     """The product library; GPU tests fail loudly if it is missing or no device is present."""
     from hivedscheduler_b200 import _cabi
     return _cabi.load_cuda_library()
+
+
+EMU_LIB = os.path.join(ROOT, "tests", "_build", "libhived_emu.so")
+
+
+@pytest.fixture(scope="session")
+def emu_lib():
+    """Host emulation of the DEVICE PROGRAM (1-thread CTA) — test-only, validates kernel logic on CPU."""
+    from hivedscheduler_b200 import _cabi
+    os.makedirs(os.path.dirname(EMU_LIB), exist_ok=True)
+    src = os.path.join(ROOT, "tests", "emu", "hived_emu.cpp")
+    deps = [src] + [os.path.join(ROOT, "hivedscheduler_b200", "csrc", f)
+                    for f in os.listdir(os.path.join(ROOT, "hivedscheduler_b200", "csrc")) if f.endswith((".h", ".hpp"))]
+    if not os.path.exists(EMU_LIB) or any(os.path.getmtime(d) > os.path.getmtime(EMU_LIB) for d in deps):
+        subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-o", EMU_LIB, src])
+    return _cabi.load_library(EMU_LIB)
+
+
+def run_trace(lib, t, n_events=None, chunks=1, device=0):
+    """Replay a trace on a library; returns (hash, results, pool, stats)."""
+    import numpy as np
+    from hivedscheduler_b200 import trace
+    bc = trace.BatchContext(lib, t["config"], t["n_groups"], t["n_pods"], t["max_group_leaves"], t["max_group_pods"],
+                            device=device)
+    bc.set_all_nodes_healthy()
+    ev = t["events"] if n_events is None else t["events"][:n_events]
+    bounds = [len(ev) * (i + 1) // chunks for i in range(chunks)]
+    start, all_res = 0, []
+    for b in bounds:
+        res, pool = bc.process(ev[start:b], 3 * 64 * (b - start) + 4096)
+        all_res.append((res, pool))
+        start = b
+    out = (bc.result_hash(), all_res, bc.stats())
+    bc.close()
+    return out
