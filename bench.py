@@ -1,0 +1,272 @@
+#!/usr/bin/env python
+"""bench.py — scheduling decisions/sec of the HiveD hot path on the BASELINE workload (C3).
+
+A "step" is one pass of the hot path over the whole synthetic C3 trace (64k-GPU, 5-level cell tree,
+8 VCs, 100 000 mixed gangs = 332 954 ordered events) starting from the same
+cluster state.  ``value`` times the kernel with the batch already resident in HBM; ``e2e`` times the
+reference-facing C-ABI call ``hived_process_events`` with pinned HOST buffers (H2D of the events and D2H
+of the results inside the timed region).  ``--impl reference`` times the reference's own CPU algorithm
+(the oracle: a faithful C++ restatement of the Go path; Go itself is not available in this image).
+
+One JSON line is printed by rank 0.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from hivedscheduler_b200 import _cabi, trace  # noqa: E402
+
+METRIC = "scheduling decisions/sec on 64k-GPU cell tree, 100k pending gangs"
+WORKLOAD = "C3: 8192 nodes x 8 GPU (65536 GPUs), 5-level tree, 8 VCs, 100000 mixed gangs (1/4/8/64-GPU), admission window 0.9"
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, device: int):
+        super().__init__(daemon=True)
+        self.device = device
+        self.samples = []
+        self.stop_flag = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.check_output(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + q,
+                                               "--format=csv,noheader,nounits"], timeout=5).decode().strip()
+                self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        mx = max(int(s[1]) for s in self.samples if s[1].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons, "samples": len(self.samples)}
+
+
+def bind_bench_hooks(lib):
+    P = C.c_void_p
+    for name, res, args in [
+        ("hived_bench_save_state", C.c_int, [P]), ("hived_bench_restore_state", C.c_int, [P]),
+        ("hived_bench_stage_events", C.c_int, [P, C.POINTER(_cabi.Event), C.c_int32, C.c_int64]),
+        ("hived_bench_run_staged", C.c_int, [P]),
+        ("hived_bench_fetch_results", C.c_int, [P, C.POINTER(_cabi.Result), C.POINTER(C.c_int32), C.c_int64, C.POINTER(C.c_int64)]),
+        ("hived_bench_flush_l2", C.c_int, [P]), ("hived_bench_last_kernel_ms", C.c_double, [P]),
+        ("hived_bench_total_kernel_ms", C.c_double, [P]), ("hived_bench_kernel_launches", C.c_int64, [P])]:
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def cpu_baseline(t, n_decisions: int, chunk_start: int = 0, ctx_holder=None):
+    """The reference's CPU algorithm (oracle port) on a bounded sample of the same trace."""
+    import __graft_entry__ as g
+    lib = _cabi.load_library(g.build_oracle())
+    if ctx_holder is None or "bc" not in ctx_holder:
+        bc = trace.BatchContext(lib, t["config"], t["n_groups"], t["n_pods"], t["max_group_leaves"], t["max_group_pods"])
+        bc.set_all_nodes_healthy()
+        if ctx_holder is not None:
+            ctx_holder["bc"] = bc
+    else:
+        bc = ctx_holder["bc"]
+    dec = np.flatnonzero(t["decision"])
+    lo = 0 if chunk_start == 0 else int(dec[chunk_start])
+    hi = int(dec[chunk_start + n_decisions]) if chunk_start + n_decisions < len(dec) else len(t["events"])
+    ev = t["events"][lo:hi]
+    t0 = time.perf_counter()
+    bc.process(ev, 3 * 64 * len(ev) + 4096)
+    dt = time.perf_counter() - t0
+    return n_decisions / dt, dt, len(ev)
+
+
+def run_reference_arm(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    t = trace.trace_c3()
+    holder = {}
+    sample = 400  # decisions per step: ~4 s of single-core work each
+    for i in range(args.warmup):
+        cpu_baseline(t, sample, i * sample, holder)
+    t0 = time.perf_counter()
+    done = 0
+    for i in range(args.steps):
+        cpu_baseline(t, sample, (args.warmup + i) * sample, holder)
+        done += sample
+    dt = time.perf_counter() - t0
+    value = done / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "decisions/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": "%d consecutive decisions of the C3 trace per step" % sample},
+        "cpu_baseline": {"value": value, "unit": "decisions/s", "cores": 1, "kind": "port",
+                         "sample": "consecutive %d-decision windows of the C3 trace (whole-trace oracle run: 88 decisions/s, "
+                                   "tests/golden/trace_hashes.json); the algorithm is serialised by one lock in the reference "
+                                   "(hived_algorithm.go:185), so 1 core" % sample},
+        "e2e": {"value": value, "unit": "decisions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--gangs", type=int, default=100000, help="C3 trace length (BASELINE: 100000)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    rank, world, local = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = _cabi.load_cuda_library()
+    bind_bench_hooks(lib)
+
+    t = trace.trace_c3(n_gangs=args.gangs)
+    ev = t["events"]
+    n_dec = int(t["decision"].sum())
+    pool_words = trace.pool_words_for(t)
+    bc = trace.BatchContext(lib, t["config"], t["n_groups"], t["n_pods"], t["max_group_leaves"], t["max_group_pods"], device=local)
+    bc.set_all_nodes_healthy()
+    ctx = bc.ctx
+    lib.hived_bench_save_state(ctx)
+
+    # pinned host buffers for the e2e leg
+    ev_pinned = torch.empty(ev.nbytes, dtype=torch.uint8, pin_memory=True)
+    ev_pinned.numpy()[:] = ev.view(np.uint8)
+    res_pinned = torch.empty(len(ev) * C.sizeof(_cabi.Result), dtype=torch.uint8, pin_memory=True)
+    pool_pinned = torch.empty(pool_words, dtype=torch.int32, pin_memory=True)
+    ev_ptr = C.cast(ev_pinned.data_ptr(), C.POINTER(_cabi.Event))
+    res_ptr = C.cast(res_pinned.data_ptr(), C.POINTER(_cabi.Result))
+    pool_ptr = C.cast(pool_pinned.data_ptr(), C.POINTER(C.c_int32))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        lib.hived_bench_restore_state(ctx)
+        lib.hived_bench_flush_l2(ctx)
+        rc = lib.hived_bench_run_staged(ctx)
+        assert rc == 0, rc
+        return lib.hived_bench_last_kernel_ms(ctx)
+
+    def step_e2e():
+        lib.hived_bench_restore_state(ctx)
+        lib.hived_bench_flush_l2(ctx)
+        t0 = time.perf_counter()
+        rc = lib.hived_process_events(ctx, ev_ptr, len(ev), None, 0, res_ptr, pool_ptr, pool_words)
+        assert rc == 0, rc
+        return time.perf_counter() - t0
+
+    # ---- resident leg (value)
+    lib.hived_bench_stage_events(ctx, ev_ptr, len(ev), pool_words)
+    for _ in range(args.warmup):
+        step_resident()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = lib.hived_bench_kernel_launches(ctx)
+    barrier()
+    t0 = time.perf_counter()
+    kernel_ms = [step_resident() for _ in range(args.steps)]
+    barrier()
+    wall = time.perf_counter() - t0
+    launches = lib.hived_bench_kernel_launches(ctx) - launches0
+    # parity witness: the hash of the last step's results
+    used = C.c_int64()
+    lib.hived_bench_fetch_results(ctx, res_ptr, pool_ptr, pool_words, C.byref(used))
+    stats = bc.stats()
+    # the restore + L2 flush between steps are not part of a step: time = sum of the kernels' CUDA-event times
+    kernel_total_s = sum(kernel_ms) / 1e3
+    # ---- e2e leg
+    for _ in range(min(args.warmup, 2)):
+        step_e2e()
+    e2e_times = [step_e2e() for _ in range(args.steps)]
+    sampler.stop_flag.set()
+    sampler.join(timeout=2)
+    e2e_s = sum(e2e_times)
+
+    times = torch.tensor([kernel_total_s, e2e_s, wall], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    kernel_total_s, e2e_s, wall = [float(x) for x in times.tolist()]
+    value = world * n_dec * args.steps / kernel_total_s
+    e2e_value = world * n_dec * args.steps / e2e_s
+    peak, peak_src = measured_peak_gbs()
+    # the device-side work counters are rewound with the state, so they describe ONE pass of the trace
+    alg_bytes = stats["algorithmic_bytes"]
+    achieved = alg_bytes / (kernel_total_s / args.steps) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": "decisions/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * kernel_total_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "events_per_step": int(len(ev)), "decisions_per_step": n_dec,
+                   "parallelism": "replicas" if world > 1 else "1 GPU", "l2": "flushed between steps (256 MiB memset)",
+                   "timing": "CUDA events on the launch stream around the kernel; max over ranks",
+                   "wall_ms_per_step_incl_state_rewind": 1e3 * wall / args.steps},
+        "e2e": {"value": e2e_value, "unit": "decisions/s", "h2d_bytes_per_step": int(ev.nbytes),
+                "d2h_bytes_per_step": int(len(ev) * C.sizeof(_cabi.Result) + 4 * used.value)},
+        "gpu_launches": int(launches),
+        "clocks": sampler.summary(),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src,
+                     "note": "latency-bound sequential contract: state (~8 MB) is L2/L1 resident; see DESIGN.md"},
+    }
+    if rank == 0:
+        if not args.no_cpu_baseline and world == 1:
+            v, dt, nev = cpu_baseline(t, 1500)
+            line["cpu_baseline"] = {"value": v, "unit": "decisions/s", "cores": 1, "kind": "port",
+                                    "sample": "first 1500 decisions (%d events) of the same C3 trace, %.1f s" % (nev, dt)}
+        line["parity"] = {"result_hash": "%016x" % bc.result_hash()}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

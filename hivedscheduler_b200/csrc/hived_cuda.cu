@@ -51,6 +51,15 @@ void bk_h2d(void* dst, const void* src, size_t bytes) { cudaMemcpy(dst, src, byt
 void bk_d2h(void* dst, const void* src, size_t bytes) { cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost); }
 void bk_d2d(void* dst, const void* src, size_t bytes) { cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToDevice); }
 
+void bk_flush_l2() {
+  static void* buf = nullptr;
+  const size_t bytes = 256u << 20;  // > 126 MB of L2
+  if (!buf && cudaMalloc(&buf, bytes) != cudaSuccess) return;
+  static int v = 0;
+  cudaMemset(buf, ++v & 0xff, bytes);
+  cudaDeviceSynchronize();
+}
+
 int bk_init(int device, std::string& err) {
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);

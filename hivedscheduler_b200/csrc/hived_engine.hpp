@@ -29,6 +29,7 @@ void bk_d2d(void* dst, const void* src, size_t bytes);
 int bk_init(int device, std::string& err);
 // runs the program over n staged events; returns 0 or a HIVED_ERR_* code
 int launchProgram(Engine& e, int n, bool withInit);
+void bk_flush_l2();
 
 struct Buf {
   void* p = nullptr;
@@ -176,6 +177,21 @@ struct Engine {
   }
   bool hasSugg = false, hasAux = false;
   int64_t poolCapWords = 0;
+  int stagedN = 0;
+  int stage(const hived_event_t* events, int n, int64_t poolCap) {
+    dEvents.ensure((size_t)(n > 0 ? n : 1) * sizeof(hived_event_t));
+    dResults.ensure((size_t)(n > 0 ? n : 1) * sizeof(hived_result_t));
+    dPool.ensure((size_t)(poolCap > 0 ? poolCap : 1) * 4);
+    if (n > 0) bk_h2d(dEvents.p, events, (size_t)n * sizeof(hived_event_t));
+    hasSugg = false; hasAux = false;
+    poolCapWords = poolCap;
+    stagedN = n;
+    return 0;
+  }
+  int runStaged() {
+    poolOff = 0;
+    return launchProgram(*this, stagedN, false);
+  }
 
   void readArray(const int32_t* devPtr, std::vector<int32_t>& out, size_t count) {
     out.resize(count ? count : 1);
@@ -401,6 +417,17 @@ uint64_t hived_result_hash(hived_ctx* ctx) { return ctx->e.hash; }
 // ---- measurement hooks (include/hived_bench.h)
 int hived_bench_save_state(hived_ctx* ctx) { ctx->e.saveState(); return 0; }
 int hived_bench_restore_state(hived_ctx* ctx) { return ctx->e.restoreState(); }
+int hived_bench_stage_events(hived_ctx* ctx, const hived_event_t* events, int32_t n, int64_t pool_cap) { return ctx->e.stage(events, n, pool_cap); }
+int hived_bench_run_staged(hived_ctx* ctx) { return ctx->e.runStaged(); }
+int hived_bench_fetch_results(hived_ctx* ctx, hived_result_t* res, int32_t* pool, int64_t pool_cap, int64_t* pool_used) {
+  hived::Engine& e = ctx->e;
+  if (e.poolOff > pool_cap) return HIVED_ERR_CAPACITY;
+  hived::bk_d2h(res, e.dResults.p, (size_t)e.stagedN * sizeof(hived_result_t));
+  if (e.poolOff > 0) hived::bk_d2h(pool, e.dPool.p, (size_t)e.poolOff * 4);
+  *pool_used = e.poolOff;
+  return 0;
+}
+int hived_bench_flush_l2(hived_ctx*) { hived::bk_flush_l2(); return 0; }
 double hived_bench_last_kernel_ms(hived_ctx* ctx) { return ctx->e.lastKernelMs; }
 double hived_bench_total_kernel_ms(hived_ctx* ctx) { return ctx->e.kernelMsTotal; }
 int64_t hived_bench_kernel_launches(hived_ctx* ctx) { return ctx->e.kernelLaunches; }

@@ -68,7 +68,9 @@ class TraceBuilder:
 
     def _grow(self):
         if self.n == len(self.ev):
-            self.ev = np.concatenate([self.ev, np.zeros(len(self.ev), dtype=EVENT_DT)])
+            grown = np.zeros(2 * len(self.ev), dtype=EVENT_DT)
+            grown.view(np.uint8)[:self.ev.nbytes] = self.ev.view(np.uint8)
+            self.ev = grown
             self.decision = np.concatenate([self.decision, np.zeros(len(self.decision), dtype=bool)])
 
     def schedule(self, group: int, vc: int, priority: int, leaf_type: int, leaf_num: int, pod_num: int,
@@ -116,7 +118,10 @@ class TraceBuilder:
         self.n += 1
 
     def finish(self) -> Tuple[np.ndarray, np.ndarray]:
-        return self.ev[:self.n].copy(), self.decision[:self.n].copy()
+        # byte-wise copy: numpy's structured copy leaves the alignment padding uninitialised
+        out = np.zeros(self.n, dtype=EVENT_DT)
+        out.view(np.uint8)[:] = self.ev[:self.n].view(np.uint8)
+        return out, self.decision[:self.n].copy()
 
 
 def trace_c1() -> Dict[str, Any]:

@@ -1,0 +1,22 @@
+/* hived_bench.h — measurement hooks exported by libhived_cuda.so next to the ABI of hived.h.
+ * They exist so that bench.py can (a) time the kernel with the batch already resident in HBM and
+ * (b) rewind the scheduler state between timed steps.  Not part of the reference-facing surface. */
+#ifndef HIVED_BENCH_H_
+#define HIVED_BENCH_H_
+#include "hived.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+int hived_bench_save_state(hived_ctx*);     /* device-to-device copy of every mutable array */
+int hived_bench_restore_state(hived_ctx*);
+int hived_bench_stage_events(hived_ctx*, const hived_event_t* events, int32_t n, int64_t pool_cap); /* H2D once */
+int hived_bench_run_staged(hived_ctx*);     /* one kernel launch over the staged batch; nothing crosses PCIe */
+int hived_bench_fetch_results(hived_ctx*, hived_result_t* res, int32_t* pool, int64_t pool_cap, int64_t* pool_used);
+int hived_bench_flush_l2(hived_ctx*);       /* overwrite a buffer larger than L2 */
+double hived_bench_last_kernel_ms(hived_ctx*);   /* CUDA-event time of the last launch, on its stream */
+double hived_bench_total_kernel_ms(hived_ctx*);
+int64_t hived_bench_kernel_launches(hived_ctx*);
+#ifdef __cplusplus
+}
+#endif
+#endif

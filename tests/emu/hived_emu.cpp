@@ -16,6 +16,7 @@ void bk_h2d(void* dst, const void* src, size_t bytes) { memcpy(dst, src, bytes);
 void bk_d2h(void* dst, const void* src, size_t bytes) { memcpy(dst, src, bytes); }
 void bk_d2d(void* dst, const void* src, size_t bytes) { memcpy(dst, src, bytes); }
 int bk_init(int, std::string&) { return 0; }
+void bk_flush_l2() {}
 int launchProgram(Engine& e, int n, bool withInit) {
   static Sm sm;
   memset(&sm, 0, sizeof sm);
