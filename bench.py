@@ -78,7 +78,8 @@ def bind_bench_hooks(lib):
         ("hived_bench_stage_events", C.c_int, [P, C.POINTER(_cabi.Event), C.c_int32, C.c_int64]),
         ("hived_bench_run_staged", C.c_int, [P]),
         ("hived_bench_fetch_results", C.c_int, [P, C.POINTER(_cabi.Result), C.POINTER(C.c_int32), C.c_int64, C.POINTER(C.c_int64)]),
-        ("hived_bench_flush_l2", C.c_int, [P]), ("hived_bench_last_kernel_ms", C.c_double, [P]),
+        ("hived_bench_flush_l2", C.c_int, [P]), ("hived_bench_phase_cycles", C.c_int, [P, C.POINTER(C.c_int64)]),
+        ("hived_bench_last_kernel_ms", C.c_double, [P]),
         ("hived_bench_total_kernel_ms", C.c_double, [P]), ("hived_bench_kernel_launches", C.c_int64, [P])]:
         fn = getattr(lib, name)
         fn.restype = res
@@ -221,6 +222,8 @@ def main():
     used = C.c_int64()
     lib.hived_bench_fetch_results(ctx, res_ptr, pool_ptr, pool_words, C.byref(used))
     stats = bc.stats()
+    cyc = (C.c_int64 * 7)()
+    lib.hived_bench_phase_cycles(ctx, cyc)
     # the restore + L2 flush between steps are not part of a step: time = sum of the kernels' CUDA-event times
     kernel_total_s = sum(kernel_ms) / 1e3
     # ---- e2e leg
@@ -263,6 +266,8 @@ def main():
             line["cpu_baseline"] = {"value": v, "unit": "decisions/s", "cores": 1, "kind": "port",
                                     "sample": "first 1500 decisions (%d events) of the same C3 trace, %.1f s" % (nev, dt)}
         line["parity"] = {"result_hash": "%016x" % bc.result_hash()}
+        names = ["view_pass", "leaf_search", "map_v2p", "emit_result", "commit", "delete", "all_events"]
+        line["phase_cycles_per_step"] = {n: int(c) for n, c in zip(names, cyc)}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -849,11 +849,14 @@ struct Core {
     for (int m = 0; m < nmem; m++)
       for (int i = 0; i < memPods[m]; i++) { HV_ST(&d.pod_need[npods], memLeaf[m]); npods++; }
     int priority = OPP_PRIO;
+    long long tc0 = hv_clock();
     bool ok = runViewPass(sched, priority, ignoreSuggested, npods, reason, rcell);
     if (!ok && p > OPP_PRIO) {
       priority = p;
       ok = runViewPass(sched, priority, ignoreSuggested, npods, reason, rcell);
     }
+    long long tc1 = hv_clock();
+    stat_add(ST_CYC_VIEW, tc1 - tc0);
     if (!ok) return false;
     stat_add(ST_PODS, npods);
     const bool isVirtual = d.s_virtual[sched] != 0;
@@ -872,6 +875,7 @@ struct Core {
       if (sm->panic) return false;
       outOff += need;
     }
+    stat_add(ST_CYC_LEAF, hv_clock() - tc1);
     reason = 0;
     rcell = -1;
     return true;
@@ -1424,11 +1428,14 @@ struct Core {
       reason |= HIVED_WAIT_SCOPE_VC;
       return false;
     }
+    long long tm0 = hv_clock();
     tryLazyPreempt(d.pl_v, r.nleaves);
     if (sm->panic) return false;
     toBindingPaths(d.pl_v, r.nleaves);
     if (sm->panic) return false;
-    if (mapVirtualPlacementToPhysical(r.chain, r.ignoreSuggested)) {
+    bool mapped = mapVirtualPlacementToPhysical(r.chain, r.ignoreSuggested);
+    stat_add(ST_CYC_MAP, hv_clock() - tm0);
+    if (mapped) {
       for (int i = 0; i < r.nleaves; i++) HV_ST(&d.pl_p[i], d.binding[d.pl_v[i]]);  // toPhysicalPlacement types.go:260-280
       reason = 0; rcell = -1;
       return true;
@@ -1886,7 +1893,9 @@ struct Core {
       stat_add(ST_PREEMPT, 1);
       return 0;
     }
+    long long te0 = hv_clock();
     emitBind(res, nmem, memLeaf, memPods, phys, virt, hasVirtual, sp.leaf_num, podIndex);
+    stat_add(ST_CYC_EMIT, hv_clock() - te0);
     stat_add(ST_BIND, 1);
     return sm->panic;
   }
@@ -1896,6 +1905,7 @@ struct Core {
   // ======================================================================================
   HIVED_DEV_NOINLINE void processEvent(const hived_event_t& ev, hived_result_t* res, const uint32_t* suggPool, const int32_t* aux) {
     HV_ST(&sm->panic, 0);
+    long long tev0 = hv_clock();
     // clearResult
     {
       int32_t* w = reinterpret_cast<int32_t*>(res);
@@ -1916,7 +1926,9 @@ struct Core {
         b.n_members = res->n_members; b.member_leaf_num = res->member_leaf_num; b.member_pod_num = res->member_pod_num;
         b.leaves = pool + res->leaf_off;
         sugg = nullptr;
+        long long ta0 = hv_clock();
         addAllocatedPod(sp, b, getAllocatedPodIndex(b, sp.leaf_num));
+        stat_add(ST_CYC_COMMIT, hv_clock() - ta0);
         rc = sm->panic;
       }
     } else if (type == EV_ADD_ALLOCATED) {
@@ -1928,7 +1940,9 @@ struct Core {
       rc = validateSpec(ev.spec);
       if (rc == 0) { addAllocatedPod(ev.spec, b, ev.arg0); rc = sm->panic; }
     } else if (type == HIVED_EV_DELETE_ALLOCATED) {
+      long long td0 = hv_clock();
       deleteAllocatedPod(ev.spec.group, ev.spec.leaf_num, ev.arg0);
+      stat_add(ST_CYC_DELETE, hv_clock() - td0);
       rc = sm->panic;
     } else if (type == HIVED_EV_DELETE_UNALLOCATED) {
       deleteUnallocatedPod(ev.spec.group, ev.spec.pod);
@@ -1940,6 +1954,7 @@ struct Core {
       rc = HIVED_ERR_PLATFORM;
     }
     HV_ST(&res->error, rc);
+    stat_add(ST_CYC_TOTAL, hv_clock() - tev0);
   }
   static constexpr int EV_SCHEDULE_ONLY = 16, EV_ADD_ALLOCATED = 17, EV_INIT = 18;
 

@@ -71,7 +71,10 @@ struct Dev {
 
 enum {
   ST_VIEW_NODES = 0, ST_LEAVES = 1, ST_FREE_CELLS = 2, ST_PODS = 3, ST_SCHEDULE = 4, ST_BIND = 5, ST_WAIT = 6,
-  ST_PREEMPT = 7, ST_PRIO_MASK = 8 /* bit (p+1) for small priorities, else bit 63 */, ST_COUNT = 16
+  ST_PREEMPT = 7, ST_PRIO_MASK = 8 /* bit (p+1) for small priorities, else bit 63 */,
+  /* SM cycles spent per phase (leader warp), for profiles/ */
+  ST_CYC_VIEW = 9, ST_CYC_LEAF = 10, ST_CYC_MAP = 11, ST_CYC_EMIT = 12, ST_CYC_COMMIT = 13, ST_CYC_DELETE = 14, ST_CYC_TOTAL = 15,
+  ST_COUNT = 16
 };
 
 // group flags

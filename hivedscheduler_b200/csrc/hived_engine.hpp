@@ -428,6 +428,13 @@ int hived_bench_fetch_results(hived_ctx* ctx, hived_result_t* res, int32_t* pool
   return 0;
 }
 int hived_bench_flush_l2(hived_ctx*) { hived::bk_flush_l2(); return 0; }
+/* out[0..7): SM cycles in view pass, leaf search, mapping, result emission, commit, delete, all events */
+int hived_bench_phase_cycles(hived_ctx* ctx, int64_t* out) {
+  long long st[hived::ST_COUNT];
+  hived::bk_d2h(st, ctx->e.dev.stats, sizeof st);
+  for (int i = 0; i < 7; i++) out[i] = st[hived::ST_CYC_VIEW + i];
+  return 0;
+}
 double hived_bench_last_kernel_ms(hived_ctx* ctx) { return ctx->e.lastKernelMs; }
 double hived_bench_total_kernel_ms(hived_ctx* ctx) { return ctx->e.kernelMsTotal; }
 int64_t hived_bench_kernel_launches(hived_ctx* ctx) { return ctx->e.kernelLaunches; }

@@ -34,6 +34,7 @@ inline int hv_shfl_up(int v, int) { return v; }
 inline int hv_shfl_xor(int v, int) { return v; }
 inline int hv_atomic_min(int* a, int v) { int o = *a; if (v < o) *a = v; return o; }
 inline int hv_atomic_add(int* a, int v) { int o = *a; *a = o + v; return o; }
+inline long long hv_clock() { return 0; }
 }  // namespace hived
 #define HV_ST(ptr, val) (*(ptr) = (val))
 #else
@@ -58,6 +59,7 @@ __device__ __forceinline__ int hv_shfl_up(int v, int delta) { return __shfl_up_s
 __device__ __forceinline__ int hv_shfl_xor(int v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 __device__ __forceinline__ int hv_atomic_min(int* a, int v) { return atomicMin(a, v); }
 __device__ __forceinline__ int hv_atomic_add(int* a, int v) { return atomicAdd(a, v); }
+__device__ __forceinline__ long long hv_clock() { return clock64(); }
 }  // namespace hived
 // leader-warp store: one lane writes, the warp is re-converged and the store ordered before later loads
 #define HV_ST(ptr, val)                      \
