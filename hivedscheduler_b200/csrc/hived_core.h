@@ -3,14 +3,18 @@
 // behaviour of the reference's pkg/algorithm (HivedAlgorithm.Schedule -> intra-VC topology-aware
 // search -> buddy-cell virtual->physical mapping -> commit) — each function cites the reference
 // lines whose observable behaviour it reproduces.  This is a re-design, not a translation:
-//   * cells are ids into SoA arrays; children / leaves of a cell are contiguous id ranges;
+//   * cells are ids into SoA arrays; children / leaves of a cell are contiguous id ranges and every
+//     cell carries its ancestor per level, so a leaf-to-root walk is ONE warp-wide gather
+//     (lane = level) instead of a chain of dependent loads;
 //   * per-priority used-leaf maps are not stored: used[q](cell) == #leaves below it with priority q,
 //     so a cluster-view node's sort key is recomputed from its leaf priorities with coalesced loads;
 //   * free / bad-free / doomed lists keep the reference's order semantics (append, swap-remove) but
 //     carry a position index per cell, so contains/remove are O(1) instead of linear scans;
 //   * findPhysicalLeafCell's scan over all leaves is a (node, chain) -> leaves table lookup;
-//   * the cluster-view pass (key computation, stable sort, greedy first-fit) is data-parallel over
-//     the whole CTA; everything else is warp-uniform control flow on the leader warp.
+//   * the cluster-view pass (key computation, stable counting sort, greedy first-fit) is
+//     data-parallel over the whole CTA; the rest runs on the leader warp as SIMT code: uniform
+//     control flow, with lanes spread over tree levels, over the children of a cell, over the
+//     candidates of a free list and over the leaf cells of a gang.
 #pragma once
 #include "../../include/hived.h"
 #include "hived_dev.h"
@@ -18,23 +22,21 @@
 
 namespace hived {
 
-#ifndef HIVED_MAXL_DEFINED
-#define HIVED_MAXL_DEFINED
 #ifndef HIVED_TOPO_CONSTS
 constexpr int MAXL = 16;
 constexpr int MAX_NODE_LEAVES = 64;
 constexpr int MAX_FANOUT = 64;
-#endif
 #endif
 
 constexpr int MAX_BINS = 4 * (MAX_NODE_LEAVES + 1);
 constexpr int MAX_WARPS = 32;
 constexpr int FREE_PRIO = HIVED_FREE_PRIORITY;
 constexpr int OPP_PRIO = HIVED_OPPORTUNISTIC_PRIORITY;
+constexpr int PF_AT_OR_ABOVE_NODE_BIT = 1, PF_NODE_LEVEL_BIT = 2, PF_PINNED_BIT = 4;
 
 // shared-memory block of the CTA
 struct Sm {
-  int cmd;        // 0 idle, 1 view pass, 2 exit
+  int cmd;  // CMD_*
   // ---- view-pass arguments
   int a_sched, a_prio, a_ignore, a_npods;
   const uint32_t* a_sugg;
@@ -42,15 +44,17 @@ struct Sm {
   int r_ok, r_reason, r_cell;
   // ---- scratch
   int best;
-  int nbins;
   int cnt[MAX_BINS * MAX_WARPS];
-  int part[1024 + 64];
-  // ---- event-scoped state (leader)
-  int panic;        // sticky platform-error code of the current event
+  int part[MAX_WARPS + 32];
+  // ---- written back at kernel exit
+  int panic;
   long long pool_off;
 };
 
 enum { CMD_IDLE = 0, CMD_VIEW = 1, CMD_EXIT = 2 };
+
+// uniform store: every lane of the (converged) leader warp writes the same value
+#define ST(lvalue, val) ((lvalue) = (val))
 
 struct Core {
   const Dev& d;
@@ -58,28 +62,74 @@ struct Core {
   const uint32_t* sugg;  // suggested-node bitmap of the current event (nullptr = every node)
   int32_t* pool;
   long long pool_cap;
-  HIVED_DEV Core(const Dev& dev, Sm* s, int32_t* pool_, long long cap) : d(dev), sm(s), sugg(nullptr), pool(pool_), pool_cap(cap) {}
+  long long poolOff;
+  int panicCode;  // sticky platform-error code of the current event
+  const int lane;
+  const int AS;
+  long long acc[ST_COUNT];  // work counters, flushed to d.stats when the batch ends
+
+  HIVED_DEV Core(const Dev& dev, Sm* s, int32_t* pool_, long long cap)
+      : d(dev), sm(s), sugg(nullptr), pool(pool_), pool_cap(cap), poolOff(0), panicCode(0), lane(hv_lane()), AS(dev.S.AS) {
+    for (int i = 0; i < ST_COUNT; i++) acc[i] = 0;
+  }
+
+  // ======================================================================================
+  // warp-level building blocks (leader warp; with HIVED_WARPSZ == 1 they degenerate to loops)
+  // ======================================================================================
+  // bit l (lo <= l < hi <= 32) set iff pred(l)
+  template <typename F>
+  HIVED_DEV unsigned levelMask(int lo, int hi, F pred) const {
+    unsigned m = 0;
+    for (int b = 0; b < hi; b += HIVED_WARPSZ) {
+      int l = b + lane;
+      bool p = l >= lo && l < hi && pred(l);
+      m |= hv_ballot(p) << b;
+    }
+    return m;
+  }
+  // smallest i in [0,n) with pred(i), else -1
+  template <typename F>
+  HIVED_DEV int firstIdx(int n, F pred) const {
+    for (int b = 0; b < n; b += HIVED_WARPSZ) {
+      int i = b + lane;
+      unsigned m = hv_ballot(i < n && pred(i));
+      if (m) return b + hv_ffs(m) - 1;
+    }
+    return -1;
+  }
+  template <typename F>
+  HIVED_DEV int maxOver(int n, F val, int init) const {
+    int v = init;
+    for (int b = 0; b < n; b += HIVED_WARPSZ) {
+      int i = b + lane;
+      if (i < n) { int x = val(i); if (x > v) v = x; }
+    }
+    for (int o = HIVED_WARPSZ / 2; o > 0; o >>= 1) { int t = hv_shfl_xor(v, o); if (t > v) v = t; }
+    return v;
+  }
 
   // ======================================================================================
   // small helpers
   // ======================================================================================
-  HIVED_DEV void panic(int code) { if (sm->panic == 0) HV_ST(&sm->panic, code); }
+  HIVED_DEV void panic(int code) { if (panicCode == 0) panicCode = code; }
   HIVED_DEV bool node_suggested(int node) const {
     if (sugg == nullptr) return true;
     if (node < 0) return false;
     return (sugg[node >> 5] >> (node & 31)) & 1u;
   }
-  HIVED_DEV void stat_add(int which, long long v) { HV_ST(&d.stats[which], d.stats[which] + v); }
+  HIVED_DEV void stat_add(int which, long long v) { acc[which] += v; }
   HIVED_DEV int cl(int chain, int level) const { return chain * MAXL + level; }
   HIVED_DEV int vcl(int vc, int chain, int level) const { return (vc * d.S.nChains + chain) * MAXL + level; }
 
-  // ---- free list of the physical cluster: order semantics of types.go:78-95 (swap-remove) and append
+  // ---- free list of the physical cluster: order semantics of types.go:78-95 (swap-remove) and append.
+  // (read everything, re-converge, then write: a lane must not see another lane's update of the length)
   HIVED_DEV void fl_append(int chain, int level, int cell) {
     int k = cl(chain, level);
     int n = d.fl_len[k];
-    HV_ST(&d.fl_data[d.fl_base[k] + n], cell);
-    HV_ST(&d.p_flpos[cell], n);
-    HV_ST(&d.fl_len[k], n + 1);
+    hv_warp_sync();
+    ST(d.fl_data[d.fl_base[k] + n], cell);
+    ST(d.p_flpos[cell], n);
+    ST(d.fl_len[k], n + 1);
   }
   HIVED_DEV void fl_remove(int chain, int level, int cell) {
     int k = cl(chain, level);
@@ -87,19 +137,21 @@ struct Core {
     if (pos < 0) { panic(HIVED_ERR_PLATFORM); return; }  // "Cell not not found in list when removing"
     int n = d.fl_len[k];
     int last = d.fl_data[d.fl_base[k] + n - 1];
-    HV_ST(&d.fl_data[d.fl_base[k] + pos], last);
-    HV_ST(&d.p_flpos[last], pos);
-    HV_ST(&d.p_flpos[cell], -1);
-    HV_ST(&d.fl_len[k], n - 1);
+    hv_warp_sync();
+    ST(d.fl_data[d.fl_base[k] + pos], last);
+    ST(d.p_flpos[last], pos);
+    ST(d.p_flpos[cell], -1);
+    ST(d.fl_len[k], n - 1);
   }
   HIVED_DEV bool fl_contains(int cell) const { return d.p_flpos[cell] >= 0; }
   // ---- bad free cells (badFreeCells, hived_algorithm.go:78)
   HIVED_DEV void bf_append(int chain, int level, int cell) {
     int k = cl(chain, level);
     int n = d.bf_len[k];
-    HV_ST(&d.bf_data[d.fl_base[k] + n], cell);
-    HV_ST(&d.p_bfpos[cell], n);
-    HV_ST(&d.bf_len[k], n + 1);
+    hv_warp_sync();
+    ST(d.bf_data[d.fl_base[k] + n], cell);
+    ST(d.p_bfpos[cell], n);
+    ST(d.bf_len[k], n + 1);
   }
   HIVED_DEV void bf_remove(int chain, int level, int cell) {
     int k = cl(chain, level);
@@ -107,20 +159,22 @@ struct Core {
     if (pos < 0) { panic(HIVED_ERR_PLATFORM); return; }
     int n = d.bf_len[k];
     int last = d.bf_data[d.fl_base[k] + n - 1];
-    HV_ST(&d.bf_data[d.fl_base[k] + pos], last);
-    HV_ST(&d.p_bfpos[last], pos);
-    HV_ST(&d.p_bfpos[cell], -1);
-    HV_ST(&d.bf_len[k], n - 1);
+    hv_warp_sync();
+    ST(d.bf_data[d.fl_base[k] + pos], last);
+    ST(d.p_bfpos[last], pos);
+    ST(d.p_bfpos[cell], -1);
+    ST(d.bf_len[k], n - 1);
   }
   // ---- doomed bad cells of a VC (vcDoomedBadCells, hived_algorithm.go:80)
   HIVED_DEV void dm_append(int vc, int chain, int level, int cell) {
     int k = vcl(vc, chain, level);
     int n = d.dm_len[k];
     if (n >= d.dm_cap[k]) { panic(HIVED_ERR_PLATFORM); return; }
-    HV_ST(&d.dm_data[d.dm_base[k] + n], cell);
-    HV_ST(&d.p_dmpos[cell], n);
-    HV_ST(&d.p_dmvc[cell], vc);
-    HV_ST(&d.dm_len[k], n + 1);
+    hv_warp_sync();
+    ST(d.dm_data[d.dm_base[k] + n], cell);
+    ST(d.p_dmpos[cell], n);
+    ST(d.p_dmvc[cell], vc);
+    ST(d.dm_len[k], n + 1);
   }
   HIVED_DEV void dm_remove(int vc, int chain, int level, int cell) {
     int k = vcl(vc, chain, level);
@@ -128,11 +182,12 @@ struct Core {
     if (pos < 0 || d.p_dmvc[cell] != vc) { panic(HIVED_ERR_PLATFORM); return; }
     int n = d.dm_len[k];
     int last = d.dm_data[d.dm_base[k] + n - 1];
-    HV_ST(&d.dm_data[d.dm_base[k] + pos], last);
-    HV_ST(&d.p_dmpos[last], pos);
-    HV_ST(&d.p_dmpos[cell], -1);
-    HV_ST(&d.p_dmvc[cell], -1);
-    HV_ST(&d.dm_len[k], n - 1);
+    hv_warp_sync();
+    ST(d.dm_data[d.dm_base[k] + pos], last);
+    ST(d.p_dmpos[last], pos);
+    ST(d.p_dmpos[cell], -1);
+    ST(d.p_dmvc[cell], -1);
+    ST(d.dm_len[k], n - 1);
   }
   HIVED_DEV bool dm_contains(int vc, int cell) const { return d.p_dmpos[cell] >= 0 && d.p_dmvc[cell] == vc; }
 
@@ -148,55 +203,67 @@ struct Core {
       c = par;
     }
   }
-  // cell.go:195-204 + utils.go:397-415
+  // cell.go:195-204 + utils.go:397-415.  Used propagates unconditionally: one gather over the levels.
   HIVED_DEV void setCellState(int c, int s) {
+    if (s == HIVED_CELL_USED) {
+      for (int b = 0; b < AS; b += HIVED_WARPSZ) {
+        int l = b + lane;
+        if (l < AS) {
+          int a = d.p_anc[c * AS + l];
+          if (a >= 0) {
+            d.p_state[a] = HIVED_CELL_USED;
+            int v = d.p_vcell[a];
+            if (v >= 0) d.v_state[v] = HIVED_CELL_USED;
+          }
+        }
+      }
+      hv_warp_sync();
+      return;
+    }
     while (true) {
-      HV_ST(&d.p_state[c], s);
+      ST(d.p_state[c], s);
       int vc = d.p_vcell[c];
-      if (vc >= 0) HV_ST(&d.v_state[vc], s);
+      if (vc >= 0) ST(d.v_state[vc], s);
       int par = d.p_parent[c];
       if (par < 0) return;
-      if (s != HIVED_CELL_USED) {
-        bool all = true;
-        int c0 = d.p_child0[par], n = d.p_nchild[par];
-        for (int i = 0; i < n; i++)
-          if (d.p_state[c0 + i] != s) { all = false; break; }
-        if (!all) return;
-      }
+      int c0 = d.p_child0[par], n = d.p_nchild[par];
+      if (firstIdx(n, [&](int i) { return d.p_state[c0 + i] != s; }) >= 0) return;
       c = par;
     }
   }
-  // cell_allocation.go:422-441, physical tree
-  HIVED_DEV void setPriorityP(int c, int p) {
-    while (true) {
-      int orig = d.p_prio[c];
-      HV_ST(&d.p_prio[c], p);
-      int par = d.p_parent[c];
-      if (par < 0) return;
-      int pp = d.p_prio[par];
-      if (p > pp) { c = par; continue; }
-      if (orig == pp && p < orig) {
-        int mx = FREE_PRIO;
-        int c0 = d.p_child0[par], n = d.p_nchild[par];
-        for (int i = 0; i < n; i++) { int q = d.p_prio[c0 + i]; if (q > mx) mx = q; }
-        c = par; p = mx; continue;
+  // cell_allocation.go:422-441.  A raise (p above the cell's priority) is max(old, p) on every
+  // ancestor independently, because a parent's priority is the max of its children's.
+  template <bool V>
+  HIVED_DEV void setPriority(int c, int p) {
+    int32_t* prio = V ? d.v_prio : d.p_prio;
+    const int32_t* anc = V ? d.v_anc : d.p_anc;
+    const int32_t* parent = V ? d.v_parent : d.p_parent;
+    const int32_t* child0 = V ? d.v_child0 : d.p_child0;
+    const int32_t* nchild = V ? d.v_nchild : d.p_nchild;
+    if (p > prio[c]) {
+      for (int b = 0; b < AS; b += HIVED_WARPSZ) {
+        int l = b + lane;
+        if (l < AS) {
+          int a = anc[c * AS + l];
+          if (a >= 0 && prio[a] < p) prio[a] = p;
+        }
       }
+      hv_warp_sync();
       return;
     }
-  }
-  HIVED_DEV void setPriorityV(int c, int p) {
     while (true) {
-      int orig = d.v_prio[c];
-      HV_ST(&d.v_prio[c], p);
-      int par = d.v_parent[c];
+      int orig = prio[c];
+      ST(prio[c], p);
+      int par = parent[c];
       if (par < 0) return;
-      int pp = d.v_prio[par];
+      int pp = prio[par];
       if (p > pp) { c = par; continue; }
       if (orig == pp && p < orig) {
-        int mx = FREE_PRIO;
-        int c0 = d.v_child0[par], n = d.v_nchild[par];
-        for (int i = 0; i < n; i++) { int q = d.v_prio[c0 + i]; if (q > mx) mx = q; }
-        c = par; p = mx; continue;
+        int c0 = child0[par];
+        int mx = maxOver(nchild[par], [&](int i) { return prio[c0 + i]; }, FREE_PRIO);
+        c = par;
+        p = mx;
+        continue;
       }
       return;
     }
@@ -204,28 +271,45 @@ struct Core {
   // cell_allocation.go:443-454 — only the opportunistic count of physical cells is ever read back
   // (getUsablePhysicalCells :238-241); every other used[] value is recomputed from leaf priorities.
   HIVED_DEV void updateUsedOpp(int c, int delta) {
-    while (c >= 0) { HV_ST(&d.p_usedopp[c], d.p_usedopp[c] + delta); c = d.p_parent[c]; }
+    for (int b = 0; b < AS; b += HIVED_WARPSZ) {
+      int l = b + lane;
+      if (l < AS) {
+        int a = d.p_anc[c * AS + l];
+        if (a >= 0) d.p_usedopp[a] += delta;
+      }
+    }
+    hv_warp_sync();
   }
   // cell.go:264-277, 401-419
   HIVED_DEV void bindPair(int pc, int vc) {
-    HV_ST(&d.p_vcell[pc], vc);
-    HV_ST(&d.v_pcell[vc], pc);
-    HV_ST(&d.v_healthy[vc], d.p_healthy[pc]);
+    ST(d.p_vcell[pc], vc);
+    ST(d.v_pcell[vc], pc);
+    ST(d.v_healthy[vc], d.p_healthy[pc]);
   }
   HIVED_DEV void unbindPair(int pc, int vc) {
-    HV_ST(&d.p_vcell[pc], -1);
-    HV_ST(&d.v_pcell[vc], -1);
-    HV_ST(&d.v_state[vc], HIVED_CELL_FREE);
-    HV_ST(&d.v_healthy[vc], 1);
+    ST(d.p_vcell[pc], -1);
+    ST(d.v_pcell[vc], -1);
+    ST(d.v_state[vc], HIVED_CELL_FREE);
+    ST(d.v_healthy[vc], 1);
   }
-  // cell_allocation.go:384-397
+  // cell_allocation.go:384-397: binds the unbound run of ancestors starting at (pc, vc)
   HIVED_DEV void bindCell(int pc, int vc) {
-    while (d.v_pcell[vc] < 0) {
-      bindPair(pc, vc);
-      if (d.v_parent[vc] < 0) break;
-      vc = d.v_parent[vc];
-      pc = d.p_parent[pc];
+    int lv = d.v_level[vc];
+    unsigned stopMask = levelMask(lv, AS, [&](int l) {
+      int va = d.v_anc[vc * AS + l];
+      return va < 0 || d.v_pcell[va] >= 0;
+    });
+    int stop = stopMask ? hv_ffs(stopMask) - 1 : AS;
+    for (int b = 0; b < stop; b += HIVED_WARPSZ) {
+      int l = b + lane;
+      if (l >= lv && l < stop) {
+        int va = d.v_anc[vc * AS + l], pa = d.p_anc[pc * AS + l];
+        d.p_vcell[pa] = va;
+        d.v_pcell[va] = pa;
+        d.v_healthy[va] = d.p_healthy[pa];
+      }
     }
+    hv_warp_sync();
   }
   // cell_allocation.go:399-420
   HIVED_DEV void unbindCell(int c) {
@@ -235,27 +319,23 @@ struct Core {
       unbindPair(bp, bv);
       int par = d.v_parent[bv];
       if (par < 0) return;
-      int c0 = d.v_child0[par], n = d.v_nchild[par];
-      for (int i = 0; i < n; i++)
-        if (d.v_pcell[c0 + i] >= 0) return;
+      int c0 = d.v_child0[par];
+      if (firstIdx(d.v_nchild[par], [&](int i) { return d.v_pcell[c0 + i] >= 0; }) >= 0) return;
       bv = par;
     }
   }
-  static constexpr int PF_AT_OR_ABOVE_NODE_BIT = 1, PF_NODE_LEVEL_BIT = 2, PF_PINNED_BIT = 4;
-
   // cell_allocation.go:374-382 over a contiguous child range
   HIVED_DEV int unboundChild(int vparent) const {
-    int c0 = d.v_child0[vparent], n = d.v_nchild[vparent];
-    for (int i = 0; i < n; i++)
-      if (d.v_pcell[c0 + i] < 0) return c0 + i;
-    return -1;
+    int c0 = d.v_child0[vparent];
+    int i = firstIdx(d.v_nchild[vparent], [&](int j) { return d.v_pcell[c0 + j] < 0; });
+    return i < 0 ? -1 : c0 + i;
   }
 
   // ======================================================================================
   // bad cells, doomed bad cells, preassigned cell (de)allocation  (hived_algorithm.go:466-653, 1354-1565)
   // ======================================================================================
   // hived_algorithm.go:1502-1527
-  HIVED_DEV int removeCellFromFreeList(int c) {
+  HIVED_DEV_NOINLINE int removeCellFromFreeList(int c) {
     int chain = d.p_chain[c];
     while (true) {
       int l = d.p_level[c];
@@ -267,7 +347,7 @@ struct Core {
         } else {
           int c0 = d.p_child0[par], n = d.p_nchild[par];
           for (int i = 0; i < n; i++) fl_append(chain, l, c0 + i);
-          HV_ST(&d.p_split[par], 1);
+          ST(d.p_split[par], 1);
         }
       } else {
         terminate = true;
@@ -278,23 +358,21 @@ struct Core {
     }
   }
   // hived_algorithm.go:1529-1565
-  HIVED_DEV int addCellToFreeList(int c) {
+  HIVED_DEV_NOINLINE int addCellToFreeList(int c) {
     int chain = d.p_chain[c];
     while (true) {
       int l = d.p_level[c];
       int par = d.p_parent[c];
       bool terminate = false;
       if (par >= 0) {
-        bool allBuddyFree = true;
         int c0 = d.p_child0[par], n = d.p_nchild[par];
-        for (int i = 0; i < n; i++)
-          if (c0 + i != c && !fl_contains(c0 + i)) { allBuddyFree = false; break; }
+        bool allBuddyFree = firstIdx(n, [&](int i) { return c0 + i != c && d.p_flpos[c0 + i] < 0; }) < 0;
         if (!allBuddyFree) {
           terminate = true;
         } else {
           for (int i = 0; i < n; i++)
             if (c0 + i != c) fl_remove(chain, l, c0 + i);
-          HV_ST(&d.p_split[par], 0);
+          ST(d.p_split[par], 0);
         }
       } else {
         terminate = true;
@@ -314,17 +392,15 @@ struct Core {
       while (d.vcFree[kv] > d.totalLeft[k] - d.bf_len[k]) {
         if (d.bf_len[k] <= 0 || ++guard > d.S.NP) { panic(HIVED_ERR_PLATFORM); return; }
         int pc = d.bf_data[d.fl_base[k] + 0];
-        int vcell = -1;
-        for (int i = 0; i < d.pre_cnt[kv]; i++) {
-          int cand = d.pre_list[d.pre_off[kv] + i];
-          if (d.v_pcell[cand] < 0) { vcell = cand; break; }
-        }
-        if (vcell < 0) { panic(HIVED_ERR_PLATFORM); return; }
+        const int32_t* pre = d.pre_list + d.pre_off[kv];
+        int idx = firstIdx(d.pre_cnt[kv], [&](int i) { return d.v_pcell[pre[i]] < 0; });
+        if (idx < 0) { panic(HIVED_ERR_PLATFORM); return; }
+        int vcell = pre[idx];
         bindPair(pc, vcell);
         dm_append(vc, chain, l, pc);
-        HV_ST(&d.allVCDoomed[k], d.allVCDoomed[k] + 1);
+        ST(d.allVCDoomed[k], d.allVCDoomed[k] + 1);
         allocatePreassignedCell(pc, vc, true);
-        if (sm->panic) return;
+        if (panicCode) return;
       }
     }
   }
@@ -340,9 +416,9 @@ struct Core {
         int pc = d.dm_data[d.dm_base[kv] + 0];
         unbindPair(pc, d.p_vcell[pc]);
         dm_remove(vc, chain, l, pc);
-        HV_ST(&d.allVCDoomed[k], d.allVCDoomed[k] - 1);
+        ST(d.allVCDoomed[k], d.allVCDoomed[k] - 1);
         releasePreassignedCell(pc, vc, true);
-        if (sm->panic) return;
+        if (panicCode) return;
       }
     }
   }
@@ -374,14 +450,14 @@ struct Core {
     bool safetyOk = true;
     int chain = d.p_chain[c], level = d.p_level[c];
     int kv = vcl(vc, chain, level), k = cl(chain, level);
-    HV_ST(&d.vcFree[kv], d.vcFree[kv] - 1);
-    HV_ST(&d.allVCFree[k], d.allVCFree[k] - 1);
-    HV_ST(&d.totalLeft[k], d.totalLeft[k] - 1);
+    ST(d.vcFree[kv], d.vcFree[kv] - 1);
+    ST(d.allVCFree[k], d.allVCFree[k] - 1);
+    ST(d.totalLeft[k], d.totalLeft[k] - 1);
     int splitLevelUpTo = removeCellFromFreeList(c);
     int parent = d.p_parent[c];
     for (int l = level + 1; l <= splitLevelUpTo; l++) {
       int kl = cl(chain, l);
-      HV_ST(&d.totalLeft[kl], d.totalLeft[kl] - 1);
+      ST(d.totalLeft[kl], d.totalLeft[kl] - 1);
       if (d.totalLeft[kl] < d.allVCFree[kl]) safetyOk = false;
       if (!d.p_healthy[parent]) {
         bf_remove(chain, l, parent);
@@ -399,7 +475,7 @@ struct Core {
     int numToReduce = d.p_nchild[c];
     for (int l = level - 1; l >= 1; l--) {
       int kl = cl(chain, l);
-      HV_ST(&d.totalLeft[kl], d.totalLeft[kl] - numToReduce);
+      ST(d.totalLeft[kl], d.totalLeft[kl] - numToReduce);
       if (d.totalLeft[kl] < d.allVCFree[kl]) safetyOk = false;
       if (!doomedBad) tryBindDoomedBadCell(chain, l);
       numToReduce *= d.chain_lvl_nchild[kl];
@@ -410,14 +486,14 @@ struct Core {
   HIVED_DEV_NOINLINE void releasePreassignedCell(int c, int vc, bool doomedBad) {
     int chain = d.p_chain[c], level = d.p_level[c];
     int kv = vcl(vc, chain, level), k = cl(chain, level);
-    HV_ST(&d.vcFree[kv], d.vcFree[kv] + 1);
-    HV_ST(&d.allVCFree[k], d.allVCFree[k] + 1);
-    HV_ST(&d.totalLeft[k], d.totalLeft[k] + 1);
+    ST(d.vcFree[kv], d.vcFree[kv] + 1);
+    ST(d.allVCFree[k], d.allVCFree[k] + 1);
+    ST(d.totalLeft[k], d.totalLeft[k] + 1);
     int mergeLevelUpTo = addCellToFreeList(c);
     int parent = d.p_parent[c];
     for (int l = level + 1; l <= mergeLevelUpTo; l++) {
       int kl = cl(chain, l);
-      HV_ST(&d.totalLeft[kl], d.totalLeft[kl] + 1);
+      ST(d.totalLeft[kl], d.totalLeft[kl] + 1);
       if (!d.p_healthy[parent]) {
         bf_append(chain, l, parent);
       } else {
@@ -434,16 +510,16 @@ struct Core {
     int numToAdd = d.p_nchild[c];
     for (int l = level - 1; l >= 1; l--) {
       int kl = cl(chain, l);
-      HV_ST(&d.totalLeft[kl], d.totalLeft[kl] + numToAdd);
+      ST(d.totalLeft[kl], d.totalLeft[kl] + numToAdd);
       if (!doomedBad) tryUnbindDoomedBadCell(chain, l);
       numToAdd *= d.chain_lvl_nchild[kl];
     }
   }
   // cell.go:302-312
   HIVED_DEV void setHealthiness(int c, int healthy) {
-    HV_ST(&d.p_healthy[c], healthy);
+    ST(d.p_healthy[c], healthy);
     int vc = d.p_vcell[c];
-    if (vc >= 0) HV_ST(&d.v_healthy[vc], healthy);
+    if (vc >= 0) ST(d.v_healthy[vc], healthy);
   }
   // hived_algorithm.go:562-581
   HIVED_DEV void addBadFreeCell(int c) {
@@ -486,16 +562,15 @@ struct Core {
           if (preassigned) {
             dm_remove(vcid, d.p_chain[c], d.p_level[c], c);
             int k = cl(d.p_chain[c], d.p_level[c]);
-            HV_ST(&d.allVCDoomed[k], d.allVCDoomed[k] - 1);
+            ST(d.allVCDoomed[k], d.allVCDoomed[k] - 1);
             releasePreassignedCell(c, vcid, true);
           }
         }
       }
       int par = d.p_parent[c];
       if (par < 0) return;
-      int c0 = d.p_child0[par], n = d.p_nchild[par];
-      for (int i = 0; i < n; i++)
-        if (!d.p_healthy[c0 + i]) return;
+      int c0 = d.p_child0[par];
+      if (firstIdx(d.p_nchild[par], [&](int i) { return !d.p_healthy[c0 + i]; }) >= 0) return;
       c = par;
     }
   }
@@ -504,17 +579,17 @@ struct Core {
     if (node < 0 || node >= d.S.nNodes) return;
     if (healthy) {
       if (!d.node_bad[node]) return;
-      HV_ST(&d.node_bad[node], 0);
+      ST(d.node_bad[node], 0);
     } else {
       if (d.node_bad[node]) return;
-      HV_ST(&d.node_bad[node], 1);
+      ST(d.node_bad[node], 1);
     }
     for (int chain = 0; chain < d.S.nChains; chain++) {
       int k = node * d.S.nChains + chain;
       for (int i = 0; i < d.ncl_cnt[k]; i++) {
         int leaf = d.ncl_list[d.ncl_off[k] + i];
         if (healthy) setHealthyCell(leaf); else setBadCell(leaf);
-        if (sm->panic) return;
+        if (panicCode) return;
       }
     }
   }
@@ -526,15 +601,15 @@ struct Core {
     bool safetyOk = true;
     stat_add(ST_LEAVES, 1);
     if (vLeaf >= 0) {
-      setPriorityV(vLeaf, p);
-      setPriorityP(pLeaf, p);
+      setPriority<true>(vLeaf, p);
+      setPriority<false>(pLeaf, p);
       if (p == OPP_PRIO) updateUsedOpp(pLeaf, 1);
       int pac = d.v_pre[vLeaf];
       bool newlyBound = d.v_pcell[pac] < 0;
       if (d.p_vcell[pLeaf] < 0) bindCell(pLeaf, vLeaf);
       if (newlyBound) safetyOk = allocatePreassignedCell(d.v_pcell[pac], vc, false);
     } else {
-      setPriorityP(pLeaf, OPP_PRIO);
+      setPriority<false>(pLeaf, OPP_PRIO);
       updateUsedOpp(pLeaf, 1);
     }
     return safetyOk;
@@ -543,7 +618,7 @@ struct Core {
     stat_add(ST_LEAVES, 1);
     int vLeaf = d.p_vcell[pLeaf];
     if (vLeaf >= 0) {
-      setPriorityV(vLeaf, FREE_PRIO);
+      setPriority<true>(vLeaf, FREE_PRIO);
       int pre = d.v_pre[vLeaf];
       int preassignedPhysical = d.v_pcell[pre];
       if (d.p_healthy[pLeaf]) unbindCell(pLeaf);
@@ -551,7 +626,7 @@ struct Core {
         releasePreassignedCell(preassignedPhysical, vc, false);
     }
     if (d.p_prio[pLeaf] == OPP_PRIO) updateUsedOpp(pLeaf, -1);
-    setPriorityP(pLeaf, FREE_PRIO);
+    setPriority<false>(pLeaf, FREE_PRIO);
   }
 
   // ======================================================================================
@@ -590,7 +665,7 @@ struct Core {
 
   // CTA-wide exclusive prefix sum of sm->cnt[0..n) (row-major: bin-major, warp-minor)
   HIVED_DEV void ctaExclusiveScan(int n) {
-    int nth = hv_nth(), tid = hv_tid(), lane = hv_lane(), w = hv_warp(), W = hv_nwarps();
+    int nth = hv_nth(), tid = hv_tid(), w = hv_warp(), W = hv_nwarps();
     int per = (n + nth - 1) / nth;
     int lo = tid * per, hi = lo + per < n ? lo + per : n;
     int s = 0;
@@ -614,7 +689,7 @@ struct Core {
   // one stable counting pass: out[rank] = in[i] ordered by bin(info[in[i]]), ties by position
   template <typename BinFn>
   HIVED_DEV void stablePass(const int32_t* in, int32_t* out, int n, int nbins, BinFn binOf) {
-    int W = hv_nwarps(), w = hv_warp(), lane = hv_lane();
+    int W = hv_nwarps(), w = hv_warp();
     for (int i = hv_tid(); i < nbins * W; i += hv_nth()) sm->cnt[i] = 0;
     hv_cta_sync();
     int chunk = (n + W - 1) / W;
@@ -692,9 +767,8 @@ struct Core {
         int mine = n;
         for (int j = nodeIndex + 1 + tid; j < n; j += nth)
           if (infoFree(sinfo[j]) >= need) { mine = j; break; }
-        // warp-level min, then one shared atomic per warp
         for (int o = HIVED_WARPSZ / 2; o > 0; o >>= 1) { int other = hv_shfl_xor(mine, o); if (other < mine) mine = other; }
-        if (hv_lane() == 0 && mine < n) hv_atomic_min(&sm->best, mine);
+        if (lane == 0 && mine < n) hv_atomic_min(&sm->best, mine);
         hv_cta_sync();
         int b = sm->best;
         hv_cta_sync();
@@ -719,15 +793,14 @@ struct Core {
 
   // leader: post the view pass to the CTA and take part in it
   HIVED_DEV bool runViewPass(int sched, int p, bool ignoreSuggested, int npods, int& reason, int& rcell) {
-    HV_ST(&sm->a_sched, sched);
-    HV_ST(&sm->a_prio, p);
-    HV_ST(&sm->a_ignore, ignoreSuggested ? 1 : 0);
-    HV_ST(&sm->a_npods, npods);
-    HV_ST(&sm->a_sugg, sugg);
-    HV_ST(&sm->cmd, CMD_VIEW);
+    ST(sm->a_sched, sched);
+    ST(sm->a_prio, p);
+    ST(sm->a_ignore, ignoreSuggested ? 1 : 0);
+    ST(sm->a_npods, npods);
+    ST(sm->a_sugg, sugg);
+    ST(sm->cmd, CMD_VIEW);
     hv_cta_sync();
     viewOp();
-    HV_ST(&sm->cmd, CMD_IDLE);
     stat_add(ST_VIEW_NODES, d.s_n[sched]);
     reason = sm->r_reason;
     rcell = sm->r_cell;
@@ -737,24 +810,17 @@ struct Core {
   // ======================================================================================
   // intra-node leaf search (topology_aware_scheduler.go:308-476)
   // ======================================================================================
-  template <bool V>
-  HIVED_DEV int tparent(int c) const { return V ? d.v_parent[c] : d.p_parent[c]; }
-  template <bool V>
-  HIVED_DEV int tlevel(int c) const { return V ? d.v_level[c] : d.p_level[c]; }
-  // :443-462
+  // :443-462 with the ancestor tables: lowest level >= level(higher) where both have the same ancestor
   template <bool V>
   HIVED_DEV int findLCA(int lower, int higher) const {
-    while (tlevel<V>(lower) < tlevel<V>(higher)) {
-      if (tparent<V>(lower) < 0) return -1;
-      lower = tparent<V>(lower);
-    }
-    if (lower == higher) return lower;
-    while (tparent<V>(lower) != tparent<V>(higher)) {
-      if (tparent<V>(lower) < 0 || tparent<V>(higher) < 0) return -1;
-      lower = tparent<V>(lower);
-      higher = tparent<V>(higher);
-    }
-    return tparent<V>(lower);
+    const int32_t* anc = V ? d.v_anc : d.p_anc;
+    int lh = V ? d.v_level[higher] : d.p_level[higher];
+    unsigned m = levelMask(lh, AS, [&](int l) {
+      int x = anc[lower * AS + l];
+      return x >= 0 && x == anc[higher * AS + l];
+    });
+    if (!m) return -1;
+    return anc[lower * AS + hv_ffs(m) - 1];
   }
   // :389-399
   HIVED_DEV int optimalAffinity(int chain, int leafNum) const {
@@ -768,17 +834,29 @@ struct Core {
     int32_t* avail = d.cand + slot * MAX_NODE_LEAVES;
     int navail;
     if (fresh) {
-      // getLeafCellsFromNode :464-476: free leaves in DFS order, then preemptible ones
+      // getLeafCellsFromNode :464-476: free leaves in DFS order, then preemptible ones (ballot compaction)
       int leaf0 = V ? d.v_leaf0[node] : d.p_leaf0[node];
       int nleaf = V ? d.v_nleaf[node] : d.p_nleaf[node];
       const int32_t* prio = V ? d.v_prio : d.p_prio;
       int n = 0;
-      for (int i = 0; i < nleaf; i++)
-        if (prio[leaf0 + i] == FREE_PRIO) { HV_ST(&avail[n], leaf0 + i); n++; }
-      for (int i = 0; i < nleaf; i++) {
-        int q = prio[leaf0 + i];
-        if (q != FREE_PRIO && q < p) { HV_ST(&avail[n], leaf0 + i); n++; }
+      for (int b = 0; b < nleaf; b += HIVED_WARPSZ) {
+        int i = b + lane;
+        bool f = i < nleaf && prio[leaf0 + i] == FREE_PRIO;
+        unsigned m = hv_ballot(f);
+        if (f) avail[n + hv_popc(m & hv_lanemask_lt())] = leaf0 + i;
+        n += hv_popc(m);
       }
+      if (p > OPP_PRIO) {
+        for (int b = 0; b < nleaf; b += HIVED_WARPSZ) {
+          int i = b + lane;
+          int q = i < nleaf ? prio[leaf0 + i] : FREE_PRIO;
+          bool f = q != FREE_PRIO && q < p;
+          unsigned m = hv_ballot(f);
+          if (f) avail[n + hv_popc(m & hv_lanemask_lt())] = leaf0 + i;
+          n += hv_popc(m);
+        }
+      }
+      hv_warp_sync();
       navail = n;
     } else {
       navail = d.cand_len[slot];
@@ -798,14 +876,15 @@ struct Core {
           curAff[si] = leaf;
         } else {
           curAff[si] = findLCA<V>(leaf, curAff[si - 1]);
-          if ((curAff[si] < 0 && bestAffinity < HIGHEST) || (curAff[si] >= 0 && tlevel<V>(curAff[si]) > bestAffinity)) {
+          int lv = curAff[si] >= 0 ? (V ? d.v_level[curAff[si]] : d.p_level[curAff[si]]) : 0;
+          if ((curAff[si] < 0 && bestAffinity < HIGHEST) || (curAff[si] >= 0 && lv > bestAffinity)) {
             ai++;
             continue;
           }
         }
         if (si == k - 1) {
           if (curAff[k - 1] < 0) { panic(HIVED_ERR_PLATFORM); return; }
-          int affinity = tlevel<V>(curAff[k - 1]);
+          int affinity = V ? d.v_level[curAff[k - 1]] : d.p_level[curAff[k - 1]];
           bool foundOptimal = false;
           if (affinity < bestAffinity) {
             for (int i = 0; i < k; i++) bestIdx[i] = curIdx[i];
@@ -826,16 +905,17 @@ struct Core {
       }
       ai = curIdx[si] + 1;
     }
-    for (int i = 0; i < k; i++) HV_ST(&out[i], avail[bestIdx[i]]);
+    for (int i = 0; i < k; i++) ST(out[i], avail[bestIdx[i]]);
     // removePickedLeafCells :425-441 (order preserving)
     int w = 0, b = 0;
     for (int i = 0; i < navail; i++) {
       if (b < k && bestIdx[b] == i) { b++; continue; }
       int v = avail[i];
-      HV_ST(&avail[w], v);
+      hv_warp_sync();
+      ST(avail[w], v);
       w++;
     }
-    HV_ST(&d.cand_len[slot], w);
+    ST(d.cand_len[slot], w);
   }
 
   // ======================================================================================
@@ -847,7 +927,7 @@ struct Core {
                                       bool ignoreSuggested, int32_t* outLeaves, int& reason, int& rcell) {
     int npods = 0;
     for (int m = 0; m < nmem; m++)
-      for (int i = 0; i < memPods[m]; i++) { HV_ST(&d.pod_need[npods], memLeaf[m]); npods++; }
+      for (int i = 0; i < memPods[m]; i++) { ST(d.pod_need[npods], memLeaf[m]); npods++; }
     int priority = OPP_PRIO;
     long long tc0 = hv_clock();
     bool ok = runViewPass(sched, priority, ignoreSuggested, npods, reason, rcell);
@@ -868,11 +948,11 @@ struct Core {
       for (int j = 0; j < nslots; j++)
         if (d.cand_node[j] == node) { slot = j; break; }
       bool fresh = slot < 0;
-      if (fresh) { slot = nslots++; HV_ST(&d.cand_node[slot], node); }
+      if (fresh) { slot = nslots++; ST(d.cand_node[slot], node); }
       int need = d.pod_need[k];
       if (isVirtual) findLeafCellsInNode<true>(node, need, priority, slot, fresh, chain, outLeaves + outOff);
       else findLeafCellsInNode<false>(node, need, priority, slot, fresh, chain, outLeaves + outOff);
-      if (sm->panic) return false;
+      if (panicCode) return false;
       outOff += need;
     }
     stat_add(ST_CYC_LEAF, hv_clock() - tc1);
@@ -887,44 +967,50 @@ struct Core {
   int vxCount;   // vertices in use
   int paCount;   // preassigned roots
   int npCount;   // non-preassigned buddy groups
+  int epochNow;
   HIVED_DEV int newVertex(int vcell) {
     int v = vxCount++;
     if (v >= d.S.VX) { panic(HIVED_ERR_CAPACITY); return 0; }
-    HV_ST(&d.vx_cell[v], vcell);
-    HV_ST(&d.vx_child[v], -1);
-    HV_ST(&d.vx_last[v], -1);
-    HV_ST(&d.vx_next[v], -1);
-    HV_ST(&d.vx_nch[v], 0);
-    HV_ST(&d.vx_of[vcell], v);
-    HV_ST(&d.vx_stamp[vcell], *d.epoch);
+    ST(d.vx_cell[v], vcell);
+    ST(d.vx_child[v], -1);
+    ST(d.vx_last[v], -1);
+    ST(d.vx_next[v], -1);
+    ST(d.vx_nch[v], 0);
+    ST(d.vx_of[vcell], v);
+    ST(d.vx_stamp[vcell], epochNow);
     return v;
   }
-  HIVED_DEV int vertexOf(int vcell) const { return d.vx_stamp[vcell] == *d.epoch ? d.vx_of[vcell] : -1; }
+  HIVED_DEV int vertexOf(int vcell) const { return d.vx_stamp[vcell] == epochNow ? d.vx_of[vcell] : -1; }
   HIVED_DEV void addChildVertex(int parentV, int childV) {
     int last = d.vx_last[parentV];
-    if (last < 0) HV_ST(&d.vx_child[parentV], childV); else HV_ST(&d.vx_next[last], childV);
-    HV_ST(&d.vx_last[parentV], childV);
-    HV_ST(&d.vx_nch[parentV], d.vx_nch[parentV] + 1);
+    int nch = d.vx_nch[parentV];
+    hv_warp_sync();
+    if (last < 0) ST(d.vx_child[parentV], childV); else ST(d.vx_next[last], childV);
+    ST(d.vx_last[parentV], childV);
+    ST(d.vx_nch[parentV], nch + 1);
   }
   // types.go:282-340
   HIVED_DEV_NOINLINE void toBindingPaths(const int32_t* vleaves, int nleaves) {
-    HV_ST(d.epoch, *d.epoch + 1);
+    epochNow = *d.epoch + 1;
+    hv_warp_sync();
+    ST(*d.epoch, epochNow);
     vxCount = 0; paCount = 0; npCount = 0;
-    int path[MAXL];
     for (int i = 0; i < nleaves; i++) {
       int leaf = vleaves[i];
       int pl = d.v_pcell[leaf];
-      if (pl >= 0) { HV_ST(&d.binding[leaf], pl); continue; }
-      int np = 0;
-      for (int c = leaf; c >= 0; c = d.v_parent[c]) {
-        if (d.v_pcell[c] >= 0 || vertexOf(c) >= 0) break;
-        path[np++] = c;
-      }
-      int root = path[np - 1];
+      if (pl >= 0) { ST(d.binding[leaf], pl); continue; }
+      // the unbound run of ancestors that are not yet vertices: levels [1, stop)
+      unsigned stopMask = levelMask(1, AS, [&](int l) {
+        int a = d.v_anc[leaf * AS + l];
+        return a < 0 || d.v_pcell[a] >= 0 || vertexOf(a) >= 0;
+      });
+      int stop = stopMask ? hv_ffs(stopMask) - 1 : AS;
+      if (stop <= 1) { panic(HIVED_ERR_PLATFORM); return; }
+      int root = d.v_anc[leaf * AS + stop - 1];
       int n = newVertex(root);
       int par = d.v_parent[root];
       if (par < 0) {
-        HV_ST(&d.pa_list[paCount], n); paCount++;
+        ST(d.pa_list[paCount], n); paCount++;
       } else if (d.v_pcell[par] >= 0) {
         bool buddy = false;
         for (int g = 0; g < npCount; g++) {
@@ -932,22 +1018,24 @@ struct Core {
             // append to the group's chain (roots are linked through vx_next)
             int t = d.np_head[g];
             while (d.vx_next[t] >= 0) t = d.vx_next[t];
-            HV_ST(&d.vx_next[t], n);
-            HV_ST(&d.np_cnt[g], d.np_cnt[g] + 1);
+            int cnt = d.np_cnt[g];
+            hv_warp_sync();
+            ST(d.vx_next[t], n);
+            ST(d.np_cnt[g], cnt + 1);
             buddy = true;
             break;
           }
         }
-        if (!buddy) { HV_ST(&d.np_head[npCount], n); HV_ST(&d.np_cnt[npCount], 1); npCount++; }
+        if (!buddy) { ST(d.np_head[npCount], n); ST(d.np_cnt[npCount], 1); npCount++; }
       } else {
         addChildVertex(vertexOf(par), n);
       }
-      for (int j = np - 2; j >= 0; j--) {
-        int c = path[j];
+      for (int l = stop - 2; l >= 1; l--) {
+        int c = d.v_anc[leaf * AS + l];
         int nn = newVertex(c);
         addChildVertex(vertexOf(d.v_parent[c]), nn);
       }
-      if (sm->panic) return;
+      if (panicCode) return;
     }
   }
 
@@ -969,7 +1057,6 @@ struct Core {
     stat_add(ST_FREE_CELLS, nin);
     // order-preserving filter, one warp-wide ballot per 32 candidates
     int n = 0;
-    const int lane = hv_lane();
     for (int b0 = 0; b0 < nin; b0 += HIVED_WARPSZ) {
       int i = b0 + lane;
       int c = i < nin ? (in ? in[i] : base + i) : -1;
@@ -981,19 +1068,13 @@ struct Core {
     hv_warp_sync();
     if (n < numNeeded) return -1;
     // sort.SliceStable by used[opportunistic]: only when some neighbour pair is out of order
-    bool unsorted = false;
-    for (int b0 = 1; b0 < n; b0 += HIVED_WARPSZ) {
-      int i = b0 + lane;
-      bool bad = i < n && d.p_usedopp[out[i - 1]] > d.p_usedopp[out[i]];
-      if (hv_ballot(bad)) { unsorted = true; break; }
-    }
-    if (unsorted) {
+    if (firstIdx(n - 1, [&](int i) { return d.p_usedopp[out[i]] > d.p_usedopp[out[i + 1]]; }) >= 0) {
       for (int i = 1; i < n; i++) {
         int c = out[i], key = d.p_usedopp[c];
         int j = i - 1;
         if (d.p_usedopp[out[j]] <= key) continue;
-        while (j >= 0 && d.p_usedopp[out[j]] > key) { HV_ST(&out[j + 1], out[j]); j--; }
-        HV_ST(&out[j + 1], c);
+        while (j >= 0 && d.p_usedopp[out[j]] > key) { int v = out[j]; hv_warp_sync(); ST(out[j + 1], v); j--; }
+        ST(out[j + 1], c);
       }
     }
     return n;
@@ -1010,7 +1091,7 @@ struct Core {
     int32_t* cellV = d.mccells + depth * MAX_FANOUT;
     {
       int v = firstV;
-      for (int i = 0; i < ncells; i++) { HV_ST(&cellV[i], v); HV_ST(&pickedIdx[i], 0); v = d.vx_next[v]; }
+      for (int i = 0; i < ncells; i++) { ST(cellV[i], v); ST(pickedIdx[i], 0); v = d.vx_next[v]; }
     }
     int cellIndex = 0;
     while (cellIndex >= 0) {
@@ -1025,17 +1106,17 @@ struct Core {
         bool picked;
         if (d.p_level[candidate] == 1) {
           picked = true;
-          HV_ST(&d.binding[d.vx_cell[vtx]], candidate);
+          ST(d.binding[d.vx_cell[vtx]], candidate);
         } else {
           picked = mapVirtualCellsToPhysical(d.vx_child[vtx], d.vx_nch[vtx], nullptr, d.p_child0[candidate], d.p_nchild[candidate],
                                              ignoreSuggested, depth + 1, nullptr);
-          if (sm->panic) return false;
+          if (panicCode) return false;
         }
         if (picked) {
-          HV_ST(&pickedIdx[cellIndex], candidateIndex);
+          ST(pickedIdx[cellIndex], candidateIndex);
           if (cellIndex == ncells - 1) {
             if (pickedOut)
-              for (int i = 0; i < ncells; i++) HV_ST(&pickedOut[i], cands[pickedIdx[i]]);
+              for (int i = 0; i < ncells; i++) ST(pickedOut[i], cands[pickedIdx[i]]);
             return true;
           }
           break;
@@ -1043,7 +1124,7 @@ struct Core {
       }
       if (candidateIndex == n) {
         cellIndex--;
-        if (cellIndex >= 0) HV_ST(&pickedIdx[cellIndex], pickedIdx[cellIndex] + 1);
+        if (cellIndex >= 0) { int v = pickedIdx[cellIndex]; hv_warp_sync(); ST(pickedIdx[cellIndex], v + 1); }
       } else {
         cellIndex++;
       }
@@ -1056,37 +1137,32 @@ struct Core {
   HIVED_DEV int32_t* sfl(int level) const { return d.sfl_data + d.fl_base[cl(sflChain, level)]; }
   HIVED_DEV void sflCopy(int chain) {
     sflChain = chain;
-    const int lane = hv_lane();
     for (int l = 1; l < MAXL; l++) {
       int k = cl(chain, l);
       int n = l <= d.chain_top[chain] ? d.fl_len[k] : 0;
-      HV_ST(&d.sfl_len[l], n);
+      ST(d.sfl_len[l], n);
       for (int i = lane; i < n; i += HIVED_WARPSZ) d.sfl_data[d.fl_base[k] + i] = d.fl_data[d.fl_base[k] + i];
     }
     hv_warp_sync();
   }
   HIVED_DEV void sflRemove(int level, int cell) {  // types.go:78-95 on the copy
     int32_t* a = sfl(level);
-    int n = d.sfl_len[level], idx = -1;
-    const int lane = hv_lane();
-    for (int b0 = 0; b0 < n && idx < 0; b0 += HIVED_WARPSZ) {
-      int i = b0 + lane;
-      unsigned m = hv_ballot(i < n && a[i] == cell);
-      if (m) idx = b0 + hv_ffs(m) - 1;
-    }
+    int n = d.sfl_len[level];
+    int idx = firstIdx(n, [&](int i) { return a[i] == cell; });
     if (idx < 0) { panic(HIVED_ERR_PLATFORM); return; }
-    HV_ST(&a[idx], a[n - 1]);
-    HV_ST(&d.sfl_len[level], n - 1);
+    int lastv = a[n - 1];
+    hv_warp_sync();
+    ST(a[idx], lastv);
+    ST(d.sfl_len[level], n - 1);
   }
 
   // cell_allocation.go:34-80
   HIVED_DEV_NOINLINE bool buddyAlloc(int vtx, int currentLevel, bool ignoreSuggested) {
     int cellLevel = d.v_level[d.vx_cell[vtx]];
     if (currentLevel == cellLevel) {
-      int32_t picked[1];
-      HV_ST(&d.vx_next[vtx], -1);
+      ST(d.vx_next[vtx], -1);
       bool ok = mapVirtualCellsToPhysical(vtx, 1, sfl(currentLevel), 0, d.sfl_len[currentLevel], ignoreSuggested, 0, d.tmp_list);
-      if (ok) { picked[0] = d.tmp_list[0]; sflRemove(currentLevel, picked[0]); return true; }
+      if (ok) { sflRemove(currentLevel, d.tmp_list[0]); return true; }
       return false;
     }
     int32_t* freeCells = d.ba_buf + (int64_t)currentLevel * d.S.maxLevelCount;
@@ -1096,14 +1172,16 @@ struct Core {
       int c = freeCells[i];
       int32_t* lower = sfl(currentLevel - 1);
       int nl = d.sfl_len[currentLevel - 1];
-      for (int j = 0; j < d.p_nchild[c]; j++) HV_ST(&lower[nl + j], d.p_child0[c] + j);
-      HV_ST(&d.sfl_len[currentLevel - 1], nl + d.p_nchild[c]);
+      int nc = d.p_nchild[c], c0 = d.p_child0[c];
+      for (int j = lane; j < nc; j += HIVED_WARPSZ) lower[nl + j] = c0 + j;
+      hv_warp_sync();
+      ST(d.sfl_len[currentLevel - 1], nl + nc);
       if (buddyAlloc(vtx, currentLevel - 1, ignoreSuggested)) {
         sflRemove(currentLevel, c);
         return true;
       }
-      if (sm->panic) return false;
-      HV_ST(&d.sfl_len[currentLevel - 1], 0);  // = nil
+      if (panicCode) return false;
+      ST(d.sfl_len[currentLevel - 1], 0);  // = nil
     }
     return false;
   }
@@ -1129,7 +1207,7 @@ struct Core {
         int ns = 0;
         for (int i = 0; i < cellNum; i++) {
           int first = sfl(l)[0];
-          HV_ST(&split[ns], first); ns++;
+          ST(split[ns], first); ns++;
           sflRemove(l, first);
         }
         splittableNum[l] -= cellNum;
@@ -1140,21 +1218,22 @@ struct Core {
           if (total > d.S.maxLevelCount) { panic(HIVED_ERR_CAPACITY); return false; }
           int w = total;
           for (int i = ns - 1; i >= 0; i--) {
-            int c = split[i], nc = d.p_nchild[c];
-            for (int j = nc - 1; j >= 0; j--) { w--; HV_ST(&split[w], d.p_child0[c] + j); }
+            int c = split[i], nc = d.p_nchild[c], c0 = d.p_child0[c];
+            hv_warp_sync();
+            for (int j = nc - 1; j >= 0; j--) { w--; ST(split[w], c0 + j); }
           }
           ns = total;
         }
         // freeList[currentLevel] = append(splitList, freeList[currentLevel]...)
         int32_t* cur = sfl(currentLevel);
         int nc = d.sfl_len[currentLevel];
-        for (int i = nc - 1; i >= 0; i--) HV_ST(&cur[i + ns], cur[i]);
-        for (int i = 0; i < ns; i++) HV_ST(&cur[i], split[i]);
-        HV_ST(&d.sfl_len[currentLevel], nc + ns);
-        HV_ST(&d.vx_next[vtx], -1);
+        for (int i = nc - 1; i >= 0; i--) { int v = cur[i]; hv_warp_sync(); ST(cur[i + ns], v); }
+        for (int i = 0; i < ns; i++) ST(cur[i], split[i]);
+        ST(d.sfl_len[currentLevel], nc + ns);
+        ST(d.vx_next[vtx], -1);
         bool ok = mapVirtualCellsToPhysical(vtx, 1, cur, 0, nc + ns, ignoreSuggested, 0, d.tmp_list);
         if (ok) { sflRemove(currentLevel, d.tmp_list[0]); return true; }
-        if (sm->panic) return false;
+        if (panicCode) return false;
       }
     }
     return false;
@@ -1178,7 +1257,7 @@ struct Core {
         if (d.sfl_len[l] != 0) break;
       if (l > top) { panic(HIVED_ERR_PLATFORM); return false; }  // getLowestFreeCellLevel: "VC Safety Broken"
       if (!buddyAlloc(vtx, l, ignoreSuggested)) {
-        if (sm->panic) return false;
+        if (panicCode) return false;
         if (!safeRelaxedBuddyAlloc(vtx, freeCellNum, level, ignoreSuggested)) return false;
       } else {
         freeCellNum[level]--;
@@ -1229,22 +1308,24 @@ struct Core {
   HIVED_DEV void newGroup(int g, const hived_pod_spec_t& sp, int state) {
     int leaf[HIVED_MAX_MEMBERS], pods[HIVED_MAX_MEMBERS];
     int n = mergeMembers(sp, leaf, pods);
-    HV_ST(&d.g_state[g], state);
-    HV_ST(&d.g_vc[g], sp.vc);
-    HV_ST(&d.g_prio[g], sp.priority);
-    HV_ST(&d.g_flags[g], ((sp.flags & HIVED_SPEC_LAZY_PREEMPTION) ? GF_LAZY_ENABLE : 0) | GF_HAS_VIRTUAL);
-    HV_ST(&d.g_nmem[g], n);
+    ST(d.g_state[g], state);
+    ST(d.g_vc[g], sp.vc);
+    ST(d.g_prio[g], sp.priority);
+    ST(d.g_flags[g], ((sp.flags & HIVED_SPEC_LAZY_PREEMPTION) ? GF_LAZY_ENABLE : 0) | GF_HAS_VIRTUAL);
+    ST(d.g_nmem[g], n);
     int nl = 0, np = 0;
     for (int m = 0; m < n; m++) {
-      HV_ST(&d.g_mem_leaf[g * 8 + m], leaf[m]);
-      HV_ST(&d.g_mem_pods[g * 8 + m], pods[m]);
+      ST(d.g_mem_leaf[g * 8 + m], leaf[m]);
+      ST(d.g_mem_pods[g * 8 + m], pods[m]);
       nl += leaf[m] * pods[m]; np += pods[m];
     }
-    for (int i = 0; i < nl; i++) { HV_ST(&gphys(g)[i], -1); HV_ST(&gvirt(g)[i], -1); }
-    for (int i = 0; i < np; i++) HV_ST(&gpods(g)[i], -1);
-    HV_ST(&d.g_npre[g], 0);
+    int32_t* ph = gphys(g); int32_t* vi = gvirt(g); int32_t* po = gpods(g);
+    for (int i = lane; i < nl; i += HIVED_WARPSZ) { ph[i] = -1; vi[i] = -1; }
+    for (int i = lane; i < np; i += HIVED_WARPSZ) po[i] = -1;
+    hv_warp_sync();
+    ST(d.g_npre[g], 0);
   }
-  HIVED_DEV void eraseGroup(int g) { HV_ST(&d.g_state[g], HIVED_GROUP_NONE); }
+  HIVED_DEV void eraseGroup(int g) { ST(d.g_state[g], HIVED_GROUP_NONE); }
   // slot offsets of member m: leaves before it / pods before it
   HIVED_DEV void memberOffsets(int g, int m, int& leafOff, int& podOff) const {
     leafOff = 0; podOff = 0;
@@ -1271,10 +1352,12 @@ struct Core {
       }
     }
     if (save) {
-      HV_ST(&save[0], had ? 1 : 0);  // word 0: non-nil marker
-      for (int i = 0; i < nl; i++) HV_ST(&save[1 + i], had ? gvirt(g)[i] : -1);
+      ST(save[0], had ? 1 : 0);  // word 0: non-nil marker
+      for (int i = 0; i < nl; i++) ST(save[1 + i], had ? gvirt(g)[i] : -1);
     }
-    HV_ST(&d.g_flags[g], (d.g_flags[g] & ~GF_HAS_VIRTUAL) | GF_LAZY_PREEMPTED);
+    int fl = d.g_flags[g];
+    hv_warp_sync();
+    ST(d.g_flags[g], (fl & ~GF_HAS_VIRTUAL) | GF_LAZY_PREEMPTED);
   }
   // hived_algorithm.go:1193-1201
   HIVED_DEV_NOINLINE void lazyPreemptCell(int vcell) {
@@ -1298,19 +1381,23 @@ struct Core {
       releaseLeafCell(pLeaf, d.g_vc[g]);
       allocateLeafCell(pLeaf, vLeaf, d.g_prio[g], d.g_vc[g]);
     }
-    for (int i = 0; i < nl; i++) HV_ST(&gvirt(g)[i], save[1 + i]);
-    HV_ST(&d.g_flags[g], (d.g_flags[g] | GF_HAS_VIRTUAL) & ~GF_LAZY_PREEMPTED);
+    for (int i = 0; i < nl; i++) ST(gvirt(g)[i], save[1 + i]);
+    int fl = d.g_flags[g];
+    hv_warp_sync();
+    ST(d.g_flags[g], (fl | GF_HAS_VIRTUAL) & ~GF_LAZY_PREEMPTED);
   }
 
   // hived_algorithm.go:1043-1070
   HIVED_DEV void deleteAllocatedAffinityGroup(int g) {
     int nl = groupLeaves(g);
+    int vc = d.g_vc[g];
+    const int32_t* ph = gphys(g);
     for (int i = 0; i < nl; i++) {
-      int pLeaf = gphys(g)[i];
+      int pLeaf = ph[i];
       if (pLeaf < 0) continue;
-      HV_ST(&d.p_using[pLeaf], -1);
+      ST(d.p_using[pLeaf], -1);
       if (d.p_state[pLeaf] == HIVED_CELL_USED) {
-        releaseLeafCell(pLeaf, d.g_vc[g]);
+        releaseLeafCell(pLeaf, vc);
         setCellState(pLeaf, HIVED_CELL_FREE);
       } else {
         setCellState(pLeaf, HIVED_CELL_RESERVED);
@@ -1320,10 +1407,9 @@ struct Core {
   }
   // utils.go:267-283
   HIVED_DEV int retrieveVirtualCell(int g, int pLeaf) const {
-    int nl = groupLeaves(g);
-    for (int i = 0; i < nl; i++)
-      if (gphys(g)[i] == pLeaf) return gvirt(g)[i];
-    return -1;
+    const int32_t* ph = gphys(g);
+    int i = firstIdx(groupLeaves(g), [&](int j) { return ph[j] == pLeaf; });
+    return i < 0 ? -1 : gvirt(g)[i];
   }
   // hived_algorithm.go:1114-1145
   HIVED_DEV_NOINLINE void deletePreemptingAffinityGroup(int g) {
@@ -1331,7 +1417,7 @@ struct Core {
     for (int i = 0; i < nl; i++) {
       int pLeaf = gphys(g)[i];
       releaseLeafCell(pLeaf, d.g_vc[g]);
-      HV_ST(&d.p_resv[pLeaf], -1);
+      ST(d.p_resv[pLeaf], -1);
       if (d.p_state[pLeaf] == HIVED_CELL_RESERVING) {
         setCellState(pLeaf, HIVED_CELL_USED);
         int bg = d.p_using[pLeaf];
@@ -1349,39 +1435,40 @@ struct Core {
     int nl = groupLeaves(g);
     for (int i = 0; i < nl; i++) {
       int pLeaf = gphys(g)[i];
-      HV_ST(&d.p_resv[pLeaf], -1);
-      HV_ST(&d.p_using[pLeaf], g);
+      ST(d.p_resv[pLeaf], -1);
+      ST(d.p_using[pLeaf], g);
       setCellState(pLeaf, HIVED_CELL_USED);
     }
-    HV_ST(&d.g_state[g], HIVED_GROUP_ALLOCATED);
-    HV_ST(&d.g_npre[g], 0);
+    ST(d.g_state[g], HIVED_GROUP_ALLOCATED);
+    ST(d.g_npre[g], 0);
   }
   // hived_algorithm.go:1072-1112
   HIVED_DEV_NOINLINE void createPreemptingAffinityGroup(int g, const hived_pod_spec_t& sp, const int32_t* phys, const int32_t* virt) {
     newGroup(g, sp, HIVED_GROUP_PREEMPTING);
     int nl = groupLeaves(g);
-    for (int i = 0; i < nl; i++) { HV_ST(&gphys(g)[i], phys[i]); HV_ST(&gvirt(g)[i], virt[i]); }
+    for (int i = 0; i < nl; i++) { ST(gphys(g)[i], phys[i]); ST(gvirt(g)[i], virt[i]); }
     for (int i = 0; i < nl; i++) {
       int pLeaf = phys[i], vLeaf = virt[i];
       if (d.p_state[pLeaf] == HIVED_CELL_USED) {
         int ug = d.p_using[pLeaf];
         releaseLeafCell(pLeaf, d.g_vc[ug]);
-        HV_ST(&d.g_state[ug], HIVED_GROUP_BEING_PREEMPTED);
+        ST(d.g_state[ug], HIVED_GROUP_BEING_PREEMPTED);
       }
       allocateLeafCell(pLeaf, vLeaf, sp.priority, sp.vc);
-      HV_ST(&d.p_resv[pLeaf], g);
+      ST(d.p_resv[pLeaf], g);
       if (d.p_state[pLeaf] == HIVED_CELL_USED) setCellState(pLeaf, HIVED_CELL_RESERVING);
       else setCellState(pLeaf, HIVED_CELL_RESERVED);
     }
-    HV_ST(&gpre(g)[0], sp.pod);
-    HV_ST(&d.g_npre[g], 1);
+    ST(gpre(g)[0], sp.pod);
+    ST(d.g_npre[g], 1);
   }
   HIVED_DEV void addPreemptingPod(int g, int pod) {  // g.preemptingPods[pod.UID] = pod
     int n = d.g_npre[g];
     for (int i = 0; i < n; i++) if (gpre(g)[i] == pod) return;
     if (n >= d.S.PS) { panic(HIVED_ERR_CAPACITY); return; }
-    HV_ST(&gpre(g)[n], pod);
-    HV_ST(&d.g_npre[g], n + 1);
+    hv_warp_sync();
+    ST(gpre(g)[n], pod);
+    ST(d.g_npre[g], n + 1);
   }
 
   // ======================================================================================
@@ -1399,6 +1486,8 @@ struct Core {
   // hived_algorithm.go:944-965
   HIVED_DEV void tryLazyPreempt(const int32_t* vleaves, int nleaves) {
     lzCount = 0;
+    // fast path: no leaf of the placement is bound to a Used physical cell
+    if (firstIdx(nleaves, [&](int i) { int pl = d.v_pcell[vleaves[i]]; return pl >= 0 && d.p_state[pl] == HIVED_CELL_USED; }) < 0) return;
     for (int i = 0; i < nleaves; i++) {
       int pLeaf = d.v_pcell[vleaves[i]];
       if (pLeaf < 0) continue;
@@ -1410,10 +1499,10 @@ struct Core {
           if (slot < 0) {
             if (lzCount >= d.S.LZ) { panic(HIVED_ERR_CAPACITY); return; }
             slot = lzCount++;
-            HV_ST(&d.lz_group[slot], victim);
+            ST(d.lz_group[slot], victim);
           }
           lazyPreemptAffinityGroup(victim, d.lz_save + (int64_t)slot * (d.S.LS + 1));
-          if (sm->panic) return;
+          if (panicCode) return;
         }
       }
     }
@@ -1430,17 +1519,19 @@ struct Core {
     }
     long long tm0 = hv_clock();
     tryLazyPreempt(d.pl_v, r.nleaves);
-    if (sm->panic) return false;
+    if (panicCode) return false;
     toBindingPaths(d.pl_v, r.nleaves);
-    if (sm->panic) return false;
+    if (panicCode) return false;
     bool mapped = mapVirtualPlacementToPhysical(r.chain, r.ignoreSuggested);
     stat_add(ST_CYC_MAP, hv_clock() - tm0);
     if (mapped) {
-      for (int i = 0; i < r.nleaves; i++) HV_ST(&d.pl_p[i], d.binding[d.pl_v[i]]);  // toPhysicalPlacement types.go:260-280
+      // toPhysicalPlacement types.go:260-280
+      for (int i = lane; i < r.nleaves; i += HIVED_WARPSZ) d.pl_p[i] = d.binding[d.pl_v[i]];
+      hv_warp_sync();
       reason = 0; rcell = -1;
       return true;
     }
-    if (sm->panic) return false;
+    if (panicCode) return false;
     for (int j = 0; j < lzCount; j++) revertLazyPreempt(d.lz_group[j], d.lz_save + (int64_t)j * (d.S.LS + 1));
     reason = HIVED_WAIT_MAPPING; rcell = -1;
     return false;
@@ -1471,7 +1562,7 @@ struct Core {
         vcHasType = true;
         r.chain = chain;
         if (handleSchedulingRequest(r, hasVirtual, reason, rcell)) { reason = 0; return 1; }
-        if (sm->panic) return 0;
+        if (panicCode) return 0;
       }
     }
     if (typeSpecified && r.priority >= 0 && !vcHasType) return -HIVED_ERR_LEAF_TYPE_NOT_IN_VC;
@@ -1502,7 +1593,7 @@ struct Core {
       int tr, tc;
       int rc = scheduleForLeafCellType(r, lt, false, hasVirtual, tr, tc);
       if (rc != 0) { reason = 0; rcell = -1; return rc; }
-      if (sm->panic) return 0;
+      if (panicCode) return 0;
       if (tr != 0) { lastReason = tr; lastCell = tc; }
     }
     reason = lastReason; rcell = lastCell;
@@ -1512,19 +1603,18 @@ struct Core {
   // ======================================================================================
   // results
   // ======================================================================================
-  HIVED_DEV void poolPut(int32_t v) {
-    if (sm->pool_off >= pool_cap) { panic(HIVED_ERR_CAPACITY); return; }
-    HV_ST(&pool[sm->pool_off], v);
-    HV_ST(&sm->pool_off, sm->pool_off + 1);
-  }
   // utils.go:202-235.  victims written to the pool (pod id, node id) sorted by pod id; overlapping
-  // preemptor groups (sorted by id) to d.tmp_list, count returned through nOverlap.
+  // preemptor groups (sorted by id) to d.lz_group, count returned through nOverlap.
   HIVED_DEV_NOINLINE void collectPreemptionVictims(const int32_t* phys, int nleaves, hived_result_t* res, int& nOverlap) {
-    int32_t* groups = d.tmp_list;  // using groups (first half) — tmp_list has >= MAX_FANOUT + maxLevelCount entries
-    int ng = 0;
     nOverlap = 0;
-    int32_t* overlap = d.lz_group;  // reuse: lazy-preempt bookkeeping is dead by now
-    long long start = sm->pool_off;
+    ST(res->victim_off, 0);
+    ST(res->n_victims, 0);
+    // fast path: every cell of the placement is Free
+    if (firstIdx(nleaves, [&](int i) { int c = phys[i]; return c >= 0 && d.p_state[c] != HIVED_CELL_FREE; }) < 0) return;
+    int32_t* groups = d.tmp_list;  // using groups
+    int ng = 0;
+    int32_t* overlap = d.lz_group;  // lazy-preempt bookkeeping is dead by now
+    long long start = poolOff;
     for (int i = 0; i < nleaves; i++) {
       int c = phys[i];
       if (c < 0) continue;
@@ -1535,7 +1625,7 @@ struct Core {
         for (int j = 0; j < ng; j++) if (groups[j] == g) { seen = true; break; }
         if (!seen && g >= 0) {
           if (ng >= d.S.maxLevelCount + MAX_FANOUT) { panic(HIVED_ERR_CAPACITY); return; }
-          HV_ST(&groups[ng], g); ng++;
+          ST(groups[ng], g); ng++;
         }
       }
       if (st == HIVED_CELL_RESERVING || st == HIVED_CELL_RESERVED) {
@@ -1544,7 +1634,7 @@ struct Core {
         for (int j = 0; j < nOverlap; j++) if (overlap[j] == g) { seen = true; break; }
         if (!seen && g >= 0) {
           if (nOverlap >= d.S.LS) { panic(HIVED_ERR_CAPACITY); return; }
-          HV_ST(&overlap[nOverlap], g); nOverlap++;
+          ST(overlap[nOverlap], g); nOverlap++;
         }
       }
     }
@@ -1554,64 +1644,73 @@ struct Core {
       for (int k = 0; k < np; k++) {
         int pod = gpods(g)[k];
         if (pod < 0) continue;
-        // insert sorted by pod id
-        poolPut(0); poolPut(0);
-        if (sm->panic) return;
-        int pos = nv;
+        if (poolOff + 2 > pool_cap) { panic(HIVED_ERR_CAPACITY); return; }
+        poolOff += 2;
+        int pos = nv;  // insert sorted by pod id
         while (pos > 0 && pool[start + 2 * (pos - 1)] > pod) {
-          HV_ST(&pool[start + 2 * pos], pool[start + 2 * (pos - 1)]);
-          HV_ST(&pool[start + 2 * pos + 1], pool[start + 2 * (pos - 1) + 1]);
+          int a = pool[start + 2 * (pos - 1)], bb = pool[start + 2 * (pos - 1) + 1];
+          hv_warp_sync();
+          ST(pool[start + 2 * pos], a);
+          ST(pool[start + 2 * pos + 1], bb);
           pos--;
         }
-        HV_ST(&pool[start + 2 * pos], pod);
-        HV_ST(&pool[start + 2 * pos + 1], d.pod_node[pod]);
+        ST(pool[start + 2 * pos], pod);
+        ST(pool[start + 2 * pos + 1], d.pod_node[pod]);
         nv++;
       }
     }
     for (int i = 1; i < nOverlap; i++) {  // ascending group id
       int g = overlap[i], j = i - 1;
-      while (j >= 0 && overlap[j] > g) { HV_ST(&overlap[j + 1], overlap[j]); j--; }
-      HV_ST(&overlap[j + 1], g);
+      while (j >= 0 && overlap[j] > g) { int v = overlap[j]; hv_warp_sync(); ST(overlap[j + 1], v); j--; }
+      ST(overlap[j + 1], g);
     }
-    HV_ST(&res->victim_off, nv ? (int)start : 0);
-    HV_ST(&res->n_victims, nv);
-    if (nv == 0) HV_ST(&sm->pool_off, start);
+    ST(res->victim_off, nv ? (int)start : 0);
+    ST(res->n_victims, nv);
   }
 
-  // generatePodScheduleResult / generateAffinityGroupBindInfo (utils.go:38-171)
-  HIVED_DEV_NOINLINE void emitBind(hived_result_t* res, int nmem, const int* memLeaf, const int* memPods, const int32_t* phys,
-                                   const int32_t* virt, bool hasVirtual, int curLeafNum, int curPodIndex) {
-    HV_ST(&res->kind, HIVED_KIND_BIND);
-    HV_ST(&res->has_virtual, hasVirtual ? 1 : 0);
-    HV_ST(&res->pod_index, curPodIndex);
-    HV_ST(&res->n_members, nmem);
-    HV_ST(&res->leaf_off, (int)sm->pool_off);
-    int k = 0;
+  // generatePodScheduleResult / generateAffinityGroupBindInfo (utils.go:38-171): lanes over the gang's leaves
+  HIVED_DEV void emitBind(hived_result_t* res, int nmem, const int* memLeaf, const int* memPods, const int32_t* phys,
+                          const int32_t* virt, bool hasVirtual, int curLeafNum, int curPodIndex) {
+    int nl = 0, thisOff = -1, thisN = 0;
     for (int m = 0; m < nmem; m++) {
-      HV_ST(&res->member_leaf_num[m], memLeaf[m]);
-      HV_ST(&res->member_pod_num[m], memPods[m]);
-      for (int pi = 0; pi < memPods[m]; pi++) {
-        if (memLeaf[m] == curLeafNum && pi == curPodIndex) {
-          HV_ST(&res->this_off, (int)sm->pool_off);
-          HV_ST(&res->this_n, memLeaf[m]);
-          int first = phys[k];
-          if (first < 0) { panic(HIVED_ERR_PLATFORM); return; }
-          HV_ST(&res->node, d.p_node[first]);
-          HV_ST(&res->chain, d.p_chain[first]);
-        }
-        for (int j = 0; j < memLeaf[m]; j++, k++) {
-          int pl = phys[k];
-          if (pl < 0) { panic(HIVED_ERR_PLATFORM); return; }  // retrieveMissingPodPlacement: recovery path
-          poolPut(d.p_node[pl]);
-          poolPut(d.p_leafidx[pl]);
+      ST(res->member_leaf_num[m], memLeaf[m]);
+      ST(res->member_pod_num[m], memPods[m]);
+      if (memLeaf[m] == curLeafNum && thisOff < 0) { thisOff = nl + curPodIndex * memLeaf[m]; thisN = memLeaf[m]; }
+      nl += memLeaf[m] * memPods[m];
+    }
+    const long long base = poolOff;
+    if (base + 3ll * nl > pool_cap) { panic(HIVED_ERR_CAPACITY); return; }
+    bool bad = false;
+    for (int b = 0; b < nl; b += HIVED_WARPSZ) {
+      int k = b + lane;
+      if (k < nl) {
+        int pl = phys[k];
+        if (pl < 0) {
+          bad = true;  // retrieveMissingPodPlacement: recovery path
+        } else {
           int t = -1;
           if (hasVirtual) { int vl = virt[k]; t = d.chain_lvl_type[cl(d.v_chain[vl], d.v_level[d.v_pre[vl]])]; }
-          poolPut(t);
-          if (sm->panic) return;
+          pool[base + 3 * k] = d.p_node[pl];
+          pool[base + 3 * k + 1] = d.p_leafidx[pl];
+          pool[base + 3 * k + 2] = t;
         }
       }
+      if (hv_ballot(bad)) { panic(HIVED_ERR_PLATFORM); return; }
     }
-    HV_ST(&res->n_leaves, k);
+    hv_warp_sync();
+    if (thisOff < 0) { panic(HIVED_ERR_PLATFORM); return; }
+    int first = phys[thisOff];
+    ST(res->kind, HIVED_KIND_BIND);
+    ST(res->has_virtual, hasVirtual ? 1 : 0);
+    ST(res->pod_index, curPodIndex);
+    ST(res->n_members, nmem);
+    ST(res->leaf_off, (int)base);
+    ST(res->n_leaves, nl);
+    ST(res->this_off, (int)(base + 3 * thisOff));
+    ST(res->this_n, thisN);
+    ST(res->node, d.p_node[first]);
+    ST(res->chain, d.p_chain[first]);
+    poolOff = base + 3ll * nl;
   }
 
   // ======================================================================================
@@ -1621,11 +1720,9 @@ struct Core {
   HIVED_DEV int findPhysicalLeafCellInChain(int chain, int node, int leafIdx) const {
     if (chain < 0 || node < 0) return -1;
     int k = node * d.S.nChains + chain;
-    for (int i = 0; i < d.ncl_cnt[k]; i++) {
-      int leaf = d.ncl_list[d.ncl_off[k] + i];
-      if (leafIdx < 0 || d.p_leafidx[leaf] == leafIdx) return leaf;
-    }
-    return -1;
+    const int32_t* list = d.ncl_list + d.ncl_off[k];
+    int i = firstIdx(d.ncl_cnt[k], [&](int j) { return leafIdx < 0 || d.p_leafidx[list[j]] == leafIdx; });
+    return i < 0 ? -1 : list[i];
   }
   // utils.go:318-345
   HIVED_DEV int findPhysicalLeafCell(int chain, int node, int leafIdx) const {
@@ -1635,41 +1732,50 @@ struct Core {
       if (c != chain) { g = findPhysicalLeafCellInChain(c, node, leafIdx); if (g >= 0) return g; }
     return -1;
   }
-  // cell_allocation.go:348-372 over a list (ptr) or a contiguous range
+  // cell_allocation.go:348-372 over a list (ptr) or a contiguous range: the first free-and-unbound cell,
+  // else the first cell of minimal priority among those below p
   HIVED_DEV int getLowestPriorityVirtualCell(const int32_t* list, int base, int n, int p) const {
-    int lowest = HIVED_MAX_GUARANTEED_PRIORITY, cell = -1;
-    for (int i = 0; i < n; i++) {
-      int vc = list ? list[i] : base + i;
-      int q = d.v_prio[vc];
-      if (q == FREE_PRIO) {
-        if (d.v_pcell[vc] < 0) return vc;
-        continue;
-      } else if (q < p && q < lowest) { lowest = q; cell = vc; }
+    int freeIdx = firstIdx(n, [&](int i) { int vc = list ? list[i] : base + i; return d.v_prio[vc] == FREE_PRIO && d.v_pcell[vc] < 0; });
+    if (freeIdx >= 0) return list ? list[freeIdx] : base + freeIdx;
+    const int NONE = 0x7fffffff;
+    int best = NONE;  // (priority + 2) * 4096 + index: minimal priority, then first position
+    for (int b = 0; b < n; b += HIVED_WARPSZ) {
+      int i = b + lane;
+      if (i < n) {
+        int vc = list ? list[i] : base + i;
+        int q = d.v_prio[vc];
+        if (q != FREE_PRIO && q < p && q < HIVED_MAX_GUARANTEED_PRIORITY) { int key = (q + 2) * 4096 + i; if (key < best) best = key; }
+      }
     }
-    return cell;
+    for (int o = HIVED_WARPSZ / 2; o > 0; o >>= 1) { int t = hv_shfl_xor(best, o); if (t < best) best = t; }
+    if (best == NONE) return -1;
+    int idx = best & 4095;
+    return list ? list[idx] : base + idx;
   }
   // cell_allocation.go:317-346.  vccl: pinned -> the vset's cells at the level; else the VC's preassigned roots
   HIVED_DEV int mapPhysicalCellToVirtual(int c, int vc, int chain, int pinned, int preassignedLevel, int p) const {
-    int steps = 0;
-    int virt = -1;
-    while (true) {
-      if (d.p_vcell[c] >= 0) { virt = d.p_vcell[c]; break; }
-      if (d.p_level[c] == preassignedLevel) {
-        if (pinned >= 0) {
-          int vset = d.vc_pinned_vset[vc * d.S.nPinned + pinned];
-          int k = vset * MAXL + preassignedLevel;
-          virt = (preassignedLevel < MAXL) ? getLowestPriorityVirtualCell(nullptr, d.v_lvl_base[k], d.v_lvl_cnt[k], p) : -1;
-        } else {
-          int k = vcl(vc, chain, preassignedLevel);
-          virt = getLowestPriorityVirtualCell(d.pre_list + d.pre_off[k], 0, d.pre_cnt[k], p);
-        }
-        break;
-      }
-      if (d.p_parent[c] < 0) return -1;
-      c = d.p_parent[c];
-      steps++;
+    int lc = d.p_level[c];
+    // first level (>= the cell's) whose ancestor is bound, or that is the preassigned level, or beyond the top
+    unsigned m = levelMask(lc, AS, [&](int l) {
+      int a = d.p_anc[c * AS + l];
+      return a < 0 || d.p_vcell[a] >= 0 || l == preassignedLevel;
+    });
+    if (!m) return -1;
+    int ls = hv_ffs(m) - 1;
+    int a = d.p_anc[c * AS + ls];
+    if (a < 0) return -1;  // ran past the top: hierarchies do not match
+    int virt;
+    if (d.p_vcell[a] >= 0) {
+      virt = d.p_vcell[a];
+    } else if (pinned >= 0) {
+      int vset = d.vc_pinned_vset[vc * d.S.nPinned + pinned];
+      int k = vset * MAXL + preassignedLevel;
+      virt = getLowestPriorityVirtualCell(nullptr, d.v_lvl_base[k], d.v_lvl_cnt[k], p);
+    } else {
+      int k = vcl(vc, chain, preassignedLevel);
+      virt = getLowestPriorityVirtualCell(d.pre_list + d.pre_off[k], 0, d.pre_cnt[k], p);
     }
-    for (int i = 0; i < steps && virt >= 0; i++) virt = getLowestPriorityVirtualCell(nullptr, d.v_child0[virt], d.v_nchild[virt], p);
+    for (int i = ls - lc; i > 0 && virt >= 0; i--) virt = getLowestPriorityVirtualCell(nullptr, d.v_child0[virt], d.v_nchild[virt], p);
     return virt;
   }
 
@@ -1681,15 +1787,16 @@ struct Core {
   };
 
   // utils.go:291-304
-  HIVED_DEV static int getAllocatedPodIndex(const BindView& b, int leafNum) {
+  HIVED_DEV int getAllocatedPodIndex(const BindView& b, int leafNum) const {
     int k = 0;
     for (int m = 0; m < b.n_members; m++) {
       int ln = b.member_leaf_num[m], pn = b.member_pod_num[m];
       if (ln == leafNum) {
         for (int pi = 0; pi < pn; pi++) {
-          if (b.leaves[3 * (k + pi * ln)] == b.node)
-            for (int j = 0; j < ln; j++)
-              if (b.leaves[3 * (k + pi * ln + j) + 1] == b.first_leaf) return pi;
+          if (b.leaves[3 * (k + pi * ln)] == b.node) {
+            const int32_t* row = b.leaves + 3 * (k + pi * ln);
+            if (firstIdx(ln, [&](int j) { return row[3 * j + 1] == b.first_leaf; }) >= 0) return pi;
+          }
         }
       }
       k += ln * pn;
@@ -1701,12 +1808,16 @@ struct Core {
     int g = sp.group;
     newGroup(g, sp, HIVED_GROUP_ALLOCATED);
     bool shouldLazyPreempt = false;
+    bool hasVirtualFlag = true;
+    int32_t* ph = gphys(g);
+    int32_t* vi = gvirt(g);
     int k = 0;
     for (int m = 0; m < b.n_members; m++) {
       int leafNumber = b.member_leaf_num[m];
       int gm = memberOf(g, leafNumber);
       int leafOff = 0, podOff = 0;
       if (gm >= 0) memberOffsets(g, gm, leafOff, podOff);
+      int gmPods = gm >= 0 ? d.g_mem_pods[g * 8 + gm] : 0;
       for (int podIndex = 0; podIndex < b.member_pod_num[m]; podIndex++) {
         int node = b.leaves[3 * k];
         for (int li = 0; li < leafNumber; li++, k++) {
@@ -1717,7 +1828,7 @@ struct Core {
           int lazy = 1;  // 0 nil, 1 false, 2 true
           if (!b.has_preassigned) {
             lazy = 2;
-          } else if ((d.g_flags[g] & GF_HAS_VIRTUAL) && !shouldLazyPreempt) {
+          } else if (hasVirtualFlag && !shouldLazyPreempt) {
             int t = b.leaves[3 * k + 2];
             if (t != -1) {
               int chainOfLeaf = d.p_chain[pLeaf];
@@ -1735,25 +1846,26 @@ struct Core {
               lazy = 0;
             }
           }
-          if (gm < 0 || podIndex >= d.g_mem_pods[g * 8 + gm]) { panic(HIVED_ERR_PLATFORM); return; }  // index out of range
+          if (gm < 0 || podIndex >= gmPods) { panic(HIVED_ERR_PLATFORM); return; }  // index out of range
           int slot = leafOff + podIndex * leafNumber + li;
-          HV_ST(&gphys(g)[slot], pLeaf);
+          ST(ph[slot], pLeaf);
           if (lazy == 0) {
-            HV_ST(&d.g_flags[g], d.g_flags[g] & ~GF_HAS_VIRTUAL);
+            hasVirtualFlag = false;
           } else if (vLeaf >= 0) {
-            HV_ST(&gvirt(g)[slot], vLeaf);
+            ST(vi[slot], vLeaf);
             if (inFreeCellList(pLeaf) && d.v_prio[d.v_pre[vLeaf]] > FREE_PRIO) lazyPreemptCell(d.v_pre[vLeaf]);
           } else {
             shouldLazyPreempt = shouldLazyPreempt || lazy == 2;
           }
           bool safetyOk = allocateLeafCell(pLeaf, vLeaf, sp.priority, sp.vc);
-          HV_ST(&d.p_using[pLeaf], g);
+          ST(d.p_using[pLeaf], g);
           setCellState(pLeaf, HIVED_CELL_USED);
           if (!safetyOk) shouldLazyPreempt = true;
-          if (sm->panic) return;
+          if (panicCode) return;
         }
       }
     }
+    if (!hasVirtualFlag) { int fl = d.g_flags[g]; hv_warp_sync(); ST(d.g_flags[g], fl & ~GF_HAS_VIRTUAL); }
     if (shouldLazyPreempt) lazyPreemptAffinityGroup(g, nullptr);
   }
 
@@ -1766,14 +1878,14 @@ struct Core {
       if (podIndex == -1) return 0;
     } else {
       createAllocatedAffinityGroup(sp, b);
-      if (sm->panic) return 0;
+      if (panicCode) return 0;
     }
     int m = memberOf(g, sp.leaf_num);
     if (m < 0 || podIndex < 0 || podIndex >= d.g_mem_pods[g * 8 + m]) { panic(HIVED_ERR_PLATFORM); return 0; }
     int leafOff, podOff;
     memberOffsets(g, m, leafOff, podOff);
-    HV_ST(&gpods(g)[podOff + podIndex], sp.pod);
-    HV_ST(&d.pod_node[sp.pod], b.node);
+    ST(gpods(g)[podOff + podIndex], sp.pod);
+    ST(d.pod_node[sp.pod], b.node);
     return 0;
   }
 
@@ -1785,9 +1897,9 @@ struct Core {
     if (m < 0 || podIndex < 0 || podIndex >= d.g_mem_pods[g * 8 + m]) { panic(HIVED_ERR_PLATFORM); return; }
     int leafOff, podOff;
     memberOffsets(g, m, leafOff, podOff);
-    HV_ST(&gpods(g)[podOff + podIndex], -1);
-    int np = groupPods(g);
-    for (int i = 0; i < np; i++) if (gpods(g)[i] >= 0) return;
+    ST(gpods(g)[podOff + podIndex], -1);
+    const int32_t* po = gpods(g);
+    if (firstIdx(groupPods(g), [&](int i) { return po[i] >= 0; }) >= 0) return;
     deleteAllocatedAffinityGroup(g);
   }
   // hived_algorithm.go:229-245
@@ -1795,7 +1907,7 @@ struct Core {
     if (g < 0 || g >= d.S.maxGroups || d.g_state[g] != HIVED_GROUP_PREEMPTING) return;
     int n = d.g_npre[g];
     for (int i = 0; i < n; i++)
-      if (gpre(g)[i] == pod) { HV_ST(&gpre(g)[i], gpre(g)[n - 1]); n--; HV_ST(&d.g_npre[g], n); break; }
+      if (gpre(g)[i] == pod) { int lastv = gpre(g)[n - 1]; hv_warp_sync(); ST(gpre(g)[i], lastv); n--; ST(d.g_npre[g], n); break; }
     if (n == 0) deletePreemptingAffinityGroup(g);
   }
 
@@ -1805,10 +1917,7 @@ struct Core {
   HIVED_DEV_NOINLINE int schedule(const hived_pod_spec_t& sp, int phase, hived_result_t* res) {
     int g = sp.group;
     stat_add(ST_SCHEDULE, 1);
-    {
-      long long bit = (sp.priority >= -1 && sp.priority < 62) ? (1ll << (sp.priority + 1)) : (1ll << 63);
-      if (!(d.stats[ST_PRIO_MASK] & bit)) HV_ST(&d.stats[ST_PRIO_MASK], d.stats[ST_PRIO_MASK] | bit);
-    }
+    acc[ST_PRIO_MASK] |= (sp.priority >= -1 && sp.priority < 62) ? (1ll << (sp.priority + 1)) : (1ll << 62);
     bool havePlacement = false, hasVirtual = false;
     const int32_t* phys = nullptr;
     const int32_t* virt = nullptr;
@@ -1818,12 +1927,12 @@ struct Core {
     if (d.g_state[g] != HIVED_GROUP_NONE) {
       // schedulePodFromExistingGroup :655-712
       int nl = groupLeaves(g);
-      bool badOrNonSuggested = false;  // collectBadOrNonSuggestedNodes utils.go:175-200 (ignoreK8sSuggestedNodes is never set on a group)
-      for (int i = 0; i < nl; i++) {
-        int c = gphys(g)[i];
-        if (c < 0) continue;
-        if (!d.p_healthy[c] || !node_suggested(d.p_node[c])) { badOrNonSuggested = true; break; }
-      }
+      const int32_t* ph = gphys(g);
+      // collectBadOrNonSuggestedNodes utils.go:175-200 (ignoreK8sSuggestedNodes is never set on a group)
+      bool badOrNonSuggested = firstIdx(nl, [&](int i) {
+        int c = ph[i];
+        return c >= 0 && (!d.p_healthy[c] || !node_suggested(d.p_node[c]));
+      }) >= 0;
       nmem = d.g_nmem[g];
       for (int m = 0; m < nmem; m++) { memLeaf[m] = d.g_mem_leaf[g * 8 + m]; memPods[m] = d.g_mem_pods[g * 8 + m]; }
       if (d.g_state[g] == HIVED_GROUP_ALLOCATED) {
@@ -1833,8 +1942,8 @@ struct Core {
         if (m >= 0) {
           int leafOff, podOff;
           memberOffsets(g, m, leafOff, podOff);
-          for (int i = 0; i < d.g_mem_pods[g * 8 + m]; i++)
-            if (gpods(g)[podOff + i] < 0) { podIndex = i; break; }
+          const int32_t* po = gpods(g) + podOff;
+          podIndex = firstIdx(d.g_mem_pods[g * 8 + m], [&](int i) { return po[i] < 0; });
         }
         if (podIndex == -1) return HIVED_ERR_TOO_MANY_PODS;
       } else {
@@ -1848,13 +1957,13 @@ struct Core {
           addPreemptingPod(g, sp.pod);
         }
       }
-      if (sm->panic) return sm->panic;
+      if (panicCode) return panicCode;
     }
     if (d.g_state[g] == HIVED_GROUP_NONE) {
       // schedulePodFromNewGroup :714-752
       Req r;
       int rc = scheduleNewAffinityGroup(sp, r, hasVirtual, reason, rcell);
-      if (sm->panic) return sm->panic;
+      if (panicCode) return panicCode;
       if (rc < 0) return -rc;
       nmem = r.nmem;
       for (int m = 0; m < nmem; m++) { memLeaf[m] = r.memLeaf[m]; memPods[m] = r.memPods[m]; }
@@ -1864,32 +1973,31 @@ struct Core {
         int nOverlap;
         collectPreemptionVictims(phys, r.nleaves, res, nOverlap);
         victimsCollected = true;
-        if (sm->panic) return sm->panic;
+        if (panicCode) return panicCode;
         if (phase == HIVED_PHASE_PREEMPTING) {
-          // copy first: cancelling preemptors never touches pl_*, but keep the order of the reference
           for (int i = 0; i < nOverlap; i++) deletePreemptingAffinityGroup(d.lz_group[i]);
           if (res->n_victims != 0) {
-            if (!hasVirtual) { panic(HIVED_ERR_PLATFORM); return sm->panic; }  // nil virtual placement indexed in the reference
-            for (int i = 0; i < r.nleaves; i++) { HV_ST(&d.pl_p2[i], d.pl_p[i]); HV_ST(&d.pl_v2[i], d.pl_v[i]); }
+            if (!hasVirtual) { panic(HIVED_ERR_PLATFORM); return panicCode; }  // nil virtual placement indexed in the reference
+            for (int i = 0; i < r.nleaves; i++) { ST(d.pl_p2[i], d.pl_p[i]); ST(d.pl_v2[i], d.pl_v[i]); }
             createPreemptingAffinityGroup(g, sp, d.pl_p2, d.pl_v2);
           }
         }
-        if (sm->panic) return sm->panic;
+        if (panicCode) return panicCode;
       } else {
         havePlacement = false;
       }
     }
     // generatePodScheduleResult utils.go:38-79
     if (!havePlacement) {
-      HV_ST(&res->kind, HIVED_KIND_WAIT);
-      HV_ST(&res->wait_code, reason);
-      HV_ST(&res->wait_cell, rcell);
+      ST(res->kind, HIVED_KIND_WAIT);
+      ST(res->wait_code, reason);
+      ST(res->wait_cell, rcell);
       stat_add(ST_WAIT, 1);
       return 0;
     }
     if (victimsCollected && res->n_victims > 0) {
-      HV_ST(&res->kind, HIVED_KIND_PREEMPT);
-      HV_ST(&res->has_virtual, hasVirtual ? 1 : 0);
+      ST(res->kind, HIVED_KIND_PREEMPT);
+      ST(res->has_virtual, hasVirtual ? 1 : 0);
       stat_add(ST_PREEMPT, 1);
       return 0;
     }
@@ -1897,66 +2005,13 @@ struct Core {
     emitBind(res, nmem, memLeaf, memPods, phys, virt, hasVirtual, sp.leaf_num, podIndex);
     stat_add(ST_CYC_EMIT, hv_clock() - te0);
     stat_add(ST_BIND, 1);
-    return sm->panic;
+    return panicCode;
   }
 
   // ======================================================================================
   // one event (leader warp).  aux: hived_bind_info_t + leaf triples for the explicit AddAllocatedPod.
   // ======================================================================================
-  HIVED_DEV_NOINLINE void processEvent(const hived_event_t& ev, hived_result_t* res, const uint32_t* suggPool, const int32_t* aux) {
-    HV_ST(&sm->panic, 0);
-    long long tev0 = hv_clock();
-    // clearResult
-    {
-      int32_t* w = reinterpret_cast<int32_t*>(res);
-      for (int i = 0; i < (int)(sizeof(hived_result_t) / 4); i++) HV_ST(&w[i], 0);
-      HV_ST(&res->wait_cell, -1); HV_ST(&res->chain, -1); HV_ST(&res->node, -1);
-    }
-    sugg = (ev.suggested_off >= 0 && suggPool) ? suggPool + ev.suggested_off : nullptr;
-    int rc = 0;
-    int type = ev.type;
-    if (type == HIVED_EV_SCHEDULE || type == EV_SCHEDULE_ONLY) {
-      const hived_pod_spec_t& sp = ev.spec;
-      rc = validateSpec(sp);
-      if (rc == 0) rc = schedule(sp, ev.phase, res);
-      if (rc == 0 && type == HIVED_EV_SCHEDULE && res->kind == HIVED_KIND_BIND) {
-        // the filterRoutine sequence: AddAllocatedPod with the PodBindInfo just produced
-        BindView b;
-        b.node = res->node; b.first_leaf = pool[res->this_off + 1]; b.chain = res->chain; b.has_preassigned = 1;
-        b.n_members = res->n_members; b.member_leaf_num = res->member_leaf_num; b.member_pod_num = res->member_pod_num;
-        b.leaves = pool + res->leaf_off;
-        sugg = nullptr;
-        long long ta0 = hv_clock();
-        addAllocatedPod(sp, b, getAllocatedPodIndex(b, sp.leaf_num));
-        stat_add(ST_CYC_COMMIT, hv_clock() - ta0);
-        rc = sm->panic;
-      }
-    } else if (type == EV_ADD_ALLOCATED) {
-      const hived_bind_info_t* bi = reinterpret_cast<const hived_bind_info_t*>(aux);
-      BindView b;
-      b.node = bi->node; b.first_leaf = bi->first_leaf; b.chain = bi->chain; b.has_preassigned = bi->has_preassigned;
-      b.n_members = bi->n_members; b.member_leaf_num = bi->member_leaf_num; b.member_pod_num = bi->member_pod_num;
-      b.leaves = aux + sizeof(hived_bind_info_t) / 4;
-      rc = validateSpec(ev.spec);
-      if (rc == 0) { addAllocatedPod(ev.spec, b, ev.arg0); rc = sm->panic; }
-    } else if (type == HIVED_EV_DELETE_ALLOCATED) {
-      long long td0 = hv_clock();
-      deleteAllocatedPod(ev.spec.group, ev.spec.leaf_num, ev.arg0);
-      stat_add(ST_CYC_DELETE, hv_clock() - td0);
-      rc = sm->panic;
-    } else if (type == HIVED_EV_DELETE_UNALLOCATED) {
-      deleteUnallocatedPod(ev.spec.group, ev.spec.pod);
-      rc = sm->panic;
-    } else if (type == HIVED_EV_NODE_HEALTH) {
-      setNodeHealth(ev.arg0, ev.arg1 != 0);
-      rc = sm->panic;
-    } else {
-      rc = HIVED_ERR_PLATFORM;
-    }
-    HV_ST(&res->error, rc);
-    stat_add(ST_CYC_TOTAL, hv_clock() - tev0);
-  }
-  static constexpr int EV_SCHEDULE_ONLY = 16, EV_ADD_ALLOCATED = 17, EV_INIT = 18;
+  static constexpr int EV_SCHEDULE_ONLY = 16, EV_ADD_ALLOCATED = 17;
 
   // pkg/internal/utils.go:256-287 + capacity checks (the shim validates first; this is defensive)
   HIVED_DEV int validateSpec(const hived_pod_spec_t& sp) const {
@@ -1976,9 +2031,63 @@ struct Core {
     return 0;
   }
 
+  HIVED_DEV_NOINLINE void processEvent(const hived_event_t& ev, hived_result_t* res, const uint32_t* suggPool, const int32_t* aux) {
+    panicCode = 0;
+    long long tev0 = hv_clock();
+    {  // clearResult: one word per lane
+      int32_t* w = reinterpret_cast<int32_t*>(res);
+      for (int i = lane; i < (int)(sizeof(hived_result_t) / 4); i += HIVED_WARPSZ) w[i] = 0;
+      hv_warp_sync();
+      ST(res->wait_cell, -1); ST(res->chain, -1); ST(res->node, -1);
+    }
+    sugg = (ev.suggested_off >= 0 && suggPool) ? suggPool + ev.suggested_off : nullptr;
+    int rc = 0;
+    int type = ev.type;
+    if (type == HIVED_EV_SCHEDULE || type == EV_SCHEDULE_ONLY) {
+      const hived_pod_spec_t& sp = ev.spec;
+      rc = validateSpec(sp);
+      if (rc == 0) rc = schedule(sp, ev.phase, res);
+      if (rc == 0 && type == HIVED_EV_SCHEDULE && res->kind == HIVED_KIND_BIND) {
+        // the filterRoutine sequence: AddAllocatedPod with the PodBindInfo just produced
+        BindView b;
+        b.node = res->node; b.first_leaf = pool[res->this_off + 1]; b.chain = res->chain; b.has_preassigned = 1;
+        b.n_members = res->n_members; b.member_leaf_num = res->member_leaf_num; b.member_pod_num = res->member_pod_num;
+        b.leaves = pool + res->leaf_off;
+        sugg = nullptr;
+        long long ta0 = hv_clock();
+        addAllocatedPod(sp, b, getAllocatedPodIndex(b, sp.leaf_num));
+        stat_add(ST_CYC_COMMIT, hv_clock() - ta0);
+        rc = panicCode;
+      }
+    } else if (type == EV_ADD_ALLOCATED) {
+      const hived_bind_info_t* bi = reinterpret_cast<const hived_bind_info_t*>(aux);
+      BindView b;
+      b.node = bi->node; b.first_leaf = bi->first_leaf; b.chain = bi->chain; b.has_preassigned = bi->has_preassigned;
+      b.n_members = bi->n_members; b.member_leaf_num = bi->member_leaf_num; b.member_pod_num = bi->member_pod_num;
+      b.leaves = aux + sizeof(hived_bind_info_t) / 4;
+      rc = validateSpec(ev.spec);
+      if (rc == 0) { addAllocatedPod(ev.spec, b, ev.arg0); rc = panicCode; }
+    } else if (type == HIVED_EV_DELETE_ALLOCATED) {
+      long long td0 = hv_clock();
+      deleteAllocatedPod(ev.spec.group, ev.spec.leaf_num, ev.arg0);
+      stat_add(ST_CYC_DELETE, hv_clock() - td0);
+      rc = panicCode;
+    } else if (type == HIVED_EV_DELETE_UNALLOCATED) {
+      deleteUnallocatedPod(ev.spec.group, ev.spec.pod);
+      rc = panicCode;
+    } else if (type == HIVED_EV_NODE_HEALTH) {
+      setNodeHealth(ev.arg0, ev.arg1 != 0);
+      rc = panicCode;
+    } else {
+      rc = HIVED_ERR_PLATFORM;
+    }
+    ST(res->error, rc);
+    stat_add(ST_CYC_TOTAL, hv_clock() - tev0);
+  }
+
   // NewHivedAlgorithm's dynamic part: initPinnedCells + initBadNodes (hived_algorithm.go:437-464)
   HIVED_DEV_NOINLINE void initState(const int32_t* pinnedOrder, int nPinnedOrder, const int32_t* badOrder, int nBad) {
-    HV_ST(&sm->panic, 0);
+    panicCode = 0;
     sugg = nullptr;
     for (int i = 0; i < nPinnedOrder; i++) {
       int pi = pinnedOrder[i];
@@ -1992,9 +2101,19 @@ struct Core {
   HIVED_DEV void run(const hived_event_t* events, int n, hived_result_t* results, const uint32_t* suggPool, const int32_t* aux,
                      const int32_t* initLists, int nPinnedOrder, int nBad) {
     if (hv_warp() == 0) {
-      if (initLists) initState(initLists, nPinnedOrder, initLists + nPinnedOrder, nBad);
+      poolOff = sm->pool_off;
+      int initPanic = 0;
+      if (initLists) { initState(initLists, nPinnedOrder, initLists + nPinnedOrder, nBad); initPanic = panicCode; }
       for (int i = 0; i < n; i++) processEvent(events[i], &results[i], suggPool, aux);
-      HV_ST(&sm->cmd, CMD_EXIT);
+      // flush the work counters
+      for (int i = 0; i < ST_COUNT; i++) {
+        long long v = d.stats[i];
+        hv_warp_sync();
+        if (i == ST_PRIO_MASK) ST(d.stats[i], v | acc[i]); else ST(d.stats[i], v + acc[i]);
+      }
+      ST(sm->pool_off, poolOff);
+      ST(sm->panic, initPanic);
+      ST(sm->cmd, CMD_EXIT);
       hv_cta_sync();
     } else {
       while (true) {

@@ -10,7 +10,7 @@ namespace hived {
 // X(name): static int32 array copied verbatim from FlatTopo::name
 #define HIVED_STATIC_ARRAYS(X)                                                                         \
   X(p_parent) X(p_child0) X(p_nchild) X(p_level) X(p_chain) X(p_leaf0) X(p_nleaf) X(p_node)           \
-  X(p_leafidx) X(p_flags) X(p_nodes_off) X(p_nodes_cnt) X(nodes_flat)                                  \
+  X(p_leafidx) X(p_flags) X(p_nodes_off) X(p_nodes_cnt) X(nodes_flat) X(p_anc) X(v_anc)                                \
   X(v_parent) X(v_child0) X(v_nchild) X(v_level) X(v_chain) X(v_leaf0) X(v_nleaf) X(v_vc) X(v_pre)    \
   X(v_vset) X(v_flags)                                                                                 \
   X(chain_top) X(chain_leaftype) X(chain_lvl_type) X(chain_lvl_leafnum) X(chain_lvl_nchild)           \
@@ -54,7 +54,7 @@ namespace hived {
 struct DevSizes {
   int32_t NP, NV, nChains, nVCs, nLeafTypes, nPinned, nNodes, nVsets, nScheds;
   int32_t flTotal, dmTotal, cvTotal, maxGroups, maxPods, LS, PS, VX, LZ;
-  int32_t maxLevelCount, maxViewN, bitmapWords, maxLevels, maxNodeLeaves;
+  int32_t maxLevelCount, maxViewN, bitmapWords, maxLevels, maxNodeLeaves, AS;
 };
 
 struct Dev {

@@ -40,6 +40,8 @@ struct FlatTopo {
   // ---- physical cells [NP]
   std::vector<int32_t> p_parent, p_child0, p_nchild, p_level, p_chain, p_leaf0, p_nleaf, p_node, p_leafidx, p_flags;
   std::vector<int32_t> p_nodes_off, p_nodes_cnt, nodes_flat;  // node ids below a cell
+  std::vector<int32_t> p_anc, v_anc;                          // [N * AS] ancestor per level
+  int32_t AS = 1;
   // ---- virtual cells [NV]
   std::vector<int32_t> v_parent, v_child0, v_nchild, v_level, v_chain, v_leaf0, v_nleaf, v_vc, v_pre, v_vset, v_flags;
 
@@ -405,6 +407,15 @@ inline FlatTopo buildTopo(const std::string& text) {
       nm = ce->child; ce = &nit->second;
     }
   }
+  // ancestor tables: anc[cell * AS + l] = the ancestor of `cell` at level l (the cell itself at its own
+  // level, -1 below it or above its tree's top) — turns every leaf-to-root walk into independent loads
+  T.AS = T.maxLevels + 1;
+  T.p_anc.assign((size_t)std::max(1, T.NP) * T.AS, -1);
+  for (int32_t i = 0; i < T.NP; i++)
+    for (int32_t c = i; c >= 0; c = T.p_parent[c]) T.p_anc[(size_t)i * T.AS + T.p_level[c]] = c;
+  T.v_anc.assign((size_t)std::max(1, T.NV) * T.AS, -1);
+  for (int32_t i = 0; i < T.NV; i++)
+    for (int32_t c = i; c >= 0; c = T.v_parent[c]) T.v_anc[(size_t)i * T.AS + T.v_level[c]] = c;
   T.lt_off.assign(T.nLeafTypes, 0); T.lt_cnt.assign(T.nLeafTypes, 0);
   for (int32_t lt = 0; lt < T.nLeafTypes; lt++) {
     T.lt_off[lt] = (int32_t)T.lt_chains.size();
