@@ -196,19 +196,12 @@ struct Core {
   // ======================================================================================
   // utils.go:381-391
   HIVED_DEV bool inFreeCellList(int c) const {
-    // walking up from c: false at the first bound-or-split cell, true at the first cell whose parent is
-    // absent or split, whichever comes first (the false test is made first at every level)
-    int lc = d.p_level[c];
-    unsigned falseMask = levelMask(lc, AS, [&](int l) { int a = d.p_anc[c * AS + l]; return a >= 0 && (d.p_vcell[a] >= 0 || d.p_split[a]); });
-    unsigned trueMask = levelMask(lc, AS, [&](int l) {
-      int a = d.p_anc[c * AS + l];
-      if (a < 0) return false;
-      int par = (l + 1 < AS) ? d.p_anc[c * AS + l + 1] : -1;
-      return par < 0 || d.p_split[par] != 0;
-    });
-    if (!trueMask) return false;
-    int ft = hv_ffs(trueMask), ff = falseMask ? hv_ffs(falseMask) : 99;
-    return ft < ff;
+    while (true) {
+      if (d.p_vcell[c] >= 0 || d.p_split[c]) return false;
+      int par = d.p_parent[c];
+      if (par < 0 || d.p_split[par]) return true;
+      c = par;
+    }
   }
   // cell.go:195-204 + utils.go:397-415.  Used propagates unconditionally: one gather over the levels.
   HIVED_DEV void setCellState(int c, int s) {
@@ -242,11 +235,11 @@ struct Core {
   // ancestor independently, because a parent's priority is the max of its children's.
   template <bool V>
   HIVED_DEV void setPriority(int c, int p) {
-    struct { const Dev& d; HIVED_DEV int32_t& operator[](int i) const { return V ? d.v_prio[i] : d.p_prio[i]; } } prio{d};
-    struct { const Dev& d; HIVED_DEV int operator[](int i) const { return V ? d.v_parent[i] : d.p_parent[i]; } } parent{d};
-    struct { const Dev& d; HIVED_DEV int operator[](int i) const { return V ? d.v_child0[i] : d.p_child0[i]; } } child0{d};
-    struct { const Dev& d; HIVED_DEV int operator[](int i) const { return V ? d.v_nchild[i] : d.p_nchild[i]; } } nchild{d};
+    int32_t* prio = V ? d.v_prio : d.p_prio;
     const int32_t* anc = V ? d.v_anc : d.p_anc;
+    const int32_t* parent = V ? d.v_parent : d.p_parent;
+    const int32_t* child0 = V ? d.v_child0 : d.p_child0;
+    const int32_t* nchild = V ? d.v_nchild : d.p_nchild;
     if (p > prio[c]) {
       for (int b = 0; b < AS; b += HIVED_WARPSZ) {
         int l = b + lane;
@@ -643,17 +636,18 @@ struct Core {
   // info word of a view node: free(8b) | usedSame(8b)<<8 | usedHigher(8b)<<16 | healthy<<24 | suggested<<25
   HIVED_DEV int viewNodeInfo(int cell, bool isVirtual, bool cross, int p, bool ignoreSuggested) const {
     int leaf0, nleaf, healthy = 1, suggested = 1;
+    const int32_t* prio;
     if (isVirtual) {
-      leaf0 = d.v_leaf0[cell]; nleaf = d.v_nleaf[cell];
+      leaf0 = d.v_leaf0[cell]; nleaf = d.v_nleaf[cell]; prio = d.v_prio;
       int pc = d.v_pcell[cell];
       if (pc >= 0) { healthy = d.p_healthy[pc]; suggested = ignoreSuggested || node_suggested(d.p_node[pc]); }
     } else {
-      leaf0 = d.p_leaf0[cell]; nleaf = d.p_nleaf[cell];
+      leaf0 = d.p_leaf0[cell]; nleaf = d.p_nleaf[cell]; prio = d.p_prio;
       healthy = d.p_healthy[cell]; suggested = ignoreSuggested || node_suggested(d.p_node[cell]);
     }
     int same = 0, higher = 0, ge = 0;
     for (int i = 0; i < nleaf; i++) {
-      int q = isVirtual ? d.v_prio[leaf0 + i] : d.p_prio[leaf0 + i];
+      int q = prio[leaf0 + i];
       if (q < OPP_PRIO) continue;  // free leaf
       if (q == p) same++;
       else if (cross) same++;
@@ -843,7 +837,7 @@ struct Core {
       // getLeafCellsFromNode :464-476: free leaves in DFS order, then preemptible ones (ballot compaction)
       int leaf0 = V ? d.v_leaf0[node] : d.p_leaf0[node];
       int nleaf = V ? d.v_nleaf[node] : d.p_nleaf[node];
-      struct { const Dev& d; HIVED_DEV int operator[](int i) const { return V ? d.v_prio[i] : d.p_prio[i]; } } prio{d};
+      const int32_t* prio = V ? d.v_prio : d.p_prio;
       int n = 0;
       for (int b = 0; b < nleaf; b += HIVED_WARPSZ) {
         int i = b + lane;
@@ -1403,11 +1397,8 @@ struct Core {
       if (pLeaf < 0) continue;
       ST(d.p_using[pLeaf], -1);
       if (d.p_state[pLeaf] == HIVED_CELL_USED) {
-        long long q0 = hv_clock();
         releaseLeafCell(pLeaf, vc);
-        long long q1 = hv_clock(); stat_add(ST_DBG0 + 5, q1 - q0);
         setCellState(pLeaf, HIVED_CELL_FREE);
-        stat_add(ST_DBG0 + 6, hv_clock() - q1);
       } else {
         setCellState(pLeaf, HIVED_CELL_RESERVED);
       }
@@ -1491,7 +1482,6 @@ struct Core {
     int nleaves;
   };
   int lzCount;
-  bool freshPlacement;  // the last schedule() produced its placement in pl_p/pl_v (new group)
 
   // hived_algorithm.go:944-965
   HIVED_DEV void tryLazyPreempt(const int32_t* vleaves, int nleaves) {
@@ -1530,9 +1520,7 @@ struct Core {
     long long tm0 = hv_clock();
     tryLazyPreempt(d.pl_v, r.nleaves);
     if (panicCode) return false;
-    long long qb0 = hv_clock();
     toBindingPaths(d.pl_v, r.nleaves);
-    stat_add(ST_DBG0 + 7, hv_clock() - qb0);
     if (panicCode) return false;
     bool mapped = mapVirtualPlacementToPhysical(r.chain, r.ignoreSuggested);
     stat_add(ST_CYC_MAP, hv_clock() - tm0);
@@ -1796,7 +1784,6 @@ struct Core {
     const int32_t* member_leaf_num;
     const int32_t* member_pod_num;
     const int32_t* leaves;  // triples
-    const int32_t* physIds;  // optional: the physical leaf cells themselves (auto-commit of a fresh placement)
   };
 
   // utils.go:291-304
@@ -1835,9 +1822,7 @@ struct Core {
         int node = b.leaves[3 * k];
         for (int li = 0; li < leafNumber; li++, k++) {
           // findAllocatedLeafCell :1224-1290
-          long long q0 = hv_clock();
-          int pLeaf = b.physIds ? b.physIds[k] : findPhysicalLeafCell(b.chain, node, b.leaves[3 * k + 1]);
-          long long q1 = hv_clock(); stat_add(ST_DBG0 + 0, q1 - q0);
+          int pLeaf = findPhysicalLeafCell(b.chain, node, b.leaves[3 * k + 1]);
           if (pLeaf < 0) continue;  // not found in the spec: ignored
           int vLeaf = -1;
           int lazy = 1;  // 0 nil, 1 false, 2 true
@@ -1861,7 +1846,6 @@ struct Core {
               lazy = 0;
             }
           }
-          long long q2 = hv_clock(); stat_add(ST_DBG0 + 1, q2 - q1);
           if (gm < 0 || podIndex >= gmPods) { panic(HIVED_ERR_PLATFORM); return; }  // index out of range
           int slot = leafOff + podIndex * leafNumber + li;
           ST(ph[slot], pLeaf);
@@ -1873,12 +1857,9 @@ struct Core {
           } else {
             shouldLazyPreempt = shouldLazyPreempt || lazy == 2;
           }
-          long long q3 = hv_clock(); stat_add(ST_DBG0 + 2, q3 - q2);
           bool safetyOk = allocateLeafCell(pLeaf, vLeaf, sp.priority, sp.vc);
-          long long q4 = hv_clock(); stat_add(ST_DBG0 + 3, q4 - q3);
           ST(d.p_using[pLeaf], g);
           setCellState(pLeaf, HIVED_CELL_USED);
-          stat_add(ST_DBG0 + 4, hv_clock() - q4);
           if (!safetyOk) shouldLazyPreempt = true;
           if (panicCode) return;
         }
@@ -1943,7 +1924,6 @@ struct Core {
     int nmem = 0, memLeaf[HIVED_MAX_MEMBERS], memPods[HIVED_MAX_MEMBERS];
     int podIndex = 0, reason = 0, rcell = -1;
     bool victimsCollected = false;
-    freshPlacement = false;
     if (d.g_state[g] != HIVED_GROUP_NONE) {
       // schedulePodFromExistingGroup :655-712
       int nl = groupLeaves(g);
@@ -1989,7 +1969,7 @@ struct Core {
       for (int m = 0; m < nmem; m++) { memLeaf[m] = r.memLeaf[m]; memPods[m] = r.memPods[m]; }
       podIndex = 0;
       if (rc == 1) {
-        havePlacement = true; phys = d.pl_p; virt = d.pl_v; freshPlacement = true;
+        havePlacement = true; phys = d.pl_p; virt = d.pl_v;
         int nOverlap;
         collectPreemptionVictims(phys, r.nleaves, res, nOverlap);
         victimsCollected = true;
@@ -2073,8 +2053,6 @@ struct Core {
         b.node = res->node; b.first_leaf = pool[res->this_off + 1]; b.chain = res->chain; b.has_preassigned = 1;
         b.n_members = res->n_members; b.member_leaf_num = res->member_leaf_num; b.member_pod_num = res->member_pod_num;
         b.leaves = pool + res->leaf_off;
-        // a fresh placement's cells are known; (node, index) identifies them uniquely when S.directLeaf
-        b.physIds = (d.S.directLeaf && freshPlacement) ? d.pl_p : nullptr;
         sugg = nullptr;
         long long ta0 = hv_clock();
         addAllocatedPod(sp, b, getAllocatedPodIndex(b, sp.leaf_num));
@@ -2087,7 +2065,6 @@ struct Core {
       b.node = bi->node; b.first_leaf = bi->first_leaf; b.chain = bi->chain; b.has_preassigned = bi->has_preassigned;
       b.n_members = bi->n_members; b.member_leaf_num = bi->member_leaf_num; b.member_pod_num = bi->member_pod_num;
       b.leaves = aux + sizeof(hived_bind_info_t) / 4;
-      b.physIds = nullptr;
       rc = validateSpec(ev.spec);
       if (rc == 0) { addAllocatedPod(ev.spec, b, ev.arg0); rc = panicCode; }
     } else if (type == HIVED_EV_DELETE_ALLOCATED) {

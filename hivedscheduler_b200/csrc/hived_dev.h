@@ -1,56 +1,18 @@
 // Device-resident state of the B200-native HiveD scheduling path: one POD struct of raw pointers
-// into HBM (see DESIGN.md "Data layout").  Static arrays come from FlatTopo (hived_topo.hpp);
-// mutable arrays are the scheduler state that the reference keeps in its pointer forest
-// (pkg/algorithm/cell.go:58-142,315-324; hived_algorithm.go:40-105).
-//
-// Per-cell fields are packed into 16/32-byte records (one 32 B sector per cell) because the
-// sequential part of a decision is bound by L2 round trips, not by bytes: a walk that needs the
-// priority, state, binding and health of a cell must pay one miss, not four.  The records are
-// accessed through the Fld<> proxies below, so the program text reads d.p_state[cell].
+// into HBM (flat int32 SoA, see DESIGN.md "Data layout").  Static arrays come from FlatTopo
+// (hived_topo.hpp); mutable arrays are the scheduler state that the reference keeps in its
+// pointer forest (pkg/algorithm/cell.go:58-142,315-324; hived_algorithm.go:40-105).
 #pragma once
 #include <cstdint>
 
-#if defined(__CUDACC__)
-#define HIVED_HD __host__ __device__ __forceinline__
-#else
-#define HIVED_HD inline
-#endif
-
 namespace hived {
-
-// field OFF of int32 records of STRIDE words
-template <int STRIDE, int OFF>
-struct Fld {
-  int32_t* b;
-  HIVED_HD int32_t& operator[](long long i) const { return b[i * STRIDE + OFF]; }
-};
-
-// ---- packed per-cell records: name, stride, then the fields in word order
-//   pS  (static, 8 words)  : parent child0 nchild level chain leaf0 nleaf node
-//   pS2 (static, 4 words)  : leafidx flags nodes_off nodes_cnt
-//   pD  (mutable, 8 words) : prio state vcell healthy split using resv usedopp
-//   pD2 (mutable, 4 words) : flpos bfpos dmpos dmvc
-//   vS  (static, 8 words)  : parent child0 nchild level chain leaf0 nleaf pre
-//   vS2 (static, 4 words)  : vc vset flags -
-//   vD  (mutable, 4 words) : prio state pcell healthy
-#define HIVED_PACKED_FIELDS(F)                                                                          \
-  F(pS, 8, 0, p_parent) F(pS, 8, 1, p_child0) F(pS, 8, 2, p_nchild) F(pS, 8, 3, p_level)                \
-  F(pS, 8, 4, p_chain) F(pS, 8, 5, p_leaf0) F(pS, 8, 6, p_nleaf) F(pS, 8, 7, p_node)                    \
-  F(pS2, 4, 0, p_leafidx) F(pS2, 4, 1, p_flags) F(pS2, 4, 2, p_nodes_off) F(pS2, 4, 3, p_nodes_cnt)     \
-  F(pD, 8, 0, p_prio) F(pD, 8, 1, p_state) F(pD, 8, 2, p_vcell) F(pD, 8, 3, p_healthy)                  \
-  F(pD, 8, 4, p_split) F(pD, 8, 5, p_using) F(pD, 8, 6, p_resv) F(pD, 8, 7, p_usedopp)                  \
-  F(pD2, 4, 0, p_flpos) F(pD2, 4, 1, p_bfpos) F(pD2, 4, 2, p_dmpos) F(pD2, 4, 3, p_dmvc)                \
-  F(vS, 8, 0, v_parent) F(vS, 8, 1, v_child0) F(vS, 8, 2, v_nchild) F(vS, 8, 3, v_level)                \
-  F(vS, 8, 4, v_chain) F(vS, 8, 5, v_leaf0) F(vS, 8, 6, v_nleaf) F(vS, 8, 7, v_pre)                     \
-  F(vS2, 4, 0, v_vc) F(vS2, 4, 1, v_vset) F(vS2, 4, 2, v_flags)                                         \
-  F(vD, 4, 0, v_prio) F(vD, 4, 1, v_state) F(vD, 4, 2, v_pcell) F(vD, 4, 3, v_healthy)
-
-// R(record, stride, isPhysical, isMutable)
-#define HIVED_RECORDS(R) R(pS, 8, 1, 0) R(pS2, 4, 1, 0) R(pD, 8, 1, 1) R(pD2, 4, 1, 1) R(vS, 8, 0, 0) R(vS2, 4, 0, 0) R(vD, 4, 0, 1)
 
 // X(name): static int32 array copied verbatim from FlatTopo::name
 #define HIVED_STATIC_ARRAYS(X)                                                                         \
-  X(nodes_flat) X(p_anc) X(v_anc)                                                                      \
+  X(p_parent) X(p_child0) X(p_nchild) X(p_level) X(p_chain) X(p_leaf0) X(p_nleaf) X(p_node)           \
+  X(p_leafidx) X(p_flags) X(p_nodes_off) X(p_nodes_cnt) X(nodes_flat) X(p_anc) X(v_anc)                                \
+  X(v_parent) X(v_child0) X(v_nchild) X(v_level) X(v_chain) X(v_leaf0) X(v_nleaf) X(v_vc) X(v_pre)    \
+  X(v_vset) X(v_flags)                                                                                 \
   X(chain_top) X(chain_leaftype) X(chain_lvl_type) X(chain_lvl_leafnum) X(chain_lvl_nchild)           \
   X(p_lvl_base) X(p_lvl_cnt) X(chain_in_vc) X(lt_off) X(lt_cnt) X(lt_chains)                           \
   X(vs_vc) X(vs_chain) X(vs_pinned) X(vs_top) X(v_lvl_base) X(v_lvl_cnt) X(vc_chain_vset)             \
@@ -61,6 +23,10 @@ struct Fld {
 // Y(name, count, init): mutable int32 array of `count` elements filled with `init`
 // (count expressions may use the Dev size fields through `S.`)
 #define HIVED_MUTABLE_ARRAYS(Y)                                                                        \
+  Y(p_prio, S.NP, -2) Y(p_state, S.NP, 0) Y(p_healthy, S.NP, 1) Y(p_vcell, S.NP, -1) Y(p_split, S.NP, 0) \
+  Y(p_using, S.NP, -1) Y(p_resv, S.NP, -1) Y(p_usedopp, S.NP, 0) Y(p_flpos, S.NP, -1)                  \
+  Y(p_bfpos, S.NP, -1) Y(p_dmpos, S.NP, -1) Y(p_dmvc, S.NP, -1)                                        \
+  Y(v_prio, S.NV, -2) Y(v_state, S.NV, 0) Y(v_healthy, S.NV, 1) Y(v_pcell, S.NV, -1)                   \
   Y(vcFree, S.nVCs * S.nChains * MAXL, 0) Y(allVCFree, S.nChains * MAXL, 0)                            \
   Y(totalLeft, S.nChains * MAXL, 0) Y(allVCDoomed, S.nChains * MAXL, 0)                                \
   Y(fl_data, S.flTotal, -1) Y(fl_len, S.nChains * MAXL, 0) Y(bf_data, S.flTotal, -1)                   \
@@ -81,41 +47,34 @@ struct Fld {
   Y(pod_need, S.PS, 0) Y(pod_pos, S.PS, -1) Y(pod_cell, S.PS, -1)                                      \
   Y(mc0, S.maxLevelCount + MAX_FANOUT, -1) Y(mcbuf, MAXL * MAX_FANOUT, -1)                             \
   Y(mcpick, MAXL * MAX_FANOUT, 0) Y(mccells, MAXL * MAX_FANOUT, -1)                                    \
-  Y(lz_group, S.LS, -1) Y(lz_save, (int64_t)S.LZ * (S.LS + 1), -1) Y(ba_buf, (int64_t)MAXL * S.maxLevelCount, -1) \
+  Y(lz_group, S.LS, -1) Y(lz_save, (int64_t)S.LZ * (S.LS + 1), -1) Y(ba_buf, (int64_t)MAXL * S.maxLevelCount, -1)                                           \
   Y(tmp_list, S.maxLevelCount + MAX_FANOUT, -1)                                                        \
   Y(vw_cell, S.maxViewN, -1) Y(vw_info, S.maxViewN, 0) Y(vw_ordA, S.maxViewN, 0) Y(vw_ordB, S.maxViewN, 0)
 
 struct DevSizes {
   int32_t NP, NV, nChains, nVCs, nLeafTypes, nPinned, nNodes, nVsets, nScheds;
   int32_t flTotal, dmTotal, cvTotal, maxGroups, maxPods, LS, PS, VX, LZ;
-  int32_t maxLevelCount, maxViewN, bitmapWords, maxLevels, maxNodeLeaves, AS, directLeaf;
+  int32_t maxLevelCount, maxViewN, bitmapWords, maxLevels, maxNodeLeaves, AS;
 };
 
 struct Dev {
   DevSizes S;
-#define R(rec, stride, isP, isMut) int32_t* rec;
-  HIVED_RECORDS(R)
-#undef R
-#define F(rec, stride, off, name) Fld<stride, off> name;
-  HIVED_PACKED_FIELDS(F)
-#undef F
 #define X(name) const int32_t* name;
   HIVED_STATIC_ARRAYS(X)
 #undef X
 #define Y(name, count, init) int32_t* name;
   HIVED_MUTABLE_ARRAYS(Y)
 #undef Y
-  long long* stats;   // [ST_COUNT] counters, see ST_* below
+  long long* stats;   // [16] counters, see ST_* below
   int32_t* epoch;     // [1] stamp for vx_stamp
 };
 
 enum {
   ST_VIEW_NODES = 0, ST_LEAVES = 1, ST_FREE_CELLS = 2, ST_PODS = 3, ST_SCHEDULE = 4, ST_BIND = 5, ST_WAIT = 6,
-  ST_PREEMPT = 7, ST_PRIO_MASK = 8 /* bit (p+1) for small priorities, else bit 62 */,
+  ST_PREEMPT = 7, ST_PRIO_MASK = 8 /* bit (p+1) for small priorities, else bit 63 */,
   /* SM cycles spent per phase (leader warp), for profiles/ */
   ST_CYC_VIEW = 9, ST_CYC_LEAF = 10, ST_CYC_MAP = 11, ST_CYC_EMIT = 12, ST_CYC_COMMIT = 13, ST_CYC_DELETE = 14, ST_CYC_TOTAL = 15,
-  ST_DBG0 = 16, /* 8 scratch cycle counters for profiling sessions */
-  ST_COUNT = 24
+  ST_COUNT = 16
 };
 
 // group flags

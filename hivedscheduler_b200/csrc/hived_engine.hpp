@@ -7,7 +7,6 @@
 #pragma once
 #include <cstdio>
 #include <cstring>
-#include <map>
 #include <memory>
 #include <string>
 #include <vector>
@@ -109,58 +108,10 @@ struct Engine {
     S.maxGroups = opt.max_groups; S.maxPods = opt.max_pods; S.LS = opt.max_group_leaves; S.PS = opt.max_group_pods;
     S.VX = S.LS * MAXL + 16; S.LZ = S.LS < 64 ? S.LS : 64;
     S.maxLevelCount = T.maxLevelCount; S.maxViewN = T.maxViewN; S.bitmapWords = (T.nNodes + 31) / 32;
-    S.maxLevels = T.maxLevels; S.maxNodeLeaves = T.maxNodeLeaves; S.AS = T.AS; S.directLeaf = T.uniqueLeafIdx ? 1 : 0;
+    S.maxLevels = T.maxLevels; S.maxNodeLeaves = T.maxNodeLeaves; S.AS = T.AS;
 #define X(name) dev.name = uploadStatic(T.name);
     HIVED_STATIC_ARRAYS(X)
 #undef X
-    // packed per-cell records (hived_dev.h): build the host images, upload, wire the field proxies
-    {
-      std::map<std::string, const std::vector<int32_t>*> statics = {
-          {"p_parent", &T.p_parent}, {"p_child0", &T.p_child0}, {"p_nchild", &T.p_nchild}, {"p_level", &T.p_level},
-          {"p_chain", &T.p_chain}, {"p_leaf0", &T.p_leaf0}, {"p_nleaf", &T.p_nleaf}, {"p_node", &T.p_node},
-          {"p_leafidx", &T.p_leafidx}, {"p_flags", &T.p_flags}, {"p_nodes_off", &T.p_nodes_off}, {"p_nodes_cnt", &T.p_nodes_cnt},
-          {"v_parent", &T.v_parent}, {"v_child0", &T.v_child0}, {"v_nchild", &T.v_nchild}, {"v_level", &T.v_level},
-          {"v_chain", &T.v_chain}, {"v_leaf0", &T.v_leaf0}, {"v_nleaf", &T.v_nleaf}, {"v_pre", &T.v_pre},
-          {"v_vc", &T.v_vc}, {"v_vset", &T.v_vset}, {"v_flags", &T.v_flags}};
-      std::map<std::string, int32_t> inits = {
-          {"p_prio", -2}, {"p_state", 0}, {"p_vcell", -1}, {"p_healthy", 1}, {"p_split", 0}, {"p_using", -1}, {"p_resv", -1},
-          {"p_usedopp", 0}, {"p_flpos", -1}, {"p_bfpos", -1}, {"p_dmpos", -1}, {"p_dmvc", -1},
-          {"v_prio", -2}, {"v_state", 0}, {"v_pcell", -1}, {"v_healthy", 1}};
-      std::map<std::string, std::vector<int32_t>> img;
-#define R(rec, stride, isP, isMut) img[#rec].assign((size_t)std::max(1, (isP) ? T.NP : T.NV) * (stride), 0);
-      HIVED_RECORDS(R)
-#undef R
-      auto setField = [&](std::vector<int32_t>& im, int stride, int off, const char* name) {
-        size_t n = im.size() / stride;
-        auto sit = statics.find(name);
-        if (sit != statics.end()) {
-          for (size_t i = 0; i < sit->second->size() && i < n; i++) im[i * stride + off] = (*sit->second)[i];
-        } else {
-          int32_t v = inits.at(name);
-          for (size_t i = 0; i < n; i++) im[i * stride + off] = v;
-        }
-      };
-#define F(rec, stride, off, name) setField(img[#rec], stride, off, #name);
-      HIVED_PACKED_FIELDS(F)
-#undef F
-      // the initial free lists (top-level cells) give the initial positions
-      for (int c = 0; c < T.nChains; c++)
-        for (int l = 1; l < MAXL; l++)
-          for (int i = 0; i < T.fl_init_len[c * MAXL + l]; i++) img["pD2"][(size_t)T.fl_init_data[T.fl_base[c * MAXL + l] + i] * 4 + 0] = i;
-#define R(rec, stride, isP, isMut)                                                        \
-  {                                                                                       \
-    std::vector<int32_t>& im = img[#rec];                                                 \
-    dev.rec = (int32_t*)bk_alloc(im.size() * 4);                                          \
-    bk_h2d(dev.rec, im.data(), im.size() * 4);                                            \
-    allocs.push_back(dev.rec);                                                            \
-    if (isMut) mutableRegions.push_back({dev.rec, im.size() * 4});                        \
-  }
-      HIVED_RECORDS(R)
-#undef R
-#define F(rec, stride, off, name) dev.name.b = dev.rec;
-      HIVED_PACKED_FIELDS(F)
-#undef F
-    }
 #define Y(name, count, init)                                                   \
   {                                                                            \
     size_t cnt_ = (size_t)(count);                                             \
@@ -179,6 +130,13 @@ struct Engine {
     bk_h2d(dev.totalLeft, T.totalLeft.data(), T.totalLeft.size() * 4);
     if (!T.fl_init_data.empty()) bk_h2d(dev.fl_data, T.fl_init_data.data(), T.fl_init_data.size() * 4);
     bk_h2d(dev.fl_len, T.fl_init_len.data(), T.fl_init_len.size() * 4);
+    {
+      std::vector<int32_t> flpos(T.NP ? T.NP : 1, -1);
+      for (int c = 0; c < T.nChains; c++)
+        for (int l = 1; l < MAXL; l++)
+          for (int i = 0; i < T.fl_init_len[c * MAXL + l]; i++) flpos[T.fl_init_data[T.fl_base[c * MAXL + l] + i]] = i;
+      bk_h2d(dev.p_flpos, flpos.data(), flpos.size() * 4);
+    }
     if (!T.cv_init.empty()) bk_h2d(dev.cv, T.cv_init.data(), T.cv_init.size() * 4);
     // initPinnedCells + initBadNodes run on the device
     std::vector<int32_t> init = T.pinned_init_order;
@@ -403,9 +361,9 @@ int hived_snapshot_physical(hived_ctx* ctx, hived_cell_status_t* out, int32_t ca
   hived::Engine& e = ctx->e;
   int n = e.T.NP;
   if (cap < n) return HIVED_ERR_CAPACITY;
-  std::vector<int32_t> rec, prio(n), state(n), healthy(n), vcell(n), split(n);
-  e.readArray(e.dev.pD, rec, (size_t)n * 8);
-  for (int i = 0; i < n; i++) { prio[i] = rec[i * 8 + 0]; state[i] = rec[i * 8 + 1]; vcell[i] = rec[i * 8 + 2]; healthy[i] = rec[i * 8 + 3]; split[i] = rec[i * 8 + 4]; }
+  std::vector<int32_t> prio, state, healthy, vcell, split, flpos;
+  e.readArray(e.dev.p_prio, prio, n); e.readArray(e.dev.p_state, state, n); e.readArray(e.dev.p_healthy, healthy, n);
+  e.readArray(e.dev.p_vcell, vcell, n); e.readArray(e.dev.p_split, split, n);
   for (int i = 0; i < n; i++) {
     out[i].priority = prio[i]; out[i].state = state[i]; out[i].healthy = healthy[i]; out[i].peer = vcell[i];
     out[i].level = e.T.p_level[i]; out[i].chain = e.T.p_chain[i]; out[i].parent = e.T.p_parent[i];
@@ -427,9 +385,9 @@ int hived_snapshot_virtual(hived_ctx* ctx, hived_cell_status_t* out, int32_t cap
   hived::Engine& e = ctx->e;
   int n = e.T.NV;
   if (cap < n) return HIVED_ERR_CAPACITY;
-  std::vector<int32_t> rec, prio(n), state(n), healthy(n), pcell(n);
-  e.readArray(e.dev.vD, rec, (size_t)n * 4);
-  for (int i = 0; i < n; i++) { prio[i] = rec[i * 4 + 0]; state[i] = rec[i * 4 + 1]; pcell[i] = rec[i * 4 + 2]; healthy[i] = rec[i * 4 + 3]; }
+  std::vector<int32_t> prio, state, healthy, pcell;
+  e.readArray(e.dev.v_prio, prio, n); e.readArray(e.dev.v_state, state, n); e.readArray(e.dev.v_healthy, healthy, n);
+  e.readArray(e.dev.v_pcell, pcell, n);
   for (int i = 0; i < n; i++) {
     out[i].priority = prio[i]; out[i].state = state[i]; out[i].healthy = healthy[i]; out[i].peer = pcell[i];
     out[i].level = e.T.v_level[i]; out[i].chain = e.T.v_chain[i]; out[i].parent = e.T.v_parent[i];
@@ -474,7 +432,7 @@ int hived_bench_flush_l2(hived_ctx*) { hived::bk_flush_l2(); return 0; }
 int hived_bench_phase_cycles(hived_ctx* ctx, int64_t* out) {
   long long st[hived::ST_COUNT];
   hived::bk_d2h(st, ctx->e.dev.stats, sizeof st);
-  for (int i = 0; i < 15; i++) out[i] = st[hived::ST_CYC_VIEW + i];
+  for (int i = 0; i < 7; i++) out[i] = st[hived::ST_CYC_VIEW + i];
   return 0;
 }
 double hived_bench_last_kernel_ms(hived_ctx* ctx) { return ctx->e.lastKernelMs; }
