@@ -1482,6 +1482,7 @@ struct Core {
     int nleaves;
   };
   int lzCount;
+  bool freshPlacement;  // the last schedule() produced its placement in pl_p/pl_v (new group)
 
   // hived_algorithm.go:944-965
   HIVED_DEV void tryLazyPreempt(const int32_t* vleaves, int nleaves) {
@@ -1784,6 +1785,7 @@ struct Core {
     const int32_t* member_leaf_num;
     const int32_t* member_pod_num;
     const int32_t* leaves;  // triples
+    const int32_t* physIds;  // optional: the physical leaf cells themselves (auto-commit of a fresh placement)
   };
 
   // utils.go:291-304
@@ -1822,7 +1824,7 @@ struct Core {
         int node = b.leaves[3 * k];
         for (int li = 0; li < leafNumber; li++, k++) {
           // findAllocatedLeafCell :1224-1290
-          int pLeaf = findPhysicalLeafCell(b.chain, node, b.leaves[3 * k + 1]);
+          int pLeaf = b.physIds ? b.physIds[k] : findPhysicalLeafCell(b.chain, node, b.leaves[3 * k + 1]);
           if (pLeaf < 0) continue;  // not found in the spec: ignored
           int vLeaf = -1;
           int lazy = 1;  // 0 nil, 1 false, 2 true
@@ -1924,6 +1926,7 @@ struct Core {
     int nmem = 0, memLeaf[HIVED_MAX_MEMBERS], memPods[HIVED_MAX_MEMBERS];
     int podIndex = 0, reason = 0, rcell = -1;
     bool victimsCollected = false;
+    freshPlacement = false;
     if (d.g_state[g] != HIVED_GROUP_NONE) {
       // schedulePodFromExistingGroup :655-712
       int nl = groupLeaves(g);
@@ -1969,7 +1972,7 @@ struct Core {
       for (int m = 0; m < nmem; m++) { memLeaf[m] = r.memLeaf[m]; memPods[m] = r.memPods[m]; }
       podIndex = 0;
       if (rc == 1) {
-        havePlacement = true; phys = d.pl_p; virt = d.pl_v;
+        havePlacement = true; phys = d.pl_p; virt = d.pl_v; freshPlacement = true;
         int nOverlap;
         collectPreemptionVictims(phys, r.nleaves, res, nOverlap);
         victimsCollected = true;
@@ -2053,6 +2056,8 @@ struct Core {
         b.node = res->node; b.first_leaf = pool[res->this_off + 1]; b.chain = res->chain; b.has_preassigned = 1;
         b.n_members = res->n_members; b.member_leaf_num = res->member_leaf_num; b.member_pod_num = res->member_pod_num;
         b.leaves = pool + res->leaf_off;
+        // a fresh placement's cells are known; (node, index) identifies them uniquely when S.directLeaf
+        b.physIds = (d.S.directLeaf && freshPlacement) ? d.pl_p : nullptr;
         sugg = nullptr;
         long long ta0 = hv_clock();
         addAllocatedPod(sp, b, getAllocatedPodIndex(b, sp.leaf_num));
@@ -2065,6 +2070,7 @@ struct Core {
       b.node = bi->node; b.first_leaf = bi->first_leaf; b.chain = bi->chain; b.has_preassigned = bi->has_preassigned;
       b.n_members = bi->n_members; b.member_leaf_num = bi->member_leaf_num; b.member_pod_num = bi->member_pod_num;
       b.leaves = aux + sizeof(hived_bind_info_t) / 4;
+      b.physIds = nullptr;
       rc = validateSpec(ev.spec);
       if (rc == 0) { addAllocatedPod(ev.spec, b, ev.arg0); rc = panicCode; }
     } else if (type == HIVED_EV_DELETE_ALLOCATED) {

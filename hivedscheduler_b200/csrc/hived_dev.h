@@ -54,7 +54,7 @@ namespace hived {
 struct DevSizes {
   int32_t NP, NV, nChains, nVCs, nLeafTypes, nPinned, nNodes, nVsets, nScheds;
   int32_t flTotal, dmTotal, cvTotal, maxGroups, maxPods, LS, PS, VX, LZ;
-  int32_t maxLevelCount, maxViewN, bitmapWords, maxLevels, maxNodeLeaves, AS;
+  int32_t maxLevelCount, maxViewN, bitmapWords, maxLevels, maxNodeLeaves, AS, directLeaf;
 };
 
 struct Dev {

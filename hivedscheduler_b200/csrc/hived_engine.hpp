@@ -108,7 +108,7 @@ struct Engine {
     S.maxGroups = opt.max_groups; S.maxPods = opt.max_pods; S.LS = opt.max_group_leaves; S.PS = opt.max_group_pods;
     S.VX = S.LS * MAXL + 16; S.LZ = S.LS < 64 ? S.LS : 64;
     S.maxLevelCount = T.maxLevelCount; S.maxViewN = T.maxViewN; S.bitmapWords = (T.nNodes + 31) / 32;
-    S.maxLevels = T.maxLevels; S.maxNodeLeaves = T.maxNodeLeaves; S.AS = T.AS;
+    S.maxLevels = T.maxLevels; S.maxNodeLeaves = T.maxNodeLeaves; S.AS = T.AS; S.directLeaf = T.uniqueLeafIdx ? 1 : 0;
 #define X(name) dev.name = uploadStatic(T.name);
     HIVED_STATIC_ARRAYS(X)
 #undef X

@@ -42,6 +42,7 @@ struct FlatTopo {
   std::vector<int32_t> p_nodes_off, p_nodes_cnt, nodes_flat;  // node ids below a cell
   std::vector<int32_t> p_anc, v_anc;                          // [N * AS] ancestor per level
   int32_t AS = 1;
+  bool uniqueLeafIdx = true;  // no two leaf cells of one (node, chain) share a leaf index
   // ---- virtual cells [NV]
   std::vector<int32_t> v_parent, v_child0, v_nchild, v_level, v_chain, v_leaf0, v_nleaf, v_vc, v_pre, v_vset, v_flags;
 
@@ -520,6 +521,8 @@ inline FlatTopo buildTopo(const std::string& text) {
     for (int32_t c = 0; c < T.nChains; c++)
       for (int32_t b : pLvl[c][1]) tmp[(size_t)P[b].nodes[0] * T.nChains + c].push_back(P[b].finalId);
     for (size_t k = 0; k < tmp.size(); k++) {
+      std::set<int32_t> seenIdx;
+      for (int32_t leaf : tmp[k]) if (!seenIdx.insert(T.p_leafidx[leaf]).second) T.uniqueLeafIdx = false;
       T.ncl_off[k] = (int32_t)T.ncl_list.size(); T.ncl_cnt[k] = (int32_t)tmp[k].size();
       T.ncl_list.insert(T.ncl_list.end(), tmp[k].begin(), tmp[k].end());
     }
