@@ -80,7 +80,8 @@ def bind_bench_hooks(lib):
         ("hived_bench_fetch_results", C.c_int, [P, C.POINTER(_cabi.Result), C.POINTER(C.c_int32), C.c_int64, C.POINTER(C.c_int64)]),
         ("hived_bench_flush_l2", C.c_int, [P]), ("hived_bench_phase_cycles", C.c_int, [P, C.POINTER(C.c_int64)]),
         ("hived_bench_last_kernel_ms", C.c_double, [P]),
-        ("hived_bench_total_kernel_ms", C.c_double, [P]), ("hived_bench_kernel_launches", C.c_int64, [P])]:
+        ("hived_bench_total_kernel_ms", C.c_double, [P]), ("hived_bench_kernel_launches", C.c_int64, [P]),
+        ("hived_bench_num_ctas", C.c_int, [P])]:
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
@@ -249,7 +250,7 @@ def main():
         "ms_per_step": 1e3 * kernel_total_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "events_per_step": int(len(ev)), "decisions_per_step": n_dec,
-                   "parallelism": "replicas" if world > 1 else "1 GPU", "l2": "flushed between steps (256 MiB memset)",
+                   "parallelism": ("replicas" if world > 1 else "1 GPU") + ", %d CTAs (one per group of VCs)" % lib.hived_bench_num_ctas(ctx), "l2": "flushed between steps (256 MiB memset)",
                    "timing": "CUDA events on the launch stream around the kernel; max over ranks",
                    "wall_ms_per_step_incl_state_rewind": 1e3 * wall / args.steps},
         "e2e": {"value": e2e_value, "unit": "decisions/s", "h2d_bytes_per_step": int(ev.nbytes),

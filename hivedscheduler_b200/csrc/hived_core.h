@@ -67,11 +67,42 @@ struct Core {
   const int lane;
   const int AS;
   long long acc[ST_COUNT];  // work counters, flushed to d.stats when the batch ends
+  Scratch s;                // this CTA's private scratch arrays
+  // ---- VC-parallel execution (several CTAs, one per group of VCs; see run())
+  const int cta, nCta;
+  const bool multi;
+  int curEvent;      // index (in the batch) of the event being processed
+  bool sharedHeld;   // this event already holds the right to touch the cluster-wide free-list state
 
-  HIVED_DEV Core(const Dev& dev, Sm* s, int32_t* pool_, long long cap)
-      : d(dev), sm(s), sugg(nullptr), pool(pool_), pool_cap(cap), poolOff(0), panicCode(0), lane(hv_lane()), AS(dev.S.AS) {
+  HIVED_DEV Core(const Dev& dev, Sm* s_, int32_t* pool_, long long cap, int nCta_)
+      : d(dev), sm(s_), sugg(nullptr), pool(pool_), pool_cap(cap), poolOff(0), panicCode(0), lane(hv_lane()), AS(dev.S.AS),
+        s(dev.scratch[hv_cta()]), cta(hv_cta()), nCta(nCta_), multi(nCta_ > 1), curEvent(0), sharedHeld(false) {
     for (int i = 0; i < ST_COUNT; i++) acc[i] = 0;
   }
+
+  // Multi-CTA ordering.  VCs are partitioned over the CTAs; an event only touches its VC's virtual
+  // tree and the physical cells bound into it, EXCEPT for the chain-wide free lists / counters used
+  // when a preassigned cell is bound or released.  Those sections run in batch order: a CTA enters
+  // one only when every other CTA is already working on a later event (so all earlier events are
+  // complete), and later events that need the shared state wait for this one the same way.
+  HIVED_DEV void sharedEnter() {
+    if (!multi || sharedHeld) return;
+    while (true) {
+      int mn = 0x7fffffff;
+      for (int b = 0; b < nCta; b += HIVED_WARPSZ) {
+        int i = b + lane;
+        if (i < nCta && i != cta) { int v = hv_ld_volatile(d.progress + i); if (v < mn) mn = v; }
+      }
+      for (int o = HIVED_WARPSZ / 2; o > 0; o >>= 1) { int t = hv_shfl_xor(mn, o); if (t < mn) mn = t; }
+      if (mn > curEvent) break;
+    }
+    hv_fence();  // acquire: drop stale L1 lines of state written by the other CTAs
+    sharedHeld = true;
+  }
+  // highest physical level an event of this VC may write: in multi-CTA mode the cells above the
+  // physical cell bound to the virtual leaf's preassigned cell are shared between VCs; their
+  // priority/state (never read by a decision) are re-derived after the batch (repairSharedAncestors)
+  HIVED_DEV int ceilOf(int vLeaf) const { return (multi && vLeaf >= 0) ? d.v_level[d.v_pre[vLeaf]] : AS; }
 
   // ======================================================================================
   // warp-level building blocks (leader warp; with HIVED_WARPSZ == 1 they degenerate to loops)
@@ -204,11 +235,11 @@ struct Core {
     }
   }
   // cell.go:195-204 + utils.go:397-415.  Used propagates unconditionally: one gather over the levels.
-  HIVED_DEV void setCellState(int c, int s) {
+  HIVED_DEV void setCellState(int c, int s, int ceil = 1 << 20) {
     if (s == HIVED_CELL_USED) {
       for (int b = 0; b < AS; b += HIVED_WARPSZ) {
         int l = b + lane;
-        if (l < AS) {
+        if (l < AS && l <= ceil) {
           int a = d.p_anc[c * AS + l];
           if (a >= 0) {
             d.p_state[a] = HIVED_CELL_USED;
@@ -225,7 +256,7 @@ struct Core {
       int vc = d.p_vcell[c];
       if (vc >= 0) ST(d.v_state[vc], s);
       int par = d.p_parent[c];
-      if (par < 0) return;
+      if (par < 0 || d.p_level[c] >= ceil) return;
       int c0 = d.p_child0[par], n = d.p_nchild[par];
       if (firstIdx(n, [&](int i) { return d.p_state[c0 + i] != s; }) >= 0) return;
       c = par;
@@ -234,7 +265,7 @@ struct Core {
   // cell_allocation.go:422-441.  A raise (p above the cell's priority) is max(old, p) on every
   // ancestor independently, because a parent's priority is the max of its children's.
   template <bool V>
-  HIVED_DEV void setPriority(int c, int p) {
+  HIVED_DEV void setPriority(int c, int p, int ceil = 1 << 20) {
     int32_t* prio = V ? d.v_prio : d.p_prio;
     const int32_t* anc = V ? d.v_anc : d.p_anc;
     const int32_t* parent = V ? d.v_parent : d.p_parent;
@@ -243,7 +274,7 @@ struct Core {
     if (p > prio[c]) {
       for (int b = 0; b < AS; b += HIVED_WARPSZ) {
         int l = b + lane;
-        if (l < AS) {
+        if (l < AS && l <= ceil) {
           int a = anc[c * AS + l];
           if (a >= 0 && prio[a] < p) prio[a] = p;
         }
@@ -255,7 +286,7 @@ struct Core {
       int orig = prio[c];
       ST(prio[c], p);
       int par = parent[c];
-      if (par < 0) return;
+      if (par < 0 || (V ? d.v_level[c] : d.p_level[c]) >= ceil) return;
       int pp = prio[par];
       if (p > pp) { c = par; continue; }
       if (orig == pp && p < orig) {
@@ -271,6 +302,7 @@ struct Core {
   // cell_allocation.go:443-454 — only the opportunistic count of physical cells is ever read back
   // (getUsablePhysicalCells :238-241); every other used[] value is recomputed from leaf priorities.
   HIVED_DEV void updateUsedOpp(int c, int delta) {
+    sharedEnter();  // the counts of the upper cells are read by every VC's buddy allocation
     for (int b = 0; b < AS; b += HIVED_WARPSZ) {
       int l = b + lane;
       if (l < AS) {
@@ -447,6 +479,7 @@ struct Core {
   }
   // hived_algorithm.go:1354-1427
   HIVED_DEV_NOINLINE bool allocatePreassignedCell(int c, int vc, bool doomedBad) {
+    sharedEnter();
     bool safetyOk = true;
     int chain = d.p_chain[c], level = d.p_level[c];
     int kv = vcl(vc, chain, level), k = cl(chain, level);
@@ -484,6 +517,7 @@ struct Core {
   }
   // hived_algorithm.go:1449-1485
   HIVED_DEV_NOINLINE void releasePreassignedCell(int c, int vc, bool doomedBad) {
+    sharedEnter();
     int chain = d.p_chain[c], level = d.p_level[c];
     int kv = vcl(vc, chain, level), k = cl(chain, level);
     ST(d.vcFree[kv], d.vcFree[kv] + 1);
@@ -576,6 +610,7 @@ struct Core {
   }
   // hived_algorithm.go:466-498: the leaves of a node, chain by chain, in level-1 list order
   HIVED_DEV void setNodeHealth(int node, bool healthy) {
+    if (multi) { panic(HIVED_ERR_PLATFORM); return; }  // the host never runs health events VC-parallel
     if (node < 0 || node >= d.S.nNodes) return;
     if (healthy) {
       if (!d.node_bad[node]) return;
@@ -602,7 +637,7 @@ struct Core {
     stat_add(ST_LEAVES, 1);
     if (vLeaf >= 0) {
       setPriority<true>(vLeaf, p);
-      setPriority<false>(pLeaf, p);
+      setPriority<false>(pLeaf, p, ceilOf(vLeaf));
       if (p == OPP_PRIO) updateUsedOpp(pLeaf, 1);
       int pac = d.v_pre[vLeaf];
       bool newlyBound = d.v_pcell[pac] < 0;
@@ -617,6 +652,7 @@ struct Core {
   HIVED_DEV void releaseLeafCell(int pLeaf, int vc) {
     stat_add(ST_LEAVES, 1);
     int vLeaf = d.p_vcell[pLeaf];
+    const int ceil = ceilOf(vLeaf);
     if (vLeaf >= 0) {
       setPriority<true>(vLeaf, FREE_PRIO);
       int pre = d.v_pre[vLeaf];
@@ -626,7 +662,7 @@ struct Core {
         releasePreassignedCell(preassignedPhysical, vc, false);
     }
     if (d.p_prio[pLeaf] == OPP_PRIO) updateUsedOpp(pLeaf, -1);
-    setPriority<false>(pLeaf, FREE_PRIO);
+    setPriority<false>(pLeaf, FREE_PRIO, ceil);
   }
 
   // ======================================================================================
@@ -697,7 +733,7 @@ struct Core {
     int lo = w * chunk, hi = lo + chunk < n ? lo + chunk : n;
     for (int base = lo; base < hi; base += HIVED_WARPSZ) {
       int i = base + lane;
-      int b = i < hi ? binOf(d.vw_info[in[i]]) : -1 - lane;  // inactive lanes get unique dummies
+      int b = i < hi ? binOf(s.vw_info[in[i]]) : -1 - lane;  // inactive lanes get unique dummies
       unsigned peers = hv_match(b);
       if (i < hi && (peers & hv_lanemask_lt()) == 0) sm->cnt[b * W + w] += hv_popc(peers);
       hv_warp_sync();
@@ -706,7 +742,7 @@ struct Core {
     ctaExclusiveScan(nbins * W);
     for (int base = lo; base < hi; base += HIVED_WARPSZ) {
       int i = base + lane;
-      int b = i < hi ? binOf(d.vw_info[in[i]]) : -1 - lane;
+      int b = i < hi ? binOf(s.vw_info[in[i]]) : -1 - lane;
       unsigned peers = hv_match(b);
       if (i < hi) {
         int rank = sm->cnt[b * W + w] + hv_popc(peers & hv_lanemask_lt());
@@ -730,14 +766,14 @@ struct Core {
     // 1. per-node keys from leaf priorities (coalesced int32 loads of contiguous leaf ranges)
     for (int i = tid; i < n; i += nth) {
       int cell = d.cv[off + i];
-      d.vw_cell[i] = cell;
-      d.vw_info[i] = viewNodeInfo(cell, isVirtual, cross, p, ignoreSuggested);
-      d.vw_ordA[i] = i;
+      s.vw_cell[i] = cell;
+      s.vw_info[i] = viewNodeInfo(cell, isVirtual, cross, p, ignoreSuggested);
+      s.vw_ordA[i] = i;
     }
     hv_cta_sync();
     // 2. stable sort by (healthy desc, suggested desc, usedSame desc, usedHigher asc): LSD passes
-    int32_t* cur = d.vw_ordA;
-    int32_t* nxt = d.vw_ordB;
+    int32_t* cur = s.vw_ordA;
+    int32_t* nxt = s.vw_ordB;
     if (!cross) {
       stablePass(cur, nxt, n, L + 1, [](int w) { return infoHigher(w); });
       int32_t* t = cur; cur = nxt; nxt = t;
@@ -749,15 +785,15 @@ struct Core {
     // 3. persist the new order (the reference sorts its slice in place) and lay the infos out in order
     for (int i = tid; i < n; i += nth) {
       int src = cur[i];
-      d.cv[off + i] = d.vw_cell[src];
-      nxt[i] = d.vw_info[src];
+      d.cv[off + i] = s.vw_cell[src];
+      nxt[i] = s.vw_info[src];
     }
     hv_cta_sync();
     const int32_t* sinfo = nxt;
     // 4. greedy first-fit (findNodesForPods :278-305); every thread tracks the same scalar state
     int nodeIndex = 0, picked = 0, ok = 1, reason = 0, rcell = -1;
     for (int k = 0; k < npods && ok; k++) {
-      int need = d.pod_need[k];
+      int need = s.pod_need[k];
       int found = -1;
       if (nodeIndex < n && infoFree(sinfo[nodeIndex]) - picked >= need) {
         found = nodeIndex;
@@ -785,7 +821,7 @@ struct Core {
       }
       nodeIndex = found;
       picked += need;
-      if (tid == 0) { d.pod_pos[k] = found; d.pod_cell[k] = d.cv[off + found]; }
+      if (tid == 0) { s.pod_pos[k] = found; s.pod_cell[k] = d.cv[off + found]; }
     }
     if (tid == 0) { sm->r_ok = ok; sm->r_reason = reason; sm->r_cell = rcell; }
     hv_cta_sync();
@@ -831,7 +867,7 @@ struct Core {
   // :308-387.  slot = index of this node's candidate list (nodeAvailableLeafCells); out = leaf ids
   template <bool V>
   HIVED_DEV_NOINLINE void findLeafCellsInNode(int node, int k, int p, int slot, bool fresh, int chain, int32_t* out) {
-    int32_t* avail = d.cand + slot * MAX_NODE_LEAVES;
+    int32_t* avail = s.cand + slot * MAX_NODE_LEAVES;
     int navail;
     if (fresh) {
       // getLeafCellsFromNode :464-476: free leaves in DFS order, then preemptible ones (ballot compaction)
@@ -859,7 +895,7 @@ struct Core {
       hv_warp_sync();
       navail = n;
     } else {
-      navail = d.cand_len[slot];
+      navail = s.cand_len[slot];
     }
     int curIdx[MAX_NODE_LEAVES], curAff[MAX_NODE_LEAVES], bestIdx[MAX_NODE_LEAVES];
     const int HIGHEST = 0x7fffffff;
@@ -915,7 +951,7 @@ struct Core {
       ST(avail[w], v);
       w++;
     }
-    ST(d.cand_len[slot], w);
+    ST(s.cand_len[slot], w);
   }
 
   // ======================================================================================
@@ -927,7 +963,7 @@ struct Core {
                                       bool ignoreSuggested, int32_t* outLeaves, int& reason, int& rcell) {
     int npods = 0;
     for (int m = 0; m < nmem; m++)
-      for (int i = 0; i < memPods[m]; i++) { ST(d.pod_need[npods], memLeaf[m]); npods++; }
+      for (int i = 0; i < memPods[m]; i++) { ST(s.pod_need[npods], memLeaf[m]); npods++; }
     int priority = OPP_PRIO;
     long long tc0 = hv_clock();
     bool ok = runViewPass(sched, priority, ignoreSuggested, npods, reason, rcell);
@@ -943,13 +979,13 @@ struct Core {
     const int chain = d.s_chain[sched];
     int nslots = 0, outOff = 0;
     for (int k = 0; k < npods; k++) {
-      int node = d.pod_cell[k];
+      int node = s.pod_cell[k];
       int slot = -1;
       for (int j = 0; j < nslots; j++)
-        if (d.cand_node[j] == node) { slot = j; break; }
+        if (s.cand_node[j] == node) { slot = j; break; }
       bool fresh = slot < 0;
-      if (fresh) { slot = nslots++; ST(d.cand_node[slot], node); }
-      int need = d.pod_need[k];
+      if (fresh) { slot = nslots++; ST(s.cand_node[slot], node); }
+      int need = s.pod_need[k];
       if (isVirtual) findLeafCellsInNode<true>(node, need, priority, slot, fresh, chain, outLeaves + outOff);
       else findLeafCellsInNode<false>(node, need, priority, slot, fresh, chain, outLeaves + outOff);
       if (panicCode) return false;
@@ -971,29 +1007,29 @@ struct Core {
   HIVED_DEV int newVertex(int vcell) {
     int v = vxCount++;
     if (v >= d.S.VX) { panic(HIVED_ERR_CAPACITY); return 0; }
-    ST(d.vx_cell[v], vcell);
-    ST(d.vx_child[v], -1);
-    ST(d.vx_last[v], -1);
-    ST(d.vx_next[v], -1);
-    ST(d.vx_nch[v], 0);
+    ST(s.vx_cell[v], vcell);
+    ST(s.vx_child[v], -1);
+    ST(s.vx_last[v], -1);
+    ST(s.vx_next[v], -1);
+    ST(s.vx_nch[v], 0);
     ST(d.vx_of[vcell], v);
     ST(d.vx_stamp[vcell], epochNow);
     return v;
   }
   HIVED_DEV int vertexOf(int vcell) const { return d.vx_stamp[vcell] == epochNow ? d.vx_of[vcell] : -1; }
   HIVED_DEV void addChildVertex(int parentV, int childV) {
-    int last = d.vx_last[parentV];
-    int nch = d.vx_nch[parentV];
+    int last = s.vx_last[parentV];
+    int nch = s.vx_nch[parentV];
     hv_warp_sync();
-    if (last < 0) ST(d.vx_child[parentV], childV); else ST(d.vx_next[last], childV);
-    ST(d.vx_last[parentV], childV);
-    ST(d.vx_nch[parentV], nch + 1);
+    if (last < 0) ST(s.vx_child[parentV], childV); else ST(s.vx_next[last], childV);
+    ST(s.vx_last[parentV], childV);
+    ST(s.vx_nch[parentV], nch + 1);
   }
   // types.go:282-340
   HIVED_DEV_NOINLINE void toBindingPaths(const int32_t* vleaves, int nleaves) {
-    epochNow = *d.epoch + 1;
+    epochNow = d.epoch[cta] + 1;
     hv_warp_sync();
-    ST(*d.epoch, epochNow);
+    ST(d.epoch[cta], epochNow);
     vxCount = 0; paCount = 0; npCount = 0;
     for (int i = 0; i < nleaves; i++) {
       int leaf = vleaves[i];
@@ -1010,23 +1046,23 @@ struct Core {
       int n = newVertex(root);
       int par = d.v_parent[root];
       if (par < 0) {
-        ST(d.pa_list[paCount], n); paCount++;
+        ST(s.pa_list[paCount], n); paCount++;
       } else if (d.v_pcell[par] >= 0) {
         bool buddy = false;
         for (int g = 0; g < npCount; g++) {
-          if (d.v_parent[d.vx_cell[d.np_head[g]]] == par) {
+          if (d.v_parent[s.vx_cell[s.np_head[g]]] == par) {
             // append to the group's chain (roots are linked through vx_next)
-            int t = d.np_head[g];
-            while (d.vx_next[t] >= 0) t = d.vx_next[t];
-            int cnt = d.np_cnt[g];
+            int t = s.np_head[g];
+            while (s.vx_next[t] >= 0) t = s.vx_next[t];
+            int cnt = s.np_cnt[g];
             hv_warp_sync();
-            ST(d.vx_next[t], n);
-            ST(d.np_cnt[g], cnt + 1);
+            ST(s.vx_next[t], n);
+            ST(s.np_cnt[g], cnt + 1);
             buddy = true;
             break;
           }
         }
-        if (!buddy) { ST(d.np_head[npCount], n); ST(d.np_cnt[npCount], 1); npCount++; }
+        if (!buddy) { ST(s.np_head[npCount], n); ST(s.np_cnt[npCount], 1); npCount++; }
       } else {
         addChildVertex(vertexOf(par), n);
       }
@@ -1084,14 +1120,14 @@ struct Core {
   HIVED_DEV_NOINLINE bool mapVirtualCellsToPhysical(int firstV, int ncells, const int32_t* candIn, int candBase, int ncand,
                                                     bool ignoreSuggested, int depth, int32_t* pickedOut) {
     if (depth >= MAXL || ncells > MAX_FANOUT || (depth > 0 && ncand > MAX_FANOUT)) { panic(HIVED_ERR_CAPACITY); return false; }
-    int32_t* cands = depth == 0 ? d.mc0 : d.mcbuf + depth * MAX_FANOUT;
+    int32_t* cands = depth == 0 ? s.mc0 : s.mcbuf + depth * MAX_FANOUT;
     int n = getUsablePhysicalCells(candIn, candBase, ncand, ncells, ignoreSuggested, cands);
     if (n < 0) return false;
-    int32_t* pickedIdx = d.mcpick + depth * MAX_FANOUT;
-    int32_t* cellV = d.mccells + depth * MAX_FANOUT;
+    int32_t* pickedIdx = s.mcpick + depth * MAX_FANOUT;
+    int32_t* cellV = s.mccells + depth * MAX_FANOUT;
     {
       int v = firstV;
-      for (int i = 0; i < ncells; i++) { ST(cellV[i], v); ST(pickedIdx[i], 0); v = d.vx_next[v]; }
+      for (int i = 0; i < ncells; i++) { ST(cellV[i], v); ST(pickedIdx[i], 0); v = s.vx_next[v]; }
     }
     int cellIndex = 0;
     while (cellIndex >= 0) {
@@ -1106,9 +1142,9 @@ struct Core {
         bool picked;
         if (d.p_level[candidate] == 1) {
           picked = true;
-          ST(d.binding[d.vx_cell[vtx]], candidate);
+          ST(d.binding[s.vx_cell[vtx]], candidate);
         } else {
-          picked = mapVirtualCellsToPhysical(d.vx_child[vtx], d.vx_nch[vtx], nullptr, d.p_child0[candidate], d.p_nchild[candidate],
+          picked = mapVirtualCellsToPhysical(s.vx_child[vtx], s.vx_nch[vtx], nullptr, d.p_child0[candidate], d.p_nchild[candidate],
                                              ignoreSuggested, depth + 1, nullptr);
           if (panicCode) return false;
         }
@@ -1134,54 +1170,54 @@ struct Core {
 
   // ---- the Schedule-time copy of the chain's free list (types.go:123-130, hived_algorithm.go:917-929)
   int sflChain;
-  HIVED_DEV int32_t* sfl(int level) const { return d.sfl_data + d.fl_base[cl(sflChain, level)]; }
+  HIVED_DEV int32_t* sfl(int level) const { return s.sfl_data + d.fl_base[cl(sflChain, level)]; }
   HIVED_DEV void sflCopy(int chain) {
     sflChain = chain;
     for (int l = 1; l < MAXL; l++) {
       int k = cl(chain, l);
       int n = l <= d.chain_top[chain] ? d.fl_len[k] : 0;
-      ST(d.sfl_len[l], n);
-      for (int i = lane; i < n; i += HIVED_WARPSZ) d.sfl_data[d.fl_base[k] + i] = d.fl_data[d.fl_base[k] + i];
+      ST(s.sfl_len[l], n);
+      for (int i = lane; i < n; i += HIVED_WARPSZ) s.sfl_data[d.fl_base[k] + i] = d.fl_data[d.fl_base[k] + i];
     }
     hv_warp_sync();
   }
   HIVED_DEV void sflRemove(int level, int cell) {  // types.go:78-95 on the copy
     int32_t* a = sfl(level);
-    int n = d.sfl_len[level];
+    int n = s.sfl_len[level];
     int idx = firstIdx(n, [&](int i) { return a[i] == cell; });
     if (idx < 0) { panic(HIVED_ERR_PLATFORM); return; }
     int lastv = a[n - 1];
     hv_warp_sync();
     ST(a[idx], lastv);
-    ST(d.sfl_len[level], n - 1);
+    ST(s.sfl_len[level], n - 1);
   }
 
   // cell_allocation.go:34-80
   HIVED_DEV_NOINLINE bool buddyAlloc(int vtx, int currentLevel, bool ignoreSuggested) {
-    int cellLevel = d.v_level[d.vx_cell[vtx]];
+    int cellLevel = d.v_level[s.vx_cell[vtx]];
     if (currentLevel == cellLevel) {
-      ST(d.vx_next[vtx], -1);
-      bool ok = mapVirtualCellsToPhysical(vtx, 1, sfl(currentLevel), 0, d.sfl_len[currentLevel], ignoreSuggested, 0, d.tmp_list);
-      if (ok) { sflRemove(currentLevel, d.tmp_list[0]); return true; }
+      ST(s.vx_next[vtx], -1);
+      bool ok = mapVirtualCellsToPhysical(vtx, 1, sfl(currentLevel), 0, s.sfl_len[currentLevel], ignoreSuggested, 0, s.tmp_list);
+      if (ok) { sflRemove(currentLevel, s.tmp_list[0]); return true; }
       return false;
     }
-    int32_t* freeCells = d.ba_buf + (int64_t)currentLevel * d.S.maxLevelCount;
-    int nfree = getUsablePhysicalCells(sfl(currentLevel), 0, d.sfl_len[currentLevel], 1, ignoreSuggested, freeCells);
+    int32_t* freeCells = s.ba_buf + (int64_t)currentLevel * d.S.maxLevelCount;
+    int nfree = getUsablePhysicalCells(sfl(currentLevel), 0, s.sfl_len[currentLevel], 1, ignoreSuggested, freeCells);
     if (nfree < 0) return false;
     for (int i = 0; i < nfree; i++) {
       int c = freeCells[i];
       int32_t* lower = sfl(currentLevel - 1);
-      int nl = d.sfl_len[currentLevel - 1];
+      int nl = s.sfl_len[currentLevel - 1];
       int nc = d.p_nchild[c], c0 = d.p_child0[c];
       for (int j = lane; j < nc; j += HIVED_WARPSZ) lower[nl + j] = c0 + j;
       hv_warp_sync();
-      ST(d.sfl_len[currentLevel - 1], nl + nc);
+      ST(s.sfl_len[currentLevel - 1], nl + nc);
       if (buddyAlloc(vtx, currentLevel - 1, ignoreSuggested)) {
         sflRemove(currentLevel, c);
         return true;
       }
       if (panicCode) return false;
-      ST(d.sfl_len[currentLevel - 1], 0);  // = nil
+      ST(s.sfl_len[currentLevel - 1], 0);  // = nil
     }
     return false;
   }
@@ -1193,17 +1229,17 @@ struct Core {
     for (int i = 0; i < MAXL; i++) splittableNum[i] = 0;
     int splittableCell = -1;
     for (int i = top; i > currentLevel; i--) {
-      splittableNum[i] = d.sfl_len[i] - freeCellNum[i];
+      splittableNum[i] = s.sfl_len[i] - freeCellNum[i];
       if (i < top && splittableCell >= 0) splittableNum[i] += splittableNum[i + 1] * d.p_nchild[splittableCell];
-      if (splittableCell < 0 && d.sfl_len[i] > 0) splittableCell = sfl(i)[0];
+      if (splittableCell < 0 && s.sfl_len[i] > 0) splittableCell = sfl(i)[0];
       else if (splittableCell >= 0) splittableCell = d.p_child0[splittableCell];
       if (splittableNum[i] < 0) { panic(HIVED_ERR_PLATFORM); return false; }  // "VC Safety Broken"
     }
     for (int l = currentLevel + 1; l <= top; l++) {
-      int cellNum = d.sfl_len[l];
+      int cellNum = s.sfl_len[l];
       if (cellNum > splittableNum[l]) cellNum = splittableNum[l];
       if (cellNum > 0) {
-        int32_t* split = d.ba_buf;  // level 0 row is otherwise unused
+        int32_t* split = s.ba_buf;  // level 0 row is otherwise unused
         int ns = 0;
         for (int i = 0; i < cellNum; i++) {
           int first = sfl(l)[0];
@@ -1226,13 +1262,13 @@ struct Core {
         }
         // freeList[currentLevel] = append(splitList, freeList[currentLevel]...)
         int32_t* cur = sfl(currentLevel);
-        int nc = d.sfl_len[currentLevel];
+        int nc = s.sfl_len[currentLevel];
         for (int i = nc - 1; i >= 0; i--) { int v = cur[i]; hv_warp_sync(); ST(cur[i + ns], v); }
         for (int i = 0; i < ns; i++) ST(cur[i], split[i]);
-        ST(d.sfl_len[currentLevel], nc + ns);
-        ST(d.vx_next[vtx], -1);
-        bool ok = mapVirtualCellsToPhysical(vtx, 1, cur, 0, nc + ns, ignoreSuggested, 0, d.tmp_list);
-        if (ok) { sflRemove(currentLevel, d.tmp_list[0]); return true; }
+        ST(s.sfl_len[currentLevel], nc + ns);
+        ST(s.vx_next[vtx], -1);
+        bool ok = mapVirtualCellsToPhysical(vtx, 1, cur, 0, nc + ns, ignoreSuggested, 0, s.tmp_list);
+        if (ok) { sflRemove(currentLevel, s.tmp_list[0]); return true; }
         if (panicCode) return false;
       }
     }
@@ -1242,19 +1278,21 @@ struct Core {
   // cell_allocation.go:152-197
   HIVED_DEV_NOINLINE bool mapVirtualPlacementToPhysical(int chain, bool ignoreSuggested) {
     int freeCellNum[MAXL];
-    for (int l = 0; l < MAXL; l++) freeCellNum[l] = (chain >= 0 && d.chain_in_vc[chain]) ? d.allVCFree[cl(chain, l)] : 0;
+    for (int l = 0; l < MAXL; l++) freeCellNum[l] = 0;
     if (paCount > 0) {
       if (chain < 0) { panic(HIVED_ERR_PLATFORM); return false; }  // nil free list: "VC Safety Broken"
+      sharedEnter();  // held until the event (and its commit) is over
+      for (int l = 0; l < MAXL; l++) freeCellNum[l] = d.chain_in_vc[chain] ? d.allVCFree[cl(chain, l)] : 0;
       sflCopy(chain);
     } else {
       sflChain = chain;
     }
     for (int i = 0; i < paCount; i++) {
-      int vtx = d.pa_list[i];
-      int level = d.v_level[d.vx_cell[vtx]];
+      int vtx = s.pa_list[i];
+      int level = d.v_level[s.vx_cell[vtx]];
       int l = level, top = d.chain_top[chain];
       for (; l <= top; l++)
-        if (d.sfl_len[l] != 0) break;
+        if (s.sfl_len[l] != 0) break;
       if (l > top) { panic(HIVED_ERR_PLATFORM); return false; }  // getLowestFreeCellLevel: "VC Safety Broken"
       if (!buddyAlloc(vtx, l, ignoreSuggested)) {
         if (panicCode) return false;
@@ -1264,9 +1302,9 @@ struct Core {
       }
     }
     for (int g = 0; g < npCount; g++) {
-      int head = d.np_head[g];
-      int parentPhysical = d.v_pcell[d.v_parent[d.vx_cell[head]]];
-      bool ok = mapVirtualCellsToPhysical(head, d.np_cnt[g], nullptr, d.p_child0[parentPhysical], d.p_nchild[parentPhysical],
+      int head = s.np_head[g];
+      int parentPhysical = d.v_pcell[d.v_parent[s.vx_cell[head]]];
+      bool ok = mapVirtualCellsToPhysical(head, s.np_cnt[g], nullptr, d.p_child0[parentPhysical], d.p_nchild[parentPhysical],
                                           ignoreSuggested, 0, nullptr);
       if (!ok) return false;
     }
@@ -1396,11 +1434,12 @@ struct Core {
       int pLeaf = ph[i];
       if (pLeaf < 0) continue;
       ST(d.p_using[pLeaf], -1);
+      const int ceil = ceilOf(d.p_vcell[pLeaf]);
       if (d.p_state[pLeaf] == HIVED_CELL_USED) {
         releaseLeafCell(pLeaf, vc);
-        setCellState(pLeaf, HIVED_CELL_FREE);
+        setCellState(pLeaf, HIVED_CELL_FREE, ceil);
       } else {
-        setCellState(pLeaf, HIVED_CELL_RESERVED);
+        setCellState(pLeaf, HIVED_CELL_RESERVED, ceil);
       }
     }
     eraseGroup(g);
@@ -1496,13 +1535,13 @@ struct Core {
         int victim = d.p_using[pLeaf];
         if (victim >= 0 && (d.g_flags[victim] & GF_LAZY_ENABLE)) {
           int slot = -1;
-          for (int j = 0; j < lzCount; j++) if (d.lz_group[j] == victim) { slot = j; break; }
+          for (int j = 0; j < lzCount; j++) if (s.lz_group[j] == victim) { slot = j; break; }
           if (slot < 0) {
             if (lzCount >= d.S.LZ) { panic(HIVED_ERR_CAPACITY); return; }
             slot = lzCount++;
-            ST(d.lz_group[slot], victim);
+            ST(s.lz_group[slot], victim);
           }
-          lazyPreemptAffinityGroup(victim, d.lz_save + (int64_t)slot * (d.S.LS + 1));
+          lazyPreemptAffinityGroup(victim, s.lz_save + (int64_t)slot * (d.S.LS + 1));
           if (panicCode) return;
         }
       }
@@ -1514,33 +1553,33 @@ struct Core {
     int vset = r.pinned >= 0 ? d.vc_pinned_vset[r.vc * d.S.nPinned + r.pinned] : (r.chain >= 0 ? d.vc_chain_vset[r.vc * d.S.nChains + r.chain] : -1);
     int sched = vset >= 0 ? d.vset_sched[vset] : -1;
     if (sched < 0) { reason = HIVED_WAIT_NO_SCHEDULER | HIVED_WAIT_SCOPE_VC; rcell = -1; return false; }
-    if (!tasSchedule(sched, r.nmem, r.memLeaf, r.memPods, r.priority, r.ignoreSuggested, d.pl_v, reason, rcell)) {
+    if (!tasSchedule(sched, r.nmem, r.memLeaf, r.memPods, r.priority, r.ignoreSuggested, s.pl_v, reason, rcell)) {
       reason |= HIVED_WAIT_SCOPE_VC;
       return false;
     }
     long long tm0 = hv_clock();
-    tryLazyPreempt(d.pl_v, r.nleaves);
+    tryLazyPreempt(s.pl_v, r.nleaves);
     if (panicCode) return false;
-    toBindingPaths(d.pl_v, r.nleaves);
+    toBindingPaths(s.pl_v, r.nleaves);
     if (panicCode) return false;
     bool mapped = mapVirtualPlacementToPhysical(r.chain, r.ignoreSuggested);
     stat_add(ST_CYC_MAP, hv_clock() - tm0);
     if (mapped) {
       // toPhysicalPlacement types.go:260-280
-      for (int i = lane; i < r.nleaves; i += HIVED_WARPSZ) d.pl_p[i] = d.binding[d.pl_v[i]];
+      for (int i = lane; i < r.nleaves; i += HIVED_WARPSZ) s.pl_p[i] = d.binding[s.pl_v[i]];
       hv_warp_sync();
       reason = 0; rcell = -1;
       return true;
     }
     if (panicCode) return false;
-    for (int j = 0; j < lzCount; j++) revertLazyPreempt(d.lz_group[j], d.lz_save + (int64_t)j * (d.S.LS + 1));
+    for (int j = 0; j < lzCount; j++) revertLazyPreempt(s.lz_group[j], s.lz_save + (int64_t)j * (d.S.LS + 1));
     reason = HIVED_WAIT_MAPPING; rcell = -1;
     return false;
   }
   // hived_algorithm.go:967-979
   HIVED_DEV bool scheduleOpportunisticAffinityGroup(const Req& r, int& reason, int& rcell) {
     int sched = d.opp_sched[r.chain];
-    if (!tasSchedule(sched, r.nmem, r.memLeaf, r.memPods, OPP_PRIO, r.ignoreSuggested, d.pl_p, reason, rcell)) {
+    if (!tasSchedule(sched, r.nmem, r.memLeaf, r.memPods, OPP_PRIO, r.ignoreSuggested, s.pl_p, reason, rcell)) {
       reason |= HIVED_WAIT_SCOPE_PHYSICAL;
       return false;
     }
@@ -1605,16 +1644,16 @@ struct Core {
   // results
   // ======================================================================================
   // utils.go:202-235.  victims written to the pool (pod id, node id) sorted by pod id; overlapping
-  // preemptor groups (sorted by id) to d.lz_group, count returned through nOverlap.
+  // preemptor groups (sorted by id) to s.lz_group, count returned through nOverlap.
   HIVED_DEV_NOINLINE void collectPreemptionVictims(const int32_t* phys, int nleaves, hived_result_t* res, int& nOverlap) {
     nOverlap = 0;
     ST(res->victim_off, 0);
     ST(res->n_victims, 0);
     // fast path: every cell of the placement is Free
     if (firstIdx(nleaves, [&](int i) { int c = phys[i]; return c >= 0 && d.p_state[c] != HIVED_CELL_FREE; }) < 0) return;
-    int32_t* groups = d.tmp_list;  // using groups
+    int32_t* groups = s.tmp_list;  // using groups
     int ng = 0;
-    int32_t* overlap = d.lz_group;  // lazy-preempt bookkeeping is dead by now
+    int32_t* overlap = s.lz_group;  // lazy-preempt bookkeeping is dead by now
     long long start = poolOff;
     for (int i = 0; i < nleaves; i++) {
       int c = phys[i];
@@ -1861,7 +1900,7 @@ struct Core {
           }
           bool safetyOk = allocateLeafCell(pLeaf, vLeaf, sp.priority, sp.vc);
           ST(d.p_using[pLeaf], g);
-          setCellState(pLeaf, HIVED_CELL_USED);
+          setCellState(pLeaf, HIVED_CELL_USED, ceilOf(vLeaf));
           if (!safetyOk) shouldLazyPreempt = true;
           if (panicCode) return;
         }
@@ -1892,8 +1931,9 @@ struct Core {
   }
 
   // hived_algorithm.go:272-296
-  HIVED_DEV void deleteAllocatedPod(int g, int leafNum, int podIndex) {
+  HIVED_DEV void deleteAllocatedPod(int g, int leafNum, int podIndex, int evVc) {
     if (g < 0 || g >= d.S.maxGroups || d.g_state[g] == HIVED_GROUP_NONE) return;
+    if (multi && d.g_vc[g] != evVc) { panic(HIVED_ERR_PLATFORM); return; }  // the event was routed by a wrong VC id
     if (podIndex == -1) return;
     int m = memberOf(g, leafNum);
     if (m < 0 || podIndex < 0 || podIndex >= d.g_mem_pods[g * 8 + m]) { panic(HIVED_ERR_PLATFORM); return; }
@@ -1972,17 +2012,17 @@ struct Core {
       for (int m = 0; m < nmem; m++) { memLeaf[m] = r.memLeaf[m]; memPods[m] = r.memPods[m]; }
       podIndex = 0;
       if (rc == 1) {
-        havePlacement = true; phys = d.pl_p; virt = d.pl_v; freshPlacement = true;
+        havePlacement = true; phys = s.pl_p; virt = s.pl_v; freshPlacement = true;
         int nOverlap;
         collectPreemptionVictims(phys, r.nleaves, res, nOverlap);
         victimsCollected = true;
         if (panicCode) return panicCode;
         if (phase == HIVED_PHASE_PREEMPTING) {
-          for (int i = 0; i < nOverlap; i++) deletePreemptingAffinityGroup(d.lz_group[i]);
+          for (int i = 0; i < nOverlap; i++) deletePreemptingAffinityGroup(s.lz_group[i]);
           if (res->n_victims != 0) {
             if (!hasVirtual) { panic(HIVED_ERR_PLATFORM); return panicCode; }  // nil virtual placement indexed in the reference
-            for (int i = 0; i < r.nleaves; i++) { ST(d.pl_p2[i], d.pl_p[i]); ST(d.pl_v2[i], d.pl_v[i]); }
-            createPreemptingAffinityGroup(g, sp, d.pl_p2, d.pl_v2);
+            for (int i = 0; i < r.nleaves; i++) { ST(s.pl_p2[i], s.pl_p[i]); ST(s.pl_v2[i], s.pl_v[i]); }
+            createPreemptingAffinityGroup(g, sp, s.pl_p2, s.pl_v2);
           }
         }
         if (panicCode) return panicCode;
@@ -2057,7 +2097,7 @@ struct Core {
         b.n_members = res->n_members; b.member_leaf_num = res->member_leaf_num; b.member_pod_num = res->member_pod_num;
         b.leaves = pool + res->leaf_off;
         // a fresh placement's cells are known; (node, index) identifies them uniquely when S.directLeaf
-        b.physIds = (d.S.directLeaf && freshPlacement) ? d.pl_p : nullptr;
+        b.physIds = (d.S.directLeaf && freshPlacement) ? s.pl_p : nullptr;
         sugg = nullptr;
         long long ta0 = hv_clock();
         addAllocatedPod(sp, b, getAllocatedPodIndex(b, sp.leaf_num));
@@ -2075,7 +2115,7 @@ struct Core {
       if (rc == 0) { addAllocatedPod(ev.spec, b, ev.arg0); rc = panicCode; }
     } else if (type == HIVED_EV_DELETE_ALLOCATED) {
       long long td0 = hv_clock();
-      deleteAllocatedPod(ev.spec.group, ev.spec.leaf_num, ev.arg0);
+      deleteAllocatedPod(ev.spec.group, ev.spec.leaf_num, ev.arg0, ev.spec.vc);
       stat_add(ST_CYC_DELETE, hv_clock() - td0);
       rc = panicCode;
     } else if (type == HIVED_EV_DELETE_UNALLOCATED) {
@@ -2103,20 +2143,57 @@ struct Core {
     for (int i = 0; i < nBad; i++) setNodeHealth(badOrder[i], false);
   }
 
-  // the CTA's main loop: leader warp walks the ordered batch, the other warps serve view passes
+  // After a VC-parallel batch: priority and state of the physical cells ABOVE every bound preassigned
+  // cell, recomputed bottom-up from their children (priority = max; state = Used iff a child is Used —
+  // exact whenever no cell is Reserving/Reserved, which is what the host checks before going parallel).
+  HIVED_DEV void repairSharedAncestors() {
+    for (int l = 2; l <= d.S.maxLevels; l++) {
+      for (int chain = 0; chain < d.S.nChains; chain++) {
+        int base = d.p_lvl_base[cl(chain, l)], cnt = d.p_lvl_cnt[cl(chain, l)];
+        for (int i = hv_tid(); i < cnt; i += hv_nth()) {
+          int cell = base + i;
+          bool under = false;
+          for (int L = l; L < AS; L++) { int a = d.p_anc[cell * AS + L]; if (a >= 0 && d.p_vcell[a] >= 0) { under = true; break; } }
+          if (under) continue;
+          int mx = FREE_PRIO; bool anyUsed = false;
+          int c0 = d.p_child0[cell], n = d.p_nchild[cell];
+          for (int j = 0; j < n; j++) { int q = d.p_prio[c0 + j]; if (q > mx) mx = q; if (d.p_state[c0 + j] == HIVED_CELL_USED) anyUsed = true; }
+          d.p_prio[cell] = mx;
+          d.p_state[cell] = anyUsed ? HIVED_CELL_USED : HIVED_CELL_FREE;
+        }
+      }
+      hv_cta_sync();
+    }
+  }
+
+  // the CTA's main loop: leader warp walks its share of the ordered batch, the other warps serve view
+  // passes.  own[0..nOwn): ascending indices of the events this CTA owns (nullptr: all of them).
   HIVED_DEV void run(const hived_event_t* events, int n, hived_result_t* results, const uint32_t* suggPool, const int32_t* aux,
-                     const int32_t* initLists, int nPinnedOrder, int nBad) {
+                     const int32_t* initLists, int nPinnedOrder, int nBad, const int32_t* own, int nOwn) {
     if (hv_warp() == 0) {
       poolOff = sm->pool_off;
       int initPanic = 0;
       if (initLists) { initState(initLists, nPinnedOrder, initLists + nPinnedOrder, nBad); initPanic = panicCode; }
-      for (int i = 0; i < n; i++) processEvent(events[i], &results[i], suggPool, aux);
-      // flush the work counters
-      for (int i = 0; i < ST_COUNT; i++) {
-        long long v = d.stats[i];
-        hv_warp_sync();
-        if (i == ST_PRIO_MASK) ST(d.stats[i], v | acc[i]); else ST(d.stats[i], v + acc[i]);
+      if (!own) nOwn = n;
+      for (int k = 0; k < nOwn; k++) {
+        int i = own ? own[k] : k;
+        curEvent = i;
+        sharedHeld = false;
+        processEvent(events[i], &results[i], suggPool, aux);
+        if (multi) {
+          int next = (k + 1 < nOwn) ? own[k + 1] : 0x7fffffff;
+          hv_fence();  // release: everything this event wrote is visible before the progress moves on
+          if (lane == 0) hv_st_volatile(d.progress + cta, next);
+          hv_warp_sync();
+        }
       }
+      // flush the work counters
+      if (lane == 0) {
+        for (int i = 0; i < ST_COUNT; i++) {
+          if (i == ST_PRIO_MASK) hv_atomic_or64(&d.stats[i], acc[i]); else if (acc[i]) hv_atomic_add64(&d.stats[i], acc[i]);
+        }
+      }
+      hv_warp_sync();
       ST(sm->pool_off, poolOff);
       ST(sm->panic, initPanic);
       ST(sm->cmd, CMD_EXIT);

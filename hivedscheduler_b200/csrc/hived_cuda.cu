@@ -15,24 +15,34 @@ namespace hived {
 
 constexpr int NT = 512;  // threads per CTA (16 warps); the kernel needs the full register file of one SM
 
+// scalars: 4 words per CTA — [0] pool offset (in: start of the CTA's slice, out: first unused word),
+// [1] end of the slice, [2] out: initialisation panic code
 __global__ void __launch_bounds__(NT, 1)
 hived_events_kernel(const __grid_constant__ Dev dev, const hived_event_t* __restrict__ events, int n, hived_result_t* results,
                     const uint32_t* suggPool, const int32_t* aux, const int32_t* initLists, int nPinnedOrder, int nBad,
-                    int32_t* pool, long long poolCap, long long* scalars) {
+                    int32_t* pool, long long* scalars, const int32_t* own, const int32_t* ownOff) {
   __shared__ Sm sm;
+  const int cta = blockIdx.x;
   if (threadIdx.x == 0) {
     sm.cmd = CMD_IDLE;
     sm.panic = 0;
-    sm.pool_off = scalars[0];
+    sm.pool_off = scalars[cta * 4 + 0];
   }
   __syncthreads();
-  Core core(dev, &sm, pool, poolCap);
-  core.run(events, n, results, suggPool, aux, initLists, nPinnedOrder, nBad);
+  Core core(dev, &sm, pool, scalars[cta * 4 + 1], gridDim.x);
+  core.run(events, n, results, suggPool, aux, initLists, nPinnedOrder, nBad, own ? own + ownOff[cta] : nullptr,
+           own ? ownOff[cta + 1] - ownOff[cta] : n);
   __syncthreads();
   if (threadIdx.x == 0) {
-    scalars[0] = sm.pool_off;
-    scalars[1] = sm.panic;
+    scalars[cta * 4 + 0] = sm.pool_off;
+    scalars[cta * 4 + 2] = sm.panic;
   }
+}
+
+__global__ void __launch_bounds__(NT, 1) hived_repair_kernel(const __grid_constant__ Dev dev) {
+  __shared__ Sm sm;
+  Core core(dev, &sm, nullptr, 0, 1);
+  core.repairSharedAncestors();
 }
 
 static bool cudaOk(cudaError_t e, std::string& err, const char* what) {
@@ -91,14 +101,21 @@ int launchProgram(Engine& e, int n, bool withInit) {
     e.stream = t;
   }
   CudaTimers* t = (CudaTimers*)e.stream;
-  long long scal[2] = {e.poolOff, 0};
+  const int C = withInit ? 1 : e.launchCta;
+  long long scal[MAX_CTAS * 4] = {0};
+  for (int c = 0; c < C; c++) {
+    scal[c * 4 + 0] = withInit ? 0 : e.poolBase[c];
+    scal[c * 4 + 1] = withInit ? 0 : e.poolBase[c + 1];
+  }
   cudaMemcpyAsync(e.dScalars.p, scal, sizeof scal, cudaMemcpyHostToDevice, t->stream);
   cudaEventRecord(t->start, t->stream);
-  hived_events_kernel<<<1, NT, 0, t->stream>>>(
+  const int32_t* own = C > 1 ? (const int32_t*)e.dOwn.p : nullptr;
+  hived_events_kernel<<<C, NT, 0, t->stream>>>(
       e.dev, (const hived_event_t*)e.dEvents.p, n, (hived_result_t*)e.dResults.p,
       e.hasSugg ? (const uint32_t*)e.dSugg.p : nullptr, e.hasAux ? (const int32_t*)e.dAux.p : nullptr,
-      withInit ? (const int32_t*)e.dInit.p : nullptr, e.nPinnedOrder, e.nBad, (int32_t*)e.dPool.p,
-      withInit ? 0 : (long long)e.poolCapWords, (long long*)e.dScalars.p);
+      withInit ? (const int32_t*)e.dInit.p : nullptr, e.nPinnedOrder, e.nBad, (int32_t*)e.dPool.p, (long long*)e.dScalars.p, own,
+      own ? own + n : nullptr);
+  if (C > 1) hived_repair_kernel<<<1, NT, 0, t->stream>>>(e.dev);
   cudaEventRecord(t->stop, t->stream);
   cudaMemcpyAsync(scal, e.dScalars.p, sizeof scal, cudaMemcpyDeviceToHost, t->stream);
   cudaError_t err = cudaStreamSynchronize(t->stream);
@@ -110,9 +127,11 @@ int launchProgram(Engine& e, int n, bool withInit) {
   cudaEventElapsedTime(&ms, t->start, t->stop);
   e.lastKernelMs = ms;
   e.kernelMsTotal += ms;
-  e.kernelLaunches++;
+  e.kernelLaunches += C > 1 ? 2 : 1;
+  e.poolEnd.assign(C, 0);
+  for (int c = 0; c < C; c++) e.poolEnd[c] = scal[c * 4 + 0];
   e.poolOff = scal[0];
-  if (withInit && scal[1]) { e.err = "initialisation panicked on the device"; return (int)scal[1]; }
+  if (withInit && scal[2]) { e.err = "initialisation panicked on the device"; return (int)scal[2]; }
   return 0;
 }
 

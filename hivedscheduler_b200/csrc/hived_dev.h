@@ -36,20 +36,28 @@ namespace hived {
   Y(g_nmem, S.maxGroups, 0) Y(g_mem_leaf, S.maxGroups * 8, 0) Y(g_mem_pods, S.maxGroups * 8, 0)        \
   Y(g_phys, (int64_t)S.maxGroups * S.LS, -1) Y(g_virt, (int64_t)S.maxGroups * S.LS, -1)                \
   Y(g_pods, (int64_t)S.maxGroups * S.PS, -1) Y(g_npre, S.maxGroups, 0)                                 \
-  Y(g_pre, (int64_t)S.maxGroups * S.PS, -1) Y(pod_node, S.maxPods, -1)                                 \
-  /* scratch of one scheduling decision */                                                             \
-  Y(sfl_data, S.flTotal, -1) Y(sfl_len, MAXL, 0)                                                       \
-  Y(vx_cell, S.VX, -1) Y(vx_child, S.VX, -1) Y(vx_last, S.VX, -1) Y(vx_next, S.VX, -1) Y(vx_nch, S.VX, 0) \
-  Y(vx_of, S.NV, -1) Y(vx_stamp, S.NV, 0) Y(binding, S.NV, -1)                                         \
-  Y(pa_list, S.LS, -1) Y(np_head, S.LS, -1) Y(np_cnt, S.LS, 0)                                         \
-  Y(pl_v, S.LS, -1) Y(pl_p, S.LS, -1) Y(pl_v2, S.LS, -1) Y(pl_p2, S.LS, -1)                            \
-  Y(cand, S.PS * MAX_NODE_LEAVES, -1) Y(cand_len, S.PS, 0) Y(cand_node, S.PS, -1)                      \
-  Y(pod_need, S.PS, 0) Y(pod_pos, S.PS, -1) Y(pod_cell, S.PS, -1)                                      \
-  Y(mc0, S.maxLevelCount + MAX_FANOUT, -1) Y(mcbuf, MAXL * MAX_FANOUT, -1)                             \
-  Y(mcpick, MAXL * MAX_FANOUT, 0) Y(mccells, MAXL * MAX_FANOUT, -1)                                    \
-  Y(lz_group, S.LS, -1) Y(lz_save, (int64_t)S.LZ * (S.LS + 1), -1) Y(ba_buf, (int64_t)MAXL * S.maxLevelCount, -1)                                           \
-  Y(tmp_list, S.maxLevelCount + MAX_FANOUT, -1)                                                        \
-  Y(vw_cell, S.maxViewN, -1) Y(vw_info, S.maxViewN, 0) Y(vw_ordA, S.maxViewN, 0) Y(vw_ordB, S.maxViewN, 0)
+  Y(g_pre, (int64_t)S.maxGroups * S.PS, -1) Y(pod_node, S.maxPods, -1) \
+  Y(vx_of, S.NV, -1) Y(vx_stamp, S.NV, 0) Y(binding, S.NV, -1)
+
+// Z(name, count): scratch of one scheduling decision — one private copy per CTA (struct Scratch)
+#define HIVED_SCRATCH_ARRAYS(Z)                                                                        \
+  Z(sfl_data, S.flTotal) Z(sfl_len, MAXL)                                                              \
+  Z(vx_cell, S.VX) Z(vx_child, S.VX) Z(vx_last, S.VX) Z(vx_next, S.VX) Z(vx_nch, S.VX)                 \
+  Z(pa_list, S.LS) Z(np_head, S.LS) Z(np_cnt, S.LS)                                                    \
+  Z(pl_v, S.LS) Z(pl_p, S.LS) Z(pl_v2, S.LS) Z(pl_p2, S.LS)                                            \
+  Z(cand, S.PS * MAX_NODE_LEAVES) Z(cand_len, S.PS) Z(cand_node, S.PS)                                 \
+  Z(pod_need, S.PS) Z(pod_pos, S.PS) Z(pod_cell, S.PS)                                                 \
+  Z(mc0, S.maxLevelCount + MAX_FANOUT) Z(mcbuf, MAXL * MAX_FANOUT)                                     \
+  Z(mcpick, MAXL * MAX_FANOUT) Z(mccells, MAXL * MAX_FANOUT)                                           \
+  Z(lz_group, S.LS) Z(lz_save, (int64_t)S.LZ * (S.LS + 1)) Z(ba_buf, (int64_t)MAXL * S.maxLevelCount)  \
+  Z(tmp_list, S.maxLevelCount + MAX_FANOUT)                                                            \
+  Z(vw_cell, S.maxViewN) Z(vw_info, S.maxViewN) Z(vw_ordA, S.maxViewN) Z(vw_ordB, S.maxViewN)
+
+struct Scratch {
+#define Z(name, count) int32_t* name;
+  HIVED_SCRATCH_ARRAYS(Z)
+#undef Z
+};
 
 struct DevSizes {
   int32_t NP, NV, nChains, nVCs, nLeafTypes, nPinned, nNodes, nVsets, nScheds;
@@ -65,17 +73,21 @@ struct Dev {
 #define Y(name, count, init) int32_t* name;
   HIVED_MUTABLE_ARRAYS(Y)
 #undef Y
-  long long* stats;   // [16] counters, see ST_* below
-  int32_t* epoch;     // [1] stamp for vx_stamp
+  long long* stats;        // [ST_COUNT] counters, see ST_* below
+  int32_t* epoch;          // [MAX_CTAS] per-CTA stamp for vx_stamp
+  const Scratch* scratch;  // [nCta] private scratch arrays of every CTA
+  int32_t* progress;       // [MAX_CTAS] index of the event each CTA is working on (multi-CTA ordering)
 };
 
 enum {
   ST_VIEW_NODES = 0, ST_LEAVES = 1, ST_FREE_CELLS = 2, ST_PODS = 3, ST_SCHEDULE = 4, ST_BIND = 5, ST_WAIT = 6,
-  ST_PREEMPT = 7, ST_PRIO_MASK = 8 /* bit (p+1) for small priorities, else bit 63 */,
+  ST_PREEMPT = 7, ST_PRIO_MASK = 8 /* bit (p+1) for small priorities, else bit 62 */,
   /* SM cycles spent per phase (leader warp), for profiles/ */
   ST_CYC_VIEW = 9, ST_CYC_LEAF = 10, ST_CYC_MAP = 11, ST_CYC_EMIT = 12, ST_CYC_COMMIT = 13, ST_CYC_DELETE = 14, ST_CYC_TOTAL = 15,
   ST_COUNT = 16
 };
+
+constexpr int MAX_CTAS = 32;
 
 // group flags
 enum { GF_LAZY_ENABLE = 1, GF_HAS_VIRTUAL = 2, GF_LAZY_PREEMPTED = 4 };

@@ -6,6 +6,7 @@
 // The backend supplies bk_* (memory) and launchProgram().
 #pragma once
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -53,8 +54,18 @@ struct Engine {
   std::vector<std::pair<void*, size_t>> mutableRegions;  // for save/restore
   std::vector<void*> savedRegions;
   // staging (device side)
-  Buf dEvents, dResults, dPool, dSugg, dAux, dInit, dScalars;
+  Buf dEvents, dResults, dPool, dSugg, dAux, dInit, dScalars, dOwn;
   long long poolOff = 0;
+  // ---- VC-parallel execution
+  int nCtaMax = 1, launchCta = 1;
+  std::vector<int32_t> ownOff;          // [launchCta + 1] into the owner-sorted index list (device: dOwn)
+  std::vector<long long> poolBase;      // [launchCta + 1] pool slice of every CTA
+  std::vector<long long> poolEnd;       // [launchCta] first unused word of every slice after the run
+  std::vector<char> nodeBadHost;        // host mirror of the node health (decides whether a batch may run VC-parallel)
+  int badCount = 0;
+  uint64_t prioMaskHost = 0;
+  bool everRecovered = false;
+  long long multiBatches = 0;
   int nPinnedOrder = 0, nBad = 0;
   uint64_t hash = HIVED_FNV_OFFSET;
   float lastKernelMs = 0.f;
@@ -122,8 +133,26 @@ struct Engine {
 #undef Y
     dev.stats = allocFill<long long>(ST_COUNT, 0);
     mutableRegions.push_back({dev.stats, ST_COUNT * sizeof(long long)});
-    dev.epoch = allocFill<int32_t>(1, 1);
-    mutableRegions.push_back({dev.epoch, sizeof(int32_t)});
+    dev.epoch = allocFill<int32_t>(MAX_CTAS, 1);
+    mutableRegions.push_back({dev.epoch, MAX_CTAS * sizeof(int32_t)});
+    dev.progress = allocFill<int32_t>(MAX_CTAS, 0);
+    // one private scratch set per CTA (VC-parallel execution uses up to nCtaMax CTAs)
+    nCtaMax = T.nVCs < 16 ? (T.nVCs > 0 ? T.nVCs : 1) : 16;
+    if (const char* env = getenv("HIVED_NCTA")) { int v = atoi(env); if (v >= 1 && v <= MAX_CTAS) nCtaMax = v < nCtaMax ? v : nCtaMax; }
+    {
+      std::vector<Scratch> sc(nCtaMax);
+      for (int c = 0; c < nCtaMax; c++) {
+#define Z(name, count) sc[c].name = allocFill<int32_t>((size_t)(count), 0);
+        HIVED_SCRATCH_ARRAYS(Z)
+#undef Z
+      }
+      Scratch* dsc = (Scratch*)bk_alloc(sizeof(Scratch) * nCtaMax);
+      bk_h2d(dsc, sc.data(), sizeof(Scratch) * nCtaMax);
+      allocs.push_back(dsc);
+      dev.scratch = dsc;
+    }
+    nodeBadHost.assign(T.nNodes > 0 ? T.nNodes : 1, 1);  // every node starts bad (hived_algorithm.go:453-464)
+    badCount = T.nNodes;
     // initial dynamic state (hived_algorithm.go:108-145, 365-409)
     bk_h2d(dev.vcFree, T.vcFree.data(), T.vcFree.size() * 4);
     bk_h2d(dev.allVCFree, T.allVCFree.data(), T.allVCFree.size() * 4);
@@ -145,7 +174,8 @@ struct Engine {
     nBad = (int)T.bad_init_order.size();
     dInit.ensure((init.size() + 1) * 4);
     if (!init.empty()) bk_h2d(dInit.p, init.data(), init.size() * 4);
-    dScalars.ensure(64);
+    dScalars.ensure(MAX_CTAS * 4 * sizeof(long long));
+    dOwn.ensure(64);
     dPool.ensure(4096 * 4);
     dResults.ensure(sizeof(hived_result_t));
     dEvents.ensure(sizeof(hived_event_t));
@@ -155,41 +185,149 @@ struct Engine {
     return 0;
   }
 
+  // Decide how the batch runs and stage everything but the results.  A batch runs VC-parallel (one CTA per
+  // group of VCs) only in the regime where VCs interact through nothing but the chain-wide free lists:
+  // every node healthy, a single guaranteed priority ever used (so no preemption, no lazy preemption, no
+  // opportunistic cells), no recovery calls, and only SCHEDULE / DELETE events with valid VC ids.
+  int prepare(const hived_event_t* events, int n, int64_t poolCap) {
+    launchCta = 1;
+    uint64_t mask = prioMaskHost;
+    bool simple = nCtaMax > 1 && n >= 256 && badCount == 0 && !everRecovered;
+    for (int i = 0; i < n; i++) {
+      const hived_event_t& ev = events[i];
+      if (ev.type == HIVED_EV_SCHEDULE || ev.type == Core::EV_SCHEDULE_ONLY || ev.type == Core::EV_ADD_ALLOCATED) {
+        int p = ev.spec.priority;
+        mask |= (p >= -1 && p < 62) ? (1ull << (p + 1)) : (1ull << 62);
+      }
+      if (ev.type != HIVED_EV_SCHEDULE && ev.type != HIVED_EV_DELETE_ALLOCATED) simple = false;
+      else if (ev.spec.vc < 0 || ev.spec.vc >= T.nVCs) simple = false;
+      if (ev.type == Core::EV_ADD_ALLOCATED) everRecovered = true;
+    }
+    prioMaskHost = mask;
+    if ((mask & (mask - 1)) != 0 || (mask & 1)) simple = false;  // more than one priority, or opportunistic (-1)
+    ownOff.assign(2, 0); ownOff[1] = n;
+    poolBase.assign(2, 0); poolBase[1] = poolCap;
+    if (simple) {
+      int C = nCtaMax < T.nVCs ? nCtaMax : T.nVCs;
+      std::vector<int32_t> cnt(C + 1, 0);
+      std::vector<long long> need(C, 0);
+      for (int i = 0; i < n; i++) {
+        int o = events[i].spec.vc % C;
+        cnt[o + 1]++;
+        if (events[i].type == HIVED_EV_SCHEDULE) {
+          long long leaves = 0;
+          for (int m = 0; m < events[i].spec.n_members && m < HIVED_MAX_MEMBERS; m++)
+            leaves += (long long)events[i].spec.member_leaf_num[m] * events[i].spec.member_pod_num[m];
+          need[o] += 3 * leaves;
+        }
+      }
+      long long total = 0;
+      for (int c = 0; c < C; c++) total += need[c];
+      if (total <= poolCap) {
+        launchCta = C;
+        ownOff.assign(C + 1, 0);
+        for (int c = 0; c < C; c++) ownOff[c + 1] = ownOff[c] + cnt[c + 1];
+        std::vector<int32_t> own(n), fill(ownOff.begin(), ownOff.end() - 1);
+        for (int i = 0; i < n; i++) own[fill[events[i].spec.vc % C]++] = i;
+        dOwn.ensure((size_t)(n + C + 2) * 4);
+        bk_h2d(dOwn.p, own.data(), (size_t)n * 4);
+        bk_h2d((int32_t*)dOwn.p + n, ownOff.data(), (size_t)(C + 1) * 4);
+        poolBase.assign(C + 1, 0);
+        for (int c = 0; c < C; c++) poolBase[c + 1] = poolBase[c] + need[c];
+        std::vector<int32_t> prog(MAX_CTAS, 0x7fffffff);
+        for (int c = 0; c < C; c++) if (ownOff[c + 1] > ownOff[c]) prog[c] = own[ownOff[c]];
+        bk_h2d(dev.progress, prog.data(), MAX_CTAS * 4);
+        multiBatches++;
+      }
+    }
+    dEvents.ensure((size_t)(n > 0 ? n : 1) * sizeof(hived_event_t));
+    dResults.ensure((size_t)(n > 0 ? n : 1) * sizeof(hived_result_t));
+    dPool.ensure((size_t)(poolCap > 0 ? poolCap : 1) * 4);
+    if (n > 0) bk_h2d(dEvents.p, events, (size_t)n * sizeof(hived_event_t));
+    poolCapWords = poolCap;
+    stagedN = n;
+    stagedEvents = events;
+    return 0;
+  }
+  // health events change the host mirror (applied after the batch ran)
+  void trackHealth(const hived_event_t* events, int n) {
+    for (int i = 0; i < n; i++) {
+      if (events[i].type != HIVED_EV_NODE_HEALTH) continue;
+      int node = events[i].arg0;
+      if (node < 0 || node >= T.nNodes) continue;
+      char bad = events[i].arg1 ? 0 : 1;
+      if (nodeBadHost[node] != bad) { nodeBadHost[node] = bad; badCount += bad ? 1 : -1; }
+    }
+  }
+  // results + pool to the caller, in the canonical layout (pool slices in event order)
+  int fetch(hived_result_t* res, int32_t* pool, int64_t poolCap, int64_t* used) {
+    int n = stagedN;
+    if (n > 0) bk_d2h(res, dResults.p, (size_t)n * sizeof(hived_result_t));
+    if (launchCta == 1) {
+      if (poolOff > poolCap) return HIVED_ERR_CAPACITY;
+      if (poolOff > 0) bk_d2h(pool, dPool.p, (size_t)poolOff * 4);
+      if (used) *used = poolOff;
+      return 0;
+    }
+    long long span = poolBase[launchCta];
+    hostPool.resize((size_t)(span > 0 ? span : 1));
+    for (int c = 0; c < launchCta; c++)
+      if (poolEnd[c] > poolBase[c]) bk_d2h(hostPool.data() + poolBase[c], (int32_t*)dPool.p + poolBase[c], (size_t)(poolEnd[c] - poolBase[c]) * 4);
+    long long off = 0;
+    for (int i = 0; i < n; i++) {
+      hived_result_t& r = res[i];
+      if (r.kind == HIVED_KIND_BIND && r.n_leaves > 0) {
+        long long words = 3ll * r.n_leaves;
+        if (off + words > poolCap) return HIVED_ERR_CAPACITY;
+        memcpy(pool + off, hostPool.data() + r.leaf_off, (size_t)words * 4);
+        r.this_off = (int32_t)(off + (r.this_off - r.leaf_off));
+        r.leaf_off = (int32_t)off;
+        off += words;
+      } else if (r.kind == HIVED_KIND_PREEMPT && r.n_victims > 0) {
+        long long words = 2ll * r.n_victims;
+        if (off + words > poolCap) return HIVED_ERR_CAPACITY;
+        memcpy(pool + off, hostPool.data() + r.victim_off, (size_t)words * 4);
+        r.victim_off = (int32_t)off;
+        off += words;
+      }
+    }
+    poolOff = off;
+    if (used) *used = off;
+    return 0;
+  }
+  std::vector<int32_t> hostPool;
+  const hived_event_t* stagedEvents = nullptr;
+
   // stage + run a batch; host result/pool buffers are caller-owned
   int runBatch(const hived_event_t* events, int n, const uint32_t* suggPool, int64_t suggWords, const int32_t* aux,
                int64_t auxWords, hived_result_t* res, int32_t* pool, int64_t poolCap) {
     if (n <= 0) return 0;
-    dEvents.ensure((size_t)n * sizeof(hived_event_t));
-    dResults.ensure((size_t)n * sizeof(hived_result_t));
-    dPool.ensure((size_t)(poolCap > 0 ? poolCap : 1) * 4);
-    bk_h2d(dEvents.p, events, (size_t)n * sizeof(hived_event_t));
+    prepare(events, n, poolCap);
     hasSugg = suggPool != nullptr && suggWords > 0;
     if (hasSugg) { dSugg.ensure((size_t)suggWords * 4); bk_h2d(dSugg.p, suggPool, (size_t)suggWords * 4); }
     hasAux = aux != nullptr && auxWords > 0;
     if (hasAux) { dAux.ensure((size_t)auxWords * 4); bk_h2d(dAux.p, aux, (size_t)auxWords * 4); }
     poolOff = 0;
-    poolCapWords = poolCap;
     int rc = launchProgram(*this, n, false);
     if (rc) return rc;
-    bk_d2h(res, dResults.p, (size_t)n * sizeof(hived_result_t));
-    if (poolOff > 0) bk_d2h(pool, dPool.p, (size_t)poolOff * 4);
-    return 0;
+    trackHealth(events, n);
+    return fetch(res, pool, poolCap, nullptr);
   }
   bool hasSugg = false, hasAux = false;
   int64_t poolCapWords = 0;
   int stagedN = 0;
   int stage(const hived_event_t* events, int n, int64_t poolCap) {
-    dEvents.ensure((size_t)(n > 0 ? n : 1) * sizeof(hived_event_t));
-    dResults.ensure((size_t)(n > 0 ? n : 1) * sizeof(hived_result_t));
-    dPool.ensure((size_t)(poolCap > 0 ? poolCap : 1) * 4);
-    if (n > 0) bk_h2d(dEvents.p, events, (size_t)n * sizeof(hived_event_t));
     hasSugg = false; hasAux = false;
-    poolCapWords = poolCap;
-    stagedN = n;
-    return 0;
+    return prepare(events, n, poolCap);
   }
   int runStaged() {
     poolOff = 0;
+    if (launchCta > 1) {  // the progress words were consumed by the previous run
+      std::vector<int32_t> own(stagedN), prog(MAX_CTAS, 0x7fffffff);
+      bk_d2h(own.data(), dOwn.p, (size_t)stagedN * 4);
+      for (int c = 0; c < launchCta; c++) if (ownOff[c + 1] > ownOff[c]) prog[c] = own[ownOff[c]];
+      bk_h2d(dev.progress, prog.data(), MAX_CTAS * 4);
+    }
     return launchProgram(*this, stagedN, false);
   }
 
@@ -421,12 +559,9 @@ int hived_bench_stage_events(hived_ctx* ctx, const hived_event_t* events, int32_
 int hived_bench_run_staged(hived_ctx* ctx) { return ctx->e.runStaged(); }
 int hived_bench_fetch_results(hived_ctx* ctx, hived_result_t* res, int32_t* pool, int64_t pool_cap, int64_t* pool_used) {
   hived::Engine& e = ctx->e;
-  if (e.poolOff > pool_cap) return HIVED_ERR_CAPACITY;
-  hived::bk_d2h(res, e.dResults.p, (size_t)e.stagedN * sizeof(hived_result_t));
-  if (e.poolOff > 0) hived::bk_d2h(pool, e.dPool.p, (size_t)e.poolOff * 4);
-  *pool_used = e.poolOff;
-  return 0;
+  return e.fetch(res, pool, pool_cap, pool_used);
 }
+int hived_bench_num_ctas(hived_ctx* ctx) { return ctx->e.launchCta; }
 int hived_bench_flush_l2(hived_ctx*) { hived::bk_flush_l2(); return 0; }
 /* out[0..7): SM cycles in view pass, leaf search, mapping, result emission, commit, delete, all events */
 int hived_bench_phase_cycles(hived_ctx* ctx, int64_t* out) {

@@ -35,6 +35,12 @@ inline int hv_shfl_xor(int v, int) { return v; }
 inline int hv_atomic_min(int* a, int v) { int o = *a; if (v < o) *a = v; return o; }
 inline int hv_atomic_add(int* a, int v) { int o = *a; *a = o + v; return o; }
 inline long long hv_clock() { return 0; }
+inline int hv_ld_volatile(const int* p) { return *p; }
+inline void hv_st_volatile(int* p, int v) { *p = v; }
+inline void hv_fence() {}
+inline void hv_atomic_add64(long long* a, long long v) { *a += v; }
+inline void hv_atomic_or64(long long* a, long long v) { *a |= v; }
+inline int hv_cta() { return 0; }
 }  // namespace hived
 #define HV_ST(ptr, val) (*(ptr) = (val))
 #else
@@ -60,6 +66,12 @@ __device__ __forceinline__ int hv_shfl_xor(int v, int m) { return __shfl_xor_syn
 __device__ __forceinline__ int hv_atomic_min(int* a, int v) { return atomicMin(a, v); }
 __device__ __forceinline__ int hv_atomic_add(int* a, int v) { return atomicAdd(a, v); }
 __device__ __forceinline__ long long hv_clock() { return clock64(); }
+__device__ __forceinline__ int hv_ld_volatile(const int* p) { return *(const volatile int*)p; }
+__device__ __forceinline__ void hv_st_volatile(int* p, int v) { *(volatile int*)p = v; }
+__device__ __forceinline__ void hv_fence() { __threadfence(); }
+__device__ __forceinline__ void hv_atomic_add64(long long* a, long long v) { atomicAdd((unsigned long long*)a, (unsigned long long)v); }
+__device__ __forceinline__ void hv_atomic_or64(long long* a, long long v) { atomicOr((unsigned long long*)a, (unsigned long long)v); }
+__device__ __forceinline__ int hv_cta() { return blockIdx.x; }
 }  // namespace hived
 // leader-warp store: one lane writes, the warp is re-converged and the store ordered before later loads
 #define HV_ST(ptr, val)                      \

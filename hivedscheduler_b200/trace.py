@@ -98,7 +98,7 @@ class TraceBuilder:
         self.next_pod += 1
         return self.next_pod - 1
 
-    def delete_allocated(self, group: int, leaf_num: int, pod_index: int):
+    def delete_allocated(self, group: int, leaf_num: int, pod_index: int, vc: int = -1):
         self._grow()
         e = self.ev[self.n]
         e["type"] = _cabi.EV_DELETE_ALLOCATED
@@ -106,6 +106,7 @@ class TraceBuilder:
         e["suggested_off"] = -1
         e["spec"]["group"] = group
         e["spec"]["leaf_num"] = leaf_num
+        e["spec"]["vc"] = vc  # the pod's VC (from its annotation): routes the event to the CTA owning the VC
         self.n += 1
 
     def node_health(self, node: int, healthy: bool):
@@ -170,7 +171,7 @@ def trace_c3(n_gangs: int = 100000, n_vcs: int = 8, vc_gpus: int = 7168, load: f
         while alive_gpus[v] + size > limit and alive[v]:
             og, opn, oln = alive[v].popleft()
             for j in range(opn):
-                tb.delete_allocated(og, oln, j)
+                tb.delete_allocated(og, oln, j, vc=v)
             alive_gpus[v] -= opn * oln
         for j in range(pod_num):
             tb.schedule(group=g, vc=v, priority=0, leaf_type=0, leaf_num=leaf_num, pod_num=pod_num, first=(j == 0))

@@ -18,6 +18,7 @@ int hived_bench_phase_cycles(hived_ctx*, int64_t* out);
 double hived_bench_last_kernel_ms(hived_ctx*);   /* CUDA-event time of the last launch, on its stream */
 double hived_bench_total_kernel_ms(hived_ctx*);
 int64_t hived_bench_kernel_launches(hived_ctx*);
+int hived_bench_num_ctas(hived_ctx*);            /* CTAs the last batch ran on (VC-parallel execution) */
 #ifdef __cplusplus
 }
 #endif

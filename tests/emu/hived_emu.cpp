@@ -18,14 +18,19 @@ void bk_d2d(void* dst, const void* src, size_t bytes) { memcpy(dst, src, bytes);
 int bk_init(int, std::string&) { return 0; }
 void bk_flush_l2() {}
 int launchProgram(Engine& e, int n, bool withInit) {
+  // the emulation runs ONE CTA: VC-parallel batches are exercised on the GPU only
+  e.launchCta = 1;
+  e.poolBase.assign(2, 0);
+  e.poolBase[1] = withInit ? 0 : e.poolCapWords;
   static Sm sm;
   memset(&sm, 0, sizeof sm);
-  sm.pool_off = e.poolOff;
-  Core core(e.dev, &sm, (int32_t*)e.dPool.p, withInit ? 0 : e.poolCapWords);
+  sm.pool_off = 0;
+  Core core(e.dev, &sm, (int32_t*)e.dPool.p, withInit ? 0 : e.poolCapWords, 1);
   core.run((const hived_event_t*)e.dEvents.p, n, (hived_result_t*)e.dResults.p,
            e.hasSugg ? (const uint32_t*)e.dSugg.p : nullptr, e.hasAux ? (const int32_t*)e.dAux.p : nullptr,
-           withInit ? (const int32_t*)e.dInit.p : nullptr, e.nPinnedOrder, e.nBad);
+           withInit ? (const int32_t*)e.dInit.p : nullptr, e.nPinnedOrder, e.nBad, nullptr, n);
   e.poolOff = sm.pool_off;
+  e.poolEnd.assign(1, sm.pool_off);
   e.kernelLaunches++;
   if (withInit && sm.panic) { e.err = "initialisation panicked"; return sm.panic; }
   return 0;
