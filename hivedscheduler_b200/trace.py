@@ -182,6 +182,134 @@ def trace_c3(n_gangs: int = 100000, n_vcs: int = 8, vc_gpus: int = 7168, load: f
             "n_groups": n_gangs, "n_pods": tb.next_pod, "max_group_leaves": 64, "max_group_pods": 8}
 
 
+def trace_c5(n_steps: int = 10, gangs_per_step: int = 2000, n_nodes: int = 8192, n_vcs: int = 8, vc_gpus: int = 7168,
+             flip_fraction: float = 0.1, load: float = 0.9, config=None) -> Dict[str, Any]:
+    """C5: churn — every step flips the health of 10 % PRNG-chosen nodes, then schedules 2000 gangs
+    (C3 mix, admission window).  Gangs on nodes that went bad stay allocated (hived_algorithm.go:677-682)."""
+    rng = XorShift64Star(seed_for(5))
+    tb = TraceBuilder(8 * n_steps * gangs_per_step)
+    healthy = [True] * n_nodes
+    alive: List[deque] = [deque() for _ in range(n_vcs)]
+    alive_gpus = [0] * n_vcs
+    limit = int(load * vc_gpus)
+    g = 0
+    for _ in range(n_steps):
+        for _k in range(int(flip_fraction * n_nodes)):
+            node = rng.below(n_nodes)
+            healthy[node] = not healthy[node]
+            tb.node_health(node, healthy[node])
+        for _k in range(gangs_per_step):
+            pod_num, leaf_num = _gang_shape(rng.below(100))
+            v = rng.below(n_vcs)
+            size = pod_num * leaf_num
+            while alive_gpus[v] + size > limit and alive[v]:
+                og, opn, oln = alive[v].popleft()
+                for j in range(opn):
+                    tb.delete_allocated(og, oln, j, vc=v)
+                alive_gpus[v] -= opn * oln
+            for j in range(pod_num):
+                tb.schedule(group=g, vc=v, priority=0, leaf_type=0, leaf_num=leaf_num, pod_num=pod_num, first=(j == 0))
+            alive[v].append((g, pod_num, leaf_num))
+            alive_gpus[v] += size
+            g += 1
+    ev, dec = tb.finish()
+    return {"name": "C5", "config": config if config is not None else config_c3(), "events": ev, "decision": dec,
+            "n_groups": g, "n_pods": tb.next_pod, "max_group_leaves": 64, "max_group_pods": 8}
+
+
+def run_c4_interactive(lib, config, n_gangs: int, n_vcs: int, vc_gpus: int, total_gpus: int, load: float = 0.9,
+                       max_groups: int = None):
+    """C4: guaranteed (priority 0/1/2, lazyPreemptionEnable false) and opportunistic (-1) gangs interleaved by
+    the PRNG.  The event stream depends on the decisions, so the harness plays kube-scheduler call by call
+    (SURVEY.md section 8d): Filtering-phase Schedule; on a preempt result -> Preempting-phase Schedule ->
+    delete every pod of every victim gang -> Filtering-phase Schedule again.  Returns (hash, decision log)."""
+    rng = XorShift64Star(seed_for(4))
+    bc = BatchContext(lib, config, max_groups or (n_gangs + 8), 8 * n_gangs + 64, 64, 8)
+    bc.set_all_nodes_healthy()
+    tb = TraceBuilder(4)
+    pod_home = {}      # pod id -> (group, leaf_num, pod_index, vc)
+    group_pods = {}    # group -> [pod ids]
+    group_size = {}
+    alive = [deque() for _ in range(n_vcs)]
+    alive_gpus = [0] * n_vcs
+    opp_alive, opp_gpus = deque(), 0
+    log = []
+
+    def one(ev_builder):
+        tb.n = 0
+        ev_builder()
+        res, pool = bc.process(tb.ev[:tb.n].copy(), 4096)
+        return res[0], pool
+
+    def delete_group(g, v):
+        for pid in group_pods.pop(g, []):
+            _, ln, pi, _ = pod_home.pop(pid)
+            one(lambda: tb.delete_allocated(g, ln, pi, vc=v))
+
+    for g in range(n_gangs):
+        pod_num, leaf_num = _gang_shape(rng.below(100))
+        v = rng.below(n_vcs)
+        opportunistic = rng.below(2) == 1
+        prio = -1 if opportunistic else rng.below(3)
+        size = pod_num * leaf_num
+        if opportunistic:
+            while opp_gpus + size > int(load * total_gpus) and opp_alive:
+                og, ov = opp_alive.popleft()
+                if og in group_pods:
+                    opp_gpus -= group_size[og]
+                    delete_group(og, ov)
+        else:
+            while alive_gpus[v] + size > int(load * vc_gpus) and alive[v]:
+                og = alive[v].popleft()
+                if og in group_pods:
+                    alive_gpus[v] -= group_size[og]
+                    delete_group(og, v)
+        bound = True
+        for j in range(pod_num):
+            def sched(phase):
+                pid = tb.next_pod
+                tb.schedule(group=g, vc=v, priority=prio, leaf_type=0, leaf_num=leaf_num, pod_num=pod_num, phase=phase,
+                            flags=_cabi.SPEC_IGNORE_SUGGESTED, first=(j == 0))
+                return pid
+            holder = {}
+            r, pool = one(lambda: holder.setdefault("pid", sched(_cabi.PHASE_FILTERING)))
+            if r["kind"] == _cabi.KIND_PREEMPT:
+                r, pool = one(lambda: holder.__setitem__("pid", sched(_cabi.PHASE_PREEMPTING)))
+                victims = sorted({int(pool[r["victim_off"] + 2 * k]) for k in range(int(r["n_victims"]))})
+                log.append((g, j, "preempt", tuple(victims)))
+                for vg in sorted({pod_home[p][0] for p in victims if p in pod_home}):
+                    vv = pod_home[group_pods[vg][0]][3]
+                    if vg in group_size:
+                        if vv >= 0 and vg in alive[vv]:
+                            alive_gpus[vv] -= group_size[vg]
+                        elif vv < 0:
+                            opp_gpus -= group_size[vg]
+                    delete_group(vg, vv if vv >= 0 else 0)
+                r, pool = one(lambda: holder.__setitem__("pid", sched(_cabi.PHASE_FILTERING)))
+            if r["kind"] == _cabi.KIND_BIND:
+                pid = holder["pid"]
+                pod_home[pid] = (g, leaf_num, int(r["pod_index"]), -1 if opportunistic else v)
+                group_pods.setdefault(g, []).append(pid)
+                log.append((g, j, "bind", int(r["node"]),
+                            tuple(int(pool[r["this_off"] + 3 * k + 1]) for k in range(int(r["this_n"])))))
+            else:
+                log.append((g, j, "wait" if r["kind"] == _cabi.KIND_WAIT else "preempt-again", int(r["wait_code"])))
+                bound = False
+                break
+        if bound:
+            group_size[g] = size
+            if opportunistic:
+                opp_alive.append((g, v)); opp_gpus += size
+            else:
+                alive[v].append(g); alive_gpus[v] += size
+        elif g in group_pods:
+            delete_group(g, v)
+    h = bc.result_hash()
+    stats = bc.stats()
+    bc.close()
+    return h, log, stats
+
+
 # ------------------------------------------------------------------------------------------------
 # batch driver
 # ------------------------------------------------------------------------------------------------

@@ -43,3 +43,28 @@ def test_emu_matches_oracle_on_small_c3(emu_lib, oracle_lib):
     assert se == so
     sched = t["events"]["type"] == 0
     assert (np.concatenate([r[0]["kind"] for r in re_])[sched] == 1).all()
+
+
+def small_cluster():
+    return config.config_c3(n_pods=4, n_vcs=2, racks_per_vc=6)
+
+
+def test_emu_matches_oracle_under_churn_c5(emu_lib, oracle_lib):
+    """C5 shape at a size the oracle finishes in seconds: node health flips + gangs (rows a11, a18)."""
+    t = trace.trace_c5(n_steps=4, gangs_per_step=300, n_nodes=4 * 16 * 32, n_vcs=2, vc_gpus=(16 + 6) * 32 * 8,
+                       config=small_cluster())
+    he, re_, se = run_trace(emu_lib, t, chunks=2)
+    ho, ro, so = run_trace(oracle_lib, t, chunks=2)
+    assert he == ho and se == so
+    kinds = np.concatenate([r[0]["kind"] for r in re_])[t["events"]["type"] == 0]
+    assert (kinds == 1).sum() > 500  # most gangs still bind around the bad nodes
+
+
+def test_emu_matches_oracle_with_preemption_c4(emu_lib, oracle_lib):
+    """C4 shape (guaranteed priorities 0/1/2 + opportunistic, kube-scheduler emulation) — rows a12, a19."""
+    kw = dict(config=small_cluster(), n_gangs=2500, n_vcs=2, vc_gpus=(16 + 6) * 32 * 8, total_gpus=4 * 16 * 32 * 8)
+    he, le, se = trace.run_c4_interactive(emu_lib, **kw)
+    ho, lo, so = trace.run_c4_interactive(oracle_lib, **kw)
+    assert le == lo
+    assert he == ho and se == so
+    assert any(x[2] == "preempt" for x in le), "the scenario is expected to exercise preemption"

@@ -118,3 +118,45 @@ def test_schedule_is_idempotent_without_commit(cuda_lib):
     b = h.Schedule(pod, h.node_names, alg.FILTERING_PHASE).pod_bind_info
     assert a == b and a["leafCellIsolation"] == [0, 1]
     h.close()
+
+
+def test_cuda_matches_oracle_under_churn_c5(cuda_lib, oracle_lib):
+    """C5 shape: node-health flips (single-CTA path: health events are global) — rows a11, a18."""
+    from test_device_program_emu import small_cluster
+    t = trace.trace_c5(n_steps=4, gangs_per_step=300, n_nodes=4 * 16 * 32, n_vcs=2, vc_gpus=(16 + 6) * 32 * 8,
+                       config=small_cluster())
+    hc, rc, sc = run_trace(cuda_lib, t, chunks=2)
+    ho, ro, so = run_trace(oracle_lib, t, chunks=2)
+    assert hc == ho and sc == so
+    for (a, pa), (b, pb) in zip(rc, ro):
+        assert a.tobytes() == b.tobytes()
+
+
+def test_cuda_matches_oracle_with_preemption_c4(cuda_lib, oracle_lib):
+    """C4 shape: priorities 0/1/2 + opportunistic pods, call-by-call kube-scheduler emulation — rows a12, a19."""
+    from test_device_program_emu import small_cluster
+    kw = dict(config=small_cluster(), n_gangs=1200, n_vcs=2, vc_gpus=(16 + 6) * 32 * 8, total_gpus=4 * 16 * 32 * 8)
+    hc, lc, sc = trace.run_c4_interactive(cuda_lib, **kw)
+    ho, lo, so = trace.run_c4_interactive(oracle_lib, **kw)
+    assert lc == lo
+    assert hc == ho and sc == so
+
+
+def test_vc_parallel_equals_single_cta(cuda_lib):
+    """The VC-parallel execution (one CTA per group of VCs) must give the bytes of the sequential one."""
+    import subprocess, sys
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "from hivedscheduler_b200 import _cabi, trace\n"
+            "from conftest import run_trace\n"
+            "from test_device_program_emu import small_c3\n"
+            "import hashlib\n"
+            "h, res, st = run_trace(_cabi.load_cuda_library(), small_c3(4000))\n"
+            "m = hashlib.sha256()\n"
+            "for r, p in res:\n"
+            "    m.update(r.tobytes()); n = int((r['leaf_off'] + 3 * r['n_leaves']).max()); m.update(p[:n].tobytes())\n"
+            "print('%%016x %%s %%s' %% (h, m.hexdigest(), sorted(st.items())))\n") % (os.path.dirname(HERE), HERE)
+    outs = []
+    for ncta in ("1", "2", "16"):
+        env = dict(os.environ, HIVED_NCTA=ncta)
+        outs.append(subprocess.check_output([sys.executable, "-c", code], env=env).decode().strip().splitlines()[-1])
+    assert outs[0] == outs[1] == outs[2], outs
