@@ -50,7 +50,7 @@ def emu_lib():
     return _cabi.load_library(EMU_LIB)
 
 
-def run_trace(lib, t, n_events=None, chunks=1, device=0):
+def run_trace(lib, t, n_events=None, chunks=1, device=0, snapshots=None):
     """Replay a trace on a library; returns (hash, results, pool, stats)."""
     import numpy as np
     from hivedscheduler_b200 import trace
@@ -65,5 +65,19 @@ def run_trace(lib, t, n_events=None, chunks=1, device=0):
         all_res.append((res, pool))
         start = b
     out = (bc.result_hash(), all_res, bc.stats())
+    if snapshots is not None:
+        snapshots.append(snapshot_bytes(lib, bc.ctx))
     bc.close()
     return out
+
+
+def snapshot_bytes(lib, ctx):
+    """Every cell's (priority, state, health, binding, split/pinned/in-free-list) — the raw material of
+    GetClusterStatus (hived_algorithm.go:323-363) — as bytes, for cross-implementation comparison."""
+    import ctypes as C
+    from hivedscheduler_b200 import _cabi
+    n_p, n_v = lib.hived_num_physical_cells(ctx), lib.hived_num_virtual_cells(ctx)
+    ps, vs = (_cabi.CellStatus * n_p)(), (_cabi.CellStatus * n_v)()
+    assert lib.hived_snapshot_physical(ctx, ps, n_p) == 0
+    assert lib.hived_snapshot_virtual(ctx, vs, n_v) == 0
+    return bytes(ps) + bytes(vs)

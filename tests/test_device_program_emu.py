@@ -37,10 +37,12 @@ def small_c3(n_gangs=1500):
 
 def test_emu_matches_oracle_on_small_c3(emu_lib, oracle_lib):
     t = small_c3()
-    he, re_, se = run_trace(emu_lib, t, chunks=3)
-    ho, ro, so = run_trace(oracle_lib, t, chunks=3)
+    snaps = []
+    he, re_, se = run_trace(emu_lib, t, chunks=3, snapshots=snaps)
+    ho, ro, so = run_trace(oracle_lib, t, chunks=3, snapshots=snaps)
     assert he == ho
     assert se == so
+    assert snaps[0] == snaps[1]  # every cell's priority / state / health / binding / free-list membership
     sched = t["events"]["type"] == 0
     assert (np.concatenate([r[0]["kind"] for r in re_])[sched] == 1).all()
 
@@ -53,9 +55,11 @@ def test_emu_matches_oracle_under_churn_c5(emu_lib, oracle_lib):
     """C5 shape at a size the oracle finishes in seconds: node health flips + gangs (rows a11, a18)."""
     t = trace.trace_c5(n_steps=4, gangs_per_step=300, n_nodes=4 * 16 * 32, n_vcs=2, vc_gpus=(16 + 6) * 32 * 8,
                        config=small_cluster())
-    he, re_, se = run_trace(emu_lib, t, chunks=2)
-    ho, ro, so = run_trace(oracle_lib, t, chunks=2)
+    snaps = []
+    he, re_, se = run_trace(emu_lib, t, chunks=2, snapshots=snaps)
+    ho, ro, so = run_trace(oracle_lib, t, chunks=2, snapshots=snaps)
     assert he == ho and se == so
+    assert snaps[0] == snaps[1]
     kinds = np.concatenate([r[0]["kind"] for r in re_])[t["events"]["type"] == 0]
     assert (kinds == 1).sum() > 500  # most gangs still bind around the bad nodes
 

@@ -31,10 +31,12 @@ def test_cuda_reproduces_reference_golden_vectors(cuda_lib, oracle_lib):
 @pytest.mark.parametrize("name", ["C1", "C2", "C3-small"])
 def test_cuda_matches_oracle_on_trace(cuda_lib, oracle_lib, name):
     t = {"C1": trace.trace_c1, "C2": trace.trace_c2, "C3-small": small_c3}[name]()
-    hc, rc, sc = run_trace(cuda_lib, t, chunks=2)
-    ho, ro, so = run_trace(oracle_lib, t, chunks=2)
+    snaps = []
+    hc, rc, sc = run_trace(cuda_lib, t, chunks=2, snapshots=snaps)
+    ho, ro, so = run_trace(oracle_lib, t, chunks=2, snapshots=snaps)
     assert hc == ho
     assert sc == so
+    assert snaps[0] == snaps[1]  # cell state after the trace, incl. the ancestors repaired after VC-parallel batches
     for (a, pa), (b, pb) in zip(rc, ro):
         assert a.tobytes() == b.tobytes()
         n = int((a["leaf_off"] + 3 * a["n_leaves"]).max()) if len(a) else 0
