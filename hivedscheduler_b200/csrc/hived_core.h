@@ -665,6 +665,134 @@ struct Core {
     setPriority<false>(pLeaf, FREE_PRIO, ceil);
   }
 
+  // ---- fused fast paths of the two per-leaf sequences that dominate commit and delete.  Each is the
+  // exact composition of the generic functions above for the common case (guarded by the preconditions);
+  // anything else falls back to the generic sequence.
+
+  // == allocateLeafCell(pLeaf, vLeaf, p, vc); p_using = g; setCellState(pLeaf, Used, ceil)
+  //    for a guaranteed allocation that raises both leaves' priorities and whose preassigned cell is bound:
+  //    one gather over the levels (lane = level) instead of five dependent walks.
+  HIVED_DEV bool commitLeaf(int pLeaf, int vLeaf, int p, int vc, int g) {
+    const int ceil = ceilOf(vLeaf);
+    bool fast = vLeaf >= 0 && p != OPP_PRIO && p > d.v_prio[vLeaf] && p > d.p_prio[pLeaf] && d.v_pcell[d.v_pre[vLeaf]] >= 0;
+    if (!fast) {
+      bool safetyOk = allocateLeafCell(pLeaf, vLeaf, p, vc);
+      ST(d.p_using[pLeaf], g);
+      setCellState(pLeaf, HIVED_CELL_USED, ceil);
+      return safetyOk;
+    }
+    stat_add(ST_LEAVES, 1);
+    const bool leafUnbound = d.p_vcell[pLeaf] < 0;
+    // bindCell: the run of unbound virtual ancestors starting at the leaf
+    unsigned stopMask = leafUnbound ? levelMask(1, AS, [&](int l) { int va = d.v_anc[vLeaf * AS + l]; return va < 0 || d.v_pcell[va] >= 0; }) : 2u;
+    const int stop = stopMask ? hv_ffs(stopMask) - 1 : AS;
+    for (int b = 0; b < AS; b += HIVED_WARPSZ) {
+      int l = b + lane;
+      if (l >= 1 && l < AS) {
+        int pa = d.p_anc[pLeaf * AS + l], va = d.v_anc[vLeaf * AS + l];
+        if (va >= 0 && d.v_prio[va] < p) d.v_prio[va] = p;                 // setPriority<true>: raise
+        if (pa >= 0) {
+          if (l <= ceil && d.p_prio[pa] < p) d.p_prio[pa] = p;             // setPriority<false>: raise up to the ceiling
+          int bound = d.p_vcell[pa];
+          if (leafUnbound && l < stop) {                                   // bindCell
+            d.p_vcell[pa] = va; d.v_pcell[va] = pa; d.v_healthy[va] = d.p_healthy[pa];
+            bound = va;
+          }
+          if (l <= ceil) { d.p_state[pa] = HIVED_CELL_USED; if (bound >= 0) d.v_state[bound] = HIVED_CELL_USED; }  // setCellState(Used)
+        }
+      }
+    }
+    hv_warp_sync();
+    ST(d.p_using[pLeaf], g);
+    return true;
+  }
+
+  // == releaseLeafCell(pLeaf, vc); setCellState(pLeaf, Free, ceil)  for a healthy, bound, non-opportunistic leaf.
+  // The four upward walks of the generic code (virtual priority, unbinding, physical priority, state) advance
+  // together, one level per iteration, sharing one warp-wide scan of the siblings (lane = child).
+  HIVED_DEV void releaseLeafAndFree(int pLeaf, int vc) {
+    int vLeaf = d.p_vcell[pLeaf];
+    const int ceil = ceilOf(vLeaf);
+    if (vLeaf < 0 || !d.p_healthy[pLeaf] || d.p_prio[pLeaf] == OPP_PRIO) {
+      releaseLeafCell(pLeaf, vc);
+      setCellState(pLeaf, HIVED_CELL_FREE, ceil);
+      return;
+    }
+    stat_add(ST_LEAVES, 1);
+    const int pre = d.v_pre[vLeaf];
+    const int preP = d.v_pcell[pre];
+    int vOrig = d.v_prio[vLeaf], vNew = FREE_PRIO;
+    int pOrig = d.p_prio[pLeaf], pNew = FREE_PRIO;
+    bool wU = !(d.p_flags[pLeaf] & PF_PINNED_BIT);
+    hv_warp_sync();
+    ST(d.v_prio[vLeaf], FREE_PRIO);
+    ST(d.p_prio[pLeaf], FREE_PRIO);
+    if (wU) unbindPair(pLeaf, vLeaf);
+    ST(d.p_state[pLeaf], HIVED_CELL_FREE);
+    if (!wU) ST(d.v_state[vLeaf], HIVED_CELL_FREE);
+    bool wV = true, wP = true, wS = true;
+    int cv = vLeaf, cp = pLeaf;
+    for (int l = 2; l < AS + 1 && (wV || wU || wP || wS); l++) {
+      int pv = wV || wU ? d.v_parent[cv] : -1;
+      int pp = wP || wS ? d.p_parent[cp] : -1;
+      if (pv < 0) { wV = false; wU = false; }
+      if (pp < 0 || l - 1 >= ceil) { wP = false; wS = false; }
+      if (wV || wU) {
+        int vpp = d.v_prio[pv];
+        bool contV = wV && vOrig == vpp && vNew < vOrig;
+        int c0 = d.v_child0[pv], n = d.v_nchild[pv];
+        int mx = FREE_PRIO; bool anyBound = false;
+        for (int b = 0; b < n; b += HIVED_WARPSZ) {
+          int i = b + lane;
+          if (i < n && c0 + i != cv) {
+            int q = d.v_prio[c0 + i]; if (q > mx) mx = q;
+            if (d.v_pcell[c0 + i] >= 0) anyBound = true;
+          }
+        }
+        for (int o = HIVED_WARPSZ / 2; o > 0; o >>= 1) { int t = hv_shfl_xor(mx, o); if (t > mx) mx = t; }
+        anyBound = hv_ballot(anyBound) != 0;
+        if (wU) {
+          if (anyBound) {
+            wU = false;
+          } else {
+            int pvP = d.v_pcell[pv];
+            if (d.p_flags[pvP] & PF_PINNED_BIT) wU = false; else unbindPair(pvP, pv);
+          }
+        }
+        if (contV) { int np = mx > vNew ? mx : vNew; vOrig = vpp; vNew = np; ST(d.v_prio[pv], np); } else wV = false;
+        cv = pv;
+      }
+      if (wP || wS) {
+        int ppp = d.p_prio[pp];
+        bool contP = wP && pOrig == ppp && pNew < pOrig;
+        int c0 = d.p_child0[pp], n = d.p_nchild[pp];
+        int mx = FREE_PRIO; bool anyNotFree = false;
+        for (int b = 0; b < n; b += HIVED_WARPSZ) {
+          int i = b + lane;
+          if (i < n && c0 + i != cp) {
+            int q = d.p_prio[c0 + i]; if (q > mx) mx = q;
+            if (d.p_state[c0 + i] != HIVED_CELL_FREE) anyNotFree = true;
+          }
+        }
+        for (int o = HIVED_WARPSZ / 2; o > 0; o >>= 1) { int t = hv_shfl_xor(mx, o); if (t > mx) mx = t; }
+        anyNotFree = hv_ballot(anyNotFree) != 0;
+        if (wS) {
+          if (anyNotFree) {
+            wS = false;
+          } else {
+            ST(d.p_state[pp], HIVED_CELL_FREE);
+            int v = d.p_vcell[pp];
+            if (v >= 0) ST(d.v_state[v], HIVED_CELL_FREE);
+          }
+        }
+        if (contP) { int np = mx > pNew ? mx : pNew; pOrig = ppp; pNew = np; ST(d.p_prio[pp], np); } else wP = false;
+        cp = pp;
+      }
+    }
+    // hived_algorithm.go:1343-1347: the preassigned cell is released once nothing in it is in real use
+    if (!(d.p_flags[preP] & PF_PINNED_BIT) && d.v_prio[pre] < 0 && !dm_contains(vc, preP)) releasePreassignedCell(preP, vc, false);
+  }
+
   // ======================================================================================
   // cluster-view pass: data-parallel over the CTA
   //   updateClusterView + sort.Stable + findNodesForPods (topology_aware_scheduler.go:231-306)
@@ -1436,8 +1564,7 @@ struct Core {
       ST(d.p_using[pLeaf], -1);
       const int ceil = ceilOf(d.p_vcell[pLeaf]);
       if (d.p_state[pLeaf] == HIVED_CELL_USED) {
-        releaseLeafCell(pLeaf, vc);
-        setCellState(pLeaf, HIVED_CELL_FREE, ceil);
+        releaseLeafAndFree(pLeaf, vc);
       } else {
         setCellState(pLeaf, HIVED_CELL_RESERVED, ceil);
       }
@@ -1898,9 +2025,7 @@ struct Core {
           } else {
             shouldLazyPreempt = shouldLazyPreempt || lazy == 2;
           }
-          bool safetyOk = allocateLeafCell(pLeaf, vLeaf, sp.priority, sp.vc);
-          ST(d.p_using[pLeaf], g);
-          setCellState(pLeaf, HIVED_CELL_USED, ceilOf(vLeaf));
+          bool safetyOk = commitLeaf(pLeaf, vLeaf, sp.priority, sp.vc, g);
           if (!safetyOk) shouldLazyPreempt = true;
           if (panicCode) return;
         }
