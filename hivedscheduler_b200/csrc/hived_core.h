@@ -46,6 +46,8 @@ struct Sm {
   int best;
   int cnt[MAX_BINS * MAX_WARPS];
   int part[MAX_WARPS + 32];
+  // ---- the current event, fetched with one coalesced 128-byte load
+  alignas(8) int32_t ev_words[sizeof(hived_event_t) / 4];
   // ---- written back at kernel exit
   int panic;
   long long pool_off;
@@ -2304,7 +2306,12 @@ struct Core {
         int i = own ? own[k] : k;
         curEvent = i;
         sharedHeld = false;
-        processEvent(events[i], &results[i], suggPool, aux);
+        {
+          const int32_t* src = reinterpret_cast<const int32_t*>(&events[i]);
+          for (int w = lane; w < (int)(sizeof(hived_event_t) / 4); w += HIVED_WARPSZ) sm->ev_words[w] = src[w];
+          hv_warp_sync();
+        }
+        processEvent(*reinterpret_cast<const hived_event_t*>(sm->ev_words), &results[i], suggPool, aux);
         if (multi) {
           int next = (k + 1 < nOwn) ? own[k + 1] : 0x7fffffff;
           hv_fence();  // release: everything this event wrote is visible before the progress moves on

@@ -7,6 +7,27 @@
 
 namespace hived {
 
+#if defined(__CUDACC__)
+#define HIVED_HD __host__ __device__ __forceinline__
+#else
+#define HIVED_HD inline
+#endif
+
+// An affinity group's scalars live in ONE 128-byte record (a decision touches a group it has not seen for
+// a while: one L2 round trip instead of eight).  Word layout: 0 state, 1 vc, 2 priority, 3 flags,
+// 4 #members, 5 #preempting pods, 8..15 member leaf numbers, 16..23 member pod numbers.
+constexpr int GROUP_HDR_WORDS = 32;
+template <int OFF>
+struct GroupFld {
+  int32_t* b;
+  HIVED_HD int32_t& operator[](long long g) const { return b[g * GROUP_HDR_WORDS + OFF]; }
+};
+template <int BASE>
+struct GroupMemFld {  // indexed by g * 8 + m like the flat arrays it replaces
+  int32_t* b;
+  HIVED_HD int32_t& operator[](long long i) const { return b[(i >> 3) * GROUP_HDR_WORDS + BASE + (i & 7)]; }
+};
+
 // X(name): static int32 array copied verbatim from FlatTopo::name
 #define HIVED_STATIC_ARRAYS(X)                                                                         \
   X(p_parent) X(p_child0) X(p_nchild) X(p_level) X(p_chain) X(p_leaf0) X(p_nleaf) X(p_node)           \
@@ -32,10 +53,9 @@ namespace hived {
   Y(fl_data, S.flTotal, -1) Y(fl_len, S.nChains * MAXL, 0) Y(bf_data, S.flTotal, -1)                   \
   Y(bf_len, S.nChains * MAXL, 0) Y(dm_data, S.dmTotal, -1) Y(dm_len, S.nVCs * S.nChains * MAXL, 0)     \
   Y(cv, S.cvTotal, -1) Y(node_bad, S.nNodes, 0)                                                        \
-  Y(g_state, S.maxGroups, 0) Y(g_vc, S.maxGroups, -1) Y(g_prio, S.maxGroups, 0) Y(g_flags, S.maxGroups, 0) \
-  Y(g_nmem, S.maxGroups, 0) Y(g_mem_leaf, S.maxGroups * 8, 0) Y(g_mem_pods, S.maxGroups * 8, 0)        \
+  Y(g_hdr, (int64_t)S.maxGroups * GROUP_HDR_WORDS, 0)                                                  \
   Y(g_phys, (int64_t)S.maxGroups * S.LS, -1) Y(g_virt, (int64_t)S.maxGroups * S.LS, -1)                \
-  Y(g_pods, (int64_t)S.maxGroups * S.PS, -1) Y(g_npre, S.maxGroups, 0)                                 \
+  Y(g_pods, (int64_t)S.maxGroups * S.PS, -1)                                                           \
   Y(g_pre, (int64_t)S.maxGroups * S.PS, -1) Y(pod_node, S.maxPods, -1) \
   Y(vx_of, S.NV, -1) Y(vx_stamp, S.NV, 0) Y(binding, S.NV, -1)
 
@@ -73,6 +93,8 @@ struct Dev {
 #define Y(name, count, init) int32_t* name;
   HIVED_MUTABLE_ARRAYS(Y)
 #undef Y
+  GroupFld<0> g_state; GroupFld<1> g_vc; GroupFld<2> g_prio; GroupFld<3> g_flags; GroupFld<4> g_nmem; GroupFld<5> g_npre;
+  GroupMemFld<8> g_mem_leaf; GroupMemFld<16> g_mem_pods;
   long long* stats;        // [ST_COUNT] counters, see ST_* below
   int32_t* epoch;          // [MAX_CTAS] per-CTA stamp for vx_stamp
   const Scratch* scratch;  // [nCta] private scratch arrays of every CTA

@@ -131,6 +131,13 @@ struct Engine {
   }
     HIVED_MUTABLE_ARRAYS(Y)
 #undef Y
+    dev.g_state.b = dev.g_vc.b = dev.g_prio.b = dev.g_flags.b = dev.g_nmem.b = dev.g_npre.b = dev.g_hdr;
+    dev.g_mem_leaf.b = dev.g_mem_pods.b = dev.g_hdr;
+    {  // g_vc starts at -1
+      std::vector<int32_t> hdr((size_t)S.maxGroups * GROUP_HDR_WORDS, 0);
+      for (int g = 0; g < S.maxGroups; g++) hdr[(size_t)g * GROUP_HDR_WORDS + 1] = -1;
+      bk_h2d(dev.g_hdr, hdr.data(), hdr.size() * 4);
+    }
     dev.stats = allocFill<long long>(ST_COUNT, 0);
     mutableRegions.push_back({dev.stats, ST_COUNT * sizeof(long long)});
     dev.epoch = allocFill<int32_t>(MAX_CTAS, 1);
@@ -482,13 +489,10 @@ int hived_get_group(hived_ctx* ctx, int32_t group, hived_group_info_t* out) {
   memset(out, 0, sizeof *out);
   hived::Engine& e = ctx->e;
   if (group < 0 || group >= e.dev.S.maxGroups) return 0;
-  int32_t v[5];
-  hived::bk_d2h(&v[0], e.dev.g_state + group, 4);
+  int32_t hdr[hived::GROUP_HDR_WORDS];
+  hived::bk_d2h(hdr, e.dev.g_hdr + (size_t)group * hived::GROUP_HDR_WORDS, sizeof hdr);
+  int32_t v[5] = {hdr[0], hdr[1], hdr[2], hdr[3], hdr[5]};
   if (v[0] == HIVED_GROUP_NONE) return 0;
-  hived::bk_d2h(&v[1], e.dev.g_vc + group, 4);
-  hived::bk_d2h(&v[2], e.dev.g_prio + group, 4);
-  hived::bk_d2h(&v[3], e.dev.g_flags + group, 4);
-  hived::bk_d2h(&v[4], e.dev.g_npre + group, 4);
   out->state = v[0]; out->vc = v[1]; out->priority = v[2];
   out->has_virtual = (v[3] & hived::GF_HAS_VIRTUAL) ? 1 : 0;
   out->n_preempting_pods = v[0] == HIVED_GROUP_PREEMPTING ? v[4] : 0;
