@@ -223,7 +223,7 @@ def main():
     used = C.c_int64()
     lib.hived_bench_fetch_results(ctx, res_ptr, pool_ptr, pool_words, C.byref(used))
     stats = bc.stats()
-    cyc = (C.c_int64 * 7)()
+    cyc = (C.c_int64 * 9)()
     lib.hived_bench_phase_cycles(ctx, cyc)
     # the restore + L2 flush between steps are not part of a step: time = sum of the kernels' CUDA-event times
     kernel_total_s = sum(kernel_ms) / 1e3
@@ -267,7 +267,7 @@ def main():
             line["cpu_baseline"] = {"value": v, "unit": "decisions/s", "cores": 1, "kind": "port",
                                     "sample": "first 1500 decisions (%d events) of the same C3 trace, %.1f s" % (nev, dt)}
         line["parity"] = {"result_hash": "%016x" % bc.result_hash()}
-        names = ["view_pass", "leaf_search", "map_v2p", "emit_result", "commit", "delete", "all_events"]
+        names = ["view_pass", "leaf_search", "map_v2p", "emit_result", "commit", "delete", "all_events", "shared_wait", "shared_sections"]
         line["phase_cycles_per_step"] = {n: int(c) for n, c in zip(names, cyc)}
         print(json.dumps(line))
     if world > 1:

@@ -89,6 +89,7 @@ struct Core {
   // complete), and later events that need the shared state wait for this one the same way.
   HIVED_DEV void sharedEnter() {
     if (!multi || sharedHeld) return;
+    long long tw0 = hv_clock();
     while (true) {
       int mn = 0x7fffffff;
       for (int b = 0; b < nCta; b += HIVED_WARPSZ) {
@@ -99,6 +100,8 @@ struct Core {
       if (mn > curEvent) break;
     }
     hv_fence();  // acquire: drop stale L1 lines of state written by the other CTAs
+    stat_add(ST_CYC_WAIT, hv_clock() - tw0);
+    stat_add(ST_SHARED_SECTIONS, 1);
     sharedHeld = true;
   }
   // highest physical level an event of this VC may write: in multi-CTA mode the cells above the

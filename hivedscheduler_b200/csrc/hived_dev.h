@@ -106,7 +106,8 @@ enum {
   ST_PREEMPT = 7, ST_PRIO_MASK = 8 /* bit (p+1) for small priorities, else bit 62 */,
   /* SM cycles spent per phase (leader warp), for profiles/ */
   ST_CYC_VIEW = 9, ST_CYC_LEAF = 10, ST_CYC_MAP = 11, ST_CYC_EMIT = 12, ST_CYC_COMMIT = 13, ST_CYC_DELETE = 14, ST_CYC_TOTAL = 15,
-  ST_COUNT = 16
+  ST_CYC_WAIT = 16 /* spinning at the entry of a shared section (VC-parallel mode) */, ST_SHARED_SECTIONS = 17,
+  ST_COUNT = 24
 };
 
 constexpr int MAX_CTAS = 32;

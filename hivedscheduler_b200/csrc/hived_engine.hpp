@@ -571,7 +571,7 @@ int hived_bench_flush_l2(hived_ctx*) { hived::bk_flush_l2(); return 0; }
 int hived_bench_phase_cycles(hived_ctx* ctx, int64_t* out) {
   long long st[hived::ST_COUNT];
   hived::bk_d2h(st, ctx->e.dev.stats, sizeof st);
-  for (int i = 0; i < 7; i++) out[i] = st[hived::ST_CYC_VIEW + i];
+  for (int i = 0; i < 9; i++) out[i] = st[hived::ST_CYC_VIEW + i];
   return 0;
 }
 double hived_bench_last_kernel_ms(hived_ctx* ctx) { return ctx->e.lastKernelMs; }

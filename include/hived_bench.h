@@ -13,7 +13,8 @@ int hived_bench_stage_events(hived_ctx*, const hived_event_t* events, int32_t n,
 int hived_bench_run_staged(hived_ctx*);     /* one kernel launch over the staged batch; nothing crosses PCIe */
 int hived_bench_fetch_results(hived_ctx*, hived_result_t* res, int32_t* pool, int64_t pool_cap, int64_t* pool_used);
 int hived_bench_flush_l2(hived_ctx*);       /* overwrite a buffer larger than L2 */
-/* out[0..7): SM cycles of the leader warp in {view pass, leaf search, v->p mapping, result emission, commit, delete, all} */
+/* out[0..9): SM cycles of the leader warps in {view pass, leaf search, v->p mapping, result emission, commit, delete,
+ * all events, waiting at shared sections} and the number of shared sections entered */
 int hived_bench_phase_cycles(hived_ctx*, int64_t* out);
 double hived_bench_last_kernel_ms(hived_ctx*);   /* CUDA-event time of the last launch, on its stream */
 double hived_bench_total_kernel_ms(hived_ctx*);
