@@ -1558,10 +1558,103 @@ struct Core {
     ST(d.g_flags[g], (fl | GF_HAS_VIRTUAL) & ~GF_LAZY_PREEMPTED);
   }
 
+  // ---- whole-gang release: the per-leaf loop of deleteAllocatedAffinityGroup for the common case (every leaf
+  // Used, healthy, bound, guaranteed, not pinned), with lanes over the gang's leaves and one step per tree level
+  // instead of one upward walk per leaf.  Equivalence with the sequential walks: leaf fields are independent;
+  // a parent's priority is the max of its children (cell_allocation.go:422-441 keeps that invariant), it turns
+  // Free iff all children are Free (utils.go:397-415) and is unbound iff no child stays bound
+  // (cell_allocation.go:399-420) — all functions of the children's FINAL values, so each level is computed once
+  // after the level below is complete (lanes sharing an ancestor write the same values).  Preassigned cells are
+  // released in the order of their last leaf, as the sequential loop would.  false: nothing written.
+  HIVED_DEV bool deleteGroupBatched(int g, int nl, int vc) {
+    const int32_t* ph = gphys(g);
+    bool bad = false;
+    for (int b0 = 0; b0 < nl; b0 += HIVED_WARPSZ) {
+      int i = b0 + lane;
+      bool ok = true;
+      if (i < nl) {
+        int L = ph[i];
+        ok = L >= 0;
+        int V = ok ? d.p_vcell[L] : -1;
+        ok = ok && V >= 0 && d.p_state[L] == HIVED_CELL_USED && d.p_healthy[L] && d.p_prio[L] != OPP_PRIO && !(d.p_flags[L] & PF_PINNED_BIT);
+        if (ok) {
+          int pre = d.v_pre[V];
+          s.pl_v[i] = V; s.pl_v2[i] = pre; s.pl_p[i] = d.v_pcell[pre];
+        }
+      }
+      if (hv_ballot(!ok)) bad = true;
+    }
+    if (bad) return false;
+    hv_warp_sync();
+    stat_add(ST_LEAVES, nl);
+    // level 1: the leaves themselves (releaseLeafCell :1319-1352 + setCellState Free)
+    for (int b0 = 0; b0 < nl; b0 += HIVED_WARPSZ) {
+      int i = b0 + lane;
+      if (i < nl) {
+        int L = ph[i], V = s.pl_v[i];
+        d.p_using[L] = -1;
+        d.v_prio[V] = FREE_PRIO; d.p_prio[L] = FREE_PRIO;
+        d.p_vcell[L] = -1; d.v_pcell[V] = -1; d.v_state[V] = HIVED_CELL_FREE; d.v_healthy[V] = 1;
+        d.p_state[L] = HIVED_CELL_FREE;
+      }
+    }
+    hv_warp_sync();
+    for (int l = 2; l < AS; l++) {
+      for (int b0 = 0; b0 < nl; b0 += HIVED_WARPSZ) {
+        int i = b0 + lane;
+        if (i < nl) {
+          int L = ph[i], V = s.pl_v[i];
+          int va = d.v_anc[V * AS + l], pa = d.p_anc[L * AS + l];
+          const int ceil = multi ? d.v_level[s.pl_v2[i]] : AS;
+          if (va >= 0) {
+            int c0 = d.v_child0[va], n = d.v_nchild[va];
+            int mx = FREE_PRIO; bool anyBound = false;
+            for (int j = 0; j < n; j++) { int q = d.v_prio[c0 + j]; if (q > mx) mx = q; if (d.v_pcell[c0 + j] >= 0) anyBound = true; }
+            d.v_prio[va] = mx;
+            if (!anyBound && d.v_pcell[d.v_anc[V * AS + l - 1]] < 0) {
+              int pvP = d.v_pcell[va];
+              if (pvP >= 0 && !(d.p_flags[pvP] & PF_PINNED_BIT)) { d.p_vcell[pvP] = -1; d.v_pcell[va] = -1; d.v_state[va] = HIVED_CELL_FREE; d.v_healthy[va] = 1; }
+            }
+          }
+          if (pa >= 0 && l <= ceil) {
+            int c0 = d.p_child0[pa], n = d.p_nchild[pa];
+            int mx = FREE_PRIO; bool allFree = true;
+            for (int j = 0; j < n; j++) { int q = d.p_prio[c0 + j]; if (q > mx) mx = q; if (d.p_state[c0 + j] != HIVED_CELL_FREE) allFree = false; }
+            d.p_prio[pa] = mx;
+            if (allFree) {
+              d.p_state[pa] = HIVED_CELL_FREE;
+              int v = d.p_vcell[pa];
+              if (v >= 0) d.v_state[v] = HIVED_CELL_FREE;
+            }
+          }
+        }
+      }
+      hv_warp_sync();
+    }
+    // hived_algorithm.go:1343-1347: a preassigned cell goes back once nothing in it is in real use
+    bool anyRelease = false;
+    for (int b0 = 0; b0 < nl; b0 += HIVED_WARPSZ) {
+      int i = b0 + lane;
+      bool c = i < nl && !(d.p_flags[s.pl_p[i]] & PF_PINNED_BIT) && d.v_prio[s.pl_v2[i]] < 0;
+      if (hv_ballot(c)) anyRelease = true;
+    }
+    if (anyRelease) {
+      for (int i = 0; i < nl; i++) {
+        int pre = s.pl_v2[i], preP = s.pl_p[i];
+        const int32_t* rest = s.pl_v2 + i + 1;
+        if (firstIdx(nl - i - 1, [&](int j) { return rest[j] == pre; }) >= 0) continue;  // a later leaf sits in the same cell
+        if (!(d.p_flags[preP] & PF_PINNED_BIT) && d.v_prio[pre] < 0 && !dm_contains(vc, preP)) releasePreassignedCell(preP, vc, false);
+        if (panicCode) return true;
+      }
+    }
+    return true;
+  }
+
   // hived_algorithm.go:1043-1070
   HIVED_DEV void deleteAllocatedAffinityGroup(int g) {
     int nl = groupLeaves(g);
     int vc = d.g_vc[g];
+    if (deleteGroupBatched(g, nl, vc)) { eraseGroup(g); return; }
     const int32_t* ph = gphys(g);
     for (int i = 0; i < nl; i++) {
       int pLeaf = ph[i];
@@ -1977,9 +2070,141 @@ struct Core {
     return -1;
   }
 
+  // ---- whole-gang commit: the per-leaf loop of createAllocatedAffinityGroup (below) for the common case, with
+  // lanes over the gang's leaves.  Preconditions (else false, nothing written): a fresh placement (cells known,
+  // slots in emission order), a guaranteed priority above everything on the leaves, every leaf under an already
+  // bound preassigned cell — then no free-list work, lazy preemption or safety check can occur.
+  // The sequential loop gives every not-yet-bound physical cell on a leaf's path the FIRST free unbound child
+  // of its parent's virtual cell (mapPhysicalCellToVirtual / getLowestPriorityVirtualCell) and binds the path
+  // before looking at the next leaf; so under one virtual cell the r-th new child (in order of first
+  // appearance among the leaves) gets the r-th free unbound virtual child: a rank/select per level, top-down.
+  // Afterwards priorities only rise (max per ancestor) and states only become Used.
+  HIVED_DEV bool commitGroupBatched(const hived_pod_spec_t& sp, const BindView& b, int g) {
+    const int p = sp.priority, chain = b.chain;
+    if (!b.physIds || !b.has_preassigned || p < 0 || sp.vc < 0 || sp.vc >= d.S.nVCs || chain < 0 || chain >= d.S.nChains) return false;
+    if (sp.pinned != -1) {
+      if (sp.pinned < 0 || sp.pinned >= d.S.nPinned || d.vc_pinned_vset[sp.vc * d.S.nPinned + sp.pinned] < 0) return false;
+    } else if (d.vc_chain_vset[sp.vc * d.S.nChains + chain] < 0) {
+      return false;
+    }
+    if (b.n_members != d.g_nmem[g]) return false;
+    int nl = 0;
+    for (int m = 0; m < b.n_members; m++) {
+      if (b.member_leaf_num[m] != d.g_mem_leaf[g * 8 + m] || b.member_pod_num[m] != d.g_mem_pods[g * 8 + m]) return false;
+      nl += b.member_leaf_num[m] * b.member_pod_num[m];
+    }
+    const int top = d.chain_top[chain];
+    bool bad = false;
+    int maxLs = 0;
+    for (int b0 = 0; b0 < nl; b0 += HIVED_WARPSZ) {
+      int i = b0 + lane;
+      bool ok = true;
+      int ls = 0;
+      if (i < nl) {
+        int L = b.physIds[i], t = b.leaves[3 * i + 2];
+        int preLevel = -1;
+        for (int l = 1; l <= top; l++) if (d.chain_lvl_type[cl(chain, l)] == t) preLevel = l;
+        ok = L >= 0 && t != -1 && preLevel >= 1;
+        ok = ok && d.p_chain[L] == chain && d.p_prio[L] < p;
+        if (ok) {
+          ls = AS;
+          for (int l = 1; l < AS; l++) {
+            int a = d.p_anc[L * AS + l];
+            if (a < 0 || d.p_vcell[a] >= 0 || l == preLevel) { ls = l; break; }
+          }
+          int a = ls < AS ? d.p_anc[L * AS + ls] : -1;
+          ok = a >= 0 && d.p_vcell[a] >= 0;
+          if (ok && ls == 1) ok = d.v_prio[d.p_vcell[L]] < p;
+          s.pl_v2[i] = ls;
+        }
+      }
+      if (hv_ballot(!ok)) bad = true;
+      for (int o = HIVED_WARPSZ / 2; o > 0; o >>= 1) { int t2 = hv_shfl_xor(ls, o); if (t2 > ls) ls = t2; }
+      if (ls > maxLs) maxLs = ls;
+    }
+    if (bad) return false;
+    hv_warp_sync();
+    // bind, top-down
+    bool failed = false;
+    for (int l = maxLs - 1; l >= 1 && !failed; l--) {
+      for (int b0 = 0; b0 < nl && !failed; b0 += HIVED_WARPSZ) {
+        int i = b0 + lane;
+        bool active = i < nl && l < s.pl_v2[i];
+        int pa = -1, pv = -1;
+        bool isNew = false;
+        if (active) {
+          int L = b.physIds[i];
+          pa = d.p_anc[L * AS + l];
+          pv = d.p_vcell[d.p_anc[L * AS + l + 1]];
+          isNew = d.p_vcell[pa] < 0;
+        }
+        unsigned grp = hv_match(active ? pa : -1 - lane);
+        bool leader = active && isNew && hv_ffs(grp) - 1 == lane;
+        unsigned sib = hv_match(leader ? pv : -1 - lane);
+        int rank = hv_popc(sib & hv_lanemask_lt());
+        int sel = -1;
+        if (leader) {
+          int c0 = d.v_child0[pv], n = d.v_nchild[pv], cnt = 0;
+          for (int j = 0; j < n; j++) {
+            if (d.v_prio[c0 + j] == FREE_PRIO && d.v_pcell[c0 + j] < 0) {
+              if (cnt == rank) { sel = c0 + j; break; }
+              cnt++;
+            }
+          }
+        }
+        if (hv_ballot(leader && sel < 0)) { failed = true; break; }
+        if (leader) { d.p_vcell[pa] = sel; d.v_pcell[sel] = pa; d.v_healthy[sel] = d.p_healthy[pa]; }
+        hv_warp_sync();
+      }
+    }
+    if (failed) {  // no free unbound virtual cell somewhere: undo the bindings, let the sequential loop decide
+      hv_warp_sync();
+      for (int b0 = 0; b0 < nl; b0 += HIVED_WARPSZ) {
+        int i = b0 + lane;
+        if (i < nl) {
+          int L = b.physIds[i];
+          for (int l = 1; l < s.pl_v2[i]; l++) {
+            int pa = d.p_anc[L * AS + l];
+            int v = d.p_vcell[pa];
+            if (v >= 0) { d.p_vcell[pa] = -1; d.v_pcell[v] = -1; d.v_state[v] = HIVED_CELL_FREE; d.v_healthy[v] = 1; }
+          }
+        }
+        hv_warp_sync();
+      }
+      return false;
+    }
+    // allocateLeafCell (raise) + using group + setCellState(Used), all leaves at once
+    stat_add(ST_LEAVES, nl);
+    int32_t* ph = gphys(g);
+    int32_t* vi = gvirt(g);
+    for (int b0 = 0; b0 < nl; b0 += HIVED_WARPSZ) {
+      int i = b0 + lane;
+      if (i < nl) {
+        int L = b.physIds[i];
+        int V = d.p_vcell[L];
+        const int ceil = multi ? d.v_level[d.v_pre[V]] : AS;
+        for (int l = 1; l < AS; l++) {
+          int pa = d.p_anc[L * AS + l], va = d.v_anc[V * AS + l];
+          if (va >= 0 && d.v_prio[va] < p) d.v_prio[va] = p;
+          if (pa >= 0 && l <= ceil) {
+            if (d.p_prio[pa] < p) d.p_prio[pa] = p;
+            d.p_state[pa] = HIVED_CELL_USED;
+            int bound = d.p_vcell[pa];
+            if (bound >= 0) d.v_state[bound] = HIVED_CELL_USED;
+          }
+        }
+        d.p_using[L] = g;
+        ph[i] = L; vi[i] = V;
+      }
+    }
+    hv_warp_sync();
+    return true;
+  }
+
   HIVED_DEV_NOINLINE void createAllocatedAffinityGroup(const hived_pod_spec_t& sp, const BindView& b) {
     int g = sp.group;
     newGroup(g, sp, HIVED_GROUP_ALLOCATED);
+    if (commitGroupBatched(sp, b, g)) return;
     bool shouldLazyPreempt = false;
     bool hasVirtualFlag = true;
     int32_t* ph = gphys(g);
