@@ -1773,6 +1773,107 @@ struct Core {
     }
   }
 
+  // ---- whole-placement mapping: toBindingPaths + mapVirtualPlacementToPhysical for the common case, lanes over
+  // the placement's virtual leaves.  Preconditions (else false; only scratch was written): every leaf has a
+  // bound virtual ancestor (no preassigned cell to allocate, hence no buddy allocation), no suggested-node
+  // filter, and every unbound child of the physical cells searched is healthy with no opportunistic use.  Then
+  // every candidate is usable, the stable sort by used[opportunistic] is the identity, no pick can fail, and the
+  // backtracking search of cell_allocation.go:245-315 degenerates to: the r-th new virtual child (in order of
+  // first appearance among the leaves) of a bound virtual cell gets the r-th unbound child of its physical cell,
+  // and below that the j-th child vertex gets the j-th child — a rank/select per level, top-down.
+  // Scratch: vx_stamp[x] == epochNow marks a virtual cell touched by this pass; binding[x] its physical cell
+  // (for unbound x), vx_of[x] the number of its children mapped so far.
+  HIVED_DEV bool mapPlacementBatched(const int32_t* vleaves, int nleaves, bool ignoreSuggested) {
+    if (sugg != nullptr && !ignoreSuggested) return false;
+    epochNow = d.epoch[cta] + 1;
+    hv_warp_sync();
+    ST(d.epoch[cta], epochNow);
+    bool bad = false;
+    int maxLs = 0;
+    for (int b0 = 0; b0 < nleaves; b0 += HIVED_WARPSZ) {
+      int i = b0 + lane;
+      bool ok = true;
+      int ls = 0;
+      if (i < nleaves) {
+        int v = vleaves[i];
+        int pl = d.v_pcell[v];
+        if (pl >= 0) {
+          d.binding[v] = pl;
+          ls = 1;
+        } else {
+          ls = AS;
+          for (int l = 2; l < AS; l++) {
+            int a = d.v_anc[v * AS + l];
+            if (a < 0 || d.v_pcell[a] >= 0) { ls = l; break; }
+          }
+          ok = ls < AS && d.v_anc[v * AS + ls] >= 0;
+        }
+        s.pl_v2[i] = ls;
+      }
+      if (hv_ballot(!ok)) bad = true;
+      for (int o = HIVED_WARPSZ / 2; o > 0; o >>= 1) { int t = hv_shfl_xor(ls, o); if (t > ls) ls = t; }
+      if (ls > maxLs) maxLs = ls;
+    }
+    if (bad) return false;
+    hv_warp_sync();
+    long long scanned = 0;
+    for (int l = maxLs - 1; l >= 1; l--) {
+      for (int b0 = 0; b0 < nleaves; b0 += HIVED_WARPSZ) {
+        int i = b0 + lane;
+        bool active = i < nleaves && l < s.pl_v2[i];
+        int va = -1, vpar = -1, ppar = -1;
+        bool topLevel = false;
+        if (active) {
+          int v = vleaves[i];
+          va = d.v_anc[v * AS + l];
+          vpar = d.v_anc[v * AS + l + 1];
+          topLevel = l + 1 == s.pl_v2[i];
+          ppar = topLevel ? d.v_pcell[vpar] : d.binding[vpar];
+        }
+        // first new child under a bound cell: one search over its physical cell's children
+        bool firstTouch = active && topLevel && d.vx_stamp[vpar] != epochNow;
+        unsigned same = hv_match(firstTouch ? vpar : -1 - lane);
+        if (firstTouch) {
+          if (hv_ffs(same) - 1 == lane) scanned += d.p_nchild[ppar];
+          d.vx_stamp[vpar] = epochNow; d.vx_of[vpar] = 0;
+        }
+        hv_warp_sync();
+        bool isNew = active && d.vx_stamp[va] != epochNow;
+        unsigned grp = hv_match(active ? va : -1 - lane);
+        bool leader = isNew && hv_ffs(grp) - 1 == lane;
+        unsigned sib = hv_match(leader ? vpar : -1 - lane);
+        int sel = -1;
+        bool unusable = false;
+        if (leader) {
+          int want = d.vx_of[vpar] + hv_popc(sib & hv_lanemask_lt());
+          int c0 = d.p_child0[ppar], n = d.p_nchild[ppar];
+          if (topLevel) {
+            int cnt = 0;
+            for (int j = 0; j < n; j++) {
+              int c = c0 + j;
+              if (d.p_vcell[c] >= 0) continue;
+              if (!d.p_healthy[c] || d.p_usedopp[c] != 0) unusable = true;
+              if (cnt == want) sel = c;
+              cnt++;
+            }
+          } else if (want < n) {
+            sel = c0 + want;
+          }
+          if (sel >= 0 && l > 1) scanned += d.p_nchild[sel];
+        }
+        if (hv_ballot(leader && (sel < 0 || unusable))) return false;
+        if (leader) {
+          d.binding[va] = sel; d.vx_stamp[va] = epochNow; d.vx_of[va] = 0;
+          if ((sib >> lane) <= 1u) d.vx_of[vpar] = d.vx_of[vpar] + hv_popc(sib);  // the last of the new siblings
+        }
+        hv_warp_sync();
+      }
+    }
+    for (int o = HIVED_WARPSZ / 2; o > 0; o >>= 1) scanned += ((long long)hv_shfl_xor((int)scanned, o));
+    stat_add(ST_FREE_CELLS, scanned);
+    return true;
+  }
+
   // hived_algorithm.go:898-942; intra_vc_scheduler.go:92-117
   HIVED_DEV_NOINLINE bool scheduleGuaranteedAffinityGroup(const Req& r, int& reason, int& rcell) {
     int vset = r.pinned >= 0 ? d.vc_pinned_vset[r.vc * d.S.nPinned + r.pinned] : (r.chain >= 0 ? d.vc_chain_vset[r.vc * d.S.nChains + r.chain] : -1);
@@ -1785,9 +1886,12 @@ struct Core {
     long long tm0 = hv_clock();
     tryLazyPreempt(s.pl_v, r.nleaves);
     if (panicCode) return false;
-    toBindingPaths(s.pl_v, r.nleaves);
-    if (panicCode) return false;
-    bool mapped = mapVirtualPlacementToPhysical(r.chain, r.ignoreSuggested);
+    bool mapped = mapPlacementBatched(s.pl_v, r.nleaves, r.ignoreSuggested);
+    if (!mapped) {
+      toBindingPaths(s.pl_v, r.nleaves);
+      if (panicCode) return false;
+      mapped = mapVirtualPlacementToPhysical(r.chain, r.ignoreSuggested);
+    }
     stat_add(ST_CYC_MAP, hv_clock() - tm0);
     if (mapped) {
       // toPhysicalPlacement types.go:260-280
