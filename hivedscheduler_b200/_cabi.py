@@ -22,7 +22,7 @@ _M = C.c_int32 * HIVED_MAX_MEMBERS
 
 class Options(C.Structure):
     _fields_ = [("max_groups", C.c_int32), ("max_pods", C.c_int32), ("max_group_leaves", C.c_int32),
-                ("max_group_pods", C.c_int32), ("device", C.c_int32), ("reserved", C.c_int32 * 3)]
+                ("max_group_pods", C.c_int32), ("device", C.c_int32), ("flags", C.c_int32), ("reserved", C.c_int32 * 2)]
 
 
 class PodSpec(C.Structure):

@@ -2548,7 +2548,10 @@ struct Core {
     if (type == HIVED_EV_SCHEDULE || type == EV_SCHEDULE_ONLY) {
       const hived_pod_spec_t& sp = ev.spec;
       rc = validateSpec(sp);
+      const bool existing = rc == 0 && d.g_state[sp.group] != HIVED_GROUP_NONE;
+      long long ts0 = hv_clock();
       if (rc == 0) rc = schedule(sp, ev.phase, res);
+      if (existing) { stat_add(ST_CYC_SCHED_EXISTING, hv_clock() - ts0); stat_add(ST_N_SCHED_EXISTING, 1); }
       if (rc == 0 && type == HIVED_EV_SCHEDULE && res->kind == HIVED_KIND_BIND) {
         // the filterRoutine sequence: AddAllocatedPod with the PodBindInfo just produced
         BindView b;
@@ -2561,6 +2564,7 @@ struct Core {
         long long ta0 = hv_clock();
         addAllocatedPod(sp, b, getAllocatedPodIndex(b, sp.leaf_num));
         stat_add(ST_CYC_COMMIT, hv_clock() - ta0);
+        if (existing) { stat_add(ST_CYC_COMMIT_POD, hv_clock() - ta0); stat_add(ST_N_COMMIT_POD, 1); }
         rc = panicCode;
       }
     } else if (type == EV_ADD_ALLOCATED) {
@@ -2576,6 +2580,9 @@ struct Core {
       long long td0 = hv_clock();
       deleteAllocatedPod(ev.spec.group, ev.spec.leaf_num, ev.arg0, ev.spec.vc);
       stat_add(ST_CYC_DELETE, hv_clock() - td0);
+      if (ev.spec.group >= 0 && ev.spec.group < d.S.maxGroups && d.g_state[ev.spec.group] != HIVED_GROUP_NONE) {
+        stat_add(ST_CYC_DELETE_POD, hv_clock() - td0); stat_add(ST_N_DELETE_POD, 1);
+      }
       rc = panicCode;
     } else if (type == HIVED_EV_DELETE_UNALLOCATED) {
       deleteUnallocatedPod(ev.spec.group, ev.spec.pod);

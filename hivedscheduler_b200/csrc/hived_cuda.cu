@@ -135,6 +135,115 @@ int launchProgram(Engine& e, int n, bool withInit) {
   return 0;
 }
 
+// ---- pool compaction after a VC-parallel run -------------------------------------------------------------
+// Every CTA appended its results' leaf triples / victim pairs to its own pool slice; the ABI promises one pool in
+// event order.  Three data-parallel kernels: per-block exclusive scan of the words each result owns, scan of
+// the block sums, then one warp per result gathers its words to the canonical offset and patches the result.
+constexpr int SCAN_T = 256, SCAN_PER = 4, SCAN_BLOCK = SCAN_T * SCAN_PER;
+
+__device__ __forceinline__ int resultWords(const hived_result_t& r) {
+  if (r.kind == HIVED_KIND_BIND && r.n_leaves > 0) return 3 * r.n_leaves;
+  if (r.kind == HIVED_KIND_PREEMPT && r.n_victims > 0) return 2 * r.n_victims;
+  return 0;
+}
+
+__global__ void __launch_bounds__(SCAN_T) pool_words_kernel(const hived_result_t* __restrict__ res, int n, int32_t* __restrict__ excl,
+                                                            long long* __restrict__ blockSum) {
+  __shared__ int warpSum[SCAN_T / 32];
+  const int base = (blockIdx.x * SCAN_T + threadIdx.x) * SCAN_PER;
+  int w[SCAN_PER], mine = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_PER; k++) { w[k] = base + k < n ? resultWords(res[base + k]) : 0; mine += w[k]; }
+  int incl = mine;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+  if (lane == 31) warpSum[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    int v = lane < SCAN_T / 32 ? warpSum[lane] : 0, inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (lane < SCAN_T / 32) warpSum[lane] = inc - v;
+    if (lane == SCAN_T / 32 - 1) blockSum[blockIdx.x] = inc;
+  }
+  __syncthreads();
+  int run = warpSum[wid] + incl - mine;
+#pragma unroll
+  for (int k = 0; k < SCAN_PER; k++) { if (base + k < n) excl[base + k] = run; run += w[k]; }
+}
+
+__global__ void __launch_bounds__(1024) pool_block_scan_kernel(long long* blockSum, int nb) {
+  // one CTA; nb is small (n / 1024): serial carry over 1024-wide tiles
+  __shared__ long long part[32];
+  __shared__ long long carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int b0 = 0; b0 <= nb; b0 += 1024) {  // entry nb receives the grand total
+    int i = b0 + threadIdx.x;
+    long long v = i < nb ? blockSum[i] : 0, incl = v;
+    for (int o = 1; o < 32; o <<= 1) { long long t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) part[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+      long long p = part[lane], inc = p;
+      for (int o = 1; o < 32; o <<= 1) { long long t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+      part[lane] = inc - p;
+    }
+    __syncthreads();
+    long long exclv = carry + part[wid] + incl - v;
+    if (i <= nb) blockSum[i] = exclv;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = exclv + v;
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256) pool_gather_kernel(hived_result_t* res, int n, const int32_t* __restrict__ excl,
+                                                          const long long* __restrict__ blockExcl, const int32_t* __restrict__ src,
+                                                          int32_t* __restrict__ dst) {
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (i >= n) return;
+  hived_result_t& r = res[i];
+  const int words = resultWords(r);
+  if (words == 0) return;
+  const long long off = blockExcl[i / SCAN_BLOCK] + excl[i];
+  const bool bind = r.kind == HIVED_KIND_BIND;
+  const int from = bind ? r.leaf_off : r.victim_off;
+  for (int k = lane; k < words; k += 32) dst[off + k] = src[from + k];
+  __syncwarp();
+  if (lane == 0) {
+    if (bind) { r.this_off = (int32_t)(off + (r.this_off - r.leaf_off)); r.leaf_off = (int32_t)off; }
+    else r.victim_off = (int32_t)off;
+  }
+}
+
+int bk_canonicalise(Engine& e, int n, long long* total) {
+  *total = 0;
+  if (n <= 0) return 0;
+  CudaTimers* t = (CudaTimers*)e.stream;
+  const int nb = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
+  e.dScan.ensure((size_t)n * 4 + (size_t)(nb + 2) * 8 + 16);
+  long long* blockSum = (long long*)e.dScan.p;              // [nb + 1], 8-byte aligned at the front
+  int32_t* excl = (int32_t*)((char*)e.dScan.p + (size_t)(nb + 2) * 8);
+  e.dPool2.ensure((size_t)(e.poolCapWords > 0 ? e.poolCapWords : 1) * 4);
+  pool_words_kernel<<<nb, SCAN_T, 0, t->stream>>>((const hived_result_t*)e.dResults.p, n, excl, blockSum);
+  pool_block_scan_kernel<<<1, 1024, 0, t->stream>>>(blockSum, nb);
+  pool_gather_kernel<<<(int)(((long long)n * 32 + 255) / 256), 256, 0, t->stream>>>((hived_result_t*)e.dResults.p, n, excl, blockSum,
+                                                                              (const int32_t*)e.dPool.p, (int32_t*)e.dPool2.p);
+  long long tot = 0;
+  cudaMemcpyAsync(&tot, blockSum + nb, 8, cudaMemcpyDeviceToHost, t->stream);
+  cudaError_t err = cudaStreamSynchronize(t->stream);
+  if (err != cudaSuccess || (err = cudaGetLastError()) != cudaSuccess) {
+    e.err = std::string("pool compaction failed: ") + cudaGetErrorString(err);
+    return HIVED_ERR_PLATFORM;
+  }
+  e.kernelLaunches += 3;
+  *total = tot;
+  return 0;
+}
+
 }  // namespace hived
 
 extern "C" const char* hived_backend(void) { return "cuda-sm100a"; }

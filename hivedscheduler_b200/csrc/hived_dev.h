@@ -107,6 +107,8 @@ enum {
   /* SM cycles spent per phase (leader warp), for profiles/ */
   ST_CYC_VIEW = 9, ST_CYC_LEAF = 10, ST_CYC_MAP = 11, ST_CYC_EMIT = 12, ST_CYC_COMMIT = 13, ST_CYC_DELETE = 14, ST_CYC_TOTAL = 15,
   ST_CYC_WAIT = 16 /* spinning at the entry of a shared section (VC-parallel mode) */, ST_SHARED_SECTIONS = 17,
+  ST_CYC_SCHED_EXISTING = 18, ST_N_SCHED_EXISTING = 19, ST_CYC_DELETE_POD = 20, ST_N_DELETE_POD = 21,
+  ST_CYC_COMMIT_POD = 22, ST_N_COMMIT_POD = 23,
   ST_COUNT = 24
 };
 

@@ -30,6 +30,9 @@ void bk_d2d(void* dst, const void* src, size_t bytes);
 int bk_init(int device, std::string& err);
 // runs the program over n staged events; returns 0 or a HIVED_ERR_* code
 int launchProgram(Engine& e, int n, bool withInit);
+// after a VC-parallel run: rewrite the per-CTA pool slices as one pool in event order (dPool2) and patch the
+// offsets in dResults; *total = words used
+int bk_canonicalise(Engine& e, int n, long long* total);
 void bk_flush_l2();
 
 struct Buf {
@@ -68,6 +71,10 @@ struct Engine {
   long long multiBatches = 0;
   int nPinnedOrder = 0, nBad = 0;
   uint64_t hash = HIVED_FNV_OFFSET;
+  bool hashing = true;                  // maintain `hash` over hived_process_events results (HIVED_OPT_NO_RESULT_HASH)
+  bool canonicalDone = false;           // the last VC-parallel run's pool was already compacted into dPool2
+  long long canonicalTotal = 0;
+  Buf dPool2, dScan;
   float lastKernelMs = 0.f;
   double kernelMsTotal = 0.0;
   long long kernelLaunches = 0;
@@ -97,6 +104,7 @@ struct Engine {
 
   int create(const char* spec, const hived_options_t* o) {
     if (o) opt = *o;
+    hashing = !(opt.flags & HIVED_OPT_NO_RESULT_HASH);
     if (opt.max_groups <= 0) opt.max_groups = 1 << 17;
     if (opt.max_pods <= 0) opt.max_pods = 1 << 20;
     if (opt.max_group_leaves <= 0) opt.max_group_leaves = 64;
@@ -269,40 +277,27 @@ struct Engine {
   // results + pool to the caller, in the canonical layout (pool slices in event order)
   int fetch(hived_result_t* res, int32_t* pool, int64_t poolCap, int64_t* used) {
     int n = stagedN;
-    if (n > 0) bk_d2h(res, dResults.p, (size_t)n * sizeof(hived_result_t));
     if (launchCta == 1) {
+      if (n > 0) bk_d2h(res, dResults.p, (size_t)n * sizeof(hived_result_t));
       if (poolOff > poolCap) return HIVED_ERR_CAPACITY;
       if (poolOff > 0) bk_d2h(pool, dPool.p, (size_t)poolOff * 4);
       if (used) *used = poolOff;
       return 0;
     }
-    long long span = poolBase[launchCta];
-    hostPool.resize((size_t)(span > 0 ? span : 1));
-    for (int c = 0; c < launchCta; c++)
-      if (poolEnd[c] > poolBase[c]) bk_d2h(hostPool.data() + poolBase[c], (int32_t*)dPool.p + poolBase[c], (size_t)(poolEnd[c] - poolBase[c]) * 4);
-    long long off = 0;
-    for (int i = 0; i < n; i++) {
-      hived_result_t& r = res[i];
-      if (r.kind == HIVED_KIND_BIND && r.n_leaves > 0) {
-        long long words = 3ll * r.n_leaves;
-        if (off + words > poolCap) return HIVED_ERR_CAPACITY;
-        memcpy(pool + off, hostPool.data() + r.leaf_off, (size_t)words * 4);
-        r.this_off = (int32_t)(off + (r.this_off - r.leaf_off));
-        r.leaf_off = (int32_t)off;
-        off += words;
-      } else if (r.kind == HIVED_KIND_PREEMPT && r.n_victims > 0) {
-        long long words = 2ll * r.n_victims;
-        if (off + words > poolCap) return HIVED_ERR_CAPACITY;
-        memcpy(pool + off, hostPool.data() + r.victim_off, (size_t)words * 4);
-        r.victim_off = (int32_t)off;
-        off += words;
-      }
+    // VC-parallel run: every CTA wrote into its own slice; compact the slices into event order on the device
+    // (scan of the per-result word counts + gather) and copy the canonical pool straight into the caller's buffer
+    if (!canonicalDone) {
+      int rc = bk_canonicalise(*this, n, &canonicalTotal);
+      if (rc) return rc;
+      canonicalDone = true;
     }
-    poolOff = off;
-    if (used) *used = off;
+    if (canonicalTotal > poolCap) return HIVED_ERR_CAPACITY;
+    if (n > 0) bk_d2h(res, dResults.p, (size_t)n * sizeof(hived_result_t));
+    if (canonicalTotal > 0) bk_d2h(pool, dPool2.p, (size_t)canonicalTotal * 4);
+    poolOff = canonicalTotal;
+    if (used) *used = canonicalTotal;
     return 0;
   }
-  std::vector<int32_t> hostPool;
   const hived_event_t* stagedEvents = nullptr;
 
   // stage + run a batch; host result/pool buffers are caller-owned
@@ -315,6 +310,7 @@ struct Engine {
     hasAux = aux != nullptr && auxWords > 0;
     if (hasAux) { dAux.ensure((size_t)auxWords * 4); bk_h2d(dAux.p, aux, (size_t)auxWords * 4); }
     poolOff = 0;
+    canonicalDone = false;
     int rc = launchProgram(*this, n, false);
     if (rc) return rc;
     trackHealth(events, n);
@@ -329,6 +325,7 @@ struct Engine {
   }
   int runStaged() {
     poolOff = 0;
+    canonicalDone = false;
     if (launchCta > 1) {  // the progress words were consumed by the previous run
       std::vector<int32_t> own(stagedN), prog(MAX_CTAS, 0x7fffffff);
       bk_d2h(own.data(), dOwn.p, (size_t)stagedN * 4);
@@ -479,7 +476,7 @@ int hived_process_events(hived_ctx* ctx, const hived_event_t* events, int32_t n,
   int rc = e.runBatch(events, n, suggested_pool, suggested_words, nullptr, 0, res, pool, pool_cap);
   if (rc) return rc;
   for (int32_t i = 0; i < n; i++) {
-    if (events[i].type == HIVED_EV_SCHEDULE) e.hash = hived_hash_result(e.hash, &res[i], pool);
+    if (e.hashing && events[i].type == HIVED_EV_SCHEDULE) e.hash = hived_hash_result(e.hash, &res[i], pool);
     if (res[i].error == HIVED_ERR_CAPACITY) { e.err = "capacity exceeded (result pool or hived_options_t)"; return HIVED_ERR_CAPACITY; }
   }
   return 0;
@@ -566,12 +563,13 @@ int hived_bench_fetch_results(hived_ctx* ctx, hived_result_t* res, int32_t* pool
   return e.fetch(res, pool, pool_cap, pool_used);
 }
 int hived_bench_num_ctas(hived_ctx* ctx) { return ctx->e.launchCta; }
+int hived_bench_set_result_hash(hived_ctx* ctx, int on) { ctx->e.hashing = on != 0; return 0; }
 int hived_bench_flush_l2(hived_ctx*) { hived::bk_flush_l2(); return 0; }
 /* out[0..7): SM cycles in view pass, leaf search, mapping, result emission, commit, delete, all events */
 int hived_bench_phase_cycles(hived_ctx* ctx, int64_t* out) {
   long long st[hived::ST_COUNT];
   hived::bk_d2h(st, ctx->e.dev.stats, sizeof st);
-  for (int i = 0; i < 9; i++) out[i] = st[hived::ST_CYC_VIEW + i];
+  for (int i = 0; i < 15; i++) out[i] = st[hived::ST_CYC_VIEW + i];
   return 0;
 }
 double hived_bench_last_kernel_ms(hived_ctx* ctx) { return ctx->e.lastKernelMs; }

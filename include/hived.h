@@ -113,8 +113,10 @@ typedef struct hived_options {
   int32_t max_group_leaves; /* max sum(leafCellNumber*podNumber) over a group's members */
   int32_t max_group_pods;   /* max sum(podNumber) over a group's members */
   int32_t device;           /* CUDA device ordinal (ignored by the CPU oracle) */
-  int32_t reserved[3];
+  int32_t flags;            /* HIVED_OPT_* */
+  int32_t reserved[2];
 } hived_options_t;
+#define HIVED_OPT_NO_RESULT_HASH 1 /* do not maintain hived_result_hash (a parity witness, ~4 CPU cycles per result byte) */
 
 /* api.PodSchedulingSpec after internal.ExtractPodSchedulingSpec (pkg/api/types.go:78-99,
  * pkg/internal/utils.go:230-289), strings interned. */

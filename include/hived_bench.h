@@ -13,13 +13,15 @@ int hived_bench_stage_events(hived_ctx*, const hived_event_t* events, int32_t n,
 int hived_bench_run_staged(hived_ctx*);     /* one kernel launch over the staged batch; nothing crosses PCIe */
 int hived_bench_fetch_results(hived_ctx*, hived_result_t* res, int32_t* pool, int64_t pool_cap, int64_t* pool_used);
 int hived_bench_flush_l2(hived_ctx*);       /* overwrite a buffer larger than L2 */
-/* out[0..9): SM cycles of the leader warps in {view pass, leaf search, v->p mapping, result emission, commit, delete,
- * all events, waiting at shared sections} and the number of shared sections entered */
+/* out[0..15): SM cycles of the leader warps in {view pass, leaf search, v->p mapping, result emission, commit, delete,
+ * all events, waiting at shared sections}, the number of shared sections entered, then cycles / events of
+ * {Schedule of a pod of an existing gang, delete of a pod that is not the gang's last, commit of such a pod} */
 int hived_bench_phase_cycles(hived_ctx*, int64_t* out);
 double hived_bench_last_kernel_ms(hived_ctx*);   /* CUDA-event time of the last launch, on its stream */
 double hived_bench_total_kernel_ms(hived_ctx*);
 int64_t hived_bench_kernel_launches(hived_ctx*);
 int hived_bench_num_ctas(hived_ctx*);            /* CTAs the last batch ran on (VC-parallel execution) */
+int hived_bench_set_result_hash(hived_ctx*, int on); /* toggle the running parity hash (HIVED_OPT_NO_RESULT_HASH) */
 #ifdef __cplusplus
 }
 #endif

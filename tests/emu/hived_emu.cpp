@@ -17,6 +17,7 @@ void bk_d2h(void* dst, const void* src, size_t bytes) { memcpy(dst, src, bytes);
 void bk_d2d(void* dst, const void* src, size_t bytes) { memcpy(dst, src, bytes); }
 int bk_init(int, std::string&) { return 0; }
 void bk_flush_l2() {}
+int bk_canonicalise(Engine&, int, long long*) { return HIVED_ERR_PLATFORM; }  // never reached: the emulation runs one CTA
 int launchProgram(Engine& e, int n, bool withInit) {
   // the emulation runs ONE CTA: VC-parallel batches are exercised on the GPU only
   e.launchCta = 1;
