@@ -1609,6 +1609,7 @@ struct Core {
           if (va >= 0) {
             int c0 = d.v_child0[va], n = d.v_nchild[va];
             int mx = FREE_PRIO; bool anyBound = false;
+#pragma unroll 4
             for (int j = 0; j < n; j++) { int q = d.v_prio[c0 + j]; if (q > mx) mx = q; if (d.v_pcell[c0 + j] >= 0) anyBound = true; }
             d.v_prio[va] = mx;
             if (!anyBound && d.v_pcell[d.v_anc[V * AS + l - 1]] < 0) {
@@ -1619,6 +1620,7 @@ struct Core {
           if (pa >= 0 && l <= ceil) {
             int c0 = d.p_child0[pa], n = d.p_nchild[pa];
             int mx = FREE_PRIO; bool allFree = true;
+#pragma unroll 4
             for (int j = 0; j < n; j++) { int q = d.p_prio[c0 + j]; if (q > mx) mx = q; if (d.p_state[c0 + j] != HIVED_CELL_FREE) allFree = false; }
             d.p_prio[pa] = mx;
             if (allFree) {
@@ -1844,24 +1846,26 @@ struct Core {
         unsigned sib = hv_match(leader ? vpar : -1 - lane);
         int sel = -1;
         bool unusable = false;
-        if (leader) {
-          int want = d.vx_of[vpar] + hv_popc(sib & hv_lanemask_lt());
-          int c0 = d.p_child0[ppar], n = d.p_nchild[ppar];
-          if (topLevel) {
-            int cnt = 0;
-            for (int j = 0; j < n; j++) {
-              int c = c0 + j;
-              if (d.p_vcell[c] >= 0) continue;
-              if (!d.p_healthy[c] || d.p_usedopp[c] != 0) unusable = true;
-              if (cnt == want) sel = c;
-              cnt++;
-            }
-          } else if (want < n) {
-            sel = c0 + want;
+        const int want = leader ? d.vx_of[vpar] + hv_popc(sib & hv_lanemask_lt()) : 0;
+        if (leader && !topLevel && want < d.p_nchild[ppar]) sel = d.p_child0[ppar] + want;
+        // below a bound cell: one warp-wide scan of its physical cell's children (lane = child) per distinct parent
+        for (unsigned todo = hv_ballot(leader && topLevel); todo;) {
+          int gpp = hv_shfl(ppar, hv_ffs(todo) - 1);
+          bool mine = leader && topLevel && ppar == gpp;
+          todo &= ~hv_ballot(mine);
+          int c0 = d.p_child0[gpp], n = d.p_nchild[gpp], before = 0;
+          for (int cb = 0; cb < n; cb += HIVED_WARPSZ) {
+            int j = cb + lane;
+            bool unbound = j < n && d.p_vcell[c0 + j] < 0;
+            if (hv_ballot(unbound && (!d.p_healthy[c0 + j] || d.p_usedopp[c0 + j] != 0))) unusable = true;
+            unsigned um = hv_ballot(unbound);
+            int cnt = hv_popc(um);
+            if (mine && want >= before && want < before + cnt) sel = c0 + cb + hv_fns(um, want - before);
+            before += cnt;
           }
-          if (sel >= 0 && l > 1) scanned += d.p_nchild[sel];
         }
-        if (hv_ballot(leader && (sel < 0 || unusable))) return false;
+        if (leader && sel >= 0 && l > 1) scanned += d.p_nchild[sel];
+        if (hv_ballot(leader && sel < 0) || unusable) return false;
         if (leader) {
           d.binding[va] = sel; d.vx_stamp[va] = epochNow; d.vx_of[va] = 0;
           if ((sib >> lane) <= 1u) d.vx_of[vpar] = d.vx_of[vpar] + hv_popc(sib);  // the last of the new siblings
@@ -2247,13 +2251,18 @@ struct Core {
         unsigned sib = hv_match(leader ? pv : -1 - lane);
         int rank = hv_popc(sib & hv_lanemask_lt());
         int sel = -1;
-        if (leader) {
-          int c0 = d.v_child0[pv], n = d.v_nchild[pv], cnt = 0;
-          for (int j = 0; j < n; j++) {
-            if (d.v_prio[c0 + j] == FREE_PRIO && d.v_pcell[c0 + j] < 0) {
-              if (cnt == rank) { sel = c0 + j; break; }
-              cnt++;
-            }
+        // one warp-wide scan of the children (lane = child) per distinct parent virtual cell
+        for (unsigned todo = hv_ballot(leader); todo;) {
+          int gpv = hv_shfl(pv, hv_ffs(todo) - 1);
+          bool mine = leader && pv == gpv;
+          todo &= ~hv_ballot(mine);
+          int c0 = d.v_child0[gpv], n = d.v_nchild[gpv], before = 0;
+          for (int cb = 0; cb < n; cb += HIVED_WARPSZ) {
+            int j = cb + lane;
+            unsigned fm = hv_ballot(j < n && d.v_prio[c0 + j] == FREE_PRIO && d.v_pcell[c0 + j] < 0);
+            int cnt = hv_popc(fm);
+            if (mine && rank >= before && rank < before + cnt) sel = c0 + cb + hv_fns(fm, rank - before);
+            before += cnt;
           }
         }
         if (hv_ballot(leader && sel < 0)) { failed = true; break; }
@@ -2287,14 +2296,29 @@ struct Core {
         int L = b.physIds[i];
         int V = d.p_vcell[L];
         const int ceil = multi ? d.v_level[d.v_pre[V]] : AS;
-        for (int l = 1; l < AS; l++) {
-          int pa = d.p_anc[L * AS + l], va = d.v_anc[V * AS + l];
-          if (va >= 0 && d.v_prio[va] < p) d.v_prio[va] = p;
-          if (pa >= 0 && l <= ceil) {
-            if (d.p_prio[pa] < p) d.p_prio[pa] = p;
-            d.p_state[pa] = HIVED_CELL_USED;
-            int bound = d.p_vcell[pa];
-            if (bound >= 0) d.v_state[bound] = HIVED_CELL_USED;
+        for (int lb = 1; lb < AS; lb += 4) {  // all loads of four levels, then their stores
+          int pa[4], va[4], vq[4], pq[4], bd[4];
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            int l = lb + k;
+            pa[k] = l < AS ? d.p_anc[L * AS + l] : -1;
+            va[k] = l < AS ? d.v_anc[V * AS + l] : -1;
+            if (l > ceil) pa[k] = -1;
+          }
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            vq[k] = va[k] >= 0 ? d.v_prio[va[k]] : p;
+            pq[k] = pa[k] >= 0 ? d.p_prio[pa[k]] : p;
+            bd[k] = pa[k] >= 0 ? d.p_vcell[pa[k]] : -1;
+          }
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            if (vq[k] < p) d.v_prio[va[k]] = p;
+            if (pa[k] >= 0) {
+              if (pq[k] < p) d.p_prio[pa[k]] = p;
+              d.p_state[pa[k]] = HIVED_CELL_USED;
+              if (bd[k] >= 0) d.v_state[bd[k]] = HIVED_CELL_USED;
+            }
           }
         }
         d.p_using[L] = g;
@@ -2653,7 +2677,11 @@ struct Core {
         processEvent(*reinterpret_cast<const hived_event_t*>(sm->ev_words), &results[i], suggPool, aux);
         if (multi) {
           int next = (k + 1 < nOwn) ? own[k + 1] : 0x7fffffff;
-          hv_fence();  // release: everything this event wrote is visible before the progress moves on
+          // release: only an event that touched the cluster-wide state publishes anything another CTA may read
+          // (free lists, counters, and the cells it put into them — with everything this CTA wrote to those
+          // cells in earlier events, the fence being cumulative).  Other events move the progress word on with a
+          // plain store: the fence (MEMBAR + L1 invalidation) after every event kept the L1 cold.
+          if (sharedHeld) hv_fence();
           if (lane == 0) hv_st_volatile(d.progress + cta, next);
           hv_warp_sync();
         }
