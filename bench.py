@@ -81,7 +81,8 @@ def bind_bench_hooks(lib):
         ("hived_bench_flush_l2", C.c_int, [P]), ("hived_bench_phase_cycles", C.c_int, [P, C.POINTER(C.c_int64)]),
         ("hived_bench_last_kernel_ms", C.c_double, [P]),
         ("hived_bench_total_kernel_ms", C.c_double, [P]), ("hived_bench_kernel_launches", C.c_int64, [P]),
-        ("hived_bench_num_ctas", C.c_int, [P]), ("hived_bench_set_result_hash", C.c_int, [P, C.c_int])]:
+        ("hived_bench_num_ctas", C.c_int, [P]), ("hived_bench_set_result_hash", C.c_int, [P, C.c_int]),
+        ("hived_bench_debug_cycles", C.c_int, [P, C.POINTER(C.c_int64)])]:
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
@@ -225,6 +226,8 @@ def main():
     stats = bc.stats()
     cyc = (C.c_int64 * 15)()
     lib.hived_bench_phase_cycles(ctx, cyc)
+    dbg = (C.c_int64 * 16)()
+    lib.hived_bench_debug_cycles(ctx, dbg)
     # the restore + L2 flush between steps are not part of a step: time = sum of the kernels' CUDA-event times
     kernel_total_s = sum(kernel_ms) / 1e3
     # ---- e2e leg
@@ -278,6 +281,8 @@ def main():
                  "schedule_pod_of_existing_gang", "n_schedule_pod_of_existing_gang", "delete_not_last_pod", "n_delete_not_last_pod",
                  "commit_pod_of_existing_gang", "n_commit_pod_of_existing_gang"]
         line["phase_cycles_per_step"] = {n: int(c) for n, c in zip(names, cyc)}
+        if os.environ.get("HIVED_BENCH_DEBUG"):
+            line["debug_cycles"] = [int(x) for x in dbg]
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -16,6 +16,8 @@
 //     control flow, with lanes spread over tree levels, over the children of a cell, over the
 //     candidates of a free list and over the leaf cells of a gang.
 #pragma once
+#include <cstddef>
+
 #include "../../include/hived.h"
 #include "hived_dev.h"
 #include "hived_prims.h"
@@ -144,6 +146,114 @@ struct Core {
     return v;
   }
 
+  // ---- scans over the children of one cell per lane (whole-gang steps).  All lanes call; `act` lanes hold a cell,
+  // lanes that share a cell get the same answer.  Two strategies, chosen per call by a cost estimate: every lane
+  // walks its own cell's children (one dependent round trip, n serial iterations of a single warp), or one
+  // warp-wide pass (lane = child) per DISTINCT cell (D round trips, no serial loop).
+  HIVED_DEV bool preferCooperative(bool act, int cell, int n, unsigned& heads) const {
+    unsigned grp = hv_match(act ? cell : -1 - lane);
+    heads = hv_ballot(act && hv_ffs(grp) - 1 == lane);
+    int nmax = act ? n : 0;
+    for (int o = HIVED_WARPSZ / 2; o > 0; o >>= 1) { int t = hv_shfl_xor(nmax, o); if (t > nmax) nmax = t; }
+    return hv_popc(heads) * 350 < 60 * nmax + 250;
+  }
+  // V: max v_prio and "some child is bound";  !V: max p_prio and "some child is not Free"
+  template <bool V>
+  HIVED_DEV void childrenSummary(bool act, int cell, int& mx, bool& flag) const {
+    const int32_t* prio = V ? d.v_prio : d.p_prio;
+    const int32_t* other = V ? d.v_pcell : d.p_state;
+    const int c0 = act ? (V ? d.v_child0[cell] : d.p_child0[cell]) : 0;
+    const int n = act ? (V ? d.v_nchild[cell] : d.p_nchild[cell]) : 0;
+    mx = FREE_PRIO; flag = false;
+    unsigned heads;
+    if (preferCooperative(act, cell, n, heads)) {
+      for (unsigned todo = heads; todo; todo &= todo - 1) {
+        const int src = hv_ffs(todo) - 1;
+        const int gc0 = hv_shfl(c0, src), gn = hv_shfl(n, src), gcell = hv_shfl(cell, src);
+        int m = FREE_PRIO; bool f = false;
+        for (int b = 0; b < gn; b += HIVED_WARPSZ) {
+          int j = b + lane;
+          if (j < gn) {
+            int q = prio[gc0 + j]; if (q > m) m = q;
+            int o = other[gc0 + j]; if (V ? o >= 0 : o != HIVED_CELL_FREE) f = true;
+          }
+        }
+        for (int o = HIVED_WARPSZ / 2; o > 0; o >>= 1) { int t = hv_shfl_xor(m, o); if (t > m) m = t; }
+        f = hv_ballot(f) != 0;
+        if (act && cell == gcell) { mx = m; flag = f; }
+      }
+    } else if (act) {
+#pragma unroll 4
+      for (int j = 0; j < n; j++) {
+        int q = prio[c0 + j]; if (q > mx) mx = q;
+        int o = other[c0 + j]; if (V ? o >= 0 : o != HIVED_CELL_FREE) flag = true;
+      }
+    }
+  }
+  // the (want)-th child of virtual cell pv that is free and unbound (cell_allocation.go:348-372, first branch), or -1
+  HIVED_DEV int selectFreeUnboundChild(bool act, int pv, int want) const {
+    const int c0 = act ? d.v_child0[pv] : 0, n = act ? d.v_nchild[pv] : 0;
+    int sel = -1;
+    unsigned heads;
+    if (preferCooperative(act, pv, n, heads)) {
+      for (unsigned todo = heads; todo; todo &= todo - 1) {
+        const int src = hv_ffs(todo) - 1;
+        const int gc0 = hv_shfl(c0, src), gn = hv_shfl(n, src), gpv = hv_shfl(pv, src);
+        int before = 0;
+        for (int b = 0; b < gn; b += HIVED_WARPSZ) {
+          int j = b + lane;
+          unsigned fm = hv_ballot(j < gn && d.v_prio[gc0 + j] == FREE_PRIO && d.v_pcell[gc0 + j] < 0);
+          int cnt = hv_popc(fm);
+          if (act && pv == gpv && want >= before && want < before + cnt) sel = gc0 + b + hv_fns(fm, want - before);
+          before += cnt;
+        }
+      }
+    } else if (act) {
+      int cnt = 0;
+#pragma unroll 4
+      for (int j = 0; j < n; j++) {
+        bool fr = d.v_prio[c0 + j] == FREE_PRIO && d.v_pcell[c0 + j] < 0;
+        if (fr && cnt == want) sel = c0 + j;
+        cnt += fr ? 1 : 0;
+      }
+    }
+    return sel;
+  }
+  // the (want)-th unbound child of physical cell pp, or -1; unusable: some unbound child is bad or opportunistically used
+  HIVED_DEV int selectUnboundPhysChild(bool act, int pp, int want, bool& unusable) const {
+    const int c0 = act ? d.p_child0[pp] : 0, n = act ? d.p_nchild[pp] : 0;
+    int sel = -1;
+    bool bad = false;
+    unsigned heads;
+    if (preferCooperative(act, pp, n, heads)) {
+      for (unsigned todo = heads; todo; todo &= todo - 1) {
+        const int src = hv_ffs(todo) - 1;
+        const int gc0 = hv_shfl(c0, src), gn = hv_shfl(n, src), gpp = hv_shfl(pp, src);
+        int before = 0;
+        for (int b = 0; b < gn; b += HIVED_WARPSZ) {
+          int j = b + lane;
+          bool unbound = j < gn && d.p_vcell[gc0 + j] < 0;
+          if (unbound && (!d.p_healthy[gc0 + j] || d.p_usedopp[gc0 + j] != 0)) bad = true;
+          unsigned um = hv_ballot(unbound);
+          int cnt = hv_popc(um);
+          if (act && pp == gpp && want >= before && want < before + cnt) sel = gc0 + b + hv_fns(um, want - before);
+          before += cnt;
+        }
+      }
+    } else if (act) {
+      int cnt = 0;
+#pragma unroll 4
+      for (int j = 0; j < n; j++) {
+        bool unbound = d.p_vcell[c0 + j] < 0;
+        if (unbound && (!d.p_healthy[c0 + j] || d.p_usedopp[c0 + j] != 0)) bad = true;
+        if (unbound && cnt == want) sel = c0 + j;
+        cnt += unbound ? 1 : 0;
+      }
+    }
+    unusable = hv_ballot(bad) != 0;
+    return sel;
+  }
+
   // ======================================================================================
   // small helpers
   // ======================================================================================
@@ -154,6 +264,12 @@ struct Core {
     return (sugg[node >> 5] >> (node & 31)) & 1u;
   }
   HIVED_DEV void stat_add(int which, long long v) { acc[which] += v; }
+  // scratch cycle counters for profiling sessions (build with -DHIVED_PROFILE; hived_bench_debug_cycles reads them)
+#ifdef HIVED_PROFILE
+  HIVED_DEV void dbg(int k, long long& t) { long long n = hv_clock(); acc[ST_DBG0 + k] += n - t; t = n; }
+#else
+  HIVED_DEV void dbg(int, long long&) {}
+#endif
   HIVED_DEV int cl(int chain, int level) const { return chain * MAXL + level; }
   HIVED_DEV int vcl(int vc, int chain, int level) const { return (vc * d.S.nChains + chain) * MAXL + level; }
 
@@ -1484,6 +1600,7 @@ struct Core {
     ST(d.g_prio[g], sp.priority);
     ST(d.g_flags[g], ((sp.flags & HIVED_SPEC_LAZY_PREEMPTION) ? GF_LAZY_ENABLE : 0) | GF_HAS_VIRTUAL);
     ST(d.g_nmem[g], n);
+    ST(d.g_npre[g], 0);
     int nl = 0, np = 0;
     for (int m = 0; m < n; m++) {
       ST(d.g_mem_leaf[g * 8 + m], leaf[m]);
@@ -1494,7 +1611,6 @@ struct Core {
     for (int i = lane; i < nl; i += HIVED_WARPSZ) { ph[i] = -1; vi[i] = -1; }
     for (int i = lane; i < np; i += HIVED_WARPSZ) po[i] = -1;
     hv_warp_sync();
-    ST(d.g_npre[g], 0);
   }
   HIVED_DEV void eraseGroup(int g) { ST(d.g_state[g], HIVED_GROUP_NONE); }
   // slot offsets of member m: leaves before it / pods before it
@@ -1569,6 +1685,7 @@ struct Core {
   HIVED_DEV bool deleteGroupBatched(int g, int nl, int vc) {
     const int32_t* ph = gphys(g);
     bool bad = false;
+    long long tq = hv_clock();
     for (int b0 = 0; b0 < nl; b0 += HIVED_WARPSZ) {
       int i = b0 + lane;
       bool ok = true;
@@ -1586,6 +1703,7 @@ struct Core {
     }
     if (bad) return false;
     hv_warp_sync();
+    dbg(7, tq);
     stat_add(ST_LEAVES, nl);
     // level 1: the leaves themselves (releaseLeafCell :1319-1352 + setCellState Free)
     for (int b0 = 0; b0 < nl; b0 += HIVED_WARPSZ) {
@@ -1599,40 +1717,47 @@ struct Core {
       }
     }
     hv_warp_sync();
+    dbg(8, tq);
     for (int l = 2; l < AS; l++) {
+      bool changedAny = false;
       for (int b0 = 0; b0 < nl; b0 += HIVED_WARPSZ) {
         int i = b0 + lane;
-        if (i < nl) {
-          int L = ph[i], V = s.pl_v[i];
-          int va = d.v_anc[V * AS + l], pa = d.p_anc[L * AS + l];
-          const int ceil = multi ? d.v_level[s.pl_v2[i]] : AS;
-          if (va >= 0) {
-            int c0 = d.v_child0[va], n = d.v_nchild[va];
-            int mx = FREE_PRIO; bool anyBound = false;
-#pragma unroll 4
-            for (int j = 0; j < n; j++) { int q = d.v_prio[c0 + j]; if (q > mx) mx = q; if (d.v_pcell[c0 + j] >= 0) anyBound = true; }
-            d.v_prio[va] = mx;
-            if (!anyBound && d.v_pcell[d.v_anc[V * AS + l - 1]] < 0) {
-              int pvP = d.v_pcell[va];
-              if (pvP >= 0 && !(d.p_flags[pvP] & PF_PINNED_BIT)) { d.p_vcell[pvP] = -1; d.v_pcell[va] = -1; d.v_state[va] = HIVED_CELL_FREE; d.v_healthy[va] = 1; }
-            }
-          }
-          if (pa >= 0 && l <= ceil) {
-            int c0 = d.p_child0[pa], n = d.p_nchild[pa];
-            int mx = FREE_PRIO; bool allFree = true;
-#pragma unroll 4
-            for (int j = 0; j < n; j++) { int q = d.p_prio[c0 + j]; if (q > mx) mx = q; if (d.p_state[c0 + j] != HIVED_CELL_FREE) allFree = false; }
-            d.p_prio[pa] = mx;
-            if (allFree) {
-              d.p_state[pa] = HIVED_CELL_FREE;
-              int v = d.p_vcell[pa];
-              if (v >= 0) d.v_state[v] = HIVED_CELL_FREE;
-            }
+        const bool act = i < nl;
+        const int L = act ? ph[i] : 0, V = act ? s.pl_v[i] : 0;
+        const int va = act ? d.v_anc[V * AS + l] : -1, pa = act ? d.p_anc[L * AS + l] : -1;
+        const int ceil = (act && multi) ? d.v_level[s.pl_v2[i]] : AS;
+        const bool actV = va >= 0, actP = pa >= 0 && l <= ceil;
+        // every load of the step first (they overlap), the stores last
+        const int vch = actV ? d.v_anc[V * AS + l - 1] : 0;
+        int vOld = 0, vPc = -1, vchPc = 0, pOld = 0, pSt = 0, pVc = -1;
+        if (actV) { vOld = d.v_prio[va]; vPc = d.v_pcell[va]; vchPc = d.v_pcell[vch]; }
+        if (actP) { pOld = d.p_prio[pa]; pSt = d.p_state[pa]; pVc = d.p_vcell[pa]; }
+        const int vPcFlags = vPc >= 0 ? d.p_flags[vPc] : PF_PINNED_BIT;
+        int vmx, pmx;
+        bool anyBound, anyNotFree;
+        childrenSummary<true>(actV, va, vmx, anyBound);
+        childrenSummary<false>(actP, pa, pmx, anyNotFree);
+        bool changed = false;
+        if (actV) {
+          if (vOld != vmx) { d.v_prio[va] = vmx; changed = true; }
+          if (!anyBound && vchPc < 0 && !(vPcFlags & PF_PINNED_BIT)) {
+            d.p_vcell[vPc] = -1; d.v_pcell[va] = -1; d.v_state[va] = HIVED_CELL_FREE; d.v_healthy[va] = 1;
+            changed = true;
           }
         }
+        if (actP) {
+          if (pOld != pmx) { d.p_prio[pa] = pmx; changed = true; }
+          if (!anyNotFree) {
+            if (pSt != HIVED_CELL_FREE) { d.p_state[pa] = HIVED_CELL_FREE; changed = true; }
+            if (pVc >= 0) d.v_state[pVc] = HIVED_CELL_FREE;
+          }
+        }
+        if (hv_ballot(changed)) changedAny = true;
       }
       hv_warp_sync();
+      if (!changedAny) break;  // nothing moved at this level: the levels above keep their values
     }
+    dbg(9, tq);
     // hived_algorithm.go:1343-1347: a preassigned cell goes back once nothing in it is in real use
     bool anyRelease = false;
     for (int b0 = 0; b0 < nl; b0 += HIVED_WARPSZ) {
@@ -1649,6 +1774,7 @@ struct Core {
         if (panicCode) return true;
       }
     }
+    dbg(10, tq);
     return true;
   }
 
@@ -1803,12 +1929,16 @@ struct Core {
           d.binding[v] = pl;
           ls = 1;
         } else {
-          ls = AS;
-          for (int l = 2; l < AS; l++) {
+          unsigned stop = 0, bound = 0;
+#pragma unroll 4
+          for (int l = 2; l < AS; l++) {  // no early exit: the loads of all levels overlap
             int a = d.v_anc[v * AS + l];
-            if (a < 0 || d.v_pcell[a] >= 0) { ls = l; break; }
+            int pc = a >= 0 ? d.v_pcell[a] : -1;
+            if (a < 0 || pc >= 0) stop |= 1u << l;
+            if (pc >= 0) bound |= 1u << l;
           }
-          ok = ls < AS && d.v_anc[v * AS + ls] >= 0;
+          ls = stop ? hv_ffs(stop) - 1 : AS;
+          ok = ls < AS && ((bound >> ls) & 1u);
         }
         s.pl_v2[i] = ls;
       }
@@ -1848,21 +1978,9 @@ struct Core {
         bool unusable = false;
         const int want = leader ? d.vx_of[vpar] + hv_popc(sib & hv_lanemask_lt()) : 0;
         if (leader && !topLevel && want < d.p_nchild[ppar]) sel = d.p_child0[ppar] + want;
-        // below a bound cell: one warp-wide scan of its physical cell's children (lane = child) per distinct parent
-        for (unsigned todo = hv_ballot(leader && topLevel); todo;) {
-          int gpp = hv_shfl(ppar, hv_ffs(todo) - 1);
-          bool mine = leader && topLevel && ppar == gpp;
-          todo &= ~hv_ballot(mine);
-          int c0 = d.p_child0[gpp], n = d.p_nchild[gpp], before = 0;
-          for (int cb = 0; cb < n; cb += HIVED_WARPSZ) {
-            int j = cb + lane;
-            bool unbound = j < n && d.p_vcell[c0 + j] < 0;
-            if (hv_ballot(unbound && (!d.p_healthy[c0 + j] || d.p_usedopp[c0 + j] != 0))) unusable = true;
-            unsigned um = hv_ballot(unbound);
-            int cnt = hv_popc(um);
-            if (mine && want >= before && want < before + cnt) sel = c0 + cb + hv_fns(um, want - before);
-            before += cnt;
-          }
+        {  // below a bound cell: the (want)-th unbound child of its physical cell
+          int t = selectUnboundPhysChild(leader && topLevel, ppar, want, unusable);
+          if (leader && topLevel) sel = t;
         }
         if (leader && sel >= 0 && l > 1) scanned += d.p_nchild[sel];
         if (hv_ballot(leader && sel < 0) || unusable) return false;
@@ -2189,6 +2307,7 @@ struct Core {
   // Afterwards priorities only rise (max per ancestor) and states only become Used.
   HIVED_DEV bool commitGroupBatched(const hived_pod_spec_t& sp, const BindView& b, int g) {
     const int p = sp.priority, chain = b.chain;
+    long long tq0 = hv_clock();
     if (!b.physIds || !b.has_preassigned || p < 0 || sp.vc < 0 || sp.vc >= d.S.nVCs || chain < 0 || chain >= d.S.nChains) return false;
     if (sp.pinned != -1) {
       if (sp.pinned < 0 || sp.pinned >= d.S.nPinned || d.vc_pinned_vset[sp.vc * d.S.nPinned + sp.pinned] < 0) return false;
@@ -2215,13 +2334,18 @@ struct Core {
         ok = L >= 0 && t != -1 && preLevel >= 1;
         ok = ok && d.p_chain[L] == chain && d.p_prio[L] < p;
         if (ok) {
-          ls = AS;
+          // first level whose ancestor is bound, or the preassigned level, or past the top (mapPhysicalCellToVirtual):
+          // all levels loaded at once (no early exit, so the loads overlap), then a bit scan
+          unsigned stop = 0, bound = 0;
+#pragma unroll 4
           for (int l = 1; l < AS; l++) {
             int a = d.p_anc[L * AS + l];
-            if (a < 0 || d.p_vcell[a] >= 0 || l == preLevel) { ls = l; break; }
+            int pv = a >= 0 ? d.p_vcell[a] : -1;
+            if (a < 0 || pv >= 0 || l == preLevel) stop |= 1u << l;
+            if (pv >= 0) bound |= 1u << l;
           }
-          int a = ls < AS ? d.p_anc[L * AS + ls] : -1;
-          ok = a >= 0 && d.p_vcell[a] >= 0;
+          ls = stop ? hv_ffs(stop) - 1 : AS;
+          ok = ls < AS && ((bound >> ls) & 1u);
           if (ok && ls == 1) ok = d.v_prio[d.p_vcell[L]] < p;
           s.pl_v2[i] = ls;
         }
@@ -2232,6 +2356,7 @@ struct Core {
     }
     if (bad) return false;
     hv_warp_sync();
+    dbg(2, tq0);
     // bind, top-down
     bool failed = false;
     for (int l = maxLs - 1; l >= 1 && !failed; l--) {
@@ -2250,21 +2375,7 @@ struct Core {
         bool leader = active && isNew && hv_ffs(grp) - 1 == lane;
         unsigned sib = hv_match(leader ? pv : -1 - lane);
         int rank = hv_popc(sib & hv_lanemask_lt());
-        int sel = -1;
-        // one warp-wide scan of the children (lane = child) per distinct parent virtual cell
-        for (unsigned todo = hv_ballot(leader); todo;) {
-          int gpv = hv_shfl(pv, hv_ffs(todo) - 1);
-          bool mine = leader && pv == gpv;
-          todo &= ~hv_ballot(mine);
-          int c0 = d.v_child0[gpv], n = d.v_nchild[gpv], before = 0;
-          for (int cb = 0; cb < n; cb += HIVED_WARPSZ) {
-            int j = cb + lane;
-            unsigned fm = hv_ballot(j < n && d.v_prio[c0 + j] == FREE_PRIO && d.v_pcell[c0 + j] < 0);
-            int cnt = hv_popc(fm);
-            if (mine && rank >= before && rank < before + cnt) sel = c0 + cb + hv_fns(fm, rank - before);
-            before += cnt;
-          }
-        }
+        int sel = selectFreeUnboundChild(leader, pv, rank);
         if (hv_ballot(leader && sel < 0)) { failed = true; break; }
         if (leader) { d.p_vcell[pa] = sel; d.v_pcell[sel] = pa; d.v_healthy[sel] = d.p_healthy[pa]; }
         hv_warp_sync();
@@ -2287,6 +2398,7 @@ struct Core {
       return false;
     }
     // allocateLeafCell (raise) + using group + setCellState(Used), all leaves at once
+    dbg(3, tq0);
     stat_add(ST_LEAVES, nl);
     int32_t* ph = gphys(g);
     int32_t* vi = gvirt(g);
@@ -2326,12 +2438,15 @@ struct Core {
       }
     }
     hv_warp_sync();
+    dbg(4, tq0);
     return true;
   }
 
   HIVED_DEV_NOINLINE void createAllocatedAffinityGroup(const hived_pod_spec_t& sp, const BindView& b) {
     int g = sp.group;
+    long long tq = hv_clock();
     newGroup(g, sp, HIVED_GROUP_ALLOCATED);
+    dbg(1, tq);
     if (commitGroupBatched(sp, b, g)) return;
     bool shouldLazyPreempt = false;
     bool hasVirtualFlag = true;
@@ -2404,17 +2519,20 @@ struct Core {
       createAllocatedAffinityGroup(sp, b);
       if (panicCode) return 0;
     }
+    long long tq = hv_clock();
     int m = memberOf(g, sp.leaf_num);
     if (m < 0 || podIndex < 0 || podIndex >= d.g_mem_pods[g * 8 + m]) { panic(HIVED_ERR_PLATFORM); return 0; }
     int leafOff, podOff;
     memberOffsets(g, m, leafOff, podOff);
     ST(gpods(g)[podOff + podIndex], sp.pod);
     ST(d.pod_node[sp.pod], b.node);
+    dbg(5, tq);
     return 0;
   }
 
   // hived_algorithm.go:272-296
   HIVED_DEV void deleteAllocatedPod(int g, int leafNum, int podIndex, int evVc) {
+    long long tq = hv_clock();
     if (g < 0 || g >= d.S.maxGroups || d.g_state[g] == HIVED_GROUP_NONE) return;
     if (multi && d.g_vc[g] != evVc) { panic(HIVED_ERR_PLATFORM); return; }  // the event was routed by a wrong VC id
     if (podIndex == -1) return;
@@ -2425,6 +2543,7 @@ struct Core {
     ST(gpods(g)[podOff + podIndex], -1);
     const int32_t* po = gpods(g);
     if (firstIdx(groupPods(g), [&](int i) { return po[i] >= 0; }) >= 0) return;
+    dbg(6, tq);
     deleteAllocatedAffinityGroup(g);
   }
   // hived_algorithm.go:229-245
@@ -2450,6 +2569,7 @@ struct Core {
     int podIndex = 0, reason = 0, rcell = -1;
     bool victimsCollected = false;
     freshPlacement = false;
+    long long tq = hv_clock();
     if (d.g_state[g] != HIVED_GROUP_NONE) {
       // schedulePodFromExistingGroup :655-712
       int nl = groupLeaves(g);
@@ -2487,6 +2607,7 @@ struct Core {
     }
     if (d.g_state[g] == HIVED_GROUP_NONE) {
       // schedulePodFromNewGroup :714-752
+      dbg(11, tq);
       Req r;
       int rc = scheduleNewAffinityGroup(sp, r, hasVirtual, reason, rcell);
       if (panicCode) return panicCode;
@@ -2497,7 +2618,9 @@ struct Core {
       if (rc == 1) {
         havePlacement = true; phys = s.pl_p; virt = s.pl_v; freshPlacement = true;
         int nOverlap;
+        tq = hv_clock();
         collectPreemptionVictims(phys, r.nleaves, res, nOverlap);
+        dbg(12, tq);
         victimsCollected = true;
         if (panicCode) return panicCode;
         if (phase == HIVED_PHASE_PREEMPTING) {
@@ -2562,13 +2685,15 @@ struct Core {
     long long tev0 = hv_clock();
     {  // clearResult: one word per lane
       int32_t* w = reinterpret_cast<int32_t*>(res);
-      for (int i = lane; i < (int)(sizeof(hived_result_t) / 4); i += HIVED_WARPSZ) w[i] = 0;
+      const int iWait = (int)(offsetof(hived_result_t, wait_cell) / 4), iChain = (int)(offsetof(hived_result_t, chain) / 4),
+                iNode = (int)(offsetof(hived_result_t, node) / 4);
+      for (int i = lane; i < (int)(sizeof(hived_result_t) / 4); i += HIVED_WARPSZ) w[i] = (i == iWait || i == iChain || i == iNode) ? -1 : 0;
       hv_warp_sync();
-      ST(res->wait_cell, -1); ST(res->chain, -1); ST(res->node, -1);
     }
     sugg = (ev.suggested_off >= 0 && suggPool) ? suggPool + ev.suggested_off : nullptr;
     int rc = 0;
     int type = ev.type;
+    { long long tq = tev0; dbg(13, tq); }
     if (type == HIVED_EV_SCHEDULE || type == EV_SCHEDULE_ONLY) {
       const hived_pod_spec_t& sp = ev.spec;
       rc = validateSpec(sp);
@@ -2586,7 +2711,10 @@ struct Core {
         b.physIds = (d.S.directLeaf && freshPlacement) ? s.pl_p : nullptr;
         sugg = nullptr;
         long long ta0 = hv_clock();
-        addAllocatedPod(sp, b, getAllocatedPodIndex(b, sp.leaf_num));
+        long long tq = ta0;
+        int api = getAllocatedPodIndex(b, sp.leaf_num);
+        dbg(0, tq);
+        addAllocatedPod(sp, b, api);
         stat_add(ST_CYC_COMMIT, hv_clock() - ta0);
         if (existing) { stat_add(ST_CYC_COMMIT_POD, hv_clock() - ta0); stat_add(ST_N_COMMIT_POD, 1); }
         rc = panicCode;
@@ -2669,12 +2797,19 @@ struct Core {
         int i = own ? own[k] : k;
         curEvent = i;
         sharedHeld = false;
+        long long tq = hv_clock();
+        constexpr int EVW = (int)(sizeof(hived_event_t) / 4);
         {
           const int32_t* src = reinterpret_cast<const int32_t*>(&events[i]);
-          for (int w = lane; w < (int)(sizeof(hived_event_t) / 4); w += HIVED_WARPSZ) sm->ev_words[w] = src[w];
+          for (int w = lane; w < EVW; w += HIVED_WARPSZ) sm->ev_words[w] = src[w];
           hv_warp_sync();
         }
+        // the events are streamed from HBM once: pull the one after next towards the SM now (no register
+        // target, so nothing waits for it at the call below)
+        if (k + 2 < nOwn) hv_prefetch(&events[own ? own[k + 2] : k + 2]);
+        dbg(14, tq);
         processEvent(*reinterpret_cast<const hived_event_t*>(sm->ev_words), &results[i], suggPool, aux);
+        tq = hv_clock();
         if (multi) {
           int next = (k + 1 < nOwn) ? own[k + 1] : 0x7fffffff;
           // release: only an event that touched the cluster-wide state publishes anything another CTA may read
@@ -2685,6 +2820,7 @@ struct Core {
           if (lane == 0) hv_st_volatile(d.progress + cta, next);
           hv_warp_sync();
         }
+        dbg(15, tq);
       }
       // flush the work counters
       if (lane == 0) {

@@ -109,7 +109,8 @@ enum {
   ST_CYC_WAIT = 16 /* spinning at the entry of a shared section (VC-parallel mode) */, ST_SHARED_SECTIONS = 17,
   ST_CYC_SCHED_EXISTING = 18, ST_N_SCHED_EXISTING = 19, ST_CYC_DELETE_POD = 20, ST_N_DELETE_POD = 21,
   ST_CYC_COMMIT_POD = 22, ST_N_COMMIT_POD = 23,
-  ST_COUNT = 24
+  ST_DBG0 = 24 /* 16 scratch cycle counters for profiling sessions (hived_bench_debug_cycles) */,
+  ST_COUNT = 40
 };
 
 constexpr int MAX_CTAS = 32;

@@ -572,6 +572,12 @@ int hived_bench_phase_cycles(hived_ctx* ctx, int64_t* out) {
   for (int i = 0; i < 15; i++) out[i] = st[hived::ST_CYC_VIEW + i];
   return 0;
 }
+int hived_bench_debug_cycles(hived_ctx* ctx, int64_t* out) {
+  long long st[hived::ST_COUNT];
+  hived::bk_d2h(st, ctx->e.dev.stats, sizeof st);
+  for (int i = 0; i < 16; i++) out[i] = st[hived::ST_DBG0 + i];
+  return 0;
+}
 double hived_bench_last_kernel_ms(hived_ctx* ctx) { return ctx->e.lastKernelMs; }
 double hived_bench_total_kernel_ms(hived_ctx* ctx) { return ctx->e.kernelMsTotal; }
 int64_t hived_bench_kernel_launches(hived_ctx* ctx) { return ctx->e.kernelLaunches; }

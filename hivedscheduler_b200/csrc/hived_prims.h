@@ -45,6 +45,7 @@ inline void hv_fence() {}
 inline void hv_atomic_add64(long long* a, long long v) { *a += v; }
 inline void hv_atomic_or64(long long* a, long long v) { *a |= v; }
 inline int hv_cta() { return 0; }
+inline void hv_prefetch(const void*) {}
 }  // namespace hived
 #define HV_ST(ptr, val) (*(ptr) = (val))
 #else
@@ -77,6 +78,7 @@ __device__ __forceinline__ void hv_fence() { __threadfence(); }
 __device__ __forceinline__ void hv_atomic_add64(long long* a, long long v) { atomicAdd((unsigned long long*)a, (unsigned long long)v); }
 __device__ __forceinline__ void hv_atomic_or64(long long* a, long long v) { atomicOr((unsigned long long*)a, (unsigned long long)v); }
 __device__ __forceinline__ int hv_cta() { return blockIdx.x; }
+__device__ __forceinline__ void hv_prefetch(const void* p) { asm volatile("prefetch.L1 [%0];" ::"l"(p)); }
 }  // namespace hived
 // leader-warp store: one lane writes, the warp is re-converged and the store ordered before later loads
 #define HV_ST(ptr, val)                      \

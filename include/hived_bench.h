@@ -17,6 +17,7 @@ int hived_bench_flush_l2(hived_ctx*);       /* overwrite a buffer larger than L2
  * all events, waiting at shared sections}, the number of shared sections entered, then cycles / events of
  * {Schedule of a pod of an existing gang, delete of a pod that is not the gang's last, commit of such a pod} */
 int hived_bench_phase_cycles(hived_ctx*, int64_t* out);
+int hived_bench_debug_cycles(hived_ctx*, int64_t* out); /* out[0..16): scratch cycle counters used in profiling sessions */
 double hived_bench_last_kernel_ms(hived_ctx*);   /* CUDA-event time of the last launch, on its stream */
 double hived_bench_total_kernel_ms(hived_ctx*);
 int64_t hived_bench_kernel_launches(hived_ctx*);
