@@ -27,6 +27,8 @@ sys.path.insert(0, ROOT)
 from hivedscheduler_b200 import _cabi, trace  # noqa: E402
 
 METRIC = "scheduling decisions/sec on 64k-GPU cell tree, 100k pending gangs"
+# dram__bytes_read.sum + dram__bytes_write.sum of hived_events_kernel over the full C3 trace (one ncu --set full capture)
+NCU_DRAM_BYTES_PER_LAUNCH_C3 = 83_630_592 + 96_510_464
 WORKLOAD = "C3: 8192 nodes x 8 GPU (65536 GPUs), 5-level tree, 8 VCs, 100000 mixed gangs (1/4/8/64-GPU), admission window 0.9"
 
 
@@ -268,8 +270,13 @@ def main():
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src,
-                     "note": "latency-bound sequential contract: state (~8 MB) is L2/L1 resident; see DESIGN.md"},
+                     "traffic": NCU_DRAM_BYTES_PER_LAUNCH_C3 if args.gangs == 100000 else None,
+                     "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one full-size launch "
+                                       "(profiles/r1e_whole_gang_steps.md); bytes per launch",
+                     "algorithmic_bytes_per_launch": int(alg_bytes), "kernel": "hived_events_kernel",
+                     "peak_source": peak_src,
+                     "note": "latency-bound sequential contract: the state (~9 MB of cells) is L2/L1 resident, DRAM traffic is "
+                             "the event stream in and the results out; see DESIGN.md section 4"},
     }
     if rank == 0:
         if not args.no_cpu_baseline and world == 1:

@@ -55,6 +55,17 @@ class GroupInfo(C.Structure):
                 ("n_preempting_pods", C.c_int32), ("reserved", C.c_int32 * 3)]
 
 
+class GroupPlacement(C.Structure):
+    _fields_ = [("state", C.c_int32), ("n_members", C.c_int32), ("member_leaf_num", _M), ("member_pod_num", _M),
+                ("n_leaves", C.c_int32), ("n_pods", C.c_int32), ("n_preempting", C.c_int32), ("has_virtual", C.c_int32),
+                ("lazy_preempted", C.c_int32), ("reserved", C.c_int32)]
+
+
+class CellInfo(C.Structure):
+    _fields_ = [("cell_type", C.c_int32), ("is_node_level", C.c_int32), ("leaf_type", C.c_int32), ("node", C.c_int32),
+                ("leaf_index", C.c_int32), ("vc", C.c_int32), ("preassigned", C.c_int32), ("pinned", C.c_int32)]
+
+
 class CellStatus(C.Structure):
     _fields_ = [("priority", C.c_int32), ("state", C.c_int32), ("healthy", C.c_int32), ("peer", C.c_int32),
                 ("level", C.c_int32), ("chain", C.c_int32), ("parent", C.c_int32), ("flags", C.c_int32)]
@@ -97,6 +108,12 @@ SYMBOLS = [
      [_P, C.POINTER(Event), C.c_int32, C.POINTER(C.c_uint32), C.c_int64, C.POINTER(Result),
       C.POINTER(C.c_int32), C.c_int64]),
     ("hived_get_group", C.c_int, [_P, C.c_int32, C.POINTER(GroupInfo)]),
+    ("hived_get_group_placement", C.c_int,
+     [_P, C.c_int32, C.POINTER(GroupPlacement), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int32,
+      C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32), C.c_int32]),
+    ("hived_list_groups", C.c_int32, [_P, C.POINTER(C.c_int32), C.c_int32]),
+    ("hived_physical_cell_info", C.c_int, [_P, C.c_int32, C.POINTER(CellInfo)]),
+    ("hived_virtual_cell_info", C.c_int, [_P, C.c_int32, C.POINTER(CellInfo)]),
     ("hived_snapshot_physical", C.c_int, [_P, C.POINTER(CellStatus), C.c_int32]),
     ("hived_snapshot_virtual", C.c_int, [_P, C.POINTER(CellStatus), C.c_int32]),
     ("hived_get_stats", C.c_int, [_P, C.POINTER(Stats)]),

@@ -452,12 +452,143 @@ class HivedAlgorithm:
                 "vc": self.vc_names[gi.vc] if gi.vc >= 0 else "", "priority": gi.priority,
                 "has_virtual_placement": bool(gi.has_virtual), "preempting_pods": gi.n_preempting_pods}
 
+    # ---------------------------------------------------------------- inspect (api objects, as JSON-shaped dicts)
+    _GROUP_STATE = {1: "Allocated", 2: "Preempting", 3: "BeingPreempted"}
+    _CELL_STATE = {0: "Free", 1: "Used", 2: "Reserving", 3: "Reserved"}
+
+    def _affinity_group(self, gid: int, name: str) -> Optional[Dict[str, Any]]:
+        """AlgoAffinityGroup.ToAffinityGroup (types.go:187-214); None when the group does not exist.
+        Placement maps are filled in (member ascending, pod, leaf) order (the reference ranges over a Go map)."""
+        gp = _cabi.GroupPlacement()
+        lcap, pcap = int(self._opt.max_group_leaves), int(self._opt.max_group_pods)
+        phys, virt = (C.c_int32 * lcap)(), (C.c_int32 * lcap)()
+        pods, pre = (C.c_int32 * pcap)(), (C.c_int32 * pcap)()
+        rc = self._lib.hived_get_group_placement(self._ctx, gid, C.byref(gp), phys, virt, lcap, pods, pcap, pre, pcap)
+        if rc != 0:
+            self._raise(rc)
+        if gp.state == _cabi.GROUP_NONE:
+            return None
+        gi = _cabi.GroupInfo()
+        self._lib.hived_get_group(self._ctx, gid, C.byref(gi))
+        status: Dict[str, Any] = {"vc": self.vc_names[gi.vc] if gi.vc >= 0 else "", "priority": gi.priority,
+                                  "state": self._GROUP_STATE[gp.state]}
+        pp: Dict[str, List[int]] = {}
+        vp: Dict[str, List[str]] = {}
+        info = _cabi.CellInfo()
+        for k in range(min(gp.n_leaves, lcap)):
+            if phys[k] >= 0:  # nodeToLeafCellIndices, types.go:223-237
+                self._lib.hived_physical_cell_info(self._ctx, phys[k], C.byref(info))
+                pp.setdefault(self.node_names[info.node], []).append(info.leaf_index)
+            if gp.has_virtual and virt[k] >= 0:  # preassignedCellToLeafCells, types.go:244-259
+                self._lib.hived_virtual_cell_info(self._ctx, virt[k], C.byref(info))
+                pre_addr = (self._lib.hived_virtual_cell_address(self._ctx, info.preassigned) or b"").decode()
+                vp.setdefault(pre_addr, []).append((self._lib.hived_virtual_cell_address(self._ctx, virt[k]) or b"").decode())
+        if pp:
+            status["physicalPlacement"] = pp
+        if gp.has_virtual and vp:
+            status["virtualPlacement"] = vp
+        allocated = [self._pod_objs[p].uid if p in self._pod_objs else self._pods.names[p]
+                     for p in pods[:min(gp.n_pods, pcap)] if p >= 0]
+        if allocated:
+            status["allocatedPods"] = allocated
+        preempting = [self._pod_objs[p].uid if p in self._pod_objs else self._pods.names[p]
+                      for p in pre[:min(gp.n_preempting, pcap)]]
+        if preempting:
+            status["preemptingPods"] = preempting
+        if gp.lazy_preempted:
+            # the library records THAT the group was lazy-preempted; preemptor name and time live in the shim
+            status["lazyPreemptionStatus"] = {"preemptor": "", "preemptionTime": None}
+        return {"metadata": {"name": name}, "status": status}
+
     def GetAffinityGroup(self, name: str) -> Dict[str, Any]:  # hived_algorithm.go:309-321
-        g = self.group_info(name)
+        gid = self._groups.ids.get(name)
+        g = self._affinity_group(gid, name) if gid is not None else None
         if g is None:
             raise new_bad_request_error(
                 "Affinity group %s does not exist since it is not allocated or preempting" % name)
         return g
+
+    def GetAllAffinityGroups(self) -> Dict[str, Any]:  # hived_algorithm.go:298-307
+        cap = self._lib.hived_list_groups(self._ctx, None, 0)
+        ids = (C.c_int32 * max(1, cap))()
+        n = self._lib.hived_list_groups(self._ctx, ids, cap)
+        items = []
+        for gid in ids[:min(n, cap)]:
+            g = self._affinity_group(gid, self._groups.names[gid] if gid < len(self._groups.names) else "g%d" % gid)
+            if g is not None:
+                items.append(g)
+        return {"items": items}
+
+    def _cell_status(self, snap, i: int, physical: bool) -> Dict[str, Any]:
+        """api.CellStatus of cell i (cell.go:144-177, 326-363 + the setters that keep it current)."""
+        info = _cabi.CellInfo()
+        if physical:
+            self._lib.hived_physical_cell_info(self._ctx, i, C.byref(info))
+            addr = self._lib.hived_physical_cell_address(self._ctx, i)
+        else:
+            self._lib.hived_virtual_cell_info(self._ctx, i, C.byref(info))
+            addr = self._lib.hived_virtual_cell_address(self._ctx, i)
+        st = snap[i]
+        out: Dict[str, Any] = {}
+        if info.leaf_type >= 0:
+            out["leafCellType"] = self.leaf_type_names[info.leaf_type]
+        out["cellType"] = self.cell_type_names[info.cell_type] if info.cell_type >= 0 else ""
+        if info.is_node_level:
+            out["isNodeLevel"] = True
+        out["cellAddress"] = (addr or b"").decode()
+        out["cellState"] = self._CELL_STATE[st.state]
+        out["cellHealthiness"] = "Healthy" if st.healthy else "Bad"
+        out["cellPriority"] = st.priority
+        if not physical:
+            out["_vc"] = self.vc_names[info.vc]
+        return out
+
+    def _status_forest(self):
+        """Both api status forests from one snapshot of each side.  The embedded peer copies (VirtualCell inside a
+        physical status and PhysicalCell inside a virtual one, cell.go:266-283, 401-419) are the peer's current
+        status without children — the reference refreshes its copies on every priority/state/health change."""
+        ps, vs = self.physical_snapshot(), self.virtual_snapshot()
+        np_, nv = len(ps), len(vs)
+        P = [self._cell_status(ps, i, True) for i in range(np_)]
+        V = [self._cell_status(vs, i, False) for i in range(nv)]
+        vc_of = [v.pop("_vc") for v in V]
+        flat_p = [dict(x) for x in P]
+        flat_v = [dict(x) for x in V]
+        for i in range(np_):
+            peer = ps[i].peer
+            if peer >= 0:
+                P[i]["vc"] = vc_of[peer]
+                P[i]["virtualCell"] = dict(flat_v[peer])
+        for i in range(nv):
+            peer = vs[i].peer
+            if peer >= 0:
+                V[i]["physicalCell"] = dict(flat_p[peer], vc=vc_of[i])
+        for side, snap in ((P, ps), (V, vs)):
+            for i in range(len(side)):  # ids are assigned parents-after-children per level; children in id order
+                par = snap[i].parent
+                if par >= 0:
+                    side[par].setdefault("cellChildren", []).append(side[i])
+        phys_top = [P[i] for i in range(np_) if ps[i].parent < 0]
+        virt_top: Dict[str, List[Dict[str, Any]]] = {vc: [] for vc in self.vc_names}
+        for i in range(nv):
+            if vs[i].parent < 0:
+                virt_top[vc_of[i]].append(V[i])
+        return phys_top, virt_top
+
+    def GetClusterStatus(self) -> Dict[str, Any]:  # hived_algorithm.go:323-336
+        p, v = self._status_forest()
+        return {"physicalCluster": p, "virtualClusters": v}
+
+    def GetPhysicalClusterStatus(self) -> List[Dict[str, Any]]:  # hived_algorithm.go:338-343
+        return self._status_forest()[0]
+
+    def GetAllVirtualClustersStatus(self) -> Dict[str, List[Dict[str, Any]]]:  # hived_algorithm.go:345-354
+        return self._status_forest()[1]
+
+    def GetVirtualClusterStatus(self, vcn: str) -> List[Dict[str, Any]]:  # hived_algorithm.go:356-363
+        if vcn not in self._vc_ids:
+            raise new_bad_request_error("VC %s not found" % vcn)
+        return self._status_forest()[1][vcn]
 
     def physical_snapshot(self) -> List[_cabi.CellStatus]:
         n = self._lib.hived_num_physical_cells(self._ctx)

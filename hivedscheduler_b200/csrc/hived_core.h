@@ -89,7 +89,7 @@ struct Core {
   // when a preassigned cell is bound or released.  Those sections run in batch order: a CTA enters
   // one only when every other CTA is already working on a later event (so all earlier events are
   // complete), and later events that need the shared state wait for this one the same way.
-  HIVED_DEV void sharedEnter() {
+  HIVED_DEV_NOINLINE void sharedEnter() {
     if (!multi || sharedHeld) return;
     long long tw0 = hv_clock();
     while (true) {
@@ -356,7 +356,7 @@ struct Core {
     }
   }
   // cell.go:195-204 + utils.go:397-415.  Used propagates unconditionally: one gather over the levels.
-  HIVED_DEV void setCellState(int c, int s, int ceil = 1 << 20) {
+  HIVED_DEV_NOINLINE void setCellState(int c, int s, int ceil = 1 << 20) {
     if (s == HIVED_CELL_USED) {
       for (int b = 0; b < AS; b += HIVED_WARPSZ) {
         int l = b + lane;
@@ -386,7 +386,7 @@ struct Core {
   // cell_allocation.go:422-441.  A raise (p above the cell's priority) is max(old, p) on every
   // ancestor independently, because a parent's priority is the max of its children's.
   template <bool V>
-  HIVED_DEV void setPriority(int c, int p, int ceil = 1 << 20) {
+  HIVED_DEV_NOINLINE void setPriority(int c, int p, int ceil = 1 << 20) {
     int32_t* prio = V ? d.v_prio : d.p_prio;
     const int32_t* anc = V ? d.v_anc : d.p_anc;
     const int32_t* parent = V ? d.v_parent : d.p_parent;
@@ -422,7 +422,7 @@ struct Core {
   }
   // cell_allocation.go:443-454 — only the opportunistic count of physical cells is ever read back
   // (getUsablePhysicalCells :238-241); every other used[] value is recomputed from leaf priorities.
-  HIVED_DEV void updateUsedOpp(int c, int delta) {
+  HIVED_DEV_NOINLINE void updateUsedOpp(int c, int delta) {
     sharedEnter();  // the counts of the upper cells are read by every VC's buddy allocation
     for (int b = 0; b < AS; b += HIVED_WARPSZ) {
       int l = b + lane;
@@ -446,7 +446,7 @@ struct Core {
     ST(d.v_healthy[vc], 1);
   }
   // cell_allocation.go:384-397: binds the unbound run of ancestors starting at (pc, vc)
-  HIVED_DEV void bindCell(int pc, int vc) {
+  HIVED_DEV_NOINLINE void bindCell(int pc, int vc) {
     int lv = d.v_level[vc];
     unsigned stopMask = levelMask(lv, AS, [&](int l) {
       int va = d.v_anc[vc * AS + l];
@@ -465,7 +465,7 @@ struct Core {
     hv_warp_sync();
   }
   // cell_allocation.go:399-420
-  HIVED_DEV void unbindCell(int c) {
+  HIVED_DEV_NOINLINE void unbindCell(int c) {
     int bv = d.p_vcell[c];
     while (!(d.p_flags[d.v_pcell[bv]] & PF_PINNED_BIT)) {
       int bp = d.v_pcell[bv];
@@ -677,7 +677,7 @@ struct Core {
     if (vc >= 0) ST(d.v_healthy[vc], healthy);
   }
   // hived_algorithm.go:562-581
-  HIVED_DEV void addBadFreeCell(int c) {
+  HIVED_DEV_NOINLINE void addBadFreeCell(int c) {
     int chain = d.p_chain[c], level = d.p_level[c];
     if (!d.chain_in_vc[chain]) { panic(HIVED_ERR_PLATFORM); return; }  // nil-map write in the reference
     bf_append(chain, level, c);
@@ -730,7 +730,7 @@ struct Core {
     }
   }
   // hived_algorithm.go:466-498: the leaves of a node, chain by chain, in level-1 list order
-  HIVED_DEV void setNodeHealth(int node, bool healthy) {
+  HIVED_DEV_NOINLINE void setNodeHealth(int node, bool healthy) {
     if (multi) { panic(HIVED_ERR_PLATFORM); return; }  // the host never runs health events VC-parallel
     if (node < 0 || node >= d.S.nNodes) return;
     if (healthy) {
@@ -753,7 +753,7 @@ struct Core {
   // ======================================================================================
   // leaf cell allocation / release (hived_algorithm.go:1292-1352)
   // ======================================================================================
-  HIVED_DEV bool allocateLeafCell(int pLeaf, int vLeaf, int p, int vc) {
+  HIVED_DEV_NOINLINE bool allocateLeafCell(int pLeaf, int vLeaf, int p, int vc) {
     bool safetyOk = true;
     stat_add(ST_LEAVES, 1);
     if (vLeaf >= 0) {
@@ -770,7 +770,7 @@ struct Core {
     }
     return safetyOk;
   }
-  HIVED_DEV void releaseLeafCell(int pLeaf, int vc) {
+  HIVED_DEV_NOINLINE void releaseLeafCell(int pLeaf, int vc) {
     stat_add(ST_LEAVES, 1);
     int vLeaf = d.p_vcell[pLeaf];
     const int ceil = ceilOf(vLeaf);
@@ -793,7 +793,7 @@ struct Core {
   // == allocateLeafCell(pLeaf, vLeaf, p, vc); p_using = g; setCellState(pLeaf, Used, ceil)
   //    for a guaranteed allocation that raises both leaves' priorities and whose preassigned cell is bound:
   //    one gather over the levels (lane = level) instead of five dependent walks.
-  HIVED_DEV bool commitLeaf(int pLeaf, int vLeaf, int p, int vc, int g) {
+  HIVED_DEV_NOINLINE bool commitLeaf(int pLeaf, int vLeaf, int p, int vc, int g) {
     const int ceil = ceilOf(vLeaf);
     bool fast = vLeaf >= 0 && p != OPP_PRIO && p > d.v_prio[vLeaf] && p > d.p_prio[pLeaf] && d.v_pcell[d.v_pre[vLeaf]] >= 0;
     if (!fast) {
@@ -831,7 +831,7 @@ struct Core {
   // == releaseLeafCell(pLeaf, vc); setCellState(pLeaf, Free, ceil)  for a healthy, bound, non-opportunistic leaf.
   // The four upward walks of the generic code (virtual priority, unbinding, physical priority, state) advance
   // together, one level per iteration, sharing one warp-wide scan of the siblings (lane = child).
-  HIVED_DEV void releaseLeafAndFree(int pLeaf, int vc) {
+  HIVED_DEV_NOINLINE void releaseLeafAndFree(int pLeaf, int vc) {
     int vLeaf = d.p_vcell[pLeaf];
     const int ceil = ceilOf(vLeaf);
     if (vLeaf < 0 || !d.p_healthy[pLeaf] || d.p_prio[pLeaf] == OPP_PRIO) {
@@ -1338,7 +1338,7 @@ struct Core {
     }
     return true;
   }
-  HIVED_DEV int getUsablePhysicalCells(const int32_t* in, int base, int nin, int numNeeded, bool ignoreSuggested, int32_t* out) {
+  HIVED_DEV_NOINLINE int getUsablePhysicalCells(const int32_t* in, int base, int nin, int numNeeded, bool ignoreSuggested, int32_t* out) {
     stat_add(ST_FREE_CELLS, nin);
     // order-preserving filter, one warp-wide ballot per 32 candidates
     int n = 0;
@@ -1420,7 +1420,7 @@ struct Core {
   // ---- the Schedule-time copy of the chain's free list (types.go:123-130, hived_algorithm.go:917-929)
   int sflChain;
   HIVED_DEV int32_t* sfl(int level) const { return s.sfl_data + d.fl_base[cl(sflChain, level)]; }
-  HIVED_DEV void sflCopy(int chain) {
+  HIVED_DEV_NOINLINE void sflCopy(int chain) {
     sflChain = chain;
     for (int l = 1; l < MAXL; l++) {
       int k = cl(chain, l);
@@ -1430,7 +1430,7 @@ struct Core {
     }
     hv_warp_sync();
   }
-  HIVED_DEV void sflRemove(int level, int cell) {  // types.go:78-95 on the copy
+  HIVED_DEV_NOINLINE void sflRemove(int level, int cell) {  // types.go:78-95 on the copy
     int32_t* a = sfl(level);
     int n = s.sfl_len[level];
     int idx = firstIdx(n, [&](int i) { return a[i] == cell; });
@@ -1658,7 +1658,7 @@ struct Core {
     for (int i = 0; i < n; i++) lazyPreemptCell(c0 + i);
   }
   // hived_algorithm.go:1203-1222
-  HIVED_DEV void revertLazyPreempt(int g, const int32_t* save) {
+  HIVED_DEV_NOINLINE void revertLazyPreempt(int g, const int32_t* save) {
     if (!save[0]) { panic(HIVED_ERR_PLATFORM); return; }  // nil placement indexed in the reference
     int nl = groupLeaves(g);
     for (int i = 0; i < nl; i++) {
@@ -1823,7 +1823,7 @@ struct Core {
     eraseGroup(g);
   }
   // hived_algorithm.go:1147-1163
-  HIVED_DEV void allocatePreemptingAffinityGroup(int g) {
+  HIVED_DEV_NOINLINE void allocatePreemptingAffinityGroup(int g) {
     int nl = groupLeaves(g);
     for (int i = 0; i < nl; i++) {
       int pLeaf = gphys(g)[i];
@@ -1877,7 +1877,7 @@ struct Core {
   bool freshPlacement;  // the last schedule() produced its placement in pl_p/pl_v (new group)
 
   // hived_algorithm.go:944-965
-  HIVED_DEV void tryLazyPreempt(const int32_t* vleaves, int nleaves) {
+  HIVED_DEV_NOINLINE void tryLazyPreempt(const int32_t* vleaves, int nleaves) {
     lzCount = 0;
     // fast path: no leaf of the placement is bound to a Used physical cell
     if (firstIdx(nleaves, [&](int i) { int pl = d.v_pcell[vleaves[i]]; return pl >= 0 && d.p_state[pl] == HIVED_CELL_USED; }) < 0) return;
@@ -2208,7 +2208,7 @@ struct Core {
   // AddAllocatedPod / createAllocatedAffinityGroup (hived_algorithm.go:247-270, 981-1041, 1224-1290)
   // ======================================================================================
   // utils.go:347-378 through the (node, chain) -> leaves table
-  HIVED_DEV int findPhysicalLeafCellInChain(int chain, int node, int leafIdx) const {
+  HIVED_DEV_NOINLINE int findPhysicalLeafCellInChain(int chain, int node, int leafIdx) const {
     if (chain < 0 || node < 0) return -1;
     int k = node * d.S.nChains + chain;
     const int32_t* list = d.ncl_list + d.ncl_off[k];
@@ -2216,7 +2216,7 @@ struct Core {
     return i < 0 ? -1 : list[i];
   }
   // utils.go:318-345
-  HIVED_DEV int findPhysicalLeafCell(int chain, int node, int leafIdx) const {
+  HIVED_DEV_NOINLINE int findPhysicalLeafCell(int chain, int node, int leafIdx) const {
     int g = findPhysicalLeafCellInChain(chain, node, leafIdx);
     if (g >= 0) return g;
     for (int c = 0; c < d.S.nChains; c++)
@@ -2225,7 +2225,7 @@ struct Core {
   }
   // cell_allocation.go:348-372 over a list (ptr) or a contiguous range: the first free-and-unbound cell,
   // else the first cell of minimal priority among those below p
-  HIVED_DEV int getLowestPriorityVirtualCell(const int32_t* list, int base, int n, int p) const {
+  HIVED_DEV_NOINLINE int getLowestPriorityVirtualCell(const int32_t* list, int base, int n, int p) const {
     int freeIdx = firstIdx(n, [&](int i) { int vc = list ? list[i] : base + i; return d.v_prio[vc] == FREE_PRIO && d.v_pcell[vc] < 0; });
     if (freeIdx >= 0) return list ? list[freeIdx] : base + freeIdx;
     const int NONE = 0x7fffffff;
@@ -2244,7 +2244,7 @@ struct Core {
     return list ? list[idx] : base + idx;
   }
   // cell_allocation.go:317-346.  vccl: pinned -> the vset's cells at the level; else the VC's preassigned roots
-  HIVED_DEV int mapPhysicalCellToVirtual(int c, int vc, int chain, int pinned, int preassignedLevel, int p) const {
+  HIVED_DEV_NOINLINE int mapPhysicalCellToVirtual(int c, int vc, int chain, int pinned, int preassignedLevel, int p) const {
     int lc = d.p_level[c];
     // first level (>= the cell's) whose ancestor is bound, or that is the preassigned level, or beyond the top
     unsigned m = levelMask(lc, AS, [&](int l) {
@@ -2547,7 +2547,7 @@ struct Core {
     deleteAllocatedAffinityGroup(g);
   }
   // hived_algorithm.go:229-245
-  HIVED_DEV void deleteUnallocatedPod(int g, int pod) {
+  HIVED_DEV_NOINLINE void deleteUnallocatedPod(int g, int pod) {
     if (g < 0 || g >= d.S.maxGroups || d.g_state[g] != HIVED_GROUP_PREEMPTING) return;
     int n = d.g_npre[g];
     for (int i = 0; i < n; i++)

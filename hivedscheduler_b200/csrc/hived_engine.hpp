@@ -5,6 +5,7 @@
 //   tests/emu/hived_emu.cpp -> test-only 1-thread emulation of the same device program (HIVED_EMU)
 // The backend supplies bk_* (memory) and launchProgram().
 #pragma once
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -493,6 +494,88 @@ int hived_get_group(hived_ctx* ctx, int32_t group, hived_group_info_t* out) {
   out->state = v[0]; out->vc = v[1]; out->priority = v[2];
   out->has_virtual = (v[3] & hived::GF_HAS_VIRTUAL) ? 1 : 0;
   out->n_preempting_pods = v[0] == HIVED_GROUP_PREEMPTING ? v[4] : 0;
+  return 0;
+}
+
+int hived_get_group_placement(hived_ctx* ctx, int32_t group, hived_group_placement_t* out, int32_t* phys, int32_t* virt,
+                              int32_t leaf_cap, int32_t* pods, int32_t pod_cap, int32_t* preempting, int32_t preempting_cap) {
+  memset(out, 0, sizeof *out);
+  hived::Engine& e = ctx->e;
+  if (group < 0 || group >= e.dev.S.maxGroups) return 0;
+  int32_t hdr[hived::GROUP_HDR_WORDS];
+  hived::bk_d2h(hdr, e.dev.g_hdr + (size_t)group * hived::GROUP_HDR_WORDS, sizeof hdr);
+  if (hdr[0] == HIVED_GROUP_NONE) return 0;
+  out->state = hdr[0];
+  out->n_members = hdr[4];
+  for (int m = 0; m < hdr[4] && m < HIVED_MAX_MEMBERS; m++) {
+    out->member_leaf_num[m] = hdr[8 + m];
+    out->member_pod_num[m] = hdr[16 + m];
+    out->n_leaves += hdr[8 + m] * hdr[16 + m];
+    out->n_pods += hdr[16 + m];
+  }
+  out->has_virtual = (hdr[3] & hived::GF_HAS_VIRTUAL) ? 1 : 0;
+  out->lazy_preempted = (hdr[3] & hived::GF_LAZY_PREEMPTED) ? 1 : 0;
+  const int nl = out->n_leaves < leaf_cap ? out->n_leaves : leaf_cap;
+  if (nl > 0 && phys) hived::bk_d2h(phys, e.dev.g_phys + (size_t)group * e.dev.S.LS, (size_t)nl * 4);
+  if (nl > 0 && virt) {
+    hived::bk_d2h(virt, e.dev.g_virt + (size_t)group * e.dev.S.LS, (size_t)nl * 4);
+    if (!out->has_virtual) for (int i = 0; i < nl; i++) virt[i] = -1;  // virtualLeafCellPlacement == nil
+  }
+  const int np = out->n_pods < pod_cap ? out->n_pods : pod_cap;
+  if (np > 0 && pods) hived::bk_d2h(pods, e.dev.g_pods + (size_t)group * e.dev.S.PS, (size_t)np * 4);
+  if (out->state == HIVED_GROUP_PREEMPTING) {
+    out->n_preempting = hdr[5];
+    const int n = hdr[5] < preempting_cap ? hdr[5] : preempting_cap;
+    if (n > 0 && preempting) {
+      hived::bk_d2h(preempting, e.dev.g_pre + (size_t)group * e.dev.S.PS, (size_t)n * 4);
+      std::sort(preempting, preempting + n);
+    }
+  }
+  return 0;
+}
+
+int32_t hived_list_groups(hived_ctx* ctx, int32_t* ids, int32_t cap) {
+  hived::Engine& e = ctx->e;
+  const int32_t G = e.dev.S.maxGroups;
+  std::vector<int32_t> hdr((size_t)G * hived::GROUP_HDR_WORDS);
+  hived::bk_d2h(hdr.data(), e.dev.g_hdr, hdr.size() * 4);
+  int32_t n = 0;
+  for (int32_t g = 0; g < G; g++) {
+    if (hdr[(size_t)g * hived::GROUP_HDR_WORDS] == HIVED_GROUP_NONE) continue;
+    if (ids && n < cap) ids[n] = g;
+    n++;
+  }
+  return n;
+}
+
+int hived_physical_cell_info(hived_ctx* ctx, int32_t c, hived_cell_info_t* out) {
+  const hived::FlatTopo& T = ctx->e.T;
+  memset(out, 0xff, sizeof *out);
+  if (c < 0 || c >= T.NP) return HIVED_ERR_PLATFORM;
+  const int chain = T.p_chain[c], level = T.p_level[c];
+  out->cell_type = T.chain_lvl_type[(size_t)chain * hived::MAXL + level];
+  out->is_node_level = (T.p_flags[c] & hived::PF_NODE_LEVEL) ? 1 : 0;
+  out->leaf_type = T.chain_leaftype[chain];
+  out->node = level == 1 ? T.p_node[c] : -1;
+  out->leaf_index = level == 1 ? T.p_leafidx[c] : -1;
+  out->vc = -1; out->preassigned = -1; out->pinned = -1;
+  if (T.p_flags[c] & hived::PF_PINNED)
+    for (int i = 0; i < T.nPinned; i++) if (T.pin_pcell[i] == c) out->pinned = i;
+  return 0;
+}
+
+int hived_virtual_cell_info(hived_ctx* ctx, int32_t c, hived_cell_info_t* out) {
+  const hived::FlatTopo& T = ctx->e.T;
+  memset(out, 0xff, sizeof *out);
+  if (c < 0 || c >= T.NV) return HIVED_ERR_PLATFORM;
+  const int chain = T.v_chain[c], level = T.v_level[c];
+  out->cell_type = T.chain_lvl_type[(size_t)chain * hived::MAXL + level];
+  out->is_node_level = (T.v_flags[c] & hived::PF_NODE_LEVEL) ? 1 : 0;
+  out->leaf_type = T.chain_leaftype[chain];
+  out->node = -1; out->leaf_index = -1;
+  out->vc = T.v_vc[c];
+  out->preassigned = T.v_pre[c];
+  out->pinned = T.vs_pinned[T.v_vset[c]];
   return 0;
 }
 

@@ -275,6 +275,39 @@ int hived_process_events(hived_ctx*, const hived_event_t* events, int32_t n,
 
 /* ---- inspect: GetAffinityGroup / GetClusterStatus raw material (hived_algorithm.go:298-363) */
 int hived_get_group(hived_ctx*, int32_t group, hived_group_info_t* out);
+/* AlgoAffinityGroup.ToAffinityGroup (types.go:187-214) in ids.  phys / virt: the leaf cells of the placement in
+ * (member ascending by leaf number, pod, leaf) order, -1 = nil (a cell that left the spec / no virtual placement);
+ * pods: one slot per pod in (member, pod) order, the allocated pod id or -1; preempting: ids of the preempting pods
+ * (ascending).  Arrays shorter than the counts in *out are filled up to their capacity. */
+typedef struct hived_group_placement {
+  int32_t state;        /* HIVED_GROUP_*; NONE = the group does not exist (everything else is 0) */
+  int32_t n_members;
+  int32_t member_leaf_num[HIVED_MAX_MEMBERS];
+  int32_t member_pod_num[HIVED_MAX_MEMBERS];
+  int32_t n_leaves;
+  int32_t n_pods;
+  int32_t n_preempting;
+  int32_t has_virtual;
+  int32_t lazy_preempted; /* lazyPreemptionStatus != nil */
+  int32_t reserved;
+} hived_group_placement_t;
+int hived_get_group_placement(hived_ctx*, int32_t group, hived_group_placement_t* out, int32_t* phys, int32_t* virt,
+                              int32_t leaf_cap, int32_t* pods, int32_t pod_cap, int32_t* preempting, int32_t preempting_cap);
+/* GetAllAffinityGroups: ids of the groups that exist (allocated or preempting), ascending; returns how many there are */
+int32_t hived_list_groups(hived_ctx*, int32_t* ids, int32_t cap);
+/* static description of a cell (api.CellStatus minus the mutable fields; cell.go:144-177, 326-363) */
+typedef struct hived_cell_info {
+  int32_t cell_type;     /* id in the cell type table */
+  int32_t is_node_level;
+  int32_t leaf_type;     /* leaf cell type of the chain */
+  int32_t node;          /* physical leaf: node id; otherwise -1 */
+  int32_t leaf_index;    /* physical leaf: its index inside the node; otherwise -1 */
+  int32_t vc;            /* virtual cell: VC id; physical: -1 */
+  int32_t preassigned;   /* virtual cell: id of its preassigned (top) cell; physical: -1 */
+  int32_t pinned;        /* pinned cell id of a pinned physical cell / of a virtual cell in a pinned cell, else -1 */
+} hived_cell_info_t;
+int hived_physical_cell_info(hived_ctx*, int32_t cell, hived_cell_info_t* out);
+int hived_virtual_cell_info(hived_ctx*, int32_t cell, hived_cell_info_t* out);
 int hived_snapshot_physical(hived_ctx*, hived_cell_status_t* out, int32_t cap);
 int hived_snapshot_virtual(hived_ctx*, hived_cell_status_t* out, int32_t cap);
 int hived_get_stats(hived_ctx*, hived_stats_t* out);

@@ -3,6 +3,7 @@
 // harness.  The adapter converts ids <-> the strings the reference works with; in particular
 // Schedule() receives suggestedNodes as node-name strings and builds the string set per call like
 // the reference does (hived_algorithm.go:190-193).
+#include <algorithm>
 #include <cstring>
 #include <memory>
 #include <set>
@@ -379,6 +380,95 @@ int hived_get_group(hived_ctx* ctx, int32_t group, hived_group_info_t* out) {
   out->priority = g->priority;
   out->has_virtual = g->virtualPlacement.nil ? 0 : 1;
   out->n_preempting_pods = (int32_t)g->preemptingPods.size();
+  return 0;
+}
+
+// AlgoAffinityGroup.ToAffinityGroup raw material (types.go:187-214)
+int hived_get_group_placement(hived_ctx* ctx, int32_t group, hived_group_placement_t* out, int32_t* phys, int32_t* virt,
+                              int32_t leaf_cap, int32_t* pods, int32_t pod_cap, int32_t* preempting, int32_t preempting_cap) {
+  memset(out, 0, sizeof(*out));
+  auto it = ctx->h->affinityGroups.find(groupName(group));
+  if (it == ctx->h->affinityGroups.end()) return 0;
+  Group* g = it->second;
+  out->state = g->state;
+  out->has_virtual = g->virtualPlacement.nil ? 0 : 1;
+  out->lazy_preempted = g->lazyPreempted ? 1 : 0;
+  int32_t k = 0, pk = 0;
+  for (auto& kv : g->totalPodNums) {  // ascending leaf number
+    int32_t m = out->n_members++;
+    if (m < HIVED_MAX_MEMBERS) { out->member_leaf_num[m] = kv.first; out->member_pod_num[m] = kv.second; }
+    for (int32_t p = 0; p < kv.second; p++) {
+      for (int32_t l = 0; l < kv.first; l++, k++) {
+        if (k >= leaf_cap) continue;
+        Cell* pc = nullptr; Cell* vc = nullptr;
+        auto pit = g->physicalPlacement.m.find(kv.first);
+        if (pit != g->physicalPlacement.m.end() && p < (int32_t)pit->second.size() && l < (int32_t)pit->second[p].size()) pc = pit->second[p][l];
+        if (!g->virtualPlacement.nil) {
+          auto vit = g->virtualPlacement.m.find(kv.first);
+          if (vit != g->virtualPlacement.m.end() && p < (int32_t)vit->second.size() && l < (int32_t)vit->second[p].size()) vc = vit->second[p][l];
+        }
+        if (phys) phys[k] = pc ? pc->id : -1;
+        if (virt) virt[k] = vc ? vc->id : -1;
+      }
+      if (pk < pod_cap && pods) {
+        auto ait = g->allocatedPods.find(kv.first);
+        Pod* pod = (ait != g->allocatedPods.end() && p < (int32_t)ait->second.size()) ? ait->second[p] : nullptr;
+        pods[pk] = pod ? pod->id : -1;
+      }
+      pk++;
+    }
+  }
+  out->n_leaves = k;
+  out->n_pods = pk;
+  if (g->state == groupPreempting) {
+    out->n_preempting = (int32_t)g->preemptingPods.size();
+    int32_t i = 0;
+    for (auto& kv : g->preemptingPods) { if (i < preempting_cap && preempting) preempting[i] = kv.first; i++; }
+  }
+  return 0;
+}
+
+int32_t hived_list_groups(hived_ctx* ctx, int32_t* ids, int32_t cap) {
+  std::vector<int32_t> v;
+  for (auto& kv : ctx->h->affinityGroups) v.push_back(kv.second->id);
+  std::sort(v.begin(), v.end());
+  for (size_t i = 0; i < v.size() && (int32_t)i < cap; i++) if (ids) ids[i] = v[i];
+  return (int32_t)v.size();
+}
+
+static void fillInfo(hived_ctx* ctx, Cell* c, hived_cell_info_t* out) {
+  HivedAlgorithm& h = *ctx->h;
+  memset(out, 0xff, sizeof(*out));
+  out->cell_type = ctx->cellTypeIds.count(c->cellType) ? ctx->cellTypeIds[c->cellType] : -1;
+  out->is_node_level = c->isNodeLevel ? 1 : 0;
+  out->leaf_type = -1;
+  for (auto& kv : h.cellChains)  // leaf type -> chains
+    for (auto& ch : kv.second)
+      if (ch == c->chain)
+        for (size_t i = 0; i < h.leafTypeNames.size(); i++) if (h.leafTypeNames[i] == kv.first) out->leaf_type = (int32_t)i;
+  out->node = -1; out->leaf_index = -1; out->vc = -1; out->preassigned = -1; out->pinned = -1;
+  if (c->physical) {
+    if (c->level == 1 && !c->nodes.empty()) {
+      out->node = h.nodeIds.count(c->nodes[0]) ? h.nodeIds[c->nodes[0]] : -1;
+      out->leaf_index = c->leafCellIndices.empty() ? -1 : c->leafCellIndices[0];
+    }
+    if (c->pinned && c->virtualCell)  // a pinned cell stays bound to its virtual cell, which carries the id
+      for (size_t i = 0; i < h.pinnedNames.size(); i++) if (h.pinnedNames[i] == c->virtualCell->pid) out->pinned = (int32_t)i;
+  } else {
+    for (size_t i = 0; i < h.vcNames.size(); i++) if (h.vcNames[i] == c->vc) out->vc = (int32_t)i;
+    out->preassigned = c->preassignedCell ? c->preassignedCell->id : -1;
+    if (!c->pid.empty())
+      for (size_t i = 0; i < h.pinnedNames.size(); i++) if (h.pinnedNames[i] == c->pid) out->pinned = (int32_t)i;
+  }
+}
+int hived_physical_cell_info(hived_ctx* ctx, int32_t cell, hived_cell_info_t* out) {
+  if (cell < 0 || cell >= (int32_t)ctx->h->physicalCells.size()) { memset(out, 0xff, sizeof(*out)); return HIVED_ERR_PLATFORM; }
+  fillInfo(ctx, ctx->h->physicalCells[cell], out);
+  return 0;
+}
+int hived_virtual_cell_info(hived_ctx* ctx, int32_t cell, hived_cell_info_t* out) {
+  if (cell < 0 || cell >= (int32_t)ctx->h->virtualCells.size()) { memset(out, 0xff, sizeof(*out)); return HIVED_ERR_PLATFORM; }
+  fillInfo(ctx, ctx->h->virtualCells[cell], out);
   return 0;
 }
 
