@@ -244,6 +244,22 @@ def main():
     # parity witness: one more (untimed) pass through the same call with the hash on
     lib.hived_bench_set_result_hash(ctx, 1)
     step_e2e()
+    parity_hash = bc.result_hash()
+    # ---- per-call leg: the extender's own pattern, one pod per call (one launch + one result round trip each):
+    # the first events of the same trace through hived_process_events(n=1) — the same path hived_schedule takes
+    lib.hived_bench_restore_state(ctx)
+    lib.hived_bench_set_result_hash(ctx, 0)
+    n_calls = min(3000, len(ev))
+    one = C.sizeof(_cabi.Event)
+    base = ev_pinned.data_ptr()
+    for i in range(64):  # warm-up calls (also part of the sequence)
+        lib.hived_process_events(ctx, C.cast(base + i * one, C.POINTER(_cabi.Event)), 1, None, 0, res_ptr, pool_ptr, pool_words)
+    t0 = time.perf_counter()
+    for i in range(64, n_calls):
+        rc = lib.hived_process_events(ctx, C.cast(base + i * one, C.POINTER(_cabi.Event)), 1, None, 0, res_ptr, pool_ptr, pool_words)
+        assert rc == 0, rc
+    per_call_s = (time.perf_counter() - t0) / max(1, n_calls - 64)
+    lib.hived_bench_set_result_hash(ctx, 1)
 
     times = torch.tensor([kernel_total_s, e2e_s, wall], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -267,6 +283,9 @@ def main():
                    "wall_ms_per_step_incl_state_rewind": 1e3 * wall / args.steps},
         "e2e": {"value": e2e_value, "unit": "decisions/s", "h2d_bytes_per_step": int(ev.nbytes),
                 "d2h_bytes_per_step": int(len(ev) * C.sizeof(_cabi.Result) + 4 * used.value)},
+        "per_call": {"us_per_event": 1e6 * per_call_s, "events": int(n_calls - 64),
+                     "note": "hived_process_events with n=1 (one kernel launch, H2D event, D2H result per pod) on the first "
+                             "events of the same trace: the latency the HTTP extender sees per Schedule/Delete"},
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -283,7 +302,7 @@ def main():
             v, dt, nev = cpu_baseline(t, 1500)
             line["cpu_baseline"] = {"value": v, "unit": "decisions/s", "cores": 1, "kind": "port",
                                     "sample": "first 1500 decisions (%d events) of the same C3 trace, %.1f s" % (nev, dt)}
-        line["parity"] = {"result_hash": "%016x" % bc.result_hash()}
+        line["parity"] = {"result_hash": "%016x" % parity_hash}
         names = ["view_pass", "leaf_search", "map_v2p", "emit_result", "commit", "delete", "all_events", "shared_wait", "shared_sections",
                  "schedule_pod_of_existing_gang", "n_schedule_pod_of_existing_gang", "delete_not_last_pod", "n_delete_not_last_pod",
                  "commit_pod_of_existing_gang", "n_commit_pod_of_existing_gang"]

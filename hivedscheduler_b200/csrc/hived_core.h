@@ -70,7 +70,6 @@ struct Core {
   int panicCode;  // sticky platform-error code of the current event
   const int lane;
   const int AS;
-  long long acc[ST_COUNT];  // work counters, flushed to d.stats when the batch ends
   Scratch s;                // this CTA's private scratch arrays
   // ---- VC-parallel execution (several CTAs, one per group of VCs; see run())
   const int cta, nCta;
@@ -81,7 +80,6 @@ struct Core {
   HIVED_DEV Core(const Dev& dev, Sm* s_, int32_t* pool_, long long cap, int nCta_)
       : d(dev), sm(s_), sugg(nullptr), pool(pool_), pool_cap(cap), poolOff(0), panicCode(0), lane(hv_lane()), AS(dev.S.AS),
         s(dev.scratch[hv_cta()]), cta(hv_cta()), nCta(nCta_), multi(nCta_ > 1), curEvent(0), sharedHeld(false) {
-    for (int i = 0; i < ST_COUNT; i++) acc[i] = 0;
   }
 
   // Multi-CTA ordering.  VCs are partitioned over the CTAs; an event only touches its VC's virtual
@@ -263,10 +261,12 @@ struct Core {
     if (node < 0) return false;
     return (sugg[node >> 5] >> (node & 31)) & 1u;
   }
-  HIVED_DEV void stat_add(int which, long long v) { acc[which] += v; }
+  // work counters: one fire-and-forget 64-bit reduction to d.stats (L2) per update — no read-modify-write chain
+  // through the thread's local memory on the leader's critical path
+  HIVED_DEV void stat_add(int which, long long v) { if (lane == 0) hv_atomic_add64(&d.stats[which], v); }
   // scratch cycle counters for profiling sessions (build with -DHIVED_PROFILE; hived_bench_debug_cycles reads them)
 #ifdef HIVED_PROFILE
-  HIVED_DEV void dbg(int k, long long& t) { long long n = hv_clock(); acc[ST_DBG0 + k] += n - t; t = n; }
+  HIVED_DEV void dbg(int k, long long& t) { long long n = hv_clock(); stat_add(ST_DBG0 + k, n - t); t = n; }
 #else
   HIVED_DEV void dbg(int, long long&) {}
 #endif
@@ -1146,6 +1146,14 @@ struct Core {
     } else {
       navail = s.cand_len[slot];
     }
+    if (k == navail && k <= MAX_NODE_LEAVES && optimalAffinity(chain, k) >= 0) {
+      // every available leaf is needed: the search below has exactly one combination to find (the leaves of one
+      // view node always share that node as an ancestor) — take them in list order and empty the list
+      for (int i = lane; i < k; i += HIVED_WARPSZ) out[i] = avail[i];
+      hv_warp_sync();
+      ST(s.cand_len[slot], 0);
+      return;
+    }
     int curIdx[MAX_NODE_LEAVES], curAff[MAX_NODE_LEAVES], bestIdx[MAX_NODE_LEAVES];
     const int HIGHEST = 0x7fffffff;
     int bestAffinity = HIGHEST;
@@ -1592,25 +1600,24 @@ struct Core {
     return n;
   }
   // newAlgoAffinityGroup types.go:150-183
-  HIVED_DEV void newGroup(int g, const hived_pod_spec_t& sp, int state) {
-    int leaf[HIVED_MAX_MEMBERS], pods[HIVED_MAX_MEMBERS];
+  HIVED_DEV int newGroup(int g, const hived_pod_spec_t& sp, int state, int* leaf, int* pods) {
     int n = mergeMembers(sp, leaf, pods);
-    ST(d.g_state[g], state);
-    ST(d.g_vc[g], sp.vc);
-    ST(d.g_prio[g], sp.priority);
-    ST(d.g_flags[g], ((sp.flags & HIVED_SPEC_LAZY_PREEMPTION) ? GF_LAZY_ENABLE : 0) | GF_HAS_VIRTUAL);
-    ST(d.g_nmem[g], n);
-    ST(d.g_npre[g], 0);
     int nl = 0, np = 0;
-    for (int m = 0; m < n; m++) {
-      ST(d.g_mem_leaf[g * 8 + m], leaf[m]);
-      ST(d.g_mem_pods[g * 8 + m], pods[m]);
-      nl += leaf[m] * pods[m]; np += pods[m];
+    for (int m = 0; m < n; m++) { nl += leaf[m] * pods[m]; np += pods[m]; }
+    if (lane == 0) {  // the header record (hived_dev.h), one sequence point for all of it
+      d.g_state[g] = state;
+      d.g_vc[g] = sp.vc;
+      d.g_prio[g] = sp.priority;
+      d.g_flags[g] = ((sp.flags & HIVED_SPEC_LAZY_PREEMPTION) ? GF_LAZY_ENABLE : 0) | GF_HAS_VIRTUAL;
+      d.g_nmem[g] = n;
+      d.g_npre[g] = 0;
+      for (int m = 0; m < n; m++) { d.g_mem_leaf[g * 8 + m] = leaf[m]; d.g_mem_pods[g * 8 + m] = pods[m]; }
     }
     int32_t* ph = gphys(g); int32_t* vi = gvirt(g); int32_t* po = gpods(g);
     for (int i = lane; i < nl; i += HIVED_WARPSZ) { ph[i] = -1; vi[i] = -1; }
     for (int i = lane; i < np; i += HIVED_WARPSZ) po[i] = -1;
     hv_warp_sync();
+    return n;
   }
   HIVED_DEV void eraseGroup(int g) { ST(d.g_state[g], HIVED_GROUP_NONE); }
   // slot offsets of member m: leaves before it / pods before it
@@ -1836,7 +1843,8 @@ struct Core {
   }
   // hived_algorithm.go:1072-1112
   HIVED_DEV_NOINLINE void createPreemptingAffinityGroup(int g, const hived_pod_spec_t& sp, const int32_t* phys, const int32_t* virt) {
-    newGroup(g, sp, HIVED_GROUP_PREEMPTING);
+    int gleaf[HIVED_MAX_MEMBERS], gpods_[HIVED_MAX_MEMBERS];
+    newGroup(g, sp, HIVED_GROUP_PREEMPTING, gleaf, gpods_);
     int nl = groupLeaves(g);
     for (int i = 0; i < nl; i++) { ST(gphys(g)[i], phys[i]); ST(gvirt(g)[i], virt[i]); }
     for (int i = 0; i < nl; i++) {
@@ -1875,6 +1883,7 @@ struct Core {
   };
   int lzCount;
   bool freshPlacement;  // the last schedule() produced its placement in pl_p/pl_v (new group)
+  int lastPodIndex;     // pod index of the last bind result (its row in the member's pod placements)
 
   // hived_algorithm.go:944-965
   HIVED_DEV_NOINLINE void tryLazyPreempt(const int32_t* vleaves, int nleaves) {
@@ -2276,6 +2285,8 @@ struct Core {
     const int32_t* member_pod_num;
     const int32_t* leaves;  // triples
     const int32_t* physIds;  // optional: the physical leaf cells themselves (auto-commit of a fresh placement)
+    const int32_t* virtIds;  // optional, with physIds: the virtual leaf cells Schedule chose (their preassigned cell's
+                             // level names the PreassignedCellTypes entry without reading the emitted triples back)
   };
 
   // utils.go:291-304
@@ -2305,7 +2316,7 @@ struct Core {
   // before looking at the next leaf; so under one virtual cell the r-th new child (in order of first
   // appearance among the leaves) gets the r-th free unbound virtual child: a rank/select per level, top-down.
   // Afterwards priorities only rise (max per ancestor) and states only become Used.
-  HIVED_DEV bool commitGroupBatched(const hived_pod_spec_t& sp, const BindView& b, int g) {
+  HIVED_DEV bool commitGroupBatched(const hived_pod_spec_t& sp, const BindView& b, int g, int gnmem, const int* gleaf, const int* gpods_) {
     const int p = sp.priority, chain = b.chain;
     long long tq0 = hv_clock();
     if (!b.physIds || !b.has_preassigned || p < 0 || sp.vc < 0 || sp.vc >= d.S.nVCs || chain < 0 || chain >= d.S.nChains) return false;
@@ -2314,10 +2325,10 @@ struct Core {
     } else if (d.vc_chain_vset[sp.vc * d.S.nChains + chain] < 0) {
       return false;
     }
-    if (b.n_members != d.g_nmem[g]) return false;
+    if (b.n_members != gnmem) return false;  // the group's merged members (newGroup), still in registers
     int nl = 0;
     for (int m = 0; m < b.n_members; m++) {
-      if (b.member_leaf_num[m] != d.g_mem_leaf[g * 8 + m] || b.member_pod_num[m] != d.g_mem_pods[g * 8 + m]) return false;
+      if (b.member_leaf_num[m] != gleaf[m] || b.member_pod_num[m] != gpods_[m]) return false;
       nl += b.member_leaf_num[m] * b.member_pod_num[m];
     }
     const int top = d.chain_top[chain];
@@ -2328,10 +2339,15 @@ struct Core {
       bool ok = true;
       int ls = 0;
       if (i < nl) {
-        int L = b.physIds[i], t = b.leaves[3 * i + 2];
+        int L = b.physIds[i];
         int preLevel = -1;
-        for (int l = 1; l <= top; l++) if (d.chain_lvl_type[cl(chain, l)] == t) preLevel = l;
-        ok = L >= 0 && t != -1 && preLevel >= 1;
+        if (b.virtIds) {  // cell types are distinct along a chain: the type emitted for this leaf names exactly this level
+          preLevel = d.v_level[d.v_pre[b.virtIds[i]]];
+        } else {
+          int t = b.leaves[3 * i + 2];
+          if (t != -1) for (int l = 1; l <= top; l++) if (d.chain_lvl_type[cl(chain, l)] == t) preLevel = l;
+        }
+        ok = L >= 0 && preLevel >= 1;
         ok = ok && d.p_chain[L] == chain && d.p_prio[L] < p;
         if (ok) {
           // first level whose ancestor is bound, or the preassigned level, or past the top (mapPhysicalCellToVirtual):
@@ -2445,9 +2461,10 @@ struct Core {
   HIVED_DEV_NOINLINE void createAllocatedAffinityGroup(const hived_pod_spec_t& sp, const BindView& b) {
     int g = sp.group;
     long long tq = hv_clock();
-    newGroup(g, sp, HIVED_GROUP_ALLOCATED);
+    int gleaf[HIVED_MAX_MEMBERS], gpods_[HIVED_MAX_MEMBERS];
+    int gnmem = newGroup(g, sp, HIVED_GROUP_ALLOCATED, gleaf, gpods_);
     dbg(1, tq);
-    if (commitGroupBatched(sp, b, g)) return;
+    if (commitGroupBatched(sp, b, g, gnmem, gleaf, gpods_)) return;
     bool shouldLazyPreempt = false;
     bool hasVirtualFlag = true;
     int32_t* ph = gphys(g);
@@ -2561,7 +2578,7 @@ struct Core {
   HIVED_DEV_NOINLINE int schedule(const hived_pod_spec_t& sp, int phase, hived_result_t* res) {
     int g = sp.group;
     stat_add(ST_SCHEDULE, 1);
-    acc[ST_PRIO_MASK] |= (sp.priority >= -1 && sp.priority < 62) ? (1ll << (sp.priority + 1)) : (1ll << 62);
+    if (lane == 0) hv_atomic_or64(&d.stats[ST_PRIO_MASK], (sp.priority >= -1 && sp.priority < 62) ? (1ll << (sp.priority + 1)) : (1ll << 62));
     bool havePlacement = false, hasVirtual = false;
     const int32_t* phys = nullptr;
     const int32_t* virt = nullptr;
@@ -2652,6 +2669,7 @@ struct Core {
     }
     long long te0 = hv_clock();
     emitBind(res, nmem, memLeaf, memPods, phys, virt, hasVirtual, sp.leaf_num, podIndex);
+    lastPodIndex = podIndex;
     stat_add(ST_CYC_EMIT, hv_clock() - te0);
     stat_add(ST_BIND, 1);
     return panicCode;
@@ -2709,10 +2727,13 @@ struct Core {
         b.leaves = pool + res->leaf_off;
         // a fresh placement's cells are known; (node, index) identifies them uniquely when S.directLeaf
         b.physIds = (d.S.directLeaf && freshPlacement) ? s.pl_p : nullptr;
+        b.virtIds = (b.physIds && res->has_virtual) ? s.pl_v : nullptr;
         sugg = nullptr;
         long long ta0 = hv_clock();
         long long tq = ta0;
-        int api = getAllocatedPodIndex(b, sp.leaf_num);
+        // getAllocatedPodIndex (utils.go:291-304) on the PodBindInfo just produced finds the row that holds this
+        // pod's node and first leaf index — the row Schedule emitted it from (leaf cells of a gang are distinct)
+        int api = lastPodIndex;
         dbg(0, tq);
         addAllocatedPod(sp, b, api);
         stat_add(ST_CYC_COMMIT, hv_clock() - ta0);
@@ -2726,6 +2747,7 @@ struct Core {
       b.n_members = bi->n_members; b.member_leaf_num = bi->member_leaf_num; b.member_pod_num = bi->member_pod_num;
       b.leaves = aux + sizeof(hived_bind_info_t) / 4;
       b.physIds = nullptr;
+      b.virtIds = nullptr;
       rc = validateSpec(ev.spec);
       if (rc == 0) { addAllocatedPod(ev.spec, b, ev.arg0); rc = panicCode; }
     } else if (type == HIVED_EV_DELETE_ALLOCATED) {
@@ -2822,13 +2844,6 @@ struct Core {
         }
         dbg(15, tq);
       }
-      // flush the work counters
-      if (lane == 0) {
-        for (int i = 0; i < ST_COUNT; i++) {
-          if (i == ST_PRIO_MASK) hv_atomic_or64(&d.stats[i], acc[i]); else if (acc[i]) hv_atomic_add64(&d.stats[i], acc[i]);
-        }
-      }
-      hv_warp_sync();
       ST(sm->pool_off, poolOff);
       ST(sm->panic, initPanic);
       ST(sm->cmd, CMD_EXIT);
