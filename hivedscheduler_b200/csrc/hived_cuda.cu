@@ -135,6 +135,83 @@ int launchProgram(Engine& e, int n, bool withInit) {
   return 0;
 }
 
+// ---- per-call path ------------------------------------------------------------------------------------------
+// hived_schedule / hived_add_allocated_pod / hived_delete_* and tiny batches: one pinned staging buffer laid out as
+// [events | scalars | suggested bitmaps | aux | results | pool window]; H2D, kernel and D2H are queued on the stream
+// and the host waits once.  (The general path issues ~6 blocking copies: ~100 us per call on B200.)
+struct SmallStage {  // never freed: a few KB of pinned memory per calling thread, and no CUDA call at thread exit
+  char* host = nullptr;
+  size_t bytes = 0;
+};
+static constexpr int64_t SMALL_POOL_WINDOW = 16384;  // words copied back with the results; more on demand
+
+int bk_run_small(Engine& e, const hived_event_t* events, int n, const uint32_t* suggPool, int64_t suggWords, const int32_t* aux,
+                 int64_t auxWords, hived_result_t* res, int32_t* pool, int64_t poolCap) {
+  if (!e.stream) return -1;  // the first launch (initialisation) creates the stream
+  CudaTimers* t = (CudaTimers*)e.stream;
+  static thread_local SmallStage stage;  // per host thread; the shim serialises calls per context anyway
+  const bool hasSugg = suggPool != nullptr && suggWords > 0, hasAux = aux != nullptr && auxWords > 0;
+  const int64_t window = poolCap < SMALL_POOL_WINDOW ? poolCap : SMALL_POOL_WINDOW;
+  const size_t oEv = 0, oScal = oEv + (size_t)n * sizeof(hived_event_t), oSugg = oScal + 4 * sizeof(long long),
+               oAux = oSugg + (hasSugg ? (size_t)suggWords * 4 : 0), oRes = (oAux + (hasAux ? (size_t)auxWords * 4 : 0) + 15) & ~(size_t)15,
+               oPool = oRes + (size_t)n * sizeof(hived_result_t), total = oPool + (size_t)(window > 0 ? window : 1) * 4;
+  if (total > stage.bytes) {
+    if (stage.host) cudaFreeHost(stage.host);
+    stage.host = nullptr;
+    stage.bytes = 0;
+    if (cudaMallocHost((void**)&stage.host, total * 2) != cudaSuccess) return -1;
+    stage.bytes = total * 2;
+  }
+  e.notePriorities(events, n);
+  e.launchCta = 1;
+  e.ownOff.assign(2, 0); e.ownOff[1] = n;
+  e.poolBase.assign(2, 0); e.poolBase[1] = poolCap;
+  e.dEvents.ensure((size_t)n * sizeof(hived_event_t));
+  e.dResults.ensure((size_t)n * sizeof(hived_result_t));
+  e.dPool.ensure((size_t)(poolCap > 0 ? poolCap : 1) * 4);
+  if (hasSugg) e.dSugg.ensure((size_t)suggWords * 4);
+  if (hasAux) e.dAux.ensure((size_t)auxWords * 4);
+  e.hasSugg = hasSugg; e.hasAux = hasAux;
+  e.poolCapWords = poolCap; e.stagedN = n; e.stagedEvents = events; e.canonicalDone = false;
+  char* h = stage.host;
+  memcpy(h + oEv, events, (size_t)n * sizeof(hived_event_t));
+  long long* scal = (long long*)(h + oScal);
+  scal[0] = 0; scal[1] = poolCap; scal[2] = 0; scal[3] = 0;
+  if (hasSugg) memcpy(h + oSugg, suggPool, (size_t)suggWords * 4);
+  if (hasAux) memcpy(h + oAux, aux, (size_t)auxWords * 4);
+  cudaStream_t st = t->stream;
+  cudaMemcpyAsync(e.dEvents.p, h + oEv, (size_t)n * sizeof(hived_event_t), cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(e.dScalars.p, scal, 4 * sizeof(long long), cudaMemcpyHostToDevice, st);
+  if (hasSugg) cudaMemcpyAsync(e.dSugg.p, h + oSugg, (size_t)suggWords * 4, cudaMemcpyHostToDevice, st);
+  if (hasAux) cudaMemcpyAsync(e.dAux.p, h + oAux, (size_t)auxWords * 4, cudaMemcpyHostToDevice, st);
+  cudaEventRecord(t->start, st);
+  hived_events_kernel<<<1, NT, 0, st>>>(e.dev, (const hived_event_t*)e.dEvents.p, n, (hived_result_t*)e.dResults.p,
+                                        hasSugg ? (const uint32_t*)e.dSugg.p : nullptr, hasAux ? (const int32_t*)e.dAux.p : nullptr,
+                                        nullptr, e.nPinnedOrder, e.nBad, (int32_t*)e.dPool.p, (long long*)e.dScalars.p, nullptr, nullptr);
+  cudaEventRecord(t->stop, st);
+  cudaMemcpyAsync(scal, e.dScalars.p, 4 * sizeof(long long), cudaMemcpyDeviceToHost, st);
+  cudaMemcpyAsync(h + oRes, e.dResults.p, (size_t)n * sizeof(hived_result_t), cudaMemcpyDeviceToHost, st);
+  if (window > 0) cudaMemcpyAsync(h + oPool, e.dPool.p, (size_t)window * 4, cudaMemcpyDeviceToHost, st);
+  cudaError_t err = cudaStreamSynchronize(st);
+  if (err != cudaSuccess || (err = cudaGetLastError()) != cudaSuccess) {
+    e.err = std::string("hived_events_kernel failed: ") + cudaGetErrorString(err);
+    return HIVED_ERR_PLATFORM;
+  }
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, t->start, t->stop);
+  e.lastKernelMs = ms;
+  e.kernelMsTotal += ms;
+  e.kernelLaunches += 1;
+  e.poolOff = scal[0];
+  e.poolEnd.assign(1, scal[0]);
+  if (e.poolOff > poolCap) return HIVED_ERR_CAPACITY;
+  memcpy(res, h + oRes, (size_t)n * sizeof(hived_result_t));
+  const int64_t got = e.poolOff < window ? e.poolOff : window;
+  if (got > 0) memcpy(pool, h + oPool, (size_t)got * 4);
+  if (e.poolOff > window) cudaMemcpy(pool + window, (int32_t*)e.dPool.p + window, (size_t)(e.poolOff - window) * 4, cudaMemcpyDeviceToHost);
+  return 0;
+}
+
 // ---- pool compaction after a VC-parallel run -------------------------------------------------------------
 // Every CTA appended its results' leaf triples / victim pairs to its own pool slice; the ABI promises one pool in
 // event order.  Three data-parallel kernels: per-block exclusive scan of the words each result owns, scan of

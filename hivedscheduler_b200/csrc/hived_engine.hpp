@@ -34,6 +34,10 @@ int launchProgram(Engine& e, int n, bool withInit);
 // after a VC-parallel run: rewrite the per-CTA pool slices as one pool in event order (dPool2) and patch the
 // offsets in dResults; *total = words used
 int bk_canonicalise(Engine& e, int n, long long* total);
+// the per-call path (one pod per call, batches of a few events): everything staged through one pinned host buffer,
+// copies and kernel queued on the context's stream, ONE synchronisation.  Returns -1 when it does not apply.
+int bk_run_small(Engine& e, const hived_event_t* events, int n, const uint32_t* suggPool, int64_t suggWords, const int32_t* aux,
+                 int64_t auxWords, hived_result_t* res, int32_t* pool, int64_t poolCap);
 void bk_flush_l2();
 
 struct Buf {
@@ -305,6 +309,10 @@ struct Engine {
   int runBatch(const hived_event_t* events, int n, const uint32_t* suggPool, int64_t suggWords, const int32_t* aux,
                int64_t auxWords, hived_result_t* res, int32_t* pool, int64_t poolCap) {
     if (n <= 0) return 0;
+    if (n <= SMALL_BATCH) {
+      int rc = bk_run_small(*this, events, n, suggPool, suggWords, aux, auxWords, res, pool, poolCap);
+      if (rc >= 0) { if (rc == 0) trackHealth(events, n); return rc; }
+    }
     prepare(events, n, poolCap);
     hasSugg = suggPool != nullptr && suggWords > 0;
     if (hasSugg) { dSugg.ensure((size_t)suggWords * 4); bk_h2d(dSugg.p, suggPool, (size_t)suggWords * 4); }
@@ -316,6 +324,18 @@ struct Engine {
     if (rc) return rc;
     trackHealth(events, n);
     return fetch(res, pool, poolCap, nullptr);
+  }
+  static constexpr int SMALL_BATCH = 8;
+  // what prepare() decides per event, for bk_run_small (no device traffic)
+  void notePriorities(const hived_event_t* events, int n) {
+    for (int i = 0; i < n; i++) {
+      const hived_event_t& ev = events[i];
+      if (ev.type == HIVED_EV_SCHEDULE || ev.type == Core::EV_SCHEDULE_ONLY || ev.type == Core::EV_ADD_ALLOCATED) {
+        int p = ev.spec.priority;
+        prioMaskHost |= (p >= -1 && p < 62) ? (1ull << (p + 1)) : (1ull << 62);
+      }
+      if (ev.type == Core::EV_ADD_ALLOCATED) everRecovered = true;
+    }
   }
   bool hasSugg = false, hasAux = false;
   int64_t poolCapWords = 0;
