@@ -222,6 +222,7 @@ def main():
     barrier()
     wall = time.perf_counter() - t0
     launches = lib.hived_bench_kernel_launches(ctx) - launches0
+    n_ctas = lib.hived_bench_num_ctas(ctx)
     # parity witness: the hash of the last step's results
     used = C.c_int64()
     lib.hived_bench_fetch_results(ctx, res_ptr, pool_ptr, pool_words, C.byref(used))
@@ -278,7 +279,7 @@ def main():
         "ms_per_step": 1e3 * kernel_total_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "events_per_step": int(len(ev)), "decisions_per_step": n_dec,
-                   "parallelism": ("replicas" if world > 1 else "1 GPU") + ", %d CTAs (one per group of VCs)" % lib.hived_bench_num_ctas(ctx), "l2": "flushed between steps (256 MiB memset)",
+                   "parallelism": ("replicas" if world > 1 else "1 GPU") + ", %d CTAs (one per group of VCs)" % n_ctas, "l2": "flushed between steps (256 MiB memset)",
                    "timing": "CUDA events on the launch stream around the kernel; max over ranks",
                    "e2e": "hived_process_events from pinned host buffers (H2D events, kernel, pool compaction, D2H results + pool); "
                           "the library's running parity hash is switched off while timing and checked on an extra pass",

@@ -96,7 +96,7 @@ struct Core {
         int i = b + lane;
         if (i < nCta && i != cta) { int v = hv_ld_volatile(d.progress + i); if (v < mn) mn = v; }
       }
-      for (int o = HIVED_WARPSZ / 2; o > 0; o >>= 1) { int t = hv_shfl_xor(mn, o); if (t < mn) mn = t; }
+      mn = hv_reduce_min(mn);
       if (mn > curEvent) break;
     }
     hv_fence();  // acquire: drop stale L1 lines of state written by the other CTAs
@@ -140,7 +140,7 @@ struct Core {
       int i = b + lane;
       if (i < n) { int x = val(i); if (x > v) v = x; }
     }
-    for (int o = HIVED_WARPSZ / 2; o > 0; o >>= 1) { int t = hv_shfl_xor(v, o); if (t > v) v = t; }
+    v = hv_reduce_max(v);
     return v;
   }
 
@@ -149,11 +149,11 @@ struct Core {
   // walks its own cell's children (one dependent round trip, n serial iterations of a single warp), or one
   // warp-wide pass (lane = child) per DISTINCT cell (D round trips, no serial loop).
   HIVED_DEV bool preferCooperative(bool act, int cell, int n, unsigned& heads) const {
-    unsigned grp = hv_match(act ? cell : -1 - lane);
-    heads = hv_ballot(act && hv_ffs(grp) - 1 == lane);
-    int nmax = act ? n : 0;
-    for (int o = HIVED_WARPSZ / 2; o > 0; o >>= 1) { int t = hv_shfl_xor(nmax, o); if (t > nmax) nmax = t; }
-    return hv_popc(heads) * 350 < 60 * nmax + 250;
+    // cooperative passes pay one round trip per distinct cell, the per-lane walk n serial iterations: wide cells
+    // (racks, pods: few distinct ones per gang) go cooperative, narrow ones (nodes: up to one per lane) per lane
+    (void)cell;
+    heads = hv_ballot(act);
+    return hv_reduce_max(act ? n : 0) > 8;
   }
   // V: max v_prio and "some child is bound";  !V: max p_prio and "some child is not Free"
   template <bool V>
@@ -165,9 +165,10 @@ struct Core {
     mx = FREE_PRIO; flag = false;
     unsigned heads;
     if (preferCooperative(act, cell, n, heads)) {
-      for (unsigned todo = heads; todo; todo &= todo - 1) {
+      for (unsigned todo = heads; todo;) {  // one pass per distinct cell: the first pending lane names it
         const int src = hv_ffs(todo) - 1;
         const int gc0 = hv_shfl(c0, src), gn = hv_shfl(n, src), gcell = hv_shfl(cell, src);
+        todo &= ~hv_ballot(act && cell == gcell);
         int m = FREE_PRIO; bool f = false;
         for (int b = 0; b < gn; b += HIVED_WARPSZ) {
           int j = b + lane;
@@ -176,7 +177,7 @@ struct Core {
             int o = other[gc0 + j]; if (V ? o >= 0 : o != HIVED_CELL_FREE) f = true;
           }
         }
-        for (int o = HIVED_WARPSZ / 2; o > 0; o >>= 1) { int t = hv_shfl_xor(m, o); if (t > m) m = t; }
+        m = hv_reduce_max(m);
         f = hv_ballot(f) != 0;
         if (act && cell == gcell) { mx = m; flag = f; }
       }
@@ -194,9 +195,10 @@ struct Core {
     int sel = -1;
     unsigned heads;
     if (preferCooperative(act, pv, n, heads)) {
-      for (unsigned todo = heads; todo; todo &= todo - 1) {
+      for (unsigned todo = heads; todo;) {
         const int src = hv_ffs(todo) - 1;
         const int gc0 = hv_shfl(c0, src), gn = hv_shfl(n, src), gpv = hv_shfl(pv, src);
+        todo &= ~hv_ballot(act && pv == gpv);
         int before = 0;
         for (int b = 0; b < gn; b += HIVED_WARPSZ) {
           int j = b + lane;
@@ -224,9 +226,10 @@ struct Core {
     bool bad = false;
     unsigned heads;
     if (preferCooperative(act, pp, n, heads)) {
-      for (unsigned todo = heads; todo; todo &= todo - 1) {
+      for (unsigned todo = heads; todo;) {
         const int src = hv_ffs(todo) - 1;
         const int gc0 = hv_shfl(c0, src), gn = hv_shfl(n, src), gpp = hv_shfl(pp, src);
+        todo &= ~hv_ballot(act && pp == gpp);
         int before = 0;
         for (int b = 0; b < gn; b += HIVED_WARPSZ) {
           int j = b + lane;
@@ -870,7 +873,7 @@ struct Core {
             if (d.v_pcell[c0 + i] >= 0) anyBound = true;
           }
         }
-        for (int o = HIVED_WARPSZ / 2; o > 0; o >>= 1) { int t = hv_shfl_xor(mx, o); if (t > mx) mx = t; }
+        mx = hv_reduce_max(mx);
         anyBound = hv_ballot(anyBound) != 0;
         if (wU) {
           if (anyBound) {
@@ -895,7 +898,7 @@ struct Core {
             if (d.p_state[c0 + i] != HIVED_CELL_FREE) anyNotFree = true;
           }
         }
-        for (int o = HIVED_WARPSZ / 2; o > 0; o >>= 1) { int t = hv_shfl_xor(mx, o); if (t > mx) mx = t; }
+        mx = hv_reduce_max(mx);
         anyNotFree = hv_ballot(anyNotFree) != 0;
         if (wS) {
           if (anyNotFree) {
@@ -1052,7 +1055,7 @@ struct Core {
         int mine = n;
         for (int j = nodeIndex + 1 + tid; j < n; j += nth)
           if (infoFree(sinfo[j]) >= need) { mine = j; break; }
-        for (int o = HIVED_WARPSZ / 2; o > 0; o >>= 1) { int other = hv_shfl_xor(mine, o); if (other < mine) mine = other; }
+        mine = hv_reduce_min(mine);
         if (lane == 0 && mine < n) hv_atomic_min(&sm->best, mine);
         hv_cta_sync();
         int b = sm->best;
@@ -1884,6 +1887,11 @@ struct Core {
   int lzCount;
   bool freshPlacement;  // the last schedule() produced its placement in pl_p/pl_v (new group)
   int lastPodIndex;     // pod index of the last bind result (its row in the member's pod placements)
+  // the essentials of the last result, kept on the SM so that the auto-commit does not read the record back from HBM
+  int lastKind, lastNode, lastChain, lastFirstLeaf, lastHasVirtual, lastNmem;
+  long long lastLeafOff;
+  int lastVictims;  // number of victims found by the last collectPreemptionVictims
+  int32_t lastMemLeaf[HIVED_MAX_MEMBERS], lastMemPods[HIVED_MAX_MEMBERS];
 
   // hived_algorithm.go:944-965
   HIVED_DEV_NOINLINE void tryLazyPreempt(const int32_t* vleaves, int nleaves) {
@@ -1952,7 +1960,7 @@ struct Core {
         s.pl_v2[i] = ls;
       }
       if (hv_ballot(!ok)) bad = true;
-      for (int o = HIVED_WARPSZ / 2; o > 0; o >>= 1) { int t = hv_shfl_xor(ls, o); if (t > ls) ls = t; }
+      ls = hv_reduce_max(ls);
       if (ls > maxLs) maxLs = ls;
     }
     if (bad) return false;
@@ -2000,7 +2008,7 @@ struct Core {
         hv_warp_sync();
       }
     }
-    for (int o = HIVED_WARPSZ / 2; o > 0; o >>= 1) scanned += ((long long)hv_shfl_xor((int)scanned, o));
+    scanned = hv_reduce_add((int)scanned);
     stat_add(ST_FREE_CELLS, scanned);
     return true;
   }
@@ -2107,8 +2115,8 @@ struct Core {
   // preemptor groups (sorted by id) to s.lz_group, count returned through nOverlap.
   HIVED_DEV_NOINLINE void collectPreemptionVictims(const int32_t* phys, int nleaves, hived_result_t* res, int& nOverlap) {
     nOverlap = 0;
-    ST(res->victim_off, 0);
-    ST(res->n_victims, 0);
+    lastVictims = 0;
+    // (victim_off / n_victims are 0 in the cleared record)
     // fast path: every cell of the placement is Free
     if (firstIdx(nleaves, [&](int i) { int c = phys[i]; return c >= 0 && d.p_state[c] != HIVED_CELL_FREE; }) < 0) return;
     int32_t* groups = s.tmp_list;  // using groups
@@ -2166,6 +2174,7 @@ struct Core {
     }
     ST(res->victim_off, nv ? (int)start : 0);
     ST(res->n_victims, nv);
+    lastVictims = nv;
   }
 
   // generatePodScheduleResult / generateAffinityGroupBindInfo (utils.go:38-171): lanes over the gang's leaves
@@ -2173,8 +2182,7 @@ struct Core {
                           const int32_t* virt, bool hasVirtual, int curLeafNum, int curPodIndex) {
     int nl = 0, thisOff = -1, thisN = 0;
     for (int m = 0; m < nmem; m++) {
-      ST(res->member_leaf_num[m], memLeaf[m]);
-      ST(res->member_pod_num[m], memPods[m]);
+      if (lane == 0) { res->member_leaf_num[m] = memLeaf[m]; res->member_pod_num[m] = memPods[m]; }
       if (memLeaf[m] == curLeafNum && thisOff < 0) { thisOff = nl + curPodIndex * memLeaf[m]; thisN = memLeaf[m]; }
       nl += memLeaf[m] * memPods[m];
     }
@@ -2200,16 +2208,23 @@ struct Core {
     hv_warp_sync();
     if (thisOff < 0) { panic(HIVED_ERR_PLATFORM); return; }
     int first = phys[thisOff];
-    ST(res->kind, HIVED_KIND_BIND);
-    ST(res->has_virtual, hasVirtual ? 1 : 0);
-    ST(res->pod_index, curPodIndex);
-    ST(res->n_members, nmem);
-    ST(res->leaf_off, (int)base);
-    ST(res->n_leaves, nl);
-    ST(res->this_off, (int)(base + 3 * thisOff));
-    ST(res->this_n, thisN);
-    ST(res->node, d.p_node[first]);
-    ST(res->chain, d.p_chain[first]);
+    lastLeafOff = base;
+    lastNode = d.p_node[first]; lastChain = d.p_chain[first]; lastFirstLeaf = d.p_leafidx[first];
+    lastKind = HIVED_KIND_BIND; lastHasVirtual = hasVirtual ? 1 : 0; lastNmem = nmem;
+    for (int m = 0; m < nmem; m++) { lastMemLeaf[m] = memLeaf[m]; lastMemPods[m] = memPods[m]; }
+    if (lane == 0) {  // the fixed part of the record, one sequence point
+      res->kind = HIVED_KIND_BIND;
+      res->has_virtual = lastHasVirtual;
+      res->pod_index = curPodIndex;
+      res->n_members = nmem;
+      res->leaf_off = (int)base;
+      res->n_leaves = nl;
+      res->this_off = (int)(base + 3 * thisOff);
+      res->this_n = thisN;
+      res->node = lastNode;
+      res->chain = lastChain;
+    }
+    hv_warp_sync();
     poolOff = base + 3ll * nl;
   }
 
@@ -2247,7 +2262,7 @@ struct Core {
         if (q != FREE_PRIO && q < p && q < HIVED_MAX_GUARANTEED_PRIORITY) { int key = (q + 2) * 4096 + i; if (key < best) best = key; }
       }
     }
-    for (int o = HIVED_WARPSZ / 2; o > 0; o >>= 1) { int t = hv_shfl_xor(best, o); if (t < best) best = t; }
+    best = hv_reduce_min(best);
     if (best == NONE) return -1;
     int idx = best & 4095;
     return list ? list[idx] : base + idx;
@@ -2367,7 +2382,7 @@ struct Core {
         }
       }
       if (hv_ballot(!ok)) bad = true;
-      for (int o = HIVED_WARPSZ / 2; o > 0; o >>= 1) { int t2 = hv_shfl_xor(ls, o); if (t2 > ls) ls = t2; }
+      ls = hv_reduce_max(ls);
       if (ls > maxLs) maxLs = ls;
     }
     if (bad) return false;
@@ -2642,7 +2657,7 @@ struct Core {
         if (panicCode) return panicCode;
         if (phase == HIVED_PHASE_PREEMPTING) {
           for (int i = 0; i < nOverlap; i++) deletePreemptingAffinityGroup(s.lz_group[i]);
-          if (res->n_victims != 0) {
+          if (lastVictims != 0) {
             if (!hasVirtual) { panic(HIVED_ERR_PLATFORM); return panicCode; }  // nil virtual placement indexed in the reference
             for (int i = 0; i < r.nleaves; i++) { ST(s.pl_p2[i], s.pl_p[i]); ST(s.pl_v2[i], s.pl_v[i]); }
             createPreemptingAffinityGroup(g, sp, s.pl_p2, s.pl_v2);
@@ -2661,7 +2676,7 @@ struct Core {
       stat_add(ST_WAIT, 1);
       return 0;
     }
-    if (victimsCollected && res->n_victims > 0) {
+    if (victimsCollected && lastVictims > 0) {
       ST(res->kind, HIVED_KIND_PREEMPT);
       ST(res->has_virtual, hasVirtual ? 1 : 0);
       stat_add(ST_PREEMPT, 1);
@@ -2717,17 +2732,18 @@ struct Core {
       rc = validateSpec(sp);
       const bool existing = rc == 0 && d.g_state[sp.group] != HIVED_GROUP_NONE;
       long long ts0 = hv_clock();
+      lastKind = -1;
       if (rc == 0) rc = schedule(sp, ev.phase, res);
       if (existing) { stat_add(ST_CYC_SCHED_EXISTING, hv_clock() - ts0); stat_add(ST_N_SCHED_EXISTING, 1); }
-      if (rc == 0 && type == HIVED_EV_SCHEDULE && res->kind == HIVED_KIND_BIND) {
+      if (rc == 0 && type == HIVED_EV_SCHEDULE && lastKind == HIVED_KIND_BIND) {
         // the filterRoutine sequence: AddAllocatedPod with the PodBindInfo just produced
         BindView b;
-        b.node = res->node; b.first_leaf = pool[res->this_off + 1]; b.chain = res->chain; b.has_preassigned = 1;
-        b.n_members = res->n_members; b.member_leaf_num = res->member_leaf_num; b.member_pod_num = res->member_pod_num;
-        b.leaves = pool + res->leaf_off;
+        b.node = lastNode; b.first_leaf = lastFirstLeaf; b.chain = lastChain; b.has_preassigned = 1;
+        b.n_members = lastNmem; b.member_leaf_num = lastMemLeaf; b.member_pod_num = lastMemPods;
+        b.leaves = pool + lastLeafOff;
         // a fresh placement's cells are known; (node, index) identifies them uniquely when S.directLeaf
         b.physIds = (d.S.directLeaf && freshPlacement) ? s.pl_p : nullptr;
-        b.virtIds = (b.physIds && res->has_virtual) ? s.pl_v : nullptr;
+        b.virtIds = (b.physIds && lastHasVirtual) ? s.pl_v : nullptr;
         sugg = nullptr;
         long long ta0 = hv_clock();
         long long tq = ta0;

@@ -46,6 +46,9 @@ inline void hv_atomic_add64(long long* a, long long v) { *a += v; }
 inline void hv_atomic_or64(long long* a, long long v) { *a |= v; }
 inline int hv_cta() { return 0; }
 inline void hv_prefetch(const void*) {}
+inline int hv_reduce_max(int v) { return v; }
+inline int hv_reduce_min(int v) { return v; }
+inline int hv_reduce_add(int v) { return v; }
 }  // namespace hived
 #define HV_ST(ptr, val) (*(ptr) = (val))
 #else
@@ -78,6 +81,10 @@ __device__ __forceinline__ void hv_fence() { __threadfence(); }
 __device__ __forceinline__ void hv_atomic_add64(long long* a, long long v) { atomicAdd((unsigned long long*)a, (unsigned long long)v); }
 __device__ __forceinline__ void hv_atomic_or64(long long* a, long long v) { atomicOr((unsigned long long*)a, (unsigned long long)v); }
 __device__ __forceinline__ int hv_cta() { return blockIdx.x; }
+// warp-wide integer reductions: one REDUX instruction (sm_80+) instead of a five-step shuffle butterfly
+__device__ __forceinline__ int hv_reduce_max(int v) { return __reduce_max_sync(0xffffffffu, v); }
+__device__ __forceinline__ int hv_reduce_min(int v) { return __reduce_min_sync(0xffffffffu, v); }
+__device__ __forceinline__ int hv_reduce_add(int v) { return __reduce_add_sync(0xffffffffu, v); }
 __device__ __forceinline__ void hv_prefetch(const void* p) { asm volatile("prefetch.L1 [%0];" ::"l"(p)); }
 }  // namespace hived
 // leader-warp store: one lane writes, the warp is re-converged and the store ordered before later loads
