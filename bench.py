@@ -309,7 +309,8 @@ def main():
         names = ["view_pass", "leaf_search", "map_v2p", "emit_result", "commit", "delete", "all_events", "shared_wait", "shared_sections",
                  "schedule_pod_of_existing_gang", "n_schedule_pod_of_existing_gang", "delete_not_last_pod", "n_delete_not_last_pod",
                  "commit_pod_of_existing_gang", "n_commit_pod_of_existing_gang"]
-        line["phase_cycles_per_step"] = {n: int(c) for n, c in zip(names, cyc)}
+        if any(int(c) for c in cyc):  # SM-cycle counters exist in profiling builds only (HIVED_PROFILE=1 at build time)
+            line["phase_cycles_per_step"] = {n: int(c) for n, c in zip(names, cyc)}
         if os.environ.get("HIVED_BENCH_DEBUG"):
             line["debug_cycles"] = [int(x) for x in dbg]
         print(json.dumps(line))

@@ -79,7 +79,8 @@ struct Core {
 
   HIVED_DEV Core(const Dev& dev, Sm* s_, int32_t* pool_, long long cap, int nCta_)
       : d(dev), sm(s_), sugg(nullptr), pool(pool_), pool_cap(cap), poolOff(0), panicCode(0), lane(hv_lane()), AS(dev.S.AS),
-        s(dev.scratch[hv_cta()]), cta(hv_cta()), nCta(nCta_), multi(nCta_ > 1), curEvent(0), sharedHeld(false) {
+        s(dev.scratch[hv_cta()]), cta(hv_cta()), nCta(nCta_), multi(nCta_ > 1), curEvent(0), sharedHeld(false), prioMask(0) {
+    for (int i = 0; i < N_WORK; i++) work[i] = 0;
   }
 
   // Multi-CTA ordering.  VCs are partitioned over the CTAs; an event only touches its VC's virtual
@@ -89,7 +90,7 @@ struct Core {
   // complete), and later events that need the shared state wait for this one the same way.
   HIVED_DEV_NOINLINE void sharedEnter() {
     if (!multi || sharedHeld) return;
-    long long tw0 = hv_clock();
+    long long tw0 = pclock();
     while (true) {
       int mn = 0x7fffffff;
       for (int b = 0; b < nCta; b += HIVED_WARPSZ) {
@@ -100,7 +101,7 @@ struct Core {
       if (mn > curEvent) break;
     }
     hv_fence();  // acquire: drop stale L1 lines of state written by the other CTAs
-    stat_add(ST_CYC_WAIT, hv_clock() - tw0);
+    stat_add(ST_CYC_WAIT, pclock() - tw0);
     stat_add(ST_SHARED_SECTIONS, 1);
     sharedHeld = true;
   }
@@ -264,15 +265,34 @@ struct Core {
     if (node < 0) return false;
     return (sugg[node >> 5] >> (node & 31)) & 1u;
   }
-  // work counters: one fire-and-forget 64-bit reduction to d.stats (L2) per update — no read-modify-write chain
-  // through the thread's local memory on the leader's critical path
-  HIVED_DEV void stat_add(int which, long long v) { if (lane == 0) hv_atomic_add64(&d.stats[which], v); }
-  // scratch cycle counters for profiling sessions (build with -DHIVED_PROFILE; hived_bench_debug_cycles reads them)
+  // Work counters (ST_VIEW_NODES .. ST_PRIO_MASK): accumulated per CTA in 32-bit slots and added to d.stats when the
+  // batch ends (a batch is far below 2^31 of anything).  The SM-cycle counters (ST_CYC_* and the scratch ST_DBG*)
+  // exist only in profiling builds (-DHIVED_PROFILE): in the product neither the clock reads nor the updates are
+  // compiled in — they were 6 % of the leader warp's time.
+  static constexpr int N_WORK = ST_PRIO_MASK;  // counters [0, N_WORK) are the work counters
+  int work[N_WORK];
+  unsigned long long prioMask;
 #ifdef HIVED_PROFILE
-  HIVED_DEV void dbg(int k, long long& t) { long long n = hv_clock(); stat_add(ST_DBG0 + k, n - t); t = n; }
+  HIVED_DEV long long pclock() const { return hv_clock(); }
+  HIVED_DEV void stat_add(int which, long long v) {
+    if (which < N_WORK) work[which] += (int)v;
+    else if (lane == 0) hv_atomic_add64(&d.stats[which], v);
+  }
+  HIVED_DEV void dbg(int k, long long& t) { long long n = pclock(); stat_add(ST_DBG0 + k, n - t); t = n; }
 #else
+  HIVED_DEV long long pclock() const { return 0; }
+  HIVED_DEV void stat_add(int which, long long v) { if (which < N_WORK) work[which] += (int)v; }
   HIVED_DEV void dbg(int, long long&) {}
 #endif
+  HIVED_DEV void flushWork() {
+    if (lane == 0) {
+      for (int i = 0; i < N_WORK; i++) if (work[i]) hv_atomic_add64(&d.stats[i], work[i]);
+      if (prioMask) hv_atomic_or64(&d.stats[ST_PRIO_MASK], (long long)prioMask);
+    }
+    for (int i = 0; i < N_WORK; i++) work[i] = 0;
+    prioMask = 0;
+    hv_warp_sync();
+  }
   HIVED_DEV int cl(int chain, int level) const { return chain * MAXL + level; }
   HIVED_DEV int vcl(int vc, int chain, int level) const { return (vc * d.S.nChains + chain) * MAXL + level; }
 
@@ -1225,13 +1245,13 @@ struct Core {
     for (int m = 0; m < nmem; m++)
       for (int i = 0; i < memPods[m]; i++) { ST(s.pod_need[npods], memLeaf[m]); npods++; }
     int priority = OPP_PRIO;
-    long long tc0 = hv_clock();
+    long long tc0 = pclock();
     bool ok = runViewPass(sched, priority, ignoreSuggested, npods, reason, rcell);
     if (!ok && p > OPP_PRIO) {
       priority = p;
       ok = runViewPass(sched, priority, ignoreSuggested, npods, reason, rcell);
     }
-    long long tc1 = hv_clock();
+    long long tc1 = pclock();
     stat_add(ST_CYC_VIEW, tc1 - tc0);
     if (!ok) return false;
     stat_add(ST_PODS, npods);
@@ -1251,7 +1271,7 @@ struct Core {
       if (panicCode) return false;
       outOff += need;
     }
-    stat_add(ST_CYC_LEAF, hv_clock() - tc1);
+    stat_add(ST_CYC_LEAF, pclock() - tc1);
     reason = 0;
     rcell = -1;
     return true;
@@ -1578,6 +1598,31 @@ struct Core {
   HIVED_DEV int32_t* gvirt(int g) const { return d.g_virt + (int64_t)g * d.S.LS; }
   HIVED_DEV int32_t* gpods(int g) const { return d.g_pods + (int64_t)g * d.S.PS; }
   HIVED_DEV int32_t* gpre(int g) const { return d.g_pre + (int64_t)g * d.S.PS; }
+  // The 32-word header record of a group is one coalesced load (lane = word); sums and searches over the member
+  // tables (words 8.. = leaf numbers, 16.. = pod numbers, word 4 = #members) are warp reductions over that row
+  // instead of loops of dependent loads.  (The 1-lane host emulation keeps the loops.)
+#ifndef HIVED_EMU
+  static_assert(GROUP_HDR_WORDS == HIVED_WARPSZ, "one header word per lane");
+  HIVED_DEV int hdrWord(int g) const { return d.g_hdr[(int64_t)g * GROUP_HDR_WORDS + lane]; }
+  HIVED_DEV int groupLeaves(int g) const {
+    int w = hdrWord(g), n = hv_shfl(w, 4), up = hv_shfl(w, (lane + 8) & 31);
+    return hv_reduce_add((lane >= 8 && lane < 8 + n) ? w * up : 0);
+  }
+  HIVED_DEV int groupPods(int g) const {
+    int w = hdrWord(g), n = hv_shfl(w, 4);
+    return hv_reduce_add((lane >= 16 && lane < 16 + n) ? w : 0);
+  }
+  HIVED_DEV void memberOffsets(int g, int m, int& leafOff, int& podOff) const {
+    int w = hdrWord(g), up = hv_shfl(w, (lane + 8) & 31);
+    leafOff = hv_reduce_add((lane >= 8 && lane < 8 + m) ? w * up : 0);
+    podOff = hv_reduce_add((lane >= 16 && lane < 16 + m) ? w : 0);
+  }
+  HIVED_DEV int memberOf(int g, int leafNum) const {
+    int w = hdrWord(g), n = hv_shfl(w, 4);
+    unsigned hit = hv_ballot(lane >= 8 && lane < 8 + n && w == leafNum);
+    return hit ? hv_ffs(hit) - 1 - 8 : -1;
+  }
+#else
   HIVED_DEV int groupLeaves(int g) const {
     int n = 0;
     for (int m = 0; m < d.g_nmem[g]; m++) n += d.g_mem_leaf[g * 8 + m] * d.g_mem_pods[g * 8 + m];
@@ -1588,6 +1633,16 @@ struct Core {
     for (int m = 0; m < d.g_nmem[g]; m++) n += d.g_mem_pods[g * 8 + m];
     return n;
   }
+  // slot offsets of member m: leaves before it / pods before it
+  HIVED_DEV void memberOffsets(int g, int m, int& leafOff, int& podOff) const {
+    leafOff = 0; podOff = 0;
+    for (int i = 0; i < m; i++) { leafOff += d.g_mem_leaf[g * 8 + i] * d.g_mem_pods[g * 8 + i]; podOff += d.g_mem_pods[g * 8 + i]; }
+  }
+  HIVED_DEV int memberOf(int g, int leafNum) const {
+    for (int m = 0; m < d.g_nmem[g]; m++) if (d.g_mem_leaf[g * 8 + m] == leafNum) return m;
+    return -1;
+  }
+#endif
   // merge + sort the spec's members (types.go:157-160, hived_algorithm.go:775-778)
   HIVED_DEV static int mergeMembers(const hived_pod_spec_t& sp, int* leaf, int* pods) {
     int n = 0;
@@ -1623,15 +1678,6 @@ struct Core {
     return n;
   }
   HIVED_DEV void eraseGroup(int g) { ST(d.g_state[g], HIVED_GROUP_NONE); }
-  // slot offsets of member m: leaves before it / pods before it
-  HIVED_DEV void memberOffsets(int g, int m, int& leafOff, int& podOff) const {
-    leafOff = 0; podOff = 0;
-    for (int i = 0; i < m; i++) { leafOff += d.g_mem_leaf[g * 8 + i] * d.g_mem_pods[g * 8 + i]; podOff += d.g_mem_pods[g * 8 + i]; }
-  }
-  HIVED_DEV int memberOf(int g, int leafNum) const {
-    for (int m = 0; m < d.g_nmem[g]; m++) if (d.g_mem_leaf[g * 8 + m] == leafNum) return m;
-    return -1;
-  }
 
   // hived_algorithm.go:1165-1191.  save != nullptr receives the original virtual placement.
   HIVED_DEV_NOINLINE void lazyPreemptAffinityGroup(int g, int32_t* save) {
@@ -1695,7 +1741,7 @@ struct Core {
   HIVED_DEV bool deleteGroupBatched(int g, int nl, int vc) {
     const int32_t* ph = gphys(g);
     bool bad = false;
-    long long tq = hv_clock();
+    long long tq = pclock();
     for (int b0 = 0; b0 < nl; b0 += HIVED_WARPSZ) {
       int i = b0 + lane;
       bool ok = true;
@@ -2022,7 +2068,7 @@ struct Core {
       reason |= HIVED_WAIT_SCOPE_VC;
       return false;
     }
-    long long tm0 = hv_clock();
+    long long tm0 = pclock();
     tryLazyPreempt(s.pl_v, r.nleaves);
     if (panicCode) return false;
     bool mapped = mapPlacementBatched(s.pl_v, r.nleaves, r.ignoreSuggested);
@@ -2031,7 +2077,7 @@ struct Core {
       if (panicCode) return false;
       mapped = mapVirtualPlacementToPhysical(r.chain, r.ignoreSuggested);
     }
-    stat_add(ST_CYC_MAP, hv_clock() - tm0);
+    stat_add(ST_CYC_MAP, pclock() - tm0);
     if (mapped) {
       // toPhysicalPlacement types.go:260-280
       for (int i = lane; i < r.nleaves; i += HIVED_WARPSZ) s.pl_p[i] = d.binding[s.pl_v[i]];
@@ -2333,7 +2379,7 @@ struct Core {
   // Afterwards priorities only rise (max per ancestor) and states only become Used.
   HIVED_DEV bool commitGroupBatched(const hived_pod_spec_t& sp, const BindView& b, int g, int gnmem, const int* gleaf, const int* gpods_) {
     const int p = sp.priority, chain = b.chain;
-    long long tq0 = hv_clock();
+    long long tq0 = pclock();
     if (!b.physIds || !b.has_preassigned || p < 0 || sp.vc < 0 || sp.vc >= d.S.nVCs || chain < 0 || chain >= d.S.nChains) return false;
     if (sp.pinned != -1) {
       if (sp.pinned < 0 || sp.pinned >= d.S.nPinned || d.vc_pinned_vset[sp.vc * d.S.nPinned + sp.pinned] < 0) return false;
@@ -2475,7 +2521,7 @@ struct Core {
 
   HIVED_DEV_NOINLINE void createAllocatedAffinityGroup(const hived_pod_spec_t& sp, const BindView& b) {
     int g = sp.group;
-    long long tq = hv_clock();
+    long long tq = pclock();
     int gleaf[HIVED_MAX_MEMBERS], gpods_[HIVED_MAX_MEMBERS];
     int gnmem = newGroup(g, sp, HIVED_GROUP_ALLOCATED, gleaf, gpods_);
     dbg(1, tq);
@@ -2551,7 +2597,7 @@ struct Core {
       createAllocatedAffinityGroup(sp, b);
       if (panicCode) return 0;
     }
-    long long tq = hv_clock();
+    long long tq = pclock();
     int m = memberOf(g, sp.leaf_num);
     if (m < 0 || podIndex < 0 || podIndex >= d.g_mem_pods[g * 8 + m]) { panic(HIVED_ERR_PLATFORM); return 0; }
     int leafOff, podOff;
@@ -2564,7 +2610,7 @@ struct Core {
 
   // hived_algorithm.go:272-296
   HIVED_DEV void deleteAllocatedPod(int g, int leafNum, int podIndex, int evVc) {
-    long long tq = hv_clock();
+    long long tq = pclock();
     if (g < 0 || g >= d.S.maxGroups || d.g_state[g] == HIVED_GROUP_NONE) return;
     if (multi && d.g_vc[g] != evVc) { panic(HIVED_ERR_PLATFORM); return; }  // the event was routed by a wrong VC id
     if (podIndex == -1) return;
@@ -2593,7 +2639,7 @@ struct Core {
   HIVED_DEV_NOINLINE int schedule(const hived_pod_spec_t& sp, int phase, hived_result_t* res) {
     int g = sp.group;
     stat_add(ST_SCHEDULE, 1);
-    if (lane == 0) hv_atomic_or64(&d.stats[ST_PRIO_MASK], (sp.priority >= -1 && sp.priority < 62) ? (1ll << (sp.priority + 1)) : (1ll << 62));
+    prioMask |= (sp.priority >= -1 && sp.priority < 62) ? (1ull << (sp.priority + 1)) : (1ull << 62);
     bool havePlacement = false, hasVirtual = false;
     const int32_t* phys = nullptr;
     const int32_t* virt = nullptr;
@@ -2601,7 +2647,7 @@ struct Core {
     int podIndex = 0, reason = 0, rcell = -1;
     bool victimsCollected = false;
     freshPlacement = false;
-    long long tq = hv_clock();
+    long long tq = pclock();
     if (d.g_state[g] != HIVED_GROUP_NONE) {
       // schedulePodFromExistingGroup :655-712
       int nl = groupLeaves(g);
@@ -2650,7 +2696,7 @@ struct Core {
       if (rc == 1) {
         havePlacement = true; phys = s.pl_p; virt = s.pl_v; freshPlacement = true;
         int nOverlap;
-        tq = hv_clock();
+        tq = pclock();
         collectPreemptionVictims(phys, r.nleaves, res, nOverlap);
         dbg(12, tq);
         victimsCollected = true;
@@ -2682,10 +2728,10 @@ struct Core {
       stat_add(ST_PREEMPT, 1);
       return 0;
     }
-    long long te0 = hv_clock();
+    long long te0 = pclock();
     emitBind(res, nmem, memLeaf, memPods, phys, virt, hasVirtual, sp.leaf_num, podIndex);
     lastPodIndex = podIndex;
-    stat_add(ST_CYC_EMIT, hv_clock() - te0);
+    stat_add(ST_CYC_EMIT, pclock() - te0);
     stat_add(ST_BIND, 1);
     return panicCode;
   }
@@ -2715,7 +2761,7 @@ struct Core {
 
   HIVED_DEV_NOINLINE void processEvent(const hived_event_t& ev, hived_result_t* res, const uint32_t* suggPool, const int32_t* aux) {
     panicCode = 0;
-    long long tev0 = hv_clock();
+    long long tev0 = pclock();
     {  // clearResult: one word per lane
       int32_t* w = reinterpret_cast<int32_t*>(res);
       const int iWait = (int)(offsetof(hived_result_t, wait_cell) / 4), iChain = (int)(offsetof(hived_result_t, chain) / 4),
@@ -2731,10 +2777,10 @@ struct Core {
       const hived_pod_spec_t& sp = ev.spec;
       rc = validateSpec(sp);
       const bool existing = rc == 0 && d.g_state[sp.group] != HIVED_GROUP_NONE;
-      long long ts0 = hv_clock();
+      long long ts0 = pclock();
       lastKind = -1;
       if (rc == 0) rc = schedule(sp, ev.phase, res);
-      if (existing) { stat_add(ST_CYC_SCHED_EXISTING, hv_clock() - ts0); stat_add(ST_N_SCHED_EXISTING, 1); }
+      if (existing) { stat_add(ST_CYC_SCHED_EXISTING, pclock() - ts0); stat_add(ST_N_SCHED_EXISTING, 1); }
       if (rc == 0 && type == HIVED_EV_SCHEDULE && lastKind == HIVED_KIND_BIND) {
         // the filterRoutine sequence: AddAllocatedPod with the PodBindInfo just produced
         BindView b;
@@ -2745,15 +2791,15 @@ struct Core {
         b.physIds = (d.S.directLeaf && freshPlacement) ? s.pl_p : nullptr;
         b.virtIds = (b.physIds && lastHasVirtual) ? s.pl_v : nullptr;
         sugg = nullptr;
-        long long ta0 = hv_clock();
+        long long ta0 = pclock();
         long long tq = ta0;
         // getAllocatedPodIndex (utils.go:291-304) on the PodBindInfo just produced finds the row that holds this
         // pod's node and first leaf index — the row Schedule emitted it from (leaf cells of a gang are distinct)
         int api = lastPodIndex;
         dbg(0, tq);
         addAllocatedPod(sp, b, api);
-        stat_add(ST_CYC_COMMIT, hv_clock() - ta0);
-        if (existing) { stat_add(ST_CYC_COMMIT_POD, hv_clock() - ta0); stat_add(ST_N_COMMIT_POD, 1); }
+        stat_add(ST_CYC_COMMIT, pclock() - ta0);
+        if (existing) { stat_add(ST_CYC_COMMIT_POD, pclock() - ta0); stat_add(ST_N_COMMIT_POD, 1); }
         rc = panicCode;
       }
     } else if (type == EV_ADD_ALLOCATED) {
@@ -2767,11 +2813,11 @@ struct Core {
       rc = validateSpec(ev.spec);
       if (rc == 0) { addAllocatedPod(ev.spec, b, ev.arg0); rc = panicCode; }
     } else if (type == HIVED_EV_DELETE_ALLOCATED) {
-      long long td0 = hv_clock();
+      long long td0 = pclock();
       deleteAllocatedPod(ev.spec.group, ev.spec.leaf_num, ev.arg0, ev.spec.vc);
-      stat_add(ST_CYC_DELETE, hv_clock() - td0);
+      stat_add(ST_CYC_DELETE, pclock() - td0);
       if (ev.spec.group >= 0 && ev.spec.group < d.S.maxGroups && d.g_state[ev.spec.group] != HIVED_GROUP_NONE) {
-        stat_add(ST_CYC_DELETE_POD, hv_clock() - td0); stat_add(ST_N_DELETE_POD, 1);
+        stat_add(ST_CYC_DELETE_POD, pclock() - td0); stat_add(ST_N_DELETE_POD, 1);
       }
       rc = panicCode;
     } else if (type == HIVED_EV_DELETE_UNALLOCATED) {
@@ -2784,7 +2830,7 @@ struct Core {
       rc = HIVED_ERR_PLATFORM;
     }
     ST(res->error, rc);
-    stat_add(ST_CYC_TOTAL, hv_clock() - tev0);
+    stat_add(ST_CYC_TOTAL, pclock() - tev0);
   }
 
   // NewHivedAlgorithm's dynamic part: initPinnedCells + initBadNodes (hived_algorithm.go:437-464)
@@ -2835,7 +2881,7 @@ struct Core {
         int i = own ? own[k] : k;
         curEvent = i;
         sharedHeld = false;
-        long long tq = hv_clock();
+        long long tq = pclock();
         constexpr int EVW = (int)(sizeof(hived_event_t) / 4);
         {
           const int32_t* src = reinterpret_cast<const int32_t*>(&events[i]);
@@ -2847,7 +2893,7 @@ struct Core {
         if (k + 2 < nOwn) hv_prefetch(&events[own ? own[k + 2] : k + 2]);
         dbg(14, tq);
         processEvent(*reinterpret_cast<const hived_event_t*>(sm->ev_words), &results[i], suggPool, aux);
-        tq = hv_clock();
+        tq = pclock();
         if (multi) {
           int next = (k + 1 < nOwn) ? own[k + 1] : 0x7fffffff;
           // release: only an event that touched the cluster-wide state publishes anything another CTA may read
@@ -2860,6 +2906,7 @@ struct Core {
         }
         dbg(15, tq);
       }
+      flushWork();
       ST(sm->pool_off, poolOff);
       ST(sm->panic, initPanic);
       ST(sm->cmd, CMD_EXIT);
