@@ -88,8 +88,11 @@ struct Core {
   // when a preassigned cell is bound or released.  Those sections run in batch order: a CTA enters
   // one only when every other CTA is already working on a later event (so all earlier events are
   // complete), and later events that need the shared state wait for this one the same way.
-  HIVED_DEV_NOINLINE void sharedEnter() {
+  HIVED_DEV void sharedEnter() {
     if (!multi || sharedHeld) return;
+    sharedEnterSlow();
+  }
+  HIVED_DEV_NOINLINE void sharedEnterSlow() {
     long long tw0 = pclock();
     while (true) {
       int mn = 0x7fffffff;
@@ -1138,7 +1141,7 @@ struct Core {
   }
   // :308-387.  slot = index of this node's candidate list (nodeAvailableLeafCells); out = leaf ids
   template <bool V>
-  HIVED_DEV_NOINLINE void findLeafCellsInNode(int node, int k, int p, int slot, bool fresh, int chain, int32_t* out) {
+  HIVED_DEV void findLeafCellsInNode(int node, int k, int p, int slot, bool fresh, int chain, int32_t* out) {
     int32_t* avail = s.cand + slot * MAX_NODE_LEAVES;
     int navail;
     if (fresh) {
@@ -1239,7 +1242,7 @@ struct Core {
   //   members: ascending leaf numbers (merged); placement written to `outLeaves` in
   //   (member, pod, leaf) order.  Returns false + reason on failure.
   // ======================================================================================
-  HIVED_DEV_NOINLINE bool tasSchedule(int sched, int nmem, const int* memLeaf, const int* memPods, int p,
+  HIVED_DEV bool tasSchedule(int sched, int nmem, const int* memLeaf, const int* memPods, int p,
                                       bool ignoreSuggested, int32_t* outLeaves, int& reason, int& rcell) {
     int npods = 0;
     for (int m = 0; m < nmem; m++)
@@ -1940,10 +1943,13 @@ struct Core {
   int32_t lastMemLeaf[HIVED_MAX_MEMBERS], lastMemPods[HIVED_MAX_MEMBERS];
 
   // hived_algorithm.go:944-965
-  HIVED_DEV_NOINLINE void tryLazyPreempt(const int32_t* vleaves, int nleaves) {
+  HIVED_DEV void tryLazyPreempt(const int32_t* vleaves, int nleaves) {
     lzCount = 0;
-    // fast path: no leaf of the placement is bound to a Used physical cell
+    // fast path (inlined at the call site): no leaf of the placement is bound to a Used physical cell
     if (firstIdx(nleaves, [&](int i) { int pl = d.v_pcell[vleaves[i]]; return pl >= 0 && d.p_state[pl] == HIVED_CELL_USED; }) < 0) return;
+    tryLazyPreemptSlow(vleaves, nleaves);
+  }
+  HIVED_DEV_NOINLINE void tryLazyPreemptSlow(const int32_t* vleaves, int nleaves) {
     for (int i = 0; i < nleaves; i++) {
       int pLeaf = d.v_pcell[vleaves[i]];
       if (pLeaf < 0) continue;
@@ -2060,7 +2066,7 @@ struct Core {
   }
 
   // hived_algorithm.go:898-942; intra_vc_scheduler.go:92-117
-  HIVED_DEV_NOINLINE bool scheduleGuaranteedAffinityGroup(const Req& r, int& reason, int& rcell) {
+  HIVED_DEV bool scheduleGuaranteedAffinityGroup(const Req& r, int& reason, int& rcell) {
     int vset = r.pinned >= 0 ? d.vc_pinned_vset[r.vc * d.S.nPinned + r.pinned] : (r.chain >= 0 ? d.vc_chain_vset[r.vc * d.S.nChains + r.chain] : -1);
     int sched = vset >= 0 ? d.vset_sched[vset] : -1;
     if (sched < 0) { reason = HIVED_WAIT_NO_SCHEDULER | HIVED_WAIT_SCOPE_VC; rcell = -1; return false; }
@@ -2123,7 +2129,7 @@ struct Core {
     return 0;
   }
   // hived_algorithm.go:754-796 (+ validateSchedulingRequest :855-870)
-  HIVED_DEV_NOINLINE int scheduleNewAffinityGroup(const hived_pod_spec_t& sp, Req& r, bool& hasVirtual, int& reason, int& rcell) {
+  HIVED_DEV int scheduleNewAffinityGroup(const hived_pod_spec_t& sp, Req& r, bool& hasVirtual, int& reason, int& rcell) {
     r.vc = sp.vc; r.pinned = sp.pinned; r.chain = -1; r.priority = sp.priority; r.group = sp.group;
     r.ignoreSuggested = (sp.flags & HIVED_SPEC_IGNORE_SUGGESTED) != 0;
     r.nmem = mergeMembers(sp, r.memLeaf, r.memPods);
@@ -2159,12 +2165,15 @@ struct Core {
   // ======================================================================================
   // utils.go:202-235.  victims written to the pool (pod id, node id) sorted by pod id; overlapping
   // preemptor groups (sorted by id) to s.lz_group, count returned through nOverlap.
-  HIVED_DEV_NOINLINE void collectPreemptionVictims(const int32_t* phys, int nleaves, hived_result_t* res, int& nOverlap) {
+  HIVED_DEV void collectPreemptionVictims(const int32_t* phys, int nleaves, hived_result_t* res, int& nOverlap) {
     nOverlap = 0;
     lastVictims = 0;
     // (victim_off / n_victims are 0 in the cleared record)
-    // fast path: every cell of the placement is Free
+    // fast path (inlined at the call site): every cell of the placement is Free
     if (firstIdx(nleaves, [&](int i) { int c = phys[i]; return c >= 0 && d.p_state[c] != HIVED_CELL_FREE; }) < 0) return;
+    collectPreemptionVictimsSlow(phys, nleaves, res, nOverlap);
+  }
+  HIVED_DEV_NOINLINE void collectPreemptionVictimsSlow(const int32_t* phys, int nleaves, hived_result_t* res, int& nOverlap) {
     int32_t* groups = s.tmp_list;  // using groups
     int ng = 0;
     int32_t* overlap = s.lz_group;  // lazy-preempt bookkeeping is dead by now
@@ -2519,7 +2528,7 @@ struct Core {
     return true;
   }
 
-  HIVED_DEV_NOINLINE void createAllocatedAffinityGroup(const hived_pod_spec_t& sp, const BindView& b) {
+  HIVED_DEV void createAllocatedAffinityGroup(const hived_pod_spec_t& sp, const BindView& b) {
     int g = sp.group;
     long long tq = pclock();
     int gleaf[HIVED_MAX_MEMBERS], gpods_[HIVED_MAX_MEMBERS];
@@ -2586,7 +2595,7 @@ struct Core {
     if (shouldLazyPreempt) lazyPreemptAffinityGroup(g, nullptr);
   }
 
-  HIVED_DEV_NOINLINE int addAllocatedPod(const hived_pod_spec_t& sp, const BindView& b, int podIndexFromInfo) {
+  HIVED_DEV int addAllocatedPod(const hived_pod_spec_t& sp, const BindView& b, int podIndexFromInfo) {
     int g = sp.group;
     int podIndex = 0;
     if (d.g_state[g] != HIVED_GROUP_NONE) {
@@ -2636,7 +2645,7 @@ struct Core {
   // ======================================================================================
   // Schedule (hived_algorithm.go:180-224, 655-752)
   // ======================================================================================
-  HIVED_DEV_NOINLINE int schedule(const hived_pod_spec_t& sp, int phase, hived_result_t* res) {
+  HIVED_DEV int schedule(const hived_pod_spec_t& sp, int phase, hived_result_t* res) {
     int g = sp.group;
     stat_add(ST_SCHEDULE, 1);
     prioMask |= (sp.priority >= -1 && sp.priority < 62) ? (1ull << (sp.priority + 1)) : (1ull << 62);
@@ -2759,7 +2768,7 @@ struct Core {
     return 0;
   }
 
-  HIVED_DEV_NOINLINE void processEvent(const hived_event_t& ev, hived_result_t* res, const uint32_t* suggPool, const int32_t* aux) {
+  HIVED_DEV void processEvent(const hived_event_t& ev, hived_result_t* res, const uint32_t* suggPool, const int32_t* aux) {
     panicCode = 0;
     long long tev0 = pclock();
     {  // clearResult: one word per lane
