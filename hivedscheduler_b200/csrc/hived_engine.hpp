@@ -69,6 +69,7 @@ struct Engine {
   std::vector<int32_t> ownOff;          // [launchCta + 1] into the owner-sorted index list (device: dOwn)
   std::vector<long long> poolBase;      // [launchCta + 1] pool slice of every CTA
   std::vector<long long> poolEnd;       // [launchCta] first unused word of every slice after the run
+  std::vector<uint8_t> ownerOf;         // owner CTA of every event of the batch being prepared (MAX_CTAS <= 255)
   std::vector<char> nodeBadHost;        // host mirror of the node health (decides whether a batch may run VC-parallel)
   int badCount = 0;
   uint64_t prioMaskHost = 0;
@@ -213,6 +214,11 @@ struct Engine {
     launchCta = 1;
     uint64_t mask = prioMaskHost;
     bool simple = nCtaMax > 1 && n >= 256 && badCount == 0 && !everRecovered;
+    // one pass over the events: regime flags, the owner CTA of every event and the pool words every owner may need
+    const int C = nCtaMax < T.nVCs ? nCtaMax : T.nVCs;
+    std::vector<int32_t> cnt(C + 1, 0);
+    std::vector<long long> need(C, 0);
+    ownerOf.resize((size_t)(n > 0 ? n : 1));
     for (int i = 0; i < n; i++) {
       const hived_event_t& ev = events[i];
       if (ev.type == HIVED_EV_SCHEDULE || ev.type == Core::EV_SCHEDULE_ONLY || ev.type == Core::EV_ADD_ALLOCATED) {
@@ -222,25 +228,23 @@ struct Engine {
       if (ev.type != HIVED_EV_SCHEDULE && ev.type != HIVED_EV_DELETE_ALLOCATED) simple = false;
       else if (ev.spec.vc < 0 || ev.spec.vc >= T.nVCs) simple = false;
       if (ev.type == Core::EV_ADD_ALLOCATED) everRecovered = true;
+      if (simple) {
+        int o = ev.spec.vc % C;
+        ownerOf[i] = (uint8_t)o;
+        cnt[o + 1]++;
+        if (ev.type == HIVED_EV_SCHEDULE) {
+          long long leaves = 0;
+          for (int m = 0; m < ev.spec.n_members && m < HIVED_MAX_MEMBERS; m++)
+            leaves += (long long)ev.spec.member_leaf_num[m] * ev.spec.member_pod_num[m];
+          need[o] += 3 * leaves;
+        }
+      }
     }
     prioMaskHost = mask;
     if ((mask & (mask - 1)) != 0 || (mask & 1)) simple = false;  // more than one priority, or opportunistic (-1)
     ownOff.assign(2, 0); ownOff[1] = n;
     poolBase.assign(2, 0); poolBase[1] = poolCap;
     if (simple) {
-      int C = nCtaMax < T.nVCs ? nCtaMax : T.nVCs;
-      std::vector<int32_t> cnt(C + 1, 0);
-      std::vector<long long> need(C, 0);
-      for (int i = 0; i < n; i++) {
-        int o = events[i].spec.vc % C;
-        cnt[o + 1]++;
-        if (events[i].type == HIVED_EV_SCHEDULE) {
-          long long leaves = 0;
-          for (int m = 0; m < events[i].spec.n_members && m < HIVED_MAX_MEMBERS; m++)
-            leaves += (long long)events[i].spec.member_leaf_num[m] * events[i].spec.member_pod_num[m];
-          need[o] += 3 * leaves;
-        }
-      }
       long long total = 0;
       for (int c = 0; c < C; c++) total += need[c];
       if (total <= poolCap) {
@@ -248,7 +252,7 @@ struct Engine {
         ownOff.assign(C + 1, 0);
         for (int c = 0; c < C; c++) ownOff[c + 1] = ownOff[c] + cnt[c + 1];
         std::vector<int32_t> own(n), fill(ownOff.begin(), ownOff.end() - 1);
-        for (int i = 0; i < n; i++) own[fill[events[i].spec.vc % C]++] = i;
+        for (int i = 0; i < n; i++) own[fill[ownerOf[i]]++] = i;
         dOwn.ensure((size_t)(n + C + 2) * 4);
         bk_h2d(dOwn.p, own.data(), (size_t)n * 4);
         bk_h2d((int32_t*)dOwn.p + n, ownOff.data(), (size_t)(C + 1) * 4);
