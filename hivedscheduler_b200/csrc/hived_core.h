@@ -49,7 +49,7 @@ struct Sm {
   int cnt[MAX_BINS * MAX_WARPS];
   int part[MAX_WARPS + 32];
   // ---- the current event, fetched with one coalesced 128-byte load
-  alignas(8) int32_t ev_words[sizeof(hived_event_t) / 4];
+  alignas(16) int32_t ev_words[2][sizeof(hived_event_t) / 4];  // double buffer: the next event arrives while this one runs
   // ---- written back at kernel exit
   int panic;
   long long pool_off;
@@ -2891,17 +2891,22 @@ struct Core {
         curEvent = i;
         sharedHeld = false;
         long long tq = pclock();
-        constexpr int EVW = (int)(sizeof(hived_event_t) / 4);
-        {
-          const int32_t* src = reinterpret_cast<const int32_t*>(&events[i]);
-          for (int w = lane; w < EVW; w += HIVED_WARPSZ) sm->ev_words[w] = src[w];
-          hv_warp_sync();
+        // The events are streamed from HBM once.  Event k was requested while event k-1 ran (asynchronous 16-byte
+        // copies into the other half of the double buffer: no register target, nothing waits at a call boundary);
+        // wait for it, then request event k+1 and pull event k+2 towards L2/L1.
+        constexpr int EVQ = (int)(sizeof(hived_event_t) / 16);
+        int32_t* cur = sm->ev_words[k & 1];
+        if (k == 0) { for (int q = lane; q < EVQ; q += HIVED_WARPSZ) hv_cp_async16(cur + 4 * q, reinterpret_cast<const char*>(&events[i]) + 16 * q); }
+        hv_cp_async_wait();
+        hv_warp_sync();
+        if (k + 1 < nOwn) {
+          const char* nxt = reinterpret_cast<const char*>(&events[own ? own[k + 1] : k + 1]);
+          int32_t* dst = sm->ev_words[(k + 1) & 1];
+          for (int q = lane; q < EVQ; q += HIVED_WARPSZ) hv_cp_async16(dst + 4 * q, nxt + 16 * q);
         }
-        // the events are streamed from HBM once: pull the one after next towards the SM now (no register
-        // target, so nothing waits for it at the call below)
         if (k + 2 < nOwn) hv_prefetch(&events[own ? own[k + 2] : k + 2]);
         dbg(14, tq);
-        processEvent(*reinterpret_cast<const hived_event_t*>(sm->ev_words), &results[i], suggPool, aux);
+        processEvent(*reinterpret_cast<const hived_event_t*>(cur), &results[i], suggPool, aux);
         tq = pclock();
         if (multi) {
           int next = (k + 1 < nOwn) ? own[k + 1] : 0x7fffffff;

@@ -46,6 +46,9 @@ inline void hv_atomic_add64(long long* a, long long v) { *a += v; }
 inline void hv_atomic_or64(long long* a, long long v) { *a |= v; }
 inline int hv_cta() { return 0; }
 inline void hv_prefetch(const void*) {}
+// asynchronous 16-byte global -> shared copies (host emulation: plain copy, nothing to wait for)
+inline void hv_cp_async16(void* smem, const void* gmem) { __builtin_memcpy(smem, gmem, 16); }
+inline void hv_cp_async_wait() {}
 inline int hv_reduce_max(int v) { return v; }
 inline int hv_reduce_min(int v) { return v; }
 inline int hv_reduce_add(int v) { return v; }
@@ -81,6 +84,12 @@ __device__ __forceinline__ void hv_fence() { __threadfence(); }
 __device__ __forceinline__ void hv_atomic_add64(long long* a, long long v) { atomicAdd((unsigned long long*)a, (unsigned long long)v); }
 __device__ __forceinline__ void hv_atomic_or64(long long* a, long long v) { atomicOr((unsigned long long*)a, (unsigned long long)v); }
 __device__ __forceinline__ int hv_cta() { return blockIdx.x; }
+// asynchronous 16-byte global -> shared copy (LDGSTS): no register target, completes in the background
+__device__ __forceinline__ void hv_cp_async16(void* smem, const void* gmem) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void hv_cp_async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 // warp-wide integer reductions: one REDUX instruction (sm_80+) instead of a five-step shuffle butterfly
 __device__ __forceinline__ int hv_reduce_max(int v) { return __reduce_max_sync(0xffffffffu, v); }
 __device__ __forceinline__ int hv_reduce_min(int v) { return __reduce_min_sync(0xffffffffu, v); }
