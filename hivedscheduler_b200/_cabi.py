@@ -20,6 +20,9 @@ ERR_PLATFORM = 100
 _M = C.c_int32 * HIVED_MAX_MEMBERS
 
 
+NIL_CELL = -2  # HIVED_NIL_CELL
+
+
 class Options(C.Structure):
     _fields_ = [("max_groups", C.c_int32), ("max_pods", C.c_int32), ("max_group_leaves", C.c_int32),
                 ("max_group_pods", C.c_int32), ("device", C.c_int32), ("flags", C.c_int32), ("reserved", C.c_int32 * 2)]
@@ -36,7 +39,7 @@ class Result(C.Structure):
                 ("chain", C.c_int32), ("pod_index", C.c_int32), ("node", C.c_int32), ("this_off", C.c_int32),
                 ("this_n", C.c_int32), ("n_members", C.c_int32), ("member_leaf_num", _M), ("member_pod_num", _M),
                 ("leaf_off", C.c_int32), ("n_leaves", C.c_int32), ("victim_off", C.c_int32),
-                ("n_victims", C.c_int32), ("has_virtual", C.c_int32), ("reserved", C.c_int32)]
+                ("n_victims", C.c_int32), ("has_virtual", C.c_int32), ("incomplete", C.c_int32)]
 
 
 class BindInfo(C.Structure):

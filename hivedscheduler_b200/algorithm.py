@@ -301,29 +301,60 @@ class HivedAlgorithm:
             reason = "%s when scheduling in physical cluster" % reason
         return reason
 
-    def _bind_info_from_result(self, res: _cabi.Result, pool) -> Dict[str, Any]:
-        """generatePodScheduleResult / generateAffinityGroupBindInfo output (pkg/algorithm/utils.go:38-171)."""
+    def _retrieve_missing_pod_placement(self, gid: int, leaf_cell_num: int, pod_index: int):
+        """retrieveMissingPodPlacement (pkg/algorithm/utils.go:250-265): the placement of a pod whose cells left the
+        spec, from the bind-info annotation of the group's allocated pods (first non-nil pod, members ascending)."""
+        gp = _cabi.GroupPlacement()
+        pcap = int(self._opt.max_group_pods)
+        pods = (C.c_int32 * pcap)()
+        self._lib.hived_get_group_placement(self._ctx, gid, C.byref(gp), None, None, 0, pods, pcap, None, 0)
+        for pid in pods[:min(gp.n_pods, pcap)]:
+            pod = self._pod_objs.get(pid) if pid >= 0 else None
+            if pod is None or ANNOTATION_POD_BIND_INFO not in pod.annotations:
+                continue
+            info = extract_pod_bind_info(pod)
+            for mbi in info["affinityGroupBindInfo"]:
+                if leaf_cell_num == len(mbi["podPlacements"][0]["physicalLeafCellIndices"]):
+                    return mbi["podPlacements"][pod_index], info["cellChain"]
+        raise PlatformError("No allocated pod found in an allocated group %s when retrieving placement for pod %d with "
+                            "leaf cell number %d" % (self._groups.names[gid], pod_index, leaf_cell_num))
+
+    def _bind_info_from_result(self, res: _cabi.Result, pool, gid: int = -1) -> Dict[str, Any]:
+        """generatePodScheduleResult / generateAffinityGroupBindInfo output (pkg/algorithm/utils.go:38-171).  Leaf cells
+        the library reports as nil (hived_result_t.incomplete: they left the cluster spec) make the pod's placement
+        come from the other pods' annotations, exactly in the reference's order: the retrieved PodPlacementInfo
+        replaces the pod's whole entry at every nil cell, later cells that still exist overwrite their own slot."""
         k = res.leaf_off
         agbi = []
+        chain = ""
+        cur_m = None
         for m in range(res.n_members):
             ln, pn = res.member_leaf_num[m], res.member_pod_num[m]
             pps = []
-            for _ in range(pn):
-                node = ""
-                idx, types = [], []
+            for pi in range(pn):
+                pp = {"physicalNode": "", "physicalLeafCellIndices": [0] * ln, "preassignedCellTypes": [""] * ln}
                 for j in range(ln):
                     nid, li, t = pool[k], pool[k + 1], pool[k + 2]
                     k += 3
-                    if j == 0:
-                        node = self.node_names[nid]
-                    idx.append(li)
-                    types.append("" if t < 0 else self.cell_type_names[t])
-                pps.append({"physicalNode": node, "physicalLeafCellIndices": idx, "preassignedCellTypes": types})
+                    if nid == _cabi.NIL_CELL and li == _cabi.NIL_CELL and t == _cabi.NIL_CELL:
+                        got, chain = self._retrieve_missing_pod_placement(gid, ln, pi)
+                        pp = {"physicalNode": got["physicalNode"],
+                              "physicalLeafCellIndices": list(got["physicalLeafCellIndices"]),
+                              "preassignedCellTypes": list(got["preassignedCellTypes"])}
+                        continue
+                    if pp["physicalNode"] == "":
+                        pp["physicalNode"] = self.node_names[nid] if nid >= 0 else ""
+                    pp["physicalLeafCellIndices"][j] = li
+                    pp["preassignedCellTypes"][j] = "" if t < 0 else self.cell_type_names[t]
+                pps.append(pp)
+            if cur_m is None and ln == res.this_n:
+                cur_m = m
             agbi.append({"podPlacements": pps})
-        iso = [pool[res.this_off + 3 * j + 1] for j in range(res.this_n)]
-        return {"node": self.node_names[res.node], "leafCellIsolation": iso,
-                "cellChain": self.chain_names[res.chain] if res.chain >= 0 else "",
-                "affinityGroupBindInfo": agbi}
+        mine = agbi[cur_m]["podPlacements"][res.pod_index]
+        if res.chain >= 0:  # utils.go:163-165: the chain of the pod's first cell when that cell exists
+            chain = self.chain_names[res.chain]
+        return {"node": mine["physicalNode"], "leafCellIsolation": list(mine["physicalLeafCellIndices"]),
+                "cellChain": chain, "affinityGroupBindInfo": agbi}
 
     def _bind_info_struct(self, info: Dict[str, Any]):
         bi = _cabi.BindInfo()
@@ -381,7 +412,7 @@ class HivedAlgorithm:
             out.pod_preempt_info = {"victim_pods": by_node[node],
                                     "all_victims": [p for n in sorted(by_node) for p in by_node[n]]}
         else:
-            out.pod_bind_info = self._bind_info_from_result(res, self._pool)
+            out.pod_bind_info = self._bind_info_from_result(res, self._pool, sp.group)
         return out
 
     def AddUnallocatedPod(self, pod: Pod) -> None:  # hived_algorithm.go:226-227

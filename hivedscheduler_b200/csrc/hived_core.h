@@ -2233,8 +2233,10 @@ struct Core {
   }
 
   // generatePodScheduleResult / generateAffinityGroupBindInfo (utils.go:38-171): lanes over the gang's leaves
+  // allowMissing: the group is an allocated one (utils.go:132-141: nil cells of such a group are reported, anything
+  // else is "The first pod in group ... was allocated invalid resource")
   HIVED_DEV void emitBind(hived_result_t* res, int nmem, const int* memLeaf, const int* memPods, const int32_t* phys,
-                          const int32_t* virt, bool hasVirtual, int curLeafNum, int curPodIndex) {
+                          const int32_t* virt, bool hasVirtual, int curLeafNum, int curPodIndex, bool allowMissing) {
     int nl = 0, thisOff = -1, thisN = 0;
     for (int m = 0; m < nmem; m++) {
       if (lane == 0) { res->member_leaf_num[m] = memLeaf[m]; res->member_pod_num[m] = memPods[m]; }
@@ -2249,7 +2251,8 @@ struct Core {
       if (k < nl) {
         int pl = phys[k];
         if (pl < 0) {
-          bad = true;  // retrieveMissingPodPlacement: recovery path
+          bad = true;  // a cell that left the spec: reported as a nil triple, completed by the shim (hived.h)
+          pool[base + 3 * k] = HIVED_NIL_CELL; pool[base + 3 * k + 1] = HIVED_NIL_CELL; pool[base + 3 * k + 2] = HIVED_NIL_CELL;
         } else {
           int t = -1;
           if (hasVirtual) { int vl = virt[k]; t = d.chain_lvl_type[cl(d.v_chain[vl], d.v_level[d.v_pre[vl]])]; }
@@ -2258,13 +2261,21 @@ struct Core {
           pool[base + 3 * k + 2] = t;
         }
       }
-      if (hv_ballot(bad)) { panic(HIVED_ERR_PLATFORM); return; }
+      bad = hv_ballot(bad) != 0;
+      if (bad && !allowMissing) { panic(HIVED_ERR_PLATFORM); return; }
     }
     hv_warp_sync();
     if (thisOff < 0) { panic(HIVED_ERR_PLATFORM); return; }
     int first = phys[thisOff];
+    if (bad) ST(res->incomplete, 1);
     lastLeafOff = base;
-    lastNode = d.p_node[first]; lastChain = d.p_chain[first]; lastFirstLeaf = d.p_leafidx[first];
+    int firstReal = first;  // PodPlacementInfo.PhysicalNode comes from the pod's first cell that still exists
+    if (bad && first < 0) {
+      int j = firstIdx(thisN, [&](int q) { return phys[thisOff + q] >= 0; });
+      firstReal = j >= 0 ? phys[thisOff + j] : -1;
+    }
+    lastNode = firstReal >= 0 ? d.p_node[firstReal] : -1; lastChain = first >= 0 ? d.p_chain[first] : -1;
+    lastFirstLeaf = first >= 0 ? d.p_leafidx[first] : -1;
     lastKind = HIVED_KIND_BIND; lastHasVirtual = hasVirtual ? 1 : 0; lastNmem = nmem;
     for (int m = 0; m < nmem; m++) { lastMemLeaf[m] = memLeaf[m]; lastMemPods[m] = memPods[m]; }
     if (lane == 0) {  // the fixed part of the record, one sequence point
@@ -2738,7 +2749,8 @@ struct Core {
       return 0;
     }
     long long te0 = pclock();
-    emitBind(res, nmem, memLeaf, memPods, phys, virt, hasVirtual, sp.leaf_num, podIndex);
+    emitBind(res, nmem, memLeaf, memPods, phys, virt, hasVirtual, sp.leaf_num, podIndex,
+             d.g_state[g] == HIVED_GROUP_ALLOCATED || d.g_state[g] == HIVED_GROUP_BEING_PREEMPTED);
     lastPodIndex = podIndex;
     stat_add(ST_CYC_EMIT, pclock() - te0);
     stat_add(ST_BIND, 1);

@@ -29,7 +29,7 @@ RESULT_DT = np.dtype([
     ("pod_index", "<i4"), ("node", "<i4"), ("this_off", "<i4"), ("this_n", "<i4"), ("n_members", "<i4"),
     ("member_leaf_num", "<i4", (8,)), ("member_pod_num", "<i4", (8,)), ("leaf_off", "<i4"),
     ("n_leaves", "<i4"), ("victim_off", "<i4"), ("n_victims", "<i4"), ("has_virtual", "<i4"),
-    ("reserved", "<i4")], align=True)
+    ("incomplete", "<i4")], align=True)
 assert RESULT_DT.itemsize == C.sizeof(_cabi.Result)
 
 MASK64 = (1 << 64) - 1

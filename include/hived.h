@@ -160,8 +160,12 @@ typedef struct hived_result {
   int32_t victim_off;
   int32_t n_victims;
   int32_t has_virtual; /* 0 when the placement has no virtual part (opportunistic) */
-  int32_t reserved;
+  int32_t incomplete;  /* 1: some leaf cells of the (allocated) group's placement are no longer in the cluster spec —
+                          their triples are (HIVED_NIL_CELL x3), node/chain are -1 when this pod's first cell is one of
+                          them.  The shim completes those pods' placements from the other pods' bind-info annotations
+                          (retrieveMissingPodPlacement, utils.go:250-265: the annotations live on the pod objects) */
 } hived_result_t;
+#define HIVED_NIL_CELL (-2)
 
 /* api.PodBindInfo as parsed from the pod-bind-info annotation by the shim
  * (internal.ExtractPodBindInfo, pkg/internal/utils.go:199-212).  leaves: 3 ints per leaf as in

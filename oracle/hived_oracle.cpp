@@ -930,9 +930,14 @@ void HivedAlgorithm::generatePodScheduleResult(ScheduleResult& r, int32_t curren
         if (pLeafCell == nullptr) {
           if (group == nullptr || group->state == groupPreempting)
             throw Panic("The first pod in group " + groupName + " was allocated invalid resource");
-          // retrieveMissingPodPlacement (utils.go:250-265) needs the other pods' annotations, which
-          // live in the shim; recovery path — not restated here.
-          throw Panic("oracle: retrieveMissingPodPlacement is outside the restated path");
+          // retrieveMissingPodPlacement (utils.go:250-265) reads the bind-info annotations of the group's other
+          // pods.  The annotations live on the pod objects, i.e. above the ABI: the cell is reported as nil
+          // (include/hived.h: hived_result_t.incomplete) and the shim completes the pod's placement.
+          info.incomplete = true;
+          mbi[podIndex].physicalLeafCellIndices[leafCellIndex] = HIVED_NIL_CELL;
+          mbi[podIndex].preassignedCellTypes[leafCellIndex] = kNilCellType;
+          mbi[podIndex].hasNil = true;
+          continue;
         }
         if (mbi[podIndex].physicalNode.empty()) mbi[podIndex].physicalNode = pLeafCell->nodes[0];
         mbi[podIndex].physicalLeafCellIndices[leafCellIndex] = pLeafCell->leafCellIndices[0];

@@ -158,8 +158,11 @@ struct PodPlacementInfo {
   std::vector<int32_t> physicalLeafCellIndices;
   std::vector<std::string> preassignedCellTypes;
   bool preassignedNil = false;
+  bool hasNil = false;  // some leaf cell of this pod is nil (left the spec): index HIVED_NIL_CELL, type kNilCellType
 };
+static const char* const kNilCellType = "\x01nil-cell";
 struct PodBindInfo {
+  bool incomplete = false;  // hived_result_t.incomplete
   std::string node;
   std::vector<int32_t> leafCellIsolation;
   std::string cellChain;

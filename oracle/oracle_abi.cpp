@@ -155,6 +155,11 @@ static int64_t emitResult(hived_ctx* ctx, const hived_pod_spec_t* sp, const Sche
       }
       if (off + 3 * (int64_t)lk.first > cap) throw Panic("result pool too small", HIVED_ERR_CAPACITY);
       for (int32_t j = 0; j < lk.first; j++) {
+        if (gms[p].physicalLeafCellIndices[j] == HIVED_NIL_CELL && gms[p].preassignedCellTypes[j] == kNilCellType) {
+          pool[off++] = HIVED_NIL_CELL; pool[off++] = HIVED_NIL_CELL; pool[off++] = HIVED_NIL_CELL;  // hived.h: incomplete
+          nLeaves++;
+          continue;
+        }
         pool[off++] = h.nodeIds.count(gms[p].physicalNode) ? h.nodeIds[gms[p].physicalNode] : -1;
         pool[off++] = gms[p].physicalLeafCellIndices[j];
         const std::string& t = gms[p].preassignedCellTypes[j];
@@ -166,6 +171,7 @@ static int64_t emitResult(hived_ctx* ctx, const hived_pod_spec_t* sp, const Sche
   }
   res->n_members = m;
   res->n_leaves = nLeaves;
+  res->incomplete = info.incomplete ? 1 : 0;
   return off - start;
 }
 

@@ -79,3 +79,66 @@ def test_inspect_device_program_matches_oracle(emu_lib, oracle_lib):
 @pytest.mark.gpu
 def test_inspect_cuda_matches_oracle(cuda_lib, oracle_lib):
     _check_inspect(cuda_lib, oracle_lib)
+
+
+# ---- recovery: a pod whose cells left the spec is "insisted on" from the other pods' annotations
+# (generateAffinityGroupBindInfo + retrieveMissingPodPlacement, pkg/algorithm/utils.go:126-141, 250-265)
+def _raw_c1(node_a="10.151.41.23", node_b="10.151.41.24"):
+    return {
+        "physicalCluster": {
+            "cellTypes": {
+                "K80-2GPU": {"childCellType": "K80", "childCellNumber": 2},
+                "K80-NODE": {"childCellType": "K80-2GPU", "childCellNumber": 2, "isNodeLevel": True},
+                "2-K80-NODE": {"childCellType": "K80-NODE", "childCellNumber": 2},
+            },
+            "physicalCells": [{"cellType": "2-K80-NODE", "cellChildren": [{"cellAddress": node_a}, {"cellAddress": node_b}]}],
+        },
+        "virtualClusters": {"default": {"virtualCells": [{"cellType": "2-K80-NODE", "cellNumber": 1}]}},
+    }
+
+
+def _check_missing_placement_is_retrieved(lib):
+    opts = dict(lib=lib, max_groups=16, max_pods=16, max_group_leaves=16, max_group_pods=8)
+    spec = {"virtualCluster": "default", "priority": 0, "leafCellType": "K80", "leafCellNumber": 4,
+            "affinityGroup": {"name": "gang", "members": [{"podNumber": 2, "leafCellNumber": 4}]}}
+
+    def pod(name):
+        p = alg.Pod(name, "ns", name)
+        p.annotations[alg.ANNOTATION_POD_SCHEDULING_SPEC] = alg.to_yaml(spec)
+        return p
+    h = alg.HivedAlgorithm(new_config(_raw_c1()), **opts)
+    for n in h.node_names:
+        h.setHealthyNode(n)
+    first = h.Schedule(pod("p0"), h.node_names, alg.FILTERING_PHASE).pod_bind_info
+    assert first is not None and len(first["leafCellIsolation"]) == 4
+    bound0 = alg.new_binding_pod(pod("p0"), first)
+    h.close()
+    # the cluster is reconfigured: the node of pod 0 is gone from the spec (renamed)
+    other = [n for n in ("10.151.41.23", "10.151.41.24") if n != first["node"]][0]
+    raw = _raw_c1("10.9.9.9", other) if first["node"] == "10.151.41.23" else _raw_c1(other, "10.9.9.9")
+    h = alg.HivedAlgorithm(new_config(raw), **opts)
+    for n in h.node_names:
+        h.setHealthyNode(n)
+    h.AddAllocatedPod(bound0)  # recovery: the cells of pod 0 are not found, the group exists without them
+    g = h.GetAffinityGroup("gang")["status"]
+    assert g["state"] == "Allocated" and g["allocatedPods"] == ["p0"]
+    assert first["node"] not in g.get("physicalPlacement", {})
+    second = h.Schedule(pod("p1"), h.node_names, alg.FILTERING_PHASE).pod_bind_info
+    assert second is not None
+    # the decision is insisted on: pod 0's placement comes back from its annotation, pod 1 gets the node that is left
+    assert second["affinityGroupBindInfo"][0]["podPlacements"][0] == first["affinityGroupBindInfo"][0]["podPlacements"][0]
+    assert second["node"] == other and second["node"] == second["affinityGroupBindInfo"][0]["podPlacements"][1]["physicalNode"]
+    assert second["cellChain"] == first["cellChain"] and sorted(second["leafCellIsolation"]) == [0, 1, 2, 3]
+    h.AddAllocatedPod(alg.new_binding_pod(pod("p1"), second))
+    assert sorted(h.GetAffinityGroup("gang")["status"]["allocatedPods"]) == ["p0", "p1"]
+    h.close()
+    return second
+
+
+def test_missing_placement_is_retrieved_device_program_matches_oracle(emu_lib, oracle_lib):
+    assert _check_missing_placement_is_retrieved(emu_lib) == _check_missing_placement_is_retrieved(oracle_lib)
+
+
+@pytest.mark.gpu
+def test_missing_placement_is_retrieved_cuda_matches_oracle(cuda_lib, oracle_lib):
+    assert _check_missing_placement_is_retrieved(cuda_lib) == _check_missing_placement_is_retrieved(oracle_lib)
