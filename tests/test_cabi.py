@@ -33,15 +33,17 @@ def test_struct_layouts_match_header():
     prog = r'''
 #include <stdio.h>
 #include "hived.h"
-int main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu\n",sizeof(hived_options_t),sizeof(hived_pod_spec_t),sizeof(hived_result_t),
-sizeof(hived_bind_info_t),sizeof(hived_event_t),sizeof(hived_group_info_t),sizeof(hived_cell_status_t),sizeof(hived_stats_t));return 0;}
+int main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n",sizeof(hived_options_t),sizeof(hived_pod_spec_t),sizeof(hived_result_t),
+sizeof(hived_bind_info_t),sizeof(hived_event_t),sizeof(hived_group_info_t),sizeof(hived_cell_status_t),sizeof(hived_stats_t),
+sizeof(hived_group_placement_t),sizeof(hived_cell_info_t));return 0;}
 '''
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "a.c"), "w").write(prog)
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(d, "a"), os.path.join(d, "a.c")])
         sizes = [int(x) for x in subprocess.check_output([os.path.join(d, "a")]).split()]
     assert sizes == [C.sizeof(x) for x in (_cabi.Options, _cabi.PodSpec, _cabi.Result, _cabi.BindInfo, _cabi.Event,
-                                           _cabi.GroupInfo, _cabi.CellStatus, _cabi.Stats)]
+                                           _cabi.GroupInfo, _cabi.CellStatus, _cabi.Stats, _cabi.GroupPlacement,
+                                           _cabi.CellInfo)]
 
 
 def test_product_fails_loudly_without_a_device():
