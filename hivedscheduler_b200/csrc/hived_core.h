@@ -977,6 +977,20 @@ struct Core {
   // CTA-wide exclusive prefix sum of sm->cnt[0..n) (row-major: bin-major, warp-minor)
   HIVED_DEV void ctaExclusiveScan(int n) {
     int nth = hv_nth(), tid = hv_tid(), w = hv_warp(), W = hv_nwarps();
+    if (n <= 32 * HIVED_WARPSZ) {  // few counters (the usual 36 bins x 16 warps): one warp scans them, one barrier
+      if (w == 0) {
+        int per = (n + HIVED_WARPSZ - 1) / HIVED_WARPSZ;
+        int lo = lane * per, hi = lo + per < n ? lo + per : n;
+        int sum = 0;
+        for (int i = lo; i < hi; i++) sum += sm->cnt[i];
+        int incl = sum;
+        for (int o = 1; o < HIVED_WARPSZ; o <<= 1) { int t = hv_shfl_up(incl, o); if (lane >= o) incl += t; }
+        int run = incl - sum;
+        for (int i = lo; i < hi; i++) { int v = sm->cnt[i]; sm->cnt[i] = run; run += v; }
+      }
+      hv_cta_sync();
+      return;
+    }
     int per = (n + nth - 1) / nth;
     int lo = tid * per, hi = lo + per < n ? lo + per : n;
     int s = 0;
@@ -998,11 +1012,15 @@ struct Core {
   }
 
   // one stable counting pass: out[rank] = in[i] ordered by bin(info[in[i]]), ties by position
+  // prezeroed: the caller cleared the counters before its last barrier.  cvOut != nullptr (the last pass): the
+  // scatter also persists the order (cvOut[rank] = cell) and lays the infos out in order (s.vw_sinfo[rank]).
   template <typename BinFn>
-  HIVED_DEV void stablePass(const int32_t* in, int32_t* out, int n, int nbins, BinFn binOf) {
+  HIVED_DEV void stablePass(const int32_t* in, int32_t* out, int n, int nbins, BinFn binOf, bool prezeroed, int32_t* cvOut) {
     int W = hv_nwarps(), w = hv_warp();
-    for (int i = hv_tid(); i < nbins * W; i += hv_nth()) sm->cnt[i] = 0;
-    hv_cta_sync();
+    if (!prezeroed) {
+      for (int i = hv_tid(); i < nbins * W; i += hv_nth()) sm->cnt[i] = 0;
+      hv_cta_sync();
+    }
     int chunk = (n + W - 1) / W;
     chunk = (chunk + HIVED_WARPSZ - 1) / HIVED_WARPSZ * HIVED_WARPSZ;
     int lo = w * chunk, hi = lo + chunk < n ? lo + chunk : n;
@@ -1021,7 +1039,9 @@ struct Core {
       unsigned peers = hv_match(b);
       if (i < hi) {
         int rank = sm->cnt[b * W + w] + hv_popc(peers & hv_lanemask_lt());
-        out[rank] = in[i];
+        int src = in[i];
+        out[rank] = src;
+        if (cvOut) { cvOut[rank] = s.vw_cell[src]; s.vw_sinfo[rank] = s.vw_info[src]; }
       }
       hv_warp_sync();
       if (i < hi && (peers & hv_lanemask_lt()) == 0) sm->cnt[b * W + w] += hv_popc(peers);
@@ -1038,7 +1058,11 @@ struct Core {
     const bool cross = d.s_cross[sched] != 0, isVirtual = d.s_virtual[sched] != 0;
     const int L = d.s_maxleaf[sched];
     const int tid = hv_tid(), nth = hv_nth();
-    // 1. per-node keys from leaf priorities (coalesced int32 loads of contiguous leaf ranges)
+    // 1. per-node keys from leaf priorities (coalesced int32 loads of contiguous leaf ranges); the counters of the
+    //    first sorting pass are cleared under the same barrier
+    const int W = hv_nwarps();
+    const int firstBins = cross ? 4 * (L + 1) : L + 1;
+    for (int i = tid; i < firstBins * W; i += nth) sm->cnt[i] = 0;
     for (int i = tid; i < n; i += nth) {
       int cell = d.cv[off + i];
       s.vw_cell[i] = cell;
@@ -1046,25 +1070,18 @@ struct Core {
       s.vw_ordA[i] = i;
     }
     hv_cta_sync();
-    // 2. stable sort by (healthy desc, suggested desc, usedSame desc, usedHigher asc): LSD passes
+    // 2. stable sort by (healthy desc, suggested desc, usedSame desc, usedHigher asc): LSD passes.  The last pass also
+    // 3. persists the new order (the reference sorts its slice in place) and lays the infos out in order.
     int32_t* cur = s.vw_ordA;
     int32_t* nxt = s.vw_ordB;
     if (!cross) {
-      stablePass(cur, nxt, n, L + 1, [](int w) { return infoHigher(w); });
+      stablePass(cur, nxt, n, L + 1, [](int w) { return infoHigher(w); }, true, nullptr);
       int32_t* t = cur; cur = nxt; nxt = t;
     }
     stablePass(cur, nxt, n, 4 * (L + 1), [L](int w) {
       return ((1 - infoHealthy(w)) * 2 + (1 - infoSuggested(w))) * (L + 1) + (L - infoSame(w));
-    });
-    { int32_t* t = cur; cur = nxt; nxt = t; }
-    // 3. persist the new order (the reference sorts its slice in place) and lay the infos out in order
-    for (int i = tid; i < n; i += nth) {
-      int src = cur[i];
-      d.cv[off + i] = s.vw_cell[src];
-      nxt[i] = s.vw_info[src];
-    }
-    hv_cta_sync();
-    const int32_t* sinfo = nxt;
+    }, cross, d.cv + off);
+    const int32_t* sinfo = s.vw_sinfo;
     // 4. greedy first-fit (findNodesForPods :278-305); every thread tracks the same scalar state
     int nodeIndex = 0, picked = 0, ok = 1, reason = 0, rcell = -1;
     for (int k = 0; k < npods && ok; k++) {

@@ -71,7 +71,7 @@ struct GroupMemFld {  // indexed by g * 8 + m like the flat arrays it replaces
   Z(mcpick, MAXL * MAX_FANOUT) Z(mccells, MAXL * MAX_FANOUT)                                           \
   Z(lz_group, S.LS) Z(lz_save, (int64_t)S.LZ * (S.LS + 1)) Z(ba_buf, (int64_t)MAXL * S.maxLevelCount)  \
   Z(tmp_list, S.maxLevelCount + MAX_FANOUT)                                                            \
-  Z(vw_cell, S.maxViewN) Z(vw_info, S.maxViewN) Z(vw_ordA, S.maxViewN) Z(vw_ordB, S.maxViewN)
+  Z(vw_cell, S.maxViewN) Z(vw_info, S.maxViewN) Z(vw_ordA, S.maxViewN) Z(vw_ordB, S.maxViewN) Z(vw_sinfo, S.maxViewN)
 
 struct Scratch {
 #define Z(name, count) int32_t* name;
