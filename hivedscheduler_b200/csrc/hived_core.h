@@ -14,7 +14,14 @@
 //   * the cluster-view pass (key computation, stable counting sort, greedy first-fit) is
 //     data-parallel over the whole CTA; the rest runs on the leader warp as SIMT code: uniform
 //     control flow, with lanes spread over tree levels, over the children of a cell, over the
-//     candidates of a free list and over the leaf cells of a gang.
+//     candidates of a free list and over the leaf cells of a gang;
+//   * commit, release and virtual->physical mapping handle a whole gang at once (commitGroupBatched,
+//     deleteGroupBatched, mapPlacementBatched): lanes over the gang's leaves, one step per tree level, a
+//     rank/select per level replacing the reference's leaf-by-leaf walks; the leaf-by-leaf code remains as the
+//     fallback for everything outside their preconditions (preemption, bad cells, pinned cells, recovery);
+//   * virtual clusters run on different CTAs and meet only in ordered shared sections (sharedEnter).
+// Everything on the leader's per-event path is inlined into the kernel (an out-of-line call costs a spill and
+// refill of the live registers); cold generic paths stay out of line behind inlined fast checks.
 #pragma once
 #include <cstddef>
 

@@ -1,10 +1,11 @@
 // libhived_cuda.so — the product: CUDA backend (sm_100a) of include/hived.h.
 //
 // One kernel, `hived_events_kernel`, runs the scheduling program of hived_core.h over an ordered
-// batch of events with ALL scheduler state resident in HBM (hived_dev.h).  It is launched as one
-// CTA: warp 0 walks the batch (the reference's contract is strictly sequential,
-// pkg/internal/types.go:64-71), the remaining warps are woken through the hardware barrier for the
-// data-parallel cluster-view pass of every scheduling decision.  There is no host implementation
+// batch of events with ALL scheduler state resident in HBM (hived_dev.h).  It is launched with one
+// CTA per group of virtual clusters (one CTA when the batch must run strictly sequentially): in every CTA
+// warp 0 walks its share of the batch (the reference's contract is sequential, pkg/internal/types.go:64-71;
+// VCs only meet in ordered shared sections), the remaining warps are woken through the hardware barrier for
+// the data-parallel cluster-view pass of every scheduling decision.  There is no host implementation
 // of the algorithm in this library: if no CUDA device is usable hived_create fails with
 // HIVED_ERR_NO_DEVICE.
 #include <cuda_runtime.h>
