@@ -75,7 +75,9 @@ class TraceBuilder:
 
     def schedule(self, group: int, vc: int, priority: int, leaf_type: int, leaf_num: int, pod_num: int,
                  phase: int = _cabi.PHASE_PREEMPTING, flags: int = _cabi.SPEC_IGNORE_SUGGESTED,
-                 first: bool = True) -> int:
+                 first: bool = True, members=None) -> int:
+        """members: [(leaf_num, pod_num), ...] of the whole gang when it has several (the pod itself asks for
+        ``leaf_num``); default: one member (leaf_num x pod_num)."""
         self._grow()
         e = self.ev[self.n]
         e["type"] = _cabi.EV_SCHEDULE
@@ -90,9 +92,12 @@ class TraceBuilder:
         s["leaf_type"] = leaf_type
         s["leaf_num"] = leaf_num
         s["flags"] = flags
-        s["n_members"] = 1
-        s["member_leaf_num"][0] = leaf_num
-        s["member_pod_num"][0] = pod_num
+        if members is None:
+            members = [(leaf_num, pod_num)]
+        s["n_members"] = len(members)
+        for i, (ln, pn) in enumerate(members):
+            s["member_leaf_num"][i] = ln
+            s["member_pod_num"][i] = pn
         self.decision[self.n] = first
         self.n += 1
         self.next_pod += 1
@@ -180,6 +185,109 @@ def trace_c3(n_gangs: int = 100000, n_vcs: int = 8, vc_gpus: int = 7168, load: f
     ev, dec = tb.finish()
     return {"name": "C%d" % config_number, "config": config_c3(), "events": ev, "decision": dec,
             "n_groups": n_gangs, "n_pods": tb.next_pod, "max_group_leaves": 64, "max_group_pods": 8}
+
+
+def trace_multi_member(n_gangs: int = 1200, n_vcs: int = 2, vc_gpus: int = (16 + 6) * 32 * 8, load: float = 0.85,
+                       config=None) -> Dict[str, Any]:
+    """Gangs with several members (AffinityGroup.Members with different leafCellNumbers, api/types.go:90-99): e.g.
+    1 x 8-GPU + 2 x 4-GPU + 3 x 1-GPU pods, scheduled pod by pod in a PRNG-shuffled member order, with the admission
+    window of C3.  Not a BASELINE config: it covers the member bookkeeping (merged, sorted members; slot offsets) of
+    the whole-gang commit / release paths, which the single-member C1-C5 traces do not."""
+    rng = XorShift64Star(seed_for(7))
+    shapes = [[(8, 1), (4, 2), (1, 3)], [(4, 1), (2, 2)], [(8, 2), (1, 1)], [(1, 2), (2, 1), (4, 1), (8, 1)], [(8, 8)],
+              [(2, 3)], [(4, 2), (8, 4)]]
+    tb = TraceBuilder(16 * n_gangs)
+    alive: List[deque] = [deque() for _ in range(n_vcs)]
+    alive_gpus = [0] * n_vcs
+    limit = int(load * vc_gpus)
+    for g in range(n_gangs):
+        members = shapes[rng.below(len(shapes))]
+        v = rng.below(n_vcs)
+        size = sum(ln * pn for ln, pn in members)
+        while alive_gpus[v] + size > limit and alive[v]:
+            og, om = alive[v].popleft()
+            for ln, pn in om:
+                for j in range(pn):
+                    tb.delete_allocated(og, ln, j, vc=v)
+            alive_gpus[v] -= sum(ln * pn for ln, pn in om)
+        # the spec lists the members in a shuffled order; pods arrive member by member in that order
+        order = list(members)
+        for i in range(len(order) - 1, 0, -1):
+            j = rng.below(i + 1)
+            order[i], order[j] = order[j], order[i]
+        first = True
+        for ln, pn in order:
+            for _ in range(pn):
+                tb.schedule(group=g, vc=v, priority=0, leaf_type=0, leaf_num=ln, pod_num=pn, first=first, members=order)
+                first = False
+        alive[v].append((g, members))
+        alive_gpus[v] += size
+    ev, dec = tb.finish()
+    from .config import config_c3
+    return {"name": "multi-member", "config": config if config is not None else config_c3(n_pods=4, n_vcs=2, racks_per_vc=6),
+            "events": ev, "decision": dec, "n_groups": n_gangs, "n_pods": tb.next_pod, "max_group_leaves": 64,
+            "max_group_pods": 16}
+
+
+def config_heterogeneous() -> Dict[str, Any]:
+    """Two chains (leaf types A and B, different depths and fan-outs), a pinned cell, VCs that own cells of both
+    chains at different levels — the shape of the reference's own test cluster, sized for thousands of decisions."""
+    from .config import new_config
+    raw = {
+        "physicalCluster": {
+            "cellTypes": {
+                "A-NODE": {"childCellType": "A", "childCellNumber": 4, "isNodeLevel": True},
+                "A-RACK": {"childCellType": "A-NODE", "childCellNumber": 4},
+                "B-NODE": {"childCellType": "B", "childCellNumber": 8, "isNodeLevel": True},
+                "B-RACK": {"childCellType": "B-NODE", "childCellNumber": 2},
+                "B-POD": {"childCellType": "B-RACK", "childCellNumber": 2},
+            },
+            "physicalCells": (
+                [{"cellType": "A-RACK",
+                  "cellChildren": [dict({"cellAddress": "a%d" % (4 * r + i)}, **({"pinnedCellId": "pin0"} if (r, i) == (0, 0) else {}))
+                                   for i in range(4)]} for r in range(4)] +
+                [{"cellType": "B-POD",
+                  "cellChildren": [{"cellChildren": [{"cellAddress": "b%d" % (4 * p + 2 * r + i)} for i in range(2)]}
+                                   for r in range(2)]} for p in range(3)]),
+        },
+        "virtualClusters": {
+            "vc0": {"virtualCells": [{"cellType": "A-RACK", "cellNumber": 1}, {"cellType": "B-POD.B-RACK", "cellNumber": 3}],
+                    "pinnedCells": [{"pinnedCellId": "pin0"}]},
+            "vc1": {"virtualCells": [{"cellType": "A-RACK.A-NODE", "cellNumber": 5}, {"cellType": "B-POD", "cellNumber": 1}]},
+        },
+    }
+    return new_config(raw)
+
+
+def trace_heterogeneous(n_gangs: int = 1500) -> Dict[str, Any]:
+    """Typed (A / B), untyped and pinned-cell requests of 1-8 GPUs over config_heterogeneous, in one ordered batch with
+    deletions; some requests must wait (the wait results are part of the parity)."""
+    rng = XorShift64Star(seed_for(8))
+    tb = TraceBuilder(8 * n_gangs)
+    alive: deque = deque()
+    for g in range(n_gangs):
+        v = rng.below(2)
+        kind = rng.below(10)
+        pinned = -1
+        if kind < 4:
+            leaf_type, leaf_num, pod_num = 0, [1, 2, 4, 4][rng.below(4)], 1 + rng.below(2)      # type A
+        elif kind < 8:
+            leaf_type, leaf_num, pod_num = 1, [1, 2, 4, 8][rng.below(4)], 1 + rng.below(2)      # type B
+        elif kind == 8:
+            leaf_type, leaf_num, pod_num = -1, 1 + rng.below(2), 1                               # any leaf cell type
+        else:
+            v, pinned, leaf_type, leaf_num, pod_num = 0, 0, -1, 1 + rng.below(2), 1             # vc0's pinned cell
+        while len(alive) > 18:
+            og, opn, oln, ov = alive.popleft()
+            for j in range(opn):
+                tb.delete_allocated(og, oln, j, vc=ov)
+        for j in range(pod_num):
+            tb.schedule(group=g, vc=v, priority=0, leaf_type=leaf_type, leaf_num=leaf_num, pod_num=pod_num, first=(j == 0))
+            tb.ev[tb.n - 1]["spec"]["pinned"] = pinned
+        alive.append((g, pod_num, leaf_num, v))
+    ev, dec = tb.finish()
+    return {"name": "heterogeneous", "config": config_heterogeneous(), "events": ev, "decision": dec, "n_groups": n_gangs,
+            "n_pods": tb.next_pod, "max_group_leaves": 16, "max_group_pods": 8}
 
 
 def trace_c5(n_steps: int = 10, gangs_per_step: int = 2000, n_nodes: int = 8192, n_vcs: int = 8, vc_gpus: int = 7168,

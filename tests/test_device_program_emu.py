@@ -47,6 +47,36 @@ def test_emu_matches_oracle_on_small_c3(emu_lib, oracle_lib):
     assert (np.concatenate([r[0]["kind"] for r in re_])[sched] == 1).all()
 
 
+def test_emu_matches_oracle_on_multi_member_gangs(emu_lib, oracle_lib):
+    """Several members per gang, listed in shuffled order (members are merged and sorted, types.go:157-160)."""
+    t = trace.trace_multi_member()
+    snaps = []
+    he, re_, se = run_trace(emu_lib, t, chunks=3, snapshots=snaps)
+    ho, ro, so = run_trace(oracle_lib, t, chunks=3, snapshots=snaps)
+    assert he == ho and se == so
+    assert snaps[0] == snaps[1]
+    for (a, pa), (b, pb) in zip(re_, ro):
+        assert a.tobytes() == b.tobytes()
+    kinds = np.concatenate([r[0]["kind"] for r in re_])[t["events"]["type"] == 0]
+    assert (kinds == 1).all()
+
+
+def test_emu_matches_oracle_on_heterogeneous_cluster(emu_lib, oracle_lib):
+    """Two chains, a pinned cell, typed / untyped / pinned requests, waits and deletes in one batch."""
+    t = trace.trace_heterogeneous()
+    snaps = []
+    he, re_, se = run_trace(emu_lib, t, chunks=2, snapshots=snaps)
+    ho, ro, so = run_trace(oracle_lib, t, chunks=2, snapshots=snaps)
+    assert he == ho and se == so
+    assert snaps[0] == snaps[1]
+    for (a, pa), (b, pb) in zip(re_, ro):
+        assert a.tobytes() == b.tobytes()
+    sched = t["events"]["type"] == 0
+    kinds = np.concatenate([r[0]["kind"] for r in re_])[sched]
+    errors = np.concatenate([r[0]["error"] for r in re_])[sched]
+    assert (errors == 0).all() and (kinds == 1).sum() > 500 and (kinds == 0).sum() > 0  # binds and waits both occur
+
+
 def small_cluster():
     return config.config_c3(n_pods=4, n_vcs=2, racks_per_vc=6)
 
