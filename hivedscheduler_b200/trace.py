@@ -290,6 +290,51 @@ def trace_heterogeneous(n_gangs: int = 1500) -> Dict[str, Any]:
             "n_pods": tb.next_pod, "max_group_leaves": 16, "max_group_pods": 8}
 
 
+def trace_suggested_nodes(n_gangs: int = 900, n_sets: int = 6) -> Dict[str, Any]:
+    """K8s suggested nodes in batch mode: most requests honour a suggested-node set (ignoreK8sSuggestedNodes = false,
+    hived_algorithm.go:190-193) drawn from a few PRNG bitmaps that leave out ~15 % of the nodes; some nodes are bad.
+    Covers the suggested / healthy sort keys, the non-suggested wait reasons and the backtracking mapping
+    (cell_allocation.go:199-315) through hived_event_t.suggested_off."""
+    from .config import config_c3
+    cfg = config_c3(n_pods=4, n_vcs=2, racks_per_vc=6)
+    n_nodes = 4 * 16 * 32
+    words = (n_nodes + 31) // 32
+    rng = XorShift64Star(seed_for(9))
+    pool = np.zeros(n_sets * words, dtype=np.uint32)
+    for k in range(n_sets):
+        for node in range(n_nodes):
+            if rng.below(100) >= 15:
+                pool[k * words + (node >> 5)] |= np.uint32(1 << (node & 31))
+    tb = TraceBuilder(8 * n_gangs)
+    for _ in range(40):
+        tb.node_health(rng.below(n_nodes), False)
+    alive: List[deque] = [deque() for _ in range(2)]
+    alive_gpus = [0, 0]
+    limit = int(0.8 * (16 + 6) * 32 * 8)
+    for g in range(n_gangs):
+        pod_num, leaf_num = _gang_shape(rng.below(100))
+        v = rng.below(2)
+        size = pod_num * leaf_num
+        while alive_gpus[v] + size > limit and alive[v]:
+            og, opn, oln = alive[v].popleft()
+            for j in range(opn):
+                tb.delete_allocated(og, oln, j, vc=v)
+            alive_gpus[v] -= opn * oln
+        honour = rng.below(10) < 7
+        off = rng.below(n_sets) * words
+        phase = _cabi.PHASE_FILTERING if rng.below(2) else _cabi.PHASE_PREEMPTING
+        for j in range(pod_num):
+            tb.schedule(group=g, vc=v, priority=0, leaf_type=0, leaf_num=leaf_num, pod_num=pod_num, first=(j == 0),
+                        flags=0 if honour else _cabi.SPEC_IGNORE_SUGGESTED, phase=phase)
+            if honour:
+                tb.ev[tb.n - 1]["suggested_off"] = off
+        alive[v].append((g, pod_num, leaf_num))
+        alive_gpus[v] += size
+    ev, dec = tb.finish()
+    return {"name": "suggested-nodes", "config": cfg, "events": ev, "decision": dec, "n_groups": n_gangs,
+            "n_pods": tb.next_pod, "max_group_leaves": 64, "max_group_pods": 8, "sugg_pool": pool}
+
+
 def trace_c5(n_steps: int = 10, gangs_per_step: int = 2000, n_nodes: int = 8192, n_vcs: int = 8, vc_gpus: int = 7168,
              flip_fraction: float = 0.1, load: float = 0.9, config=None) -> Dict[str, Any]:
     """C5: churn — every step flips the health of 10 % PRNG-chosen nodes, then schedules 2000 gangs
@@ -446,15 +491,20 @@ class BatchContext:
         ev["suggested_off"] = -1
         self.process(ev, pool_words=16)
 
-    def process(self, events: np.ndarray, pool_words: int = None):
+    def process(self, events: np.ndarray, pool_words: int = None, sugg_pool: np.ndarray = None):
+        """sugg_pool: uint32 words backing hived_event_t.suggested_off (node bitmaps), or None."""
         n = len(events)
         if pool_words is None:
             pool_words = 3 * 64 * n // 4 + 4096
         res = np.zeros(n, dtype=RESULT_DT)
         pool = np.zeros(pool_words, dtype=np.int32)
         events = np.ascontiguousarray(events)
+        sp, sw = None, 0
+        if sugg_pool is not None and len(sugg_pool):
+            sugg_pool = np.ascontiguousarray(sugg_pool, dtype=np.uint32)
+            sp, sw = sugg_pool.ctypes.data_as(C.POINTER(C.c_uint32)), len(sugg_pool)
         rc = self.lib.hived_process_events(
-            self.ctx, events.ctypes.data_as(C.POINTER(_cabi.Event)), n, None, 0,
+            self.ctx, events.ctypes.data_as(C.POINTER(_cabi.Event)), n, sp, sw,
             res.ctypes.data_as(C.POINTER(_cabi.Result)), pool.ctypes.data_as(C.POINTER(C.c_int32)), pool_words)
         if rc != 0:
             raise RuntimeError("hived_process_events failed (%d): %s" % (

@@ -61,7 +61,7 @@ def run_trace(lib, t, n_events=None, chunks=1, device=0, snapshots=None):
     bounds = [len(ev) * (i + 1) // chunks for i in range(chunks)]
     start, all_res = 0, []
     for b in bounds:
-        res, pool = bc.process(ev[start:b], 3 * 64 * (b - start) + 4096)
+        res, pool = bc.process(ev[start:b], 3 * 64 * (b - start) + 4096, t.get("sugg_pool"))
         all_res.append((res, pool))
         start = b
     out = (bc.result_hash(), all_res, bc.stats())

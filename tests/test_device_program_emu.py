@@ -77,6 +77,23 @@ def test_emu_matches_oracle_on_heterogeneous_cluster(emu_lib, oracle_lib):
     assert (errors == 0).all() and (kinds == 1).sum() > 500 and (kinds == 0).sum() > 0  # binds and waits both occur
 
 
+def test_emu_matches_oracle_with_suggested_node_sets(emu_lib, oracle_lib):
+    """Suggested-node bitmaps through the batch interface, bad nodes, both scheduling phases."""
+    t = trace.trace_suggested_nodes()
+    snaps = []
+    he, re_, se = run_trace(emu_lib, t, chunks=2, snapshots=snaps)
+    ho, ro, so = run_trace(oracle_lib, t, chunks=2, snapshots=snaps)
+    assert he == ho and se == so
+    assert snaps[0] == snaps[1]
+    for (a, pa), (b, pb) in zip(re_, ro):
+        assert a.tobytes() == b.tobytes()
+    sched = t["events"]["type"] == 0
+    kinds = np.concatenate([r[0]["kind"] for r in re_])[sched]
+    codes = np.concatenate([r[0]["wait_code"] for r in re_])[sched]
+    assert (kinds == 1).sum() > 300
+    assert len(np.unique(codes[kinds == 0])) >= 1  # some requests wait on bad / non-suggested nodes
+
+
 def small_cluster():
     return config.config_c3(n_pods=4, n_vcs=2, racks_per_vc=6)
 
