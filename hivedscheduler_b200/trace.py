@@ -371,12 +371,16 @@ def trace_c5(n_steps: int = 10, gangs_per_step: int = 2000, n_nodes: int = 8192,
 
 
 def run_c4_interactive(lib, config, n_gangs: int, n_vcs: int, vc_gpus: int, total_gpus: int, load: float = 0.9,
-                       max_groups: int = None):
+                       max_groups: int = None, lazy_percent: int = 0):
     """C4: guaranteed (priority 0/1/2, lazyPreemptionEnable false) and opportunistic (-1) gangs interleaved by
     the PRNG.  The event stream depends on the decisions, so the harness plays kube-scheduler call by call
     (SURVEY.md section 8d): Filtering-phase Schedule; on a preempt result -> Preempting-phase Schedule ->
-    delete every pod of every victim gang -> Filtering-phase Schedule again.  Returns (hash, decision log)."""
+    delete every pod of every victim gang -> Filtering-phase Schedule again.  Returns (hash, decision log).
+    lazy_percent > 0 (not a BASELINE config): that share of the guaranteed gangs sets lazyPreemptionEnable, so a
+    higher-priority gang downgrades them to opportunistic instead of preempting them (hived_algorithm.go:944-965,
+    1165-1222)."""
     rng = XorShift64Star(seed_for(4))
+    lazy_rng = XorShift64Star(seed_for(14))
     bc = BatchContext(lib, config, max_groups or (n_gangs + 8), 8 * n_gangs + 64, 64, 8)
     bc.set_all_nodes_healthy()
     tb = TraceBuilder(4)
@@ -387,6 +391,7 @@ def run_c4_interactive(lib, config, n_gangs: int, n_vcs: int, vc_gpus: int, tota
     alive_gpus = [0] * n_vcs
     opp_alive, opp_gpus = deque(), 0
     log = []
+    lazy_seen = set()
 
     def one(ev_builder):
         tb.n = 0
@@ -405,6 +410,9 @@ def run_c4_interactive(lib, config, n_gangs: int, n_vcs: int, vc_gpus: int, tota
         opportunistic = rng.below(2) == 1
         prio = -1 if opportunistic else rng.below(3)
         size = pod_num * leaf_num
+        gang_flags = _cabi.SPEC_IGNORE_SUGGESTED
+        if lazy_percent > 0 and not opportunistic and lazy_rng.below(100) < lazy_percent:
+            gang_flags |= _cabi.SPEC_LAZY_PREEMPTION
         if opportunistic:
             while opp_gpus + size > int(load * total_gpus) and opp_alive:
                 og, ov = opp_alive.popleft()
@@ -422,7 +430,7 @@ def run_c4_interactive(lib, config, n_gangs: int, n_vcs: int, vc_gpus: int, tota
             def sched(phase):
                 pid = tb.next_pod
                 tb.schedule(group=g, vc=v, priority=prio, leaf_type=0, leaf_num=leaf_num, pod_num=pod_num, phase=phase,
-                            flags=_cabi.SPEC_IGNORE_SUGGESTED, first=(j == 0))
+                            flags=gang_flags, first=(j == 0))
                 return pid
             holder = {}
             r, pool = one(lambda: holder.setdefault("pid", sched(_cabi.PHASE_FILTERING)))
@@ -449,6 +457,14 @@ def run_c4_interactive(lib, config, n_gangs: int, n_vcs: int, vc_gpus: int, tota
                 log.append((g, j, "wait" if r["kind"] == _cabi.KIND_WAIT else "preempt-again", int(r["wait_code"])))
                 bound = False
                 break
+        if bound and lazy_percent > 0 and not opportunistic:
+            # which alive gangs of this VC have lost their virtual placement (were lazy-preempted) by now?
+            gi = _cabi.GroupInfo()
+            for og in alive[v]:
+                if og in group_pods and og not in lazy_seen:
+                    lib.hived_get_group(bc.ctx, og, C.byref(gi))
+                    if gi.state != _cabi.GROUP_NONE and not gi.has_virtual:
+                        lazy_seen.add(og)
         if bound:
             group_size[g] = size
             if opportunistic:
@@ -459,6 +475,7 @@ def run_c4_interactive(lib, config, n_gangs: int, n_vcs: int, vc_gpus: int, tota
             delete_group(g, v)
     h = bc.result_hash()
     stats = bc.stats()
+    stats["lazy_preempted_groups"] = len(lazy_seen)  # gangs observed without a virtual placement while alive
     bc.close()
     return h, log, stats
 

@@ -94,6 +94,19 @@ def test_emu_matches_oracle_with_suggested_node_sets(emu_lib, oracle_lib):
     assert len(np.unique(codes[kinds == 0])) >= 1  # some requests wait on bad / non-suggested nodes
 
 
+def test_emu_matches_oracle_with_lazy_preemption(emu_lib, oracle_lib):
+    """C4's call-by-call harness with lazyPreemptionEnable on half of the guaranteed gangs (lazy preemption,
+    revert on a failed mapping, downgraded gangs being deleted / preempted later)."""
+    # no admission window (load 3): the VCs fill up, higher priorities have to take cells from lower ones
+    kw = dict(config=small_cluster(), n_gangs=4500, n_vcs=2, vc_gpus=(16 + 6) * 32 * 8, total_gpus=4 * 16 * 32 * 8,
+              lazy_percent=50, load=3.0)
+    he, le, se = trace.run_c4_interactive(emu_lib, **kw)
+    ho, lo, so = trace.run_c4_interactive(oracle_lib, **kw)
+    assert le == lo
+    assert he == ho and se == so
+    assert so["lazy_preempted_groups"] > 0  # lazy preemption really happens in this workload
+
+
 def small_cluster():
     return config.config_c3(n_pods=4, n_vcs=2, racks_per_vc=6)
 

@@ -163,3 +163,16 @@ def test_vc_parallel_equals_single_cta(cuda_lib):
         env = dict(os.environ, HIVED_NCTA=ncta)
         outs.append(subprocess.check_output([sys.executable, "-c", code], env=env).decode().strip().splitlines()[-1])
     assert outs[0] == outs[1] == outs[2], outs
+
+
+def test_cuda_matches_oracle_with_lazy_preemption(cuda_lib, oracle_lib):
+    """C4's call-by-call harness, VCs left to fill up, lazyPreemptionEnable on half of the guaranteed gangs: lazy
+    preemption, its revert on a failed mapping, and downgraded gangs being preempted later — rows a7, a19."""
+    from test_device_program_emu import small_cluster
+    kw = dict(config=small_cluster(), n_gangs=4500, n_vcs=2, vc_gpus=(16 + 6) * 32 * 8, total_gpus=4 * 16 * 32 * 8,
+              lazy_percent=50, load=3.0)
+    hc, lc, sc = trace.run_c4_interactive(cuda_lib, **kw)
+    ho, lo, so = trace.run_c4_interactive(oracle_lib, **kw)
+    assert lc == lo
+    assert hc == ho and sc == so
+    assert so["lazy_preempted_groups"] > 0
