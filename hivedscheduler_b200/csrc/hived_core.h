@@ -2682,7 +2682,6 @@ struct Core {
   // ======================================================================================
   HIVED_DEV int schedule(const hived_pod_spec_t& sp, int phase, hived_result_t* res) {
     int g = sp.group;
-    stat_add(ST_SCHEDULE, 1);
     prioMask |= (sp.priority >= -1 && sp.priority < 62) ? (1ull << (sp.priority + 1)) : (1ull << 62);
     bool havePlacement = false, hasVirtual = false;
     const int32_t* phys = nullptr;
@@ -2824,7 +2823,10 @@ struct Core {
       const bool existing = rc == 0 && d.g_state[sp.group] != HIVED_GROUP_NONE;
       long long ts0 = pclock();
       lastKind = -1;
-      if (rc == 0) rc = schedule(sp, ev.phase, res);
+      if (rc == 0) {
+        rc = schedule(sp, ev.phase, res);
+        if (rc == 0) stat_add(ST_SCHEDULE, 1);  // Schedule calls that returned a result (a panic is not a decision)
+      }
       if (existing) { stat_add(ST_CYC_SCHED_EXISTING, pclock() - ts0); stat_add(ST_N_SCHED_EXISTING, 1); }
       if (rc == 0 && type == HIVED_EV_SCHEDULE && lastKind == HIVED_KIND_BIND) {
         // the filterRoutine sequence: AddAllocatedPod with the PodBindInfo just produced

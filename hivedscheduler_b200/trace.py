@@ -335,6 +335,53 @@ def trace_suggested_nodes(n_gangs: int = 900, n_sets: int = 6) -> Dict[str, Any]
             "n_pods": tb.next_pod, "max_group_leaves": 64, "max_group_pods": 8, "sugg_pool": pool}
 
 
+def trace_bad_requests() -> Dict[str, Any]:
+    """Requests the reference answers with a 400 / a panic, interleaved with good ones in one batch (every event gets its
+    own error code; a failing event leaves the state unchanged, pkg/internal/types.go:58-61): unknown VC, unknown /
+    foreign leaf type, unknown pinned cell, opportunistic pod in a pinned cell, priority / leaf number out of range,
+    a pod that is not a member of its own group, more pods than the member has, deletes of unknown groups and slots.
+    (Ids or sizes beyond hived_options_t fail the whole call with HIVED_ERR_CAPACITY and are not part of this batch.)"""
+    cfg = config_heterogeneous()
+    tb = TraceBuilder(256)
+
+    def bad(**over):
+        tb.schedule(group=over.pop("group", 900), vc=over.pop("vc", 0), priority=over.pop("priority", 0),
+                    leaf_type=over.pop("leaf_type", 0), leaf_num=over.pop("leaf_num", 1), pod_num=over.pop("pod_num", 1),
+                    members=over.pop("members", None), first=True)
+        e = tb.ev[tb.n - 1]
+        for k, val in over.items():
+            e["spec"][k] = val
+
+    for rnd in range(3):
+        g0 = 10 * rnd
+        tb.schedule(group=g0, vc=0, priority=0, leaf_type=0, leaf_num=2, pod_num=2)          # good: pod 0 of a 2-pod gang
+        bad(vc=-1)                                                                           # unknown VC
+        bad(vc=7)
+        bad(leaf_type=-2)                                                                    # unknown leaf type string
+        bad(leaf_type=5)
+        bad(pinned=-2)                                                                       # unknown pinned cell id
+        bad(pinned=3)
+        bad(vc=1, pinned=0)                                                                  # vc1 does not own pin0
+        bad(pinned=0, priority=-1)                                                           # opportunistic in a pinned cell
+        bad(priority=-2)
+        bad(priority=1001)
+        bad(leaf_num=0)
+        bad(leaf_num=3, members=[(2, 1)])                                                    # pod not among the members
+        bad(members=[(1, 0)])
+        tb.schedule(group=g0, vc=0, priority=0, leaf_type=0, leaf_num=2, pod_num=2)          # good: pod 1
+        tb.schedule(group=g0, vc=0, priority=0, leaf_type=0, leaf_num=2, pod_num=2)          # a third pod: too many
+        tb.schedule(group=g0 + 1, vc=1, priority=0, leaf_type=1, leaf_num=8, pod_num=1)      # good, other chain
+        tb.delete_allocated(777, 1, 0, vc=0)                                                 # unknown group: no-op
+        tb.delete_allocated(g0, 2, 5, vc=0)                                                  # slot out of range
+        tb.delete_allocated(g0, 3, 0, vc=0)                                                  # no member with 3 leaves
+        tb.delete_allocated(g0, 2, 0, vc=0)
+        tb.delete_allocated(g0, 2, 1, vc=0)                                                  # last pod: the gang is released
+        tb.delete_allocated(g0, 2, 1, vc=0)                                                  # again: unknown by now
+    ev, dec = tb.finish()
+    return {"name": "bad-requests", "config": cfg, "events": ev, "decision": dec, "n_groups": 1000, "n_pods": tb.next_pod,
+            "max_group_leaves": 16, "max_group_pods": 8}
+
+
 def trace_c5(n_steps: int = 10, gangs_per_step: int = 2000, n_nodes: int = 8192, n_vcs: int = 8, vc_gpus: int = 7168,
              flip_fraction: float = 0.1, load: float = 0.9, config=None) -> Dict[str, Any]:
     """C5: churn — every step flips the health of 10 % PRNG-chosen nodes, then schedules 2000 gangs

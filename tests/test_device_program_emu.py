@@ -107,6 +107,40 @@ def test_emu_matches_oracle_with_lazy_preemption(emu_lib, oracle_lib):
     assert so["lazy_preempted_groups"] > 0  # lazy preemption really happens in this workload
 
 
+def test_emu_matches_oracle_on_bad_requests(emu_lib, oracle_lib):
+    """Requests the reference rejects (400s and panics), interleaved with good ones: per-event error codes, and the
+    state after a failing event is the state before it."""
+    t = trace.trace_bad_requests()
+    snaps = []
+    he, re_, se = run_trace(emu_lib, t, snapshots=snaps)
+    ho, ro, so = run_trace(oracle_lib, t, snapshots=snaps)
+    assert he == ho and se == so and snaps[0] == snaps[1]
+    assert re_[0][0].tobytes() == ro[0][0].tobytes()
+    errors = set(int(e) for e in re_[0][0]["error"])
+    assert {0, 1, 2, 3, 4, 6, 7, 100} <= errors  # unknown VC / pinned / opp-in-pinned / leaf type / too many pods / bad spec / panic
+
+
+@pytest.mark.parametrize("field,value", [("group", 5000), ("group", -1), ("pod", 10 ** 6), ("member_leaf_num", 64)])
+def test_ids_beyond_the_capacities_fail_the_call(emu_lib, oracle_lib, field, value):
+    """Interned ids / gang sizes beyond hived_options_t are a HIVED_ERR_CAPACITY for the whole call (102), on both."""
+    t = trace.trace_bad_requests()
+    tb = trace.TraceBuilder(4)
+    tb.schedule(group=1, vc=0, priority=0, leaf_type=0, leaf_num=1, pod_num=1)
+    if field == "member_leaf_num":
+        tb.ev[0]["spec"]["member_leaf_num"][0] = value
+        tb.ev[0]["spec"]["leaf_num"] = value
+    else:
+        tb.ev[0]["spec"][field] = value
+    ev, _ = tb.finish()
+    for lib in (emu_lib, oracle_lib):
+        bc = trace.BatchContext(lib, t["config"], 1000, 64, 16, 8)
+        bc.set_all_nodes_healthy()
+        with pytest.raises(RuntimeError) as ei:
+            bc.process(ev, 4096)
+        assert "(102)" in str(ei.value)
+        bc.close()
+
+
 def small_cluster():
     return config.config_c3(n_pods=4, n_vcs=2, racks_per_vc=6)
 

@@ -28,10 +28,11 @@ def test_cuda_reproduces_reference_golden_vectors(cuda_lib, oracle_lib):
     assert sc.decisions == so.decisions
 
 
-@pytest.mark.parametrize("name", ["C1", "C2", "C3-small", "multi-member", "heterogeneous", "suggested-nodes"])
+@pytest.mark.parametrize("name", ["C1", "C2", "C3-small", "multi-member", "heterogeneous", "suggested-nodes", "bad-requests"])
 def test_cuda_matches_oracle_on_trace(cuda_lib, oracle_lib, name):
     t = {"C1": trace.trace_c1, "C2": trace.trace_c2, "C3-small": small_c3, "multi-member": trace.trace_multi_member,
-         "heterogeneous": trace.trace_heterogeneous, "suggested-nodes": trace.trace_suggested_nodes}[name]()
+         "heterogeneous": trace.trace_heterogeneous, "suggested-nodes": trace.trace_suggested_nodes,
+         "bad-requests": trace.trace_bad_requests}[name]()
     snaps = []
     hc, rc, sc = run_trace(cuda_lib, t, chunks=2, snapshots=snaps)
     ho, ro, so = run_trace(oracle_lib, t, chunks=2, snapshots=snaps)
