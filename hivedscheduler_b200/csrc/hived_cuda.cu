@@ -172,6 +172,7 @@ int bk_run_small(Engine& e, const hived_event_t* events, int n, const uint32_t* 
   e.dPool.ensure((size_t)(poolCap > 0 ? poolCap : 1) * 4);
   if (hasSugg) e.dSugg.ensure((size_t)suggWords * 4);
   if (hasAux) e.dAux.ensure((size_t)auxWords * 4);
+  if (e.buffersFailed()) { e.err = "out of device memory while staging the call"; return HIVED_ERR_CAPACITY; }
   e.hasSugg = hasSugg; e.hasAux = hasAux;
   e.poolCapWords = poolCap; e.stagedN = n; e.stagedEvents = events; e.canonicalDone = false;
   char* h = stage.host;

@@ -48,8 +48,10 @@ struct Buf {
     if (p) bk_free(p);
     size_t cap = need + need / 2 + 256;
     p = bk_alloc(cap);
-    bytes = cap;
+    bytes = p ? cap : 0;
+    if (!p) failed = true;
   }
+  bool failed = false;  // an allocation failed: the owner reports HIVED_ERR_CAPACITY instead of launching
   ~Buf() { if (p) bk_free(p); }
 };
 
@@ -96,13 +98,16 @@ struct Engine {
     if (count == 0) count = 1;
     std::vector<TT> h(count, init);
     TT* p = (TT*)bk_alloc(count * sizeof(TT));
+    if (!p) { allocFailed = true; return nullptr; }
     bk_h2d(p, h.data(), count * sizeof(TT));
     allocs.push_back(p);
     return p;
   }
+  bool allocFailed = false;  // some device allocation of create() failed (reported as HIVED_ERR_CAPACITY)
   const int32_t* uploadStatic(const std::vector<int32_t>& v) {
     size_t count = v.empty() ? 1 : v.size();
     int32_t* p = (int32_t*)bk_alloc(count * sizeof(int32_t));
+    if (!p) { allocFailed = true; return nullptr; }
     if (!v.empty()) bk_h2d(p, v.data(), v.size() * sizeof(int32_t));
     allocs.push_back(p);
     return p;
@@ -201,6 +206,11 @@ struct Engine {
     dResults.ensure(sizeof(hived_result_t));
     dEvents.ensure(sizeof(hived_event_t));
     poolOff = 0;
+    if (allocFailed || buffersFailed()) {
+      err = "out of device memory while creating the context (see hived_options_t: the group tables grow with "
+            "max_groups * max_group_leaves)";
+      return HIVED_ERR_CAPACITY;
+    }
     rc = launchProgram(*this, 0, true);
     if (rc) { if (err.empty()) err = "device initialisation failed"; return rc; }
     return 0;
@@ -324,6 +334,7 @@ struct Engine {
     if (hasAux) { dAux.ensure((size_t)auxWords * 4); bk_h2d(dAux.p, aux, (size_t)auxWords * 4); }
     poolOff = 0;
     canonicalDone = false;
+    if (buffersFailed()) { err = "out of device memory while staging the batch"; return HIVED_ERR_CAPACITY; }
     int rc = launchProgram(*this, n, false);
     if (rc) return rc;
     trackHealth(events, n);
@@ -340,6 +351,10 @@ struct Engine {
       }
       if (ev.type == Core::EV_ADD_ALLOCATED) everRecovered = true;
     }
+  }
+  bool buffersFailed() const {
+    return dEvents.failed || dResults.failed || dPool.failed || dSugg.failed || dAux.failed || dInit.failed || dScalars.failed ||
+           dOwn.failed || dPool2.failed || dScan.failed;
   }
   bool hasSugg = false, hasAux = false;
   int64_t poolCapWords = 0;
