@@ -118,7 +118,7 @@ struct Core {
   // highest physical level an event of this VC may write: in multi-CTA mode the cells above the
   // physical cell bound to the virtual leaf's preassigned cell are shared between VCs; their
   // priority/state (never read by a decision) are re-derived after the batch (repairSharedAncestors)
-  HIVED_DEV int ceilOf(int vLeaf) const { return (multi && vLeaf >= 0) ? d.v_level[d.v_pre[vLeaf]] : AS; }
+  HIVED_DEV int ceilOf(int vLeaf) const { return (multi && vLeaf >= 0) ? d.v_prelevel[vLeaf] : AS; }
 
   // ======================================================================================
   // warp-level building blocks (leader warp; with HIVED_WARPSZ == 1 they degenerate to loops)
@@ -2279,7 +2279,7 @@ struct Core {
           pool[base + 3 * k] = HIVED_NIL_CELL; pool[base + 3 * k + 1] = HIVED_NIL_CELL; pool[base + 3 * k + 2] = HIVED_NIL_CELL;
         } else {
           int t = -1;
-          if (hasVirtual) { int vl = virt[k]; t = d.chain_lvl_type[cl(d.v_chain[vl], d.v_level[d.v_pre[vl]])]; }
+          if (hasVirtual) t = d.v_pretype[virt[k]];  // type of the virtual leaf's preassigned cell (static per cell)
           pool[base + 3 * k] = d.p_node[pl];
           pool[base + 3 * k + 1] = d.p_leafidx[pl];
           pool[base + 3 * k + 2] = t;
@@ -2447,7 +2447,7 @@ struct Core {
         int L = b.physIds[i];
         int preLevel = -1;
         if (b.virtIds) {  // cell types are distinct along a chain: the type emitted for this leaf names exactly this level
-          preLevel = d.v_level[d.v_pre[b.virtIds[i]]];
+          preLevel = d.v_prelevel[b.virtIds[i]];
         } else {
           int t = b.leaves[3 * i + 2];
           if (t != -1) for (int l = 1; l <= top; l++) if (d.chain_lvl_type[cl(chain, l)] == t) preLevel = l;
@@ -2528,7 +2528,7 @@ struct Core {
       if (i < nl) {
         int L = b.physIds[i];
         int V = d.p_vcell[L];
-        const int ceil = multi ? d.v_level[d.v_pre[V]] : AS;
+        const int ceil = multi ? d.v_prelevel[V] : AS;
         for (int lb = 1; lb < AS; lb += 4) {  // all loads of four levels, then their stores
           int pa[4], va[4], vq[4], pq[4], bd[4];
 #pragma unroll

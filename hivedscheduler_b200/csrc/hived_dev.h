@@ -33,7 +33,7 @@ struct GroupMemFld {  // indexed by g * 8 + m like the flat arrays it replaces
   X(p_parent) X(p_child0) X(p_nchild) X(p_level) X(p_chain) X(p_leaf0) X(p_nleaf) X(p_node)           \
   X(p_leafidx) X(p_flags) X(p_nodes_off) X(p_nodes_cnt) X(nodes_flat) X(p_anc) X(v_anc)                                \
   X(v_parent) X(v_child0) X(v_nchild) X(v_level) X(v_chain) X(v_leaf0) X(v_nleaf) X(v_vc) X(v_pre)    \
-  X(v_vset) X(v_flags)                                                                                 \
+  X(v_vset) X(v_flags) X(v_pretype) X(v_prelevel)                                                      \
   X(chain_top) X(chain_leaftype) X(chain_lvl_type) X(chain_lvl_leafnum) X(chain_lvl_nchild)           \
   X(p_lvl_base) X(p_lvl_cnt) X(chain_in_vc) X(lt_off) X(lt_cnt) X(lt_chains)                           \
   X(vs_vc) X(vs_chain) X(vs_pinned) X(vs_top) X(v_lvl_base) X(v_lvl_cnt) X(vc_chain_vset)             \

@@ -45,6 +45,7 @@ struct FlatTopo {
   bool uniqueLeafIdx = true;  // no two leaf cells of one (node, chain) share a leaf index
   // ---- virtual cells [NV]
   std::vector<int32_t> v_parent, v_child0, v_nchild, v_level, v_chain, v_leaf0, v_nleaf, v_vc, v_pre, v_vset, v_flags;
+  std::vector<int32_t> v_pretype, v_prelevel;  // level of a virtual cell's preassigned (top) cell and that level's cell type id
 
   // ---- per chain
   std::vector<int32_t> chain_top, chain_leaftype;         // [nChains]
@@ -407,6 +408,14 @@ inline FlatTopo buildTopo(const std::string& text) {
       if (nit == el.end()) break;
       nm = ce->child; ce = &nit->second;
     }
+  }
+  // PreassignedCellTypes of a virtual cell (utils.go:150-153): level of its preassigned cell and that level's type
+  T.v_prelevel.assign(std::max(1, T.NV), 0); T.v_pretype.assign(std::max(1, T.NV), -1);
+  for (int32_t i = 0; i < T.NV; i++) {
+    int32_t pre = T.v_pre[i];
+    if (pre < 0) continue;
+    T.v_prelevel[i] = T.v_level[pre];
+    T.v_pretype[i] = T.chain_lvl_type[(size_t)T.v_chain[i] * MAXL + T.v_level[pre]];
   }
   // ancestor tables: anc[cell * AS + l] = the ancestor of `cell` at level l (the cell itself at its own
   // level, -1 below it or above its tree's top) — turns every leaf-to-root walk into independent loads
