@@ -5,7 +5,10 @@ tests/golden/trace_hashes.json.  The full C3 trace takes the oracle ~20-30 minut
 parity test at BASELINE size compares against these committed checkpoints instead of re-running it.
 
     python tests/golden/make_trace_hashes.py C3 [n_chunks]
+    python tests/golden/make_trace_hashes.py C5 [n_chunks]      (full-size churn trace, ~10 min of oracle time)
+    python tests/golden/make_trace_hashes.py C4 [n_gangs]       (call-by-call preemption harness, ~1 h at 100 000 gangs)
 """
+import hashlib
 import json
 import os
 import sys
@@ -18,11 +21,37 @@ from hivedscheduler_b200 import _cabi, trace  # noqa: E402
 OUT = os.path.join(ROOT, "tests", "golden", "trace_hashes.json")
 
 
+def log_digest(log) -> str:
+    """sha256 over the decision log of the interactive harness (gang, pod, kind, node / victims / wait code)."""
+    m = hashlib.sha256()
+    for entry in log:
+        m.update(repr(entry).encode())
+    return m.hexdigest()
+
+
+def c4_kwargs(n_gangs: int):
+    from hivedscheduler_b200.config import config_c3
+    return dict(config=config_c3(), n_gangs=n_gangs, n_vcs=8, vc_gpus=7168, total_gpus=65536)
+
+
+def main_c4(lib, n_gangs: int):
+    t0 = time.time()
+    h, log, stats = trace.run_c4_interactive(lib, **c4_kwargs(n_gangs))
+    data = json.load(open(OUT)) if os.path.exists(OUT) else {}
+    from collections import Counter
+    data["C4"] = {"n_gangs": n_gangs, "hash": "%016x" % h, "log_sha256": log_digest(log), "log_entries": len(log),
+                  "kinds": dict(Counter(e[2] for e in log)), "stats": stats, "oracle_seconds": time.time() - t0}
+    json.dump(data, open(OUT, "w"), indent=1, sort_keys=True)
+    print("C4", data["C4"], flush=True)
+
+
 def main():
     name = sys.argv[1] if len(sys.argv) > 1 else "C3"
     n_chunks = int(sys.argv[2]) if len(sys.argv) > 2 else 20
     lib = _cabi.load_library(os.path.join(ROOT, "oracle", "libhived_oracle.so"))
-    t = {"C2": trace.trace_c2, "C3": trace.trace_c3}[name]()
+    if name == "C4":
+        return main_c4(lib, int(sys.argv[2]) if len(sys.argv) > 2 else 100000)
+    t = {"C2": trace.trace_c2, "C3": trace.trace_c3, "C5": trace.trace_c5}[name]()
     ev = t["events"]
     bc = trace.BatchContext(lib, t["config"], t["n_groups"], t["n_pods"], t["max_group_leaves"], t["max_group_pods"])
     bc.set_all_nodes_healthy()

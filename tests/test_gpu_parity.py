@@ -177,3 +177,42 @@ def test_cuda_matches_oracle_with_lazy_preemption(cuda_lib, oracle_lib):
     assert lc == lo
     assert hc == ho and sc == so
     assert so["lazy_preempted_groups"] > 0
+
+
+def test_cuda_full_size_c5_against_oracle_checkpoints(cuda_lib):
+    """BASELINE config 5 at full size (64k GPUs, 10 % of the nodes flipping per step, 20 000 gangs): the oracle's parity
+    hash after every tenth of the trace and its work counters are committed (tests/golden/make_trace_hashes.py C5)."""
+    t = trace.trace_c5()
+    golden = json.load(open(os.path.join(HERE, "golden", "trace_hashes.json")))["C5"]
+    assert golden["n_events"] == len(t["events"])
+    bc = trace.BatchContext(cuda_lib, t["config"], t["n_groups"], t["n_pods"], t["max_group_leaves"], t["max_group_pods"])
+    bc.set_all_nodes_healthy()
+    start = 0
+    for cp in golden["checkpoints"]:
+        chunk = t["events"][start:cp["events"]]
+        res, pool = bc.process(chunk, 3 * 64 * len(chunk) + 4096)
+        sched = chunk["type"] == _cabi.EV_SCHEDULE
+        assert "%016x" % bc.result_hash() == cp["hash"], "diverged from the oracle before event %d" % cp["events"]
+        assert int((res["kind"][sched] == 1).sum()) == cp["binds"] and int((res["kind"][sched] == 0).sum()) == cp["waits"]
+        start = cp["events"]
+    assert bc.stats() == golden["stats"]
+    bc.close()
+
+
+def test_cuda_full_size_c4_against_oracle(cuda_lib):
+    """BASELINE config 4 at full size (64k GPUs, 50 000 guaranteed + 50 000 opportunistic gangs with preemption), played
+    call by call like kube-scheduler would: final parity hash, sha256 of the decision log and the work counters of the
+    oracle's run are committed (tests/golden/make_trace_hashes.py C4, about an hour of oracle time)."""
+    golden = json.load(open(os.path.join(HERE, "golden", "trace_hashes.json"))).get("C4")
+    if golden is None:
+        pytest.skip("tests/golden/trace_hashes.json has no C4 entry")
+    sys_path = os.path.join(HERE, "golden")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_trace_hashes", os.path.join(sys_path, "make_trace_hashes.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    h, log, stats = trace.run_c4_interactive(cuda_lib, **gen.c4_kwargs(golden["n_gangs"]))
+    assert len(log) == golden["log_entries"]
+    assert gen.log_digest(log) == golden["log_sha256"]
+    assert "%016x" % h == golden["hash"]
+    assert stats == golden["stats"]
