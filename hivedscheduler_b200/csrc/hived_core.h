@@ -2394,23 +2394,8 @@ struct Core {
                              // level names the PreassignedCellTypes entry without reading the emitted triples back)
   };
 
-  // utils.go:291-304
-  HIVED_DEV int getAllocatedPodIndex(const BindView& b, int leafNum) const {
-    int k = 0;
-    for (int m = 0; m < b.n_members; m++) {
-      int ln = b.member_leaf_num[m], pn = b.member_pod_num[m];
-      if (ln == leafNum) {
-        for (int pi = 0; pi < pn; pi++) {
-          if (b.leaves[3 * (k + pi * ln)] == b.node) {
-            const int32_t* row = b.leaves + 3 * (k + pi * ln);
-            if (firstIdx(ln, [&](int j) { return row[3 * j + 1] == b.first_leaf; }) >= 0) return pi;
-          }
-        }
-      }
-      k += ln * pn;
-    }
-    return -1;
-  }
+  // (getAllocatedPodIndex, utils.go:291-304, runs in the shim for recovered pods — algorithm.py — and is the identity on
+  // a PodBindInfo that Schedule has just produced, see processEvent)
 
   // ---- whole-gang commit: the per-leaf loop of createAllocatedAffinityGroup (below) for the common case, with
   // lanes over the gang's leaves.  Preconditions (else false, nothing written): a fresh placement (cells known,
