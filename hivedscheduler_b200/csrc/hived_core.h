@@ -38,7 +38,7 @@ constexpr int MAX_FANOUT = 64;
 #endif
 
 constexpr int MAX_BINS = 4 * (MAX_NODE_LEAVES + 1);
-constexpr int MAX_WARPS = 32;
+constexpr int MAX_WARPS = 16;  // warps per CTA (hived_cuda.cu launches 512 threads)
 constexpr int FREE_PRIO = HIVED_FREE_PRIORITY;
 constexpr int OPP_PRIO = HIVED_OPPORTUNISTIC_PRIORITY;
 constexpr int PF_AT_OR_ABOVE_NODE_BIT = 1, PF_NODE_LEVEL_BIT = 2, PF_PINNED_BIT = 4;

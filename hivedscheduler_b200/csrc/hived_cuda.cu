@@ -93,8 +93,12 @@ struct CudaTimers {
   cudaStream_t stream = nullptr;
 };
 
+static_assert(NT / 32 <= MAX_WARPS, "the shared counters are sized for MAX_WARPS warps per CTA");
+
 int launchProgram(Engine& e, int n, bool withInit) {
   if (!e.stream) {
+    // the kernel wants L1, not shared memory: ask for the smallest carveout that holds its ~18 KB of static smem
+    cudaFuncSetAttribute(hived_events_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 10);
     CudaTimers* t = new CudaTimers();
     if (!cudaOk(cudaStreamCreate(&t->stream), e.err, "cudaStreamCreate")) return HIVED_ERR_NO_DEVICE;
     cudaEventCreate(&t->start);
