@@ -571,6 +571,8 @@ struct Core {
   // hived_algorithm.go:602-628 (VCs in ascending id order)
   HIVED_DEV_NOINLINE void tryBindDoomedBadCell(int chain, int l) {
     int k = cl(chain, l);
+    // no VC can be short of healthy cells while even the sum of their free cells fits (vcFree[vc] <= allVCFree)
+    if (d.allVCFree[k] <= d.totalLeft[k] - d.bf_len[k]) return;
     for (int vc = 0; vc < d.S.nVCs; vc++) {
       if (!d.vc_chain_counter[vc * d.S.nChains + chain]) continue;
       int kv = vcl(vc, chain, l);
@@ -593,6 +595,7 @@ struct Core {
   // hived_algorithm.go:630-653
   HIVED_DEV_NOINLINE void tryUnbindDoomedBadCell(int chain, int l) {
     int k = cl(chain, l);
+    if (d.allVCDoomed[k] == 0) return;  // no doomed bad cell of any VC at this level
     for (int vc = 0; vc < d.S.nVCs; vc++) {
       if (!d.vc_chain_counter[vc * d.S.nChains + chain]) continue;
       int kv = vcl(vc, chain, l);
