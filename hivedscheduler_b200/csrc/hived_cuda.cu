@@ -115,11 +115,34 @@ int launchProgram(Engine& e, int n, bool withInit) {
   cudaMemcpyAsync(e.dScalars.p, scal, sizeof scal, cudaMemcpyHostToDevice, t->stream);
   cudaEventRecord(t->start, t->stream);
   const int32_t* own = C > 1 ? (const int32_t*)e.dOwn.p : nullptr;
-  hived_events_kernel<<<C, NT, 0, t->stream>>>(
-      e.dev, (const hived_event_t*)e.dEvents.p, n, (hived_result_t*)e.dResults.p,
-      e.hasSugg ? (const uint32_t*)e.dSugg.p : nullptr, e.hasAux ? (const int32_t*)e.dAux.p : nullptr,
-      withInit ? (const int32_t*)e.dInit.p : nullptr, e.nPinnedOrder, e.nBad, (int32_t*)e.dPool.p, (long long*)e.dScalars.p, own,
-      own ? own + n : nullptr);
+  if (C > 1) {
+    // The CTAs of a VC-parallel batch wait for each other (ordered shared sections): launch them cooperatively, so
+    // that the runtime guarantees that all of them are resident at the same time.
+    Dev devArg = e.dev;
+    const hived_event_t* aEvents = (const hived_event_t*)e.dEvents.p;
+    int aN = n;
+    hived_result_t* aResults = (hived_result_t*)e.dResults.p;
+    const uint32_t* aSugg = e.hasSugg ? (const uint32_t*)e.dSugg.p : nullptr;
+    const int32_t* aAux = e.hasAux ? (const int32_t*)e.dAux.p : nullptr;
+    const int32_t* aInit = nullptr;
+    int aPinned = e.nPinnedOrder, aBad = e.nBad;
+    int32_t* aPool = (int32_t*)e.dPool.p;
+    long long* aScal = (long long*)e.dScalars.p;
+    const int32_t* aOwn = own;
+    const int32_t* aOwnOff = own + n;
+    void* args[] = {&devArg, &aEvents, &aN, &aResults, &aSugg, &aAux, &aInit, &aPinned, &aBad, &aPool, &aScal, &aOwn, &aOwnOff};
+    cudaError_t le = cudaLaunchCooperativeKernel((const void*)hived_events_kernel, dim3(C), dim3(NT), args, 0, t->stream);
+    if (le != cudaSuccess) {
+      e.err = std::string("cooperative launch of hived_events_kernel failed: ") + cudaGetErrorString(le);
+      return HIVED_ERR_PLATFORM;
+    }
+  } else {
+    hived_events_kernel<<<C, NT, 0, t->stream>>>(
+        e.dev, (const hived_event_t*)e.dEvents.p, n, (hived_result_t*)e.dResults.p,
+        e.hasSugg ? (const uint32_t*)e.dSugg.p : nullptr, e.hasAux ? (const int32_t*)e.dAux.p : nullptr,
+        withInit ? (const int32_t*)e.dInit.p : nullptr, e.nPinnedOrder, e.nBad, (int32_t*)e.dPool.p, (long long*)e.dScalars.p, own,
+        own ? own + n : nullptr);
+  }
   if (C > 1) hived_repair_kernel<<<1, NT, 0, t->stream>>>(e.dev);
   cudaEventRecord(t->stop, t->stream);
   cudaMemcpyAsync(scal, e.dScalars.p, sizeof scal, cudaMemcpyDeviceToHost, t->stream);
