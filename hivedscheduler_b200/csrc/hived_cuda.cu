@@ -71,7 +71,12 @@ void bk_flush_l2() {
   cudaDeviceSynchronize();
 }
 
-int bk_init(int device, std::string& err) {
+void bk_use_device(int device) {
+  int cur = -1;
+  if (cudaGetDevice(&cur) == cudaSuccess && cur != device) cudaSetDevice(device);
+}
+
+int bk_init(int& device, std::string& err) {
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
   if (e != cudaSuccess || count == 0) {

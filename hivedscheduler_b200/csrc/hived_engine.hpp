@@ -28,7 +28,8 @@ void bk_free(void* p);
 void bk_h2d(void* dst, const void* src, size_t bytes);
 void bk_d2h(void* dst, const void* src, size_t bytes);
 void bk_d2d(void* dst, const void* src, size_t bytes);
-int bk_init(int device, std::string& err);
+int bk_init(int& device, std::string& err);  // device: in = requested ordinal, out = the one in use
+void bk_use_device(int device);  // make `device` current for the calling thread (contexts on several GPUs in one process)
 // runs the program over n staged events; returns 0 or a HIVED_ERR_* code
 int launchProgram(Engine& e, int n, bool withInit);
 // after a VC-parallel run: rewrite the per-CTA pool slices as one pool in event order (dPool2) and patch the
@@ -120,7 +121,8 @@ struct Engine {
     if (opt.max_pods <= 0) opt.max_pods = 1 << 20;
     if (opt.max_group_leaves <= 0) opt.max_group_leaves = 64;
     if (opt.max_group_pods <= 0) opt.max_group_pods = 8;
-    int rc = bk_init(opt.device, err);
+    deviceOrdinal = opt.device;
+    int rc = bk_init(deviceOrdinal, err);
     if (rc) return rc;
     try {
       T = buildTopo(spec);
@@ -295,6 +297,7 @@ struct Engine {
   }
   // results + pool to the caller, in the canonical layout (pool slices in event order)
   int fetch(hived_result_t* res, int32_t* pool, int64_t poolCap, int64_t* used) {
+    bk_use_device(deviceOrdinal);
     int n = stagedN;
     if (launchCta == 1) {
       if (n > 0) bk_d2h(res, dResults.p, (size_t)n * sizeof(hived_result_t));
@@ -323,6 +326,7 @@ struct Engine {
   int runBatch(const hived_event_t* events, int n, const uint32_t* suggPool, int64_t suggWords, const int32_t* aux,
                int64_t auxWords, hived_result_t* res, int32_t* pool, int64_t poolCap) {
     if (n <= 0) return 0;
+    bk_use_device(deviceOrdinal);
     if (n <= SMALL_BATCH) {
       int rc = bk_run_small(*this, events, n, suggPool, suggWords, aux, auxWords, res, pool, poolCap);
       if (rc >= 0) { if (rc == 0) trackHealth(events, n); return rc; }
@@ -356,14 +360,17 @@ struct Engine {
     return dEvents.failed || dResults.failed || dPool.failed || dSugg.failed || dAux.failed || dInit.failed || dScalars.failed ||
            dOwn.failed || dPool2.failed || dScan.failed;
   }
+  int deviceOrdinal = 0;
   bool hasSugg = false, hasAux = false;
   int64_t poolCapWords = 0;
   int stagedN = 0;
   int stage(const hived_event_t* events, int n, int64_t poolCap) {
+    bk_use_device(deviceOrdinal);
     hasSugg = false; hasAux = false;
     return prepare(events, n, poolCap);
   }
   int runStaged() {
+    bk_use_device(deviceOrdinal);
     poolOff = 0;
     canonicalDone = false;
     if (launchCta > 1) {  // the progress words were consumed by the previous run
@@ -380,6 +387,7 @@ struct Engine {
     bk_d2h(out.data(), devPtr, out.size() * 4);
   }
   void saveState() {
+    bk_use_device(deviceOrdinal);
     if (savedRegions.empty())
       for (auto& r : mutableRegions) savedRegions.push_back(bk_alloc(r.second));
     for (size_t i = 0; i < mutableRegions.size(); i++) bk_d2d(savedRegions[i], mutableRegions[i].first, mutableRegions[i].second);

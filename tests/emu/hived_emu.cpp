@@ -15,7 +15,8 @@ void bk_free(void* p) { free(p); }
 void bk_h2d(void* dst, const void* src, size_t bytes) { memcpy(dst, src, bytes); }
 void bk_d2h(void* dst, const void* src, size_t bytes) { memcpy(dst, src, bytes); }
 void bk_d2d(void* dst, const void* src, size_t bytes) { memcpy(dst, src, bytes); }
-int bk_init(int, std::string&) { return 0; }
+int bk_init(int&, std::string&) { return 0; }
+void bk_use_device(int) {}
 void bk_flush_l2() {}
 int bk_canonicalise(Engine&, int, long long*) { return HIVED_ERR_PLATFORM; }  // never reached: the emulation runs one CTA
 int bk_run_small(Engine&, const hived_event_t*, int, const uint32_t*, int64_t, const int32_t*, int64_t, hived_result_t*, int32_t*,
