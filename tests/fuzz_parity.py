@@ -28,6 +28,32 @@ def families():
     ]
 
 
+def run_seeds(lib, oracle, first: int, count: int, verbose: bool = True) -> int:
+    """Replays every family for seeds first .. first+count-1 on both libraries; returns the number of divergences."""
+    base = trace.seed_for
+    bad = 0
+    t0 = time.time()
+    try:
+        for seed in range(first, first + count):
+            trace.seed_for = lambda n, s=seed: base(n) ^ ((0x9E3779B97F4A7C15 * s) & 0xFFFFFFFFFFFFFFFF)
+            for name, gen in families():
+                t = gen()
+                snaps = []
+                ha, ra, sa = run_trace(lib, t, chunks=2, snapshots=snaps)
+                hb, rb, sb = run_trace(oracle, t, chunks=2, snapshots=snaps)
+                same = (ha == hb and sa == sb and snaps[0] == snaps[1] and
+                        all(x.tobytes() == y.tobytes() for (x, _), (y, _) in zip(ra, rb)))
+                if not same:
+                    bad += 1
+                    print("DIVERGED seed %d family %s (hash %s stats %s cells %s)" % (seed, name, ha == hb, sa == sb, snaps[0] == snaps[1]),
+                          flush=True)
+            if verbose:
+                print("seed %d done, %d divergences so far, %.0f s" % (seed, bad, time.time() - t0), flush=True)
+    finally:
+        trace.seed_for = base
+    return bad
+
+
 def main():
     which = sys.argv[1] if len(sys.argv) > 1 else "emu"
     first = int(sys.argv[2]) if len(sys.argv) > 2 else 1
@@ -43,24 +69,7 @@ def main():
         subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-o", emu_path,
                                os.path.join(HERE, "emu", "hived_emu.cpp")])
         lib = _cabi.load_library(emu_path)
-    base = trace.seed_for
-    bad = 0
-    t0 = time.time()
-    for seed in range(first, first + count):
-        trace.seed_for = lambda n, s=seed: base(n) ^ ((0x9E3779B97F4A7C15 * s) & 0xFFFFFFFFFFFFFFFF)
-        for name, gen in families():
-            t = gen()
-            snaps = []
-            ha, ra, sa = run_trace(lib, t, chunks=2, snapshots=snaps)
-            hb, rb, sb = run_trace(oracle, t, chunks=2, snapshots=snaps)
-            same = (ha == hb and sa == sb and snaps[0] == snaps[1] and
-                    all(x.tobytes() == y.tobytes() for (x, _), (y, _) in zip(ra, rb)))
-            if not same:
-                bad += 1
-                print("DIVERGED seed %d family %s (hash %s stats %s cells %s)" % (seed, name, ha == hb, sa == sb, snaps[0] == snaps[1]),
-                      flush=True)
-        print("seed %d done, %d divergences so far, %.0f s" % (seed, bad, time.time() - t0), flush=True)
-    trace.seed_for = base
+    bad = run_seeds(lib, oracle, first, count)
     print("fuzz %s vs oracle: %d seeds x %d families, %d divergences" % (which, count, len(families()), bad))
     return 1 if bad else 0
 

@@ -141,6 +141,12 @@ def test_ids_beyond_the_capacities_fail_the_call(emu_lib, oracle_lib, field, val
         bc.close()
 
 
+def test_emu_matches_oracle_on_reseeded_traces(emu_lib, oracle_lib):
+    """Two more seeds of every trace family (tests/fuzz_parity.py runs as many as one likes)."""
+    import fuzz_parity
+    assert fuzz_parity.run_seeds(emu_lib, oracle_lib, 1001, 2, verbose=False) == 0
+
+
 def small_cluster():
     return config.config_c3(n_pods=4, n_vcs=2, racks_per_vc=6)
 
