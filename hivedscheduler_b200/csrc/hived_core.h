@@ -65,7 +65,13 @@ struct Sm {
 enum { CMD_IDLE = 0, CMD_VIEW = 1, CMD_EXIT = 2 };
 
 // uniform store: every lane of the (converged) leader warp writes the same value
+#ifdef HIVED_SIMT_EMU
+// the functional emulator runs the lanes of a warp one after the other between two collectives: a uniform
+// read-modify-write is made phase-correct by finishing every lane's reads (value evaluated, barrier) before the write
+#define ST(lvalue, val) do { auto st_v_ = (val); hv_phase(); (lvalue) = st_v_; } while (0)
+#else
 #define ST(lvalue, val) ((lvalue) = (val))
+#endif
 
 struct Core {
   const Dev& d;
@@ -390,6 +396,7 @@ struct Core {
   }
   // cell.go:195-204 + utils.go:397-415.  Used propagates unconditionally: one gather over the levels.
   HIVED_DEV_NOINLINE void setCellState(int c, int s, int ceil = 1 << 20) {
+    hv_phase();
     if (s == HIVED_CELL_USED) {
       for (int b = 0; b < AS; b += HIVED_WARPSZ) {
         int l = b + lane;
@@ -425,7 +432,9 @@ struct Core {
     const int32_t* parent = V ? d.v_parent : d.p_parent;
     const int32_t* child0 = V ? d.v_child0 : d.p_child0;
     const int32_t* nchild = V ? d.v_nchild : d.p_nchild;
-    if (p > prio[c]) {
+    const bool raise = p > prio[c];
+    hv_phase();
+    if (raise) {
       for (int b = 0; b < AS; b += HIVED_WARPSZ) {
         int l = b + lane;
         if (l < AS && l <= ceil) {
@@ -457,6 +466,7 @@ struct Core {
   // (getUsablePhysicalCells :238-241); every other used[] value is recomputed from leaf priorities.
   HIVED_DEV_NOINLINE void updateUsedOpp(int c, int delta) {
     sharedEnter();  // the counts of the upper cells are read by every VC's buddy allocation
+    hv_phase();
     for (int b = 0; b < AS; b += HIVED_WARPSZ) {
       int l = b + lane;
       if (l < AS) {
@@ -843,6 +853,7 @@ struct Core {
     // bindCell: the run of unbound virtual ancestors starting at the leaf
     unsigned stopMask = leafUnbound ? levelMask(1, AS, [&](int l) { int va = d.v_anc[vLeaf * AS + l]; return va < 0 || d.v_pcell[va] >= 0; }) : 2u;
     const int stop = stopMask ? hv_ffs(stopMask) - 1 : AS;
+    hv_phase();
     for (int b = 0; b < AS; b += HIVED_WARPSZ) {
       int l = b + lane;
       if (l >= 1 && l < AS) {
@@ -1692,6 +1703,7 @@ struct Core {
     int n = mergeMembers(sp, leaf, pods);
     int nl = 0, np = 0;
     for (int m = 0; m < n; m++) { nl += leaf[m] * pods[m]; np += pods[m]; }
+    hv_phase();
     if (lane == 0) {  // the header record (hived_dev.h), one sequence point for all of it
       d.g_state[g] = state;
       d.g_vc[g] = sp.vc;

@@ -24,6 +24,7 @@ inline int hv_warp() { return 0; }
 inline int hv_nwarps() { return 1; }
 inline void hv_cta_sync() {}
 inline void hv_warp_sync() {}
+inline void hv_phase() {}
 inline unsigned hv_ballot(bool p) { return p ? 1u : 0u; }
 inline unsigned hv_match(int) { return 1u; }
 inline unsigned hv_lanemask_lt() { return 0u; }
@@ -54,6 +55,81 @@ inline int hv_reduce_min(int v) { return v; }
 inline int hv_reduce_add(int v) { return v; }
 }  // namespace hived
 #define HV_ST(ptr, val) (*(ptr) = (val))
+#elif defined(HIVED_SIMT_EMU)
+// tests/emu/simt_rt.h: the same program with the real geometry (32 lanes, several warps, several CTAs), every CUDA
+// thread a fiber on one host thread — functional checking of the warp-level code without a GPU (test only)
+#define HIVED_DEV inline
+#define HIVED_DEV_NOINLINE
+#define HIVED_WARPSZ 32
+namespace hived {
+inline int hv_lane() { return simt::lane(); }
+inline int hv_tid() { return simt::tid(); }
+inline int hv_nth() { return simt::nth(); }
+inline int hv_warp() { return simt::warp(); }
+inline int hv_nwarps() { return simt::nth() / 32; }
+inline void hv_cta_sync() { simt::cta_barrier(); }
+inline void hv_warp_sync() { simt::warp_collective(0, [](const int*, int*) {}); }
+// phase boundary: every lane has finished the reads of the phase before any lane starts the writes of the next one
+inline void hv_phase() { hv_warp_sync(); }
+inline unsigned hv_ballot(bool p) {
+  return (unsigned)simt::warp_collective(p ? 1 : 0, [](const int* v, int* r) {
+    unsigned m = 0;
+    for (int i = 0; i < 32; i++) if (v[i]) m |= 1u << i;
+    for (int i = 0; i < 32; i++) r[i] = (int)m;
+  });
+}
+inline unsigned hv_match(int x) {
+  return (unsigned)simt::warp_collective(x, [](const int* v, int* r) {
+    for (int i = 0; i < 32; i++) { unsigned m = 0; for (int j = 0; j < 32; j++) if (v[j] == v[i]) m |= 1u << j; r[i] = (int)m; }
+  });
+}
+inline unsigned hv_lanemask_lt() { return (1u << simt::lane()) - 1u; }
+inline int hv_popc(unsigned m) { return __builtin_popcount(m); }
+inline int hv_ffs(unsigned m) { return __builtin_ffs((int)m); }
+inline int hv_fns(unsigned m, int k) {
+  for (int b = 0; b < 32; b++) if ((m >> b) & 1u) { if (k == 0) return b; k--; }
+  return -1;
+}
+inline int hv_shfl(int x, int src) {
+  // every lane names its own source: deposit the values, then read the named one
+  simt::warp_collective(x, [](const int* v, int* r) { for (int i = 0; i < 32; i++) r[i] = v[i]; });
+  int got = simt::rt().cur->w->res[src & 31];
+  simt::warp_collective(0, [](const int*, int*) {});  // nobody overwrites res[] before every lane has read
+  return got;
+}
+inline int hv_shfl_up(int x, int d) {
+  return simt::warp_collective(x, [d](const int* v, int* r) { for (int i = 0; i < 32; i++) r[i] = i >= d ? v[i - d] : v[i]; });
+}
+inline int hv_shfl_xor(int x, int m) {
+  return simt::warp_collective(x, [m](const int* v, int* r) { for (int i = 0; i < 32; i++) r[i] = v[i ^ m]; });
+}
+inline int hv_atomic_min(int* a, int v) { int o = *a; if (v < o) *a = v; return o; }
+inline int hv_atomic_add(int* a, int v) { int o = *a; *a = o + v; return o; }
+inline long long hv_clock() { return 0; }
+inline int hv_ld_volatile(const int* p) { simt::yield_to_scheduler(); return *(const volatile int*)p; }
+inline void hv_st_volatile(int* p, int v) { *(volatile int*)p = v; }
+inline void hv_fence() {}
+inline void hv_atomic_add64(long long* a, long long v) { *a += v; }
+inline void hv_atomic_or64(long long* a, long long v) { *a |= v; }
+inline int hv_cta() { return simt::cta(); }
+inline void hv_prefetch(const void*) {}
+inline void hv_cp_async16(void* smem, const void* gmem) { __builtin_memcpy(smem, gmem, 16); }
+inline void hv_cp_async_wait() {}
+inline int hv_reduce_max(int x) {
+  return simt::warp_collective(x, [](const int* v, int* r) { int m = v[0]; for (int i = 1; i < 32; i++) if (v[i] > m) m = v[i]; for (int i = 0; i < 32; i++) r[i] = m; });
+}
+inline int hv_reduce_min(int x) {
+  return simt::warp_collective(x, [](const int* v, int* r) { int m = v[0]; for (int i = 1; i < 32; i++) if (v[i] < m) m = v[i]; for (int i = 0; i < 32; i++) r[i] = m; });
+}
+inline int hv_reduce_add(int x) {
+  return simt::warp_collective(x, [](const int* v, int* r) { int m = 0; for (int i = 0; i < 32; i++) m += v[i]; for (int i = 0; i < 32; i++) r[i] = m; });
+}
+}  // namespace hived
+#define HV_ST(ptr, val)                      \
+  do {                                       \
+    if (hived::hv_lane() == 0) *(ptr) = (val); \
+    hived::hv_warp_sync();                   \
+  } while (0)
 #else
 #define HIVED_DEV __device__ __forceinline__
 #define HIVED_DEV_NOINLINE __device__ __noinline__
@@ -66,6 +142,15 @@ __device__ __forceinline__ int hv_warp() { return threadIdx.x >> 5; }
 __device__ __forceinline__ int hv_nwarps() { return blockDim.x >> 5; }
 __device__ __forceinline__ void hv_cta_sync() { __syncthreads(); }
 __device__ __forceinline__ void hv_warp_sync() { __syncwarp(); }
+// phase boundary of the leader warp's uniform code (all lanes read, then one or all lanes write the same locations).
+// The warp is converged there (uniform control flow, no divergent call in between), so the hardware executes the
+// reads of all lanes before the writes; the functional emulator (tests/emu/simt_rt.h), which runs lanes one after
+// the other, makes the boundary explicit.  -DHIVED_STRICT_PHASES turns it into a real __syncwarp().
+#ifdef HIVED_STRICT_PHASES
+__device__ __forceinline__ void hv_phase() { __syncwarp(); }
+#else
+__device__ __forceinline__ void hv_phase() {}
+#endif
 __device__ __forceinline__ unsigned hv_ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
 __device__ __forceinline__ unsigned hv_match(int v) { return __match_any_sync(0xffffffffu, v); }
 __device__ __forceinline__ unsigned hv_lanemask_lt() { return (1u << (threadIdx.x & 31)) - 1u; }

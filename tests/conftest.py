@@ -81,3 +81,22 @@ def snapshot_bytes(lib, ctx):
     assert lib.hived_snapshot_physical(ctx, ps, n_p) == 0
     assert lib.hived_snapshot_virtual(ctx, vs, n_v) == 0
     return bytes(ps) + bytes(vs)
+
+
+SIMT_LIB = os.path.join(ROOT, "tests", "_build", "libhived_simt.so")
+
+
+@pytest.fixture(scope="session")
+def simt_lib():
+    """Functional SIMT emulation of the DEVICE PROGRAM with the kernel's real geometry (32-lane warps, leader + worker
+    warps, one CTA per group of VCs; tests/emu/simt_rt.h) — test-only, covers the warp-level code and the ordered
+    shared sections between CTAs on a box without a GPU."""
+    from hivedscheduler_b200 import _cabi
+    os.makedirs(os.path.dirname(SIMT_LIB), exist_ok=True)
+    src = os.path.join(ROOT, "tests", "emu", "hived_simt.cpp")
+    deps = [src, os.path.join(ROOT, "tests", "emu", "simt_rt.h")] + [
+        os.path.join(ROOT, "hivedscheduler_b200", "csrc", f)
+        for f in os.listdir(os.path.join(ROOT, "hivedscheduler_b200", "csrc")) if f.endswith((".h", ".hpp"))]
+    if not os.path.exists(SIMT_LIB) or any(os.path.getmtime(d) > os.path.getmtime(SIMT_LIB) for d in deps):
+        subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-o", SIMT_LIB, src])
+    return _cabi.load_library(SIMT_LIB)
