@@ -94,6 +94,7 @@ struct Core {
       : d(dev), sm(s_), sugg(nullptr), pool(pool_), pool_cap(cap), poolOff(0), panicCode(0), lane(hv_lane()), AS(dev.S.AS),
         s(dev.scratch[hv_cta()]), cta(hv_cta()), nCta(nCta_), multi(nCta_ > 1), curEvent(0), sharedHeld(false), prioMask(0) {
     for (int i = 0; i < N_WORK; i++) work[i] = 0;
+    for (int i = 0; i < PC_COUNT; i++) pathCnt[i] = 0;
   }
 
   // Multi-CTA ordering.  VCs are partitioned over the CTAs; an event only touches its VC's virtual
@@ -287,7 +288,9 @@ struct Core {
   // compiled in — they were 6 % of the leader warp's time.
   static constexpr int N_WORK = ST_PRIO_MASK;  // counters [0, N_WORK) are the work counters
   int work[N_WORK];
+  int pathCnt[PC_COUNT];  // which path the events took (ST_PATH0 + PC_*)
   unsigned long long prioMask;
+  HIVED_DEV void path_add(int which, int v = 1) { pathCnt[which] += v; }
 #ifdef HIVED_PROFILE
   HIVED_DEV long long pclock() const { return hv_clock(); }
   HIVED_DEV void stat_add(int which, long long v) {
@@ -303,9 +306,11 @@ struct Core {
   HIVED_DEV void flushWork() {
     if (lane == 0) {
       for (int i = 0; i < N_WORK; i++) if (work[i]) hv_atomic_add64(&d.stats[i], work[i]);
+      for (int i = 0; i < PC_COUNT; i++) if (pathCnt[i]) hv_atomic_add64(&d.stats[ST_PATH0 + i], pathCnt[i]);
       if (prioMask) hv_atomic_or64(&d.stats[ST_PRIO_MASK], (long long)prioMask);
     }
     for (int i = 0; i < N_WORK; i++) work[i] = 0;
+    for (int i = 0; i < PC_COUNT; i++) pathCnt[i] = 0;
     prioMask = 0;
     hv_warp_sync();
   }
@@ -427,6 +432,7 @@ struct Core {
   // ancestor independently, because a parent's priority is the max of its children's.
   template <bool V>
   HIVED_DEV_NOINLINE void setPriority(int c, int p, int ceil = 1 << 20) {
+    if (V) bkMarkLeaf(c);  // the key of the view node above this virtual leaf changes
     int32_t* prio = V ? d.v_prio : d.p_prio;
     const int32_t* anc = V ? d.v_anc : d.p_anc;
     const int32_t* parent = V ? d.v_parent : d.p_parent;
@@ -782,9 +788,11 @@ struct Core {
     if (healthy) {
       if (!d.node_bad[node]) return;
       ST(d.node_bad[node], 0);
+      ST(d.nbad[0], d.nbad[0] - 1);  // bad nodes in the cluster (0: the bucketed cluster views apply)
     } else {
       if (d.node_bad[node]) return;
       ST(d.node_bad[node], 1);
+      ST(d.nbad[0], d.nbad[0] + 1);
     }
     for (int chain = 0; chain < d.S.nChains; chain++) {
       int k = node * d.S.nChains + chain;
@@ -849,6 +857,7 @@ struct Core {
       return safetyOk;
     }
     stat_add(ST_LEAVES, 1);
+    bkMarkLeaf(vLeaf);
     const bool leafUnbound = d.p_vcell[pLeaf] < 0;
     // bindCell: the run of unbound virtual ancestors starting at the leaf
     unsigned stopMask = leafUnbound ? levelMask(1, AS, [&](int l) { int va = d.v_anc[vLeaf * AS + l]; return va < 0 || d.v_pcell[va] >= 0; }) : 2u;
@@ -887,6 +896,7 @@ struct Core {
       return;
     }
     stat_add(ST_LEAVES, 1);
+    bkMarkLeaf(vLeaf);
     const int pre = d.v_pre[vLeaf];
     const int preP = d.v_pcell[pre];
     int vOrig = d.v_prio[vLeaf], vNew = FREE_PRIO;
@@ -959,6 +969,268 @@ struct Core {
     }
     // hived_algorithm.go:1343-1347: the preassigned cell is released once nothing in it is in real use
     if (!(d.p_flags[preP] & PF_PINNED_BIT) && d.v_prio[pre] < 0 && !dm_contains(vc, preP)) releasePreassignedCell(preP, vc, false);
+  }
+
+  // ======================================================================================
+  // incremental (bucketed) cluster view — the fast form of updateClusterView + sort.Stable + findNodesForPods
+  // (topology_aware_scheduler.go:231-306) for an intra-VC view whose nodes are all healthy and suggested.
+  //
+  // There the sort key of a node is its number of used leaf cells u (descending; usedHigher is 0 with
+  // crossPriorityPack, intra_vc_scheduler.go:66-70) and sort.Stable keeps the previous order among equal keys.  The
+  // persisted order is therefore the concatenation of the buckets u = L, L-1, ..., 0, each an ordered list, and a
+  // sort only MOVES the nodes whose u changed since the previous sort: into bucket u' go,
+  // in this order, the nodes that dropped into it (from higher buckets; among themselves in their previous global
+  // order), the nodes that stayed, and the nodes that rose into it (from lower buckets; previous global order).
+  // Buckets are doubly linked lists with a sequence label per node (order inside a bucket = ascending label: a
+  // dropper gets a label below the head's, a riser one above the tail's), so the previous global order of two
+  // nodes is (u at the last sort descending, label ascending) without walking a list.  Greedy first-fit becomes:
+  // the head of the first non-empty bucket with L - u >= need, then its successors in the concatenated order.
+  //
+  // The general view pass (viewOp) keeps working on the order ARRAY d.cv; the two forms are converted on demand:
+  // bkMaterialise writes the buckets out to d.cv (before a general pass on that view), bkRebuild sorts d.cv into
+  // buckets (first fast call after a general pass).  Every change of a virtual leaf's priority marks the view node
+  // above it dirty (bkMarkLeaf / bkMarkLeaves), whichever path made it.
+  // ======================================================================================
+  HIVED_DEV int bkIdx(int sched, int u) const { return sched * BK_STRIDE + u; }
+  HIVED_DEV int schedOfVirtual(int vcell) const { return d.vset_sched[d.v_vset[vcell]]; }
+  // number of used (non-free) leaf cells of a view node
+  HIVED_DEV int usedLeaves(int node) const {
+    const int l0 = d.v_leaf0[node], n = d.v_nleaf[node];
+    int u = 0;
+    for (int i = 0; i < n; i++) u += d.v_prio[l0 + i] != FREE_PRIO ? 1 : 0;
+    return u;
+  }
+  // uniform code: the view node above one virtual leaf whose priority changes
+  HIVED_DEV void bkMarkLeaf(int vLeaf) {
+    const int sched = schedOfVirtual(vLeaf);
+    if (sched < 0 || !d.s_fast[sched]) return;
+    const int node = d.v_anc[vLeaf * AS + d.s_level[sched]];
+    if (node < 0 || d.vn_dirty[node]) return;
+    const int n = d.bk_ndirty[sched];
+    hv_phase();
+    ST(d.vn_dirty[node], 1);
+    ST(d.bk_dl[d.s_off[sched] + n], node);
+    ST(d.bk_ndirty[sched], n + 1);
+  }
+  // lane-parallel code: every `act` lane holds a virtual leaf whose priority changes (lanes may share view nodes)
+  HIVED_DEV void bkMarkLeaves(bool act, int vLeaf) {
+    int sched = act ? schedOfVirtual(vLeaf) : -1;
+    if (sched >= 0 && !d.s_fast[sched]) sched = -1;
+    const int node = sched >= 0 ? d.v_anc[vLeaf * AS + d.s_level[sched]] : -1;
+    const bool want = node >= 0 && !d.vn_dirty[node];
+    const unsigned grp = hv_match(want ? node : -1 - lane);
+    if (want && hv_ffs(grp) - 1 == lane) {
+      d.vn_dirty[node] = 1;
+      const int pos = hv_atomic_add(&d.bk_ndirty[sched], 1);
+      d.bk_dl[d.s_off[sched] + pos] = node;
+    }
+    hv_warp_sync();
+  }
+  // unlink / link at the front / link at the back of a bucket (uniform code)
+  HIVED_DEV void bkUnlink(int sched, int node) {
+    const int k = bkIdx(sched, d.vn_u[node]);
+    const int pv = d.vn_prev[node], nx = d.vn_next[node], cnt = d.bk_cnt[k];
+    hv_phase();
+    if (pv >= 0) ST(d.vn_next[pv], nx); else ST(d.bk_head[k], nx);
+    if (nx >= 0) ST(d.vn_prev[nx], pv); else ST(d.bk_tail[k], pv);
+    ST(d.bk_cnt[k], cnt - 1);
+  }
+  HIVED_DEV void bkPushBack(int sched, int u, int node) {
+    const int k = bkIdx(sched, u);
+    const int tail = d.bk_tail[k], seq = d.bk_tseq[k], cnt = d.bk_cnt[k];
+    hv_phase();
+    ST(d.vn_prev[node], tail); ST(d.vn_next[node], -1); ST(d.vn_seq[node], seq); ST(d.vn_u[node], u);
+    if (tail >= 0) ST(d.vn_next[tail], node); else ST(d.bk_head[k], node);
+    ST(d.bk_tail[k], node); ST(d.bk_tseq[k], seq + 1); ST(d.bk_cnt[k], cnt + 1);
+  }
+  HIVED_DEV void bkPushFront(int sched, int u, int node) {
+    const int k = bkIdx(sched, u);
+    const int head = d.bk_head[k], seq = d.bk_hseq[k], cnt = d.bk_cnt[k];
+    hv_phase();
+    ST(d.vn_next[node], head); ST(d.vn_prev[node], -1); ST(d.vn_seq[node], seq); ST(d.vn_u[node], u);
+    if (head >= 0) ST(d.vn_prev[head], node); else ST(d.bk_tail[k], node);
+    ST(d.bk_head[k], node); ST(d.bk_hseq[k], seq - 1); ST(d.bk_cnt[k], cnt + 1);
+  }
+  // buckets -> d.cv (the order array of the general pass); the buckets stop being the authority
+  HIVED_DEV_NOINLINE void bkMaterialise(int sched) {
+    if (!d.bk_valid[sched]) return;
+    const int off = d.s_off[sched], L = d.s_maxleaf[sched];
+    for (int b0 = 0; b0 <= L; b0 += HIVED_WARPSZ) {  // one lane per bucket; bucket u starts after the buckets above it
+      const int u = b0 + lane;
+      if (u <= L) {
+        int base = 0;
+        for (int q = L; q > u; q--) base += d.bk_cnt[bkIdx(sched, q)];
+        int i = 0;
+        for (int x = d.bk_head[bkIdx(sched, u)]; x >= 0; x = d.vn_next[x]) { d.cv[off + base + i] = x; i++; }
+      }
+    }
+    hv_warp_sync();
+    ST(d.bk_valid[sched], 0);
+  }
+  // d.cv (+ the current keys) -> buckets: a stable sort by used leaves, descending
+  HIVED_DEV_NOINLINE void bkRebuild(int sched) {
+    const int off = d.s_off[sched], n = d.s_n[sched], L = d.s_maxleaf[sched];
+    hv_phase();
+    for (int b0 = 0; b0 <= L; b0 += HIVED_WARPSZ) {
+      const int u = b0 + lane;
+      if (u <= L) {
+        const int k = bkIdx(sched, u);
+        d.bk_head[k] = -1; d.bk_tail[k] = -1; d.bk_cnt[k] = 0; d.bk_hseq[k] = -1; d.bk_tseq[k] = 0;
+      }
+    }
+    {  // forget the dirty marks: every key is recomputed
+      const int nd = d.bk_ndirty[sched];
+      for (int i = lane; i < nd; i += HIVED_WARPSZ) d.vn_dirty[d.bk_dl[off + i]] = 0;
+    }
+    hv_warp_sync();
+    for (int b0 = 0; b0 < n; b0 += HIVED_WARPSZ) {
+      const int i = b0 + lane;
+      const bool act = i < n;
+      const int x = act ? d.cv[off + i] : -1;
+      const int u = act ? usedLeaves(x) : -1;
+      for (unsigned todo = hv_ballot(act); todo;) {  // one step per distinct key of the chunk
+        const int uu = hv_shfl(u, hv_ffs(todo) - 1);
+        const unsigned m = hv_ballot(act && u == uu);
+        todo &= ~m;
+        const int k = bkIdx(sched, uu);
+        const int oldTail = d.bk_tail[k], seq0 = d.bk_tseq[k], cnt = d.bk_cnt[k];
+        const unsigned below = m & hv_lanemask_lt();
+        const unsigned above = (m >> lane) >> 1;
+        const int prevLane = below ? hv_hibit(below) : lane;
+        const int nextLane = above ? lane + hv_ffs(above) : lane;
+        const int px = hv_shfl(x, prevLane), nx = hv_shfl(x, nextLane);
+        hv_phase();
+        if (act && u == uu) {
+          d.vn_prev[x] = below ? px : oldTail;
+          d.vn_next[x] = above ? nx : -1;
+          d.vn_seq[x] = seq0 + hv_popc(below);
+          d.vn_u[x] = uu;
+          if (!below) { if (oldTail >= 0) d.vn_next[oldTail] = x; else d.bk_head[k] = x; }
+          if (!above) { d.bk_tail[k] = x; d.bk_tseq[k] = seq0 + hv_popc(m); d.bk_cnt[k] = cnt + hv_popc(m); }
+        }
+        hv_warp_sync();
+      }
+    }
+    ST(d.bk_ndirty[sched], 0);
+    ST(d.bk_valid[sched], 1);
+  }
+  // apply the sort to the nodes whose key changed since the last one
+  HIVED_DEV void bkSort(int sched) {
+    if (!d.bk_valid[sched]) { path_add(PC_BK_REBUILD); bkRebuild(sched); return; }
+    const int nd = d.bk_ndirty[sched];
+    if (nd == 0) return;
+    bkSortDirty(sched, nd);
+  }
+  HIVED_DEV_NOINLINE void bkSortDirty(int sched, int nd) {
+    const int off = d.s_off[sched], L = d.s_maxleaf[sched];
+    // the movers, with their keys before (u at the last sort, label) and after; scratch: vw_ordA = new u, vw_ordB = class key
+    int32_t* dl = d.bk_dl + off;
+    int movers = 0;
+    for (int b0 = 0; b0 < nd; b0 += HIVED_WARPSZ) {
+      const int i = b0 + lane;
+      bool mv = false;
+      if (i < nd) {
+        const int x = dl[i];
+        const int nu = usedLeaves(x), ou = d.vn_u[x];
+        d.vn_dirty[x] = 0;
+        mv = nu != ou;
+        s.vw_ordA[i] = nu;
+        // processing order: first the risers by (old u descending, label ascending) — appended to the back of their
+        // bucket —, then the droppers by (old u ascending, label descending) — pushed to the front, so that they end
+        // up in (old u descending, label ascending) order
+        s.vw_ordB[i] = !mv ? 0x7fffffff : (nu > ou ? (L - ou) : (BK_STRIDE + ou));
+      }
+      movers += hv_popc(hv_ballot(mv));
+    }
+    hv_warp_sync();
+    path_add(PC_BK_MOVERS, movers);
+    for (int r = 0; r < movers; r++) {
+      // the pending mover with the smallest (class key, label [ascending for risers, descending for droppers])
+      int best = 0x7fffffff;
+      for (int b0 = 0; b0 < nd; b0 += HIVED_WARPSZ) { const int i = b0 + lane; if (i < nd && s.vw_ordB[i] < best) best = s.vw_ordB[i]; }
+      best = hv_reduce_min(best);
+      const bool riser = best < BK_STRIDE;
+      int bl = 0x7fffffff;
+      for (int b0 = 0; b0 < nd; b0 += HIVED_WARPSZ) {
+        const int i = b0 + lane;
+        if (i < nd && s.vw_ordB[i] == best) { const int q = d.vn_seq[dl[i]]; const int key = riser ? q : ~q; if (key < bl) bl = key; }
+      }
+      bl = hv_reduce_min(bl);
+      const int wantSeq = riser ? bl : ~bl;
+      const int idx = firstIdx(nd, [&](int i) { return s.vw_ordB[i] == best && d.vn_seq[dl[i]] == wantSeq; });
+      const int x = dl[idx], nu = s.vw_ordA[idx];
+      hv_phase();
+      ST(s.vw_ordB[idx], 0x7fffffff);
+      bkUnlink(sched, x);
+      if (riser) bkPushBack(sched, nu, x); else bkPushFront(sched, nu, x);
+    }
+    ST(d.bk_ndirty[sched], 0);
+  }
+
+  // fast form of pass 1 of topologyAwareScheduler.Schedule (topology_aware_scheduler.go:65-116) for a gang of m pods
+  // with k leaf cells each in an all-healthy intra-VC view: sort, greedy first-fit, intra-node leaf search.
+  // 1: placed (outLeaves = virtual leaf cells in (pod, leaf) order, s.pod_cell = view node per pod);
+  // 0: no capacity without preemption — the general code takes over (its sorts start from the order persisted here).
+  HIVED_DEV bool fastEligible(int sched, int nmem, bool ignoreSuggested) const {
+    return d.s_fast[sched] != 0 && nmem == 1 && (sugg == nullptr || ignoreSuggested) && d.nbad[0] == 0;
+  }
+  HIVED_DEV int fastPlace(int sched, int k, int m, int32_t* outLeaves) {
+    const int L = d.s_maxleaf[sched], chain = d.s_chain[sched], viewLevel = d.s_level[sched];
+    if (k > L || k <= 0 || m > d.S.PS) return 0;
+    const int optimal = optimalAffinity(chain, k);
+    if (optimal < 0) return 0;
+    bkSort(sched);
+    // findNodesForPods (:268-306): nodes in sorted order = buckets L .. 0, free leaves of a node = L - u
+    int u = L - k;
+    for (; u >= 0; u--) if (d.bk_head[bkIdx(sched, u)] >= 0) break;
+    if (u < 0) return 0;
+    int node = d.bk_head[bkIdx(sched, u)];
+    int picked = 0;
+    for (int j = 0; j < m; j++) {
+      if ((L - u) - picked < k) {  // next node in the concatenated order (every later node has at least as many free leaves)
+        int nx = d.vn_next[node];
+        while (nx < 0) { u--; if (u < 0) return 0; nx = d.bk_head[bkIdx(sched, u)]; }
+        node = nx;
+        picked = 0;
+      }
+      picked += k;
+      ST(s.pod_cell[j], node);
+    }
+    // findLeafCellsInNode (:308-387) among the free leaves of the node: the first k free leaves of the first cell of
+    // the lowest level >= the optimal one that holds k of them (the lexicographically first subset of minimal LCA level)
+    int outOff = 0, prevNode = -1;
+    unsigned taken = 0;
+    for (int j = 0; j < m; j++) {
+      const int nd = s.pod_cell[j];
+      if (nd != prevNode) { taken = 0; prevNode = nd; }
+      const int l0 = d.v_leaf0[nd];
+      unsigned freeMask = 0;
+      for (int b0 = 0; b0 < L; b0 += HIVED_WARPSZ) {
+        const int i = b0 + lane;
+        freeMask |= hv_ballot(i < L && d.v_prio[l0 + i] == FREE_PRIO) << b0;
+      }
+      freeMask &= ~taken;
+      unsigned pick = 0;
+      for (int l = optimal; l <= viewLevel && !pick; l++) {
+        const int sl = l == viewLevel ? L : d.chain_lvl_leafnum[cl(chain, l)];
+        for (int g0 = 0; g0 < L && !pick; g0 += sl) {
+          const unsigned gm = (sl >= 32 ? 0xffffffffu : ((1u << sl) - 1u)) << g0;
+          if (hv_popc(freeMask & gm) >= k) {
+            unsigned c = freeMask & gm;
+            for (int q = 0; q < k; q++) { const unsigned low = c & (0u - c); pick |= low; c ^= low; }
+          }
+        }
+      }
+      if (!pick) { panic(HIVED_ERR_PLATFORM); return 0; }  // the node was chosen because it has k free leaves
+      taken |= pick;
+      for (int b0 = 0; b0 < L; b0 += HIVED_WARPSZ) {
+        const int i = b0 + lane;
+        if (i < L && ((pick >> i) & 1u)) outLeaves[outOff + hv_popc(pick & ((1u << i) - 1u))] = l0 + i;
+      }
+      hv_warp_sync();
+      outOff += k;
+    }
+    return 1;
   }
 
   // ======================================================================================
@@ -1142,6 +1414,8 @@ struct Core {
 
   // leader: post the view pass to the CTA and take part in it
   HIVED_DEV bool runViewPass(int sched, int p, bool ignoreSuggested, int npods, int& reason, int& rcell) {
+    if (d.bk_valid[sched]) bkMaterialise(sched);  // the general pass sorts the order array
+    path_add(PC_GENERAL_VIEW);
     ST(sm->a_sched, sched);
     ST(sm->a_prio, p);
     ST(sm->a_ignore, ignoreSuggested ? 1 : 0);
@@ -1287,6 +1561,18 @@ struct Core {
       for (int i = 0; i < memPods[m]; i++) { ST(s.pod_need[npods], memLeaf[m]); npods++; }
     int priority = OPP_PRIO;
     long long tc0 = pclock();
+    if (fastEligible(sched, nmem, ignoreSuggested)) {
+      const int fp = fastPlace(sched, memLeaf[0], memPods[0], outLeaves);
+      if (panicCode) return false;
+      if (fp == 1) {
+        path_add(PC_FAST_VIEW);
+        stat_add(ST_VIEW_NODES, d.s_n[sched]);
+        stat_add(ST_PODS, npods);
+        stat_add(ST_CYC_VIEW, pclock() - tc0);
+        reason = 0; rcell = -1;
+        return true;
+      }
+    }
     bool ok = runViewPass(sched, priority, ignoreSuggested, npods, reason, rcell);
     if (!ok && p > OPP_PRIO) {
       priority = p;
@@ -1806,6 +2092,7 @@ struct Core {
     // level 1: the leaves themselves (releaseLeafCell :1319-1352 + setCellState Free)
     for (int b0 = 0; b0 < nl; b0 += HIVED_WARPSZ) {
       int i = b0 + lane;
+      bkMarkLeaves(i < nl, i < nl ? s.pl_v[i] : 0);
       if (i < nl) {
         int L = ph[i], V = s.pl_v[i];
         d.p_using[L] = -1;
@@ -2525,6 +2812,7 @@ struct Core {
     int32_t* vi = gvirt(g);
     for (int b0 = 0; b0 < nl; b0 += HIVED_WARPSZ) {
       int i = b0 + lane;
+      bkMarkLeaves(i < nl, i < nl ? d.p_vcell[b.physIds[i]] : 0);
       if (i < nl) {
         int L = b.physIds[i];
         int V = d.p_vcell[L];

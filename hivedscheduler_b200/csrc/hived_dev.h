@@ -17,6 +17,7 @@ namespace hived {
 // a while: one L2 round trip instead of eight).  Word layout: 0 state, 1 vc, 2 priority, 3 flags,
 // 4 #members, 5 #preempting pods, 8..15 member leaf numbers, 16..23 member pod numbers.
 constexpr int GROUP_HDR_WORDS = 32;
+constexpr int BK_STRIDE = 33;  // buckets of a bucketed cluster view: used-leaf counts 0..32
 template <int OFF>
 struct GroupFld {
   int32_t* b;
@@ -38,7 +39,7 @@ struct GroupMemFld {  // indexed by g * 8 + m like the flat arrays it replaces
   X(p_lvl_base) X(p_lvl_cnt) X(chain_in_vc) X(lt_off) X(lt_cnt) X(lt_chains)                           \
   X(vs_vc) X(vs_chain) X(vs_pinned) X(vs_top) X(v_lvl_base) X(v_lvl_cnt) X(vc_chain_vset)             \
   X(vc_pinned_vset) X(pre_off) X(pre_cnt) X(pre_list) X(vc_chain_counter) X(pin_pcell) X(pin_vcell)   \
-  X(pin_vc) X(s_off) X(s_n) X(s_cross) X(s_chain) X(s_virtual) X(s_maxleaf) X(vset_sched) X(opp_sched) \
+  X(pin_vc) X(s_off) X(s_n) X(s_cross) X(s_chain) X(s_virtual) X(s_maxleaf) X(s_level) X(s_vc) X(s_fast) X(vset_sched) X(opp_sched) \
   X(ncl_off) X(ncl_cnt) X(ncl_list) X(fl_base) X(fl_cap) X(dm_base) X(dm_cap)
 
 // Y(name, count, init): mutable int32 array of `count` elements filled with `init`
@@ -57,7 +58,13 @@ struct GroupMemFld {  // indexed by g * 8 + m like the flat arrays it replaces
   Y(g_phys, (int64_t)S.maxGroups * S.LS, -1) Y(g_virt, (int64_t)S.maxGroups * S.LS, -1)                \
   Y(g_pods, (int64_t)S.maxGroups * S.PS, -1)                                                           \
   Y(g_pre, (int64_t)S.maxGroups * S.PS, -1) Y(pod_node, S.maxPods, -1) \
-  Y(vx_of, S.NV, -1) Y(vx_stamp, S.NV, 0) Y(binding, S.NV, -1)
+  Y(vx_of, S.NV, -1) Y(vx_stamp, S.NV, 0) Y(binding, S.NV, -1)                                         \
+  /* bucketed cluster views (hived_core.h, "incremental cluster view") */                              \
+  Y(bk_valid, S.nScheds, 0) Y(bk_ndirty, S.nScheds, 0) Y(bk_head, S.nScheds * BK_STRIDE, -1)           \
+  Y(bk_tail, S.nScheds * BK_STRIDE, -1) Y(bk_cnt, S.nScheds * BK_STRIDE, 0)                            \
+  Y(bk_hseq, S.nScheds * BK_STRIDE, -1) Y(bk_tseq, S.nScheds * BK_STRIDE, 0)                           \
+  Y(vn_next, S.NV, -1) Y(vn_prev, S.NV, -1) Y(vn_seq, S.NV, 0) Y(vn_u, S.NV, 0) Y(vn_dirty, S.NV, 0)   \
+  Y(bk_dl, S.cvTotal, -1) Y(nbad, 4, 0)
 
 // Z(name, count): scratch of one scheduling decision — one private copy per CTA (struct Scratch)
 #define HIVED_SCRATCH_ARRAYS(Z)                                                                        \
@@ -110,7 +117,11 @@ enum {
   ST_CYC_SCHED_EXISTING = 18, ST_N_SCHED_EXISTING = 19, ST_CYC_DELETE_POD = 20, ST_N_DELETE_POD = 21,
   ST_CYC_COMMIT_POD = 22, ST_N_COMMIT_POD = 23,
   ST_DBG0 = 24 /* 16 scratch cycle counters for profiling sessions (hived_bench_debug_cycles) */,
-  ST_COUNT = 40
+  /* which path the events took (always counted; hived_bench_path_counters) */
+  ST_PATH0 = 40, PC_FAST_VIEW = 0 /* scheduling passes answered by the bucketed view */, PC_GENERAL_VIEW = 1 /* full view passes */,
+  PC_BK_REBUILD = 2, PC_BK_MOVERS = 3, PC_FAST_COMMIT = 4, PC_GENERAL_COMMIT = 5, PC_FAST_DELETE = 6, PC_GENERAL_DELETE = 7,
+  PC_FAST_MAP = 8, PC_GENERAL_MAP = 9, PC_COUNT = 12,
+  ST_COUNT = 40 + PC_COUNT
 };
 
 constexpr int MAX_CTAS = 32;

@@ -708,6 +708,13 @@ int hived_bench_debug_cycles(hived_ctx* ctx, int64_t* out) {
   for (int i = 0; i < 16; i++) out[i] = st[hived::ST_DBG0 + i];
   return 0;
 }
+/* out[0..PC_COUNT): how many scheduling passes / commits / deletes took the fast and the general paths (hived_dev.h PC_*) */
+int hived_bench_path_counters(hived_ctx* ctx, int64_t* out) {
+  long long st[hived::ST_COUNT];
+  hived::bk_d2h(st, ctx->e.dev.stats, sizeof st);
+  for (int i = 0; i < hived::PC_COUNT; i++) out[i] = st[hived::ST_PATH0 + i];
+  return hived::PC_COUNT;
+}
 double hived_bench_last_kernel_ms(hived_ctx* ctx) { return ctx->e.lastKernelMs; }
 double hived_bench_total_kernel_ms(hived_ctx* ctx) { return ctx->e.kernelMsTotal; }
 int64_t hived_bench_kernel_launches(hived_ctx* ctx) { return ctx->e.kernelLaunches; }

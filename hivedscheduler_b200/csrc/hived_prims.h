@@ -30,6 +30,7 @@ inline unsigned hv_match(int) { return 1u; }
 inline unsigned hv_lanemask_lt() { return 0u; }
 inline int hv_popc(unsigned m) { return __builtin_popcount(m); }
 inline int hv_ffs(unsigned m) { return __builtin_ffs((int)m); }
+inline int hv_hibit(unsigned m) { return m ? 31 - __builtin_clz(m) : -1; }  // index of the highest set bit
 inline int hv_fns(unsigned m, int k) {  // position of the (k+1)-th set bit, -1 if there is none
   for (int b = 0; b < 32; b++) if ((m >> b) & 1u) { if (k == 0) return b; k--; }
   return -1;
@@ -86,6 +87,7 @@ inline unsigned hv_match(int x) {
 inline unsigned hv_lanemask_lt() { return (1u << simt::lane()) - 1u; }
 inline int hv_popc(unsigned m) { return __builtin_popcount(m); }
 inline int hv_ffs(unsigned m) { return __builtin_ffs((int)m); }
+inline int hv_hibit(unsigned m) { return m ? 31 - __builtin_clz(m) : -1; }
 inline int hv_fns(unsigned m, int k) {
   for (int b = 0; b < 32; b++) if ((m >> b) & 1u) { if (k == 0) return b; k--; }
   return -1;
@@ -156,6 +158,7 @@ __device__ __forceinline__ unsigned hv_match(int v) { return __match_any_sync(0x
 __device__ __forceinline__ unsigned hv_lanemask_lt() { return (1u << (threadIdx.x & 31)) - 1u; }
 __device__ __forceinline__ int hv_popc(unsigned m) { return __popc(m); }
 __device__ __forceinline__ int hv_ffs(unsigned m) { return __ffs((int)m); }
+__device__ __forceinline__ int hv_hibit(unsigned m) { return 31 - __clz((int)m); }  // index of the highest set bit, -1 if none
 __device__ __forceinline__ int hv_fns(unsigned m, int k) { return (int)__fns(m, 0, k + 1); }  // (k+1)-th set bit, -1 if none
 __device__ __forceinline__ int hv_shfl(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 __device__ __forceinline__ int hv_shfl_up(int v, int delta) { return __shfl_up_sync(0xffffffffu, v, delta); }

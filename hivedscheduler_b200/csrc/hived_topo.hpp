@@ -64,6 +64,10 @@ struct FlatTopo {
   std::vector<int32_t> pin_pcell, pin_vcell, pin_vc;        // [nPinned]
   // ---- schedulers (cluster views)
   std::vector<int32_t> s_off, s_n, s_cross, s_chain, s_virtual, s_maxleaf;  // [nScheds]
+  // bucketed (incremental) cluster views: s_level = level of the view cells, s_vc = owning VC (-1: physical view),
+  // s_fast = 1 when every view cell is a virtual cell of that one level with the same number (<= 32) of leaf cells
+  // laid out uniformly (the level-l cells below a view cell are aligned runs of chain_lvl_leafnum[l] leaves)
+  std::vector<int32_t> s_level, s_vc, s_fast;
   std::vector<int32_t> cv_init;                                             // initial view order (cell ids)
   std::vector<int32_t> vset_sched, opp_sched;                               // [nVsets], [nChains]
   // ---- node -> leaves per chain (findPhysicalLeafCellInChain without the linear scan)
@@ -515,6 +519,26 @@ inline FlatTopo buildTopo(const std::string& text) {
     if (n > T.maxViewN) T.maxViewN = n;
     T.s_n.push_back(n); T.s_cross.push_back(cross ? 1 : 0); T.s_chain.push_back(chain); T.s_virtual.push_back(isVirtual ? 1 : 0);
     T.s_maxleaf.push_back(maxleaf);
+    // ---- eligibility for the bucketed view (hived_core.h: fastPlace)
+    int32_t viewLevel = -1, vc = -1;
+    bool fast = isVirtual && n > 0 && maxleaf <= 32;
+    const int32_t off = T.s_off.back();
+    for (int32_t i = 0; i < n && fast; i++) {
+      int32_t c = T.cv_init[off + i];
+      if (i == 0) { viewLevel = T.v_level[c]; vc = T.v_vc[c]; }
+      if (T.v_level[c] != viewLevel || T.v_nleaf[c] != maxleaf || T.v_vc[c] != vc) fast = false;
+      for (int32_t l = 1; l < viewLevel && fast; l++) {
+        int32_t sl = T.chain_lvl_leafnum[(size_t)chain * MAXL + l];
+        if (sl <= 0 || maxleaf % sl) { fast = false; break; }
+        for (int32_t j = 0; j < maxleaf; j++) {
+          int32_t leaf = T.v_leaf0[c] + j, first = T.v_leaf0[c] + j / sl * sl;
+          if (T.v_anc[(size_t)leaf * T.AS + l] != T.v_anc[(size_t)first * T.AS + l]) fast = false;
+          if (j % sl == 0 && j > 0 && T.v_anc[(size_t)leaf * T.AS + l] == T.v_anc[(size_t)(leaf - 1) * T.AS + l]) fast = false;
+        }
+      }
+    }
+    if (isVirtual && n > 0 && viewLevel < 0) viewLevel = T.v_level[T.cv_init[off]];
+    T.s_level.push_back(viewLevel); T.s_vc.push_back(isVirtual ? vc : -1); T.s_fast.push_back(fast ? 1 : 0);
     return sid;
   };
   T.vset_sched.assign(T.nVsets, -1);

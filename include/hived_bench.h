@@ -18,6 +18,10 @@ int hived_bench_flush_l2(hived_ctx*);       /* overwrite a buffer larger than L2
  * {Schedule of a pod of an existing gang, delete of a pod that is not the gang's last, commit of such a pod} */
 int hived_bench_phase_cycles(hived_ctx*, int64_t* out);
 int hived_bench_debug_cycles(hived_ctx*, int64_t* out); /* out[0..16): scratch cycle counters used in profiling sessions */
+/* out[0..12): events by path — [0] scheduling passes answered by the bucketed cluster view, [1] full view passes,
+   [2] bucket rebuilds, [3] nodes moved between buckets, [4]/[5] gang commits fast/general, [6]/[7] gang releases
+   fast/general, [8]/[9] virtual->physical mappings fast/general; returns the number of counters */
+int hived_bench_path_counters(hived_ctx*, int64_t* out);
 double hived_bench_last_kernel_ms(hived_ctx*);   /* CUDA-event time of the last launch, on its stream */
 double hived_bench_total_kernel_ms(hived_ctx*);
 int64_t hived_bench_kernel_launches(hived_ctx*);
