@@ -84,7 +84,8 @@ def bind_bench_hooks(lib):
         ("hived_bench_last_kernel_ms", C.c_double, [P]),
         ("hived_bench_total_kernel_ms", C.c_double, [P]), ("hived_bench_kernel_launches", C.c_int64, [P]),
         ("hived_bench_num_ctas", C.c_int, [P]), ("hived_bench_set_result_hash", C.c_int, [P, C.c_int]),
-        ("hived_bench_debug_cycles", C.c_int, [P, C.POINTER(C.c_int64)])]:
+        ("hived_bench_debug_cycles", C.c_int, [P, C.POINTER(C.c_int64)]),
+        ("hived_bench_path_counters", C.c_int, [P, C.POINTER(C.c_int64)])]:
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
@@ -231,6 +232,8 @@ def main():
     lib.hived_bench_phase_cycles(ctx, cyc)
     dbg = (C.c_int64 * 16)()
     lib.hived_bench_debug_cycles(ctx, dbg)
+    pathc = (C.c_int64 * 16)()
+    n_pathc = lib.hived_bench_path_counters(ctx, pathc)
     # the restore + L2 flush between steps are not part of a step: time = sum of the kernels' CUDA-event times
     kernel_total_s = sum(kernel_ms) / 1e3
     # ---- e2e leg
@@ -306,6 +309,9 @@ def main():
             line["cpu_baseline"] = {"value": v, "unit": "decisions/s", "cores": 1, "kind": "port",
                                     "sample": "first 1500 decisions (%d events) of the same C3 trace, %.1f s" % (nev, dt)}
         line["parity"] = {"result_hash": "%016x" % parity_hash}
+        pc_names = ["view_bucketed", "view_full_pass", "bucket_rebuilds", "bucket_moves", "commit_lean", "commit_general",
+                    "release_lean", "release_general", "map_lean", "map_general", "pod_of_gang_lean", "delete_pod_lean"]
+        line["paths_per_step"] = {n: int(pathc[i]) for i, n in enumerate(pc_names[:n_pathc])}
         names = ["view_pass", "leaf_search", "map_v2p", "emit_result", "commit", "delete", "all_events", "shared_wait", "shared_sections",
                  "schedule_pod_of_existing_gang", "n_schedule_pod_of_existing_gang", "delete_not_last_pod", "n_delete_not_last_pod",
                  "commit_pod_of_existing_gang", "n_commit_pod_of_existing_gang"]

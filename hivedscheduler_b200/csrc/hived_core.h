@@ -1179,7 +1179,9 @@ struct Core {
     if (k > L || k <= 0 || m > d.S.PS) return 0;
     const int optimal = optimalAffinity(chain, k);
     if (optimal < 0) return 0;
+    long long tq = pclock();
     bkSort(sched);
+    dbg(0, tq);
     // findNodesForPods (:268-306): nodes in sorted order = buckets L .. 0, free leaves of a node = L - u
     int u = L - k;
     for (; u >= 0; u--) if (d.bk_head[bkIdx(sched, u)] >= 0) break;
@@ -1198,6 +1200,7 @@ struct Core {
     }
     // findLeafCellsInNode (:308-387) among the free leaves of the node: the first k free leaves of the first cell of
     // the lowest level >= the optimal one that holds k of them (the lexicographically first subset of minimal LCA level)
+    dbg(1, tq);
     int outOff = 0, prevNode = -1;
     unsigned taken = 0;
     for (int j = 0; j < m; j++) {
@@ -1211,6 +1214,7 @@ struct Core {
       }
       freeMask &= ~taken;
       unsigned pick = 0;
+      int unitLevel = 1, unitFirst = 0;  // the pod takes a COMPLETE cell of this level (1: single leaves), starting at this leaf
       for (int l = optimal; l <= viewLevel && !pick; l++) {
         const int sl = l == viewLevel ? L : d.chain_lvl_leafnum[cl(chain, l)];
         for (int g0 = 0; g0 < L && !pick; g0 += sl) {
@@ -1218,10 +1222,13 @@ struct Core {
           if (hv_popc(freeMask & gm) >= k) {
             unsigned c = freeMask & gm;
             for (int q = 0; q < k; q++) { const unsigned low = c & (0u - c); pick |= low; c ^= low; }
+            if (sl == k) { unitLevel = l; unitFirst = g0; }
           }
         }
       }
       if (!pick) { panic(HIVED_ERR_PLATFORM); return 0; }  // the node was chosen because it has k free leaves
+      ST(s.pod_pos[j], unitLevel);
+      ST(s.pod_unit[j], unitLevel > 1 ? d.v_anc[(l0 + unitFirst) * AS + unitLevel] : -1);
       taken |= pick;
       for (int b0 = 0; b0 < L; b0 += HIVED_WARPSZ) {
         const int i = b0 + lane;
@@ -1230,6 +1237,7 @@ struct Core {
       hv_warp_sync();
       outOff += k;
     }
+    dbg(2, tq);
     return 1;
   }
 
@@ -1565,6 +1573,7 @@ struct Core {
       const int fp = fastPlace(sched, memLeaf[0], memPods[0], outLeaves);
       if (panicCode) return false;
       if (fp == 1) {
+        fastPlaced = true; fastK = memLeaf[0]; fastM = memPods[0]; fastSched = sched;
         path_add(PC_FAST_VIEW);
         stat_add(ST_VIEW_NODES, d.s_n[sched]);
         stat_add(ST_PODS, npods);
@@ -2087,7 +2096,6 @@ struct Core {
     }
     if (bad) return false;
     hv_warp_sync();
-    dbg(7, tq);
     stat_add(ST_LEAVES, nl);
     // level 1: the leaves themselves (releaseLeafCell :1319-1352 + setCellState Free)
     for (int b0 = 0; b0 < nl; b0 += HIVED_WARPSZ) {
@@ -2102,7 +2110,6 @@ struct Core {
       }
     }
     hv_warp_sync();
-    dbg(8, tq);
     for (int l = 2; l < AS; l++) {
       bool changedAny = false;
       for (int b0 = 0; b0 < nl; b0 += HIVED_WARPSZ) {
@@ -2142,7 +2149,6 @@ struct Core {
       hv_warp_sync();
       if (!changedAny) break;  // nothing moved at this level: the levels above keep their values
     }
-    dbg(9, tq);
     // hived_algorithm.go:1343-1347: a preassigned cell goes back once nothing in it is in real use
     bool anyRelease = false;
     for (int b0 = 0; b0 < nl; b0 += HIVED_WARPSZ) {
@@ -2159,7 +2165,184 @@ struct Core {
         if (panicCode) return true;
       }
     }
-    dbg(10, tq);
+    return true;
+  }
+
+  // ---- lean release: the gang as UNITS (see planLean), one unit after the other.  Everything at and below a unit
+  // becomes free and unbound (stores only, lanes over its leaves).  Above it, every ancestor is recomputed from its
+  // children as deleteGroupBatched does — but the ancestors of ONE unit form a single path, so the values of the
+  // OTHER children of every level are fetched up front, all levels at once (lane = child, one coalesced load per
+  // level and array), and the walk itself runs in registers: max of the children for the priority, Free iff every
+  // child is Free, unbound iff no child stays bound (never a pinned cell).  false: nothing written.
+  HIVED_DEV bool leanDelete(int g, int nl, int vc) {
+    if (AS > LEAN_LV) return false;
+    long long tq = pclock();
+    const int hw = d.g_hdr[(int64_t)g * GROUP_HDR_WORDS + (lane & (GROUP_HDR_WORDS - 1))];
+    (void)hw;
+    if (d.g_nmem[g] != 1 || !(d.g_flags[g] & GF_HAS_VIRTUAL)) return false;
+    const int k = d.g_mem_leaf[g * 8], m = d.g_mem_pods[g * 8];
+    const int32_t* ph = gphys(g);
+    const int32_t* vi = gvirt(g);
+    const int P0 = ph[0];
+    if (P0 < 0) return false;
+    const int chain = d.p_chain[P0];
+    // unit level: the level whose cells hold exactly k leaves, if every pod is one such complete cell
+    int u0 = 1;
+    if (k > 1) for (int l = 2; l <= d.chain_top[chain]; l++) if (d.chain_lvl_leafnum[cl(chain, l)] == k) u0 = l;
+    // preconditions of the whole-gang release (deleteGroupBatched), per leaf; complete-cell shape, per pod
+    bool bad = false;
+    for (int b0 = 0; b0 < nl; b0 += HIVED_WARPSZ) {
+      const int i = b0 + lane;
+      bool ok = true;
+      if (i < nl) {
+        const int L = ph[i], V = vi[i];
+        ok = L >= 0 && V >= 0 && d.p_vcell[L] == V && d.p_state[L] == HIVED_CELL_USED && d.p_healthy[L] && d.p_prio[L] != OPP_PRIO &&
+             !(d.p_flags[L] & PF_PINNED_BIT);
+        if (ok && u0 > 1) {
+          const int first = i / k * k;
+          const int Lf = ph[first], Vf = vi[first];
+          ok = Lf >= 0 && Vf >= 0 && L == Lf + (i - first) && V == Vf + (i - first);
+          if (ok && i == first) {
+            const int Pu = d.p_anc[Lf * AS + u0], Cu = d.v_anc[Vf * AS + u0];
+            ok = Pu >= 0 && Cu >= 0 && d.p_leaf0[Pu] == Lf && d.v_leaf0[Cu] == Vf && d.p_vcell[Pu] == Cu && !(d.p_flags[Pu] & PF_PINNED_BIT);
+          }
+        }
+      }
+      if (hv_ballot(!ok)) bad = true;
+    }
+    if (bad && u0 > 1) {
+      // not complete cells: leaves as units (a second look at the per-leaf conditions only)
+      u0 = 1; bad = false;
+      for (int b0 = 0; b0 < nl; b0 += HIVED_WARPSZ) {
+        const int i = b0 + lane;
+        bool ok = true;
+        if (i < nl) {
+          const int L = ph[i], V = vi[i];
+          ok = L >= 0 && V >= 0 && d.p_vcell[L] == V && d.p_state[L] == HIVED_CELL_USED && d.p_healthy[L] && d.p_prio[L] != OPP_PRIO &&
+               !(d.p_flags[L] & PF_PINNED_BIT);
+        }
+        if (hv_ballot(!ok)) bad = true;
+      }
+    }
+    if (bad) return false;
+    const int K = u0 > 1 ? k : 1, units = u0 > 1 ? m : nl;
+    stat_add(ST_LEAVES, nl);
+    path_add(PC_FAST_DELETE);
+    dbg(7, tq);
+    int lastPre = -1;
+    for (int un = 0; un < units; un++) {
+      const int Lf = ph[un * K], Vf = vi[un * K];
+      const int Pu = u0 > 1 ? d.p_anc[Lf * AS + u0] : Lf, Cu = u0 > 1 ? d.v_anc[Vf * AS + u0] : Vf;
+      const int pre = d.v_pre[Cu];
+      const int preP = d.v_pcell[pre];
+      const int ceil = multi ? d.v_level[pre] : AS;
+      // ---- the values of the other children along the path, all levels at once
+      int va[LEAN_LV], pa[LEAN_LV], vOld[LEAN_LV], vPc[LEAN_LV], pOld[LEAN_LV], pSt[LEAN_LV], pVc[LEAN_LV];
+      int oMaxV[LEAN_LV], oMaxP[LEAN_LV];
+      bool oBoundV[LEAN_LV], oNotFreeP[LEAN_LV];
+#pragma unroll
+      for (int l = 0; l < LEAN_LV; l++) {
+        va[l] = (l >= u0 && l < AS) ? d.v_anc[Cu * AS + l] : -1;
+        pa[l] = (l >= u0 && l < AS && l <= ceil) ? d.p_anc[Pu * AS + l] : -1;
+      }
+#pragma unroll
+      for (int l = 0; l < LEAN_LV; l++) {
+        vOld[l] = 0; vPc[l] = -1; pOld[l] = 0; pSt[l] = 0; pVc[l] = -1;
+        oMaxV[l] = FREE_PRIO; oMaxP[l] = FREE_PRIO; oBoundV[l] = false; oNotFreeP[l] = false;
+        if (l < 2 || l <= u0) continue;
+        if (va[l] >= 0) {
+          vOld[l] = d.v_prio[va[l]]; vPc[l] = d.v_pcell[va[l]];
+          const int c0 = d.v_child0[va[l]], n = d.v_nchild[va[l]], skip = va[l - 1] - c0;
+          int mx = FREE_PRIO; bool bd = false;
+          for (int b0 = 0; b0 < n; b0 += HIVED_WARPSZ) {
+            const int j = b0 + lane;
+            if (j < n && j != skip) { const int q = d.v_prio[c0 + j]; if (q > mx) mx = q; if (d.v_pcell[c0 + j] >= 0) bd = true; }
+          }
+          oMaxV[l] = mx; oBoundV[l] = bd;
+        }
+        if (pa[l] >= 0) {
+          pOld[l] = d.p_prio[pa[l]]; pSt[l] = d.p_state[pa[l]]; pVc[l] = d.p_vcell[pa[l]];
+          const int c0 = d.p_child0[pa[l]], n = d.p_nchild[pa[l]], skip = pa[l - 1] - c0;
+          int mx = FREE_PRIO; bool nf = false;
+          for (int b0 = 0; b0 < n; b0 += HIVED_WARPSZ) {
+            const int j = b0 + lane;
+            if (j < n && j != skip) { const int q = d.p_prio[c0 + j]; if (q > mx) mx = q; if (d.p_state[c0 + j] != HIVED_CELL_FREE) nf = true; }
+          }
+          oMaxP[l] = mx; oNotFreeP[l] = nf;
+        }
+      }
+#pragma unroll
+      for (int l = 0; l < LEAN_LV; l++) {
+        if (l < 2 || l <= u0 || l >= AS) continue;
+        oMaxV[l] = hv_reduce_max(oMaxV[l]); oBoundV[l] = hv_ballot(oBoundV[l]) != 0;
+        oMaxP[l] = hv_reduce_max(oMaxP[l]); oNotFreeP[l] = hv_ballot(oNotFreeP[l]) != 0;
+      }
+      dbg(8, tq);
+      // ---- the unit and everything below it: free and unbound
+      hv_phase();
+      {
+        const int pl0 = u0 > 1 ? Lf : Pu, vl0 = u0 > 1 ? Vf : Cu;
+        for (int b0 = 0; b0 < K; b0 += HIVED_WARPSZ) {
+          const int j = b0 + lane;
+          bkMarkLeaves(j < K, vl0 + j);
+          if (j < K) {
+            const int Pl = pl0 + j, Cl = vl0 + j;
+            d.p_using[Pl] = -1;
+            for (int l = 1; l <= u0; l++) {
+              const int a = d.p_anc[Pl * AS + l], v = d.v_anc[Cl * AS + l];
+              d.v_prio[v] = FREE_PRIO; d.p_prio[a] = FREE_PRIO;
+              d.p_vcell[a] = -1; d.v_pcell[v] = -1; d.v_state[v] = HIVED_CELL_FREE; d.v_healthy[v] = 1;
+              d.p_state[a] = HIVED_CELL_FREE;
+            }
+          }
+        }
+      }
+      dbg(9, tq);
+      // ---- the path above, in registers (uniform)
+      int childPrioV = FREE_PRIO, childPrioP = FREE_PRIO;
+      bool childBoundV = false, childFreeP = true, goV = true, goP = true;
+#pragma unroll
+      for (int l = 0; l < LEAN_LV; l++) {
+        if (l < 2 || l <= u0 || l >= AS) continue;
+        if (va[l] >= 0 && goV) {
+          const int nv = oMaxV[l] > childPrioV ? oMaxV[l] : childPrioV;
+          bool changed = false;
+          if (nv != vOld[l]) { ST(d.v_prio[va[l]], nv); changed = true; }
+          bool stillBound = vPc[l] >= 0;
+          if (!oBoundV[l] && !childBoundV && vPc[l] >= 0 && !(d.p_flags[vPc[l]] & PF_PINNED_BIT)) {
+            ST(d.p_vcell[vPc[l]], -1); ST(d.v_pcell[va[l]], -1); ST(d.v_state[va[l]], HIVED_CELL_FREE); ST(d.v_healthy[va[l]], 1);
+            stillBound = false; changed = true;
+            if (pa[l] == vPc[l]) pVc[l] = -1;
+          }
+          childPrioV = nv; childBoundV = stillBound;
+          if (!changed) goV = false;  // nothing moved: the levels above keep their values
+        }
+        if (pa[l] >= 0 && goP) {
+          const int np_ = oMaxP[l] > childPrioP ? oMaxP[l] : childPrioP;
+          bool changed = false;
+          if (np_ != pOld[l]) { ST(d.p_prio[pa[l]], np_); changed = true; }
+          bool nowFree = false;
+          if (!oNotFreeP[l] && childFreeP) {
+            nowFree = true;
+            if (pSt[l] != HIVED_CELL_FREE) { ST(d.p_state[pa[l]], HIVED_CELL_FREE); changed = true; }
+            if (pVc[l] >= 0) ST(d.v_state[pVc[l]], HIVED_CELL_FREE);
+          }
+          childPrioP = np_; childFreeP = nowFree;
+          if (!changed) goP = false;
+        }
+      }
+      hv_warp_sync();
+      dbg(10, tq);
+      // hived_algorithm.go:1343-1347: a preassigned cell goes back once nothing in it is in real use — after the last
+      // of the gang's units inside it (units of one preassigned cell need not be adjacent: check the later ones)
+      if (!(d.p_flags[preP] & PF_PINNED_BIT) && d.v_prio[pre] < 0) {
+        bool later = false;
+        for (int q = un + 1; q < units; q++) if (d.v_pre[vi[q * K]] == pre) later = true;
+        if (!later && !dm_contains(vc, preP)) releasePreassignedCell(preP, vc, false);
+        if (panicCode) return true;
+      }
+      (void)lastPre;
+    }
     return true;
   }
 
@@ -2167,6 +2350,8 @@ struct Core {
   HIVED_DEV void deleteAllocatedAffinityGroup(int g) {
     int nl = groupLeaves(g);
     int vc = d.g_vc[g];
+    if (leanDelete(g, nl, vc)) { eraseGroup(g); return; }
+    path_add(PC_GENERAL_DELETE);
     if (deleteGroupBatched(g, nl, vc)) { eraseGroup(g); return; }
     const int32_t* ph = gphys(g);
     for (int i = 0; i < nl; i++) {
@@ -2391,16 +2576,173 @@ struct Core {
     return true;
   }
 
+  // ======================================================================================
+  // lean lane: a gang placed by fastPlace is mapped, emitted and committed as a set of UNITS — a unit is one leaf
+  // cell, or one complete cell (a whole half / node / ...) when every pod takes exactly that — with one lane per unit
+  // and the tree levels unrolled.  planLean only READS the scheduler state (so that any precondition that does not
+  // hold hands the placement over to the general code, nothing having changed) and produces, per unit, the physical
+  // cell the placement maps to (mapVirtualPlacementToPhysical) and the virtual cell the commit will bind it to
+  // (mapPhysicalCellToVirtual); applyLean is the commit: stores only.  The two mappings share their structure:
+  // under an already bound virtual cell y the r-th NEW child (in order of first appearance among the leaves) gets
+  // the r-th unbound child of y's physical cell resp. the r-th free unbound virtual child of y; under a new cell it
+  // gets the r-th child on both sides (see mapPlacementBatched / commitGroupBatched for the derivation).
+  // ======================================================================================
+  static constexpr int LEAN_LV = 8;  // tree levels held in registers
+  bool leanOn;       // the current event's placement was planned by planLean (apply it instead of the general commit)
+  bool fastPlaced;   // the current placement came from fastPlace (pods x leaves below)
+  int fastK, fastM, fastSched;
+  int leanU0, leanUnits, leanK;  // unit level, number of units, leaf cells per unit
+  int lnP, lnC, lnLs;            // per lane (= unit): physical cell, commit-time virtual cell, first bound level above
+
+  HIVED_DEV_NOINLINE bool planLean(int sched, int k, int m) {
+    if (AS > LEAN_LV || !d.S.directLeaf || (sugg != nullptr)) return false;
+    long long tq = pclock();
+    const int chain = d.s_chain[sched];
+    // units: complete cells when every pod takes one of the same level, else leaves
+    int u0 = s.pod_pos[0];
+    for (int j = 1; j < m; j++) if (s.pod_pos[j] != u0) u0 = 1;
+    const int K = u0 > 1 ? k : 1;
+    const int units = u0 > 1 ? m : m * k;
+    if (units > HIVED_WARPSZ || units <= 0) return false;
+    const bool act = lane < units;
+    const int S = act ? (u0 > 1 ? s.pod_unit[lane] : s.pl_v[lane]) : 0;
+    int anc[LEAN_LV], bnd[LEAN_LV];
+#pragma unroll
+    for (int l = 0; l < LEAN_LV; l++) anc[l] = (act && l >= u0 && l < AS) ? d.v_anc[S * AS + l] : -1;
+#pragma unroll
+    for (int l = 0; l < LEAN_LV; l++) bnd[l] = anc[l] >= 0 ? d.v_pcell[anc[l]] : -1;
+    unsigned boundBits = 0;
+#pragma unroll
+    for (int l = 0; l < LEAN_LV; l++) if (bnd[l] >= 0) boundBits |= 1u << l;
+    const int ls = boundBits ? hv_ffs(boundBits) - 1 : 0;
+    // every unit is unbound itself and sits below a bound cell (else: bound leaves, or a preassigned cell to allocate)
+    if (hv_ballot(act && ls <= u0)) return false;
+    const int maxLs = hv_reduce_max(act ? ls : 0);
+    dbg(3, tq);
+    int curP = -1, curC = -1, unitP = -1, unitC = -1;
+    int scanned = 0;
+#pragma unroll
+    for (int l = LEAN_LV - 2; l >= 1; l--) {
+      if (l >= maxLs || l < u0) continue;  // uniform
+      if (act && l + 1 == ls) { curP = bnd[l + 1]; curC = anc[l + 1]; }
+      const bool a = act && l < ls;
+      const int x = anc[l], y = anc[l + 1];
+      const bool parentBound = a && l + 1 == ls;
+      const unsigned grp = hv_match(a ? x : -1 - lane);
+      const bool leader = a && hv_ffs(grp) - 1 == lane;
+      const unsigned sib = hv_match(leader ? y : -1 - lane);
+      const int r = hv_popc(sib & hv_lanemask_lt());
+      int selP = -1, selC = -1;
+      if (leader && !parentBound) {
+        selP = r < d.p_nchild[curP] ? d.p_child0[curP] + r : -1;
+        selC = r < d.v_nchild[curC] ? d.v_child0[curC] + r : -1;
+      }
+      bool unusable = false;
+      { const int t = selectUnboundPhysChild(leader && parentBound, curP, r, unusable); if (leader && parentBound) selP = t; }
+      { const int t = selectFreeUnboundChild(leader && parentBound, curC, r); if (leader && parentBound) selC = t; }
+      if (hv_ballot(leader && (selP < 0 || selC < 0)) || unusable) return false;
+      if (leader && parentBound && (sib & hv_lanemask_lt()) == 0) scanned += d.p_nchild[curP];  // getUsablePhysicalCells over the bound cell's children
+      if (leader && l > 1) scanned += d.p_nchild[selP];                                          // ... and over the new cell's own
+      const int src = hv_ffs(grp) - 1;
+      const int bP = hv_shfl(selP, src), bC = hv_shfl(selC, src);
+      if (a) { curP = bP; curC = bC; if (l == u0) { unitP = bP; unitC = bC; } }
+    }
+    dbg(4, tq);
+    // the cells the gang takes are free (an unbound, healthy cell without opportunistic use is; checked all the same)
+    if (hv_ballot(act && (unitP < 0 || unitC < 0 || d.p_state[unitP] != HIVED_CELL_FREE || d.p_chain[unitP] != chain))) return false;
+    // new cells below a complete-cell unit pair up by index; the general search scans the children of each of them
+    int sub = 0;
+    for (int l = 2; l < u0; l++) sub += K / d.chain_lvl_leafnum[cl(chain, l - 1)];
+    scanned = hv_reduce_add(scanned) + units * sub;
+    stat_add(ST_FREE_CELLS, scanned);
+    // the placement for result emission (physical leaves) and for the commit (its virtual leaves)
+    const int pl0 = act ? (u0 > 1 ? d.p_leaf0[unitP] : unitP) : 0, vl0 = act ? (u0 > 1 ? d.v_leaf0[unitC] : unitC) : 0;
+    hv_phase();
+    if (act) for (int j = 0; j < K; j++) { s.pl_p[lane * K + j] = pl0 + j; s.pl_v2[lane * K + j] = vl0 + j; }
+    hv_warp_sync();
+    lnP = unitP; lnC = unitC; lnLs = ls;
+    leanU0 = u0; leanUnits = units; leanK = K;
+    leanOn = true;
+    dbg(5, tq);
+    return true;
+  }
+
+  // the commit of a planned gang (= AddAllocatedPod of its first pod with the PodBindInfo just produced,
+  // hived_algorithm.go:247-270, 981-1041): group record, bindings, priorities, states — stores only
+  HIVED_DEV void applyLean(const hived_pod_spec_t& sp, int podIndex, int node) {
+    const int g = sp.group, p = sp.priority, u0 = leanU0, K = leanK;
+    const int nl = leanUnits * K, np = fastM;
+    long long tq = pclock();
+    hv_phase();
+    for (int w = lane; w < GROUP_HDR_WORDS; w += HIVED_WARPSZ) {  // the header record, one coalesced row
+      int v = 0;
+      if (w == 0) v = HIVED_GROUP_ALLOCATED;
+      else if (w == 1) v = sp.vc;
+      else if (w == 2) v = p;
+      else if (w == 3) v = ((sp.flags & HIVED_SPEC_LAZY_PREEMPTION) ? GF_LAZY_ENABLE : 0) | GF_HAS_VIRTUAL;
+      else if (w == 4) v = 1;
+      else if (w == 8) v = fastK;
+      else if (w == 16) v = fastM;
+      d.g_hdr[(int64_t)g * GROUP_HDR_WORDS + w] = v;
+    }
+    int32_t* ph = gphys(g); int32_t* vi = gvirt(g); int32_t* po = gpods(g);
+    for (int i = lane; i < np; i += HIVED_WARPSZ) po[i] = i == podIndex ? sp.pod : -1;
+    if (lane == 0) d.pod_node[sp.pod] = node;
+    stat_add(ST_LEAVES, nl);
+    path_add(PC_FAST_COMMIT);
+    // the units and everything above them
+    const bool act = lane < leanUnits;
+    if (act) {
+      const int ceil = multi ? d.v_prelevel[lnC] : AS;
+#pragma unroll
+      for (int l = 1; l < LEAN_LV; l++) {
+        if (l < u0 || l >= AS) continue;
+        const int pa = d.p_anc[lnP * AS + l], va = d.v_anc[lnC * AS + l];
+        if (pa < 0) continue;
+        if (l < lnLs) { d.p_vcell[pa] = va; d.v_pcell[va] = pa; d.v_healthy[va] = d.p_healthy[pa]; }  // bindCell
+        if (va >= 0) { hv_red_max(&d.v_prio[va], p); d.v_state[va] = HIVED_CELL_USED; }
+        if (l <= ceil) { hv_red_max(&d.p_prio[pa], p); d.p_state[pa] = HIVED_CELL_USED; }
+      }
+    }
+    // the leaves (and, below a complete-cell unit, the cells between: they pair up by index)
+    for (int b0 = 0; b0 < nl; b0 += HIVED_WARPSZ) {
+      const int i = b0 + lane;
+      const int Pl = i < nl ? s.pl_p[i] : 0, Cl = i < nl ? s.pl_v2[i] : 0;
+      bkMarkLeaves(i < nl, Cl);
+      if (i < nl) {
+        for (int l = 1; l < u0; l++) {
+          const int pa = d.p_anc[Pl * AS + l], va = d.v_anc[Cl * AS + l];
+          d.p_vcell[pa] = va; d.v_pcell[va] = pa; d.v_healthy[va] = d.p_healthy[pa];
+          d.v_prio[va] = p; d.v_state[va] = HIVED_CELL_USED;
+          d.p_prio[pa] = p; d.p_state[pa] = HIVED_CELL_USED;
+        }
+        d.p_using[Pl] = g;
+        ph[i] = Pl; vi[i] = Cl;
+      }
+    }
+    hv_warp_sync();
+    dbg(6, tq);
+  }
+
   // hived_algorithm.go:898-942; intra_vc_scheduler.go:92-117
   HIVED_DEV bool scheduleGuaranteedAffinityGroup(const Req& r, int& reason, int& rcell) {
     int vset = r.pinned >= 0 ? d.vc_pinned_vset[r.vc * d.S.nPinned + r.pinned] : (r.chain >= 0 ? d.vc_chain_vset[r.vc * d.S.nChains + r.chain] : -1);
     int sched = vset >= 0 ? d.vset_sched[vset] : -1;
     if (sched < 0) { reason = HIVED_WAIT_NO_SCHEDULER | HIVED_WAIT_SCOPE_VC; rcell = -1; return false; }
+    fastPlaced = false;
     if (!tasSchedule(sched, r.nmem, r.memLeaf, r.memPods, r.priority, r.ignoreSuggested, s.pl_v, reason, rcell)) {
       reason |= HIVED_WAIT_SCOPE_VC;
       return false;
     }
     long long tm0 = pclock();
+    if (fastPlaced && planLean(fastSched, fastK, fastM)) {
+      lzCount = 0;
+      path_add(PC_FAST_MAP);
+      stat_add(ST_CYC_MAP, pclock() - tm0);
+      reason = 0; rcell = -1;
+      return true;
+    }
+    path_add(PC_GENERAL_MAP);
     tryLazyPreempt(s.pl_v, r.nleaves);
     if (panicCode) return false;
     bool mapped = mapPlacementBatched(s.pl_v, r.nleaves, r.ignoreSuggested);
@@ -2764,7 +3106,6 @@ struct Core {
     }
     if (bad) return false;
     hv_warp_sync();
-    dbg(2, tq0);
     // bind, top-down
     bool failed = false;
     for (int l = maxLs - 1; l >= 1 && !failed; l--) {
@@ -2806,7 +3147,6 @@ struct Core {
       return false;
     }
     // allocateLeafCell (raise) + using group + setCellState(Used), all leaves at once
-    dbg(3, tq0);
     stat_add(ST_LEAVES, nl);
     int32_t* ph = gphys(g);
     int32_t* vi = gvirt(g);
@@ -2847,7 +3187,6 @@ struct Core {
       }
     }
     hv_warp_sync();
-    dbg(4, tq0);
     return true;
   }
 
@@ -2856,7 +3195,6 @@ struct Core {
     long long tq = pclock();
     int gleaf[HIVED_MAX_MEMBERS], gpods_[HIVED_MAX_MEMBERS];
     int gnmem = newGroup(g, sp, HIVED_GROUP_ALLOCATED, gleaf, gpods_);
-    dbg(1, tq);
     if (commitGroupBatched(sp, b, g, gnmem, gleaf, gpods_)) return;
     bool shouldLazyPreempt = false;
     bool hasVirtualFlag = true;
@@ -2936,7 +3274,6 @@ struct Core {
     memberOffsets(g, m, leafOff, podOff);
     ST(gpods(g)[podOff + podIndex], sp.pod);
     ST(d.pod_node[sp.pod], b.node);
-    dbg(5, tq);
     return 0;
   }
 
@@ -2953,7 +3290,6 @@ struct Core {
     ST(gpods(g)[podOff + podIndex], -1);
     const int32_t* po = gpods(g);
     if (firstIdx(groupPods(g), [&](int i) { return po[i] >= 0; }) >= 0) return;
-    dbg(6, tq);
     deleteAllocatedAffinityGroup(g);
   }
   // hived_algorithm.go:229-245
@@ -2978,6 +3314,7 @@ struct Core {
     int podIndex = 0, reason = 0, rcell = -1;
     bool victimsCollected = false;
     freshPlacement = false;
+    leanOn = false; fastPlaced = false;
     long long tq = pclock();
     if (d.g_state[g] != HIVED_GROUP_NONE) {
       // schedulePodFromExistingGroup :655-712
@@ -3016,7 +3353,6 @@ struct Core {
     }
     if (d.g_state[g] == HIVED_GROUP_NONE) {
       // schedulePodFromNewGroup :714-752
-      dbg(11, tq);
       Req r;
       int rc = scheduleNewAffinityGroup(sp, r, hasVirtual, reason, rcell);
       if (panicCode) return panicCode;
@@ -3028,8 +3364,8 @@ struct Core {
         havePlacement = true; phys = s.pl_p; virt = s.pl_v; freshPlacement = true;
         int nOverlap;
         tq = pclock();
-        collectPreemptionVictims(phys, r.nleaves, res, nOverlap);
-        dbg(12, tq);
+        if (leanOn) { nOverlap = 0; lastVictims = 0; }  // planLean saw every cell of the placement Free
+        else collectPreemptionVictims(phys, r.nleaves, res, nOverlap);
         victimsCollected = true;
         if (panicCode) return panicCode;
         if (phase == HIVED_PHASE_PREEMPTING) {
@@ -3131,8 +3467,8 @@ struct Core {
         // getAllocatedPodIndex (utils.go:291-304) on the PodBindInfo just produced finds the row that holds this
         // pod's node and first leaf index — the row Schedule emitted it from (leaf cells of a gang are distinct)
         int api = lastPodIndex;
-        dbg(0, tq);
-        addAllocatedPod(sp, b, api);
+        if (leanOn && freshPlacement) applyLean(sp, api, lastNode);
+        else { if (!existing) path_add(PC_GENERAL_COMMIT); addAllocatedPod(sp, b, api); }
         stat_add(ST_CYC_COMMIT, pclock() - ta0);
         if (existing) { stat_add(ST_CYC_COMMIT_POD, pclock() - ta0); stat_add(ST_N_COMMIT_POD, 1); }
         rc = panicCode;

@@ -73,7 +73,7 @@ struct GroupMemFld {  // indexed by g * 8 + m like the flat arrays it replaces
   Z(pa_list, S.LS) Z(np_head, S.LS) Z(np_cnt, S.LS)                                                    \
   Z(pl_v, S.LS) Z(pl_p, S.LS) Z(pl_v2, S.LS) Z(pl_p2, S.LS)                                            \
   Z(cand, S.PS * MAX_NODE_LEAVES) Z(cand_len, S.PS) Z(cand_node, S.PS)                                 \
-  Z(pod_need, S.PS) Z(pod_pos, S.PS) Z(pod_cell, S.PS)                                                 \
+  Z(pod_need, S.PS) Z(pod_pos, S.PS) Z(pod_cell, S.PS) Z(pod_unit, S.PS)                               \
   Z(mc0, S.maxLevelCount + MAX_FANOUT) Z(mcbuf, MAXL * MAX_FANOUT)                                     \
   Z(mcpick, MAXL * MAX_FANOUT) Z(mccells, MAXL * MAX_FANOUT)                                           \
   Z(lz_group, S.LS) Z(lz_save, (int64_t)S.LZ * (S.LS + 1)) Z(ba_buf, (int64_t)MAXL * S.maxLevelCount)  \

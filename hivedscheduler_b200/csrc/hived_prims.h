@@ -40,6 +40,7 @@ inline int hv_shfl_up(int v, int) { return v; }
 inline int hv_shfl_xor(int v, int) { return v; }
 inline int hv_atomic_min(int* a, int v) { int o = *a; if (v < o) *a = v; return o; }
 inline int hv_atomic_add(int* a, int v) { int o = *a; *a = o + v; return o; }
+inline void hv_red_max(int* a, int v) { if (v > *a) *a = v; }
 inline long long hv_clock() { return 0; }
 inline int hv_ld_volatile(const int* p) { return *p; }
 inline void hv_st_volatile(int* p, int v) { *p = v; }
@@ -107,6 +108,7 @@ inline int hv_shfl_xor(int x, int m) {
 }
 inline int hv_atomic_min(int* a, int v) { int o = *a; if (v < o) *a = v; return o; }
 inline int hv_atomic_add(int* a, int v) { int o = *a; *a = o + v; return o; }
+inline void hv_red_max(int* a, int v) { if (v > *a) *a = v; }
 inline long long hv_clock() { return 0; }
 inline int hv_ld_volatile(const int* p) { simt::yield_to_scheduler(); return *(const volatile int*)p; }
 inline void hv_st_volatile(int* p, int v) { *(volatile int*)p = v; }
@@ -165,6 +167,8 @@ __device__ __forceinline__ int hv_shfl_up(int v, int delta) { return __shfl_up_s
 __device__ __forceinline__ int hv_shfl_xor(int v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 __device__ __forceinline__ int hv_atomic_min(int* a, int v) { return atomicMin(a, v); }
 __device__ __forceinline__ int hv_atomic_add(int* a, int v) { return atomicAdd(a, v); }
+// fire-and-forget maximum (RED.MAX: no return value, nothing waits for the old value)
+__device__ __forceinline__ void hv_red_max(int* a, int v) { atomicMax(a, v); }
 __device__ __forceinline__ long long hv_clock() { return clock64(); }
 __device__ __forceinline__ int hv_ld_volatile(const int* p) { return *(const volatile int*)p; }
 __device__ __forceinline__ void hv_st_volatile(int* p, int v) { *(volatile int*)p = v; }
