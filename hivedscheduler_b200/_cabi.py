@@ -146,4 +146,5 @@ def load_library(path: str) -> C.CDLL:
 
 
 def load_cuda_library() -> C.CDLL:
-    return load_library(CUDA_LIB_PATH)
+    # HIVED_CUDA_LIB: another BUILD of the same CUDA library (the profiling variant with SM-cycle counters, -DHIVED_PROFILE)
+    return load_library(os.environ.get("HIVED_CUDA_LIB") or CUDA_LIB_PATH)

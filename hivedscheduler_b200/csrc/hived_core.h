@@ -57,6 +57,15 @@ struct Sm {
   int part[MAX_WARPS + 32];
   // ---- the current event, fetched with one coalesced 128-byte load
   alignas(16) int32_t ev_words[2][sizeof(hived_event_t) / 4];  // double buffer: the next event arrives while this one runs
+  // ---- lean-lane workspace of the leader warp: values per tree level (lane = level) and per bucket
+  int lw_va[MAXL], lw_pa[MAXL], lw_vold[MAXL], lw_vpc[MAXL], lw_vc0[MAXL], lw_vn[MAXL], lw_pold[MAXL], lw_pst[MAXL], lw_pvc[MAXL],
+      lw_pc0[MAXL], lw_pn[MAXL], lw_pin[MAXL];
+  int lw_omaxv[MAXL], lw_omaxp[MAXL], lw_oflagv[MAXL], lw_oflagp[MAXL];
+  int un_p[32], un_c[32], un_ls[32];   // planned units: physical cell, commit-time virtual cell, first bound level above
+  int pl_anc[8][32], pl_bnd[8][32];    // planLeanMulti: path and bindings per (level, unit)
+  int bkc_sched;              // the view whose bucket heads are cached below (-1: none)
+  int bkc_head[BK_STRIDE];
+  int own_win[64];            // window of the CTA's event-index list
   // ---- written back at kernel exit
   int panic;
   long long pool_off;
@@ -972,274 +981,9 @@ struct Core {
   }
 
   // ======================================================================================
-  // incremental (bucketed) cluster view — the fast form of updateClusterView + sort.Stable + findNodesForPods
-  // (topology_aware_scheduler.go:231-306) for an intra-VC view whose nodes are all healthy and suggested.
-  //
-  // There the sort key of a node is its number of used leaf cells u (descending; usedHigher is 0 with
-  // crossPriorityPack, intra_vc_scheduler.go:66-70) and sort.Stable keeps the previous order among equal keys.  The
-  // persisted order is therefore the concatenation of the buckets u = L, L-1, ..., 0, each an ordered list, and a
-  // sort only MOVES the nodes whose u changed since the previous sort: into bucket u' go,
-  // in this order, the nodes that dropped into it (from higher buckets; among themselves in their previous global
-  // order), the nodes that stayed, and the nodes that rose into it (from lower buckets; previous global order).
-  // Buckets are doubly linked lists with a sequence label per node (order inside a bucket = ascending label: a
-  // dropper gets a label below the head's, a riser one above the tail's), so the previous global order of two
-  // nodes is (u at the last sort descending, label ascending) without walking a list.  Greedy first-fit becomes:
-  // the head of the first non-empty bucket with L - u >= need, then its successors in the concatenated order.
-  //
-  // The general view pass (viewOp) keeps working on the order ARRAY d.cv; the two forms are converted on demand:
-  // bkMaterialise writes the buckets out to d.cv (before a general pass on that view), bkRebuild sorts d.cv into
-  // buckets (first fast call after a general pass).  Every change of a virtual leaf's priority marks the view node
-  // above it dirty (bkMarkLeaf / bkMarkLeaves), whichever path made it.
+  // the lean lane: incremental (bucketed) cluster view, gangs as units, plan / apply / release
   // ======================================================================================
-  HIVED_DEV int bkIdx(int sched, int u) const { return sched * BK_STRIDE + u; }
-  HIVED_DEV int schedOfVirtual(int vcell) const { return d.vset_sched[d.v_vset[vcell]]; }
-  // number of used (non-free) leaf cells of a view node
-  HIVED_DEV int usedLeaves(int node) const {
-    const int l0 = d.v_leaf0[node], n = d.v_nleaf[node];
-    int u = 0;
-    for (int i = 0; i < n; i++) u += d.v_prio[l0 + i] != FREE_PRIO ? 1 : 0;
-    return u;
-  }
-  // uniform code: the view node above one virtual leaf whose priority changes
-  HIVED_DEV void bkMarkLeaf(int vLeaf) {
-    const int sched = schedOfVirtual(vLeaf);
-    if (sched < 0 || !d.s_fast[sched]) return;
-    const int node = d.v_anc[vLeaf * AS + d.s_level[sched]];
-    if (node < 0 || d.vn_dirty[node]) return;
-    const int n = d.bk_ndirty[sched];
-    hv_phase();
-    ST(d.vn_dirty[node], 1);
-    ST(d.bk_dl[d.s_off[sched] + n], node);
-    ST(d.bk_ndirty[sched], n + 1);
-  }
-  // lane-parallel code: every `act` lane holds a virtual leaf whose priority changes (lanes may share view nodes)
-  HIVED_DEV void bkMarkLeaves(bool act, int vLeaf) {
-    int sched = act ? schedOfVirtual(vLeaf) : -1;
-    if (sched >= 0 && !d.s_fast[sched]) sched = -1;
-    const int node = sched >= 0 ? d.v_anc[vLeaf * AS + d.s_level[sched]] : -1;
-    const bool want = node >= 0 && !d.vn_dirty[node];
-    const unsigned grp = hv_match(want ? node : -1 - lane);
-    if (want && hv_ffs(grp) - 1 == lane) {
-      d.vn_dirty[node] = 1;
-      const int pos = hv_atomic_add(&d.bk_ndirty[sched], 1);
-      d.bk_dl[d.s_off[sched] + pos] = node;
-    }
-    hv_warp_sync();
-  }
-  // unlink / link at the front / link at the back of a bucket (uniform code)
-  HIVED_DEV void bkUnlink(int sched, int node) {
-    const int k = bkIdx(sched, d.vn_u[node]);
-    const int pv = d.vn_prev[node], nx = d.vn_next[node], cnt = d.bk_cnt[k];
-    hv_phase();
-    if (pv >= 0) ST(d.vn_next[pv], nx); else ST(d.bk_head[k], nx);
-    if (nx >= 0) ST(d.vn_prev[nx], pv); else ST(d.bk_tail[k], pv);
-    ST(d.bk_cnt[k], cnt - 1);
-  }
-  HIVED_DEV void bkPushBack(int sched, int u, int node) {
-    const int k = bkIdx(sched, u);
-    const int tail = d.bk_tail[k], seq = d.bk_tseq[k], cnt = d.bk_cnt[k];
-    hv_phase();
-    ST(d.vn_prev[node], tail); ST(d.vn_next[node], -1); ST(d.vn_seq[node], seq); ST(d.vn_u[node], u);
-    if (tail >= 0) ST(d.vn_next[tail], node); else ST(d.bk_head[k], node);
-    ST(d.bk_tail[k], node); ST(d.bk_tseq[k], seq + 1); ST(d.bk_cnt[k], cnt + 1);
-  }
-  HIVED_DEV void bkPushFront(int sched, int u, int node) {
-    const int k = bkIdx(sched, u);
-    const int head = d.bk_head[k], seq = d.bk_hseq[k], cnt = d.bk_cnt[k];
-    hv_phase();
-    ST(d.vn_next[node], head); ST(d.vn_prev[node], -1); ST(d.vn_seq[node], seq); ST(d.vn_u[node], u);
-    if (head >= 0) ST(d.vn_prev[head], node); else ST(d.bk_tail[k], node);
-    ST(d.bk_head[k], node); ST(d.bk_hseq[k], seq - 1); ST(d.bk_cnt[k], cnt + 1);
-  }
-  // buckets -> d.cv (the order array of the general pass); the buckets stop being the authority
-  HIVED_DEV_NOINLINE void bkMaterialise(int sched) {
-    if (!d.bk_valid[sched]) return;
-    const int off = d.s_off[sched], L = d.s_maxleaf[sched];
-    for (int b0 = 0; b0 <= L; b0 += HIVED_WARPSZ) {  // one lane per bucket; bucket u starts after the buckets above it
-      const int u = b0 + lane;
-      if (u <= L) {
-        int base = 0;
-        for (int q = L; q > u; q--) base += d.bk_cnt[bkIdx(sched, q)];
-        int i = 0;
-        for (int x = d.bk_head[bkIdx(sched, u)]; x >= 0; x = d.vn_next[x]) { d.cv[off + base + i] = x; i++; }
-      }
-    }
-    hv_warp_sync();
-    ST(d.bk_valid[sched], 0);
-  }
-  // d.cv (+ the current keys) -> buckets: a stable sort by used leaves, descending
-  HIVED_DEV_NOINLINE void bkRebuild(int sched) {
-    const int off = d.s_off[sched], n = d.s_n[sched], L = d.s_maxleaf[sched];
-    hv_phase();
-    for (int b0 = 0; b0 <= L; b0 += HIVED_WARPSZ) {
-      const int u = b0 + lane;
-      if (u <= L) {
-        const int k = bkIdx(sched, u);
-        d.bk_head[k] = -1; d.bk_tail[k] = -1; d.bk_cnt[k] = 0; d.bk_hseq[k] = -1; d.bk_tseq[k] = 0;
-      }
-    }
-    {  // forget the dirty marks: every key is recomputed
-      const int nd = d.bk_ndirty[sched];
-      for (int i = lane; i < nd; i += HIVED_WARPSZ) d.vn_dirty[d.bk_dl[off + i]] = 0;
-    }
-    hv_warp_sync();
-    for (int b0 = 0; b0 < n; b0 += HIVED_WARPSZ) {
-      const int i = b0 + lane;
-      const bool act = i < n;
-      const int x = act ? d.cv[off + i] : -1;
-      const int u = act ? usedLeaves(x) : -1;
-      for (unsigned todo = hv_ballot(act); todo;) {  // one step per distinct key of the chunk
-        const int uu = hv_shfl(u, hv_ffs(todo) - 1);
-        const unsigned m = hv_ballot(act && u == uu);
-        todo &= ~m;
-        const int k = bkIdx(sched, uu);
-        const int oldTail = d.bk_tail[k], seq0 = d.bk_tseq[k], cnt = d.bk_cnt[k];
-        const unsigned below = m & hv_lanemask_lt();
-        const unsigned above = (m >> lane) >> 1;
-        const int prevLane = below ? hv_hibit(below) : lane;
-        const int nextLane = above ? lane + hv_ffs(above) : lane;
-        const int px = hv_shfl(x, prevLane), nx = hv_shfl(x, nextLane);
-        hv_phase();
-        if (act && u == uu) {
-          d.vn_prev[x] = below ? px : oldTail;
-          d.vn_next[x] = above ? nx : -1;
-          d.vn_seq[x] = seq0 + hv_popc(below);
-          d.vn_u[x] = uu;
-          if (!below) { if (oldTail >= 0) d.vn_next[oldTail] = x; else d.bk_head[k] = x; }
-          if (!above) { d.bk_tail[k] = x; d.bk_tseq[k] = seq0 + hv_popc(m); d.bk_cnt[k] = cnt + hv_popc(m); }
-        }
-        hv_warp_sync();
-      }
-    }
-    ST(d.bk_ndirty[sched], 0);
-    ST(d.bk_valid[sched], 1);
-  }
-  // apply the sort to the nodes whose key changed since the last one
-  HIVED_DEV void bkSort(int sched) {
-    if (!d.bk_valid[sched]) { path_add(PC_BK_REBUILD); bkRebuild(sched); return; }
-    const int nd = d.bk_ndirty[sched];
-    if (nd == 0) return;
-    bkSortDirty(sched, nd);
-  }
-  HIVED_DEV_NOINLINE void bkSortDirty(int sched, int nd) {
-    const int off = d.s_off[sched], L = d.s_maxleaf[sched];
-    // the movers, with their keys before (u at the last sort, label) and after; scratch: vw_ordA = new u, vw_ordB = class key
-    int32_t* dl = d.bk_dl + off;
-    int movers = 0;
-    for (int b0 = 0; b0 < nd; b0 += HIVED_WARPSZ) {
-      const int i = b0 + lane;
-      bool mv = false;
-      if (i < nd) {
-        const int x = dl[i];
-        const int nu = usedLeaves(x), ou = d.vn_u[x];
-        d.vn_dirty[x] = 0;
-        mv = nu != ou;
-        s.vw_ordA[i] = nu;
-        // processing order: first the risers by (old u descending, label ascending) — appended to the back of their
-        // bucket —, then the droppers by (old u ascending, label descending) — pushed to the front, so that they end
-        // up in (old u descending, label ascending) order
-        s.vw_ordB[i] = !mv ? 0x7fffffff : (nu > ou ? (L - ou) : (BK_STRIDE + ou));
-      }
-      movers += hv_popc(hv_ballot(mv));
-    }
-    hv_warp_sync();
-    path_add(PC_BK_MOVERS, movers);
-    for (int r = 0; r < movers; r++) {
-      // the pending mover with the smallest (class key, label [ascending for risers, descending for droppers])
-      int best = 0x7fffffff;
-      for (int b0 = 0; b0 < nd; b0 += HIVED_WARPSZ) { const int i = b0 + lane; if (i < nd && s.vw_ordB[i] < best) best = s.vw_ordB[i]; }
-      best = hv_reduce_min(best);
-      const bool riser = best < BK_STRIDE;
-      int bl = 0x7fffffff;
-      for (int b0 = 0; b0 < nd; b0 += HIVED_WARPSZ) {
-        const int i = b0 + lane;
-        if (i < nd && s.vw_ordB[i] == best) { const int q = d.vn_seq[dl[i]]; const int key = riser ? q : ~q; if (key < bl) bl = key; }
-      }
-      bl = hv_reduce_min(bl);
-      const int wantSeq = riser ? bl : ~bl;
-      const int idx = firstIdx(nd, [&](int i) { return s.vw_ordB[i] == best && d.vn_seq[dl[i]] == wantSeq; });
-      const int x = dl[idx], nu = s.vw_ordA[idx];
-      hv_phase();
-      ST(s.vw_ordB[idx], 0x7fffffff);
-      bkUnlink(sched, x);
-      if (riser) bkPushBack(sched, nu, x); else bkPushFront(sched, nu, x);
-    }
-    ST(d.bk_ndirty[sched], 0);
-  }
-
-  // fast form of pass 1 of topologyAwareScheduler.Schedule (topology_aware_scheduler.go:65-116) for a gang of m pods
-  // with k leaf cells each in an all-healthy intra-VC view: sort, greedy first-fit, intra-node leaf search.
-  // 1: placed (outLeaves = virtual leaf cells in (pod, leaf) order, s.pod_cell = view node per pod);
-  // 0: no capacity without preemption — the general code takes over (its sorts start from the order persisted here).
-  HIVED_DEV bool fastEligible(int sched, int nmem, bool ignoreSuggested) const {
-    return d.s_fast[sched] != 0 && nmem == 1 && (sugg == nullptr || ignoreSuggested) && d.nbad[0] == 0;
-  }
-  HIVED_DEV int fastPlace(int sched, int k, int m, int32_t* outLeaves) {
-    const int L = d.s_maxleaf[sched], chain = d.s_chain[sched], viewLevel = d.s_level[sched];
-    if (k > L || k <= 0 || m > d.S.PS) return 0;
-    const int optimal = optimalAffinity(chain, k);
-    if (optimal < 0) return 0;
-    long long tq = pclock();
-    bkSort(sched);
-    dbg(0, tq);
-    // findNodesForPods (:268-306): nodes in sorted order = buckets L .. 0, free leaves of a node = L - u
-    int u = L - k;
-    for (; u >= 0; u--) if (d.bk_head[bkIdx(sched, u)] >= 0) break;
-    if (u < 0) return 0;
-    int node = d.bk_head[bkIdx(sched, u)];
-    int picked = 0;
-    for (int j = 0; j < m; j++) {
-      if ((L - u) - picked < k) {  // next node in the concatenated order (every later node has at least as many free leaves)
-        int nx = d.vn_next[node];
-        while (nx < 0) { u--; if (u < 0) return 0; nx = d.bk_head[bkIdx(sched, u)]; }
-        node = nx;
-        picked = 0;
-      }
-      picked += k;
-      ST(s.pod_cell[j], node);
-    }
-    // findLeafCellsInNode (:308-387) among the free leaves of the node: the first k free leaves of the first cell of
-    // the lowest level >= the optimal one that holds k of them (the lexicographically first subset of minimal LCA level)
-    dbg(1, tq);
-    int outOff = 0, prevNode = -1;
-    unsigned taken = 0;
-    for (int j = 0; j < m; j++) {
-      const int nd = s.pod_cell[j];
-      if (nd != prevNode) { taken = 0; prevNode = nd; }
-      const int l0 = d.v_leaf0[nd];
-      unsigned freeMask = 0;
-      for (int b0 = 0; b0 < L; b0 += HIVED_WARPSZ) {
-        const int i = b0 + lane;
-        freeMask |= hv_ballot(i < L && d.v_prio[l0 + i] == FREE_PRIO) << b0;
-      }
-      freeMask &= ~taken;
-      unsigned pick = 0;
-      int unitLevel = 1, unitFirst = 0;  // the pod takes a COMPLETE cell of this level (1: single leaves), starting at this leaf
-      for (int l = optimal; l <= viewLevel && !pick; l++) {
-        const int sl = l == viewLevel ? L : d.chain_lvl_leafnum[cl(chain, l)];
-        for (int g0 = 0; g0 < L && !pick; g0 += sl) {
-          const unsigned gm = (sl >= 32 ? 0xffffffffu : ((1u << sl) - 1u)) << g0;
-          if (hv_popc(freeMask & gm) >= k) {
-            unsigned c = freeMask & gm;
-            for (int q = 0; q < k; q++) { const unsigned low = c & (0u - c); pick |= low; c ^= low; }
-            if (sl == k) { unitLevel = l; unitFirst = g0; }
-          }
-        }
-      }
-      if (!pick) { panic(HIVED_ERR_PLATFORM); return 0; }  // the node was chosen because it has k free leaves
-      ST(s.pod_pos[j], unitLevel);
-      ST(s.pod_unit[j], unitLevel > 1 ? d.v_anc[(l0 + unitFirst) * AS + unitLevel] : -1);
-      taken |= pick;
-      for (int b0 = 0; b0 < L; b0 += HIVED_WARPSZ) {
-        const int i = b0 + lane;
-        if (i < L && ((pick >> i) & 1u)) outLeaves[outOff + hv_popc(pick & ((1u << i) - 1u))] = l0 + i;
-      }
-      hv_warp_sync();
-      outOff += k;
-    }
-    dbg(2, tq);
-    return 1;
-  }
+#include "hived_lean.inc"
 
   // ======================================================================================
   // cluster-view pass: data-parallel over the CTA
@@ -2006,6 +1750,7 @@ struct Core {
       d.g_flags[g] = ((sp.flags & HIVED_SPEC_LAZY_PREEMPTION) ? GF_LAZY_ENABLE : 0) | GF_HAS_VIRTUAL;
       d.g_nmem[g] = n;
       d.g_npre[g] = 0;
+      d.g_hdr[(int64_t)g * GROUP_HDR_WORDS + 6] = 0;  // no unit decomposition known (applyLean writes one)
       for (int m = 0; m < n; m++) { d.g_mem_leaf[g * 8 + m] = leaf[m]; d.g_mem_pods[g * 8 + m] = pods[m]; }
     }
     int32_t* ph = gphys(g); int32_t* vi = gvirt(g); int32_t* po = gpods(g);
@@ -2164,184 +1909,6 @@ struct Core {
         if (!(d.p_flags[preP] & PF_PINNED_BIT) && d.v_prio[pre] < 0 && !dm_contains(vc, preP)) releasePreassignedCell(preP, vc, false);
         if (panicCode) return true;
       }
-    }
-    return true;
-  }
-
-  // ---- lean release: the gang as UNITS (see planLean), one unit after the other.  Everything at and below a unit
-  // becomes free and unbound (stores only, lanes over its leaves).  Above it, every ancestor is recomputed from its
-  // children as deleteGroupBatched does — but the ancestors of ONE unit form a single path, so the values of the
-  // OTHER children of every level are fetched up front, all levels at once (lane = child, one coalesced load per
-  // level and array), and the walk itself runs in registers: max of the children for the priority, Free iff every
-  // child is Free, unbound iff no child stays bound (never a pinned cell).  false: nothing written.
-  HIVED_DEV bool leanDelete(int g, int nl, int vc) {
-    if (AS > LEAN_LV) return false;
-    long long tq = pclock();
-    const int hw = d.g_hdr[(int64_t)g * GROUP_HDR_WORDS + (lane & (GROUP_HDR_WORDS - 1))];
-    (void)hw;
-    if (d.g_nmem[g] != 1 || !(d.g_flags[g] & GF_HAS_VIRTUAL)) return false;
-    const int k = d.g_mem_leaf[g * 8], m = d.g_mem_pods[g * 8];
-    const int32_t* ph = gphys(g);
-    const int32_t* vi = gvirt(g);
-    const int P0 = ph[0];
-    if (P0 < 0) return false;
-    const int chain = d.p_chain[P0];
-    // unit level: the level whose cells hold exactly k leaves, if every pod is one such complete cell
-    int u0 = 1;
-    if (k > 1) for (int l = 2; l <= d.chain_top[chain]; l++) if (d.chain_lvl_leafnum[cl(chain, l)] == k) u0 = l;
-    // preconditions of the whole-gang release (deleteGroupBatched), per leaf; complete-cell shape, per pod
-    bool bad = false;
-    for (int b0 = 0; b0 < nl; b0 += HIVED_WARPSZ) {
-      const int i = b0 + lane;
-      bool ok = true;
-      if (i < nl) {
-        const int L = ph[i], V = vi[i];
-        ok = L >= 0 && V >= 0 && d.p_vcell[L] == V && d.p_state[L] == HIVED_CELL_USED && d.p_healthy[L] && d.p_prio[L] != OPP_PRIO &&
-             !(d.p_flags[L] & PF_PINNED_BIT);
-        if (ok && u0 > 1) {
-          const int first = i / k * k;
-          const int Lf = ph[first], Vf = vi[first];
-          ok = Lf >= 0 && Vf >= 0 && L == Lf + (i - first) && V == Vf + (i - first);
-          if (ok && i == first) {
-            const int Pu = d.p_anc[Lf * AS + u0], Cu = d.v_anc[Vf * AS + u0];
-            ok = Pu >= 0 && Cu >= 0 && d.p_leaf0[Pu] == Lf && d.v_leaf0[Cu] == Vf && d.p_vcell[Pu] == Cu && !(d.p_flags[Pu] & PF_PINNED_BIT);
-          }
-        }
-      }
-      if (hv_ballot(!ok)) bad = true;
-    }
-    if (bad && u0 > 1) {
-      // not complete cells: leaves as units (a second look at the per-leaf conditions only)
-      u0 = 1; bad = false;
-      for (int b0 = 0; b0 < nl; b0 += HIVED_WARPSZ) {
-        const int i = b0 + lane;
-        bool ok = true;
-        if (i < nl) {
-          const int L = ph[i], V = vi[i];
-          ok = L >= 0 && V >= 0 && d.p_vcell[L] == V && d.p_state[L] == HIVED_CELL_USED && d.p_healthy[L] && d.p_prio[L] != OPP_PRIO &&
-               !(d.p_flags[L] & PF_PINNED_BIT);
-        }
-        if (hv_ballot(!ok)) bad = true;
-      }
-    }
-    if (bad) return false;
-    const int K = u0 > 1 ? k : 1, units = u0 > 1 ? m : nl;
-    stat_add(ST_LEAVES, nl);
-    path_add(PC_FAST_DELETE);
-    dbg(7, tq);
-    int lastPre = -1;
-    for (int un = 0; un < units; un++) {
-      const int Lf = ph[un * K], Vf = vi[un * K];
-      const int Pu = u0 > 1 ? d.p_anc[Lf * AS + u0] : Lf, Cu = u0 > 1 ? d.v_anc[Vf * AS + u0] : Vf;
-      const int pre = d.v_pre[Cu];
-      const int preP = d.v_pcell[pre];
-      const int ceil = multi ? d.v_level[pre] : AS;
-      // ---- the values of the other children along the path, all levels at once
-      int va[LEAN_LV], pa[LEAN_LV], vOld[LEAN_LV], vPc[LEAN_LV], pOld[LEAN_LV], pSt[LEAN_LV], pVc[LEAN_LV];
-      int oMaxV[LEAN_LV], oMaxP[LEAN_LV];
-      bool oBoundV[LEAN_LV], oNotFreeP[LEAN_LV];
-#pragma unroll
-      for (int l = 0; l < LEAN_LV; l++) {
-        va[l] = (l >= u0 && l < AS) ? d.v_anc[Cu * AS + l] : -1;
-        pa[l] = (l >= u0 && l < AS && l <= ceil) ? d.p_anc[Pu * AS + l] : -1;
-      }
-#pragma unroll
-      for (int l = 0; l < LEAN_LV; l++) {
-        vOld[l] = 0; vPc[l] = -1; pOld[l] = 0; pSt[l] = 0; pVc[l] = -1;
-        oMaxV[l] = FREE_PRIO; oMaxP[l] = FREE_PRIO; oBoundV[l] = false; oNotFreeP[l] = false;
-        if (l < 2 || l <= u0) continue;
-        if (va[l] >= 0) {
-          vOld[l] = d.v_prio[va[l]]; vPc[l] = d.v_pcell[va[l]];
-          const int c0 = d.v_child0[va[l]], n = d.v_nchild[va[l]], skip = va[l - 1] - c0;
-          int mx = FREE_PRIO; bool bd = false;
-          for (int b0 = 0; b0 < n; b0 += HIVED_WARPSZ) {
-            const int j = b0 + lane;
-            if (j < n && j != skip) { const int q = d.v_prio[c0 + j]; if (q > mx) mx = q; if (d.v_pcell[c0 + j] >= 0) bd = true; }
-          }
-          oMaxV[l] = mx; oBoundV[l] = bd;
-        }
-        if (pa[l] >= 0) {
-          pOld[l] = d.p_prio[pa[l]]; pSt[l] = d.p_state[pa[l]]; pVc[l] = d.p_vcell[pa[l]];
-          const int c0 = d.p_child0[pa[l]], n = d.p_nchild[pa[l]], skip = pa[l - 1] - c0;
-          int mx = FREE_PRIO; bool nf = false;
-          for (int b0 = 0; b0 < n; b0 += HIVED_WARPSZ) {
-            const int j = b0 + lane;
-            if (j < n && j != skip) { const int q = d.p_prio[c0 + j]; if (q > mx) mx = q; if (d.p_state[c0 + j] != HIVED_CELL_FREE) nf = true; }
-          }
-          oMaxP[l] = mx; oNotFreeP[l] = nf;
-        }
-      }
-#pragma unroll
-      for (int l = 0; l < LEAN_LV; l++) {
-        if (l < 2 || l <= u0 || l >= AS) continue;
-        oMaxV[l] = hv_reduce_max(oMaxV[l]); oBoundV[l] = hv_ballot(oBoundV[l]) != 0;
-        oMaxP[l] = hv_reduce_max(oMaxP[l]); oNotFreeP[l] = hv_ballot(oNotFreeP[l]) != 0;
-      }
-      dbg(8, tq);
-      // ---- the unit and everything below it: free and unbound
-      hv_phase();
-      {
-        const int pl0 = u0 > 1 ? Lf : Pu, vl0 = u0 > 1 ? Vf : Cu;
-        for (int b0 = 0; b0 < K; b0 += HIVED_WARPSZ) {
-          const int j = b0 + lane;
-          bkMarkLeaves(j < K, vl0 + j);
-          if (j < K) {
-            const int Pl = pl0 + j, Cl = vl0 + j;
-            d.p_using[Pl] = -1;
-            for (int l = 1; l <= u0; l++) {
-              const int a = d.p_anc[Pl * AS + l], v = d.v_anc[Cl * AS + l];
-              d.v_prio[v] = FREE_PRIO; d.p_prio[a] = FREE_PRIO;
-              d.p_vcell[a] = -1; d.v_pcell[v] = -1; d.v_state[v] = HIVED_CELL_FREE; d.v_healthy[v] = 1;
-              d.p_state[a] = HIVED_CELL_FREE;
-            }
-          }
-        }
-      }
-      dbg(9, tq);
-      // ---- the path above, in registers (uniform)
-      int childPrioV = FREE_PRIO, childPrioP = FREE_PRIO;
-      bool childBoundV = false, childFreeP = true, goV = true, goP = true;
-#pragma unroll
-      for (int l = 0; l < LEAN_LV; l++) {
-        if (l < 2 || l <= u0 || l >= AS) continue;
-        if (va[l] >= 0 && goV) {
-          const int nv = oMaxV[l] > childPrioV ? oMaxV[l] : childPrioV;
-          bool changed = false;
-          if (nv != vOld[l]) { ST(d.v_prio[va[l]], nv); changed = true; }
-          bool stillBound = vPc[l] >= 0;
-          if (!oBoundV[l] && !childBoundV && vPc[l] >= 0 && !(d.p_flags[vPc[l]] & PF_PINNED_BIT)) {
-            ST(d.p_vcell[vPc[l]], -1); ST(d.v_pcell[va[l]], -1); ST(d.v_state[va[l]], HIVED_CELL_FREE); ST(d.v_healthy[va[l]], 1);
-            stillBound = false; changed = true;
-            if (pa[l] == vPc[l]) pVc[l] = -1;
-          }
-          childPrioV = nv; childBoundV = stillBound;
-          if (!changed) goV = false;  // nothing moved: the levels above keep their values
-        }
-        if (pa[l] >= 0 && goP) {
-          const int np_ = oMaxP[l] > childPrioP ? oMaxP[l] : childPrioP;
-          bool changed = false;
-          if (np_ != pOld[l]) { ST(d.p_prio[pa[l]], np_); changed = true; }
-          bool nowFree = false;
-          if (!oNotFreeP[l] && childFreeP) {
-            nowFree = true;
-            if (pSt[l] != HIVED_CELL_FREE) { ST(d.p_state[pa[l]], HIVED_CELL_FREE); changed = true; }
-            if (pVc[l] >= 0) ST(d.v_state[pVc[l]], HIVED_CELL_FREE);
-          }
-          childPrioP = np_; childFreeP = nowFree;
-          if (!changed) goP = false;
-        }
-      }
-      hv_warp_sync();
-      dbg(10, tq);
-      // hived_algorithm.go:1343-1347: a preassigned cell goes back once nothing in it is in real use — after the last
-      // of the gang's units inside it (units of one preassigned cell need not be adjacent: check the later ones)
-      if (!(d.p_flags[preP] & PF_PINNED_BIT) && d.v_prio[pre] < 0) {
-        bool later = false;
-        for (int q = un + 1; q < units; q++) if (d.v_pre[vi[q * K]] == pre) later = true;
-        if (!later && !dm_contains(vc, preP)) releasePreassignedCell(preP, vc, false);
-        if (panicCode) return true;
-      }
-      (void)lastPre;
     }
     return true;
   }
@@ -2574,154 +2141,6 @@ struct Core {
     scanned = hv_reduce_add((int)scanned);
     stat_add(ST_FREE_CELLS, scanned);
     return true;
-  }
-
-  // ======================================================================================
-  // lean lane: a gang placed by fastPlace is mapped, emitted and committed as a set of UNITS — a unit is one leaf
-  // cell, or one complete cell (a whole half / node / ...) when every pod takes exactly that — with one lane per unit
-  // and the tree levels unrolled.  planLean only READS the scheduler state (so that any precondition that does not
-  // hold hands the placement over to the general code, nothing having changed) and produces, per unit, the physical
-  // cell the placement maps to (mapVirtualPlacementToPhysical) and the virtual cell the commit will bind it to
-  // (mapPhysicalCellToVirtual); applyLean is the commit: stores only.  The two mappings share their structure:
-  // under an already bound virtual cell y the r-th NEW child (in order of first appearance among the leaves) gets
-  // the r-th unbound child of y's physical cell resp. the r-th free unbound virtual child of y; under a new cell it
-  // gets the r-th child on both sides (see mapPlacementBatched / commitGroupBatched for the derivation).
-  // ======================================================================================
-  static constexpr int LEAN_LV = 8;  // tree levels held in registers
-  bool leanOn;       // the current event's placement was planned by planLean (apply it instead of the general commit)
-  bool fastPlaced;   // the current placement came from fastPlace (pods x leaves below)
-  int fastK, fastM, fastSched;
-  int leanU0, leanUnits, leanK;  // unit level, number of units, leaf cells per unit
-  int lnP, lnC, lnLs;            // per lane (= unit): physical cell, commit-time virtual cell, first bound level above
-
-  HIVED_DEV_NOINLINE bool planLean(int sched, int k, int m) {
-    if (AS > LEAN_LV || !d.S.directLeaf || (sugg != nullptr)) return false;
-    long long tq = pclock();
-    const int chain = d.s_chain[sched];
-    // units: complete cells when every pod takes one of the same level, else leaves
-    int u0 = s.pod_pos[0];
-    for (int j = 1; j < m; j++) if (s.pod_pos[j] != u0) u0 = 1;
-    const int K = u0 > 1 ? k : 1;
-    const int units = u0 > 1 ? m : m * k;
-    if (units > HIVED_WARPSZ || units <= 0) return false;
-    const bool act = lane < units;
-    const int S = act ? (u0 > 1 ? s.pod_unit[lane] : s.pl_v[lane]) : 0;
-    int anc[LEAN_LV], bnd[LEAN_LV];
-#pragma unroll
-    for (int l = 0; l < LEAN_LV; l++) anc[l] = (act && l >= u0 && l < AS) ? d.v_anc[S * AS + l] : -1;
-#pragma unroll
-    for (int l = 0; l < LEAN_LV; l++) bnd[l] = anc[l] >= 0 ? d.v_pcell[anc[l]] : -1;
-    unsigned boundBits = 0;
-#pragma unroll
-    for (int l = 0; l < LEAN_LV; l++) if (bnd[l] >= 0) boundBits |= 1u << l;
-    const int ls = boundBits ? hv_ffs(boundBits) - 1 : 0;
-    // every unit is unbound itself and sits below a bound cell (else: bound leaves, or a preassigned cell to allocate)
-    if (hv_ballot(act && ls <= u0)) return false;
-    const int maxLs = hv_reduce_max(act ? ls : 0);
-    dbg(3, tq);
-    int curP = -1, curC = -1, unitP = -1, unitC = -1;
-    int scanned = 0;
-#pragma unroll
-    for (int l = LEAN_LV - 2; l >= 1; l--) {
-      if (l >= maxLs || l < u0) continue;  // uniform
-      if (act && l + 1 == ls) { curP = bnd[l + 1]; curC = anc[l + 1]; }
-      const bool a = act && l < ls;
-      const int x = anc[l], y = anc[l + 1];
-      const bool parentBound = a && l + 1 == ls;
-      const unsigned grp = hv_match(a ? x : -1 - lane);
-      const bool leader = a && hv_ffs(grp) - 1 == lane;
-      const unsigned sib = hv_match(leader ? y : -1 - lane);
-      const int r = hv_popc(sib & hv_lanemask_lt());
-      int selP = -1, selC = -1;
-      if (leader && !parentBound) {
-        selP = r < d.p_nchild[curP] ? d.p_child0[curP] + r : -1;
-        selC = r < d.v_nchild[curC] ? d.v_child0[curC] + r : -1;
-      }
-      bool unusable = false;
-      { const int t = selectUnboundPhysChild(leader && parentBound, curP, r, unusable); if (leader && parentBound) selP = t; }
-      { const int t = selectFreeUnboundChild(leader && parentBound, curC, r); if (leader && parentBound) selC = t; }
-      if (hv_ballot(leader && (selP < 0 || selC < 0)) || unusable) return false;
-      if (leader && parentBound && (sib & hv_lanemask_lt()) == 0) scanned += d.p_nchild[curP];  // getUsablePhysicalCells over the bound cell's children
-      if (leader && l > 1) scanned += d.p_nchild[selP];                                          // ... and over the new cell's own
-      const int src = hv_ffs(grp) - 1;
-      const int bP = hv_shfl(selP, src), bC = hv_shfl(selC, src);
-      if (a) { curP = bP; curC = bC; if (l == u0) { unitP = bP; unitC = bC; } }
-    }
-    dbg(4, tq);
-    // the cells the gang takes are free (an unbound, healthy cell without opportunistic use is; checked all the same)
-    if (hv_ballot(act && (unitP < 0 || unitC < 0 || d.p_state[unitP] != HIVED_CELL_FREE || d.p_chain[unitP] != chain))) return false;
-    // new cells below a complete-cell unit pair up by index; the general search scans the children of each of them
-    int sub = 0;
-    for (int l = 2; l < u0; l++) sub += K / d.chain_lvl_leafnum[cl(chain, l - 1)];
-    scanned = hv_reduce_add(scanned) + units * sub;
-    stat_add(ST_FREE_CELLS, scanned);
-    // the placement for result emission (physical leaves) and for the commit (its virtual leaves)
-    const int pl0 = act ? (u0 > 1 ? d.p_leaf0[unitP] : unitP) : 0, vl0 = act ? (u0 > 1 ? d.v_leaf0[unitC] : unitC) : 0;
-    hv_phase();
-    if (act) for (int j = 0; j < K; j++) { s.pl_p[lane * K + j] = pl0 + j; s.pl_v2[lane * K + j] = vl0 + j; }
-    hv_warp_sync();
-    lnP = unitP; lnC = unitC; lnLs = ls;
-    leanU0 = u0; leanUnits = units; leanK = K;
-    leanOn = true;
-    dbg(5, tq);
-    return true;
-  }
-
-  // the commit of a planned gang (= AddAllocatedPod of its first pod with the PodBindInfo just produced,
-  // hived_algorithm.go:247-270, 981-1041): group record, bindings, priorities, states — stores only
-  HIVED_DEV void applyLean(const hived_pod_spec_t& sp, int podIndex, int node) {
-    const int g = sp.group, p = sp.priority, u0 = leanU0, K = leanK;
-    const int nl = leanUnits * K, np = fastM;
-    long long tq = pclock();
-    hv_phase();
-    for (int w = lane; w < GROUP_HDR_WORDS; w += HIVED_WARPSZ) {  // the header record, one coalesced row
-      int v = 0;
-      if (w == 0) v = HIVED_GROUP_ALLOCATED;
-      else if (w == 1) v = sp.vc;
-      else if (w == 2) v = p;
-      else if (w == 3) v = ((sp.flags & HIVED_SPEC_LAZY_PREEMPTION) ? GF_LAZY_ENABLE : 0) | GF_HAS_VIRTUAL;
-      else if (w == 4) v = 1;
-      else if (w == 8) v = fastK;
-      else if (w == 16) v = fastM;
-      d.g_hdr[(int64_t)g * GROUP_HDR_WORDS + w] = v;
-    }
-    int32_t* ph = gphys(g); int32_t* vi = gvirt(g); int32_t* po = gpods(g);
-    for (int i = lane; i < np; i += HIVED_WARPSZ) po[i] = i == podIndex ? sp.pod : -1;
-    if (lane == 0) d.pod_node[sp.pod] = node;
-    stat_add(ST_LEAVES, nl);
-    path_add(PC_FAST_COMMIT);
-    // the units and everything above them
-    const bool act = lane < leanUnits;
-    if (act) {
-      const int ceil = multi ? d.v_prelevel[lnC] : AS;
-#pragma unroll
-      for (int l = 1; l < LEAN_LV; l++) {
-        if (l < u0 || l >= AS) continue;
-        const int pa = d.p_anc[lnP * AS + l], va = d.v_anc[lnC * AS + l];
-        if (pa < 0) continue;
-        if (l < lnLs) { d.p_vcell[pa] = va; d.v_pcell[va] = pa; d.v_healthy[va] = d.p_healthy[pa]; }  // bindCell
-        if (va >= 0) { hv_red_max(&d.v_prio[va], p); d.v_state[va] = HIVED_CELL_USED; }
-        if (l <= ceil) { hv_red_max(&d.p_prio[pa], p); d.p_state[pa] = HIVED_CELL_USED; }
-      }
-    }
-    // the leaves (and, below a complete-cell unit, the cells between: they pair up by index)
-    for (int b0 = 0; b0 < nl; b0 += HIVED_WARPSZ) {
-      const int i = b0 + lane;
-      const int Pl = i < nl ? s.pl_p[i] : 0, Cl = i < nl ? s.pl_v2[i] : 0;
-      bkMarkLeaves(i < nl, Cl);
-      if (i < nl) {
-        for (int l = 1; l < u0; l++) {
-          const int pa = d.p_anc[Pl * AS + l], va = d.v_anc[Cl * AS + l];
-          d.p_vcell[pa] = va; d.v_pcell[va] = pa; d.v_healthy[va] = d.p_healthy[pa];
-          d.v_prio[va] = p; d.v_state[va] = HIVED_CELL_USED;
-          d.p_prio[pa] = p; d.p_state[pa] = HIVED_CELL_USED;
-        }
-        d.p_using[Pl] = g;
-        ph[i] = Pl; vi[i] = Cl;
-      }
-    }
-    hv_warp_sync();
-    dbg(6, tq);
   }
 
   // hived_algorithm.go:898-942; intra_vc_scheduler.go:92-117
@@ -3321,7 +2740,8 @@ struct Core {
       int nl = groupLeaves(g);
       const int32_t* ph = gphys(g);
       // collectBadOrNonSuggestedNodes utils.go:175-200 (ignoreK8sSuggestedNodes is never set on a group)
-      bool badOrNonSuggested = firstIdx(nl, [&](int i) {
+      // (only a preempting group's answer depends on it)
+      bool badOrNonSuggested = d.g_state[g] != HIVED_GROUP_ALLOCATED && firstIdx(nl, [&](int i) {
         int c = ph[i];
         return c >= 0 && (!d.p_healthy[c] || !node_suggested(d.p_node[c]));
       }) >= 0;
@@ -3447,7 +2867,9 @@ struct Core {
       const bool existing = rc == 0 && d.g_state[sp.group] != HIVED_GROUP_NONE;
       long long ts0 = pclock();
       lastKind = -1;
-      if (rc == 0) {
+      if (rc == 0 && existing && type == HIVED_EV_SCHEDULE && leanPodOfGang(sp, res)) {
+        stat_add(ST_SCHEDULE, 1);  // scheduled and recorded (the commit is part of the lean step)
+      } else if (rc == 0) {
         rc = schedule(sp, ev.phase, res);
         if (rc == 0) stat_add(ST_SCHEDULE, 1);  // Schedule calls that returned a result (a panic is not a decision)
       }
@@ -3548,8 +2970,18 @@ struct Core {
       int initPanic = 0;
       if (initLists) { initState(initLists, nPinnedOrder, initLists + nPinnedOrder, nBad); initPanic = panicCode; }
       if (!own) nOwn = n;
+      // the CTA's event indices travel through a 64-entry window in shared memory, refilled 32 at a time (lane =
+      // entry): the index of the next event is never a dependent global load on the leader's path
+      if (own) { for (int q = lane; q < 64 && q < nOwn; q += HIVED_WARPSZ) sm->own_win[q] = own[q]; }
+      ST(sm->bkc_sched, -1);
+      hv_warp_sync();
+      auto ownAt = [&](int kk) { return own ? sm->own_win[kk & 63] : kk; };
       for (int k = 0; k < nOwn; k++) {
-        int i = own ? own[k] : k;
+        if (own && k > 0 && (k & 31) == 0) {
+          for (int q = lane; q < 32; q += HIVED_WARPSZ) { const int idx = k + 32 + q; if (idx < nOwn) sm->own_win[idx & 63] = own[idx]; }
+          hv_warp_sync();
+        }
+        int i = ownAt(k);
         curEvent = i;
         sharedHeld = false;
         long long tq = pclock();
@@ -3562,16 +2994,16 @@ struct Core {
         hv_cp_async_wait();
         hv_warp_sync();
         if (k + 1 < nOwn) {
-          const char* nxt = reinterpret_cast<const char*>(&events[own ? own[k + 1] : k + 1]);
+          const char* nxt = reinterpret_cast<const char*>(&events[ownAt(k + 1)]);
           int32_t* dst = sm->ev_words[(k + 1) & 1];
           for (int q = lane; q < EVQ; q += HIVED_WARPSZ) hv_cp_async16(dst + 4 * q, nxt + 16 * q);
         }
-        if (k + 2 < nOwn) hv_prefetch(&events[own ? own[k + 2] : k + 2]);
+        if (k + 2 < nOwn) hv_prefetch(&events[ownAt(k + 2)]);
         dbg(14, tq);
         processEvent(*reinterpret_cast<const hived_event_t*>(cur), &results[i], suggPool, aux);
         tq = pclock();
         if (multi) {
-          int next = (k + 1 < nOwn) ? own[k + 1] : 0x7fffffff;
+          int next = (k + 1 < nOwn) ? ownAt(k + 1) : 0x7fffffff;
           // release: only an event that touched the cluster-wide state publishes anything another CTA may read
           // (free lists, counters, and the cells it put into them — with everything this CTA wrote to those
           // cells in earlier events, the fence being cumulative).  Other events move the progress word on with a

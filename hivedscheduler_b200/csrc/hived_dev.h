@@ -39,7 +39,7 @@ struct GroupMemFld {  // indexed by g * 8 + m like the flat arrays it replaces
   X(p_lvl_base) X(p_lvl_cnt) X(chain_in_vc) X(lt_off) X(lt_cnt) X(lt_chains)                           \
   X(vs_vc) X(vs_chain) X(vs_pinned) X(vs_top) X(v_lvl_base) X(v_lvl_cnt) X(vc_chain_vset)             \
   X(vc_pinned_vset) X(pre_off) X(pre_cnt) X(pre_list) X(vc_chain_counter) X(pin_pcell) X(pin_vcell)   \
-  X(pin_vc) X(s_off) X(s_n) X(s_cross) X(s_chain) X(s_virtual) X(s_maxleaf) X(s_level) X(s_vc) X(s_fast) X(vset_sched) X(opp_sched) \
+  X(pin_vc) X(s_off) X(s_n) X(s_cross) X(s_chain) X(s_virtual) X(s_maxleaf) X(s_level) X(s_vc) X(s_fast) X(s_cell0) X(s_leaf0) X(vset_sched) X(opp_sched) \
   X(ncl_off) X(ncl_cnt) X(ncl_list) X(fl_base) X(fl_cap) X(dm_base) X(dm_cap)
 
 // Y(name, count, init): mutable int32 array of `count` elements filled with `init`
@@ -120,7 +120,7 @@ enum {
   /* which path the events took (always counted; hived_bench_path_counters) */
   ST_PATH0 = 40, PC_FAST_VIEW = 0 /* scheduling passes answered by the bucketed view */, PC_GENERAL_VIEW = 1 /* full view passes */,
   PC_BK_REBUILD = 2, PC_BK_MOVERS = 3, PC_FAST_COMMIT = 4, PC_GENERAL_COMMIT = 5, PC_FAST_DELETE = 6, PC_GENERAL_DELETE = 7,
-  PC_FAST_MAP = 8, PC_GENERAL_MAP = 9, PC_COUNT = 12,
+  PC_FAST_MAP = 8, PC_GENERAL_MAP = 9, PC_POD_LEAN = 10, PC_COUNT = 12,
   ST_COUNT = 40 + PC_COUNT
 };
 

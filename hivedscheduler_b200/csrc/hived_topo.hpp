@@ -68,6 +68,7 @@ struct FlatTopo {
   // s_fast = 1 when every view cell is a virtual cell of that one level with the same number (<= 32) of leaf cells
   // laid out uniformly (the level-l cells below a view cell are aligned runs of chain_lvl_leafnum[l] leaves)
   std::vector<int32_t> s_level, s_vc, s_fast;
+  std::vector<int32_t> s_cell0, s_leaf0;  // fast views: the view cells are the ids s_cell0 + i, their leaves s_leaf0 + i * L + j
   std::vector<int32_t> cv_init;                                             // initial view order (cell ids)
   std::vector<int32_t> vset_sched, opp_sched;                               // [nVsets], [nChains]
   // ---- node -> leaves per chain (findPhysicalLeafCellInChain without the linear scan)
@@ -537,6 +538,12 @@ inline FlatTopo buildTopo(const std::string& text) {
         }
       }
     }
+    int32_t cell0 = n > 0 ? T.cv_init[off] : 0, leaf0 = (isVirtual && n > 0) ? T.v_leaf0[T.cv_init[off]] : 0;
+    for (int32_t i = 0; i < n && fast; i++)
+      if (T.cv_init[off + i] != cell0 + i || T.v_leaf0[cell0 + i] != leaf0 + i * maxleaf) fast = false;
+    for (int32_t l = 2; l <= T.chain_top[chain] && fast; l++)
+      if (T.chain_lvl_nchild[(size_t)chain * MAXL + l] > 32) fast = false;  // child masks are 32 bits wide
+    T.s_cell0.push_back(cell0); T.s_leaf0.push_back(leaf0);
     if (isVirtual && n > 0 && viewLevel < 0) viewLevel = T.v_level[T.cv_init[off]];
     T.s_level.push_back(viewLevel); T.s_vc.push_back(isVirtual ? vc : -1); T.s_fast.push_back(fast ? 1 : 0);
     return sid;

@@ -44,7 +44,7 @@ def emu_lib():
     os.makedirs(os.path.dirname(EMU_LIB), exist_ok=True)
     src = os.path.join(ROOT, "tests", "emu", "hived_emu.cpp")
     deps = [src] + [os.path.join(ROOT, "hivedscheduler_b200", "csrc", f)
-                    for f in os.listdir(os.path.join(ROOT, "hivedscheduler_b200", "csrc")) if f.endswith((".h", ".hpp"))]
+                    for f in os.listdir(os.path.join(ROOT, "hivedscheduler_b200", "csrc")) if f.endswith((".h", ".hpp", ".inc"))]
     if not os.path.exists(EMU_LIB) or any(os.path.getmtime(d) > os.path.getmtime(EMU_LIB) for d in deps):
         subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-o", EMU_LIB, src])
     return _cabi.load_library(EMU_LIB)
@@ -96,7 +96,7 @@ def simt_lib():
     src = os.path.join(ROOT, "tests", "emu", "hived_simt.cpp")
     deps = [src, os.path.join(ROOT, "tests", "emu", "simt_rt.h")] + [
         os.path.join(ROOT, "hivedscheduler_b200", "csrc", f)
-        for f in os.listdir(os.path.join(ROOT, "hivedscheduler_b200", "csrc")) if f.endswith((".h", ".hpp"))]
+        for f in os.listdir(os.path.join(ROOT, "hivedscheduler_b200", "csrc")) if f.endswith((".h", ".hpp", ".inc"))]
     if not os.path.exists(SIMT_LIB) or any(os.path.getmtime(d) > os.path.getmtime(SIMT_LIB) for d in deps):
         subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-o", SIMT_LIB, src])
     return _cabi.load_library(SIMT_LIB)
