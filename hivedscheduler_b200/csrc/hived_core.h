@@ -62,10 +62,12 @@ struct Sm {
       lw_pc0[MAXL], lw_pn[MAXL], lw_pin[MAXL];
   int lw_omaxv[MAXL], lw_omaxp[MAXL], lw_oflagv[MAXL], lw_oflagp[MAXL];
   int un_p[32], un_c[32], un_ls[32];   // planned units: physical cell, commit-time virtual cell, first bound level above
+  int un_pl0[32], un_vl0[32], un_node[32];  // ... their first physical / virtual leaf and the view node they will sit in
   int pl_anc[8][32], pl_bnd[8][32];    // planLeanMulti: path and bindings per (level, unit)
   int bkc_sched;              // the view whose bucket heads are cached below (-1: none)
   int bkc_head[BK_STRIDE];
   int own_win[64];            // window of the CTA's event-index list
+  int lead_k;                 // index (in the CTA's list) of the event the leader works on; 0x7fffffff when it is done
   // ---- written back at kernel exit
   int panic;
   long long pool_off;
@@ -984,6 +986,7 @@ struct Core {
   // the lean lane: incremental (bucketed) cluster view, gangs as units, plan / apply / release
   // ======================================================================================
 #include "hived_lean.inc"
+#include "hived_runahead.inc"
 
   // ======================================================================================
   // cluster-view pass: data-parallel over the CTA
@@ -1834,7 +1837,7 @@ struct Core {
         ok = ok && V >= 0 && d.p_state[L] == HIVED_CELL_USED && d.p_healthy[L] && d.p_prio[L] != OPP_PRIO && !(d.p_flags[L] & PF_PINNED_BIT);
         if (ok) {
           int pre = d.v_pre[V];
-          s.pl_v[i] = V; s.pl_v2[i] = pre; s.pl_p[i] = d.v_pcell[pre];
+          s.pl_v[i] = V; s.pl_v2[i] = pre; s.pl_p[i] = d.v_pcell[pre]; s.pl_p2[i] = L;
         }
       }
       if (hv_ballot(!ok)) bad = true;
@@ -1855,12 +1858,18 @@ struct Core {
       }
     }
     hv_warp_sync();
-    for (int l = 2; l < AS; l++) {
+    return releaseAbove(nl, 2, vc);
+  }
+  // The levels above a set of released ITEMS (s.pl_p2 / s.pl_v: the physical / virtual cell of item i — leaf cells
+  // for deleteGroupBatched, complete cells for leanDeleteMulti —, s.pl_v2 / s.pl_p: its preassigned cell, virtual /
+  // physical), from startLevel up, then the release of the preassigned cells that became unused.
+  HIVED_DEV bool releaseAbove(int nl, int startLevel, int vc) {
+    for (int l = startLevel; l < AS; l++) {
       bool changedAny = false;
       for (int b0 = 0; b0 < nl; b0 += HIVED_WARPSZ) {
         int i = b0 + lane;
         const bool act = i < nl;
-        const int L = act ? ph[i] : 0, V = act ? s.pl_v[i] : 0;
+        const int L = act ? s.pl_p2[i] : 0, V = act ? s.pl_v[i] : 0;
         const int va = act ? d.v_anc[V * AS + l] : -1, pa = act ? d.p_anc[L * AS + l] : -1;
         const int ceil = (act && multi) ? d.v_level[s.pl_v2[i]] : AS;
         const bool actV = va >= 0, actP = pa >= 0 && l <= ceil;
@@ -2942,6 +2951,7 @@ struct Core {
   // cell, recomputed bottom-up from their children (priority = max; state = Used iff a child is Used —
   // exact whenever no cell is Reserving/Reserved, which is what the host checks before going parallel).
   HIVED_DEV void repairSharedAncestors() {
+    if (hv_is_runahead()) return;  // (launched with the events kernel's geometry)
     for (int l = 2; l <= d.S.maxLevels; l++) {
       for (int chain = 0; chain < d.S.nChains; chain++) {
         int base = d.p_lvl_base[cl(chain, l)], cnt = d.p_lvl_cnt[cl(chain, l)];
@@ -2982,6 +2992,7 @@ struct Core {
           hv_warp_sync();
         }
         int i = ownAt(k);
+        if (lane == 0) hv_st_volatile(&sm->lead_k, k);
         curEvent = i;
         sharedHeld = false;
         long long tq = pclock();
@@ -3014,11 +3025,14 @@ struct Core {
         }
         dbg(15, tq);
       }
+      if (lane == 0) hv_st_volatile(&sm->lead_k, 0x7fffffff);
       flushWork();
       ST(sm->pool_off, poolOff);
       ST(sm->panic, initPanic);
       ST(sm->cmd, CMD_EXIT);
       hv_cta_sync();
+    } else if (hv_is_runahead()) {
+      if (!initLists) runAhead(events, n, own, nOwn);
     } else {
       while (true) {
         hv_cta_sync();

@@ -27,6 +27,7 @@ hived_events_kernel(const __grid_constant__ Dev dev, const hived_event_t* __rest
   if (threadIdx.x == 0) {
     sm.cmd = CMD_IDLE;
     sm.panic = 0;
+    sm.lead_k = -1;
     sm.pool_off = scalars[cta * 4 + 0];
   }
   __syncthreads();

@@ -22,6 +22,9 @@ inline int hv_tid() { return 0; }
 inline int hv_nth() { return 1; }
 inline int hv_warp() { return 0; }
 inline int hv_nwarps() { return 1; }
+inline bool hv_is_runahead() { return false; }
+inline void hv_nanosleep() {}
+inline void hv_touch(const void*) {}
 inline void hv_cta_sync() {}
 inline void hv_warp_sync() {}
 inline void hv_phase() {}
@@ -66,10 +69,16 @@ inline int hv_reduce_add(int v) { return v; }
 namespace hived {
 inline int hv_lane() { return simt::lane(); }
 inline int hv_tid() { return simt::tid(); }
-inline int hv_nth() { return simt::nth(); }
+// the last warp of a CTA with three or more warps is the run-ahead (prefetch) warp: it takes no part in the CTA-wide
+// passes, whose barrier spans the other warps only
+inline bool hv_has_runahead() { return simt::nth() >= 96; }
+inline int hv_nth() { return simt::nth() - (hv_has_runahead() ? 32 : 0); }
 inline int hv_warp() { return simt::warp(); }
-inline int hv_nwarps() { return simt::nth() / 32; }
-inline void hv_cta_sync() { simt::cta_barrier(); }
+inline int hv_nwarps() { return hv_nth() / 32; }
+inline bool hv_is_runahead() { return hv_has_runahead() && simt::warp() == hv_nwarps(); }
+inline void hv_nanosleep() { simt::yield_to_scheduler(); }
+inline void hv_touch(const void* p) { (void)*(const volatile char*)p; }
+inline void hv_cta_sync() { simt::cta_barrier_n(hv_nth()); }
 inline void hv_warp_sync() { simt::warp_collective(0, [](const int*, int*) {}); }
 // phase boundary: every lane has finished the reads of the phase before any lane starts the writes of the next one
 inline void hv_phase() { hv_warp_sync(); }
@@ -141,10 +150,16 @@ inline int hv_reduce_add(int x) {
 namespace hived {
 __device__ __forceinline__ int hv_lane() { return threadIdx.x & 31; }
 __device__ __forceinline__ int hv_tid() { return threadIdx.x; }
-__device__ __forceinline__ int hv_nth() { return blockDim.x; }
+// The last warp of the CTA is the run-ahead (prefetch) warp (hived_core.h: runAhead): it takes no part in the
+// CTA-wide passes, whose barrier (a named barrier) spans the other warps only.
+__device__ __forceinline__ int hv_nth() { return blockDim.x - 32; }
 __device__ __forceinline__ int hv_warp() { return threadIdx.x >> 5; }
-__device__ __forceinline__ int hv_nwarps() { return blockDim.x >> 5; }
-__device__ __forceinline__ void hv_cta_sync() { __syncthreads(); }
+__device__ __forceinline__ int hv_nwarps() { return (blockDim.x >> 5) - 1; }
+__device__ __forceinline__ bool hv_is_runahead() { return (threadIdx.x >> 5) == (blockDim.x >> 5) - 1; }
+__device__ __forceinline__ void hv_nanosleep() { __nanosleep(200); }
+// pull a line towards L1 without a register target
+__device__ __forceinline__ void hv_touch(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void hv_cta_sync() { asm volatile("bar.sync 1, %0;" ::"r"(blockDim.x - 32) : "memory"); }
 __device__ __forceinline__ void hv_warp_sync() { __syncwarp(); }
 // phase boundary of the leader warp's uniform code (all lanes read, then one or all lanes write the same locations).
 // The warp is converged there (uniform control flow, no divergent call in between), so the hardware executes the

@@ -29,6 +29,7 @@ int launchProgram(Engine& e, int n, bool withInit) {
   static Sm sm;
   memset(&sm, 0, sizeof sm);
   sm.pool_off = 0;
+  sm.lead_k = -1;
   Core core(e.dev, &sm, (int32_t*)e.dPool.p, withInit ? 0 : e.poolCapWords, 1);
   core.run((const hived_event_t*)e.dEvents.p, n, (hived_result_t*)e.dResults.p,
            e.hasSugg ? (const uint32_t*)e.dSugg.p : nullptr, e.hasAux ? (const int32_t*)e.dAux.p : nullptr,

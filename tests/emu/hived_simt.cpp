@@ -70,7 +70,7 @@ static void kernelEntry(void* p) {
     core.repairSharedAncestors();
     return;
   }
-  if (simt::tid() == 0) { sm.cmd = CMD_IDLE; sm.panic = 0; sm.pool_off = a.scal[cta * 4 + 0]; }
+  if (simt::tid() == 0) { sm.cmd = CMD_IDLE; sm.panic = 0; sm.lead_k = -1; sm.pool_off = a.scal[cta * 4 + 0]; }
   simt::cta_barrier();
   Core core(e.dev, &sm, (int32_t*)e.dPool.p, a.scal[cta * 4 + 1], a.C);
   const int32_t* own = a.C > 1 ? (const int32_t*)e.dOwn.p : nullptr;
@@ -84,7 +84,7 @@ static void kernelEntry(void* p) {
 
 int launchProgram(Engine& e, int n, bool withInit) {
   static int NT = 0;
-  if (!NT) { const char* env = getenv("HIVED_SIMT_NT"); NT = env ? atoi(env) : 64; if (NT < 32 || NT % 32 || NT > 32 * MAX_WARPS) NT = 64; }
+  if (!NT) { const char* env = getenv("HIVED_SIMT_NT"); NT = env ? atoi(env) : 96; if (NT < 32 || NT % 32 || NT > 32 * MAX_WARPS) NT = 96; }
   const int C = withInit ? 1 : e.launchCta;
   std::vector<Sm> sms(C);
   memset((void*)sms.data(), 0, sizeof(Sm) * C);

@@ -59,6 +59,8 @@ struct CtaState {
   unsigned gen = 0;
   int nThreads = 0;
   int finished = 0;
+  int arrivedN = 0;      // named barrier over the first n threads (bar.sync 1, n)
+  unsigned genN = 0;
 };
 
 struct Fiber {
@@ -165,6 +167,25 @@ inline void cta_barrier() {
     f->blocked = true; f->waitKind = 2;
     if (tracing()) f->nbt = backtrace(f->bt, 12);
     while (c.gen == g) yield_to_scheduler();
+  }
+}
+
+// bar.sync 1, n: the first n threads of the CTA (none of them has left the kernel while the others wait here)
+inline void cta_barrier_n(int n) {
+  Fiber* f = rt().cur;
+  CtaState& c = *f->c;
+  f->nBar++;
+  if (f->tid >= n) { fprintf(stderr, "simt: thread %d outside the named barrier of %d threads\n", f->tid, n); abort(); }
+  if (++c.arrivedN >= n) {
+    c.arrivedN = 0;
+    c.genN++;
+    Fiber* base = f - f->tid;
+    for (int i = 0; i < n; i++) base[i].blocked = false;
+  } else {
+    unsigned g = c.genN;
+    f->blocked = true; f->waitKind = 2;
+    if (tracing()) f->nbt = backtrace(f->bt, 12);
+    while (c.genN == g) yield_to_scheduler();
   }
 }
 
