@@ -45,12 +45,24 @@ inline int hv_atomic_min(int* a, int v) { int o = *a; if (v < o) *a = v; return 
 inline int hv_atomic_add(int* a, int v) { int o = *a; *a = o + v; return o; }
 inline void hv_red_max(int* a, int v) { if (v > *a) *a = v; }
 inline long long hv_clock() { return 0; }
+#ifdef HIVED_EMU_MT
+// several 1-lane CTAs on host threads (tests/emu/hived_emu_mt.cpp: the CPU comparator of bench.py): the ordered
+// shared sections between CTAs use the same progress protocol, with host atomics
+extern thread_local int hv_tls_cta;
+inline int hv_ld_volatile(const int* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+inline void hv_st_volatile(int* p, int v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+inline void hv_fence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+inline void hv_atomic_add64(long long* a, long long v) { __atomic_fetch_add(a, v, __ATOMIC_RELAXED); }
+inline void hv_atomic_or64(long long* a, long long v) { __atomic_fetch_or(a, v, __ATOMIC_RELAXED); }
+inline int hv_cta() { return hv_tls_cta; }
+#else
 inline int hv_ld_volatile(const int* p) { return *p; }
 inline void hv_st_volatile(int* p, int v) { *p = v; }
 inline void hv_fence() {}
 inline void hv_atomic_add64(long long* a, long long v) { *a += v; }
 inline void hv_atomic_or64(long long* a, long long v) { *a |= v; }
 inline int hv_cta() { return 0; }
+#endif
 inline void hv_prefetch(const void*) {}
 // asynchronous 16-byte global -> shared copies (host emulation: plain copy, nothing to wait for)
 inline void hv_cp_async16(void* smem, const void* gmem) { __builtin_memcpy(smem, gmem, 16); }
