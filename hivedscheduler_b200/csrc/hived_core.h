@@ -67,6 +67,9 @@ struct Sm {
   int bkc_sched;              // the view whose bucket heads are cached below (-1: none)
   int bkc_head[BK_STRIDE];
   int own_win[64];            // window of the CTA's event-index list
+  // the small scratch arrays of a decision that are read back right after they are written (a global store does not
+  // allocate in L1: reading it back is a round trip to L2) live here when the group sizes allow (LS <= 64, PS <= 16)
+  int32_t sc_pl_v[64], sc_pl_p[64], sc_pl_v2[64], sc_pl_p2[64], sc_pod_need[16], sc_pod_pos[16], sc_pod_cell[16], sc_pod_unit[16];
   int lead_k;                 // index (in the CTA's list) of the event the leader works on; 0x7fffffff when it is done
   // ---- written back at kernel exit
   int panic;
@@ -106,6 +109,10 @@ struct Core {
         s(dev.scratch[hv_cta()]), cta(hv_cta()), nCta(nCta_), multi(nCta_ > 1), curEvent(0), sharedHeld(false), prioMask(0) {
     for (int i = 0; i < N_WORK; i++) work[i] = 0;
     for (int i = 0; i < PC_COUNT; i++) pathCnt[i] = 0;
+    if (dev.S.LS <= 64 && dev.S.PS <= 16) {
+      s.pl_v = sm->sc_pl_v; s.pl_p = sm->sc_pl_p; s.pl_v2 = sm->sc_pl_v2; s.pl_p2 = sm->sc_pl_p2;
+      s.pod_need = sm->sc_pod_need; s.pod_pos = sm->sc_pod_pos; s.pod_cell = sm->sc_pod_cell; s.pod_unit = sm->sc_pod_unit;
+    }
   }
 
   // Multi-CTA ordering.  VCs are partitioned over the CTAs; an event only touches its VC's virtual
@@ -598,8 +605,17 @@ struct Core {
   // hived_algorithm.go:602-628 (VCs in ascending id order)
   HIVED_DEV_NOINLINE void tryBindDoomedBadCell(int chain, int l) {
     int k = cl(chain, l);
-    // no VC can be short of healthy cells while even the sum of their free cells fits (vcFree[vc] <= allVCFree)
-    if (d.allVCFree[k] <= d.totalLeft[k] - d.bf_len[k]) return;
+    // no VC is short of healthy cells (lane = VC: the largest vcFree decides; the sum allVCFree is no bound once a
+    // safety violation has driven some VC's count negative)
+    {
+      const int room = d.totalLeft[k] - d.bf_len[k];
+      int mx = -0x7fffffff;
+      for (int b = 0; b < d.S.nVCs; b += HIVED_WARPSZ) {
+        const int vc = b + lane;
+        if (vc < d.S.nVCs && d.vc_chain_counter[vc * d.S.nChains + chain]) { const int f = d.vcFree[vcl(vc, chain, l)]; if (f > mx) mx = f; }
+      }
+      if (hv_reduce_max(mx) <= room) return;
+    }
     for (int vc = 0; vc < d.S.nVCs; vc++) {
       if (!d.vc_chain_counter[vc * d.S.nChains + chain]) continue;
       int kv = vcl(vc, chain, l);
@@ -630,6 +646,7 @@ struct Core {
       while (d.dm_len[kv] != 0 && d.vcFree[kv] < d.totalLeft[k] - d.bf_len[k]) {
         if (++guard > d.S.NP) { panic(HIVED_ERR_PLATFORM); return; }
         int pc = d.dm_data[d.dm_base[kv] + 0];
+        if (d.p_vcell[pc] < 0) { panic(HIVED_ERR_PLATFORM); return; }  // nil virtual cell dereferenced in the reference (:643-646)
         unbindPair(pc, d.p_vcell[pc]);
         dm_remove(vc, chain, l, pc);
         ST(d.allVCDoomed[k], d.allVCDoomed[k] - 1);
@@ -818,10 +835,52 @@ struct Core {
   // ======================================================================================
   // leaf cell allocation / release (hived_algorithm.go:1292-1352)
   // ======================================================================================
+  // The reference keeps a map priority -> number of used leaf cells on every cell and updates it incrementally
+  // (cell_allocation.go:443-454): +1 at p in allocateLeafCell, -1 at the leaf's CURRENT priority in releaseLeafCell
+  // (hived_algorithm.go:1302-1317, 1329, 1350).  Here the counts are derived from the leaf priorities, which is the
+  // same thing as long as every allocation meets a free leaf and every release a used one.  The reference's own call
+  // sequences break that in two ways, and its counters then drift for good (nothing ever repairs them):
+  //   * allocateLeafCell on a leaf that still has a priority o (a bind that lands on Reserved cells while their
+  //     preemptor is alive; cells re-allocated around lazy preemption): the entry at o is never decremented;
+  //   * releaseLeafCell on a leaf whose priority is already FREE (a gang lazy-preempted on a bad node keeps its
+  //     bindings, :1332-1335, and is released again when deleted): the entry at freePriority goes negative.
+  // The cluster views sort and fit on those counters (topology_aware_scheduler.go:138-154), so the differences are
+  // kept — (priority, difference) pairs on the leaf and all its ancestors — and added to the derived counts of a
+  // view whose s_anom is non-zero (viewNodeInfo); such a view leaves the bucketed form for good.
+  template <bool V>
+  HIVED_DEV_NOINLINE void noteDelta(int leaf, int prio, int delta) {
+    int32_t* dprio = V ? d.v_dprio : d.p_dprio;
+    int32_t* dcnt = V ? d.v_dcnt : d.p_dcnt;
+    const int32_t* anc = V ? d.v_anc : d.p_anc;
+    hv_phase();
+    bool full = false;
+    for (int b = 0; b < AS; b += HIVED_WARPSZ) {
+      int l = b + lane;
+      if (l < AS) {
+        int a = anc[leaf * AS + l];
+        if (a >= 0) {
+          int slot = -1;
+          for (int i = 0; i < DELTA_SLOTS; i++) if (dprio[a * DELTA_SLOTS + i] == prio) slot = i;
+          if (slot < 0) for (int i = DELTA_SLOTS - 1; i >= 0; i--) if (dprio[a * DELTA_SLOTS + i] == DELTA_EMPTY) slot = i;
+          if (slot < 0) full = true;
+          else { dprio[a * DELTA_SLOTS + slot] = prio; dcnt[a * DELTA_SLOTS + slot] += delta; }
+        }
+      }
+    }
+    if (hv_ballot(full)) { panic(HIVED_ERR_CAPACITY); return; }
+    hv_warp_sync();
+    int sched = -1;
+    if (V) sched = schedOfVirtual(leaf);
+    else { const int chain = d.p_chain[leaf]; sched = chain >= 0 ? d.opp_sched[chain] : -1; }
+    if (sched >= 0) ST(d.s_anom[sched], d.s_anom[sched] + 1);
+    if (V) bkMarkLeaf(leaf);
+  }
   HIVED_DEV_NOINLINE bool allocateLeafCell(int pLeaf, int vLeaf, int p, int vc) {
     bool safetyOk = true;
     stat_add(ST_LEAVES, 1);
     if (vLeaf >= 0) {
+      if (d.v_prio[vLeaf] != FREE_PRIO) noteDelta<true>(vLeaf, d.v_prio[vLeaf], 1);   // the old entry stays in the reference's map
+      if (d.p_prio[pLeaf] != FREE_PRIO) noteDelta<false>(pLeaf, d.p_prio[pLeaf], 1);
       setPriority<true>(vLeaf, p);
       setPriority<false>(pLeaf, p, ceilOf(vLeaf));
       if (p == OPP_PRIO) updateUsedOpp(pLeaf, 1);
@@ -830,6 +889,7 @@ struct Core {
       if (d.p_vcell[pLeaf] < 0) bindCell(pLeaf, vLeaf);
       if (newlyBound) safetyOk = allocatePreassignedCell(d.v_pcell[pac], vc, false);
     } else {
+      if (d.p_prio[pLeaf] != FREE_PRIO) noteDelta<false>(pLeaf, d.p_prio[pLeaf], 1);
       setPriority<false>(pLeaf, OPP_PRIO);
       updateUsedOpp(pLeaf, 1);
     }
@@ -840,14 +900,17 @@ struct Core {
     int vLeaf = d.p_vcell[pLeaf];
     const int ceil = ceilOf(vLeaf);
     if (vLeaf >= 0) {
+      if (d.v_prio[vLeaf] == FREE_PRIO) noteDelta<true>(vLeaf, FREE_PRIO, -1);  // decremented at the free priority in the reference
       setPriority<true>(vLeaf, FREE_PRIO);
       int pre = d.v_pre[vLeaf];
       int preassignedPhysical = d.v_pcell[pre];
+      if (preassignedPhysical < 0) { panic(HIVED_ERR_PLATFORM); return; }  // nil dereference in the reference (hived_algorithm.go:1343)
       if (d.p_healthy[pLeaf]) unbindCell(pLeaf);
       if (!(d.p_flags[preassignedPhysical] & PF_PINNED_BIT) && d.v_prio[pre] < 0 && !dm_contains(vc, preassignedPhysical))
         releasePreassignedCell(preassignedPhysical, vc, false);
     }
     if (d.p_prio[pLeaf] == OPP_PRIO) updateUsedOpp(pLeaf, -1);
+    if (d.p_prio[pLeaf] == FREE_PRIO) noteDelta<false>(pLeaf, FREE_PRIO, -1);
     setPriority<false>(pLeaf, FREE_PRIO, ceil);
   }
 
@@ -860,7 +923,7 @@ struct Core {
   //    one gather over the levels (lane = level) instead of five dependent walks.
   HIVED_DEV_NOINLINE bool commitLeaf(int pLeaf, int vLeaf, int p, int vc, int g) {
     const int ceil = ceilOf(vLeaf);
-    bool fast = vLeaf >= 0 && p != OPP_PRIO && p > d.v_prio[vLeaf] && p > d.p_prio[pLeaf] && d.v_pcell[d.v_pre[vLeaf]] >= 0;
+    bool fast = vLeaf >= 0 && p > OPP_PRIO && d.v_prio[vLeaf] == FREE_PRIO && d.p_prio[pLeaf] == FREE_PRIO && d.v_pcell[d.v_pre[vLeaf]] >= 0;
     if (!fast) {
       bool safetyOk = allocateLeafCell(pLeaf, vLeaf, p, vc);
       ST(d.p_using[pLeaf], g);
@@ -901,7 +964,7 @@ struct Core {
   HIVED_DEV_NOINLINE void releaseLeafAndFree(int pLeaf, int vc) {
     int vLeaf = d.p_vcell[pLeaf];
     const int ceil = ceilOf(vLeaf);
-    if (vLeaf < 0 || !d.p_healthy[pLeaf] || d.p_prio[pLeaf] == OPP_PRIO) {
+    if (vLeaf < 0 || !d.p_healthy[pLeaf] || d.p_prio[pLeaf] < 0 || d.v_prio[vLeaf] == FREE_PRIO) {
       releaseLeafCell(pLeaf, vc);
       setCellState(pLeaf, HIVED_CELL_FREE, ceil);
       return;
@@ -910,6 +973,7 @@ struct Core {
     bkMarkLeaf(vLeaf);
     const int pre = d.v_pre[vLeaf];
     const int preP = d.v_pcell[pre];
+    if (preP < 0) { panic(HIVED_ERR_PLATFORM); return; }  // nil dereference in the reference (hived_algorithm.go:1343)
     int vOrig = d.v_prio[vLeaf], vNew = FREE_PRIO;
     int pOrig = d.p_prio[pLeaf], pNew = FREE_PRIO;
     bool wU = !(d.p_flags[pLeaf] & PF_PINNED_BIT);
@@ -993,7 +1057,7 @@ struct Core {
   //   updateClusterView + sort.Stable + findNodesForPods (topology_aware_scheduler.go:231-306)
   // ======================================================================================
   // info word of a view node: free(8b) | usedSame(8b)<<8 | usedHigher(8b)<<16 | healthy<<24 | suggested<<25
-  HIVED_DEV int viewNodeInfo(int cell, bool isVirtual, bool cross, int p, bool ignoreSuggested) const {
+  HIVED_DEV int viewNodeInfo(int cell, bool isVirtual, bool cross, int p, bool ignoreSuggested, bool anomalous) const {
     int leaf0, nleaf, healthy = 1, suggested = 1;
     const int32_t* prio;
     if (isVirtual) {
@@ -1014,13 +1078,26 @@ struct Core {
       if (q >= p) ge++;
     }
     int free = nleaf - ge;
-    return (free & 255) | (same << 8) | (higher << 16) | (healthy << 24) | (suggested << 25);
+    if (anomalous) {  // add what the reference's counters hold beyond the leaf priorities (noteDelta)
+      const int32_t* dprio = isVirtual ? d.v_dprio : d.p_dprio;
+      const int32_t* dcnt = isVirtual ? d.v_dcnt : d.p_dcnt;
+      for (int i = 0; i < DELTA_SLOTS; i++) {
+        const int q = dprio[cell * DELTA_SLOTS + i], c = dcnt[cell * DELTA_SLOTS + i];
+        if (q == DELTA_EMPTY || c == 0) continue;
+        if (q == p) same += c;
+        else if (cross) same += c;
+        else if (q > p) higher += c;
+        if (q >= p) free -= c;
+      }
+    }
+    // free, same, higher: 9 bits each, biased by 128 (the reference's counters may be negative or exceed the leaf count)
+    return ((free + 128) & 511) | (((same + 128) & 511) << 9) | (((higher + 128) & 511) << 18) | (healthy << 27) | (suggested << 28);
   }
-  HIVED_DEV static int infoFree(int w) { return w & 255; }
-  HIVED_DEV static int infoSame(int w) { return (w >> 8) & 255; }
-  HIVED_DEV static int infoHigher(int w) { return (w >> 16) & 255; }
-  HIVED_DEV static int infoHealthy(int w) { return (w >> 24) & 1; }
-  HIVED_DEV static int infoSuggested(int w) { return (w >> 25) & 1; }
+  HIVED_DEV static int infoFree(int w) { return (w & 511) - 128; }
+  HIVED_DEV static int infoSame(int w) { return ((w >> 9) & 511) - 128; }
+  HIVED_DEV static int infoHigher(int w) { return ((w >> 18) & 511) - 128; }
+  HIVED_DEV static int infoHealthy(int w) { return (w >> 27) & 1; }
+  HIVED_DEV static int infoSuggested(int w) { return (w >> 28) & 1; }
 
   // CTA-wide exclusive prefix sum of sm->cnt[0..n) (row-major: bin-major, warp-minor)
   HIVED_DEV void ctaExclusiveScan(int n) {
@@ -1109,26 +1186,47 @@ struct Core {
     // 1. per-node keys from leaf priorities (coalesced int32 loads of contiguous leaf ranges); the counters of the
     //    first sorting pass are cleared under the same barrier
     const int W = hv_nwarps();
+    const bool anomalous = d.s_anom[sched] != 0;
     const int firstBins = cross ? 4 * (L + 1) : L + 1;
     for (int i = tid; i < firstBins * W; i += nth) sm->cnt[i] = 0;
     for (int i = tid; i < n; i += nth) {
       int cell = d.cv[off + i];
       s.vw_cell[i] = cell;
-      s.vw_info[i] = viewNodeInfo(cell, isVirtual, cross, p, ignoreSuggested);
+      s.vw_info[i] = viewNodeInfo(cell, isVirtual, cross, p, ignoreSuggested, anomalous);
       s.vw_ordA[i] = i;
     }
     hv_cta_sync();
     // 2. stable sort by (healthy desc, suggested desc, usedSame desc, usedHigher asc): LSD passes.  The last pass also
     // 3. persists the new order (the reference sorts its slice in place) and lays the infos out in order.
-    int32_t* cur = s.vw_ordA;
-    int32_t* nxt = s.vw_ordB;
-    if (!cross) {
-      stablePass(cur, nxt, n, L + 1, [](int w) { return infoHigher(w); }, true, nullptr);
-      int32_t* t = cur; cur = nxt; nxt = t;
+    if (anomalous) {
+      // keys outside [0, L] (noteDelta): a stable insertion sort on the full keys by one thread — the order is the
+      // persisted one from the last pass, so it is nearly sorted already
+      if (tid == 0) {
+        auto key = [&](int w) {
+          return ((long long)((1 - infoHealthy(w)) * 2 + (1 - infoSuggested(w))) << 40) | ((long long)(512 - infoSame(w)) << 20) |
+                 (long long)(infoHigher(w) + 128);
+        };
+        for (int i = 1; i < n; i++) {
+          const int idx = s.vw_ordA[i];
+          const long long k = key(s.vw_info[idx]);
+          int j = i - 1;
+          while (j >= 0 && key(s.vw_info[s.vw_ordA[j]]) > k) { s.vw_ordA[j + 1] = s.vw_ordA[j]; j--; }
+          s.vw_ordA[j + 1] = idx;
+        }
+        for (int i = 0; i < n; i++) { const int src = s.vw_ordA[i]; d.cv[off + i] = s.vw_cell[src]; s.vw_sinfo[i] = s.vw_info[src]; }
+      }
+      hv_cta_sync();
+    } else {
+      int32_t* cur = s.vw_ordA;
+      int32_t* nxt = s.vw_ordB;
+      if (!cross) {
+        stablePass(cur, nxt, n, L + 1, [](int w) { return infoHigher(w); }, true, nullptr);
+        int32_t* t = cur; cur = nxt; nxt = t;
+      }
+      stablePass(cur, nxt, n, 4 * (L + 1), [L](int w) {
+        return ((1 - infoHealthy(w)) * 2 + (1 - infoSuggested(w))) * (L + 1) + (L - infoSame(w));
+      }, cross, d.cv + off);
     }
-    stablePass(cur, nxt, n, 4 * (L + 1), [L](int w) {
-      return ((1 - infoHealthy(w)) * 2 + (1 - infoSuggested(w))) * (L + 1) + (L - infoSame(w));
-    }, cross, d.cv + off);
     const int32_t* sinfo = s.vw_sinfo;
     // 4. greedy first-fit (findNodesForPods :278-305); every thread tracks the same scalar state
     int nodeIndex = 0, picked = 0, ok = 1, reason = 0, rcell = -1;
@@ -1834,16 +1932,22 @@ struct Core {
         int L = ph[i];
         ok = L >= 0;
         int V = ok ? d.p_vcell[L] : -1;
-        ok = ok && V >= 0 && d.p_state[L] == HIVED_CELL_USED && d.p_healthy[L] && d.p_prio[L] != OPP_PRIO && !(d.p_flags[L] & PF_PINNED_BIT);
+        ok = ok && V >= 0 && d.p_state[L] == HIVED_CELL_USED && d.p_healthy[L] && d.p_prio[L] >= 0 && !(d.p_flags[L] & PF_PINNED_BIT);
+        ok = ok && d.v_prio[V] != FREE_PRIO;
         if (ok) {
           int pre = d.v_pre[V];
           s.pl_v[i] = V; s.pl_v2[i] = pre; s.pl_p[i] = d.v_pcell[pre]; s.pl_p2[i] = L;
+          ok = s.pl_p[i] >= 0;  // (an unbound preassigned cell above a bound leaf: the per-leaf code reports the reference's panic)
         }
       }
       if (hv_ballot(!ok)) bad = true;
     }
     if (bad) return false;
     hv_warp_sync();
+    // With bad cells around, releasing one preassigned cell can re-bind doomed bad cells (tryBind/tryUnbindDoomedBadCell)
+    // and so change the binding of ANOTHER preassigned cell that later leaves of the gang sit in: the sequential
+    // order then matters.  One preassigned cell for the whole gang, or no bad node at all, rules that out.
+    if (d.nbad[0] != 0 && firstIdx(nl, [&](int i) { return s.pl_v2[i] != s.pl_v2[0]; }) >= 0) return false;
     stat_add(ST_LEAVES, nl);
     // level 1: the leaves themselves (releaseLeafCell :1319-1352 + setCellState Free)
     for (int b0 = 0; b0 < nl; b0 += HIVED_WARPSZ) {
@@ -2510,7 +2614,7 @@ struct Core {
           if (t != -1) for (int l = 1; l <= top; l++) if (d.chain_lvl_type[cl(chain, l)] == t) preLevel = l;
         }
         ok = L >= 0 && preLevel >= 1;
-        ok = ok && d.p_chain[L] == chain && d.p_prio[L] < p;
+        ok = ok && d.p_chain[L] == chain && d.p_prio[L] == FREE_PRIO;
         if (ok) {
           // first level whose ancestor is bound, or the preassigned level, or past the top (mapPhysicalCellToVirtual):
           // all levels loaded at once (no early exit, so the loads overlap), then a bit scan
@@ -2524,7 +2628,7 @@ struct Core {
           }
           ls = stop ? hv_ffs(stop) - 1 : AS;
           ok = ls < AS && ((bound >> ls) & 1u);
-          if (ok && ls == 1) ok = d.v_prio[d.p_vcell[L]] < p;
+          if (ok && ls == 1) ok = d.v_prio[d.p_vcell[L]] == FREE_PRIO;
           s.pl_v2[i] = ls;
         }
       }

@@ -17,6 +17,8 @@ namespace hived {
 // a while: one L2 round trip instead of eight).  Word layout: 0 state, 1 vc, 2 priority, 3 flags,
 // 4 #members, 5 #preempting pods, 8..15 member leaf numbers, 16..23 member pod numbers.
 constexpr int GROUP_HDR_WORDS = 32;
+constexpr int DELTA_SLOTS = 4;          // (priority, difference) pairs per cell, see noteDelta
+constexpr int DELTA_EMPTY = -1000000;
 constexpr int BK_STRIDE = 33;  // buckets of a bucketed cluster view: used-leaf counts 0..32
 template <int OFF>
 struct GroupFld {
@@ -64,7 +66,11 @@ struct GroupMemFld {  // indexed by g * 8 + m like the flat arrays it replaces
   Y(bk_tail, S.nScheds * BK_STRIDE, -1) Y(bk_cnt, S.nScheds * BK_STRIDE, 0)                            \
   Y(bk_hseq, S.nScheds * BK_STRIDE, -1) Y(bk_tseq, S.nScheds * BK_STRIDE, 0)                           \
   Y(vn_next, S.NV, -1) Y(vn_prev, S.NV, -1) Y(vn_seq, S.NV, 0) Y(vn_u, S.NV, 0) Y(vn_dirty, S.NV, 0)   \
-  Y(bk_dl, S.cvTotal, -1) Y(nbad, 4, 0)
+  Y(bk_dl, S.cvTotal, -1) Y(nbad, 4, 0)                                                                \
+  /* where the reference's incremental used-leaf counters differ from the leaf priorities (hived_core.h noteDelta): */ \
+  /* up to DELTA_SLOTS (priority, difference) pairs per cell; s_anom counts the anomalies of a view                  */ \
+  Y(v_dprio, S.NV * DELTA_SLOTS, DELTA_EMPTY) Y(v_dcnt, S.NV * DELTA_SLOTS, 0)                         \
+  Y(p_dprio, S.NP * DELTA_SLOTS, DELTA_EMPTY) Y(p_dcnt, S.NP * DELTA_SLOTS, 0) Y(s_anom, S.nScheds, 0)
 
 // Z(name, count): scratch of one scheduling decision — one private copy per CTA (struct Scratch)
 #define HIVED_SCRATCH_ARRAYS(Z)                                                                        \

@@ -715,6 +715,36 @@ int hived_bench_path_counters(hived_ctx* ctx, int64_t* out) {
   for (int i = 0; i < hived::PC_COUNT; i++) out[i] = st[hived::ST_PATH0 + i];
   return hived::PC_COUNT;
 }
+/* test hook: a hash of every cluster view's persisted order (cell addresses in order; order-independent across views).
+   The order is state that no result shows until a tie is broken by it. */
+uint64_t hived_debug_view_hash(hived_ctx* ctx) {
+  hived::Engine& e = ctx->e;
+  const hived::FlatTopo& T = e.T;
+  std::vector<int32_t> cv, valid, head, cnt, next;
+  e.readArray(e.dev.cv, cv, T.cv_init.size());
+  e.readArray(e.dev.bk_valid, valid, T.nScheds);
+  e.readArray(e.dev.bk_head, head, (size_t)T.nScheds * hived::BK_STRIDE);
+  e.readArray(e.dev.bk_cnt, cnt, (size_t)T.nScheds * hived::BK_STRIDE);
+  e.readArray(e.dev.vn_next, next, T.NV);
+  uint64_t total = 0;
+  for (int s = 0; s < T.nScheds; s++) {
+    std::vector<int32_t> order;
+    if (valid[s]) {
+      for (int u = T.s_maxleaf[s]; u >= 0; u--)
+        for (int x = head[(size_t)s * hived::BK_STRIDE + u]; x >= 0; x = next[x]) order.push_back(x);
+    } else {
+      for (int i = 0; i < T.s_n[s]; i++) order.push_back(cv[T.s_off[s] + i]);
+    }
+    uint64_t h = HIVED_FNV_OFFSET;
+    for (int32_t c : order) {
+      const std::string& a = T.s_virtual[s] ? T.vAddr[c] : T.pAddr[c];
+      for (char ch : a) { h ^= (uint8_t)ch; h *= HIVED_FNV_PRIME; }
+      h ^= 0xff; h *= HIVED_FNV_PRIME;
+    }
+    total += h;
+  }
+  return total;
+}
 double hived_bench_last_kernel_ms(hived_ctx* ctx) { return ctx->e.lastKernelMs; }
 double hived_bench_total_kernel_ms(hived_ctx* ctx) { return ctx->e.kernelMsTotal; }
 int64_t hived_bench_kernel_launches(hived_ctx* ctx) { return ctx->e.kernelLaunches; }

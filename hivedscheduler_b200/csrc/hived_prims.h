@@ -170,7 +170,12 @@ __device__ __forceinline__ int hv_nwarps() { return (blockDim.x >> 5) - 1; }
 __device__ __forceinline__ bool hv_is_runahead() { return (threadIdx.x >> 5) == (blockDim.x >> 5) - 1; }
 __device__ __forceinline__ void hv_nanosleep() { __nanosleep(200); }
 // pull a line towards L1 without a register target
-__device__ __forceinline__ void hv_touch(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void hv_touch(const void* p) {
+  // an ordinary cached load whose result nobody waits for: unlike prefetch.global.L1 (a hint), it is certain to
+  // allocate the line in L1
+  unsigned t;
+  asm volatile("ld.global.ca.u32 %0, [%1];" : "=r"(t) : "l"(p));
+}
 __device__ __forceinline__ void hv_cta_sync() { asm volatile("bar.sync 1, %0;" ::"r"(blockDim.x - 32) : "memory"); }
 __device__ __forceinline__ void hv_warp_sync() { __syncwarp(); }
 // phase boundary of the leader warp's uniform code (all lanes read, then one or all lanes write the same locations).

@@ -542,6 +542,7 @@ HivedAlgorithm::HivedAlgorithm(const std::string& specText) { parseConfig(specTe
 
 HivedAlgorithm::~HivedAlgorithm() {
   for (auto& kv : affinityGroups) delete kv.second;
+  for (Group* g : deletedGroups) delete g;
   for (auto& kv : pods) delete kv.second;
 }
 
@@ -754,6 +755,8 @@ void HivedAlgorithm::tryUnbindDoomedBadCell(const std::string& c, int32_t l) {
     while (!vcDoomedBadCells[vcName][c].at(l).empty() &&
            mapGet(vcFreeNumC, l) < mapGet(totalLeftCellNum[c], l) - (int32_t)badFreeCells[c].at(l).size()) {
       Cell* pc = vcDoomedBadCells[vcName][c].at(l)[0];
+      // (pc.GetVirtualCell().GetAddress() / .SetPhysicalCell(nil) on a nil virtual cell: a Go panic in the reference)
+      if (pc->virtualCell == nullptr) throw Panic("runtime error: invalid memory address or nil pointer dereference (doomed bad cell is not bound)");
       SetPhysicalCell(pc->virtualCell, nullptr);
       SetVirtualCell(pc, nullptr);
       listRemove(vcDoomedBadCells[vcName][c].mut(l), pc);
@@ -1970,7 +1973,7 @@ void HivedAlgorithm::deleteAllocatedAffinityGroup(Group* g) {
         }
       }
   affinityGroups.erase(g->name);
-  delete g;
+  deletedGroups.push_back(g);  // Go's GC keeps a deleted group alive while a cell still points to it (a stale usingGroup is READ by the reference)
 }
 
 // hived_algorithm.go:1072-1112
@@ -2024,7 +2027,7 @@ void HivedAlgorithm::deletePreemptingAffinityGroup(Group* g) {
         }
       }
   affinityGroups.erase(g->name);
-  delete g;
+  deletedGroups.push_back(g);  // Go's GC keeps a deleted group alive while a cell still points to it (a stale usingGroup is READ by the reference)
 }
 
 // hived_algorithm.go:1147-1163
@@ -2156,6 +2159,9 @@ void HivedAlgorithm::releaseLeafCell(Cell* pLeafCell, const std::string& vcn) {
     updateUsedLeafCellNumAtPriority(vLeafCell, vLeafCell->priority, false);
     setCellPriority(vLeafCell, freePriority);
     Cell* preassignedPhysical = vLeafCell->preassignedCell->physicalCell;
+    // (nil when health churn left the preassigned cell unbound above a bound leaf: IsPinned() on it is a nil-pointer
+    // dereference in the reference, i.e. a Go panic = platform error)
+    if (preassignedPhysical == nullptr) throw Panic("runtime error: invalid memory address or nil pointer dereference (preassigned cell is not bound)");
     if (pLeafCell->healthy) unbindCell(pLeafCell);
     if (!preassignedPhysical->pinned && vLeafCell->preassignedCell->priority < minGuaranteedPriority &&
         !listContains(vcDoomedBadCells[vcn][preassignedPhysical->chain].at(preassignedPhysical->level), preassignedPhysical)) {

@@ -248,6 +248,7 @@ class HivedAlgorithm {
   std::map<std::string, ChainCellList> fullCellList;
   std::map<std::string, ChainCellList> freeCellList;
   std::unordered_map<std::string, Group*> affinityGroups;
+  std::vector<Group*> deletedGroups;  // freed with the algorithm object (see deleteAllocatedAffinityGroup)
   std::map<std::string, std::map<std::string, std::map<int32_t, int32_t>>> vcFreeCellNum;
   std::map<std::string, std::map<int32_t, int32_t>> allVCFreeCellNum;
   std::map<std::string, std::map<int32_t, int32_t>> totalLeftCellNum;

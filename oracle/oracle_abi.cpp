@@ -528,4 +528,23 @@ int hived_get_stats(hived_ctx* ctx, hived_stats_t* out) {
 
 uint64_t hived_result_hash(hived_ctx* ctx) { return ctx->hash; }
 
+/* test hook (same definition as the device library's): a hash of every cluster view's persisted order */
+uint64_t hived_debug_view_hash(hived_ctx* ctx) {
+  uint64_t total = 0;
+  auto one = [&](const TopologyAwareScheduler* t) {
+    uint64_t h = HIVED_FNV_OFFSET;
+    for (const Node* n : t->cv) {
+      for (char ch : n->c->address) { h ^= (uint8_t)ch; h *= HIVED_FNV_PRIME; }
+      h ^= 0xff; h *= HIVED_FNV_PRIME;
+    }
+    total += h;
+  };
+  for (auto& kv : ctx->h->vcSchedulers) {
+    for (auto& s : kv.second->nonPinnedCellSchedulers) one(s.second);
+    for (auto& s : kv.second->pinnedCellSchedulers) one(s.second);
+  }
+  for (auto& s : ctx->h->opportunisticSchedulers) one(s.second);
+  return total;
+}
+
 }  // extern "C"
