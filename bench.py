@@ -119,6 +119,72 @@ def cpu_baseline(t, n_decisions: int, chunk_start: int = 0, ctx_holder=None):
     return n_decisions / dt, dt, len(ev)
 
 
+def cpu_flat(t, max_threads: int = 8):
+    """The DEVICE PROGRAM itself compiled for the host (-O2, tests/emu/hived_emu_mt.cpp): what the flat data structures
+    and the algorithmic work of this repo give on CPU cores — 1 thread, and one thread per group of VCs with the same
+    ordered shared sections as on the GPU.  Kernel-only time (events staged, results not fetched), like ``value``."""
+    import __graft_entry__ as g
+    lib = _cabi.load_library(g.build_cpu_flat())
+    bind_bench_hooks(lib)
+    ev = t["events"]
+    n_dec = int(t["decision"].sum())
+    pw = trace.pool_words_for(t)
+    evp = ev.ctypes.data_as(C.POINTER(_cabi.Event))
+    out = {"unit": "decisions/s", "what": "the device program compiled for the host (g++ -O2), 1-lane CTAs on host threads; "
+                                          "kernel-only time over the whole C3 trace, best of 3"}
+    nthreads = max(1, min(max_threads, os.cpu_count() or 1))
+    for key, ncta in (("threads_1", 1), ("threads_n", nthreads)):
+        os.environ["HIVED_NCTA"] = str(ncta)
+        bc = trace.BatchContext(lib, t["config"], t["n_groups"], t["n_pods"], t["max_group_leaves"], t["max_group_pods"])
+        bc.set_all_nodes_healthy()
+        lib.hived_bench_save_state(bc.ctx)
+        res, pool = bc.process(ev, pw)  # one pass through the ABI for the parity hash
+        h = bc.result_hash()
+        lib.hived_bench_stage_events(bc.ctx, evp, len(ev), pw)
+        best = None
+        for _ in range(3):
+            lib.hived_bench_restore_state(bc.ctx)
+            t0 = time.perf_counter()
+            rc = lib.hived_bench_run_staged(bc.ctx)
+            dt = time.perf_counter() - t0
+            assert rc == 0, rc
+            best = dt if best is None else min(best, dt)
+        out[key] = {"value": n_dec / best, "threads": lib.hived_bench_num_ctas(bc.ctx), "seconds": best, "result_hash": "%016x" % h}
+        bc.close()
+    os.environ.pop("HIVED_NCTA", None)
+    return out
+
+
+def other_configs(lib):
+    """BASELINE's other configurations on the GPU, end to end through the C ABI from host buffers, each checked against
+    the oracle's committed hash (tests/golden/trace_hashes.json): C2 and C5 as one batch, C4 call by call (its event
+    stream depends on the decisions: the harness plays kube-scheduler)."""
+    golden = json.load(open(os.path.join(ROOT, "tests", "golden", "trace_hashes.json")))
+    out = {}
+    t = trace.trace_c2()
+    bc = trace.BatchContext(lib, t["config"], t["n_groups"], t["n_pods"], t["max_group_leaves"], t["max_group_pods"])
+    bc.set_all_nodes_healthy()
+    t0 = time.perf_counter(); bc.process(t["events"], 3 * 8 * len(t["events"]) + 4096); dt = time.perf_counter() - t0
+    out["C2"] = {"decisions_per_s": len(t["events"]) / dt, "seconds_e2e": dt, "result_hash": "%016x" % bc.result_hash(),
+                 "matches_oracle": "%016x" % bc.result_hash() == golden["C2"]["checkpoints"][-1]["hash"]}
+    bc.close()
+    t = trace.trace_c5()
+    bc = trace.BatchContext(lib, t["config"], t["n_groups"], t["n_pods"], t["max_group_leaves"], t["max_group_pods"])
+    bc.set_all_nodes_healthy()
+    t0 = time.perf_counter(); bc.process(t["events"], 3 * 64 * len(t["events"]) + 4096); dt = time.perf_counter() - t0
+    out["C5"] = {"gangs_per_s": int(t["decision"].sum()) / dt, "seconds_e2e": dt, "events": int(len(t["events"])),
+                 "result_hash": "%016x" % bc.result_hash(),
+                 "matches_oracle": "%016x" % bc.result_hash() == golden["C5"]["checkpoints"][-1]["hash"]}
+    bc.close()
+    from importlib import util
+    spec = util.spec_from_file_location("mth", os.path.join(ROOT, "tests", "golden", "make_trace_hashes.py"))
+    mth = util.module_from_spec(spec); spec.loader.exec_module(mth)
+    t0 = time.perf_counter(); h, log, st = trace.run_c4_interactive(lib, **mth.c4_kwargs(100000)); dt = time.perf_counter() - t0
+    out["C4"] = {"gangs_per_s": 100000 / dt, "seconds_wall_incl_python_harness": dt, "schedule_calls": int(st["schedule_events"]),
+                 "result_hash": "%016x" % h, "matches_oracle": "%016x" % h == golden.get("C4", {}).get("hash")}
+    return out
+
+
 def run_reference_arm(args):
     rank, world, _ = dist_env()
     if rank != 0:
@@ -157,6 +223,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--gangs", type=int, default=100000, help="C3 trace length (BASELINE: 100000)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the C2 / C4 / C5 sub-lines (about 45 s)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -308,6 +375,10 @@ def main():
             v, dt, nev = cpu_baseline(t, 1500)
             line["cpu_baseline"] = {"value": v, "unit": "decisions/s", "cores": 1, "kind": "port",
                                     "sample": "first 1500 decisions (%d events) of the same C3 trace, %.1f s" % (nev, dt)}
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_flat"] = cpu_flat(t)
+        if not args.no_other_configs and world == 1 and args.gangs == 100000:
+            line["other_configs"] = other_configs(lib)
         line["parity"] = {"result_hash": "%016x" % parity_hash}
         pc_names = ["view_bucketed", "view_full_pass", "bucket_rebuilds", "bucket_moves", "commit_lean", "commit_general",
                     "release_lean", "release_general", "map_lean", "map_general", "pod_of_gang_lean", "delete_pod_lean"]

@@ -172,17 +172,31 @@ def get_allocated_pod_index(info: Dict[str, Any], leaf_cell_num: int) -> int:  #
 
 
 class _Interner:
+    """name -> dense id, with the ids taken back once their owner is gone (the library's group / pod tables are dense
+    and bounded by hived_options_t: a long-running scheduler must not run out of them; include/hived.h "Id lifetime")."""
+
     def __init__(self):
         self.ids: Dict[str, int] = {}
         self.names: List[str] = []
+        self.free: List[int] = []
 
     def intern(self, name: str) -> int:
         i = self.ids.get(name)
         if i is None:
-            i = len(self.names)
+            if self.free:
+                i = self.free.pop()
+                self.names[i] = name
+            else:
+                i = len(self.names)
+                self.names.append(name)
             self.ids[name] = i
-            self.names.append(name)
         return i
+
+    def release(self, name: str) -> None:
+        i = self.ids.pop(name, None)
+        if i is not None:
+            self.names[i] = ""
+            self.free.append(i)
 
 
 class HivedAlgorithm:
@@ -420,10 +434,28 @@ class HivedAlgorithm:
 
     def DeleteUnallocatedPod(self, pod: Pod) -> None:  # hived_algorithm.go:229-245
         s = extract_pod_scheduling_spec(pod)
-        rc = self._lib.hived_delete_unallocated_pod(self._ctx, self._groups.intern(s["affinityGroup"]["name"]),
-                                                    self._pods.intern(pod.uid))
+        name = s["affinityGroup"]["name"]
+        gid = self._groups.ids.get(name)
+        if gid is None:
+            return  # never seen: nothing is preempting under that name
+        rc = self._lib.hived_delete_unallocated_pod(self._ctx, gid, self._pods.intern(pod.uid))
         if rc != 0:
             self._raise(rc)
+        self._release_pod(pod)
+        self._release_group_if_gone(name, gid)
+
+    def _release_pod(self, pod: Pod) -> None:
+        pid = self._pods.ids.get(pod.uid)
+        if pid is not None:
+            self._pod_objs.pop(pid, None)
+            self._pods.release(pod.uid)
+
+    def _release_group_if_gone(self, name: str, gid: int) -> None:
+        """The id of a group that no longer exists goes back to the interner (include/hived.h "Id lifetime")."""
+        gi = _cabi.GroupInfo()
+        self._lib.hived_get_group(self._ctx, gid, C.byref(gi))
+        if gi.state == _cabi.GROUP_NONE:
+            self._groups.release(name)
 
     def AddAllocatedPod(self, pod: Pod) -> None:  # hived_algorithm.go:247-270
         s = extract_pod_scheduling_spec(pod)
@@ -440,10 +472,15 @@ class HivedAlgorithm:
         s = extract_pod_scheduling_spec(pod)
         info = extract_pod_bind_info(pod)
         pod_index = get_allocated_pod_index(info, s["leafCellNumber"])
-        rc = self._lib.hived_delete_allocated_pod(self._ctx, self._groups.intern(s["affinityGroup"]["name"]),
-                                                  s["leafCellNumber"], pod_index)
+        name = s["affinityGroup"]["name"]
+        gid = self._groups.ids.get(name)
+        if gid is None:
+            return  # "Group %v not found when deleting pod" in the reference
+        rc = self._lib.hived_delete_allocated_pod(self._ctx, gid, s["leafCellNumber"], pod_index)
         if rc != 0:
             self._raise(rc)
+        self._release_pod(pod)
+        self._release_group_if_gone(name, gid)
 
     # AddNode / UpdateNode / DeleteNode (hived_algorithm.go:147-178); node = {"name":..., "healthy": bool}
     def AddNode(self, node: Dict[str, Any]) -> None:

@@ -684,6 +684,7 @@ struct Core {
     bool safetyOk = true;
     int chain = d.p_chain[c], level = d.p_level[c];
     int kv = vcl(vc, chain, level), k = cl(chain, level);
+    if (!d.vc_chain_counter[vc * d.S.nChains + chain]) { panic(HIVED_ERR_PLATFORM); return false; }  // write to a nil map in the reference (:1364)
     ST(d.vcFree[kv], d.vcFree[kv] - 1);
     ST(d.allVCFree[k], d.allVCFree[k] - 1);
     ST(d.totalLeft[k], d.totalLeft[k] - 1);
@@ -721,6 +722,7 @@ struct Core {
     sharedEnter();
     int chain = d.p_chain[c], level = d.p_level[c];
     int kv = vcl(vc, chain, level), k = cl(chain, level);
+    if (!d.vc_chain_counter[vc * d.S.nChains + chain]) { panic(HIVED_ERR_PLATFORM); return; }  // write to a nil map in the reference (:1454)
     ST(d.vcFree[kv], d.vcFree[kv] + 1);
     ST(d.allVCFree[k], d.allVCFree[k] + 1);
     ST(d.totalLeft[k], d.totalLeft[k] + 1);
@@ -2813,7 +2815,7 @@ struct Core {
   HIVED_DEV void deleteAllocatedPod(int g, int leafNum, int podIndex, int evVc) {
     long long tq = pclock();
     if (g < 0 || g >= d.S.maxGroups || d.g_state[g] == HIVED_GROUP_NONE) return;
-    if (multi && d.g_vc[g] != evVc) { panic(HIVED_ERR_PLATFORM); return; }  // the event was routed by a wrong VC id
+    (void)evVc;  // (the host routes a DELETE by the VC its group was scheduled under, hived_engine.hpp prepare())
     if (podIndex == -1) return;
     int m = memberOf(g, leafNum);
     if (m < 0 || podIndex < 0 || podIndex >= d.g_mem_pods[g * 8 + m]) { panic(HIVED_ERR_PLATFORM); return; }

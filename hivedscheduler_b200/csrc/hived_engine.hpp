@@ -74,6 +74,8 @@ struct Engine {
   std::vector<long long> poolEnd;       // [launchCta] first unused word of every slice after the run
   std::vector<uint8_t> ownerOf;         // owner CTA of every event of the batch being prepared (MAX_CTAS <= 255)
   std::vector<char> nodeBadHost;        // host mirror of the node health (decides whether a batch may run VC-parallel)
+  std::vector<int32_t> groupVcHost;     // VC under which a group id was last scheduled (-1: never): DELETE events are routed
+                                        // by it, not by the VC field of the event (which hived_delete_allocated_pod leaves 0)
   int badCount = 0;
   uint64_t prioMaskHost = 0;
   bool everRecovered = false;
@@ -179,6 +181,7 @@ struct Engine {
       allocs.push_back(dsc);
       dev.scratch = dsc;
     }
+    groupVcHost.assign((size_t)S.maxGroups, -1);
     nodeBadHost.assign(T.nNodes > 0 ? T.nNodes : 1, 1);  // every node starts bad (hived_algorithm.go:453-464)
     badCount = T.nNodes;
     // initial dynamic state (hived_algorithm.go:108-145, 365-409)
@@ -238,10 +241,23 @@ struct Engine {
         mask |= (p >= -1 && p < 62) ? (1ull << (p + 1)) : (1ull << 62);
       }
       if (ev.type != HIVED_EV_SCHEDULE && ev.type != HIVED_EV_DELETE_ALLOCATED) simple = false;
-      else if (ev.spec.vc < 0 || ev.spec.vc >= T.nVCs) simple = false;
+      // the VC that owns the event: a SCHEDULE names it; a DELETE belongs to the VC its group was scheduled under
+      // (the event's own VC field is optional, hived.h).  A group id seen under two VCs, or an unknown one: sequential.
+      int evVc = ev.spec.vc;
+      const int g = ev.spec.group;
+      if (ev.type == HIVED_EV_SCHEDULE || ev.type == Core::EV_SCHEDULE_ONLY) {
+        if (g >= 0 && g < (int)groupVcHost.size() && ev.spec.vc >= 0 && ev.spec.vc < T.nVCs) {
+          if (groupVcHost[g] >= 0 && groupVcHost[g] != ev.spec.vc) simple = false;
+          groupVcHost[g] = ev.spec.vc;
+        }
+      } else if (ev.type == HIVED_EV_DELETE_ALLOCATED) {
+        evVc = (g >= 0 && g < (int)groupVcHost.size()) ? groupVcHost[g] : -1;
+        if (evVc < 0) evVc = (ev.spec.vc >= 0 && ev.spec.vc < T.nVCs) ? ev.spec.vc : 0;  // unknown group: a no-op wherever it runs
+      }
+      if (evVc < 0 || evVc >= T.nVCs) simple = false;
       if (ev.type == Core::EV_ADD_ALLOCATED) everRecovered = true;
       if (simple) {
-        int o = ev.spec.vc % C;
+        int o = evVc % C;
         ownerOf[i] = (uint8_t)o;
         cnt[o + 1]++;
         if (ev.type == HIVED_EV_SCHEDULE) {
@@ -354,6 +370,9 @@ struct Engine {
         prioMaskHost |= (p >= -1 && p < 62) ? (1ull << (p + 1)) : (1ull << 62);
       }
       if (ev.type == Core::EV_ADD_ALLOCATED) everRecovered = true;
+      if ((ev.type == HIVED_EV_SCHEDULE || ev.type == Core::EV_SCHEDULE_ONLY) && ev.spec.group >= 0 &&
+          ev.spec.group < (int)groupVcHost.size() && ev.spec.vc >= 0 && ev.spec.vc < T.nVCs)
+        groupVcHost[ev.spec.group] = ev.spec.vc;
     }
   }
   bool buffersFailed() const {
@@ -523,9 +542,16 @@ int hived_process_events(hived_ctx* ctx, const hived_event_t* events, int32_t n,
   hived::Engine& e = ctx->e;
   int rc = e.runBatch(events, n, suggested_pool, suggested_words, nullptr, 0, res, pool, pool_cap);
   if (rc) return rc;
+  bool noted = false;
   for (int32_t i = 0; i < n; i++) {
     if (e.hashing && events[i].type == HIVED_EV_SCHEDULE) e.hash = hived_hash_result(e.hash, &res[i], pool);
     if (res[i].error == HIVED_ERR_CAPACITY) { e.err = "capacity exceeded (result pool or hived_options_t)"; return HIVED_ERR_CAPACITY; }
+    if (res[i].error >= 100 && !noted) {  // per-event platform errors stay in the results; the text names the first
+      char buf[128];
+      snprintf(buf, sizeof buf, "event %d failed with platform error %d (see hived_result_t.error of every event)", (int)i, (int)res[i].error);
+      e.err = buf;
+      noted = true;
+    }
   }
   return 0;
 }

@@ -29,6 +29,11 @@
  *   - virtual cell ids: for VC in id order: non-pinned chains in id order then pinned cells in id
  *     order; inside each: level 1..top, construction order (config.go:282-317).
  *   Group ids and pod ids are interned by the caller (dense, < the capacities in hived_options_t).
+ *   Id lifetime: a group id may be handed to another group once hived_get_group reports HIVED_GROUP_NONE for it (after
+ *   the DeleteAllocatedPod / DeleteUnallocatedPod that removed its last pod), a pod id once the pod has been deleted;
+ *   the shims recycle them that way (hivedscheduler_b200/algorithm.py, integration/pkg/algorithm/cuda_backend.go), so a
+ *   long-running scheduler never meets HIVED_ERR_CAPACITY.  Batch callers (hived_process_events) number the gangs of
+ *   one batch themselves.
  *
  * Order canonicalisation of the reference's Go-map iteration sites: chains
  * of one leaf type are tried in DESCENDING name order (the order the reference's own test pins,
@@ -182,10 +187,14 @@ typedef struct hived_bind_info {
   int32_t reserved;
 } hived_bind_info_t;
 
-/* One element of an ordered batch (hived_process_events). */
+/* One element of an ordered batch (hived_process_events).  The batch is equivalent to the calls one by one, in order;
+ * every event reports its own return code in hived_result_t.error (a user or platform error of ONE event does not
+ * stop the batch: that event changed nothing — validated before it mutates — and the following ones run; only
+ * HIVED_ERR_CAPACITY is also returned by the call itself, and hived_last_error names the first failing event). */
 #define HIVED_EV_SCHEDULE 0           /* Schedule; on a bind result immediately AddAllocatedPod with that
                                          PodBindInfo (the filterRoutine sequence, pkg/scheduler/scheduler.go:516-523) */
-#define HIVED_EV_DELETE_ALLOCATED 1   /* DeleteAllocatedPod(group=spec.group, leaf_num=spec.leaf_num, pod_index=arg0) */
+#define HIVED_EV_DELETE_ALLOCATED 1   /* DeleteAllocatedPod(group=spec.group, leaf_num=spec.leaf_num, pod_index=arg0); spec.vc is
+                                         not needed: the event runs with the VC its group was scheduled under */
 #define HIVED_EV_DELETE_UNALLOCATED 2 /* DeleteUnallocatedPod(group, pod) */
 #define HIVED_EV_NODE_HEALTH 3        /* node arg0 becomes healthy (arg1=1) / bad (arg1=0) */
 typedef struct hived_event {

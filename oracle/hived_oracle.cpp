@@ -2177,6 +2177,8 @@ bool HivedAlgorithm::allocatePreassignedCell(Cell* c, const std::string& vcn, bo
   bool safetyOk = true;
   const std::string chain = c->chain;
   int32_t level = c->level;
+  // h.vcFreeCellNum[vcn][chain][level]-- on a VC that has no counters for the chain writes into a nil map: a Go panic
+  if (!vcFreeCellNum[vcn].count(chain)) throw Panic("assignment to entry in nil map (VC " + vcn + " has no cells of chain " + chain + ")");
   vcFreeCellNum[vcn][chain][level]--;
   allVCFreeCellNum[chain][level]--;
   totalLeftCellNum[chain][level]--;
@@ -2227,6 +2229,7 @@ void HivedAlgorithm::allocateBadCell(Cell* c) {
 void HivedAlgorithm::releasePreassignedCell(Cell* c, const std::string& vcn, bool doomedBad) {
   const std::string chain = c->chain;
   int32_t level = c->level;
+  if (!vcFreeCellNum[vcn].count(chain)) throw Panic("assignment to entry in nil map (VC " + vcn + " has no cells of chain " + chain + ")");
   vcFreeCellNum[vcn][chain][level]++;
   allVCFreeCellNum[chain][level]++;
   totalLeftCellNum[chain][level]++;
