@@ -216,3 +216,20 @@ def test_cuda_full_size_c4_against_oracle(cuda_lib):
     assert gen.log_digest(log) == golden["log_sha256"]
     assert "%016x" % h == golden["hash"]
     assert stats == golden["stats"]
+
+
+def test_c_driver_through_the_abi(cuda_lib, tmp_path):
+    """Schedule -> AddAllocatedPod -> DeleteAllocatedPod on the GPU from plain C (tests/c/test_cabi_gpu.c): the
+    boundary as a cgo shim sees it, without Python in between."""
+    import subprocess
+    from hivedscheduler_b200.config import config_c1, to_spec_text
+    root = os.path.dirname(HERE)
+    csrc = os.path.join(root, "hivedscheduler_b200", "csrc")
+    exe = str(tmp_path / "test_cabi_gpu")
+    subprocess.check_call(["gcc", "-O1", "-std=c99", "-I", os.path.join(root, "include"), "-o", exe,
+                           os.path.join(HERE, "c", "test_cabi_gpu.c"), "-L", csrc, "-lhived_cuda", "-Wl,-rpath," + csrc])
+    spec = tmp_path / "c1.spec"
+    spec.write_text(to_spec_text(config_c1()))
+    out = subprocess.run([exe, str(spec)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr + out.stdout
+    assert "test_cabi_gpu: ok" in out.stdout
