@@ -215,6 +215,110 @@ def run_reference_arm(args):
     print(json.dumps(line))
 
 
+def main_partitioned(args, lib, rank, world, local):
+    """N > 1: ONE C3 batch partitioned over the ranks by virtual cluster (include/hived_multigpu.h; strong scaling:
+    the total work is fixed).  Every rank holds the whole cluster; the result of the job is the merged results."""
+    import torch
+    import torch.distributed as dist
+    from hivedscheduler_b200 import dist as hd
+    hd.bind_multigpu(lib)
+    t = trace.trace_c3(n_gangs=args.gangs)
+    ev = t["events"]
+    n = len(ev)
+    n_dec = int(t["decision"].sum())
+    pool_words = trace.pool_words_for(t)
+    bc = trace.BatchContext(lib, t["config"], t["n_groups"], t["n_pods"], t["max_group_leaves"], t["max_group_pods"], device=local)
+    bc.set_all_nodes_healthy()
+    ctx = bc.ctx
+    lib.hived_bench_save_state(ctx)
+    ev_pinned = torch.empty(ev.nbytes, dtype=torch.uint8, pin_memory=True)
+    ev_pinned.numpy()[:] = ev.view(np.uint8)
+    ev_ptr = C.cast(ev_pinned.data_ptr(), C.POINTER(_cabi.Event))
+    res_pinned = torch.empty(n * C.sizeof(_cabi.Result), dtype=torch.uint8, pin_memory=True)
+    pool_pinned = torch.empty(pool_words, dtype=torch.int32, pin_memory=True)
+    res_ptr = C.cast(res_pinned.data_ptr(), C.POINTER(_cabi.Result))
+    pool_ptr = C.cast(pool_pinned.data_ptr(), C.POINTER(C.c_int32))
+    device = "cuda:%d" % local
+    used = C.c_int64()
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    info = {}
+
+    def step(e2e: bool):
+        lib.hived_bench_restore_state(ctx)
+        lib.hived_bench_flush_l2(ctx)
+        if not e2e:
+            assert lib.hived_mg_reset(ctx) == 0
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0 = lib.hived_bench_total_kernel_ms(ctx)
+        a.record()
+        info.update(hd.run_partitioned(lib, ctx, ev_ptr, n, pool_words, rank, world, device=device, staged=not e2e))
+        if e2e:
+            assert lib.hived_bench_fetch_results(ctx, res_ptr, pool_ptr, pool_words, C.byref(used)) == 0
+        b.record()
+        torch.cuda.synchronize()
+        info["kernel_ms"] = lib.hived_bench_total_kernel_ms(ctx) - k0
+        return a.elapsed_time(b) / 1e3
+
+    assert lib.hived_mg_stage(ctx, ev_ptr, n, pool_words, rank, world) == 0, lib.hived_last_error(ctx)
+    for _ in range(args.warmup):
+        step(False)
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = lib.hived_bench_kernel_launches(ctx)
+    res_s = [step(False) for _ in range(args.steps)]
+    launches = lib.hived_bench_kernel_launches(ctx) - launches0
+    kernel_ms, coll_s, rounds = info["kernel_ms"], info["collective_s"], info["rounds"]
+    for _ in range(min(args.warmup, 2)):
+        step(True)
+    e2e_s = [step(True) for _ in range(args.steps)]
+    sampler.stop_flag.set()
+    sampler.join(timeout=2)
+    times = torch.tensor([sum(res_s), sum(e2e_s), kernel_ms / 1e3, coll_s], dtype=torch.float64, device="cuda")
+    dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    tot_s, tot_e2e, kernel_s_last, coll_s_last = [float(x) for x in times.tolist()]
+    # parity witness: the chain hash over the merged results of the last (e2e) step
+    res = np.frombuffer(res_pinned.numpy(), dtype=trace.RESULT_DT)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (res.tobytes(), pool_pinned.numpy()[:max(int(used.value), 1)].tobytes()))
+    if rank == 0:
+        rs = [np.frombuffer(g[0], dtype=trace.RESULT_DT) for g in gathered]
+        ps = [np.frombuffer(g[1], dtype=np.int32) for g in gathered]
+        h = hd.chain_hash(lib, ev_ptr, n, world, [r.ctypes.data for r in rs], [p_.ctypes.data for p_ in ps])
+        peak, peak_src = measured_peak_gbs()
+        stats = bc.stats()
+        line = {
+            "metric": METRIC, "value": n_dec * args.steps / tot_s, "unit": "decisions/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "events_per_step": int(n), "decisions_per_step": n_dec,
+                       "parallelism": "VC partition: rank r owns the VCs v %% %d == r, one CTA per owned VC; events that touch the "
+                                      "chain-wide free lists run alone, in batch order (include/hived_multigpu.h)" % world,
+                       "l2": "flushed between steps (256 MiB memset)",
+                       "timing": "CUDA events on the torch stream around the whole partitioned pass (kernels + NCCL rounds); max over ranks",
+                       "rounds_per_step": rounds, "broadcast_bytes_per_round": info["shared_bytes"],
+                       "slowest_rank_kernel_ms_last_step": 1e3 * kernel_s_last, "slowest_rank_collective_ms_last_step": 1e3 * coll_s_last,
+                       "e2e": "hived_mg_stage from pinned host memory (H2D of the whole batch on every rank), the partitioned pass, "
+                              "D2H of the rank's results + pool"},
+            "e2e": {"value": n_dec * args.steps / tot_e2e, "unit": "decisions/s", "h2d_bytes_per_step": int(ev.nbytes) * world,
+                    "d2h_bytes_per_step": int(n * C.sizeof(_cabi.Result)) * world},
+            "gpu_launches": int(launches) * world,
+            "clocks": sampler.summary(),
+            "roofline": {"bound": "hbm", "achieved": stats["algorithmic_bytes"] / (tot_s / args.steps) / 1e9 * world, "peak": peak * world,
+                         "unit": "GB/s", "frac": stats["algorithmic_bytes"] / (tot_s / args.steps) / 1e9 / peak, "traffic": None,
+                         "kernel": "hived_events_kernel", "peak_source": peak_src,
+                         "note": "rank 0's algorithmic bytes x ranks; the pass is latency-bound (DESIGN.md section 4)"},
+            "parity": {"result_hash": "%016x" % h, "note": "chain hash over the merged results of all ranks"},
+        }
+        print(json.dumps(line))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -223,6 +327,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--gangs", type=int, default=100000, help="C3 trace length (BASELINE: 100000)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--replicas", action="store_true", help="N > 1: independent replicas (weak scaling) instead of the VC partition")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the C2 / C4 / C5 sub-lines (about 45 s)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -238,6 +343,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = _cabi.load_cuda_library()
     bind_bench_hooks(lib)
+    if world > 1 and not args.replicas:
+        return main_partitioned(args, lib, rank, world, local)
 
     t = trace.trace_c3(n_gangs=args.gangs)
     ev = t["events"]

@@ -243,8 +243,17 @@ class HivedAlgorithm:
         self._pool = (C.c_int32 * self._pool_cap)()
         self._rand = random.Random(0)
         self._bitmap_words = (len(self.node_names) + 31) // 32
+        # request ingest (include/hived_ingest.h): the product library interns the node names itself; the CPU checker
+        # (oracle, tests only) does not export the helpers and gets the plain-Python statement below
+        self._ingest = None
+        if hasattr(lib_, "hived_ingest_create"):
+            from .ingest import Ingest
+            self._ingest = Ingest(lib_, self._ctx)
 
     def close(self):
+        if getattr(self, "_ingest", None):
+            self._ingest.close()
+            self._ingest = None
         if getattr(self, "_ctx", None):
             self._lib.hived_destroy(self._ctx)
             self._ctx = None
@@ -288,6 +297,11 @@ class HivedAlgorithm:
 
     def _suggested_bitmap(self, suggested_nodes: List[str]):
         """suggestedNodes []string -> node bitmap (the reference builds a string set, hived_algorithm.go:190-193)."""
+        if self._ingest is not None:
+            # one buffer for the C helper (a ctypes array of 8192 char* costs more than the whole decode)
+            joined = '","'.join(suggested_nodes)
+            if '\\' not in joined and joined.count('"') == 2 * max(0, len(suggested_nodes) - 1):
+                return self._ingest.node_names_json(('["' + joined + '"]').encode() if suggested_nodes else b"[]")[0]
         words = (C.c_uint32 * max(1, self._bitmap_words))()
         ids = self._node_ids
         for n in suggested_nodes:

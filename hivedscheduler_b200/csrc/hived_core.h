@@ -70,6 +70,7 @@ struct Sm {
   // the small scratch arrays of a decision that are read back right after they are written (a global store does not
   // allocate in L1: reading it back is a round trip to L2) live here when the group sizes allow (LS <= 64, PS <= 16)
   int32_t sc_pl_v[64], sc_pl_p[64], sc_pl_v2[64], sc_pl_p2[64], sc_pod_need[16], sc_pod_pos[16], sc_pod_cell[16], sc_pod_unit[16];
+  int stop_k;                 // multi-GPU partition: index (in the CTA's list) of the event the CTA stopped before; nOwn when done
   int lead_k;                 // index (in the CTA's list) of the event the leader works on; 0x7fffffff when it is done
   // ---- written back at kernel exit
   int panic;
@@ -100,7 +101,12 @@ struct Core {
   Scratch s;                // this CTA's private scratch arrays
   // ---- VC-parallel execution (several CTAs, one per group of VCs; see run())
   const int cta, nCta;
-  const bool multi;
+  bool multi;
+  // multi-GPU partition (hived_multigpu.h): 0 off; 1 this CTA runs its VCs' events up to the first one that may touch
+  // the cluster-wide state and stops BEFORE it (nothing of that event is written); 2 one such event, alone on the
+  // cluster (every other CTA of every rank is parked), the cluster-wide state being this rank's to write
+  int mgMode = 0, mgStart = 0;
+  bool mgStop = false;
   int curEvent;      // index (in the batch) of the event being processed
   bool sharedHeld;   // this event already holds the right to touch the cluster-wide free-list state
 
@@ -122,8 +128,11 @@ struct Core {
   // complete), and later events that need the shared state wait for this one the same way.
   HIVED_DEV void sharedEnter() {
     if (!multi || sharedHeld) return;
+    if (mgMode == 2) { sharedHeld = true; stat_add(ST_SHARED_SECTIONS, 1); return; }
+    if (mgMode == 1) { panic(HIVED_ERR_PLATFORM); return; }  // (unreachable: such an event stops before it starts)
     sharedEnterSlow();
   }
+  HIVED_DEV void setMultiGpu(int mode, int start) { mgMode = mode; mgStart = start; if (mode) multi = true; }
   HIVED_DEV_NOINLINE void sharedEnterSlow() {
     long long tw0 = pclock();
     while (true) {
@@ -1429,6 +1438,7 @@ struct Core {
         return true;
       }
     }
+    if (mgMode == 1) { mgStop = true; return false; }  // not a lean placement: the event runs alone, later
     bool ok = runViewPass(sched, priority, ignoreSuggested, npods, reason, rcell);
     if (!ok && p > OPP_PRIO) {
       priority = p;
@@ -2032,6 +2042,7 @@ struct Core {
   HIVED_DEV void deleteAllocatedAffinityGroup(int g) {
     int nl = groupLeaves(g);
     int vc = d.g_vc[g];
+    if (mgMode == 1 && mgDeleteNeedsShared(g, nl)) { mgStop = true; return; }
     if (leanDelete(g, nl, vc)) { eraseGroup(g); return; }
     path_add(PC_GENERAL_DELETE);
     if (deleteGroupBatched(g, nl, vc)) { eraseGroup(g); return; }
@@ -2276,6 +2287,7 @@ struct Core {
       reason = 0; rcell = -1;
       return true;
     }
+    if (mgMode == 1) { mgStop = true; return false; }  // the mapping may bind a preassigned cell (free lists)
     path_add(PC_GENERAL_MAP);
     tryLazyPreempt(s.pl_v, r.nleaves);
     if (panicCode) return false;
@@ -2891,6 +2903,7 @@ struct Core {
       Req r;
       int rc = scheduleNewAffinityGroup(sp, r, hasVirtual, reason, rcell);
       if (panicCode) return panicCode;
+      if (mgStop) return 0;
       if (rc < 0) return -rc;
       nmem = r.nmem;
       for (int m = 0; m < nmem; m++) { memLeaf[m] = r.memLeaf[m]; memPods[m] = r.memPods[m]; }
@@ -2986,6 +2999,7 @@ struct Core {
         stat_add(ST_SCHEDULE, 1);  // scheduled and recorded (the commit is part of the lean step)
       } else if (rc == 0) {
         rc = schedule(sp, ev.phase, res);
+        if (mgStop) return;
         if (rc == 0) stat_add(ST_SCHEDULE, 1);  // Schedule calls that returned a result (a panic is not a decision)
       }
       if (existing) { stat_add(ST_CYC_SCHED_EXISTING, pclock() - ts0); stat_add(ST_N_SCHED_EXISTING, 1); }
@@ -3023,11 +3037,15 @@ struct Core {
     } else if (type == HIVED_EV_DELETE_ALLOCATED) {
       long long td0 = pclock();
       deleteAllocatedPod(ev.spec.group, ev.spec.leaf_num, ev.arg0, ev.spec.vc);
+      if (mgStop) return;
       stat_add(ST_CYC_DELETE, pclock() - td0);
       if (ev.spec.group >= 0 && ev.spec.group < d.S.maxGroups && d.g_state[ev.spec.group] != HIVED_GROUP_NONE) {
         stat_add(ST_CYC_DELETE_POD, pclock() - td0); stat_add(ST_N_DELETE_POD, 1);
       }
       rc = panicCode;
+    } else if (mgMode == 1) {
+      mgStop = true;  // (the host only partitions calm batches; anything else runs alone)
+      return;
     } else if (type == HIVED_EV_DELETE_UNALLOCATED) {
       deleteUnallocatedPod(ev.spec.group, ev.spec.pod);
       rc = panicCode;
@@ -3088,12 +3106,14 @@ struct Core {
       if (!own) nOwn = n;
       // the CTA's event indices travel through a 64-entry window in shared memory, refilled 32 at a time (lane =
       // entry): the index of the next event is never a dependent global load on the leader's path
-      if (own) { for (int q = lane; q < 64 && q < nOwn; q += HIVED_WARPSZ) sm->own_win[q] = own[q]; }
+      if (own) { for (int q = lane; q < 64; q += HIVED_WARPSZ) { const int idx = mgStart + q; if (idx < nOwn) sm->own_win[idx & 63] = own[idx]; } }
       ST(sm->bkc_sched, -1);
       hv_warp_sync();
       auto ownAt = [&](int kk) { return own ? sm->own_win[kk & 63] : kk; };
-      for (int k = 0; k < nOwn; k++) {
-        if (own && k > 0 && (k & 31) == 0) {
+      int stopK = nOwn;
+      mgStop = false;
+      for (int k = mgStart; k < nOwn; k++) {
+        if (own && k > mgStart && (k & 31) == 0) {
           for (int q = lane; q < 32; q += HIVED_WARPSZ) { const int idx = k + 32 + q; if (idx < nOwn) sm->own_win[idx & 63] = own[idx]; }
           hv_warp_sync();
         }
@@ -3107,7 +3127,7 @@ struct Core {
         // wait for it, then request event k+1 and pull event k+2 towards L2/L1.
         constexpr int EVQ = (int)(sizeof(hived_event_t) / 16);
         int32_t* cur = sm->ev_words[k & 1];
-        if (k == 0) { for (int q = lane; q < EVQ; q += HIVED_WARPSZ) hv_cp_async16(cur + 4 * q, reinterpret_cast<const char*>(&events[i]) + 16 * q); }
+        if (k == mgStart) { for (int q = lane; q < EVQ; q += HIVED_WARPSZ) hv_cp_async16(cur + 4 * q, reinterpret_cast<const char*>(&events[i]) + 16 * q); }
         hv_cp_async_wait();
         hv_warp_sync();
         if (k + 1 < nOwn) {
@@ -3118,6 +3138,7 @@ struct Core {
         if (k + 2 < nOwn) hv_prefetch(&events[ownAt(k + 2)]);
         dbg(14, tq);
         processEvent(*reinterpret_cast<const hived_event_t*>(cur), &results[i], suggPool, aux);
+        if (mgStop) { hv_cp_async_wait(); stopK = k; break; }
         tq = pclock();
         if (multi) {
           int next = (k + 1 < nOwn) ? ownAt(k + 1) : 0x7fffffff;
@@ -3134,6 +3155,7 @@ struct Core {
       if (lane == 0) hv_st_volatile(&sm->lead_k, 0x7fffffff);
       flushWork();
       ST(sm->pool_off, poolOff);
+      ST(sm->stop_k, stopK);
       ST(sm->panic, initPanic);
       ST(sm->cmd, CMD_EXIT);
       hv_cta_sync();

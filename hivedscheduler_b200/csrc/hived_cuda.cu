@@ -32,12 +32,16 @@ hived_events_kernel(const __grid_constant__ Dev dev, const hived_event_t* __rest
   }
   __syncthreads();
   Core core(dev, &sm, pool, scalars[cta * 4 + 1], gridDim.x);
-  core.run(events, n, results, suggPool, aux, initLists, nPinnedOrder, nBad, own ? own + ownOff[cta] : nullptr,
-           own ? ownOff[cta + 1] - ownOff[cta] : n);
+  int nOwn = own ? ownOff[cta + 1] - ownOff[cta] : n;
+  // multi-GPU partition: [start, limit) of this CTA's list and the mode, packed by launchProgram (0: an ordinary run)
+  const long long mg = scalars[cta * 4 + 3];
+  if (mg) { core.setMultiGpu((int)((mg >> 62) & 3), (int)(mg & 0x7fffffff)); nOwn = (int)((mg >> 31) & 0x7fffffff); }
+  core.run(events, n, results, suggPool, aux, initLists, nPinnedOrder, nBad, own ? own + ownOff[cta] : nullptr, nOwn);
   __syncthreads();
   if (threadIdx.x == 0) {
     scalars[cta * 4 + 0] = sm.pool_off;
     scalars[cta * 4 + 2] = sm.panic;
+    scalars[cta * 4 + 3] = sm.stop_k;
   }
 }
 
@@ -62,6 +66,7 @@ void bk_free(void* p) { cudaFree(p); }
 void bk_h2d(void* dst, const void* src, size_t bytes) { cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice); }
 void bk_d2h(void* dst, const void* src, size_t bytes) { cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost); }
 void bk_d2d(void* dst, const void* src, size_t bytes) { cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToDevice); }
+void bk_zero(void* dst, size_t bytes) { cudaMemset(dst, 0, bytes); }
 
 void bk_flush_l2() {
   static void* buf = nullptr;
@@ -112,16 +117,25 @@ int launchProgram(Engine& e, int n, bool withInit) {
     e.stream = t;
   }
   CudaTimers* t = (CudaTimers*)e.stream;
+  const int mgMode = withInit ? 0 : e.mgMode;
+  if (mgMode == 3) {  // end of a multi-GPU partition run: the repair pass alone
+    hived_repair_kernel<<<1, NT, 0, t->stream>>>(e.dev);
+    cudaError_t err = cudaStreamSynchronize(t->stream);
+    if (err != cudaSuccess) { e.err = std::string("hived_repair_kernel failed: ") + cudaGetErrorString(err); return HIVED_ERR_PLATFORM; }
+    e.kernelLaunches++;
+    return 0;
+  }
   const int C = withInit ? 1 : e.launchCta;
   long long scal[MAX_CTAS * 4] = {0};
   for (int c = 0; c < C; c++) {
-    scal[c * 4 + 0] = withInit ? 0 : e.poolBase[c];
+    scal[c * 4 + 0] = withInit ? 0 : (mgMode ? e.mgPoolCur[c] : e.poolBase[c]);
     scal[c * 4 + 1] = withInit ? 0 : e.poolBase[c + 1];
+    if (mgMode) scal[c * 4 + 3] = ((long long)mgMode << 62) | ((long long)e.mgLimit[c] << 31) | (long long)e.mgCursor[c];
   }
   cudaMemcpyAsync(e.dScalars.p, scal, sizeof scal, cudaMemcpyHostToDevice, t->stream);
   cudaEventRecord(t->start, t->stream);
-  const int32_t* own = C > 1 ? (const int32_t*)e.dOwn.p : nullptr;
-  if (C > 1) {
+  const int32_t* own = (C > 1 || mgMode) ? (const int32_t*)e.dOwn.p : nullptr;
+  if (C > 1 && !mgMode) {
     // The CTAs of a VC-parallel batch wait for each other (ordered shared sections): launch them cooperatively, so
     // that the runtime guarantees that all of them are resident at the same time.
     Dev devArg = e.dev;
@@ -149,7 +163,7 @@ int launchProgram(Engine& e, int n, bool withInit) {
         withInit ? (const int32_t*)e.dInit.p : nullptr, e.nPinnedOrder, e.nBad, (int32_t*)e.dPool.p, (long long*)e.dScalars.p, own,
         own ? own + n : nullptr);
   }
-  if (C > 1) hived_repair_kernel<<<1, NT, 0, t->stream>>>(e.dev);
+  if (C > 1 && !mgMode) hived_repair_kernel<<<1, NT, 0, t->stream>>>(e.dev);
   cudaEventRecord(t->stop, t->stream);
   cudaMemcpyAsync(scal, e.dScalars.p, sizeof scal, cudaMemcpyDeviceToHost, t->stream);
   cudaError_t err = cudaStreamSynchronize(t->stream);
@@ -161,9 +175,10 @@ int launchProgram(Engine& e, int n, bool withInit) {
   cudaEventElapsedTime(&ms, t->start, t->stop);
   e.lastKernelMs = ms;
   e.kernelMsTotal += ms;
-  e.kernelLaunches += C > 1 ? 2 : 1;
+  e.kernelLaunches += (C > 1 && !mgMode) ? 2 : 1;
   e.poolEnd.assign(C, 0);
   for (int c = 0; c < C; c++) e.poolEnd[c] = scal[c * 4 + 0];
+  if (mgMode) { e.mgStopOut.assign(C, 0); for (int c = 0; c < C; c++) e.mgStopOut[c] = (int32_t)scal[c * 4 + 3]; }
   e.poolOff = scal[0];
   if (withInit && scal[2]) { e.err = "initialisation panicked on the device"; return (int)scal[2]; }
   return 0;

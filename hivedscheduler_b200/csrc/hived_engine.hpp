@@ -15,6 +15,7 @@
 
 #include "../../include/hived.h"
 #include "../../include/hived_hash.h"
+#include "../../include/hived_multigpu.h"
 #include "hived_topo.hpp"
 #define HIVED_TOPO_CONSTS
 #include "hived_core.h"
@@ -28,6 +29,7 @@ void bk_free(void* p);
 void bk_h2d(void* dst, const void* src, size_t bytes);
 void bk_d2h(void* dst, const void* src, size_t bytes);
 void bk_d2d(void* dst, const void* src, size_t bytes);
+void bk_zero(void* dst, size_t bytes);
 int bk_init(int& device, std::string& err);  // device: in = requested ordinal, out = the one in use
 void bk_use_device(int device);  // make `device` current for the calling thread (contexts on several GPUs in one process)
 // runs the program over n staged events; returns 0 or a HIVED_ERR_* code
@@ -401,6 +403,161 @@ struct Engine {
     return launchProgram(*this, stagedN, false);
   }
 
+  // ---- multi-GPU partition of one calm batch (include/hived_multigpu.h) --------------------------------------
+  // Every rank holds the whole cluster; rank r owns the VCs v with v % world == r and runs one CTA per owned VC.
+  // VCs interact only through the chain-wide buddy free lists and counters (`sharedArrays`): a rank runs its
+  // events up to the first one that may touch them (mgRun), the ranks agree on the smallest such event (min over
+  // ranks: the caller's collective), its owner runs it alone (mgSolo) and ships the arrays to everybody else.
+  int mgMode = 0, mgRank = 0, mgWorld = 1;
+  std::vector<int32_t> mgCursor, mgLimit, mgStopOut, mgOwnHost;
+  std::vector<long long> mgPoolCur;
+  std::vector<std::pair<void*, size_t>> sharedArrays() {
+    std::vector<std::pair<void*, size_t>> v;
+    const size_t NP = (size_t)dev.S.NP * 4, LV = (size_t)dev.S.nChains * MAXL * 4;
+    v.push_back({dev.p_split, NP}); v.push_back({dev.p_flpos, NP}); v.push_back({dev.p_bfpos, NP});
+    v.push_back({dev.p_dmpos, NP}); v.push_back({dev.p_dmvc, NP});
+    v.push_back({dev.vcFree, LV * dev.S.nVCs}); v.push_back({dev.allVCFree, LV}); v.push_back({dev.totalLeft, LV});
+    v.push_back({dev.allVCDoomed, LV});
+    v.push_back({dev.fl_data, (size_t)dev.S.flTotal * 4}); v.push_back({dev.fl_len, LV});
+    v.push_back({dev.bf_data, (size_t)dev.S.flTotal * 4}); v.push_back({dev.bf_len, LV});
+    v.push_back({dev.dm_data, (size_t)dev.S.dmTotal * 4}); v.push_back({dev.dm_len, LV * dev.S.nVCs});
+    return v;
+  }
+  int64_t mgSharedBytes() { int64_t t = 0; for (auto& r : sharedArrays()) t += (int64_t)((r.second + 15) & ~(size_t)15); return t; }
+  void mgExportShared(void* dst) {
+    bk_use_device(deviceOrdinal);
+    char* o = (char*)dst;
+    for (auto& r : sharedArrays()) { if (r.second) bk_d2d(o, r.first, r.second); o += (r.second + 15) & ~(size_t)15; }
+  }
+  void mgImportShared(const void* src) {
+    bk_use_device(deviceOrdinal);
+    const char* o = (const char*)src;
+    for (auto& r : sharedArrays()) { if (r.second) bk_d2d(r.first, o, r.second); o += (r.second + 15) & ~(size_t)15; }
+  }
+  int mgStage(const hived_event_t* events, int n, int64_t poolCap, int rank, int world) {
+    bk_use_device(deviceOrdinal);
+    if (world < 1 || rank < 0 || rank >= world) { err = "multi-GPU partition: bad rank/world"; return HIVED_ERR_BAD_SPEC; }
+    if (badCount != 0 || everRecovered) { err = "multi-GPU partition: only calm batches (every node healthy, no recovery)"; return HIVED_ERR_BAD_SPEC; }
+    uint64_t mask = prioMaskHost;
+    const int C = (T.nVCs - rank + world - 1) / world > 0 ? (T.nVCs - rank + world - 1) / world : 0;
+    if (C > MAX_CTAS) { err = "multi-GPU partition: more VCs per rank than CTAs"; return HIVED_ERR_CAPACITY; }
+    const int CL = C > 0 ? C : 1;
+    std::vector<std::vector<int32_t>> lists(CL);
+    std::vector<long long> need(CL, 0);
+    for (int i = 0; i < n; i++) {
+      const hived_event_t& ev = events[i];
+      if (ev.type != HIVED_EV_SCHEDULE && ev.type != HIVED_EV_DELETE_ALLOCATED) { err = "multi-GPU partition: only SCHEDULE / DELETE_ALLOCATED events"; return HIVED_ERR_BAD_SPEC; }
+      int evVc = ev.spec.vc;
+      const int g = ev.spec.group;
+      if (ev.type == HIVED_EV_SCHEDULE) {
+        int p = ev.spec.priority;
+        mask |= (p >= -1 && p < 62) ? (1ull << (p + 1)) : (1ull << 62);
+        if (g >= 0 && g < (int)groupVcHost.size() && evVc >= 0 && evVc < T.nVCs) {
+          if (groupVcHost[g] >= 0 && groupVcHost[g] != evVc) { err = "multi-GPU partition: a group id used under two VCs"; return HIVED_ERR_BAD_SPEC; }
+          groupVcHost[g] = evVc;
+        }
+      } else {
+        evVc = (g >= 0 && g < (int)groupVcHost.size()) ? groupVcHost[g] : -1;
+        if (evVc < 0) evVc = (ev.spec.vc >= 0 && ev.spec.vc < T.nVCs) ? ev.spec.vc : 0;
+      }
+      if (evVc < 0 || evVc >= T.nVCs) { err = "multi-GPU partition: event with an unknown VC"; return HIVED_ERR_BAD_SPEC; }
+      if (evVc % world != rank) continue;
+      const int c = evVc / world;
+      lists[c].push_back(i);
+      if (ev.type == HIVED_EV_SCHEDULE) {
+        long long leaves = 0;
+        for (int m = 0; m < ev.spec.n_members && m < HIVED_MAX_MEMBERS; m++) leaves += (long long)ev.spec.member_leaf_num[m] * ev.spec.member_pod_num[m];
+        need[c] += 3 * leaves;
+      }
+    }
+    prioMaskHost = mask;
+    if ((mask & (mask - 1)) != 0 || (mask & 1)) { err = "multi-GPU partition: more than one priority in use"; return HIVED_ERR_BAD_SPEC; }
+    launchCta = CL;
+    ownOff.assign(CL + 1, 0);
+    mgOwnHost.clear();
+    for (int c = 0; c < CL; c++) { mgOwnHost.insert(mgOwnHost.end(), lists[c].begin(), lists[c].end()); ownOff[c + 1] = (int32_t)mgOwnHost.size(); }
+    poolBase.assign(CL + 1, 0);
+    for (int c = 0; c < CL; c++) poolBase[c + 1] = poolBase[c] + need[c];
+    if (poolBase[CL] > poolCap) { err = "multi-GPU partition: pool too small"; return HIVED_ERR_CAPACITY; }
+    dOwn.ensure((size_t)(n + CL + 2) * 4);
+    if (!mgOwnHost.empty()) bk_h2d(dOwn.p, mgOwnHost.data(), mgOwnHost.size() * 4);
+    bk_h2d((int32_t*)dOwn.p + n, ownOff.data(), (size_t)(CL + 1) * 4);
+    dEvents.ensure((size_t)(n > 0 ? n : 1) * sizeof(hived_event_t));
+    dResults.ensure((size_t)(n > 0 ? n : 1) * sizeof(hived_result_t));
+    dPool.ensure((size_t)(poolCap > 0 ? poolCap : 1) * 4);
+    if (buffersFailed()) { err = "out of device memory while staging the batch"; return HIVED_ERR_CAPACITY; }
+    if (n > 0) bk_h2d(dEvents.p, events, (size_t)n * sizeof(hived_event_t));
+    bk_zero(dResults.p, (size_t)(n > 0 ? n : 1) * sizeof(hived_result_t));  // events of other ranks stay all-zero here
+    poolCapWords = poolCap;
+    stagedN = n;
+    stagedEvents = events;
+    hasSugg = false; hasAux = false;
+    canonicalDone = false;
+    mgRank = rank; mgWorld = world;
+    mgCursor.assign(CL, 0);
+    mgPoolCur.assign(poolBase.begin(), poolBase.end() - 1);
+    return 0;
+  }
+  // run the staged batch again (bench: after the scheduler state was rewound)
+  int mgReset() {
+    bk_use_device(deviceOrdinal);
+    if (mgCursor.empty()) { err = "multi-GPU partition: nothing staged"; return HIVED_ERR_BAD_SPEC; }
+    bk_zero(dResults.p, (size_t)(stagedN > 0 ? stagedN : 1) * sizeof(hived_result_t));
+    mgCursor.assign(launchCta, 0);
+    mgPoolCur.assign(poolBase.begin(), poolBase.end() - 1);
+    canonicalDone = false;
+    return 0;
+  }
+  // first pending event of every CTA's list; 0x7fffffff when the rank is through
+  int mgNextStop() const {
+    int mn = 0x7fffffff;
+    for (int c = 0; c < launchCta; c++) {
+      const int k = mgCursor[c], cnt = ownOff[c + 1] - ownOff[c];
+      if (k < cnt && mgOwnHost[ownOff[c] + k] < mn) mn = mgOwnHost[ownOff[c] + k];
+    }
+    return mn;
+  }
+  int mgLaunch(int mode) {
+    mgMode = mode;
+    int rc = launchProgram(*this, stagedN, false);
+    mgMode = 0;
+    if (rc) return rc;
+    for (int c = 0; c < launchCta; c++) { mgCursor[c] = mgStopOut[c]; mgPoolCur[c] = poolEnd[c]; }
+    return 0;
+  }
+  // every CTA of this rank runs until its next event that may touch the cluster-wide state (or the end of its list)
+  int mgRun(int32_t* stopEvent) {
+    bk_use_device(deviceOrdinal);
+    mgLimit.assign(launchCta, 0);
+    for (int c = 0; c < launchCta; c++) mgLimit[c] = ownOff[c + 1] - ownOff[c];
+    int rc = mgLaunch(1);
+    if (rc) return rc;
+    *stopEvent = mgNextStop();
+    return 0;
+  }
+  // the event every rank stopped at or before runs alone on the cluster, on the rank that owns it
+  int mgSolo(int eventIndex) {
+    bk_use_device(deviceOrdinal);
+    mgLimit.assign(mgCursor.begin(), mgCursor.end());
+    int owner = -1;
+    for (int c = 0; c < launchCta; c++) {
+      const int k = mgCursor[c], cnt = ownOff[c + 1] - ownOff[c];
+      if (k < cnt && mgOwnHost[ownOff[c] + k] == eventIndex) { owner = c; break; }
+    }
+    if (owner < 0) { err = "multi-GPU partition: this rank is not stopped at that event"; return HIVED_ERR_BAD_SPEC; }
+    mgLimit[owner] = mgCursor[owner] + 1;
+    return mgLaunch(2);
+  }
+  // after the last round: the cells above the bound preassigned cells are re-derived (as after a VC-parallel batch)
+  int mgFinish() {
+    bk_use_device(deviceOrdinal);
+    mgMode = 3;
+    int rc = launchProgram(*this, stagedN, false);
+    mgMode = 0;
+    poolEnd.assign(mgPoolCur.begin(), mgPoolCur.end());
+    return rc;
+  }
+
   void readArray(const int32_t* devPtr, std::vector<int32_t>& out, size_t count) {
     out.resize(count ? count : 1);
     bk_d2h(out.data(), devPtr, out.size() * 4);
@@ -718,6 +875,30 @@ int hived_bench_fetch_results(hived_ctx* ctx, hived_result_t* res, int32_t* pool
   hived::Engine& e = ctx->e;
   return e.fetch(res, pool, pool_cap, pool_used);
 }
+// ---- include/hived_multigpu.h
+int hived_mg_stage(hived_ctx* ctx, const hived_event_t* events, int32_t n, int64_t pool_cap, int32_t rank, int32_t world) {
+  return ctx->e.mgStage(events, n, pool_cap, rank, world);
+}
+int hived_mg_reset(hived_ctx* ctx) { return ctx->e.mgReset(); }
+int hived_mg_run(hived_ctx* ctx, int32_t* stop_event) { return ctx->e.mgRun(stop_event); }
+int hived_mg_solo(hived_ctx* ctx, int32_t event_index) { return ctx->e.mgSolo(event_index); }
+int64_t hived_mg_shared_bytes(hived_ctx* ctx) { return ctx->e.mgSharedBytes(); }
+int hived_mg_export_shared(hived_ctx* ctx, void* buf) { ctx->e.mgExportShared(buf); return 0; }
+int hived_mg_import_shared(hived_ctx* ctx, const void* buf) { ctx->e.mgImportShared(buf); return 0; }
+int hived_mg_finish(hived_ctx* ctx) { return ctx->e.mgFinish(); }
+int hived_mg_chain_hash(const hived_event_t* events, int32_t n, int32_t world, const hived_result_t* const* res,
+                        const int32_t* const* pools, uint64_t seed, uint64_t* out) {
+  uint64_t h = seed;
+  for (int i = 0; i < n; i++) {
+    if (events[i].type != HIVED_EV_SCHEDULE) continue;
+    const int vc = events[i].spec.vc;
+    if (vc < 0 || world < 1) return HIVED_ERR_BAD_SPEC;
+    const int r = vc % world;
+    h = hived_hash_result(h, &res[r][i], pools[r]);
+  }
+  *out = h;
+  return 0;
+}
 int hived_bench_num_ctas(hived_ctx* ctx) { return ctx->e.launchCta; }
 int hived_bench_set_result_hash(hived_ctx* ctx, int on) { ctx->e.hashing = on != 0; return 0; }
 int hived_bench_flush_l2(hived_ctx*) { hived::bk_flush_l2(); return 0; }
@@ -776,3 +957,5 @@ double hived_bench_total_kernel_ms(hived_ctx* ctx) { return ctx->e.kernelMsTotal
 int64_t hived_bench_kernel_launches(hived_ctx* ctx) { return ctx->e.kernelLaunches; }
 
 }  // extern "C"
+
+#include "hived_ingest.hpp"

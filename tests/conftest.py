@@ -50,6 +50,15 @@ def emu_lib():
     return _cabi.load_library(EMU_LIB)
 
 
+@pytest.fixture(scope="session")
+def emu_mt_lib():
+    """The DEVICE PROGRAM on host threads (one 1-lane "CTA" per thread, tests/emu/hived_emu_mt.cpp) — test / bench only."""
+    from hivedscheduler_b200 import _cabi
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as g
+    return _cabi.load_library(g.build_cpu_flat())
+
+
 def run_trace(lib, t, n_events=None, chunks=1, device=0, snapshots=None):
     """Replay a trace on a library; returns (hash, results, pool, stats)."""
     import numpy as np

@@ -20,6 +20,7 @@ void bk_free(void* p) { free(p); }
 void bk_h2d(void* dst, const void* src, size_t bytes) { memcpy(dst, src, bytes); }
 void bk_d2h(void* dst, const void* src, size_t bytes) { memcpy(dst, src, bytes); }
 void bk_d2d(void* dst, const void* src, size_t bytes) { memcpy(dst, src, bytes); }
+void bk_zero(void* dst, size_t bytes) { memset(dst, 0, bytes); }
 int bk_init(int&, std::string&) { return 0; }
 void bk_use_device(int) {}
 void bk_flush_l2() {}
@@ -54,21 +55,35 @@ int bk_canonicalise(Engine& e, int n, long long* total) {
 
 int launchProgram(Engine& e, int n, bool withInit) {
   const int C = withInit ? 1 : e.launchCta;
+  const int mgMode = withInit ? 0 : e.mgMode;
+  if (mgMode == 3) {
+    hv_tls_cta = 0;
+    Sm sm;
+    memset((void*)&sm, 0, sizeof sm);
+    Core core(e.dev, &sm, nullptr, 0, 1);
+    core.repairSharedAncestors();
+    e.kernelLaunches++;
+    return 0;
+  }
+  std::vector<int32_t> stops(C, 0);
   std::vector<Sm> sms(C);
   memset((void*)sms.data(), 0, sizeof(Sm) * C);
   std::vector<long long> poolEnd(C, 0);
   std::vector<int> panics(C, 0);
-  const int32_t* own = C > 1 ? (const int32_t*)e.dOwn.p : nullptr;
+  const int32_t* own = (C > 1 || mgMode) ? (const int32_t*)e.dOwn.p : nullptr;
   const int32_t* ownOff = own ? own + n : nullptr;
   auto body = [&](int cta) {
     hv_tls_cta = cta;
     Sm& sm = sms[cta];
     sm.lead_k = -1;
-    sm.pool_off = withInit ? 0 : e.poolBase[cta];
+    sm.pool_off = withInit ? 0 : (mgMode ? e.mgPoolCur[cta] : e.poolBase[cta]);
     Core core(e.dev, &sm, (int32_t*)e.dPool.p, withInit ? 0 : e.poolBase[cta + 1], C);
+    int nOwn = own ? ownOff[cta + 1] - ownOff[cta] : n;
+    if (mgMode) { core.setMultiGpu(mgMode, e.mgCursor[cta]); nOwn = e.mgLimit[cta]; }
     core.run((const hived_event_t*)e.dEvents.p, n, (hived_result_t*)e.dResults.p, e.hasSugg ? (const uint32_t*)e.dSugg.p : nullptr,
              e.hasAux ? (const int32_t*)e.dAux.p : nullptr, withInit ? (const int32_t*)e.dInit.p : nullptr, e.nPinnedOrder, e.nBad,
-             own ? own + ownOff[cta] : nullptr, own ? ownOff[cta + 1] - ownOff[cta] : n);
+             own ? own + ownOff[cta] : nullptr, nOwn);
+    stops[cta] = sm.stop_k;
     poolEnd[cta] = sm.pool_off;
     panics[cta] = sm.panic;
   };
@@ -79,13 +94,16 @@ int launchProgram(Engine& e, int n, bool withInit) {
     for (int c = 0; c < C; c++) th.emplace_back(body, c);
     for (auto& t : th) t.join();
     hv_tls_cta = 0;
+  }
+  if (C > 1 && !mgMode) {
     Sm sm;
     memset((void*)&sm, 0, sizeof sm);
     Core core(e.dev, &sm, nullptr, 0, 1);
     core.repairSharedAncestors();
   }
-  e.kernelLaunches += C > 1 ? 2 : 1;
+  e.kernelLaunches += (C > 1 && !mgMode) ? 2 : 1;
   e.poolEnd.assign(poolEnd.begin(), poolEnd.end());
+  if (mgMode) e.mgStopOut.assign(stops.begin(), stops.end());
   e.poolOff = poolEnd[0];
   if (withInit && panics[0]) { e.err = "initialisation panicked"; return panics[0]; }
   return 0;

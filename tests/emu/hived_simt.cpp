@@ -17,6 +17,7 @@ void bk_free(void* p) { free(p); }
 void bk_h2d(void* dst, const void* src, size_t bytes) { memcpy(dst, src, bytes); }
 void bk_d2h(void* dst, const void* src, size_t bytes) { memcpy(dst, src, bytes); }
 void bk_d2d(void* dst, const void* src, size_t bytes) { memcpy(dst, src, bytes); }
+void bk_zero(void* dst, size_t bytes) { memset(dst, 0, bytes); }
 int bk_init(int&, std::string&) { return 0; }
 void bk_use_device(int) {}
 void bk_flush_l2() {}
@@ -58,6 +59,7 @@ struct LaunchArgs {
   Sm* sms;
   long long* scal;
   bool repair;
+  int mgMode;
 };
 
 static void kernelEntry(void* p) {
@@ -73,35 +75,45 @@ static void kernelEntry(void* p) {
   if (simt::tid() == 0) { sm.cmd = CMD_IDLE; sm.panic = 0; sm.lead_k = -1; sm.pool_off = a.scal[cta * 4 + 0]; }
   simt::cta_barrier();
   Core core(e.dev, &sm, (int32_t*)e.dPool.p, a.scal[cta * 4 + 1], a.C);
-  const int32_t* own = a.C > 1 ? (const int32_t*)e.dOwn.p : nullptr;
+  const int32_t* own = (a.C > 1 || a.mgMode) ? (const int32_t*)e.dOwn.p : nullptr;
   const int32_t* ownOff = own ? own + a.n : nullptr;
+  int nOwn = own ? ownOff[cta + 1] - ownOff[cta] : a.n;
+  if (a.mgMode) { core.setMultiGpu(a.mgMode, e.mgCursor[cta]); nOwn = e.mgLimit[cta]; }
   core.run((const hived_event_t*)e.dEvents.p, a.n, (hived_result_t*)e.dResults.p, e.hasSugg ? (const uint32_t*)e.dSugg.p : nullptr,
            e.hasAux ? (const int32_t*)e.dAux.p : nullptr, a.withInit ? (const int32_t*)e.dInit.p : nullptr, e.nPinnedOrder, e.nBad,
-           own ? own + ownOff[cta] : nullptr, own ? ownOff[cta + 1] - ownOff[cta] : a.n);
+           own ? own + ownOff[cta] : nullptr, nOwn);
   simt::cta_barrier();
-  if (simt::tid() == 0) { a.scal[cta * 4 + 0] = sm.pool_off; a.scal[cta * 4 + 2] = sm.panic; }
+  if (simt::tid() == 0) { a.scal[cta * 4 + 0] = sm.pool_off; a.scal[cta * 4 + 2] = sm.panic; a.scal[cta * 4 + 3] = sm.stop_k; }
 }
 
 int launchProgram(Engine& e, int n, bool withInit) {
   static int NT = 0;
   if (!NT) { const char* env = getenv("HIVED_SIMT_NT"); NT = env ? atoi(env) : 96; if (NT < 32 || NT % 32 || NT > 32 * MAX_WARPS) NT = 96; }
   const int C = withInit ? 1 : e.launchCta;
+  const int mgMode = withInit ? 0 : e.mgMode;
   std::vector<Sm> sms(C);
   memset((void*)sms.data(), 0, sizeof(Sm) * C);
   long long scal[MAX_CTAS * 4] = {0};
+  if (mgMode == 3) {
+    LaunchArgs r{&e, n, false, 1, sms.data(), scal, true, 0};
+    simt::launch(1, NT, kernelEntry, &r);
+    e.kernelLaunches++;
+    return 0;
+  }
   for (int c = 0; c < C; c++) {
-    scal[c * 4 + 0] = withInit ? 0 : e.poolBase[c];
+    scal[c * 4 + 0] = withInit ? 0 : (mgMode ? e.mgPoolCur[c] : e.poolBase[c]);
     scal[c * 4 + 1] = withInit ? 0 : e.poolBase[c + 1];
   }
-  LaunchArgs a{&e, n, withInit, C, sms.data(), scal, false};
+  LaunchArgs a{&e, n, withInit, C, sms.data(), scal, false, mgMode};
   simt::launch(C, NT, kernelEntry, &a);
-  if (C > 1) {
-    LaunchArgs r{&e, n, false, 1, sms.data(), scal, true};
+  if (C > 1 && !mgMode) {
+    LaunchArgs r{&e, n, false, 1, sms.data(), scal, true, 0};
     simt::launch(1, NT, kernelEntry, &r);
   }
-  e.kernelLaunches += C > 1 ? 2 : 1;
+  e.kernelLaunches += (C > 1 && !mgMode) ? 2 : 1;
   e.poolEnd.assign(C, 0);
   for (int c = 0; c < C; c++) e.poolEnd[c] = scal[c * 4 + 0];
+  if (mgMode) { e.mgStopOut.assign(C, 0); for (int c = 0; c < C; c++) e.mgStopOut[c] = (int32_t)scal[c * 4 + 3]; }
   e.poolOff = scal[0];
   if (withInit && scal[2]) { e.err = "initialisation panicked"; return (int)scal[2]; }
   return 0;

@@ -10,8 +10,8 @@ from hivedscheduler_b200 import _cabi, config
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def declared_symbols():
-    src = open(os.path.join(ROOT, "include", "hived.h")).read()
+def declared_symbols(header="hived.h"):
+    src = open(os.path.join(ROOT, "include", header)).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     return sorted(set(re.findall(r"\b(hived_[a-z_0-9]+)\s*\(", src)))
 
@@ -25,6 +25,18 @@ def test_header_symbols_are_bound_and_exported():
         assert sym in bound, "include/hived.h declares %s but _cabi does not bind it" % sym
         assert getattr(lib, sym) is not None
     assert lib.hived_backend() == b"cuda-sm100a"
+    # the other headers of include/: measurement hooks, multi-GPU partition, request ingest
+    from hivedscheduler_b200 import dist, ingest
+    dist.bind_multigpu(lib)
+    ingest.bind(lib)
+    typed = {n for n, _, _ in ingest.SYMBOLS}
+    for header in ("hived_bench.h", "hived_multigpu.h", "hived_ingest.h"):
+        syms = declared_symbols(header)
+        assert syms, header
+        for sym in syms:
+            assert getattr(lib, sym) is not None, "%s declares %s but the library does not export it" % (header, sym)
+            if header == "hived_ingest.h":
+                assert sym in typed, sym
 
 
 def test_struct_layouts_match_header():

@@ -233,3 +233,22 @@ def test_c_driver_through_the_abi(cuda_lib, tmp_path):
     out = subprocess.run([exe, str(spec)], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr + out.stdout
     assert "test_cabi_gpu: ok" in out.stdout
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_vc_partition_over_ranks_matches_single_gpu_run(cuda_lib, world):
+    """the C3 cluster's 8 VCs partitioned over `world` ranks (here: `world` contexts on
+    one GPU, the two collectives done by hand — the protocol of hivedscheduler_b200/dist.py without the process
+    group); the chain hash over the merged results equals the hash of the ordinary single-context run."""
+    import torch
+    from test_multigpu_partition import simulate
+    t = trace.trace_c3(n_gangs=6000)
+    h1, _, _ = run_trace(cuda_lib, t)
+
+    def alloc(nbytes):
+        b = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+        return b, b.data_ptr()
+
+    h, rounds = simulate(cuda_lib, t, world, alloc=alloc)
+    assert h == h1
+    assert rounds >= 8
