@@ -215,6 +215,109 @@ def run_reference_arm(args):
     print(json.dumps(line))
 
 
+def frontend_leg(lib, n_events: int = 24000, clients: int = 32):
+    """The extender-shaped path: the first `n_events` events of the C3 trace as filter
+    calls / pod deletions through the pod state machine of include/hived_frontend.h.  Two shapes: (a) everything
+    queued, then drained (one hived_process_events per max_batch events); (b) `clients` concurrent callers blocking in
+    hived_fe_filter like HTTP handler threads, batches forming while the GPU is busy.  Parity: every pod must get the
+    node and GPUs the plain batch path gives it."""
+    import threading
+    from hivedscheduler_b200 import frontend as fe_mod
+    t = trace.trace_c3(n_gangs=max(2000, n_events // 2))
+    ev = t["events"][:n_events]
+    # the plain batch path: the reference answers
+    bc0 = trace.BatchContext(lib, t["config"], t["n_groups"], t["n_pods"], t["max_group_leaves"], t["max_group_pods"])
+    bc0.set_all_nodes_healthy()
+    res0, pool0 = bc0.process(ev, trace.pool_words_for(t))
+    bc0.close()
+    want = {}
+    pods, order, counters = {}, [], {}
+    for i in range(len(ev)):
+        e = ev[i]
+        g = int(e["spec"]["group"])
+        if e["type"] == _cabi.EV_SCHEDULE:
+            j = counters.get(g, 0)
+            counters[g] = j + 1
+            uid = "g%d-%d" % (g, j)
+            sp = e["spec"]
+            ann = ("virtualCluster: vc%d\npriority: %d\nleafCellType: B200\nleafCellNumber: %d\naffinityGroup:\n  name: default/gang%d\n"
+                   "  members:\n  - podNumber: %d\n    leafCellNumber: %d\n" % (sp["vc"], sp["priority"], sp["leaf_num"], g,
+                                                                               sp["member_pod_num"][0], sp["member_leaf_num"][0]))
+            pods[uid] = ann
+            order.append(("filter", uid))
+            r = res0[i]
+            want[uid] = (int(r["node"]), tuple(int(pool0[r["this_off"] + 3 * k + 1]) for k in range(int(r["this_n"])))) if r["kind"] == 1 else None
+        else:
+            order.append(("delete", "g%d-%d" % (g, int(e["arg0"]))))
+
+    def fresh(max_batch):
+        bc = trace.BatchContext(lib, t["config"], t["n_groups"], t["n_pods"], t["max_group_leaves"], t["max_group_pods"])
+        bc.set_all_nodes_healthy()
+        f = fe_mod.FrontEnd(lib, bc.ctx, t["n_groups"], t["n_pods"], max_batch=max_batch)
+        for uid, ann in pods.items():
+            f.add_unbound_pod(uid, "default/" + uid, ann)
+        return bc, f
+
+    def check(answers):
+        bad = 0
+        for uid, r in answers.items():
+            got = (int(r.node), tuple(r.leaf_index[:r.n_leaves])) if r.kind == fe_mod.FE_BIND else None
+            bad += got != want[uid]
+        return bad == 0
+
+    out = {"events": len(ev), "filter_calls": len(pods)}
+    # (a) queued, then drained
+    bc, f = fresh(4096)
+    t0 = time.perf_counter()
+    tickets = {}
+    for kind, uid in order:
+        if kind == "filter":
+            tickets[uid] = f.enqueue_filter(uid)
+        else:
+            f.delete_pod(uid)
+    t1 = time.perf_counter()
+    f.drain()
+    t2 = time.perf_counter()
+    answers = {uid: f.take(tk) for uid, tk in tickets.items()}
+    st = f.stats()
+    out["queued_then_drained"] = {"events_per_s": len(ev) / (t2 - t1), "drain_ms": 1e3 * (t2 - t1), "enqueue_ms": 1e3 * (t1 - t0),
+                                  "drains": st["drains"], "largest_batch": st["largest_batch"], "matches_batch_path": check(answers)}
+    f.close()
+    bc.close()
+    # (b) concurrent blocking callers; a pod's deletion is issued by the client that owns the pod's gang (order within
+    # a gang preserved; across gangs the arrival order is whatever the threads produce: parity is not defined, only
+    # that no GPU is handed out twice)
+    bc, f = fresh(4096)
+    per = [[] for _ in range(clients)]
+    for kind, uid in order:
+        per[int(uid[1:].split("-")[0]) % clients].append((kind, uid))
+    answers = {}
+
+    def client(items):
+        for kind, uid in items:
+            if kind == "filter":
+                answers[uid] = f.filter(uid)
+            else:
+                f.delete_pod(uid)
+
+    ths = [threading.Thread(target=client, args=(items,)) for items in per]
+    t0 = time.perf_counter()
+    for th in ths:
+        th.start()
+    for th in ths:
+        th.join()
+    f.drain()
+    dt = time.perf_counter() - t0
+    st = f.stats()
+    binds = sum(1 for r in answers.values() if r.kind == fe_mod.FE_BIND)
+    out["concurrent_clients"] = {"clients": clients, "events_per_s": len(ev) / dt, "us_per_filter_call": 1e6 * dt / max(1, len(pods)),
+                                 "drains": st["drains"], "mean_batch": st["events"] / max(1, st["drains"]), "largest_batch": st["largest_batch"],
+                                 "bind_answers": binds, "note": "Python client threads (GIL): a lower bound for a Go / C++ extender"}
+    f.close()
+    bc.close()
+    return out
+
+
 def main_partitioned(args, lib, rank, world, local):
     """N > 1: ONE C3 batch partitioned over the ranks by virtual cluster (include/hived_multigpu.h; strong scaling:
     the total work is fixed).  Every rank holds the whole cluster; the result of the job is the merged results."""
@@ -486,6 +589,7 @@ def main():
             line["cpu_flat"] = cpu_flat(t)
         if not args.no_other_configs and world == 1 and args.gangs == 100000:
             line["other_configs"] = other_configs(lib)
+            line["frontend"] = frontend_leg(lib)
         line["parity"] = {"result_hash": "%016x" % parity_hash}
         pc_names = ["view_bucketed", "view_full_pass", "bucket_rebuilds", "bucket_moves", "commit_lean", "commit_general",
                     "release_lean", "release_general", "map_lean", "map_general", "pod_of_gang_lean", "delete_pod_lean"]

@@ -959,3 +959,4 @@ int64_t hived_bench_kernel_launches(hived_ctx* ctx) { return ctx->e.kernelLaunch
 }  // extern "C"
 
 #include "hived_ingest.hpp"
+#include "hived_frontend.hpp"

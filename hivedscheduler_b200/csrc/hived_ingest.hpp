@@ -331,7 +331,7 @@ struct hived_ingest {
   std::string cachedText;
   std::vector<uint32_t> cachedBitmap;
   int32_t cachedCount = -1;
-  std::string err;
+  std::string err, lastGroup;
 
   void build() {
     size_t cap = 16;
@@ -385,6 +385,7 @@ int32_t hived_ingest_node_id(const hived_ingest* g, const char* name, int32_t le
   return g->find(name, len < 0 ? strlen(name) : (size_t)len);
 }
 const char* hived_ingest_last_error(const hived_ingest* g) { return g->err.c_str(); }
+const char* hived_ingest_last_group_name(const hived_ingest* g) { return g->lastGroup.c_str(); }
 
 int32_t hived_ingest_node_names(hived_ingest* g, const char* const* names, int32_t n, uint32_t* bm, int32_t* is_all) {
   memset(bm, 0, (size_t)g->words * 4);
@@ -573,6 +574,7 @@ int hived_ingest_pod_spec_yaml(hived_ingest* g, const char* yaml, int64_t len, c
   if (members.size() > HIVED_MAX_MEMBERS) { g->err = "affinity group has more members than HIVED_MAX_MEMBERS"; return HIVED_ERR_CAPACITY; }
   out->pod = pod_name ? g->pods.intern(pod_name, (int32_t)strlen(pod_name), max_pods) : -1;
   out->group = g->groups.intern(groupName.data(), (int32_t)groupName.size(), max_groups);
+  g->lastGroup = groupName;
   if (out->pod < 0 || out->group < 0) { g->err = "id table full (max_groups / max_pods)"; return HIVED_ERR_CAPACITY; }
   auto idOf = [](const std::unordered_map<std::string, int32_t>& m, const std::string& k, int32_t none, int32_t unknown) {
     if (k.empty()) return none;

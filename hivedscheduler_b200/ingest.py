@@ -24,6 +24,7 @@ SYMBOLS = [
     ("hived_ingest_pod_spec_yaml", C.c_int,
      [_P, C.c_char_p, C.c_int64, C.c_char_p, C.c_int32, C.c_int32, C.POINTER(_cabi.PodSpec)]),
     ("hived_ingest_last_error", C.c_char_p, [_P]),
+    ("hived_ingest_last_group_name", C.c_char_p, [_P]),
 ]
 
 

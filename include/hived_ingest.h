@@ -51,11 +51,12 @@ int32_t hived_ingest_release(hived_ingest*, int32_t kind, const char* name, int3
  * Interns the affinity group's name (group capacity `max_groups`) and `pod_name` (capacity `max_pods`); resolves
  * virtualCluster / leafCellType / pinnedCellId against the scheduler's tables.  Defaults as in
  * ExtractPodSchedulingSpec (internal/utils.go:244-287): no affinityGroup -> a gang of its own named after the pod;
- * leafCellNumber falls back to gpuNumber; the v1 field names (gpuType, gpuNumber, reservationId) are accepted.
+ * leafCellNumber falls back to gpuNumber; the v1 field names (gpuType, gpuNumber, ...: convertOldAnnotation :187-197) are accepted.
  * Returns 0, or HIVED_ERR_BAD_SPEC / HIVED_ERR_UNKNOWN_VC / ... with hived_ingest_last_error() describing why.    */
 int hived_ingest_pod_spec_yaml(hived_ingest*, const char* yaml, int64_t len, const char* pod_name, int32_t max_groups,
                                int32_t max_pods, hived_pod_spec_t* out);
 const char* hived_ingest_last_error(const hived_ingest*);
+const char* hived_ingest_last_group_name(const hived_ingest*);  /* AffinityGroup.Name of the last annotation parsed */
 #ifdef __cplusplus
 }
 #endif
