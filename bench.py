@@ -325,6 +325,7 @@ def main_partitioned(args, lib, rank, world, local):
     import torch.distributed as dist
     from hivedscheduler_b200 import dist as hd
     hd.bind_multigpu(lib)
+    on_gpu = torch.cuda.is_available()  # (False only in the gloo plumbing test of tests/test_multigpu_partition.py)
     t = trace.trace_c3(n_gangs=args.gangs)
     ev = t["events"]
     n = len(ev)
@@ -334,19 +335,20 @@ def main_partitioned(args, lib, rank, world, local):
     bc.set_all_nodes_healthy()
     ctx = bc.ctx
     lib.hived_bench_save_state(ctx)
-    ev_pinned = torch.empty(ev.nbytes, dtype=torch.uint8, pin_memory=True)
+    ev_pinned = torch.empty(ev.nbytes, dtype=torch.uint8, pin_memory=on_gpu)
     ev_pinned.numpy()[:] = ev.view(np.uint8)
     ev_ptr = C.cast(ev_pinned.data_ptr(), C.POINTER(_cabi.Event))
-    res_pinned = torch.empty(n * C.sizeof(_cabi.Result), dtype=torch.uint8, pin_memory=True)
-    pool_pinned = torch.empty(pool_words, dtype=torch.int32, pin_memory=True)
+    res_pinned = torch.empty(n * C.sizeof(_cabi.Result), dtype=torch.uint8, pin_memory=on_gpu)
+    pool_pinned = torch.empty(pool_words, dtype=torch.int32, pin_memory=on_gpu)
     res_ptr = C.cast(res_pinned.data_ptr(), C.POINTER(_cabi.Result))
     pool_ptr = C.cast(pool_pinned.data_ptr(), C.POINTER(C.c_int32))
-    device = "cuda:%d" % local
+    device = "cuda:%d" % local if on_gpu else "cpu"
     used = C.c_int64()
 
     def barrier():
         dist.barrier()
-        torch.cuda.synchronize()
+        if on_gpu:
+            torch.cuda.synchronize()
 
     info = {}
 
@@ -356,22 +358,26 @@ def main_partitioned(args, lib, rank, world, local):
         if not e2e:
             assert lib.hived_mg_reset(ctx) == 0
         barrier()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         k0 = lib.hived_bench_total_kernel_ms(ctx)
-        a.record()
+        if on_gpu:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+        t0 = time.perf_counter()
         info.update(hd.run_partitioned(lib, ctx, ev_ptr, n, pool_words, rank, world, device=device, staged=not e2e))
         if e2e:
             assert lib.hived_bench_fetch_results(ctx, res_ptr, pool_ptr, pool_words, C.byref(used)) == 0
-        b.record()
-        torch.cuda.synchronize()
+        if on_gpu:
+            b.record()
+            torch.cuda.synchronize()
         info["kernel_ms"] = lib.hived_bench_total_kernel_ms(ctx) - k0
-        return a.elapsed_time(b) / 1e3
+        return a.elapsed_time(b) / 1e3 if on_gpu else time.perf_counter() - t0
 
     assert lib.hived_mg_stage(ctx, ev_ptr, n, pool_words, rank, world) == 0, lib.hived_last_error(ctx)
     for _ in range(args.warmup):
         step(False)
     sampler = ClockSampler(local)
-    sampler.start()
+    if on_gpu:
+        sampler.start()
     launches0 = lib.hived_bench_kernel_launches(ctx)
     res_s = [step(False) for _ in range(args.steps)]
     launches = lib.hived_bench_kernel_launches(ctx) - launches0
@@ -380,8 +386,9 @@ def main_partitioned(args, lib, rank, world, local):
         step(True)
     e2e_s = [step(True) for _ in range(args.steps)]
     sampler.stop_flag.set()
-    sampler.join(timeout=2)
-    times = torch.tensor([sum(res_s), sum(e2e_s), kernel_ms / 1e3, coll_s], dtype=torch.float64, device="cuda")
+    if on_gpu:
+        sampler.join(timeout=2)
+    times = torch.tensor([sum(res_s), sum(e2e_s), kernel_ms / 1e3, coll_s], dtype=torch.float64, device=device)
     dist.all_reduce(times, op=dist.ReduceOp.MAX)
     tot_s, tot_e2e, kernel_s_last, coll_s_last = [float(x) for x in times.tolist()]
     # parity witness: the chain hash over the merged results of the last (e2e) step
@@ -410,7 +417,7 @@ def main_partitioned(args, lib, rank, world, local):
             "e2e": {"value": n_dec * args.steps / tot_e2e, "unit": "decisions/s", "h2d_bytes_per_step": int(ev.nbytes) * world,
                     "d2h_bytes_per_step": int(n * C.sizeof(_cabi.Result)) * world},
             "gpu_launches": int(launches) * world,
-            "clocks": sampler.summary(),
+            "clocks": sampler.summary() if on_gpu else None,
             "roofline": {"bound": "hbm", "achieved": stats["algorithmic_bytes"] / (tot_s / args.steps) / 1e9 * world, "peak": peak * world,
                          "unit": "GB/s", "frac": stats["algorithmic_bytes"] / (tot_s / args.steps) / 1e9 / peak, "traffic": None,
                          "kernel": "hived_events_kernel", "peak_source": peak_src,
@@ -439,6 +446,12 @@ def main():
     import torch
     import torch.distributed as dist
     rank, world, local = dist_env()
+    emu = os.environ.get("HIVED_BENCH_PLUMBING_TEST_LIB")  # tests only: the N > 1 plumbing under gloo, on the emulation library
+    if emu and world > 1 and not torch.cuda.is_available():
+        dist.init_process_group("gloo")
+        lib = _cabi.load_library(emu)
+        bind_bench_hooks(lib)
+        return main_partitioned(args, lib, rank, world, local)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)

@@ -44,6 +44,12 @@ constexpr int OPP_PRIO = HIVED_OPPORTUNISTIC_PRIORITY;
 constexpr int PF_AT_OR_ABOVE_NODE_BIT = 1, PF_NODE_LEVEL_BIT = 2, PF_PINNED_BIT = 4;
 
 // shared-memory block of the CTA
+// resident mode (Core::serve): slot geometry in 32-bit words
+constexpr int SERVE_MAX_EVENTS = 8, SERVE_POOL_WINDOW = 16384, SERVE_EV_OFF = 32, SERVE_SUGG_MAX = 8 * 512, SERVE_AUX_MAX = 8192;
+constexpr int SERVE_RES_OFF = SERVE_EV_OFF + SERVE_MAX_EVENTS * 32 + SERVE_SUGG_MAX + SERVE_AUX_MAX;
+constexpr int SERVE_DONE_OFF = SERVE_RES_OFF + SERVE_MAX_EVENTS * 32 + SERVE_POOL_WINDOW;
+constexpr int SERVE_SLOT_WORDS = SERVE_DONE_OFF + 32;
+
 struct Sm {
   int cmd;  // CMD_*
   // ---- view-pass arguments
@@ -3118,7 +3124,7 @@ struct Core {
           hv_warp_sync();
         }
         int i = ownAt(k);
-        if (lane == 0) hv_st_volatile(&sm->lead_k, k);
+        if (lane == 0) hv_publish_smem(&sm->lead_k, k);
         curEvent = i;
         sharedHeld = false;
         long long tq = pclock();
@@ -3152,7 +3158,7 @@ struct Core {
         }
         dbg(15, tq);
       }
-      if (lane == 0) hv_st_volatile(&sm->lead_k, 0x7fffffff);
+      if (lane == 0) hv_publish_smem(&sm->lead_k, 0x7fffffff);
       flushWork();
       ST(sm->pool_off, poolOff);
       ST(sm->stop_k, stopK);
@@ -3170,6 +3176,83 @@ struct Core {
       }
     }
   }
+
+#if defined(__CUDACC__) && !defined(HIVED_EMU)
+  // ---- resident ("serve") mode: the per-call path without a launch per call (hived_cuda.cu bk_run_small) ----------
+  // The leader polls a request slot in MAPPED HOST memory, runs the request's events (at most SERVE_MAX_EVENTS) and
+  // writes results + pool words back to mapped host memory; the workers serve view passes as in run().  The kernel
+  // leaves by itself after `idleSpins` empty polls (a resident kernel must not outlive the calls it serves: any
+  // device-wide synchronisation elsewhere in the process would wait for it) or on a STOP request.
+  // slot layout: see ServeSlot in hived_cuda.cu; all offsets in 32-bit words.
+  HIVED_DEV void serve(volatile int32_t* slot, int seq0, int idleSpins, hived_result_t* stageRes, uint32_t* dSugg, int32_t* dAux,
+                       int nPinnedOrder, int nBad) {
+    (void)nPinnedOrder; (void)nBad;
+    if (hv_warp() == 0) {
+      int lastSeq = seq0;
+      ST(sm->bkc_sched, -1);
+      while (true) {
+        int seq = lastSeq, spins = 0;
+        // header line: [0] seq  [1] n (0 = STOP)  [2] suggWords  [3] auxWords  [4] poolCap
+        int hdr = 0;
+        while (true) {
+          hdr = lane < 8 ? slot[lane] : 0;
+          seq = hv_shfl(hdr, 0);
+          if (seq != lastSeq) break;
+          if (++spins > idleSpins) break;
+        }
+        if (seq == lastSeq) break;  // idle: leave
+        const int n = hv_shfl(hdr, 1), suggWords = hv_shfl(hdr, 2), auxWords = hv_shfl(hdr, 3);
+        pool_cap = hv_shfl(hdr, 4);
+        lastSeq = seq;
+        if (n <= 0) break;  // STOP
+        // payload: events at word SERVE_EV_OFF, then the suggested bitmaps, then aux
+        const volatile int32_t* pay = slot + SERVE_EV_OFF;
+        const int evWords = (int)(sizeof(hived_event_t) / 4);
+        const volatile int32_t* hs = pay + SERVE_MAX_EVENTS * evWords;
+        for (int i = lane; i < suggWords; i += HIVED_WARPSZ) dSugg[i] = (uint32_t)hs[i];
+        const volatile int32_t* ha = hs + suggWords;
+        for (int i = lane; i < auxWords; i += HIVED_WARPSZ) dAux[i] = ha[i];
+        hv_warp_sync();
+        poolOff = 0;
+        for (int k = 0; k < n; k++) {
+          int32_t* cur = sm->ev_words[k & 1];
+          for (int i = lane; i < evWords; i += HIVED_WARPSZ) cur[i] = pay[k * evWords + i];
+          hv_warp_sync();
+          curEvent = k;
+          sharedHeld = false;
+          processEvent(*reinterpret_cast<const hived_event_t*>(cur), &stageRes[k], suggWords > 0 ? dSugg : nullptr, auxWords > 0 ? dAux : nullptr);
+        }
+        flushWork();
+        hv_warp_sync();
+        // response: results at SERVE_RES_OFF, pool window after them, then [poolOff, panic]; `done` last
+        volatile int32_t* out = slot + SERVE_RES_OFF;
+        const int32_t* sr = reinterpret_cast<const int32_t*>(stageRes);
+        const int resWords = n * (int)(sizeof(hived_result_t) / 4);
+        for (int i = lane; i < resWords; i += HIVED_WARPSZ) out[i] = sr[i];
+        volatile int32_t* op = out + SERVE_MAX_EVENTS * (int)(sizeof(hived_result_t) / 4);
+        const long long used = poolOff < SERVE_POOL_WINDOW ? poolOff : SERVE_POOL_WINDOW;
+        for (int i = lane; i < (int)used; i += HIVED_WARPSZ) op[i] = pool[i];
+        if (lane == 0) { slot[SERVE_DONE_OFF + 1] = (int32_t)poolOff; slot[SERVE_DONE_OFF + 2] = (int32_t)(poolOff >> 32); }
+        __threadfence_system();
+        hv_warp_sync();
+        if (lane == 0) slot[SERVE_DONE_OFF] = seq;
+        hv_warp_sync();
+      }
+      ST(sm->cmd, CMD_EXIT);
+      hv_cta_sync();
+      if (lane == 0) { __threadfence_system(); slot[SERVE_DONE_OFF + 3] = lastSeq; slot[SERVE_DONE_OFF + 4] = 1; }  // exited
+    } else if (hv_is_runahead()) {
+      return;
+    } else {
+      while (true) {
+        hv_cta_sync();
+        if (sm->cmd == CMD_EXIT) break;
+        sugg = sm->a_sugg;
+        viewOp();
+      }
+    }
+  }
+#endif
 };
 
 }  // namespace hived

@@ -51,6 +51,22 @@ __global__ void __launch_bounds__(NT, 1) hived_repair_kernel(const __grid_consta
   core.repairSharedAncestors();
 }
 
+// The per-call path, resident: one CTA that stays on an SM while calls keep coming (Core::serve).
+__global__ void __launch_bounds__(NT, 1)
+hived_serve_kernel(const __grid_constant__ Dev dev, volatile int32_t* slot, int seq0, int idleSpins, hived_result_t* stageRes,
+                   uint32_t* dSugg, int32_t* dAux, int nPinnedOrder, int nBad, int32_t* pool) {
+  __shared__ Sm sm;
+  if (threadIdx.x == 0) {
+    sm.cmd = CMD_IDLE;
+    sm.panic = 0;
+    sm.lead_k = 0x7fffffff;
+    sm.pool_off = 0;
+  }
+  __syncthreads();
+  Core core(dev, &sm, pool, 0, 1);
+  core.serve(slot, seq0, idleSpins, stageRes, dSugg, dAux, nPinnedOrder, nBad);
+}
+
 static bool cudaOk(cudaError_t e, std::string& err, const char* what) {
   if (e == cudaSuccess) return true;
   err = std::string(what) + ": " + cudaGetErrorString(e);
@@ -102,7 +118,35 @@ int bk_init(int& device, std::string& err) {
 struct CudaTimers {
   cudaEvent_t start = nullptr, stop = nullptr;
   cudaStream_t stream = nullptr;
+  // resident per-call kernel (bk_run_small): a non-blocking stream of its own, one request slot in mapped host memory
+  cudaStream_t serveStream = nullptr;
+  volatile int32_t* slotHost = nullptr;  // cudaHostAlloc(mapped)
+  int32_t* slotDev = nullptr;
+  hived_result_t* stageRes = nullptr;
+  uint32_t* dSugg = nullptr;
+  int32_t* dAux = nullptr;
+  int32_t* servePool = nullptr;
+  long long servePoolCap = 0;
+  int seq = 0;
+  bool alive = false;    // a serve kernel was launched and has not been seen to exit
+  bool disabled = false; // HIVED_NO_RESIDENT=1, or setting it up failed: one launch per call
+  long long served = 0, launches = 0;
 };
+
+// Stop the resident kernel (if any) and wait until it has left: before anything else launches on or writes to the
+// scheduler state.  Called with the context's device current.
+void bk_quiesce(Engine& e) {
+  CudaTimers* t = (CudaTimers*)e.stream;
+  if (!t || !t->alive) return;
+  volatile int32_t* s = t->slotHost;
+  if (!s[SERVE_DONE_OFF + 4]) {
+    s[1] = 0;  // n = 0: STOP
+    __sync_synchronize();
+    s[0] = ++t->seq;
+  }
+  cudaStreamSynchronize(t->serveStream);
+  t->alive = false;
+}
 
 static_assert(NT / 32 <= MAX_WARPS, "the shared counters are sized for MAX_WARPS warps per CTA");
 
@@ -117,6 +161,7 @@ int launchProgram(Engine& e, int n, bool withInit) {
     e.stream = t;
   }
   CudaTimers* t = (CudaTimers*)e.stream;
+  bk_quiesce(e);
   const int mgMode = withInit ? 0 : e.mgMode;
   if (mgMode == 3) {  // end of a multi-GPU partition run: the repair pass alone
     hived_repair_kernel<<<1, NT, 0, t->stream>>>(e.dev);
@@ -194,10 +239,108 @@ struct SmallStage {  // never freed: a few KB of pinned memory per calling threa
 };
 static constexpr int64_t SMALL_POOL_WINDOW = 16384;  // words copied back with the results; more on demand
 
+// ---- resident per-call path -------------------------------------------------------------------------------------
+// One request slot in mapped, pinned host memory.  The host writes the payload, then the header's sequence number
+// (x86 stores are observed in order); the resident leader warp polls the header over PCIe, runs the events, writes
+// results and pool words back into the slot, fences system-wide and stores `done`.  No launch, no cudaMemcpy, no
+// stream synchronisation per call.  The kernel leaves after ~2 ms without a request and is relaunched on demand.
+static bool serveSetup(Engine& e, CudaTimers* t) {
+  if (t->disabled) return false;
+  if (t->slotHost) return true;
+  const char* off = getenv("HIVED_NO_RESIDENT");
+  if (off && *off && *off != '0') { t->disabled = true; return false; }
+  void* h = nullptr;
+  if (cudaStreamCreateWithFlags(&t->serveStream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaHostAlloc(&h, (size_t)SERVE_SLOT_WORDS * 4, cudaHostAllocMapped) != cudaSuccess) { t->disabled = true; return false; }
+  memset(h, 0, (size_t)SERVE_SLOT_WORDS * 4);
+  t->slotHost = (volatile int32_t*)h;
+  void* d = nullptr;
+  if (cudaHostGetDevicePointer(&d, h, 0) != cudaSuccess) { t->disabled = true; return false; }
+  t->slotDev = (int32_t*)d;
+  t->servePoolCap = 3ll * e.dev.S.LS + 2 * 4096 + 64 > SERVE_POOL_WINDOW ? 3ll * e.dev.S.LS + 2 * 4096 + 64 : SERVE_POOL_WINDOW;
+  t->servePoolCap *= SERVE_MAX_EVENTS;
+  if (cudaMalloc((void**)&t->stageRes, sizeof(hived_result_t) * SERVE_MAX_EVENTS) != cudaSuccess ||
+      cudaMalloc((void**)&t->dSugg, (size_t)SERVE_SUGG_MAX * 4) != cudaSuccess || cudaMalloc((void**)&t->dAux, (size_t)SERVE_AUX_MAX * 4) != cudaSuccess ||
+      cudaMalloc((void**)&t->servePool, (size_t)t->servePoolCap * 4) != cudaSuccess) { t->disabled = true; return false; }
+  cudaFuncSetAttribute(hived_serve_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 10);
+  return true;
+}
+
+static int serveCall(Engine& e, CudaTimers* t, const hived_event_t* events, int n, const uint32_t* suggPool, int64_t suggWords,
+                     const int32_t* aux, int64_t auxWords, hived_result_t* res, int32_t* pool, int64_t poolCap) {
+  const bool hasSugg = suggPool != nullptr && suggWords > 0, hasAux = aux != nullptr && auxWords > 0;
+  if (n > SERVE_MAX_EVENTS || (hasSugg && suggWords > SERVE_SUGG_MAX) || (hasAux && auxWords > SERVE_AUX_MAX)) return -2;
+  if (!serveSetup(e, t)) return -2;
+  const long long cap = poolCap < t->servePoolCap ? poolCap : t->servePoolCap;
+  e.notePriorities(events, n);
+  e.launchCta = 1;
+  e.hasSugg = hasSugg; e.hasAux = hasAux;
+  e.poolCapWords = poolCap; e.stagedN = n; e.stagedEvents = events; e.canonicalDone = false;
+  volatile int32_t* s = t->slotHost;
+  int32_t* pay = (int32_t*)(s + SERVE_EV_OFF);
+  memcpy(pay, events, (size_t)n * sizeof(hived_event_t));
+  int32_t* hs = pay + SERVE_MAX_EVENTS * (int)(sizeof(hived_event_t) / 4);
+  if (hasSugg) memcpy(hs, suggPool, (size_t)suggWords * 4);
+  if (hasAux) memcpy(hs + (hasSugg ? suggWords : 0), aux, (size_t)auxWords * 4);
+  s[1] = n; s[2] = hasSugg ? (int32_t)suggWords : 0; s[3] = hasAux ? (int32_t)auxWords : 0; s[4] = (int32_t)cap;
+  const int seq = ++t->seq;
+  __sync_synchronize();
+  s[0] = seq;
+  auto launch = [&]() {
+    s[SERVE_DONE_OFF + 4] = 0;
+    __sync_synchronize();
+    // ~1.5 us per poll over PCIe: leave after about 2 ms without a request
+    hived_serve_kernel<<<1, NT, 0, t->serveStream>>>(e.dev, t->slotDev, seq - 1, 1500, t->stageRes, t->dSugg, t->dAux, e.nPinnedOrder,
+                                                      e.nBad, t->servePool);
+    t->alive = true;
+    t->launches++;
+    e.kernelLaunches++;
+  };
+  if (!t->alive) launch();
+  // wait for `done`; a kernel that left just before the request arrived is replaced
+  long long spins = 0;
+  while (s[SERVE_DONE_OFF] != seq) {
+    if (s[SERVE_DONE_OFF + 4] && s[SERVE_DONE_OFF] != seq) {
+      cudaError_t err = cudaStreamSynchronize(t->serveStream);
+      if (err != cudaSuccess) { e.err = std::string("hived_serve_kernel failed: ") + cudaGetErrorString(err); t->alive = false; return HIVED_ERR_PLATFORM; }
+      if (s[SERVE_DONE_OFF] == seq) break;
+      launch();
+    }
+    if ((++spins & 0xfffff) == 0) {  // every ~million polls: is the kernel still healthy?
+      cudaError_t err = cudaStreamQuery(t->serveStream);
+      if (err != cudaSuccess && err != cudaErrorNotReady) {
+        e.err = std::string("hived_serve_kernel failed: ") + cudaGetErrorString(err);
+        t->alive = false;
+        return HIVED_ERR_PLATFORM;
+      }
+    }
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#endif
+  }
+  __sync_synchronize();
+  t->served++;
+  const long long used = (long long)(uint32_t)s[SERVE_DONE_OFF + 1] | ((long long)s[SERVE_DONE_OFF + 2] << 32);
+  e.poolOff = used;
+  e.poolEnd.assign(1, used);
+  e.lastKernelMs = 0.f;
+  if (used > cap) return HIVED_ERR_CAPACITY;
+  memcpy(res, (const void*)(s + SERVE_RES_OFF), (size_t)n * sizeof(hived_result_t));
+  const long long got = used < SERVE_POOL_WINDOW ? used : SERVE_POOL_WINDOW;
+  if (got > 0) memcpy(pool, (const void*)(s + SERVE_RES_OFF + SERVE_MAX_EVENTS * (int)(sizeof(hived_result_t) / 4)), (size_t)got * 4);
+  if (used > SERVE_POOL_WINDOW)
+    cudaMemcpy(pool + SERVE_POOL_WINDOW, t->servePool + SERVE_POOL_WINDOW, (size_t)(used - SERVE_POOL_WINDOW) * 4, cudaMemcpyDeviceToHost);
+  return 0;
+}
+
 int bk_run_small(Engine& e, const hived_event_t* events, int n, const uint32_t* suggPool, int64_t suggWords, const int32_t* aux,
                  int64_t auxWords, hived_result_t* res, int32_t* pool, int64_t poolCap) {
   if (!e.stream) return -1;  // the first launch (initialisation) creates the stream
   CudaTimers* t = (CudaTimers*)e.stream;
+  {
+    int rc = serveCall(e, t, events, n, suggPool, suggWords, aux, auxWords, res, pool, poolCap);
+    if (rc != -2) return rc;  // -2: the resident path does not take this call
+  }
   static thread_local SmallStage stage;  // per host thread; the shim serialises calls per context anyway
   const bool hasSugg = suggPool != nullptr && suggWords > 0, hasAux = aux != nullptr && auxWords > 0;
   const int64_t window = poolCap < SMALL_POOL_WINDOW ? poolCap : SMALL_POOL_WINDOW;

@@ -30,6 +30,7 @@ void bk_h2d(void* dst, const void* src, size_t bytes);
 void bk_d2h(void* dst, const void* src, size_t bytes);
 void bk_d2d(void* dst, const void* src, size_t bytes);
 void bk_zero(void* dst, size_t bytes);
+void bk_quiesce(Engine& e);  // stop a resident per-call kernel before the state is written from elsewhere (CUDA backend)
 int bk_init(int& device, std::string& err);  // device: in = requested ordinal, out = the one in use
 void bk_use_device(int device);  // make `device` current for the calling thread (contexts on several GPUs in one process)
 // runs the program over n staged events; returns 0 or a HIVED_ERR_* code
@@ -76,6 +77,8 @@ struct Engine {
   std::vector<long long> poolEnd;       // [launchCta] first unused word of every slice after the run
   std::vector<uint8_t> ownerOf;         // owner CTA of every event of the batch being prepared (MAX_CTAS <= 255)
   std::vector<char> nodeBadHost;        // host mirror of the node health (decides whether a batch may run VC-parallel)
+  std::vector<int32_t> groupStamp;      // batch that last named a group id (the two-VCs check is per batch)
+  int32_t batchStamp = 0;
   std::vector<int32_t> groupVcHost;     // VC under which a group id was last scheduled (-1: never): DELETE events are routed
                                         // by it, not by the VC field of the event (which hived_delete_allocated_pod leaves 0)
   int badCount = 0;
@@ -94,6 +97,7 @@ struct Engine {
   void* stream = nullptr;
 
   ~Engine() {
+    bk_quiesce(*this);
     for (void* p : allocs) bk_free(p);
     for (void* p : savedRegions) bk_free(p);
   }
@@ -229,6 +233,8 @@ struct Engine {
   // opportunistic cells), no recovery calls, and only SCHEDULE / DELETE events with valid VC ids.
   int prepare(const hived_event_t* events, int n, int64_t poolCap) {
     launchCta = 1;
+    batchStamp++;
+    if (groupStamp.size() != groupVcHost.size()) groupStamp.assign(groupVcHost.size(), 0);
     uint64_t mask = prioMaskHost;
     bool simple = nCtaMax > 1 && n >= 256 && badCount == 0 && !everRecovered;
     // one pass over the events: regime flags, the owner CTA of every event and the pool words every owner may need
@@ -249,12 +255,16 @@ struct Engine {
       const int g = ev.spec.group;
       if (ev.type == HIVED_EV_SCHEDULE || ev.type == Core::EV_SCHEDULE_ONLY) {
         if (g >= 0 && g < (int)groupVcHost.size() && ev.spec.vc >= 0 && ev.spec.vc < T.nVCs) {
-          if (groupVcHost[g] >= 0 && groupVcHost[g] != ev.spec.vc) simple = false;
+          // a group id that THIS batch has already used under another VC (ids are recycled, hived.h "Id lifetime": the
+          // old incarnation's release and the new one's creation would meet in the same table row on two CTAs)
+          if (groupStamp[g] == batchStamp && groupVcHost[g] >= 0 && groupVcHost[g] != ev.spec.vc) simple = false;
           groupVcHost[g] = ev.spec.vc;
+          groupStamp[g] = batchStamp;
         }
       } else if (ev.type == HIVED_EV_DELETE_ALLOCATED) {
         evVc = (g >= 0 && g < (int)groupVcHost.size()) ? groupVcHost[g] : -1;
         if (evVc < 0) evVc = (ev.spec.vc >= 0 && ev.spec.vc < T.nVCs) ? ev.spec.vc : 0;  // unknown group: a no-op wherever it runs
+        if (g >= 0 && g < (int)groupStamp.size()) groupStamp[g] = batchStamp;
       }
       if (evVc < 0 || evVc >= T.nVCs) simple = false;
       if (ev.type == Core::EV_ADD_ALLOCATED) everRecovered = true;
@@ -431,6 +441,7 @@ struct Engine {
   }
   void mgImportShared(const void* src) {
     bk_use_device(deviceOrdinal);
+    bk_quiesce(*this);
     const char* o = (const char*)src;
     for (auto& r : sharedArrays()) { if (r.second) bk_d2d(r.first, o, r.second); o += (r.second + 15) & ~(size_t)15; }
   }
@@ -438,6 +449,8 @@ struct Engine {
     bk_use_device(deviceOrdinal);
     if (world < 1 || rank < 0 || rank >= world) { err = "multi-GPU partition: bad rank/world"; return HIVED_ERR_BAD_SPEC; }
     if (badCount != 0 || everRecovered) { err = "multi-GPU partition: only calm batches (every node healthy, no recovery)"; return HIVED_ERR_BAD_SPEC; }
+    batchStamp++;
+    if (groupStamp.size() != groupVcHost.size()) groupStamp.assign(groupVcHost.size(), 0);
     uint64_t mask = prioMaskHost;
     const int C = (T.nVCs - rank + world - 1) / world > 0 ? (T.nVCs - rank + world - 1) / world : 0;
     if (C > MAX_CTAS) { err = "multi-GPU partition: more VCs per rank than CTAs"; return HIVED_ERR_CAPACITY; }
@@ -453,10 +466,12 @@ struct Engine {
         int p = ev.spec.priority;
         mask |= (p >= -1 && p < 62) ? (1ull << (p + 1)) : (1ull << 62);
         if (g >= 0 && g < (int)groupVcHost.size() && evVc >= 0 && evVc < T.nVCs) {
-          if (groupVcHost[g] >= 0 && groupVcHost[g] != evVc) { err = "multi-GPU partition: a group id used under two VCs"; return HIVED_ERR_BAD_SPEC; }
+          if (groupStamp[g] == batchStamp && groupVcHost[g] >= 0 && groupVcHost[g] != evVc) { err = "multi-GPU partition: a group id used under two VCs in one batch"; return HIVED_ERR_BAD_SPEC; }
           groupVcHost[g] = evVc;
+          groupStamp[g] = batchStamp;
         }
       } else {
+        if (g >= 0 && g < (int)groupStamp.size()) groupStamp[g] = batchStamp;
         evVc = (g >= 0 && g < (int)groupVcHost.size()) ? groupVcHost[g] : -1;
         if (evVc < 0) evVc = (ev.spec.vc >= 0 && ev.spec.vc < T.nVCs) ? ev.spec.vc : 0;
       }
@@ -571,6 +586,7 @@ struct Engine {
   }
   int restoreState() {
     if (savedRegions.empty()) return HIVED_ERR_PLATFORM;
+    bk_quiesce(*this);
     for (size_t i = 0; i < mutableRegions.size(); i++) bk_d2d(mutableRegions[i].first, savedRegions[i], mutableRegions[i].second);
     hash = savedHash;
     return 0;

@@ -26,6 +26,8 @@ inline bool hv_is_runahead() { return false; }
 inline void hv_nanosleep() {}
 inline void hv_touch(const void*) {}
 inline void hv_cta_sync() {}
+inline void hv_publish_smem(int* p, int v) { *(volatile int*)p = v; }
+inline int hv_peek_smem(int* p) { return *(volatile int*)p; }
 inline void hv_warp_sync() {}
 inline void hv_phase() {}
 inline unsigned hv_ballot(bool p) { return p ? 1u : 0u; }
@@ -91,6 +93,8 @@ inline bool hv_is_runahead() { return hv_has_runahead() && simt::warp() == hv_nw
 inline void hv_nanosleep() { simt::yield_to_scheduler(); }
 inline void hv_touch(const void* p) { (void)*(const volatile char*)p; }
 inline void hv_cta_sync() { simt::cta_barrier_n(hv_nth()); }
+inline void hv_publish_smem(int* p, int v) { *(volatile int*)p = v; }
+inline int hv_peek_smem(int* p) { simt::yield_to_scheduler(); return *(volatile int*)p; }
 inline void hv_warp_sync() { simt::warp_collective(0, [](const int*, int*) {}); }
 // phase boundary: every lane has finished the reads of the phase before any lane starts the writes of the next one
 inline void hv_phase() { hv_warp_sync(); }
@@ -176,7 +180,22 @@ __device__ __forceinline__ void hv_touch(const void* p) {
   unsigned t;
   asm volatile("ld.global.ca.u32 %0, [%1];" : "=r"(t) : "l"(p));
 }
+// named barrier 1 over the leader + worker warps (the run-ahead warp never joins).  The leader and the workers reach it
+// from different instructions, so it is the UNALIGNED form (PTX: bar.sync == barrier.sync.aligned asks every
+// participant to execute the same barrier instruction; compute-sanitizer synccheck enforces that).
+#ifdef HIVED_AB_ALIGNED_BAR  // (A/B builds only)
 __device__ __forceinline__ void hv_cta_sync() { asm volatile("bar.sync 1, %0;" ::"r"(blockDim.x - 32) : "memory"); }
+#else
+__device__ __forceinline__ void hv_cta_sync() { asm volatile("barrier.sync 1, %0;" ::"r"(blockDim.x - 32) : "memory"); }
+#endif
+// a progress word in SHARED memory polled by another warp of the CTA (the run-ahead warp follows the leader): atomic
+// on both sides, so that the intended concurrent access is not a data race (compute-sanitizer racecheck)
+#ifdef HIVED_AB_VOLATILE_PUBLISH  // (A/B builds only)
+__device__ __forceinline__ void hv_publish_smem(int* p, int v) { *(volatile int*)p = v; }
+#else
+__device__ __forceinline__ void hv_publish_smem(int* p, int v) { atomicExch(p, v); }
+#endif
+__device__ __forceinline__ int hv_peek_smem(int* p) { return atomicAdd(p, 0); }
 __device__ __forceinline__ void hv_warp_sync() { __syncwarp(); }
 // phase boundary of the leader warp's uniform code (all lanes read, then one or all lanes write the same locations).
 // The warp is converged there (uniform control flow, no divergent call in between), so the hardware executes the

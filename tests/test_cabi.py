@@ -26,16 +26,17 @@ def test_header_symbols_are_bound_and_exported():
         assert getattr(lib, sym) is not None
     assert lib.hived_backend() == b"cuda-sm100a"
     # the other headers of include/: measurement hooks, multi-GPU partition, request ingest
-    from hivedscheduler_b200 import dist, ingest
+    from hivedscheduler_b200 import dist, frontend, ingest
     dist.bind_multigpu(lib)
     ingest.bind(lib)
-    typed = {n for n, _, _ in ingest.SYMBOLS}
-    for header in ("hived_bench.h", "hived_multigpu.h", "hived_ingest.h"):
+    frontend.bind(lib)
+    typed = {n for n, _, _ in ingest.SYMBOLS} | {n for n, _, _ in frontend.SYMBOLS}
+    for header in ("hived_bench.h", "hived_multigpu.h", "hived_ingest.h", "hived_frontend.h"):
         syms = declared_symbols(header)
         assert syms, header
         for sym in syms:
             assert getattr(lib, sym) is not None, "%s declares %s but the library does not export it" % (header, sym)
-            if header == "hived_ingest.h":
+            if header in ("hived_ingest.h", "hived_frontend.h"):
                 assert sym in typed, sym
 
 

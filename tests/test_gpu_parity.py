@@ -252,3 +252,62 @@ def test_vc_partition_over_ranks_matches_single_gpu_run(cuda_lib, world):
     h, rounds = simulate(cuda_lib, t, world, alloc=alloc)
     assert h == h1
     assert rounds >= 8
+
+
+def test_frontend_batch_drain_on_gpu(cuda_lib, oracle_lib):
+    """SURVEY.md section 8 row f4 on the GPU: queued filter calls and pod deletions answered from ONE
+    hived_process_events batch give every pod the node and GPUs the reference-shaped mirror (one Schedule +
+    AddAllocatedPod at a time, on the CPU checker) gives it; request bodies go through the ingest helpers (f1)."""
+    import json as _json
+    from hivedscheduler_b200 import frontend as fe_mod
+    import test_frontend as tf
+    bc = trace.BatchContext(cuda_lib, tf.cluster(), tf.MAXG, tf.MAXP, 64, 8)
+    bc.set_all_nodes_healthy()
+    f = fe_mod.FrontEnd(cuda_lib, bc.ctx, tf.MAXG, tf.MAXP)
+    pods = tf.workload(120)
+    deletes = {10: "uid-3", 25: "uid-7", 40: "uid-g4-1", 90: "uid-51"}
+    want = tf.mirror_answers(oracle_lib, pods, deletes)
+    names = [cuda_lib.hived_node_name(bc.ctx, i).decode() for i in range(bc.n_nodes)]
+    body = _json.dumps(names).encode()  # kube-scheduler found every node feasible
+    for uid, key, ann in pods:
+        assert f.add_unbound_pod(uid, key, ann) == 0
+    tickets = {}
+    for k, (uid, key, ann) in enumerate(pods):
+        tickets[uid] = f.enqueue_filter(uid, body)
+        if k in deletes:
+            f.delete_pod(deletes[k])
+    assert f.drain() == 0
+    got = {uid: tf.fe_answer(f, cuda_lib, bc, f.take(t)) for uid, t in tickets.items()}
+    assert got == want
+    st = f.stats()
+    assert st["drains"] <= 1 + len(deletes) and st["events"] == len(pods) + len(deletes)
+    # and one at a time (the per-call path of the engine) from a fresh scheduler: the same answers
+    f.close()
+    bc.close()
+    bc = trace.BatchContext(cuda_lib, tf.cluster(), tf.MAXG, tf.MAXP, 64, 8)
+    bc.set_all_nodes_healthy()
+    f = fe_mod.FrontEnd(cuda_lib, bc.ctx, tf.MAXG, tf.MAXP)
+    got = {}
+    for k, (uid, key, ann) in enumerate(pods):
+        f.add_unbound_pod(uid, key, ann)
+        got[uid] = tf.fe_answer(f, cuda_lib, bc, f.filter(uid, body))
+        if k in deletes:
+            f.delete_pod(deletes[k])
+    assert got == want
+    f.close()
+    bc.close()
+
+
+def test_shared_section_protocol_litmus(tmp_path):
+    """The message-passing protocol of the ordered shared sections (plain stores, fence, volatile progress word /
+    spin, fence, plain loads through a warm L1) with the library's own primitives: tests/litmus/shared_enter_litmus.cu."""
+    import shutil
+    import subprocess
+    if shutil.which("nvcc") is None:
+        pytest.skip("nvcc is not on PATH")
+    exe = str(tmp_path / "litmus")
+    subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17", "-w", "-o", exe,
+                           os.path.join(HERE, "litmus", "shared_enter_litmus.cu")])
+    out = subprocess.run([exe, "20000", "4096"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "shared_enter_litmus: ok" in out.stdout
