@@ -82,6 +82,9 @@ struct Sm {
   int panic;
   long long pool_off;
 };
+#if defined(__CUDACC__) && !defined(HIVED_SIMT_EMU) && !defined(HIVED_EMU)
+__shared__ Sm g_hived_sm;  // one per CTA (both kernels of hived_cuda.cu use it)
+#endif
 
 enum { CMD_IDLE = 0, CMD_VIEW = 1, CMD_EXIT = 2 };
 
@@ -96,7 +99,14 @@ enum { CMD_IDLE = 0, CMD_VIEW = 1, CMD_EXIT = 2 };
 
 struct Core {
   const Dev& d;
-  Sm* sm;
+#if defined(__CUDACC__) && !defined(HIVED_SIMT_EMU) && !defined(HIVED_EMU)
+  // the CTA's shared block is ONE file-scope __shared__ object: every access compiles to LDS / STS / ATOMS (through a
+  // generic Sm* the compiler loses the address space as soon as `this` goes through memory: LD.E / ATOM.E)
+  HIVED_DEV static Sm* smp() { return &g_hived_sm; }
+#else
+  Sm* sm_;
+  Sm* smp() const { return sm_; }
+#endif
   const uint32_t* sugg;  // suggested-node bitmap of the current event (nullptr = every node)
   int32_t* pool;
   long long pool_cap;
@@ -117,13 +127,17 @@ struct Core {
   bool sharedHeld;   // this event already holds the right to touch the cluster-wide free-list state
 
   HIVED_DEV Core(const Dev& dev, Sm* s_, int32_t* pool_, long long cap, int nCta_)
-      : d(dev), sm(s_), sugg(nullptr), pool(pool_), pool_cap(cap), poolOff(0), panicCode(0), lane(hv_lane()), AS(dev.S.AS),
+      : d(dev),
+#if !(defined(__CUDACC__) && !defined(HIVED_SIMT_EMU) && !defined(HIVED_EMU))
+        sm_(s_),
+#endif
+        sugg(nullptr), pool(pool_), pool_cap(cap), poolOff(0), panicCode(0), lane(hv_lane()), AS(dev.S.AS),
         s(dev.scratch[hv_cta()]), cta(hv_cta()), nCta(nCta_), multi(nCta_ > 1), curEvent(0), sharedHeld(false), prioMask(0) {
     for (int i = 0; i < N_WORK; i++) work[i] = 0;
     for (int i = 0; i < PC_COUNT; i++) pathCnt[i] = 0;
     if (dev.S.LS <= 64 && dev.S.PS <= 16) {
-      s.pl_v = sm->sc_pl_v; s.pl_p = sm->sc_pl_p; s.pl_v2 = sm->sc_pl_v2; s.pl_p2 = sm->sc_pl_p2;
-      s.pod_need = sm->sc_pod_need; s.pod_pos = sm->sc_pod_pos; s.pod_cell = sm->sc_pod_cell; s.pod_unit = sm->sc_pod_unit;
+      s.pl_v = smp()->sc_pl_v; s.pl_p = smp()->sc_pl_p; s.pl_v2 = smp()->sc_pl_v2; s.pl_p2 = smp()->sc_pl_p2;
+      s.pod_need = smp()->sc_pod_need; s.pod_pos = smp()->sc_pod_pos; s.pod_cell = smp()->sc_pod_cell; s.pod_unit = smp()->sc_pod_unit;
     }
   }
 
@@ -1116,7 +1130,7 @@ struct Core {
   HIVED_DEV static int infoHealthy(int w) { return (w >> 27) & 1; }
   HIVED_DEV static int infoSuggested(int w) { return (w >> 28) & 1; }
 
-  // CTA-wide exclusive prefix sum of sm->cnt[0..n) (row-major: bin-major, warp-minor)
+  // CTA-wide exclusive prefix sum of smp()->cnt[0..n) (row-major: bin-major, warp-minor)
   HIVED_DEV void ctaExclusiveScan(int n) {
     int nth = hv_nth(), tid = hv_tid(), w = hv_warp(), W = hv_nwarps();
     if (n <= 32 * HIVED_WARPSZ) {  // few counters (the usual 36 bins x 16 warps): one warp scans them, one barrier
@@ -1124,11 +1138,11 @@ struct Core {
         int per = (n + HIVED_WARPSZ - 1) / HIVED_WARPSZ;
         int lo = lane * per, hi = lo + per < n ? lo + per : n;
         int sum = 0;
-        for (int i = lo; i < hi; i++) sum += sm->cnt[i];
+        for (int i = lo; i < hi; i++) sum += smp()->cnt[i];
         int incl = sum;
         for (int o = 1; o < HIVED_WARPSZ; o <<= 1) { int t = hv_shfl_up(incl, o); if (lane >= o) incl += t; }
         int run = incl - sum;
-        for (int i = lo; i < hi; i++) { int v = sm->cnt[i]; sm->cnt[i] = run; run += v; }
+        for (int i = lo; i < hi; i++) { int v = smp()->cnt[i]; smp()->cnt[i] = run; run += v; }
       }
       hv_cta_sync();
       return;
@@ -1136,20 +1150,20 @@ struct Core {
     int per = (n + nth - 1) / nth;
     int lo = tid * per, hi = lo + per < n ? lo + per : n;
     int s = 0;
-    for (int i = lo; i < hi; i++) s += sm->cnt[i];
+    for (int i = lo; i < hi; i++) s += smp()->cnt[i];
     int incl = s;
     for (int o = 1; o < HIVED_WARPSZ; o <<= 1) { int t = hv_shfl_up(incl, o); if (lane >= o) incl += t; }
-    if (lane == HIVED_WARPSZ - 1) sm->part[w] = incl;
+    if (lane == HIVED_WARPSZ - 1) smp()->part[w] = incl;
     hv_cta_sync();
     if (w == 0) {
-      int v = lane < W ? sm->part[lane] : 0;
+      int v = lane < W ? smp()->part[lane] : 0;
       int inc = v;
       for (int o = 1; o < HIVED_WARPSZ; o <<= 1) { int t = hv_shfl_up(inc, o); if (lane >= o) inc += t; }
-      if (lane < W) sm->part[lane] = inc - v;
+      if (lane < W) smp()->part[lane] = inc - v;
     }
     hv_cta_sync();
-    int run = sm->part[w] + incl - s;
-    for (int i = lo; i < hi; i++) { int v = sm->cnt[i]; sm->cnt[i] = run; run += v; }
+    int run = smp()->part[w] + incl - s;
+    for (int i = lo; i < hi; i++) { int v = smp()->cnt[i]; smp()->cnt[i] = run; run += v; }
     hv_cta_sync();
   }
 
@@ -1160,7 +1174,7 @@ struct Core {
   HIVED_DEV void stablePass(const int32_t* in, int32_t* out, int n, int nbins, BinFn binOf, bool prezeroed, int32_t* cvOut) {
     int W = hv_nwarps(), w = hv_warp();
     if (!prezeroed) {
-      for (int i = hv_tid(); i < nbins * W; i += hv_nth()) sm->cnt[i] = 0;
+      for (int i = hv_tid(); i < nbins * W; i += hv_nth()) smp()->cnt[i] = 0;
       hv_cta_sync();
     }
     int chunk = (n + W - 1) / W;
@@ -1170,7 +1184,7 @@ struct Core {
       int i = base + lane;
       int b = i < hi ? binOf(s.vw_info[in[i]]) : -1 - lane;  // inactive lanes get unique dummies
       unsigned peers = hv_match(b);
-      if (i < hi && (peers & hv_lanemask_lt()) == 0) sm->cnt[b * W + w] += hv_popc(peers);
+      if (i < hi && (peers & hv_lanemask_lt()) == 0) smp()->cnt[b * W + w] += hv_popc(peers);
       hv_warp_sync();
     }
     hv_cta_sync();
@@ -1180,13 +1194,13 @@ struct Core {
       int b = i < hi ? binOf(s.vw_info[in[i]]) : -1 - lane;
       unsigned peers = hv_match(b);
       if (i < hi) {
-        int rank = sm->cnt[b * W + w] + hv_popc(peers & hv_lanemask_lt());
+        int rank = smp()->cnt[b * W + w] + hv_popc(peers & hv_lanemask_lt());
         int src = in[i];
         out[rank] = src;
         if (cvOut) { cvOut[rank] = s.vw_cell[src]; s.vw_sinfo[rank] = s.vw_info[src]; }
       }
       hv_warp_sync();
-      if (i < hi && (peers & hv_lanemask_lt()) == 0) sm->cnt[b * W + w] += hv_popc(peers);
+      if (i < hi && (peers & hv_lanemask_lt()) == 0) smp()->cnt[b * W + w] += hv_popc(peers);
       hv_warp_sync();
     }
     hv_cta_sync();
@@ -1194,8 +1208,8 @@ struct Core {
 
   // all threads of the CTA
   HIVED_DEV void viewOp() {
-    const int sched = sm->a_sched, p = sm->a_prio, npods = sm->a_npods;
-    const bool ignoreSuggested = sm->a_ignore != 0;
+    const int sched = smp()->a_sched, p = smp()->a_prio, npods = smp()->a_npods;
+    const bool ignoreSuggested = smp()->a_ignore != 0;
     const int off = d.s_off[sched], n = d.s_n[sched];
     const bool cross = d.s_cross[sched] != 0, isVirtual = d.s_virtual[sched] != 0;
     const int L = d.s_maxleaf[sched];
@@ -1205,7 +1219,7 @@ struct Core {
     const int W = hv_nwarps();
     const bool anomalous = d.s_anom[sched] != 0;
     const int firstBins = cross ? 4 * (L + 1) : L + 1;
-    for (int i = tid; i < firstBins * W; i += nth) sm->cnt[i] = 0;
+    for (int i = tid; i < firstBins * W; i += nth) smp()->cnt[i] = 0;
     for (int i = tid; i < n; i += nth) {
       int cell = d.cv[off + i];
       s.vw_cell[i] = cell;
@@ -1253,15 +1267,15 @@ struct Core {
       if (nodeIndex < n && infoFree(sinfo[nodeIndex]) - picked >= need) {
         found = nodeIndex;
       } else {
-        if (tid == 0) sm->best = n;
+        if (tid == 0) smp()->best = n;
         hv_cta_sync();
         int mine = n;
         for (int j = nodeIndex + 1 + tid; j < n; j += nth)
           if (infoFree(sinfo[j]) >= need) { mine = j; break; }
         mine = hv_reduce_min(mine);
-        if (lane == 0 && mine < n) hv_atomic_min(&sm->best, mine);
+        if (lane == 0 && mine < n) hv_atomic_min(&smp()->best, mine);
         hv_cta_sync();
-        int b = sm->best;
+        int b = smp()->best;
         hv_cta_sync();
         if (b < n) { found = b; picked = 0; }
       }
@@ -1278,7 +1292,7 @@ struct Core {
       picked += need;
       if (tid == 0) { s.pod_pos[k] = found; s.pod_cell[k] = d.cv[off + found]; }
     }
-    if (tid == 0) { sm->r_ok = ok; sm->r_reason = reason; sm->r_cell = rcell; }
+    if (tid == 0) { smp()->r_ok = ok; smp()->r_reason = reason; smp()->r_cell = rcell; }
     hv_cta_sync();
   }
 
@@ -1286,18 +1300,18 @@ struct Core {
   HIVED_DEV bool runViewPass(int sched, int p, bool ignoreSuggested, int npods, int& reason, int& rcell) {
     if (d.bk_valid[sched]) bkMaterialise(sched);  // the general pass sorts the order array
     path_add(PC_GENERAL_VIEW);
-    ST(sm->a_sched, sched);
-    ST(sm->a_prio, p);
-    ST(sm->a_ignore, ignoreSuggested ? 1 : 0);
-    ST(sm->a_npods, npods);
-    ST(sm->a_sugg, sugg);
-    ST(sm->cmd, CMD_VIEW);
+    ST(smp()->a_sched, sched);
+    ST(smp()->a_prio, p);
+    ST(smp()->a_ignore, ignoreSuggested ? 1 : 0);
+    ST(smp()->a_npods, npods);
+    ST(smp()->a_sugg, sugg);
+    ST(smp()->cmd, CMD_VIEW);
     hv_cta_sync();
     viewOp();
     stat_add(ST_VIEW_NODES, d.s_n[sched]);
-    reason = sm->r_reason;
-    rcell = sm->r_cell;
-    return sm->r_ok != 0;
+    reason = smp()->r_reason;
+    rcell = smp()->r_cell;
+    return smp()->r_ok != 0;
   }
 
   // ======================================================================================
@@ -3106,25 +3120,25 @@ struct Core {
   HIVED_DEV void run(const hived_event_t* events, int n, hived_result_t* results, const uint32_t* suggPool, const int32_t* aux,
                      const int32_t* initLists, int nPinnedOrder, int nBad, const int32_t* own, int nOwn) {
     if (hv_warp() == 0) {
-      poolOff = sm->pool_off;
+      poolOff = smp()->pool_off;
       int initPanic = 0;
       if (initLists) { initState(initLists, nPinnedOrder, initLists + nPinnedOrder, nBad); initPanic = panicCode; }
       if (!own) nOwn = n;
       // the CTA's event indices travel through a 64-entry window in shared memory, refilled 32 at a time (lane =
       // entry): the index of the next event is never a dependent global load on the leader's path
-      if (own) { for (int q = lane; q < 64; q += HIVED_WARPSZ) { const int idx = mgStart + q; if (idx < nOwn) sm->own_win[idx & 63] = own[idx]; } }
-      ST(sm->bkc_sched, -1);
+      if (own) { for (int q = lane; q < 64; q += HIVED_WARPSZ) { const int idx = mgStart + q; if (idx < nOwn) smp()->own_win[idx & 63] = own[idx]; } }
+      ST(smp()->bkc_sched, -1);
       hv_warp_sync();
-      auto ownAt = [&](int kk) { return own ? sm->own_win[kk & 63] : kk; };
+      auto ownAt = [&](int kk) { return own ? smp()->own_win[kk & 63] : kk; };
       int stopK = nOwn;
       mgStop = false;
       for (int k = mgStart; k < nOwn; k++) {
         if (own && k > mgStart && (k & 31) == 0) {
-          for (int q = lane; q < 32; q += HIVED_WARPSZ) { const int idx = k + 32 + q; if (idx < nOwn) sm->own_win[idx & 63] = own[idx]; }
+          for (int q = lane; q < 32; q += HIVED_WARPSZ) { const int idx = k + 32 + q; if (idx < nOwn) smp()->own_win[idx & 63] = own[idx]; }
           hv_warp_sync();
         }
         int i = ownAt(k);
-        if (lane == 0) hv_publish_smem(&sm->lead_k, k);
+        if (lane == 0) hv_publish_smem(&smp()->lead_k, k);
         curEvent = i;
         sharedHeld = false;
         long long tq = pclock();
@@ -3132,13 +3146,13 @@ struct Core {
         // copies into the other half of the double buffer: no register target, nothing waits at a call boundary);
         // wait for it, then request event k+1 and pull event k+2 towards L2/L1.
         constexpr int EVQ = (int)(sizeof(hived_event_t) / 16);
-        int32_t* cur = sm->ev_words[k & 1];
+        int32_t* cur = smp()->ev_words[k & 1];
         if (k == mgStart) { for (int q = lane; q < EVQ; q += HIVED_WARPSZ) hv_cp_async16(cur + 4 * q, reinterpret_cast<const char*>(&events[i]) + 16 * q); }
         hv_cp_async_wait();
         hv_warp_sync();
         if (k + 1 < nOwn) {
           const char* nxt = reinterpret_cast<const char*>(&events[ownAt(k + 1)]);
-          int32_t* dst = sm->ev_words[(k + 1) & 1];
+          int32_t* dst = smp()->ev_words[(k + 1) & 1];
           for (int q = lane; q < EVQ; q += HIVED_WARPSZ) hv_cp_async16(dst + 4 * q, nxt + 16 * q);
         }
         if (k + 2 < nOwn) hv_prefetch(&events[ownAt(k + 2)]);
@@ -3158,20 +3172,20 @@ struct Core {
         }
         dbg(15, tq);
       }
-      if (lane == 0) hv_publish_smem(&sm->lead_k, 0x7fffffff);
+      if (lane == 0) hv_publish_smem(&smp()->lead_k, 0x7fffffff);
       flushWork();
-      ST(sm->pool_off, poolOff);
-      ST(sm->stop_k, stopK);
-      ST(sm->panic, initPanic);
-      ST(sm->cmd, CMD_EXIT);
+      ST(smp()->pool_off, poolOff);
+      ST(smp()->stop_k, stopK);
+      ST(smp()->panic, initPanic);
+      ST(smp()->cmd, CMD_EXIT);
       hv_cta_sync();
     } else if (hv_is_runahead()) {
       if (!initLists) runAhead(events, n, own, nOwn);
     } else {
       while (true) {
         hv_cta_sync();
-        if (sm->cmd == CMD_EXIT) break;
-        sugg = sm->a_sugg;
+        if (smp()->cmd == CMD_EXIT) break;
+        sugg = smp()->a_sugg;
         viewOp();
       }
     }
@@ -3189,7 +3203,7 @@ struct Core {
     (void)nPinnedOrder; (void)nBad;
     if (hv_warp() == 0) {
       int lastSeq = seq0;
-      ST(sm->bkc_sched, -1);
+      ST(smp()->bkc_sched, -1);
       while (true) {
         int seq = lastSeq, spins = 0;
         // header line: [0] seq  [1] n (0 = STOP)  [2] suggWords  [3] auxWords  [4] poolCap
@@ -3215,7 +3229,7 @@ struct Core {
         hv_warp_sync();
         poolOff = 0;
         for (int k = 0; k < n; k++) {
-          int32_t* cur = sm->ev_words[k & 1];
+          int32_t* cur = smp()->ev_words[k & 1];
           for (int i = lane; i < evWords; i += HIVED_WARPSZ) cur[i] = pay[k * evWords + i];
           hv_warp_sync();
           curEvent = k;
@@ -3238,7 +3252,7 @@ struct Core {
         if (lane == 0) slot[SERVE_DONE_OFF] = seq;
         hv_warp_sync();
       }
-      ST(sm->cmd, CMD_EXIT);
+      ST(smp()->cmd, CMD_EXIT);
       hv_cta_sync();
       if (lane == 0) { __threadfence_system(); slot[SERVE_DONE_OFF + 3] = lastSeq; slot[SERVE_DONE_OFF + 4] = 1; }  // exited
     } else if (hv_is_runahead()) {
@@ -3246,8 +3260,8 @@ struct Core {
     } else {
       while (true) {
         hv_cta_sync();
-        if (sm->cmd == CMD_EXIT) break;
-        sugg = sm->a_sugg;
+        if (smp()->cmd == CMD_EXIT) break;
+        sugg = smp()->a_sugg;
         viewOp();
       }
     }

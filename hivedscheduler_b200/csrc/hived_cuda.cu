@@ -22,7 +22,7 @@ __global__ void __launch_bounds__(NT, 1)
 hived_events_kernel(const __grid_constant__ Dev dev, const hived_event_t* __restrict__ events, int n, hived_result_t* results,
                     const uint32_t* suggPool, const int32_t* aux, const int32_t* initLists, int nPinnedOrder, int nBad,
                     int32_t* pool, long long* scalars, const int32_t* own, const int32_t* ownOff) {
-  __shared__ Sm sm;
+  Sm& sm = g_hived_sm;
   const int cta = blockIdx.x;
   if (threadIdx.x == 0) {
     sm.cmd = CMD_IDLE;
@@ -46,7 +46,7 @@ hived_events_kernel(const __grid_constant__ Dev dev, const hived_event_t* __rest
 }
 
 __global__ void __launch_bounds__(NT, 1) hived_repair_kernel(const __grid_constant__ Dev dev) {
-  __shared__ Sm sm;
+  Sm& sm = g_hived_sm;
   Core core(dev, &sm, nullptr, 0, 1);
   core.repairSharedAncestors();
 }
@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(NT, 1) hived_repair_kernel(const __grid_consta
 __global__ void __launch_bounds__(NT, 1)
 hived_serve_kernel(const __grid_constant__ Dev dev, volatile int32_t* slot, int seq0, int idleSpins, hived_result_t* stageRes,
                    uint32_t* dSugg, int32_t* dAux, int nPinnedOrder, int nBad, int32_t* pool) {
-  __shared__ Sm sm;
+  Sm& sm = g_hived_sm;
   if (threadIdx.x == 0) {
     sm.cmd = CMD_IDLE;
     sm.panic = 0;

@@ -157,3 +157,26 @@ def test_partitioned_over_gloo_world_size_2(emu_mt_lib, oracle_lib):
         assert p.returncode == 0, o
     line = [l for l in outs[0].splitlines() if l.startswith("HASH")][0]
     assert int(line.split()[1], 16) == h1, line
+
+
+def test_bench_partitioned_leg_plumbing_over_gloo(emu_mt_lib, oracle_lib):
+    """bench.py --gpus 2 as the driver launches it (torch.distributed.run, one process per rank), on the emulation
+    library under gloo: one JSON line from rank 0, strong scaling, the merged chain hash equal to the oracle's."""
+    import json
+    t = trace.trace_c3(n_gangs=1200)
+    h1 = run_trace(oracle_lib, t)[0]
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    env = dict(os.environ, HIVED_BENCH_PLUMBING_TEST_LIB=emu_mt_lib._name)
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                          "--master-port", str(port), os.path.join(ROOT, "bench.py"), "--gpus", "2", "--steps", "1", "--warmup", "1",
+                          "--gangs", "1200"], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-3000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    assert line["n_gpus"] == 2 and line["scaling"] == "strong" and line["unit"] == "decisions/s"
+    assert line["parity"]["result_hash"] == "%016x" % h1
+    assert line["config"]["rounds_per_step"] >= 8 and line["e2e"]["value"] > 0
