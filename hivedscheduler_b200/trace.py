@@ -527,6 +527,47 @@ def run_c4_interactive(lib, config, n_gangs: int, n_vcs: int, vc_gpus: int, tota
     return h, log, stats
 
 
+def run_c4_compiled(lib, config, n_gangs: int, n_vcs: int, vc_gpus: int, total_gpus: int, load: float = 0.9,
+                    max_groups: int = None, batch_deletes: bool = True, player_path: str = None):
+    """The closed loop of run_c4_interactive played by compiled code (tests/harness/c4_player.cpp; built by
+    __graft_entry__.build_c4_player) — no interpreter between the calls; the deletions of one gang's pods travel as one
+    batch of <= 8 events.  Returns (hash, decision log in run_c4_interactive's format, stats, timing dict)."""
+    import os
+    if player_path is None:
+        player_path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "_build",
+                                   "libhived_c4player.so")
+    player = C.CDLL(player_path)
+    player.c4_play.restype = C.c_int
+    bc = BatchContext(lib, config, max_groups or (n_gangs + 8), 8 * n_gangs + 64, 64, 8)
+    bc.set_all_nodes_healthy()
+    cap = 80 * n_gangs + 4096
+    buf = np.zeros(cap, dtype=np.int32)
+    words, calls, events, secs = C.c_int64(0), C.c_int64(0), C.c_int64(0), C.c_double(0.0)
+    rc = player.c4_play(C.cast(lib.hived_process_events, C.c_void_p), bc.ctx, C.c_int32(n_gangs), C.c_int32(n_vcs),
+                        C.c_int32(vc_gpus), C.c_int32(total_gpus), C.c_double(load), C.c_int32(1 if batch_deletes else 0),
+                        buf.ctypes.data_as(C.POINTER(C.c_int32)), C.c_int64(cap), C.byref(words), C.byref(calls),
+                        C.byref(events), C.byref(secs))
+    if rc != 0:
+        raise RuntimeError("c4_play failed (%d): %s" % (rc, (lib.hived_last_error(bc.ctx) or b"").decode()))
+    log, i, w = [], 0, buf[:words.value].tolist()
+    kinds = ("preempt", "bind", "wait", "preempt-again")
+    while i < len(w):
+        g, j, kind, n = w[i:i + 4]
+        payload = w[i + 4:i + 4 + n]
+        i += 4 + n
+        if kind == 0:
+            log.append((g, j, "preempt", tuple(payload)))
+        elif kind == 1:
+            log.append((g, j, "bind", payload[0], tuple(payload[1:])))
+        else:
+            log.append((g, j, kinds[kind], payload[0]))
+    h = bc.result_hash()
+    stats = bc.stats()
+    stats["lazy_preempted_groups"] = 0
+    bc.close()
+    return h, log, stats, {"calls": calls.value, "events": events.value, "seconds": secs.value}
+
+
 # ------------------------------------------------------------------------------------------------
 # batch driver
 # ------------------------------------------------------------------------------------------------

@@ -172,3 +172,20 @@ def test_emu_matches_oracle_with_preemption_c4(emu_lib, oracle_lib):
     assert le == lo
     assert he == ho and se == so
     assert any(x[2] == "preempt" for x in le), "the scenario is expected to exercise preemption"
+
+
+def test_compiled_c4_player_equals_python_harness(emu_lib):
+    """tests/harness/c4_player.cpp (the closed loop of C4 as compiled code, what bench.py times) issues exactly the
+    calls of trace.run_c4_interactive: same parity hash, decision log and work counters — with the deletions of a
+    gang's pods sent one by one and as one batch."""
+    import __graft_entry__ as ge
+    ge.build_c4_player()
+    kw = dict(config=small_cluster(), n_gangs=3500, n_vcs=2, vc_gpus=(16 + 6) * 32 * 8, total_gpus=4 * 16 * 32 * 8)
+    hp, lp, sp = trace.run_c4_interactive(emu_lib, **kw)
+    assert any(x[2] == "preempt" for x in lp)
+    for batch in (False, True):
+        hc, lc, sc, tm = trace.run_c4_compiled(emu_lib, batch_deletes=batch, **kw)
+        assert lc == lp
+        assert hc == hp and sc == sp
+        assert tm["events"] > sp["schedule_events"]  # the deletions
+        assert (tm["calls"] < tm["events"]) == batch

@@ -218,6 +218,23 @@ def test_cuda_full_size_c4_against_oracle(cuda_lib):
     assert stats == golden["stats"]
 
 
+def test_cuda_full_size_c4_compiled_player(cuda_lib):
+    """The same full-size C4 run driven by compiled code (tests/harness/c4_player.cpp: no interpreter between the calls,
+    a gang's pod deletions as one batch): same hash, log and counters as the oracle's committed run."""
+    golden = json.load(open(os.path.join(HERE, "golden", "trace_hashes.json"))).get("C4")
+    if golden is None:
+        pytest.skip("tests/golden/trace_hashes.json has no C4 entry")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_trace_hashes", os.path.join(HERE, "golden", "make_trace_hashes.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    h, log, stats, tm = trace.run_c4_compiled(cuda_lib, **gen.c4_kwargs(golden["n_gangs"]))
+    assert len(log) == golden["log_entries"]
+    assert gen.log_digest(log) == golden["log_sha256"]
+    assert "%016x" % h == golden["hash"]
+    assert stats == golden["stats"]
+
+
 def test_c_driver_through_the_abi(cuda_lib, tmp_path):
     """Schedule -> AddAllocatedPod -> DeleteAllocatedPod on the GPU from plain C (tests/c/test_cabi_gpu.c): the
     boundary as a cgo shim sees it, without Python in between."""
