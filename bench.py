@@ -543,7 +543,7 @@ def main():
     lib.hived_bench_set_result_hash(ctx, 1)
     step_e2e()
     parity_hash = bc.result_hash()
-    # ---- per-call leg: the extender's own pattern, one pod per call (one launch + one result round trip each):
+    # ---- per-call leg: the extender's own pattern, one pod per call (one request / result round trip each):
     # the first events of the same trace through hived_process_events(n=1) — the same path hived_schedule takes
     lib.hived_bench_restore_state(ctx)
     lib.hived_bench_set_result_hash(ctx, 0)
@@ -584,8 +584,11 @@ def main():
         "e2e": {"value": e2e_value, "unit": "decisions/s", "h2d_bytes_per_step": int(ev.nbytes),
                 "d2h_bytes_per_step": int(len(ev) * C.sizeof(_cabi.Result) + 4 * used.value)},
         "per_call": {"us_per_event": 1e6 * per_call_s, "kernel_us_per_event": per_call_kernel_us, "events": int(n_calls - 64),
-                     "note": "hived_process_events with n=1 (one kernel launch, H2D event, D2H result per pod) on the first "
-                             "events of the same trace: the latency the HTTP extender sees per Schedule/Delete"},
+                     "resident_kernel": os.environ.get("HIVED_NO_RESIDENT", "0") in ("", "0"),
+                     "note": "hived_process_events with n=1 on the first events of the same trace, from Python: the latency the "
+                             "HTTP extender sees per Schedule/Delete.  Served by the resident per-call kernel (request slot in "
+                             "mapped host memory, no launch / memcpy / stream sync per call); HIVED_NO_RESIDENT=1 = one launch "
+                             "per call.  From C: profiles/micro/percall_latency.c"},
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -84,6 +84,14 @@ struct Sm {
 };
 #if defined(__CUDACC__) && !defined(HIVED_SIMT_EMU) && !defined(HIVED_EMU)
 __shared__ Sm g_hived_sm;  // one per CTA (both kernels of hived_cuda.cu use it)
+// The device's view of the scheduler state (array pointers and sizes, hived_dev.h) lives in the CONSTANT bank: `d.p_prio[i]`
+// is one load whose base address is an instruction operand (c[3][offset]).  Through a `const Dev&` member the
+// compiler fetched the pointer with a generic load (LD.E.64) before nearly every data load — a dependent L1 round trip
+// on the leader warp's critical path and a third of its memory instructions (profiles/r2_sass_summary.md).  One
+// context's Dev is loaded per device at a time; launchProgram / the per-call path reload it when the owner changes
+// (hived_cuda.cu: ensureDevLoaded).
+__constant__ Dev g_hived_dev;
+#define HIVED_DEV_IN_CONSTANT 1
 #endif
 
 enum { CMD_IDLE = 0, CMD_VIEW = 1, CMD_EXIT = 2 };
@@ -98,7 +106,11 @@ enum { CMD_IDLE = 0, CMD_VIEW = 1, CMD_EXIT = 2 };
 #endif
 
 struct Core {
+#ifdef HIVED_DEV_IN_CONSTANT
+#define d g_hived_dev  /* (until the end of this header) */
+#else
   const Dev& d;
+#endif
 #if defined(__CUDACC__) && !defined(HIVED_SIMT_EMU) && !defined(HIVED_EMU)
   // the CTA's shared block is ONE file-scope __shared__ object: every access compiles to LDS / STS / ATOMS (through a
   // generic Sm* the compiler loses the address space as soon as `this` goes through memory: LD.E / ATOM.E)
@@ -127,7 +139,10 @@ struct Core {
   bool sharedHeld;   // this event already holds the right to touch the cluster-wide free-list state
 
   HIVED_DEV Core(const Dev& dev, Sm* s_, int32_t* pool_, long long cap, int nCta_)
-      : d(dev),
+      :
+#ifndef HIVED_DEV_IN_CONSTANT
+        d(dev),
+#endif
 #if !(defined(__CUDACC__) && !defined(HIVED_SIMT_EMU) && !defined(HIVED_EMU))
         sm_(s_),
 #endif
@@ -709,6 +724,7 @@ struct Core {
   }
   // hived_algorithm.go:1354-1427
   HIVED_DEV_NOINLINE bool allocatePreassignedCell(int c, int vc, bool doomedBad) {
+    if (c < 0) { panic(HIVED_ERR_PLATFORM); return false; }  // nil *PhysicalCell dereferenced in the reference (:1358): see allocateLeafCell
     sharedEnter();
     bool safetyOk = true;
     int chain = d.p_chain[c], level = d.p_level[c];
@@ -1893,6 +1909,40 @@ struct Core {
     return n;
   }
   HIVED_DEV void eraseGroup(int g) { ST(d.g_state[g], HIVED_GROUP_NONE); }
+  // Object identity of an erased group.  The reference's cells point at *AlgoAffinityGroup objects (cell.usingGroup,
+  // cell.reservingOrReservedGroup), its name map at whichever object carries the name now.  One path erases a group
+  // from the map while its own leaves keep naming it: schedulePodFromExistingGroup treats every state but Allocated as
+  // Preempting (hived_algorithm.go:671-707), so a pod of a group that is BEING PREEMPTED whose placement has a bad or
+  // non-suggested node runs deletePreemptingAffinityGroup on it (:1114-1145) — the Reserving leaves go back to "the group
+  // being preempted" (the group itself) and the name is freed; the next Schedule creates a NEW object under that name,
+  // while the victims of whoever preempts those leaves later are still the OLD object's pods (utils.go:217).  Below the
+  // ABI a group is its interned id, so the old incarnation moves to a ghost record and the leaves are re-pointed;
+  // a ghost whose leaves no longer name it is garbage (the reference's GC) and its slot is reused.
+  HIVED_DEV bool groupNamedByOwnLeaves(int g) const {
+    const int32_t* ph = gphys(g);
+    return firstIdx(groupLeaves(g), [&](int i) { const int c = ph[i]; return c >= 0 && (d.p_using[c] == g || d.p_resv[c] == g); }) >= 0;
+  }
+  HIVED_DEV_NOINLINE void ghostify(int g) {
+    if (!groupNamedByOwnLeaves(g)) return;
+    int gg = -1;
+    for (int k = 0; k < GHOST_GROUPS && gg < 0; k++) {
+      const int c = d.S.maxGroups + k;
+      if (d.g_nmem[c] == 0 || !groupNamedByOwnLeaves(c)) gg = c;
+    }
+    if (gg < 0) { panic(HIVED_ERR_CAPACITY); return; }
+    const int nl = groupLeaves(g), np = groupPods(g), npre = d.g_npre[g];
+    hv_phase();
+    for (int w = lane; w < GROUP_HDR_WORDS; w += HIVED_WARPSZ) d.g_hdr[(int64_t)gg * GROUP_HDR_WORDS + w] = d.g_hdr[(int64_t)g * GROUP_HDR_WORDS + w];
+    for (int i = lane; i < nl; i += HIVED_WARPSZ) { gphys(gg)[i] = gphys(g)[i]; gvirt(gg)[i] = gvirt(g)[i]; }
+    for (int i = lane; i < np; i += HIVED_WARPSZ) gpods(gg)[i] = gpods(g)[i];
+    for (int i = lane; i < npre; i += HIVED_WARPSZ) gpre(gg)[i] = gpre(g)[i];
+    hv_warp_sync();
+    for (int i = lane; i < nl; i += HIVED_WARPSZ) {
+      const int c = gphys(g)[i];
+      if (c >= 0) { if (d.p_using[c] == g) d.p_using[c] = gg; if (d.p_resv[c] == g) d.p_resv[c] = gg; }
+    }
+    hv_warp_sync();
+  }
 
   // hived_algorithm.go:1165-1191.  save != nullptr receives the original virtual placement.
   HIVED_DEV_NOINLINE void lazyPreemptAffinityGroup(int g, int32_t* save) {
@@ -2103,6 +2153,7 @@ struct Core {
         setCellState(pLeaf, HIVED_CELL_FREE);
       }
     }
+    ghostify(g);  // (only a group that was not Preempting can still be named by its leaves here)
     eraseGroup(g);
   }
   // hived_algorithm.go:1147-1163
@@ -3268,5 +3319,9 @@ struct Core {
   }
 #endif
 };
+
+#ifdef HIVED_DEV_IN_CONSTANT
+#undef d
+#endif
 
 }  // namespace hived

@@ -10,6 +10,8 @@
 // HIVED_ERR_NO_DEVICE.
 #include <cuda_runtime.h>
 
+#include <mutex>
+
 #include "hived_engine.hpp"
 
 namespace hived {
@@ -19,7 +21,7 @@ constexpr int NT = 512;  // threads per CTA (16 warps); the kernel needs the ful
 // scalars: 4 words per CTA — [0] pool offset (in: start of the CTA's slice, out: first unused word),
 // [1] end of the slice, [2] out: initialisation panic code
 __global__ void __launch_bounds__(NT, 1)
-hived_events_kernel(const __grid_constant__ Dev dev, const hived_event_t* __restrict__ events, int n, hived_result_t* results,
+hived_events_kernel(const hived_event_t* __restrict__ events, int n, hived_result_t* results,
                     const uint32_t* suggPool, const int32_t* aux, const int32_t* initLists, int nPinnedOrder, int nBad,
                     int32_t* pool, long long* scalars, const int32_t* own, const int32_t* ownOff) {
   Sm& sm = g_hived_sm;
@@ -31,7 +33,7 @@ hived_events_kernel(const __grid_constant__ Dev dev, const hived_event_t* __rest
     sm.pool_off = scalars[cta * 4 + 0];
   }
   __syncthreads();
-  Core core(dev, &sm, pool, scalars[cta * 4 + 1], gridDim.x);
+  Core core(g_hived_dev, &sm, pool, scalars[cta * 4 + 1], gridDim.x);
   int nOwn = own ? ownOff[cta + 1] - ownOff[cta] : n;
   // multi-GPU partition: [start, limit) of this CTA's list and the mode, packed by launchProgram (0: an ordinary run)
   const long long mg = scalars[cta * 4 + 3];
@@ -45,15 +47,15 @@ hived_events_kernel(const __grid_constant__ Dev dev, const hived_event_t* __rest
   }
 }
 
-__global__ void __launch_bounds__(NT, 1) hived_repair_kernel(const __grid_constant__ Dev dev) {
+__global__ void __launch_bounds__(NT, 1) hived_repair_kernel() {
   Sm& sm = g_hived_sm;
-  Core core(dev, &sm, nullptr, 0, 1);
+  Core core(g_hived_dev, &sm, nullptr, 0, 1);
   core.repairSharedAncestors();
 }
 
 // The per-call path, resident: one CTA that stays on an SM while calls keep coming (Core::serve).
 __global__ void __launch_bounds__(NT, 1)
-hived_serve_kernel(const __grid_constant__ Dev dev, volatile int32_t* slot, int seq0, int idleSpins, hived_result_t* stageRes,
+hived_serve_kernel(volatile int32_t* slot, int seq0, int idleSpins, hived_result_t* stageRes,
                    uint32_t* dSugg, int32_t* dAux, int nPinnedOrder, int nBad, int32_t* pool) {
   Sm& sm = g_hived_sm;
   if (threadIdx.x == 0) {
@@ -63,7 +65,7 @@ hived_serve_kernel(const __grid_constant__ Dev dev, volatile int32_t* slot, int 
     sm.pool_off = 0;
   }
   __syncthreads();
-  Core core(dev, &sm, pool, 0, 1);
+  Core core(g_hived_dev, &sm, pool, 0, 1);
   core.serve(slot, seq0, idleSpins, stageRes, dSugg, dAux, nPinnedOrder, nBad);
 }
 
@@ -133,9 +135,34 @@ struct CudaTimers {
   long long served = 0, launches = 0;
 };
 
+// ---- whose Dev is in the constant bank (g_hived_dev, hived_core.h) of each device ---------------------------------
+// One context per device at a time.  Every section that launches a kernel or talks to a resident one holds g_devMu
+// (contexts of one process take turns on the GPU; a context by itself is single-threaded per the ABI), makes sure its
+// own Dev is the one loaded, and leaves nothing of its own running except the resident per-call kernel — which the
+// next owner stops (bk_quiesce) before it overwrites the constant bank.
+static std::recursive_mutex g_devMu;
+static Engine* g_devOwner[64] = {nullptr};
+
+void bk_quiesce(Engine& e);
+static int ensureDevLoaded(Engine& e) {  // g_devMu held, the context's device current
+  const int dv = e.deviceOrdinal >= 0 && e.deviceOrdinal < 64 ? e.deviceOrdinal : 0;
+  if (g_devOwner[dv] == &e) return 0;
+  if (g_devOwner[dv]) bk_quiesce(*g_devOwner[dv]);
+  g_devOwner[dv] = nullptr;
+  cudaError_t ce = cudaMemcpyToSymbol(g_hived_dev, &e.dev, sizeof(Dev));  // synchronous: nothing of ours is running
+  if (ce != cudaSuccess) { e.err = std::string("cudaMemcpyToSymbol(g_hived_dev): ") + cudaGetErrorString(ce); return HIVED_ERR_PLATFORM; }
+  g_devOwner[dv] = &e;
+  return 0;
+}
+void bk_forget(Engine& e) {  // the context is going away
+  std::lock_guard<std::recursive_mutex> lk(g_devMu);
+  for (auto& o : g_devOwner) if (o == &e) o = nullptr;
+}
+
 // Stop the resident kernel (if any) and wait until it has left: before anything else launches on or writes to the
 // scheduler state.  Called with the context's device current.
 void bk_quiesce(Engine& e) {
+  std::lock_guard<std::recursive_mutex> lk(g_devMu);
   CudaTimers* t = (CudaTimers*)e.stream;
   if (!t || !t->alive) return;
   volatile int32_t* s = t->slotHost;
@@ -151,6 +178,7 @@ void bk_quiesce(Engine& e) {
 static_assert(NT / 32 <= MAX_WARPS, "the shared counters are sized for MAX_WARPS warps per CTA");
 
 int launchProgram(Engine& e, int n, bool withInit) {
+  std::lock_guard<std::recursive_mutex> lk(g_devMu);
   if (!e.stream) {
     // the kernel wants L1, not shared memory: ask for the smallest carveout that holds its ~18 KB of static smem
     cudaFuncSetAttribute(hived_events_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 10);
@@ -162,9 +190,10 @@ int launchProgram(Engine& e, int n, bool withInit) {
   }
   CudaTimers* t = (CudaTimers*)e.stream;
   bk_quiesce(e);
+  if (int rc = ensureDevLoaded(e)) return rc;
   const int mgMode = withInit ? 0 : e.mgMode;
   if (mgMode == 3) {  // end of a multi-GPU partition run: the repair pass alone
-    hived_repair_kernel<<<1, NT, 0, t->stream>>>(e.dev);
+    hived_repair_kernel<<<1, NT, 0, t->stream>>>();
     cudaError_t err = cudaStreamSynchronize(t->stream);
     if (err != cudaSuccess) { e.err = std::string("hived_repair_kernel failed: ") + cudaGetErrorString(err); return HIVED_ERR_PLATFORM; }
     e.kernelLaunches++;
@@ -183,7 +212,6 @@ int launchProgram(Engine& e, int n, bool withInit) {
   if (C > 1 && !mgMode) {
     // The CTAs of a VC-parallel batch wait for each other (ordered shared sections): launch them cooperatively, so
     // that the runtime guarantees that all of them are resident at the same time.
-    Dev devArg = e.dev;
     const hived_event_t* aEvents = (const hived_event_t*)e.dEvents.p;
     int aN = n;
     hived_result_t* aResults = (hived_result_t*)e.dResults.p;
@@ -195,7 +223,7 @@ int launchProgram(Engine& e, int n, bool withInit) {
     long long* aScal = (long long*)e.dScalars.p;
     const int32_t* aOwn = own;
     const int32_t* aOwnOff = own + n;
-    void* args[] = {&devArg, &aEvents, &aN, &aResults, &aSugg, &aAux, &aInit, &aPinned, &aBad, &aPool, &aScal, &aOwn, &aOwnOff};
+    void* args[] = {&aEvents, &aN, &aResults, &aSugg, &aAux, &aInit, &aPinned, &aBad, &aPool, &aScal, &aOwn, &aOwnOff};
     cudaError_t le = cudaLaunchCooperativeKernel((const void*)hived_events_kernel, dim3(C), dim3(NT), args, 0, t->stream);
     if (le != cudaSuccess) {
       e.err = std::string("cooperative launch of hived_events_kernel failed: ") + cudaGetErrorString(le);
@@ -203,12 +231,12 @@ int launchProgram(Engine& e, int n, bool withInit) {
     }
   } else {
     hived_events_kernel<<<C, NT, 0, t->stream>>>(
-        e.dev, (const hived_event_t*)e.dEvents.p, n, (hived_result_t*)e.dResults.p,
+        (const hived_event_t*)e.dEvents.p, n, (hived_result_t*)e.dResults.p,
         e.hasSugg ? (const uint32_t*)e.dSugg.p : nullptr, e.hasAux ? (const int32_t*)e.dAux.p : nullptr,
         withInit ? (const int32_t*)e.dInit.p : nullptr, e.nPinnedOrder, e.nBad, (int32_t*)e.dPool.p, (long long*)e.dScalars.p, own,
         own ? own + n : nullptr);
   }
-  if (C > 1 && !mgMode) hived_repair_kernel<<<1, NT, 0, t->stream>>>(e.dev);
+  if (C > 1 && !mgMode) hived_repair_kernel<<<1, NT, 0, t->stream>>>();
   cudaEventRecord(t->stop, t->stream);
   cudaMemcpyAsync(scal, e.dScalars.p, sizeof scal, cudaMemcpyDeviceToHost, t->stream);
   cudaError_t err = cudaStreamSynchronize(t->stream);
@@ -290,7 +318,7 @@ static int serveCall(Engine& e, CudaTimers* t, const hived_event_t* events, int 
     s[SERVE_DONE_OFF + 4] = 0;
     __sync_synchronize();
     // ~1.5 us per poll over PCIe: leave after about 2 ms without a request
-    hived_serve_kernel<<<1, NT, 0, t->serveStream>>>(e.dev, t->slotDev, seq - 1, 1500, t->stageRes, t->dSugg, t->dAux, e.nPinnedOrder,
+    hived_serve_kernel<<<1, NT, 0, t->serveStream>>>(t->slotDev, seq - 1, 1500, t->stageRes, t->dSugg, t->dAux, e.nPinnedOrder,
                                                       e.nBad, t->servePool);
     t->alive = true;
     t->launches++;
@@ -336,7 +364,9 @@ static int serveCall(Engine& e, CudaTimers* t, const hived_event_t* events, int 
 int bk_run_small(Engine& e, const hived_event_t* events, int n, const uint32_t* suggPool, int64_t suggWords, const int32_t* aux,
                  int64_t auxWords, hived_result_t* res, int32_t* pool, int64_t poolCap) {
   if (!e.stream) return -1;  // the first launch (initialisation) creates the stream
+  std::lock_guard<std::recursive_mutex> lk(g_devMu);
   CudaTimers* t = (CudaTimers*)e.stream;
+  if (int rc = ensureDevLoaded(e)) return rc;
   {
     int rc = serveCall(e, t, events, n, suggPool, suggWords, aux, auxWords, res, pool, poolCap);
     if (rc != -2) return rc;  // -2: the resident path does not take this call
@@ -378,7 +408,7 @@ int bk_run_small(Engine& e, const hived_event_t* events, int n, const uint32_t* 
   if (hasSugg) cudaMemcpyAsync(e.dSugg.p, h + oSugg, (size_t)suggWords * 4, cudaMemcpyHostToDevice, st);
   if (hasAux) cudaMemcpyAsync(e.dAux.p, h + oAux, (size_t)auxWords * 4, cudaMemcpyHostToDevice, st);
   cudaEventRecord(t->start, st);
-  hived_events_kernel<<<1, NT, 0, st>>>(e.dev, (const hived_event_t*)e.dEvents.p, n, (hived_result_t*)e.dResults.p,
+  hived_events_kernel<<<1, NT, 0, st>>>((const hived_event_t*)e.dEvents.p, n, (hived_result_t*)e.dResults.p,
                                         hasSugg ? (const uint32_t*)e.dSugg.p : nullptr, hasAux ? (const int32_t*)e.dAux.p : nullptr,
                                         nullptr, e.nPinnedOrder, e.nBad, (int32_t*)e.dPool.p, (long long*)e.dScalars.p, nullptr, nullptr);
   cudaEventRecord(t->stop, st);

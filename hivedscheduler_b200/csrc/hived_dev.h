@@ -17,6 +17,9 @@ namespace hived {
 // a while: one L2 round trip instead of eight).  Word layout: 0 state, 1 vc, 2 priority, 3 flags,
 // 4 #members, 5 #preempting pods, 8..15 member leaf numbers, 16..23 member pod numbers.
 constexpr int GROUP_HDR_WORDS = 32;
+// Records [maxGroups, maxGroups + GHOST_GROUPS) of the group tables hold GHOSTS: a group that the reference erases from
+// its name map while cells still point at the object (cell.usingGroup), see Core::ghostify.  Never visible by id.
+constexpr int GHOST_GROUPS = 64;
 constexpr int DELTA_SLOTS = 4;          // (priority, difference) pairs per cell, see noteDelta
 constexpr int DELTA_EMPTY = -1000000;
 constexpr int BK_STRIDE = 33;  // buckets of a bucketed cluster view: used-leaf counts 0..32
@@ -56,10 +59,10 @@ struct GroupMemFld {  // indexed by g * 8 + m like the flat arrays it replaces
   Y(fl_data, S.flTotal, -1) Y(fl_len, S.nChains * MAXL, 0) Y(bf_data, S.flTotal, -1)                   \
   Y(bf_len, S.nChains * MAXL, 0) Y(dm_data, S.dmTotal, -1) Y(dm_len, S.nVCs * S.nChains * MAXL, 0)     \
   Y(cv, S.cvTotal, -1) Y(node_bad, S.nNodes, 0)                                                        \
-  Y(g_hdr, (int64_t)S.maxGroups * GROUP_HDR_WORDS, 0)                                                  \
-  Y(g_phys, (int64_t)S.maxGroups * S.LS, -1) Y(g_virt, (int64_t)S.maxGroups * S.LS, -1)                \
-  Y(g_pods, (int64_t)S.maxGroups * S.PS, -1)                                                           \
-  Y(g_pre, (int64_t)S.maxGroups * S.PS, -1) Y(pod_node, S.maxPods, -1) \
+  Y(g_hdr, (int64_t)(S.maxGroups + GHOST_GROUPS) * GROUP_HDR_WORDS, 0)                                                  \
+  Y(g_phys, (int64_t)(S.maxGroups + GHOST_GROUPS) * S.LS, -1) Y(g_virt, (int64_t)(S.maxGroups + GHOST_GROUPS) * S.LS, -1)                \
+  Y(g_pods, (int64_t)(S.maxGroups + GHOST_GROUPS) * S.PS, -1)                                                           \
+  Y(g_pre, (int64_t)(S.maxGroups + GHOST_GROUPS) * S.PS, -1) Y(pod_node, S.maxPods, -1) \
   Y(vx_of, S.NV, -1) Y(vx_stamp, S.NV, 0) Y(binding, S.NV, -1)                                         \
   /* bucketed cluster views (hived_core.h, "incremental cluster view") */                              \
   Y(bk_valid, S.nScheds, 0) Y(bk_ndirty, S.nScheds, 0) Y(bk_head, S.nScheds * BK_STRIDE, -1)           \

@@ -31,6 +31,7 @@ void bk_d2h(void* dst, const void* src, size_t bytes);
 void bk_d2d(void* dst, const void* src, size_t bytes);
 void bk_zero(void* dst, size_t bytes);
 void bk_quiesce(Engine& e);  // stop a resident per-call kernel before the state is written from elsewhere (CUDA backend)
+void bk_forget(Engine& e);   // the context is being destroyed (CUDA backend: it may own the device's constant bank)
 int bk_init(int& device, std::string& err);  // device: in = requested ordinal, out = the one in use
 void bk_use_device(int device);  // make `device` current for the calling thread (contexts on several GPUs in one process)
 // runs the program over n staged events; returns 0 or a HIVED_ERR_* code
@@ -98,6 +99,7 @@ struct Engine {
 
   ~Engine() {
     bk_quiesce(*this);
+    bk_forget(*this);
     for (void* p : allocs) bk_free(p);
     for (void* p : savedRegions) bk_free(p);
   }
@@ -163,8 +165,8 @@ struct Engine {
     dev.g_state.b = dev.g_vc.b = dev.g_prio.b = dev.g_flags.b = dev.g_nmem.b = dev.g_npre.b = dev.g_hdr;
     dev.g_mem_leaf.b = dev.g_mem_pods.b = dev.g_hdr;
     {  // g_vc starts at -1
-      std::vector<int32_t> hdr((size_t)S.maxGroups * GROUP_HDR_WORDS, 0);
-      for (int g = 0; g < S.maxGroups; g++) hdr[(size_t)g * GROUP_HDR_WORDS + 1] = -1;
+      std::vector<int32_t> hdr((size_t)(S.maxGroups + GHOST_GROUPS) * GROUP_HDR_WORDS, 0);
+      for (int g = 0; g < S.maxGroups + GHOST_GROUPS; g++) hdr[(size_t)g * GROUP_HDR_WORDS + 1] = -1;
       bk_h2d(dev.g_hdr, hdr.data(), hdr.size() * 4);
     }
     dev.stats = allocFill<long long>(ST_COUNT, 0);

@@ -2175,6 +2175,9 @@ void HivedAlgorithm::releaseLeafCell(Cell* pLeafCell, const std::string& vcn) {
 // hived_algorithm.go:1354-1427
 bool HivedAlgorithm::allocatePreassignedCell(Cell* c, const std::string& vcn, bool doomedBad) {
   bool safetyOk = true;
+  // allocateLeafCell (:1312-1316) passes preassignedCell.GetPhysicalCell(), which is still nil when the physical leaf was
+  // already bound to another virtual cell (bindCell skipped): c.GetChain() on a nil *PhysicalCell is a Go panic
+  if (c == nullptr) throw Panic("runtime error: invalid memory address or nil pointer dereference (allocating a nil preassigned cell)");
   const std::string chain = c->chain;
   int32_t level = c->level;
   // h.vcFreeCellNum[vcn][chain][level]-- on a VC that has no counters for the chain writes into a nil map: a Go panic

@@ -17,6 +17,7 @@ void bk_d2h(void* dst, const void* src, size_t bytes) { memcpy(dst, src, bytes);
 void bk_d2d(void* dst, const void* src, size_t bytes) { memcpy(dst, src, bytes); }
 void bk_zero(void* dst, size_t bytes) { memset(dst, 0, bytes); }
 void bk_quiesce(Engine&) {}
+void bk_forget(Engine&) {}
 int bk_init(int&, std::string&) { return 0; }
 void bk_use_device(int) {}
 void bk_flush_l2() {}

@@ -88,7 +88,7 @@ def run_seed(lib_a, lib_b, seed: int, n_ops: int, fx=None, verbose=False):
                 filtering = os.environ.get("FUZZ_FILTERING") == "1" and rng.random() < 0.4
                 phase = alg.FILTERING_PHASE if filtering else alg.PREEMPTING_PHASE
                 sugg = nodes if rng.random() < 0.8 else [n for n in nodes if rng.random() < 0.7]
-                what = "Schedule(%s as %s, %s)" % (name, pods[0].uid, phase)
+                what = "Schedule(%s [%s] as %s, %s)" % (name, spec["affinityGroup"]["name"], pods[0].uid, phase)
                 ra, rb = both(lambda h, k: _norm(h.Schedule(pods[k], sugg, phase)))
                 if ra != rb:
                     return "seed %d op %d %s: %r != %r" % (seed, step, what, ra, rb)
@@ -96,7 +96,7 @@ def run_seed(lib_a, lib_b, seed: int, n_ops: int, fx=None, verbose=False):
                     return None
                 if ra[0] == "ok" and ra[1][0] == "bind":
                     bound = [alg.new_binding_pod(pods[k], (ra, rb)[k][1][1]) for k in range(2)]
-                    what = "AddAllocatedPod(%s = %s on %s %s)" % (pods[0].uid, name, ra[1][1]["node"], ra[1][1]["leafCellIsolation"])
+                    what = "AddAllocatedPod(%s = %s [%s] on %s %s)" % (pods[0].uid, name, spec["affinityGroup"]["name"], ra[1][1]["node"], ra[1][1]["leafCellIsolation"])
                     ra, rb = both(lambda h, k: h.AddAllocatedPod(bound[k]))
                     if ra != rb:
                         return "seed %d op %d %s: %r != %r" % (seed, step, what, ra, rb)
@@ -137,7 +137,7 @@ def run_seed(lib_a, lib_b, seed: int, n_ops: int, fx=None, verbose=False):
             if va != vb:
                 return "seed %d op %d %s: the persisted order of a cluster view differs" % (seed, step, what)
             if verbose:
-                print(step, what)
+                print(step, what, ra if what.startswith("Schedule") else "")
     finally:
         for h in hs:
             h.close()

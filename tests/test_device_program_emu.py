@@ -189,3 +189,13 @@ def test_compiled_c4_player_equals_python_harness(emu_lib):
         assert hc == hp and sc == sp
         assert tm["events"] > sp["schedule_events"]  # the deletions
         assert (tm["calls"] < tm["events"]) == batch
+
+
+@pytest.mark.parametrize("seed", [16, 31, 7])
+def test_api_fuzz_seeds_with_recreated_group(emu_lib, oracle_lib, seed):
+    """tests/fuzz_api.py: random calls of the 14-method API, results + every cell + every view order compared after every
+    call.  Seeds 16 and 31 erase a group that is being preempted while its leaves still name it and create a new group
+    under the same name (hived_algorithm.go:671-707 -> :1114-1145): the old object lives on as a ghost record
+    (Core::ghostify) — the victims of a later preemption are ITS pods."""
+    import fuzz_api
+    assert fuzz_api.run_seed(emu_lib, oracle_lib, seed, 300) is None

@@ -218,6 +218,14 @@ def test_cuda_full_size_c4_against_oracle(cuda_lib):
     assert stats == golden["stats"]
 
 
+@pytest.mark.parametrize("seed", [16, 31, 3])
+def test_cuda_api_fuzz_seeds(cuda_lib, oracle_lib, seed):
+    """API-level fuzz (tests/fuzz_api.py) on the GPU through the per-call path: results, every cell and every view order
+    after every call; 16 and 31 are the re-created-group seeds (ghost records)."""
+    import fuzz_api
+    assert fuzz_api.run_seed(cuda_lib, oracle_lib, seed, 300) is None
+
+
 def test_cuda_full_size_c4_compiled_player(cuda_lib):
     """The same full-size C4 run driven by compiled code (tests/harness/c4_player.cpp: no interpreter between the calls,
     a gang's pod deletions as one batch): same hash, log and counters as the oracle's committed run."""
