@@ -269,11 +269,40 @@ class HivedAlgorithm:
     def backend(self) -> str:
         return self._lib.hived_backend().decode()
 
-    def _raise(self, rc: int):
+    def _raise(self, rc: int, s: Dict[str, Any] = None, pod: "Pod" = None):
+        """Library return code -> the reference's panic.  User errors (1..99) carry the reference's own message text
+        (the names live above the ABI: the library only knows ids), the one its HTTP 400 body would show."""
         msg = (self._lib.hived_last_error(self._ctx) or b"").decode()
         if 1 <= rc < 100:
-            raise new_bad_request_error(msg)
+            raise new_bad_request_error(self._user_error_message(rc, s, pod) or msg)
         raise PlatformError("panic (%d): %s" % (rc, msg))
+
+    def _user_error_message(self, rc: int, s: Dict[str, Any], pod: "Pod"):
+        if s is None:
+            return None
+        key = "[%s]: " % pod.key() if pod is not None else ""
+        vc, pinned, leaf_type = s["virtualCluster"], s["pinnedCellId"], s["leafCellType"]
+        if rc == 1:    # validateSchedulingRequest, hived_algorithm.go:858-859
+            return key + "VC %s does not exists!" % vc
+        if rc == 2:    # :861-862
+            return key + "VC %s does not have pinned cell %s" % (vc, pinned)
+        if rc == 3:    # :863-864
+            return key + "opportunistic pod not supported to use pinned cell %s" % pinned
+        if rc == 4:    # scheduleNewAffinityGroup, :785-787
+            return key + "Pod requesting leaf cell type %s which the whole cluster does not have" % leaf_type
+        if rc == 5:    # scheduleAffinityGroupForLeafCellType, :824-826 (the type the search was trying: the spec's own)
+            return key + "Pod requesting leaf cell type %s which VC %s does not have" % (leaf_type, vc)
+        if rc == 6:    # schedulePodFromExistingGroup, :684-686: g.totalPodNums of the group as first created
+            name = s["affinityGroup"]["name"]
+            total = 0
+            gid = self._groups.ids.get(name)
+            if gid is not None:
+                gp = _cabi.GroupPlacement()
+                self._lib.hived_get_group_placement(self._ctx, gid, C.byref(gp), None, None, 0, None, 0, None, 0)
+                total = sum(gp.member_pod_num[i] for i in range(gp.n_members) if gp.member_leaf_num[i] == s["leafCellNumber"])
+            return ("Requesting more pods than the configured number for %d leaf cells (%d pods) in affinity group %s"
+                    % (s["leafCellNumber"], total, name))
+        return None
 
     def _spec_struct(self, s: Dict[str, Any], pod: Pod) -> _cabi.PodSpec:
         sp = _cabi.PodSpec()
@@ -426,7 +455,7 @@ class HivedAlgorithm:
                                       _cabi.PHASE_PREEMPTING if phase == PREEMPTING_PHASE else _cabi.PHASE_FILTERING,
                                       C.byref(res), self._pool, self._pool_cap)
         if rc != 0:
-            self._raise(rc)
+            self._raise(rc, s, pod)
         out = PodScheduleResult()
         if res.kind == _cabi.KIND_WAIT:
             out.pod_wait_info = {"reason": self._wait_reason(res, s)}

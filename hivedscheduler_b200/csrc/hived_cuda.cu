@@ -81,17 +81,30 @@ void* bk_alloc(size_t bytes) {
   return p;
 }
 void bk_free(void* p) { cudaFree(p); }
-void bk_h2d(void* dst, const void* src, size_t bytes) { cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice); }
-void bk_d2h(void* dst, const void* src, size_t bytes) { cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost); }
-void bk_d2d(void* dst, const void* src, size_t bytes) { cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToDevice); }
-void bk_zero(void* dst, size_t bytes) { cudaMemset(dst, 0, bytes); }
+// The copy hooks have no return value (the engine is backend-neutral): the first failure of the calling thread is kept
+// and reported by the next launchProgram / bk_run_small as a platform error (bk_init, i.e. hived_create, starts clean).
+static thread_local cudaError_t g_copyErr = cudaSuccess;
+static inline void noteCopy(cudaError_t e) { if (e != cudaSuccess && g_copyErr == cudaSuccess) g_copyErr = e; }
+static int takeCopyError(std::string& err) {
+  if (g_copyErr == cudaSuccess) return 0;
+  err = std::string("a device copy failed: ") + cudaGetErrorString(g_copyErr);
+  g_copyErr = cudaSuccess;
+  cudaGetLastError();
+  return HIVED_ERR_PLATFORM;
+}
+void bk_h2d(void* dst, const void* src, size_t bytes) { if (bytes) noteCopy(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice)); }
+void bk_d2h(void* dst, const void* src, size_t bytes) { if (bytes) noteCopy(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost)); }
+void bk_d2d(void* dst, const void* src, size_t bytes) { if (bytes) noteCopy(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToDevice)); }
+void bk_zero(void* dst, size_t bytes) { if (bytes) noteCopy(cudaMemset(dst, 0, bytes)); }
 
-void bk_flush_l2() {
-  static void* buf = nullptr;
+void bk_flush_l2() {  // one buffer per device (the current one)
+  static void* bufs[64] = {nullptr};
+  int dv = 0;
+  if (cudaGetDevice(&dv) != cudaSuccess || dv < 0 || dv >= 64) return;
   const size_t bytes = 256u << 20;  // > 126 MB of L2
-  if (!buf && cudaMalloc(&buf, bytes) != cudaSuccess) return;
+  if (!bufs[dv] && cudaMalloc(&bufs[dv], bytes) != cudaSuccess) { bufs[dv] = nullptr; return; }
   static int v = 0;
-  cudaMemset(buf, ++v & 0xff, bytes);
+  cudaMemset(bufs[dv], ++v & 0xff, bytes);
   cudaDeviceSynchronize();
 }
 
@@ -110,6 +123,7 @@ int bk_init(int& device, std::string& err) {
   }
   if (device < 0 || device >= count) device = 0;
   if (!cudaOk(cudaSetDevice(device), err, "cudaSetDevice")) return HIVED_ERR_NO_DEVICE;
+  g_copyErr = cudaSuccess;
   // the program recurses (bad-cell propagation, buddy allocation, cell mapping): give it stack
   size_t cur = 0;
   cudaDeviceGetLimit(&cur, cudaLimitStackSize);
@@ -190,6 +204,7 @@ int launchProgram(Engine& e, int n, bool withInit) {
   }
   CudaTimers* t = (CudaTimers*)e.stream;
   bk_quiesce(e);
+  if (int rc = takeCopyError(e.err)) return rc;  // a staging copy of this batch (or of create()) failed
   if (int rc = ensureDevLoaded(e)) return rc;
   const int mgMode = withInit ? 0 : e.mgMode;
   if (mgMode == 3) {  // end of a multi-GPU partition run: the repair pass alone
@@ -528,6 +543,7 @@ int bk_canonicalise(Engine& e, int n, long long* total) {
   long long* blockSum = (long long*)e.dScan.p;              // [nb + 1], 8-byte aligned at the front
   int32_t* excl = (int32_t*)((char*)e.dScan.p + (size_t)(nb + 2) * 8);
   e.dPool2.ensure((size_t)(e.poolCapWords > 0 ? e.poolCapWords : 1) * 4);
+  if (e.buffersFailed()) { e.err = "out of device memory for the pool compaction"; return HIVED_ERR_CAPACITY; }
   pool_words_kernel<<<nb, SCAN_T, 0, t->stream>>>((const hived_result_t*)e.dResults.p, n, excl, blockSum);
   pool_block_scan_kernel<<<1, 1024, 0, t->stream>>>(blockSum, nb);
   pool_gather_kernel<<<(int)(((long long)n * 32 + 255) / 256), 256, 0, t->stream>>>((hived_result_t*)e.dResults.p, n, excl, blockSum,

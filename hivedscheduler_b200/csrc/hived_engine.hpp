@@ -162,6 +162,12 @@ struct Engine {
   }
     HIVED_MUTABLE_ARRAYS(Y)
 #undef Y
+    auto oom = [&]() {
+      err = "out of device memory while creating the context (see hived_options_t: the group tables grow with "
+            "max_groups * max_group_leaves)";
+      return HIVED_ERR_CAPACITY;
+    };
+    if (allocFailed) return oom();  // before anything is copied into a null array
     dev.g_state.b = dev.g_vc.b = dev.g_prio.b = dev.g_flags.b = dev.g_nmem.b = dev.g_npre.b = dev.g_hdr;
     dev.g_mem_leaf.b = dev.g_mem_pods.b = dev.g_hdr;
     {  // g_vc starts at -1
@@ -174,6 +180,7 @@ struct Engine {
     dev.epoch = allocFill<int32_t>(MAX_CTAS, 1);
     mutableRegions.push_back({dev.epoch, MAX_CTAS * sizeof(int32_t)});
     dev.progress = allocFill<int32_t>(MAX_CTAS, 0);
+    if (allocFailed) return oom();
     // one private scratch set per CTA (VC-parallel execution uses up to nCtaMax CTAs)
     nCtaMax = T.nVCs < 16 ? (T.nVCs > 0 ? T.nVCs : 1) : 16;
     if (const char* env = getenv("HIVED_NCTA")) { int v = atoi(env); if (v >= 1 && v <= MAX_CTAS) nCtaMax = v < nCtaMax ? v : nCtaMax; }
@@ -185,6 +192,7 @@ struct Engine {
 #undef Z
       }
       Scratch* dsc = (Scratch*)bk_alloc(sizeof(Scratch) * nCtaMax);
+      if (!dsc || allocFailed) { if (dsc) bk_free(dsc); return oom(); }
       bk_h2d(dsc, sc.data(), sizeof(Scratch) * nCtaMax);
       allocs.push_back(dsc);
       dev.scratch = dsc;

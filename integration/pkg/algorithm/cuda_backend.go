@@ -230,6 +230,40 @@ func (h *CudaHivedAlgorithm) raise(rc C.int) {
 	panic(fmt.Errorf("panic (%d): %s", int(rc), msg))
 }
 
+// raiseForPod is raise for a Schedule call: user errors carry the reference's own message text (the names live above
+// the ABI, the library only knows ids) — hived_algorithm.go:684-686, 785-787, 824-826, 858-868.
+func (h *CudaHivedAlgorithm) raiseForPod(rc C.int, s *api.PodSchedulingSpec, sp *C.hived_pod_spec_t, pod *core.Pod) {
+	key := internal.Key(pod)
+	switch int(rc) {
+	case C.HIVED_ERR_UNKNOWN_VC:
+		panic(internal.NewBadRequestError(fmt.Sprintf("[%v]: VC %v does not exists!", key, s.VirtualCluster)))
+	case C.HIVED_ERR_UNKNOWN_PINNED_CELL:
+		panic(internal.NewBadRequestError(fmt.Sprintf("[%v]: VC %v does not have pinned cell %v", key, s.VirtualCluster, s.PinnedCellId)))
+	case C.HIVED_ERR_OPPORTUNISTIC_PINNED:
+		panic(internal.NewBadRequestError(fmt.Sprintf("[%v]: opportunistic pod not supported to use pinned cell %v", key, s.PinnedCellId)))
+	case C.HIVED_ERR_LEAF_TYPE_NOT_IN_CLUSTER:
+		panic(internal.NewBadRequestError(fmt.Sprintf(
+			"[%v]: Pod requesting leaf cell type %v which the whole cluster does not have", key, s.LeafCellType)))
+	case C.HIVED_ERR_LEAF_TYPE_NOT_IN_VC:
+		panic(internal.NewBadRequestError(fmt.Sprintf(
+			"[%v]: Pod requesting leaf cell type %v which VC %v does not have", key, s.LeafCellType, s.VirtualCluster)))
+	case C.HIVED_ERR_TOO_MANY_PODS:
+		var gp C.hived_group_placement_t
+		total := int32(0)
+		if C.hived_get_group_placement(h.ctx, sp.group, &gp, nil, nil, 0, nil, 0, nil, 0) == 0 {
+			for i := 0; i < int(gp.n_members); i++ {
+				if int32(gp.member_leaf_num[i]) == s.LeafCellNumber {
+					total += int32(gp.member_pod_num[i])
+				}
+			}
+		}
+		panic(internal.NewBadRequestError(fmt.Sprintf(
+			"Requesting more pods than the configured number for %v leaf cells (%v pods) in affinity group %v",
+			s.LeafCellNumber, total, s.AffinityGroup.Name)))
+	}
+	h.raise(rc)
+}
+
 func (h *CudaHivedAlgorithm) toSpec(s *api.PodSchedulingSpec, pod *core.Pod) C.hived_pod_spec_t {
 	var sp C.hived_pod_spec_t
 	sp.pod = h.pods.intern(string(pod.UID))
@@ -445,7 +479,7 @@ func (h *CudaHivedAlgorithm) Schedule(pod *core.Pod, suggestedNodes []string, ph
 	var res C.hived_result_t
 	rc := C.hived_schedule(h.ctx, &sp, (*C.uint32_t)(unsafe.Pointer(&bitmap[0])), ph, &res, &h.pool[0], C.int32_t(len(h.pool)))
 	if rc != 0 {
-		h.raise(rc)
+		h.raiseForPod(rc, s, &sp, pod)
 	}
 	switch res.kind {
 	case C.HIVED_KIND_WAIT:

@@ -2051,6 +2051,9 @@ Placement HivedAlgorithm::lazyPreemptAffinityGroup(Group* victim, const std::str
       for (Cell* vLeafCell : podVirtualPlacement) {
         if (vLeafCell != nullptr) {
           Cell* pLeafCell = vLeafCell->physicalCell;
+          // (a virtual leaf that health churn left unbound: releaseLeafCell reads pLeafCell.virtualCell through a nil
+          // *PhysicalCell in the reference, :1331 — a Go panic)
+          if (pLeafCell == nullptr) throw Panic("runtime error: invalid memory address or nil pointer dereference (lazy preemption of an unbound virtual leaf cell)");
           releaseLeafCell(pLeafCell, victim->vc);
           allocateLeafCell(pLeafCell, nullptr, opportunisticPriority, victim->vc);
         }

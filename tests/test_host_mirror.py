@@ -81,3 +81,48 @@ def test_trace_generators_are_deterministic():
     x ^= (x << 25) & (2 ** 64 - 1)
     x ^= x >> 27
     assert r.next() == (x * 0x2545F4914F6CDD1D) % 2 ** 64
+
+
+def test_user_error_messages_are_the_references(emu_lib):
+    """The HTTP 400 body: the shims format the reference's own message (the names live above the ABI) —
+    hived_algorithm.go:684-686, 785-787, 824-826, 858-868; cases of casesThatShouldFail (hived_algorithm_test.go)."""
+    import copy
+    from golden_scenario import load_fixture
+    from hivedscheduler_b200 import algorithm as alg
+    from hivedscheduler_b200.config import new_config
+    fx = load_fixture()
+    h = alg.HivedAlgorithm(new_config(copy.deepcopy(fx["design_config"])), lib=emu_lib, max_groups=256, max_pods=1024,
+                           max_group_leaves=128, max_group_pods=16)
+    for n in h.node_names:
+        h.setHealthyNode(n)
+
+    def sched(spec, uid):
+        pod = alg.Pod(name=uid, namespace="test", uid=uid, annotations={alg.ANNOTATION_POD_SCHEDULING_SPEC: alg.to_yaml(spec)})
+        return pod, h.Schedule(pod, list(h.node_names), alg.PREEMPTING_PHASE)
+
+    base = copy.deepcopy(fx["pss"]["pod1"])
+    cases = []
+    s = copy.deepcopy(base); s["virtualCluster"] = "surprise!"
+    cases.append((s, "[u1(test/u1)]: VC surprise! does not exists!"))
+    s = copy.deepcopy(base); s["pinnedCellId"] = "surprise!"
+    cases.append((s, "[u2(test/u2)]: VC %s does not have pinned cell surprise!" % base["virtualCluster"]))
+    s = copy.deepcopy(base); s["leafCellType"] = "no-such-gpu"
+    cases.append((s, "[u3(test/u3)]: Pod requesting leaf cell type no-such-gpu which the whole cluster does not have"))
+    for i, (spec, want) in enumerate(cases):
+        with pytest.raises(alg.WebServerError) as ei:
+            sched(spec, "u%d" % (i + 1))
+        assert ei.value.code == 400 and ei.value.message == want
+    # more pods than the group declares
+    spec = copy.deepcopy(base)
+    pod, psr = sched(spec, "u10")
+    assert psr.pod_bind_info is not None
+    h.AddAllocatedPod(alg.new_binding_pod(pod, psr.pod_bind_info))
+    declared = sum(m["podNumber"] for m in spec["affinityGroup"]["members"] if m["leafCellNumber"] == spec["leafCellNumber"])
+    for k in range(declared - 1):
+        pod, psr = sched(spec, "u1%d" % (k + 1))
+        h.AddAllocatedPod(alg.new_binding_pod(pod, psr.pod_bind_info))
+    with pytest.raises(alg.WebServerError) as ei:
+        sched(spec, "u19")
+    assert ei.value.message == ("Requesting more pods than the configured number for %d leaf cells (%d pods) in affinity group %s"
+                                % (spec["leafCellNumber"], declared, spec["affinityGroup"]["name"]))
+    h.close()
