@@ -415,6 +415,7 @@ def main_partitioned(args, lib, rank, world, local):
                        "l2": "flushed between steps (256 MiB memset)",
                        "timing": "CUDA events on the torch stream around the whole partitioned pass (kernels + NCCL rounds); max over ranks",
                        "rounds_per_step": rounds, "broadcast_bytes_per_round": info["shared_bytes"],
+                       "horizon_window_events": info.get("window"), "horizon_advances_per_step": info.get("windows"),
                        "slowest_rank_kernel_ms_last_step": 1e3 * kernel_s_last, "slowest_rank_collective_ms_last_step": 1e3 * coll_s_last,
                        "e2e": "hived_mg_stage from pinned host memory (H2D of the whole batch on every rank), the partitioned pass, "
                               "D2H of the rank's results + pool"},

@@ -699,28 +699,45 @@ struct Core {
       }
     }
   }
-  // hived_algorithm.go:1429-1447
-  HIVED_DEV_NOINLINE void allocateBadCell(int c) {
-    if (d.p_bfpos[c] >= 0) bf_remove(d.p_chain[c], d.p_level[c], c);
-    if (d.p_vcell[c] < 0) {
-      int par = d.p_parent[c];
-      int pv = par >= 0 ? d.p_vcell[par] : -1;
-      int vc = pv >= 0 ? unboundChild(pv) : -1;
-      if (vc < 0) { panic(HIVED_ERR_PLATFORM); return; }
-      bindPair(c, vc);
+  // The reference walks the bad cells below a cell recursively, parent before children, children in order
+  // (hived_algorithm.go:1429-1447, 1487-1500).  Here: the same pre-order walk with an explicit stack of (cell, next
+  // child) — the device program does not recurse, so its stack is sized by the compiler (no cudaLimitStackSize).
+  template <typename Body>
+  HIVED_DEV void forEachBadCellBelow(int c, Body body) {
+    int cell[MAXL], next[MAXL];
+    if (!body(c)) return;
+    int sp = 0;
+    cell[0] = c; next[0] = 0;
+    while (sp >= 0) {
+      const int x = cell[sp], i = next[sp];
+      if (i >= d.p_nchild[x]) { sp--; continue; }
+      next[sp] = i + 1;
+      const int ch = d.p_child0[x] + i;
+      if (!d.p_healthy[ch] && body(ch) && sp + 1 < MAXL) { sp++; cell[sp] = ch; next[sp] = 0; }
     }
-    int c0 = d.p_child0[c], n = d.p_nchild[c];
-    for (int i = 0; i < n; i++)
-      if (!d.p_healthy[c0 + i]) allocateBadCell(c0 + i);
+  }
+  // hived_algorithm.go:1429-1447
+  HIVED_DEV_NOINLINE void allocateBadCell(int c0_) {
+    forEachBadCellBelow(c0_, [&](int c) {
+      if (d.p_bfpos[c] >= 0) bf_remove(d.p_chain[c], d.p_level[c], c);
+      if (d.p_vcell[c] < 0) {
+        int par = d.p_parent[c];
+        int pv = par >= 0 ? d.p_vcell[par] : -1;
+        int vc = pv >= 0 ? unboundChild(pv) : -1;
+        if (vc < 0) { panic(HIVED_ERR_PLATFORM); return false; }
+        bindPair(c, vc);
+      }
+      return true;
+    });
   }
   // hived_algorithm.go:1487-1500
-  HIVED_DEV_NOINLINE void releaseBadCell(int c) {
-    bf_append(d.p_chain[c], d.p_level[c], c);
-    int vc = d.p_vcell[c];
-    if (vc >= 0) unbindPair(c, vc);
-    int c0 = d.p_child0[c], n = d.p_nchild[c];
-    for (int i = 0; i < n; i++)
-      if (!d.p_healthy[c0 + i]) releaseBadCell(c0 + i);
+  HIVED_DEV_NOINLINE void releaseBadCell(int c0_) {
+    forEachBadCellBelow(c0_, [&](int c) {
+      bf_append(d.p_chain[c], d.p_level[c], c);
+      int vc = d.p_vcell[c];
+      if (vc >= 0) unbindPair(c, vc);
+      return true;
+    });
   }
   // hived_algorithm.go:1354-1427
   HIVED_DEV_NOINLINE bool allocatePreassignedCell(int c, int vc, bool doomedBad) {
@@ -811,19 +828,23 @@ struct Core {
     int k = cl(chain, level);
     if (d.allVCFree[k] > d.totalLeft[k] - d.bf_len[k]) tryBindDoomedBadCell(chain, level);
   }
-  // hived_algorithm.go:500-522
+  // hived_algorithm.go:500-522.  The reference marks the cell, recurses into the parent and only then handles the cell
+  // itself: the healthy path is marked bottom-up first, then its cells are handled top-down (no recursion here).
   HIVED_DEV_NOINLINE void setBadCell(int c) {
-    if (!d.p_healthy[c]) return;
-    setHealthiness(c, 0);
-    int par = d.p_parent[c];
-    if (par >= 0) setBadCell(par);
-    if (inFreeCellList(c)) {
-      addBadFreeCell(c);
-    } else if (d.p_vcell[c] < 0 && !d.p_split[c]) {
-      int pv = par >= 0 ? d.p_vcell[par] : -1;
-      int vc = pv >= 0 ? unboundChild(pv) : -1;
-      if (vc < 0) { panic(HIVED_ERR_PLATFORM); return; }
-      bindPair(c, vc);
+    int path[MAXL];
+    int n = 0;
+    for (int x = c; x >= 0 && n < MAXL && d.p_healthy[x]; x = d.p_parent[x]) { setHealthiness(x, 0); path[n++] = x; }
+    for (int k = n - 1; k >= 0; k--) {
+      const int x = path[k];
+      if (inFreeCellList(x)) {
+        addBadFreeCell(x);
+      } else if (d.p_vcell[x] < 0 && !d.p_split[x]) {
+        int par = d.p_parent[x];
+        int pv = par >= 0 ? d.p_vcell[par] : -1;
+        int vc = pv >= 0 ? unboundChild(pv) : -1;
+        if (vc < 0) { panic(HIVED_ERR_PLATFORM); continue; }
+        bindPair(x, vc);
+      }
     }
   }
   // hived_algorithm.go:524-560
@@ -1626,55 +1647,92 @@ struct Core {
   }
 
   // cell_allocation.go:245-315.  cells: ncells vertices linked through vx_next from firstV.
-  HIVED_DEV_NOINLINE bool mapVirtualCellsToPhysical(int firstV, int ncells, const int32_t* candIn, int candBase, int ncand,
-                                                    bool ignoreSuggested, int depth, int32_t* pickedOut) {
-    if (depth >= MAXL || ncells > MAX_FANOUT || (depth > 0 && ncand > MAX_FANOUT)) { panic(HIVED_ERR_CAPACITY); return false; }
-    int32_t* cands = depth == 0 ? s.mc0 : s.mcbuf + depth * MAX_FANOUT;
-    int n = getUsablePhysicalCells(candIn, candBase, ncand, ncells, ignoreSuggested, cands);
-    if (n < 0) return false;
-    int32_t* pickedIdx = s.mcpick + depth * MAX_FANOUT;
-    int32_t* cellV = s.mccells + depth * MAX_FANOUT;
-    {
-      int v = firstV;
-      for (int i = 0; i < ncells; i++) { ST(cellV[i], v); ST(pickedIdx[i], 0); v = s.vx_next[v]; }
-    }
-    int cellIndex = 0;
-    while (cellIndex >= 0) {
+  // The reference recurses into the children of every candidate it tries (one call per tree level) and backtracks over
+  // the candidates of a level.  Here the same search runs as one loop over explicit frames, one per level: the frame's
+  // candidate list / picked indices / cell list already live in per-depth scratch rows (mc0 / mcbuf, mcpick, mccells),
+  // the frame's scalars (usable candidates, cells, current cell, candidate being tried) in four small arrays.  The
+  // order of everything observable — candidates tried, bindings written, where a level resumes after a failed
+  // subtree, the picked indices a revisited cell starts from — is the reference's.
+  HIVED_DEV_NOINLINE bool mapVirtualCellsToPhysical(int firstV, int ncells0, const int32_t* candIn, int candBase, int ncand0,
+                                                    bool ignoreSuggested, int /*depth0*/, int32_t* pickedOut) {
+    int fN[MAXL], fNc[MAXL], fCi[MAXL], fCand[MAXL];
+    int depth = 0;
+    int aFirst = firstV, aNc = ncells0, aBase = candBase, aNcand = ncand0;  // arguments of the frame being entered
+    const int32_t* aIn = candIn;
+    bool ret = false;  // what the frame that just ended returned
+    enum { ENTER = 0, NEWCELL = 1, RESUME = 2, POP = 3 };
+    int st = ENTER;
+    while (true) {
+      if (st == ENTER) {
+        if (depth >= MAXL || aNc > MAX_FANOUT || (depth > 0 && aNcand > MAX_FANOUT)) { panic(HIVED_ERR_CAPACITY); return false; }
+        int32_t* cands = depth == 0 ? s.mc0 : s.mcbuf + depth * MAX_FANOUT;
+        const int n = getUsablePhysicalCells(aIn, aBase, aNcand, aNc, ignoreSuggested, cands);
+        if (n < 0) { ret = false; st = POP; continue; }
+        int32_t* pickedIdx = s.mcpick + depth * MAX_FANOUT;
+        int32_t* cellV = s.mccells + depth * MAX_FANOUT;
+        int v = aFirst;
+        for (int i = 0; i < aNc; i++) { ST(cellV[i], v); ST(pickedIdx[i], 0); v = s.vx_next[v]; }
+        fN[depth] = n; fNc[depth] = aNc; fCi[depth] = 0;
+        st = NEWCELL;
+        continue;
+      }
+      if (st == POP) {
+        if (depth == 0) return ret;
+        depth--;
+        st = RESUME;
+        continue;
+      }
+      // a frame at work
+      int32_t* cands = depth == 0 ? s.mc0 : s.mcbuf + depth * MAX_FANOUT;
+      int32_t* pickedIdx = s.mcpick + depth * MAX_FANOUT;
+      int32_t* cellV = s.mccells + depth * MAX_FANOUT;
+      const int n = fN[depth], ncells = fNc[depth];
+      int cellIndex = fCi[depth];
       int candidateIndex;
-      for (candidateIndex = pickedIdx[cellIndex]; candidateIndex < n; candidateIndex++) {
+      bool picked = false;
+      if (st == NEWCELL) {
+        if (cellIndex < 0) { ret = false; st = POP; continue; }
+        candidateIndex = pickedIdx[cellIndex];
+      } else {  // RESUME: the subtree below candidate fCand[depth] has been tried
+        if (panicCode) return false;
+        candidateIndex = fCand[depth];
+        if (ret) picked = true; else candidateIndex++;
+      }
+      bool descend = false;
+      for (; !picked && candidateIndex < n; candidateIndex++) {
         bool used = false;  // pickedIndexSet == picks of the cells before cellIndex
         for (int j = 0; j < cellIndex; j++)
           if (pickedIdx[j] == candidateIndex) { used = true; break; }
         if (used) continue;
-        int candidate = cands[candidateIndex];
-        int vtx = cellV[cellIndex];
-        bool picked;
+        const int candidate = cands[candidateIndex];
+        const int vtx = cellV[cellIndex];
         if (d.p_level[candidate] == 1) {
-          picked = true;
           ST(d.binding[s.vx_cell[vtx]], candidate);
-        } else {
-          picked = mapVirtualCellsToPhysical(s.vx_child[vtx], s.vx_nch[vtx], nullptr, d.p_child0[candidate], d.p_nchild[candidate],
-                                             ignoreSuggested, depth + 1, nullptr);
-          if (panicCode) return false;
-        }
-        if (picked) {
-          ST(pickedIdx[cellIndex], candidateIndex);
-          if (cellIndex == ncells - 1) {
-            if (pickedOut)
-              for (int i = 0; i < ncells; i++) ST(pickedOut[i], cands[pickedIdx[i]]);
-            return true;
-          }
+          picked = true;
           break;
         }
+        fCand[depth] = candidateIndex;
+        aFirst = s.vx_child[vtx]; aNc = s.vx_nch[vtx]; aIn = nullptr; aBase = d.p_child0[candidate]; aNcand = d.p_nchild[candidate];
+        descend = true;
+        break;
       }
-      if (candidateIndex == n) {
+      if (descend) { depth++; st = ENTER; continue; }
+      if (picked) {
+        ST(pickedIdx[cellIndex], candidateIndex);
+        if (cellIndex == ncells - 1) {
+          if (depth == 0 && pickedOut)
+            for (int i = 0; i < ncells; i++) ST(pickedOut[i], cands[pickedIdx[i]]);
+          ret = true; st = POP;
+          continue;
+        }
+        fCi[depth] = cellIndex + 1;
+      } else {  // every candidate of this cell failed: back to the previous cell, which moves on to its next candidate
         cellIndex--;
         if (cellIndex >= 0) { int v = pickedIdx[cellIndex]; hv_warp_sync(); ST(pickedIdx[cellIndex], v + 1); }
-      } else {
-        cellIndex++;
+        fCi[depth] = cellIndex;
       }
+      st = NEWCELL;
     }
-    return false;
   }
 
   // ---- the Schedule-time copy of the chain's free list (types.go:123-130, hived_algorithm.go:917-929)
@@ -1701,34 +1759,62 @@ struct Core {
     ST(s.sfl_len[level], n - 1);
   }
 
-  // cell_allocation.go:34-80
-  HIVED_DEV_NOINLINE bool buddyAlloc(int vtx, int currentLevel, bool ignoreSuggested) {
-    int cellLevel = d.v_level[s.vx_cell[vtx]];
-    if (currentLevel == cellLevel) {
-      ST(s.vx_next[vtx], -1);
-      bool ok = mapVirtualCellsToPhysical(vtx, 1, sfl(currentLevel), 0, s.sfl_len[currentLevel], ignoreSuggested, 0, s.tmp_list);
-      if (ok) { sflRemove(currentLevel, s.tmp_list[0]); return true; }
-      return false;
-    }
-    int32_t* freeCells = s.ba_buf + (int64_t)currentLevel * d.S.maxLevelCount;
-    int nfree = getUsablePhysicalCells(sfl(currentLevel), 0, s.sfl_len[currentLevel], 1, ignoreSuggested, freeCells);
-    if (nfree < 0) return false;
-    for (int i = 0; i < nfree; i++) {
-      int c = freeCells[i];
-      int32_t* lower = sfl(currentLevel - 1);
-      int nl = s.sfl_len[currentLevel - 1];
-      int nc = d.p_nchild[c], c0 = d.p_child0[c];
-      for (int j = lane; j < nc; j += HIVED_WARPSZ) lower[nl + j] = c0 + j;
-      hv_warp_sync();
-      ST(s.sfl_len[currentLevel - 1], nl + nc);
-      if (buddyAlloc(vtx, currentLevel - 1, ignoreSuggested)) {
-        sflRemove(currentLevel, c);
-        return true;
+  // cell_allocation.go:34-80.  The reference recurses one level down per split; here one loop over the levels with
+  // the loop index and the number of usable cells of every level in two small arrays (the usable cells themselves are
+  // per-level rows of ba_buf already).
+  HIVED_DEV_NOINLINE bool buddyAlloc(int vtx, int startLevel, bool ignoreSuggested) {
+    const int cellLevel = d.v_level[s.vx_cell[vtx]];
+    int fI[MAXL], fCnt[MAXL];
+    int level = startLevel;
+    bool ret = false;
+    enum { ENTER = 0, LOOP = 1, RESUME = 2, POP = 3 };
+    int st = ENTER;
+    while (true) {
+      if (st == ENTER) {
+        if (level == cellLevel) {
+          ST(s.vx_next[vtx], -1);
+          const bool ok = mapVirtualCellsToPhysical(vtx, 1, sfl(level), 0, s.sfl_len[level], ignoreSuggested, 0, s.tmp_list);
+          if (ok) sflRemove(level, s.tmp_list[0]);
+          ret = ok; st = POP;
+          continue;
+        }
+        if (level <= 1 || level >= MAXL) { ret = false; st = POP; continue; }  // (no level below to split into)
+        int32_t* freeCells = s.ba_buf + (int64_t)level * d.S.maxLevelCount;
+        const int nfree = getUsablePhysicalCells(sfl(level), 0, s.sfl_len[level], 1, ignoreSuggested, freeCells);
+        if (nfree < 0) { ret = false; st = POP; continue; }
+        fCnt[level] = nfree; fI[level] = 0;
+        st = LOOP;
+        continue;
       }
-      if (panicCode) return false;
-      ST(s.sfl_len[currentLevel - 1], 0);  // = nil
+      if (st == POP) {
+        if (level == startLevel) return ret;
+        level++;  // back in the frame that split one of its cells
+        st = RESUME;
+        continue;
+      }
+      int32_t* freeCells = s.ba_buf + (int64_t)level * d.S.maxLevelCount;
+      if (st == RESUME) {
+        const int c = freeCells[fI[level]];
+        if (ret) { sflRemove(level, c); ret = true; st = POP; continue; }
+        if (panicCode) return false;
+        ST(s.sfl_len[level - 1], 0);  // = nil
+        fI[level]++;
+        st = LOOP;
+      }
+      // LOOP: split the next usable cell of this level and try one level down
+      if (fI[level] >= fCnt[level]) { ret = false; st = POP; continue; }
+      {
+        const int c = freeCells[fI[level]];
+        int32_t* lower = sfl(level - 1);
+        const int nl = s.sfl_len[level - 1];
+        const int nc = d.p_nchild[c], c0 = d.p_child0[c];
+        for (int j = lane; j < nc; j += HIVED_WARPSZ) lower[nl + j] = c0 + j;
+        hv_warp_sync();
+        ST(s.sfl_len[level - 1], nl + nc);
+        level--;
+        st = ENTER;
+      }
     }
-    return false;
   }
 
   // cell_allocation.go:82-150
@@ -1967,16 +2053,18 @@ struct Core {
     hv_warp_sync();
     ST(d.g_flags[g], (fl & ~GF_HAS_VIRTUAL) | GF_LAZY_PREEMPTED);
   }
-  // hived_algorithm.go:1193-1201
+  // hived_algorithm.go:1193-1201: every Used leaf below the cell, in depth-first order = ascending id (the leaves below
+  // a cell are a contiguous range in child order, hived_topo.hpp fillTree)
   HIVED_DEV_NOINLINE void lazyPreemptCell(int vcell) {
-    if (d.v_level[vcell] == 1 && d.v_state[vcell] == HIVED_CELL_USED) {
-      int pc = d.v_pcell[vcell];
+    const int l0 = d.v_leaf0[vcell], nl = d.v_nleaf[vcell];
+    for (int i = 0; i < nl; i++) {
+      const int leaf = l0 + i;
+      if (d.v_state[leaf] != HIVED_CELL_USED) continue;
+      int pc = d.v_pcell[leaf];
       int g = pc >= 0 ? d.p_using[pc] : -1;
-      if (g < 0) { panic(HIVED_ERR_PLATFORM); return; }
+      if (g < 0) { panic(HIVED_ERR_PLATFORM); continue; }
       lazyPreemptAffinityGroup(g, nullptr);
     }
-    int c0 = d.v_child0[vcell], n = d.v_nchild[vcell];
-    for (int i = 0; i < n; i++) lazyPreemptCell(c0 + i);
   }
   // hived_algorithm.go:1203-1222
   HIVED_DEV_NOINLINE void revertLazyPreempt(int g, const int32_t* save) {

@@ -124,10 +124,8 @@ int bk_init(int& device, std::string& err) {
   if (device < 0 || device >= count) device = 0;
   if (!cudaOk(cudaSetDevice(device), err, "cudaSetDevice")) return HIVED_ERR_NO_DEVICE;
   g_copyErr = cudaSuccess;
-  // the program recurses (bad-cell propagation, buddy allocation, cell mapping): give it stack
-  size_t cur = 0;
-  cudaDeviceGetLimit(&cur, cudaLimitStackSize);
-  if (cur < 16384 && !cudaOk(cudaDeviceSetLimit(cudaLimitStackSize, 16384), err, "cudaDeviceSetLimit")) return HIVED_ERR_NO_DEVICE;
+  // (the device program does not recurse — explicit stacks in hived_core.h — so its stack frame is known to the
+  // compiler and cudaLimitStackSize stays at the driver's default)
   return 0;
 }
 

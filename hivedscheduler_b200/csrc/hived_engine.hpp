@@ -550,14 +550,30 @@ struct Engine {
     for (int c = 0; c < launchCta; c++) { mgCursor[c] = mgStopOut[c]; mgPoolCur[c] = poolEnd[c]; }
     return 0;
   }
-  // every CTA of this rank runs until its next event that may touch the cluster-wide state (or the end of its list)
-  int mgRun(int32_t* stopEvent) {
+  // every CTA of this rank runs its events BELOW `horizon` until its next event that may touch the cluster-wide state.
+  // *stopEvent = the first such event among this rank's events below the horizon (the CTA is parked before it), or
+  // 0x7fffffff when every owned event below the horizon has run.  The horizon keeps the VCs moving together: without
+  // one, a CTA runs on to its own next such event while the others stay parked at theirs, and the whole batch
+  // degenerates to one VC at a time (measured: 8x slower than one GPU).
+  int mgRun(int32_t horizon, int32_t* stopEvent) {
     bk_use_device(deviceOrdinal);
     mgLimit.assign(launchCta, 0);
-    for (int c = 0; c < launchCta; c++) mgLimit[c] = ownOff[c + 1] - ownOff[c];
-    int rc = mgLaunch(1);
-    if (rc) return rc;
-    *stopEvent = mgNextStop();
+    bool work = false;
+    for (int c = 0; c < launchCta; c++) {
+      const int32_t* lst = mgOwnHost.data() + ownOff[c];
+      const int cnt = ownOff[c + 1] - ownOff[c];
+      mgLimit[c] = (int32_t)(std::lower_bound(lst, lst + cnt, horizon) - lst);  // events of the list with index < horizon
+      if (mgLimit[c] < mgCursor[c]) mgLimit[c] = mgCursor[c];
+      if (mgLimit[c] > mgCursor[c]) work = true;
+    }
+    if (work) {
+      int rc = mgLaunch(1);
+      if (rc) return rc;
+    }
+    int mn = 0x7fffffff;
+    for (int c = 0; c < launchCta; c++)
+      if (mgCursor[c] < mgLimit[c] && mgOwnHost[ownOff[c] + mgCursor[c]] < mn) mn = mgOwnHost[ownOff[c] + mgCursor[c]];  // parked
+    *stopEvent = mn;
     return 0;
   }
   // the event every rank stopped at or before runs alone on the cluster, on the rank that owns it
@@ -906,7 +922,8 @@ int hived_mg_stage(hived_ctx* ctx, const hived_event_t* events, int32_t n, int64
   return ctx->e.mgStage(events, n, pool_cap, rank, world);
 }
 int hived_mg_reset(hived_ctx* ctx) { return ctx->e.mgReset(); }
-int hived_mg_run(hived_ctx* ctx, int32_t* stop_event) { return ctx->e.mgRun(stop_event); }
+int hived_mg_run(hived_ctx* ctx, int32_t* stop_event) { return ctx->e.mgRun(0x7fffffff, stop_event); }
+int hived_mg_run_window(hived_ctx* ctx, int32_t horizon, int32_t* stop_event) { return ctx->e.mgRun(horizon, stop_event); }
 int hived_mg_solo(hived_ctx* ctx, int32_t event_index) { return ctx->e.mgSolo(event_index); }
 int64_t hived_mg_shared_bytes(hived_ctx* ctx) { return ctx->e.mgSharedBytes(); }
 int hived_mg_export_shared(hived_ctx* ctx, void* buf) { ctx->e.mgExportShared(buf); return 0; }

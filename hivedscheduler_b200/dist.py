@@ -51,6 +51,8 @@ def bind_multigpu(lib: C.CDLL) -> None:
     lib.hived_mg_reset.argtypes = [P]
     lib.hived_mg_run.restype = C.c_int
     lib.hived_mg_run.argtypes = [P, C.POINTER(C.c_int32)]
+    lib.hived_mg_run_window.restype = C.c_int
+    lib.hived_mg_run_window.argtypes = [P, C.c_int32, C.POINTER(C.c_int32)]
     lib.hived_mg_solo.restype = C.c_int
     lib.hived_mg_solo.argtypes = [P, C.c_int32]
     lib.hived_mg_shared_bytes.restype = C.c_int64
@@ -84,12 +86,13 @@ def event_owner(events, i: int, group_vc: dict, world: int) -> int:
 
 
 def run_partitioned(lib: C.CDLL, ctx, events, n: int, pool_cap: int, rank: int, world: int, device: Optional[str] = None,
-                    staged: bool = False) -> dict:
+                    staged: bool = False, window: Optional[int] = None) -> dict:
     """Drive one partitioned batch on this rank (collective: every rank of the process group calls it with the same
     batch).  `device`: torch device of the exchange buffer ("cuda:k" for the product library; "cpu" for the
     emulation library under gloo).  Returns {"rounds": events run alone on the cluster, "solo_here": those this rank ran,
     "shared_bytes": bytes of one broadcast, "collective_s": host time inside the two collectives (waiting for the
-    slowest rank included)}."""
+    slowest rank included), "windows": horizon advances}.  `window`: events per horizon step (default
+    HIVED_MG_WINDOW or 1024; 0 = no horizon, the first form of the protocol)."""
     import torch
     import torch.distributed as dist
     if not staged:
@@ -101,11 +104,14 @@ def run_partitioned(lib: C.CDLL, ctx, events, n: int, pool_cap: int, rank: int, 
     # who owns an event: only the owner of the winning event needs to know, and it knows (its stop == the minimum);
     # the broadcast needs the owner's RANK on every rank: a second MIN over (stop == E ? rank : world)
     import time
-    rounds = solo_here = 0
+    rounds = solo_here = windows = 0
     t_coll = 0.0
     stop = C.c_int32(0)
+    if window is None:
+        window = int(os.environ.get("HIVED_MG_WINDOW", "1024"))
+    horizon = window if window > 0 else DONE
     while True:
-        _check(lib, ctx, lib.hived_mg_run(ctx, C.byref(stop)), "hived_mg_run")
+        _check(lib, ctx, lib.hived_mg_run_window(ctx, min(horizon, DONE), C.byref(stop)), "hived_mg_run_window")
         mine = int(stop.value)
         tc = time.perf_counter()
         if multi:
@@ -118,7 +124,11 @@ def run_partitioned(lib: C.CDLL, ctx, events, n: int, pool_cap: int, rank: int, 
             e_min, owner = mine, 0
         t_coll += time.perf_counter() - tc
         if e_min == DONE:
-            break
+            if horizon >= n:
+                break
+            horizon += window
+            windows += 1
+            continue
         rounds += 1
         if owner == rank:
             _check(lib, ctx, lib.hived_mg_solo(ctx, e_min), "hived_mg_solo")
@@ -134,7 +144,8 @@ def run_partitioned(lib: C.CDLL, ctx, events, n: int, pool_cap: int, rank: int, 
             if owner != rank:
                 lib.hived_mg_import_shared(ctx, C.c_void_p(buf.data_ptr()))
     _check(lib, ctx, lib.hived_mg_finish(ctx), "hived_mg_finish")
-    return {"rounds": rounds, "solo_here": solo_here, "shared_bytes": nbytes, "collective_s": t_coll}
+    return {"rounds": rounds, "solo_here": solo_here, "shared_bytes": nbytes, "collective_s": t_coll, "windows": windows,
+            "window": window}
 
 
 def chain_hash(lib: C.CDLL, events, n: int, world: int, results: Sequence, pools: Sequence, seed: int = 0xCBF29CE484222325) -> int:

@@ -12,14 +12,19 @@
  * order.  Protocol, driven by the caller (bench.py / tests use torch.distributed for the two collectives):
  *
  *   hived_mg_stage(ctx, events, n, pool_cap, rank, world)        every rank, the whole batch
+ *   H = W                               the horizon: an event index; windows of W events keep the VCs moving together
  *   loop:
- *     hived_mg_run(ctx, &stop)          every rank runs its events up to (not including) its first event that may
- *                                       touch the cluster-wide state; stop = that event's index, 0x7fffffff = done
- *     E = allreduce_min(stop)           (collective #1)                         E == 0x7fffffff: leave the loop
+ *     hived_mg_run_window(ctx, H, &stop) every rank runs its events below H; a CTA whose next event may touch the
+ *                                       cluster-wide state parks BEFORE it: stop = the first such event of the rank,
+ *                                       0x7fffffff = every owned event below H has run
+ *     E = allreduce_min(stop)           (collective #1)
+ *     E == 0x7fffffff:                  H >= n: leave the loop; else H += W, next round
  *     owner of E: hived_mg_solo(ctx, E); hived_mg_export_shared(ctx, buf)
  *     broadcast(buf, src = owner)       (collective #2, hived_mg_shared_bytes() bytes of device memory)
  *     everyone else: hived_mg_import_shared(ctx, buf)
  *   hived_mg_finish(ctx)
+ *   (hived_mg_run = hived_mg_run_window with H = infinity: correct, but a CTA then runs on to ITS next such event
+ *   while every other one is parked at theirs — one VC at a time.)
  *   hived_bench_fetch_results()         rank r holds the results of ITS events (the other records are all-zero)
  *
  * Every event of every rank before E is complete when E runs, and E is complete before any later event that may
@@ -37,6 +42,7 @@ extern "C" {
 int hived_mg_stage(hived_ctx*, const hived_event_t* events, int32_t n, int64_t pool_cap, int32_t rank, int32_t world);
 int hived_mg_reset(hived_ctx*);   /* the staged batch once more (after hived_bench_restore_state): cursors and results cleared */
 int hived_mg_run(hived_ctx*, int32_t* stop_event);
+int hived_mg_run_window(hived_ctx*, int32_t horizon, int32_t* stop_event);
 int hived_mg_solo(hived_ctx*, int32_t event_index);
 int64_t hived_mg_shared_bytes(hived_ctx*);
 int hived_mg_export_shared(hived_ctx*, void* device_buffer);       /* device pointer on the context's GPU */

@@ -27,7 +27,7 @@ def _contexts(lib, t, world):
     return out
 
 
-def simulate(lib, t, world, alloc=None):
+def simulate(lib, t, world, alloc=None, window=0):
     """`world` ranks in one process, the two collectives done by hand.  alloc(nbytes) -> (keepalive, pointer) of the
     exchange buffer (device memory for the CUDA library; default: host memory for the emulation libraries)."""
     dist.bind_multigpu(lib)
@@ -45,15 +45,22 @@ def simulate(lib, t, world, alloc=None):
     else:
         buf, buf_ptr = alloc(nbytes)
     rounds = 0
+    horizon = window if window > 0 else dist.DONE  # window = 0: the protocol without a horizon (hived_mg_run)
     while True:
         stops = []
         for bc in ranks:
             s = C.c_int32(0)
-            assert lib.hived_mg_run(bc.ctx, C.byref(s)) == 0, lib.hived_last_error(bc.ctx)
+            if window > 0:
+                assert lib.hived_mg_run_window(bc.ctx, min(horizon, dist.DONE), C.byref(s)) == 0, lib.hived_last_error(bc.ctx)
+            else:
+                assert lib.hived_mg_run(bc.ctx, C.byref(s)) == 0, lib.hived_last_error(bc.ctx)
             stops.append(s.value)
         e = min(stops)
         if e == dist.DONE:
-            break
+            if horizon >= n:
+                break
+            horizon += window
+            continue
         rounds += 1
         owner = stops.index(e)
         assert lib.hived_mg_solo(ranks[owner].ctx, e) == 0, lib.hived_last_error(ranks[owner].ctx)
@@ -75,11 +82,11 @@ def simulate(lib, t, world, alloc=None):
     return h, rounds
 
 
-@pytest.mark.parametrize("world", [1, 2, 3])
-def test_partitioned_simt_matches_single_run(simt_lib, oracle_lib, world):
+@pytest.mark.parametrize("world,window", [(1, 0), (2, 0), (3, 0), (2, 64), (3, 7)])
+def test_partitioned_simt_matches_single_run(simt_lib, oracle_lib, world, window):
     t = small_c3(400)
     h1, _, _ = run_trace(oracle_lib, t)
-    h, rounds = simulate(simt_lib, t, world)
+    h, rounds = simulate(simt_lib, t, world, window=window)
     assert h == h1
     assert rounds >= 1  # the first gang of each VC binds a preassigned cell
 
@@ -90,10 +97,11 @@ def c3_8vc(oracle_lib):
     return t, run_trace(oracle_lib, t)[0]
 
 
-@pytest.mark.parametrize("world", [1, 2, 4, 8])
-def test_partitioned_mt_matches_single_run_on_8_vcs(emu_mt_lib, c3_8vc, world):
+@pytest.mark.parametrize("world,window", [(1, 0), (2, 0), (4, 0), (8, 0), (2, 256), (4, 100), (8, 1), (8, 1024)])
+def test_partitioned_mt_matches_single_run_on_8_vcs(emu_mt_lib, c3_8vc, world, window):
+    """window > 0: the horizon form of the protocol (hived_mg_run_window), what dist.run_partitioned drives."""
     t, h1 = c3_8vc
-    h, rounds = simulate(emu_mt_lib, t, world)
+    h, rounds = simulate(emu_mt_lib, t, world, window=window)
     assert h == h1
     assert rounds >= 8
 
