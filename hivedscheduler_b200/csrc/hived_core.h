@@ -646,8 +646,20 @@ struct Core {
     }
   }
 
+  // ---- allocate/releasePreassignedCell and tryBind/tryUnbindDoomedBadCell call each other in the reference
+  // (hived_algorithm.go:602-653, 1354-1485): binding a doomed bad cell allocates it as a preassigned cell, which may
+  // leave another level short of healthy cells, and so on.  Every nested call is a doomed-bad one and only looks at
+  // levels ABOVE its own, so the nesting is bounded by the height of the chain; the four functions are templates on
+  // the nesting depth D (the call graph is a finite DAG, the device stack stays statically sized) and a cascade deeper
+  // than DOOM_DEPTH reports HIVED_ERR_CAPACITY.  D > 0 implies doomedBad.
+  static constexpr int DOOM_DEPTH = 10;
+  HIVED_DEV void tryBindDoomedBadCell(int chain, int l) { tryBindDoomedBadCellT<0>(chain, l); }
+  HIVED_DEV void tryUnbindDoomedBadCell(int chain, int l) { tryUnbindDoomedBadCellT<0>(chain, l); }
+  HIVED_DEV bool allocatePreassignedCell(int c, int vc, bool doomedBad) { return allocatePreassignedCellT<0>(c, vc, doomedBad); }
+  HIVED_DEV void releasePreassignedCell(int c, int vc, bool doomedBad) { releasePreassignedCellT<0>(c, vc, doomedBad); }
   // hived_algorithm.go:602-628 (VCs in ascending id order)
-  HIVED_DEV_NOINLINE void tryBindDoomedBadCell(int chain, int l) {
+  template <int D>
+  HIVED_DEV_NOINLINE void tryBindDoomedBadCellT(int chain, int l) {
     int k = cl(chain, l);
     // no VC is short of healthy cells (lane = VC: the largest vcFree decides; the sum allVCFree is no bound once a
     // safety violation has driven some VC's count negative)
@@ -674,13 +686,15 @@ struct Core {
         bindPair(pc, vcell);
         dm_append(vc, chain, l, pc);
         ST(d.allVCDoomed[k], d.allVCDoomed[k] + 1);
-        allocatePreassignedCell(pc, vc, true);
+        if constexpr (D < DOOM_DEPTH) allocatePreassignedCellT<D + 1>(pc, vc, true);
+        else panic(HIVED_ERR_CAPACITY);
         if (panicCode) return;
       }
     }
   }
   // hived_algorithm.go:630-653
-  HIVED_DEV_NOINLINE void tryUnbindDoomedBadCell(int chain, int l) {
+  template <int D>
+  HIVED_DEV_NOINLINE void tryUnbindDoomedBadCellT(int chain, int l) {
     int k = cl(chain, l);
     if (d.allVCDoomed[k] == 0) return;  // no doomed bad cell of any VC at this level
     for (int vc = 0; vc < d.S.nVCs; vc++) {
@@ -694,7 +708,8 @@ struct Core {
         unbindPair(pc, d.p_vcell[pc]);
         dm_remove(vc, chain, l, pc);
         ST(d.allVCDoomed[k], d.allVCDoomed[k] - 1);
-        releasePreassignedCell(pc, vc, true);
+        if constexpr (D < DOOM_DEPTH) releasePreassignedCellT<D + 1>(pc, vc, true);
+        else panic(HIVED_ERR_CAPACITY);
         if (panicCode) return;
       }
     }
@@ -740,7 +755,8 @@ struct Core {
     });
   }
   // hived_algorithm.go:1354-1427
-  HIVED_DEV_NOINLINE bool allocatePreassignedCell(int c, int vc, bool doomedBad) {
+  template <int D>
+  HIVED_DEV_NOINLINE bool allocatePreassignedCellT(int c, int vc, bool doomedBad) {
     if (c < 0) { panic(HIVED_ERR_PLATFORM); return false; }  // nil *PhysicalCell dereferenced in the reference (:1358): see allocateLeafCell
     sharedEnter();
     bool safetyOk = true;
@@ -759,28 +775,29 @@ struct Core {
       if (!d.p_healthy[parent]) {
         bf_remove(chain, l, parent);
       } else {
-        tryBindDoomedBadCell(chain, l);
+        tryBindDoomedBadCellT<D>(chain, l);
       }
       parent = d.p_parent[parent];
     }
     if (!d.p_healthy[c]) {
       allocateBadCell(c);
-      if (!doomedBad) tryUnbindDoomedBadCell(chain, level);
+      if constexpr (D == 0) { if (!doomedBad) tryUnbindDoomedBadCellT<D>(chain, level); }
     } else {
-      tryBindDoomedBadCell(chain, level);
+      tryBindDoomedBadCellT<D>(chain, level);
     }
     int numToReduce = d.p_nchild[c];
     for (int l = level - 1; l >= 1; l--) {
       int kl = cl(chain, l);
       ST(d.totalLeft[kl], d.totalLeft[kl] - numToReduce);
       if (d.totalLeft[kl] < d.allVCFree[kl]) safetyOk = false;
-      if (!doomedBad) tryBindDoomedBadCell(chain, l);
+      if constexpr (D == 0) { if (!doomedBad) tryBindDoomedBadCellT<D>(chain, l); }
       numToReduce *= d.chain_lvl_nchild[kl];
     }
     return safetyOk;
   }
   // hived_algorithm.go:1449-1485
-  HIVED_DEV_NOINLINE void releasePreassignedCell(int c, int vc, bool doomedBad) {
+  template <int D>
+  HIVED_DEV_NOINLINE void releasePreassignedCellT(int c, int vc, bool doomedBad) {
     sharedEnter();
     int chain = d.p_chain[c], level = d.p_level[c];
     int kv = vcl(vc, chain, level), k = cl(chain, level);
@@ -796,21 +813,21 @@ struct Core {
       if (!d.p_healthy[parent]) {
         bf_append(chain, l, parent);
       } else {
-        tryUnbindDoomedBadCell(chain, l);
+        tryUnbindDoomedBadCellT<D>(chain, l);
       }
       parent = d.p_parent[parent];
     }
     if (!d.p_healthy[c]) {
       releaseBadCell(c);
-      if (!doomedBad) tryBindDoomedBadCell(chain, level);
+      if constexpr (D == 0) { if (!doomedBad) tryBindDoomedBadCellT<D>(chain, level); }
     } else {
-      tryUnbindDoomedBadCell(chain, level);
+      tryUnbindDoomedBadCellT<D>(chain, level);
     }
     int numToAdd = d.p_nchild[c];
     for (int l = level - 1; l >= 1; l--) {
       int kl = cl(chain, l);
       ST(d.totalLeft[kl], d.totalLeft[kl] + numToAdd);
-      if (!doomedBad) tryUnbindDoomedBadCell(chain, l);
+      if constexpr (D == 0) { if (!doomedBad) tryUnbindDoomedBadCellT<D>(chain, l); }
       numToAdd *= d.chain_lvl_nchild[kl];
     }
   }

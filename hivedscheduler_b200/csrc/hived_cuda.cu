@@ -125,7 +125,11 @@ int bk_init(int& device, std::string& err) {
   if (!cudaOk(cudaSetDevice(device), err, "cudaSetDevice")) return HIVED_ERR_NO_DEVICE;
   g_copyErr = cudaSuccess;
   // (the device program does not recurse — explicit stacks in hived_core.h — so its stack frame is known to the
-  // compiler and cudaLimitStackSize stays at the driver's default)
+  // compiler and cudaLimitStackSize stays at the driver's default; HIVED_STACK_BYTES overrides it for experiments)
+  if (const char* sb = getenv("HIVED_STACK_BYTES")) {
+    const long v = atol(sb);
+    if (v > 0 && !cudaOk(cudaDeviceSetLimit(cudaLimitStackSize, (size_t)v), err, "cudaDeviceSetLimit")) return HIVED_ERR_NO_DEVICE;
+  }
   return 0;
 }
 
