@@ -2119,7 +2119,8 @@ struct Core {
         int L = ph[i];
         ok = L >= 0;
         int V = ok ? d.p_vcell[L] : -1;
-        ok = ok && V >= 0 && d.p_state[L] == HIVED_CELL_USED && d.p_healthy[L] && d.p_prio[L] >= 0 && !(d.p_flags[L] & PF_PINNED_BIT);
+        // (a leaf on a bad node is released like a healthy one except that it stays bound, releaseLeafCell :1340)
+        ok = ok && V >= 0 && d.p_state[L] == HIVED_CELL_USED && d.p_prio[L] >= 0 && !(d.p_flags[L] & PF_PINNED_BIT);
         ok = ok && d.v_prio[V] != FREE_PRIO;
         if (ok) {
           int pre = d.v_pre[V];
@@ -2142,9 +2143,11 @@ struct Core {
       bkMarkLeaves(i < nl, i < nl ? s.pl_v[i] : 0);
       if (i < nl) {
         int L = ph[i], V = s.pl_v[i];
+        const bool healthy = d.p_healthy[L] != 0;
         d.p_using[L] = -1;
         d.v_prio[V] = FREE_PRIO; d.p_prio[L] = FREE_PRIO;
-        d.p_vcell[L] = -1; d.v_pcell[V] = -1; d.v_state[V] = HIVED_CELL_FREE; d.v_healthy[V] = 1;
+        if (healthy) { d.p_vcell[L] = -1; d.v_pcell[V] = -1; d.v_healthy[V] = 1; }  // unbindCell only "if pLeafCell.IsHealthy()"
+        d.v_state[V] = HIVED_CELL_FREE;
         d.p_state[L] = HIVED_CELL_FREE;
       }
     }
