@@ -106,6 +106,7 @@ SYMBOLS = [
     ("hived_add_allocated_pod", C.c_int,
      [_P, C.POINTER(PodSpec), C.POINTER(BindInfo), C.POINTER(C.c_int32), C.c_int32]),
     ("hived_delete_allocated_pod", C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32]),
+    ("hived_delete_allocated_pod_ex", C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),
     ("hived_delete_unallocated_pod", C.c_int, [_P, C.c_int32, C.c_int32]),
     ("hived_process_events", C.c_int,
      [_P, C.POINTER(Event), C.c_int32, C.POINTER(C.c_uint32), C.c_int64, C.POINTER(Result),

@@ -519,10 +519,16 @@ class HivedAlgorithm:
         gid = self._groups.ids.get(name)
         if gid is None:
             return  # "Group %v not found when deleting pod" in the reference
-        rc = self._lib.hived_delete_allocated_pod(self._ctx, gid, s["leafCellNumber"], pod_index)
+        removed = C.c_int32(-1)
+        rc = self._lib.hived_delete_allocated_pod_ex(self._ctx, gid, s["leafCellNumber"], pod_index, C.byref(removed))
         if rc != 0:
             self._raise(rc)
-        self._release_pod(pod)
+        # The reference clears the slot whoever sits there (:287).  Only when that was THIS pod has it left the
+        # library's tables: otherwise (its group object was replaced under the same name and lives on through
+        # cell.usingGroup, or the slot held another pod) the pod can still come back as a preemption victim, so its
+        # object and id are kept (include/hived.h "Id lifetime").
+        if removed.value == self._pods.ids.get(pod.uid, -2):
+            self._release_pod(pod)
         self._release_group_if_gone(name, gid)
 
     # AddNode / UpdateNode / DeleteNode (hived_algorithm.go:147-178); node = {"name":..., "healthy": bool}

@@ -652,7 +652,7 @@ struct Core {
   // levels ABOVE its own, so the nesting is bounded by the height of the chain; the four functions are templates on
   // the nesting depth D (the call graph is a finite DAG, the device stack stays statically sized) and a cascade deeper
   // than DOOM_DEPTH reports HIVED_ERR_CAPACITY.  D > 0 implies doomedBad.
-  static constexpr int DOOM_DEPTH = 10;
+  static constexpr int DOOM_DEPTH = 6;  // nested calls go strictly up the chain: enough for chains of 7 levels (C3 has 5, the design config 7)
   HIVED_DEV void tryBindDoomedBadCell(int chain, int l) { tryBindDoomedBadCellT<0>(chain, l); }
   HIVED_DEV void tryUnbindDoomedBadCell(int chain, int l) { tryUnbindDoomedBadCellT<0>(chain, l); }
   HIVED_DEV bool allocatePreassignedCell(int c, int vc, bool doomedBad) { return allocatePreassignedCellT<0>(c, vc, doomedBad); }
@@ -3003,8 +3003,12 @@ struct Core {
   }
 
   // hived_algorithm.go:272-296
-  HIVED_DEV void deleteAllocatedPod(int g, int leafNum, int podIndex, int evVc) {
+  // res->pod_index of a DELETE_ALLOCATED event: the pod id that occupied the slot the call cleared, -1 when it cleared
+  // nothing (the reference clears allocatedPods[leafNum][podIndex] whoever sits there, :287: the shims need to know
+  // whether THEIR pod left the table, see hived.h "Id lifetime")
+  HIVED_DEV void deleteAllocatedPod(int g, int leafNum, int podIndex, int evVc, hived_result_t* res) {
     long long tq = pclock();
+    ST(res->pod_index, -1);
     if (g < 0 || g >= d.S.maxGroups || d.g_state[g] == HIVED_GROUP_NONE) return;
     (void)evVc;  // (the host routes a DELETE by the VC its group was scheduled under, hived_engine.hpp prepare())
     if (podIndex == -1) return;
@@ -3012,7 +3016,9 @@ struct Core {
     if (m < 0 || podIndex < 0 || podIndex >= d.g_mem_pods[g * 8 + m]) { panic(HIVED_ERR_PLATFORM); return; }
     int leafOff, podOff;
     memberOffsets(g, m, leafOff, podOff);
+    const int occupant = gpods(g)[podOff + podIndex];
     ST(gpods(g)[podOff + podIndex], -1);
+    ST(res->pod_index, occupant);
     const int32_t* po = gpods(g);
     if (firstIdx(groupPods(g), [&](int i) { return po[i] >= 0; }) >= 0) return;
     deleteAllocatedAffinityGroup(g);
@@ -3215,7 +3221,7 @@ struct Core {
       if (rc == 0) { addAllocatedPod(ev.spec, b, ev.arg0); rc = panicCode; }
     } else if (type == HIVED_EV_DELETE_ALLOCATED) {
       long long td0 = pclock();
-      deleteAllocatedPod(ev.spec.group, ev.spec.leaf_num, ev.arg0, ev.spec.vc);
+      deleteAllocatedPod(ev.spec.group, ev.spec.leaf_num, ev.arg0, ev.spec.vc, res);
       if (mgStop) return;
       stat_add(ST_CYC_DELETE, pclock() - td0);
       if (ev.spec.group >= 0 && ev.spec.group < d.S.maxGroups && d.g_state[ev.spec.group] != HIVED_GROUP_NONE) {

@@ -720,12 +720,18 @@ int hived_add_allocated_pod(hived_ctx* ctx, const hived_pod_spec_t* spec, const 
   return hived_run_one(ctx, ev, nullptr, aux.data(), (int64_t)aux.size(), &res, pool, 4);
 }
 
-int hived_delete_allocated_pod(hived_ctx* ctx, int32_t group, int32_t leaf_num, int32_t pod_index) {
+int hived_delete_allocated_pod_ex(hived_ctx* ctx, int32_t group, int32_t leaf_num, int32_t pod_index, int32_t* removed_pod) {
   hived_event_t ev;
   memset(&ev, 0, sizeof ev);
   ev.type = HIVED_EV_DELETE_ALLOCATED; ev.arg0 = pod_index; ev.spec.group = group; ev.spec.leaf_num = leaf_num;
   hived_result_t res; int32_t pool[4];
-  return hived_run_one(ctx, ev, nullptr, nullptr, 0, &res, pool, 4);
+  res.pod_index = -1;
+  int rc = hived_run_one(ctx, ev, nullptr, nullptr, 0, &res, pool, 4);
+  if (removed_pod) *removed_pod = res.pod_index;
+  return rc;
+}
+int hived_delete_allocated_pod(hived_ctx* ctx, int32_t group, int32_t leaf_num, int32_t pod_index) {
+  return hived_delete_allocated_pod_ex(ctx, group, leaf_num, pod_index, nullptr);
 }
 
 int hived_delete_unallocated_pod(hived_ctx* ctx, int32_t group, int32_t pod) {

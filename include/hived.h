@@ -30,7 +30,8 @@
  *     order; inside each: level 1..top, construction order (config.go:282-317).
  *   Group ids and pod ids are interned by the caller (dense, < the capacities in hived_options_t).
  *   Id lifetime: a group id may be handed to another group once hived_get_group reports HIVED_GROUP_NONE for it (after
- *   the DeleteAllocatedPod / DeleteUnallocatedPod that removed its last pod), a pod id once the pod has been deleted;
+ *   the DeleteAllocatedPod / DeleteUnallocatedPod that removed its last pod), a pod id once the pod has been deleted
+ *   AND hived_delete_allocated_pod_ex reported it as the removed occupant (see there);
  *   the shims recycle them that way (hivedscheduler_b200/algorithm.py, integration/pkg/algorithm/cuda_backend.go), so a
  *   long-running scheduler never meets HIVED_ERR_CAPACITY.  Batch callers (hived_process_events) number the gangs of
  *   one batch themselves.
@@ -274,8 +275,14 @@ int hived_schedule(hived_ctx*, const hived_pod_spec_t* spec, const uint32_t* sug
  * (utils.go:291-304), computed by the shim from the annotation; leaves as in hived_bind_info_t. */
 int hived_add_allocated_pod(hived_ctx*, const hived_pod_spec_t* spec, const hived_bind_info_t* info,
                             const int32_t* leaves, int32_t pod_index);
-/* DeleteAllocatedPod (hived_algorithm.go:272-296) */
+/* DeleteAllocatedPod (hived_algorithm.go:272-296).  The reference clears allocatedPods[leaf_num][pod_index] WHOEVER sits
+ * there (:287).  _ex also reports that occupant: *removed_pod = its pod id, -1 when the call cleared nothing (unknown
+ * group, pod_index -1, empty slot).  A shim may recycle its pod's id only when *removed_pod is that pod; otherwise the
+ * pod object can still be named by the library (the group object it was added to has been replaced under the same
+ * name — the reference keeps such objects alive through cell.usingGroup) and must be kept.  In a batch the same value
+ * is hived_result_t.pod_index of the DELETE_ALLOCATED event. */
 int hived_delete_allocated_pod(hived_ctx*, int32_t group, int32_t leaf_num, int32_t pod_index);
+int hived_delete_allocated_pod_ex(hived_ctx*, int32_t group, int32_t leaf_num, int32_t pod_index, int32_t* removed_pod);
 /* DeleteUnallocatedPod (hived_algorithm.go:229-245); AddUnallocatedPod is a no-op in the reference */
 int hived_delete_unallocated_pod(hived_ctx*, int32_t group, int32_t pod);
 

@@ -607,10 +607,14 @@ func (h *CudaHivedAlgorithm) DeleteAllocatedPod(pod *core.Pod) {
 		return // "Group %v not found when deleting pod" in the reference
 	}
 	podIndex := cudaGetAllocatedPodIndex(info, s.LeafCellNumber)
-	if rc := C.hived_delete_allocated_pod(h.ctx, gid, C.int32_t(s.LeafCellNumber), C.int32_t(podIndex)); rc != 0 {
+	removed := C.int32_t(-1)
+	if rc := C.hived_delete_allocated_pod_ex(h.ctx, gid, C.int32_t(s.LeafCellNumber), C.int32_t(podIndex), &removed); rc != 0 {
 		h.raise(rc)
 	}
-	if pid, ok := h.pods.lookup(string(pod.UID)); ok {
+	// The reference clears the slot whoever sits there (hived_algorithm.go:287).  Only when that was THIS pod has it
+	// left the library's tables; otherwise it can still come back as a preemption victim (its group object was replaced
+	// under the same name and lives on through cell.usingGroup): its object and id are kept (hived.h "Id lifetime").
+	if pid, ok := h.pods.lookup(string(pod.UID)); ok && pid == removed {
 		h.releasePod(pod, pid)
 	}
 	h.releaseGroupIfGone(s.AffinityGroup.Name, gid)

@@ -1700,15 +1700,20 @@ void HivedAlgorithm::AddAllocatedPod(const PodSchedulingSpec& s, const PodBindIn
 }
 
 // hived_algorithm.go:272-296
-void HivedAlgorithm::DeleteAllocatedPod(const std::string& groupName, int32_t leafCellNumber, int32_t podIndex) {
+// returns the id of the pod that occupied the cleared slot (-1: nothing cleared) — hived_result_t.pod_index of the event
+int32_t HivedAlgorithm::DeleteAllocatedPod(const std::string& groupName, int32_t leafCellNumber, int32_t podIndex) {
+  lastRemovedPod = -1;
   auto git = affinityGroups.find(groupName);
-  if (git == affinityGroups.end()) return;
+  if (git == affinityGroups.end()) return -1;
   Group* g = git->second;
-  if (podIndex == -1) return;
+  if (podIndex == -1) return -1;
   auto& slots = g->allocatedPods[leafCellNumber];
   if (podIndex < 0 || podIndex >= (int32_t)slots.size()) throw Panic("DeleteAllocatedPod: index out of range");
+  const int32_t occupant = slots[podIndex] ? slots[podIndex]->id : -1;
   slots[podIndex] = nullptr;
+  lastRemovedPod = occupant;  // (also when the group's deletion below panics)
   if (allPodsReleased(g->allocatedPods)) deleteAllocatedAffinityGroup(g);
+  return occupant;
 }
 
 // hived_algorithm.go:655-712

@@ -237,7 +237,8 @@ class HivedAlgorithm {
                           const std::vector<std::string>& suggestedNodes, bool preemptingPhase);
   void AddAllocatedPod(const PodSchedulingSpec& s, const PodBindInfo& info, int32_t podId,
                        int32_t nodeId, int32_t podIndexFromInfo);
-  void DeleteAllocatedPod(const std::string& groupName, int32_t leafCellNumber, int32_t podIndex);
+  int32_t DeleteAllocatedPod(const std::string& groupName, int32_t leafCellNumber, int32_t podIndex);
+  int32_t lastRemovedPod = -1;  // occupant of the slot the last DeleteAllocatedPod cleared
   void DeleteUnallocatedPod(const std::string& groupName, int32_t podId);
   void setBadNode(const std::string& nodeName);
   void setHealthyNode(const std::string& nodeName);

@@ -330,8 +330,13 @@ int hived_add_allocated_pod(hived_ctx* ctx, const hived_pod_spec_t* spec, const 
   });
 }
 
+int hived_delete_allocated_pod_ex(hived_ctx* ctx, int32_t group, int32_t leaf_num, int32_t pod_index, int32_t* removed_pod) {
+  int rc = guarded(ctx, [&] { ctx->h->DeleteAllocatedPod(groupName(group), leaf_num, pod_index); });
+  if (removed_pod) *removed_pod = ctx->h->lastRemovedPod;
+  return rc;
+}
 int hived_delete_allocated_pod(hived_ctx* ctx, int32_t group, int32_t leaf_num, int32_t pod_index) {
-  return guarded(ctx, [&] { ctx->h->DeleteAllocatedPod(groupName(group), leaf_num, pod_index); });
+  return hived_delete_allocated_pod_ex(ctx, group, leaf_num, pod_index, nullptr);
 }
 
 int hived_delete_unallocated_pod(hived_ctx* ctx, int32_t group, int32_t pod) {
@@ -356,7 +361,8 @@ int hived_process_events(hived_ctx* ctx, const hived_event_t* events, int32_t n,
         break;
       }
       case HIVED_EV_DELETE_ALLOCATED:
-        rc = hived_delete_allocated_pod(ctx, ev.spec.group, ev.spec.leaf_num, ev.arg0);
+        r->pod_index = -1;
+        rc = hived_delete_allocated_pod_ex(ctx, ev.spec.group, ev.spec.leaf_num, ev.arg0, &r->pod_index);
         break;
       case HIVED_EV_DELETE_UNALLOCATED:
         rc = hived_delete_unallocated_pod(ctx, ev.spec.group, ev.spec.pod);
