@@ -28,7 +28,7 @@ from hivedscheduler_b200 import _cabi, trace  # noqa: E402
 
 METRIC = "scheduling decisions/sec on 64k-GPU cell tree, 100k pending gangs"
 # dram__bytes_read.sum + dram__bytes_write.sum of hived_events_kernel over the full C3 trace (one ncu --set full capture)
-NCU_DRAM_BYTES_PER_LAUNCH_C3 = 81_649_920 + 92_605_696
+NCU_DRAM_BYTES_PER_LAUNCH_C3 = 88_998_912 + 93_801_728  # profiles/r2_final.md section 2 (the final kernel)
 WORKLOAD = "C3: 8192 nodes x 8 GPU (65536 GPUs), 5-level tree, 8 VCs, 100000 mixed gangs (1/4/8/64-GPU), admission window 0.9"
 
 
@@ -595,7 +595,7 @@ def main():
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": NCU_DRAM_BYTES_PER_LAUNCH_C3 if args.gangs == 100000 else None,
                      "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one full-size launch "
-                                       "(profiles/r1g_inlined_hot_chain.md); bytes per launch",
+                                       "(profiles/r2_final.md section 2); bytes per launch",
                      "algorithmic_bytes_per_launch": int(alg_bytes), "kernel": "hived_events_kernel",
                      "peak_source": peak_src,
                      "note": "latency-bound sequential contract: the state (~9 MB of cells) is L2/L1 resident, DRAM traffic is "
