@@ -218,10 +218,11 @@ def test_cuda_full_size_c4_against_oracle(cuda_lib):
     assert stats == golden["stats"]
 
 
-@pytest.mark.parametrize("seed", [16, 31, 3])
+@pytest.mark.parametrize("seed", [16, 31, 160, 553, 775, 3, 5, 8])
 def test_cuda_api_fuzz_seeds(cuda_lib, oracle_lib, seed):
     """API-level fuzz (tests/fuzz_api.py) on the GPU through the per-call path: results, every cell and every view order
-    after every call; 16 and 31 are the re-created-group seeds (ghost records)."""
+    after every call; 16 and 31 are the re-created-group seeds (ghost records), 160 / 553 nil dereferences of the
+    reference (platform errors on both sides), 775 a pod deleted through another pod's slot."""
     import fuzz_api
     assert fuzz_api.run_seed(cuda_lib, oracle_lib, seed, 300) is None
 
@@ -260,11 +261,13 @@ def test_c_driver_through_the_abi(cuda_lib, tmp_path):
     assert "test_cabi_gpu: ok" in out.stdout
 
 
-@pytest.mark.parametrize("world", [1, 2, 4, 8])
-def test_vc_partition_over_ranks_matches_single_gpu_run(cuda_lib, world):
+@pytest.mark.parametrize("world,window", [(1, 0), (2, 0), (4, 0), (8, 0), (2, 1024), (4, 256), (8, 1024)])
+def test_vc_partition_over_ranks_matches_single_gpu_run(cuda_lib, world, window):
     """the C3 cluster's 8 VCs partitioned over `world` ranks (here: `world` contexts on
     one GPU, the two collectives done by hand — the protocol of hivedscheduler_b200/dist.py without the process
-    group); the chain hash over the merged results equals the hash of the ordinary single-context run."""
+    group); the chain hash over the merged results equals the hash of the ordinary single-context run.  window > 0: the
+    horizon form (hived_mg_run_window), what dist.run_partitioned drives; several contexts of one process also take
+    turns on the device's constant bank (ensureDevLoaded)."""
     import torch
     from test_multigpu_partition import simulate
     t = trace.trace_c3(n_gangs=6000)
@@ -274,7 +277,7 @@ def test_vc_partition_over_ranks_matches_single_gpu_run(cuda_lib, world):
         b = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
         return b, b.data_ptr()
 
-    h, rounds = simulate(cuda_lib, t, world, alloc=alloc)
+    h, rounds = simulate(cuda_lib, t, world, alloc=alloc, window=window)
     assert h == h1
     assert rounds >= 8
 
