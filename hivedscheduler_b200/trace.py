@@ -534,8 +534,14 @@ def run_c4_compiled(lib, config, n_gangs: int, n_vcs: int, vc_gpus: int, total_g
     batch of <= 8 events.  Returns (hash, decision log in run_c4_interactive's format, stats, timing dict)."""
     import os
     if player_path is None:
-        player_path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "_build",
-                                   "libhived_c4player.so")
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        player_path = os.path.join(root, "tests", "_build", "libhived_c4player.so")
+        if not os.path.exists(player_path):  # (normally built by __graft_entry__.build())
+            import sys
+            if root not in sys.path:
+                sys.path.insert(0, root)
+            import __graft_entry__ as ge
+            ge.build_c4_player()
     player = C.CDLL(player_path)
     player.c4_play.restype = C.c_int
     bc = BatchContext(lib, config, max_groups or (n_gangs + 8), 8 * n_gangs + 64, 64, 8)
