@@ -227,6 +227,28 @@ def test_cuda_api_fuzz_seeds(cuda_lib, oracle_lib, seed):
     assert fuzz_api.run_seed(cuda_lib, oracle_lib, seed, 300) is None
 
 
+def test_contexts_of_several_threads_take_turns_on_one_device(cuda_lib, oracle_lib):
+    """Three host threads, each driving ITS OWN context through the per-call path (API fuzz vs the oracle, every cell
+    compared after every call): the contexts share the device's constant bank (one Dev loaded at a time,
+    hived_cuda.cu ensureDevLoaded) and each has a resident per-call kernel that the next owner must stop first."""
+    import threading
+    import fuzz_api
+    out = {}
+
+    def work(seed):
+        try:
+            out[seed] = fuzz_api.run_seed(cuda_lib, oracle_lib, seed, 150)
+        except BaseException as e:  # noqa
+            out[seed] = "exception: %r" % (e,)
+
+    threads = [threading.Thread(target=work, args=(s,)) for s in (21, 22, 23)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=600)
+    assert out == {21: None, 22: None, 23: None}
+
+
 def test_cuda_full_size_c4_compiled_player(cuda_lib):
     """The same full-size C4 run driven by compiled code (tests/harness/c4_player.cpp: no interpreter between the calls,
     a gang's pod deletions as one batch): same hash, log and counters as the oracle's committed run."""
