@@ -181,11 +181,36 @@ def other_configs(lib):
     mth = util.module_from_spec(spec); spec.loader.exec_module(mth)
     # the closed loop played by compiled code (tests/harness/c4_player.cpp): every call goes through hived_process_events
     h, log, st, tm = trace.run_c4_compiled(lib, **mth.c4_kwargs(100000))
+    c4_gpu = tm
     out["C4"] = {"gangs_per_s": 100000 / tm["seconds"], "seconds": tm["seconds"], "calls": tm["calls"], "events": tm["events"],
                  "us_per_call": 1e6 * tm["seconds"] / tm["calls"], "schedule_calls": int(st["schedule_events"]),
                  "harness": "compiled (c4_player.cpp), a gang's pod deletions as one batch",
                  "result_hash": "%016x" % h, "log_sha256_matches_oracle": mth.log_digest(log) == golden.get("C4", {}).get("log_sha256"),
                  "matches_oracle": "%016x" % h == golden.get("C4", {}).get("hash")}
+    # the honest comparator for these configurations too: the DEVICE PROGRAM compiled for the host (cpu_flat, one thread:
+    # C4 and C5 run on one CTA on the GPU as well; C2 on as many threads as CTAs), same calls, same hashes
+    try:
+        import __graft_entry__ as g
+        flat = _cabi.load_library(g.build_cpu_flat())
+        cf = {}
+        for name, t_, pw in (("C2", trace.trace_c2(), lambda t: 3 * 8 * len(t["events"]) + 4096),
+                             ("C5", trace.trace_c5(), lambda t: 3 * 64 * len(t["events"]) + 4096)):
+            if name == "C5":
+                os.environ["HIVED_NCTA"] = "1"
+            bc = trace.BatchContext(flat, t_["config"], t_["n_groups"], t_["n_pods"], t_["max_group_leaves"], t_["max_group_pods"])
+            bc.set_all_nodes_healthy()
+            t0 = time.perf_counter(); bc.process(t_["events"], pw(t_)); dt = time.perf_counter() - t0
+            os.environ.pop("HIVED_NCTA", None)
+            units = len(t_["events"]) if name == "C2" else int(t_["decision"].sum())
+            cf[name] = {"per_s": units / dt, "seconds": dt, "result_hash": "%016x" % bc.result_hash()}
+            bc.close()
+        h, log, st, tm = trace.run_c4_compiled(flat, **mth.c4_kwargs(100000))
+        cf["C4"] = {"per_s": 100000 / tm["seconds"], "seconds": tm["seconds"], "us_per_call": 1e6 * tm["seconds"] / tm["calls"],
+                    "result_hash": "%016x" % h}
+        out["cpu_flat"] = dict(cf, what="the device program compiled for the host (g++ -O2), same calls; C2 on one thread per "
+                                        "group of VCs, C4 / C5 on one thread (they run on one CTA on the GPU too)")
+    except Exception as e:  # noqa  (a comparator must not take the bench line down)
+        out["cpu_flat"] = {"unavailable": repr(e)}
     return out
 
 
