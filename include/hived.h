@@ -154,7 +154,9 @@ typedef struct hived_result {
   int32_t wait_code;   /* HIVED_WAIT_* | scope */
   int32_t wait_cell;   /* physical cell id named by the wait reason, or -1 */
   int32_t chain;       /* PodBindInfo.CellChain (chain id) */
-  int32_t pod_index;   /* index of this pod among those with the same leaf number */
+  int32_t pod_index;   /* SCHEDULE: index of this pod among those with the same leaf number;
+                          DELETE_ALLOCATED: the pod id that occupied the cleared slot, -1 = nothing cleared
+                          (see hived_delete_allocated_pod_ex) */
   int32_t node;        /* PodBindInfo.Node (node id) */
   int32_t this_off;    /* this pod's slice of the leaves (LeafCellIsolation = the leaf indices) */
   int32_t this_n;
