@@ -2577,18 +2577,20 @@ struct Core {
       int st = d.p_state[c];
       if (st == HIVED_CELL_USED || st == HIVED_CELL_RESERVING) {
         int g = d.p_using[c];
+        if (g < 0) { panic(HIVED_ERR_PLATFORM); return; }  // GetUsingGroup() == nil dereferenced in the reference (utils.go:217)
         bool seen = false;
         for (int j = 0; j < ng; j++) if (groups[j] == g) { seen = true; break; }
-        if (!seen && g >= 0) {
+        if (!seen) {
           if (ng >= d.S.maxLevelCount + MAX_FANOUT) { panic(HIVED_ERR_CAPACITY); return; }
           ST(groups[ng], g); ng++;
         }
       }
       if (st == HIVED_CELL_RESERVING || st == HIVED_CELL_RESERVED) {
-        int g = d.p_resv[c];
+        int g = d.p_resv[c];  // (-1 = nil: the reference adds it to the set all the same, utils.go:229, and dereferences
+                              // it when it cancels the overlapping preemptions in the Preempting phase)
         bool seen = false;
         for (int j = 0; j < nOverlap; j++) if (overlap[j] == g) { seen = true; break; }
-        if (!seen && g >= 0) {
+        if (!seen) {
           if (nOverlap >= d.S.LS) { panic(HIVED_ERR_CAPACITY); return; }
           ST(overlap[nOverlap], g); nOverlap++;
         }
@@ -3102,7 +3104,10 @@ struct Core {
         victimsCollected = true;
         if (panicCode) return panicCode;
         if (phase == HIVED_PHASE_PREEMPTING) {
-          for (int i = 0; i < nOverlap; i++) deletePreemptingAffinityGroup(s.lz_group[i]);
+          for (int i = 0; i < nOverlap; i++) {
+            if (s.lz_group[i] < 0) { panic(HIVED_ERR_PLATFORM); return panicCode; }  // nil *AlgoAffinityGroup dereferenced (:1116)
+            deletePreemptingAffinityGroup(s.lz_group[i]);
+          }
           if (lastVictims != 0) {
             if (!hasVirtual) { panic(HIVED_ERR_PLATFORM); return panicCode; }  // nil virtual placement indexed in the reference
             for (int i = 0; i < r.nleaves; i++) { ST(s.pl_p2[i], s.pl_p[i]); ST(s.pl_v2[i], s.pl_v[i]); }

@@ -821,6 +821,8 @@ static void collectPreemptionVictims(const Placement& placement, std::vector<std
         if (leafCell == nullptr) continue;
         int32_t state = leafCell->state;
         if (state == cellUsed || state == cellReserving) {
+          // pLeafCell.GetUsingGroup().allocatedPods (utils.go:217) on a nil group: a Go panic
+          if (leafCell->usingGroup == nullptr) throw Panic("runtime error: invalid memory address or nil pointer dereference (a used cell without a using group)");
           for (auto& pk : leafCell->usingGroup->allocatedPods)
             for (Pod* v : pk.second)
               if (v != nullptr && !seen.count(v)) {
@@ -839,8 +841,9 @@ static void collectPreemptionVictims(const Placement& placement, std::vector<std
   std::sort(victimPods.begin(), victimPods.end(),
             [](const std::pair<Pod*, int32_t>& a, const std::pair<Pod*, int32_t>& b) { return a.first->id < b.first->id; });
   // overlapping preemptors: the reference iterates a Go set; canonical order = group id
+  // (a nil entry — a Reserving / Reserved cell without a reserving group, utils.go:229 adds it all the same — sorts first)
   std::sort(overlappingPreemptorGroups.begin(), overlappingPreemptorGroups.end(),
-            [](Group* a, Group* b) { return a->id < b->id; });
+            [](Group* a, Group* b) { return (a ? a->id : -1) < (b ? b->id : -1); });
 }
 
 // utils.go:267-283
@@ -1759,7 +1762,11 @@ void HivedAlgorithm::schedulePodFromNewGroup(const PodSchedulingSpec& s,
   r.victims.clear();
   collectPreemptionVictims(r.physical, r.victims, overlappingPreemptors);
   if (preemptingPhase) {
-    for (Group* preemptor : overlappingPreemptors) deletePreemptingAffinityGroup(preemptor);
+    for (Group* preemptor : overlappingPreemptors) {
+      // deletePreemptingAffinityGroup(nil) reads g.physicalLeafCellPlacement (:1116): a Go panic
+      if (preemptor == nullptr) throw Panic("runtime error: invalid memory address or nil pointer dereference (cancelling the preemption of a nil group)");
+      deletePreemptingAffinityGroup(preemptor);
+    }
     if (!r.victims.empty()) createPreemptingAffinityGroup(s, r.physical, r.virtual_, podId);
   }
 }
