@@ -381,12 +381,18 @@ struct Core {
 
   // ---- free list of the physical cluster: order semantics of types.go:78-95 (swap-remove) and append.
   // (read everything, re-converge, then write: a lane must not see another lane's update of the length)
+  // The reference's list is a slice and nothing stops it from holding a cell twice (a preassigned cell released again
+  // while it is already free): p_flpos is the position of a cell's FIRST occurrence (what CellList.remove finds), fl_dup
+  // counts the later occurrences of a segment; while a segment has none the position table is exact and O(1).
   HIVED_DEV void fl_append(int chain, int level, int cell) {
     int k = cl(chain, level);
     int n = d.fl_len[k];
+    if (n >= d.fl_cap[k]) { panic(HIVED_ERR_CAPACITY); return; }  // more duplicates than FL_DUP_SLACK (hived_topo.hpp)
+    const int first = d.p_flpos[cell];
+    const int dups = d.fl_dup[k];
     hv_warp_sync();
     ST(d.fl_data[d.fl_base[k] + n], cell);
-    ST(d.p_flpos[cell], n);
+    if (first < 0) ST(d.p_flpos[cell], n); else ST(d.fl_dup[k], dups + 1);
     ST(d.fl_len[k], n + 1);
   }
   HIVED_DEV void fl_remove(int chain, int level, int cell) {
@@ -395,11 +401,25 @@ struct Core {
     if (pos < 0) { panic(HIVED_ERR_PLATFORM); return; }  // "Cell not not found in list when removing"
     int n = d.fl_len[k];
     int last = d.fl_data[d.fl_base[k] + n - 1];
+    const int dups = d.fl_dup[k];
     hv_warp_sync();
     ST(d.fl_data[d.fl_base[k] + pos], last);
-    ST(d.p_flpos[last], pos);
-    ST(d.p_flpos[cell], -1);
     ST(d.fl_len[k], n - 1);
+    if (dups == 0) {
+      ST(d.p_flpos[last], pos);
+      ST(d.p_flpos[cell], -1);
+      return;
+    }
+    // the segment holds duplicates: first occurrences and their number again, in list order (uniform, short lists)
+    int32_t* a = d.fl_data + d.fl_base[k];
+    ST(d.p_flpos[cell], -1);
+    for (int i = 0; i < n - 1; i++) ST(d.p_flpos[a[i]], -1);
+    int nd = 0;
+    for (int i = 0; i < n - 1; i++) {
+      const int c = a[i];
+      if (d.p_flpos[c] < 0) ST(d.p_flpos[c], i); else nd++;
+    }
+    ST(d.fl_dup[k], nd);
   }
   HIVED_DEV bool fl_contains(int cell) const { return d.p_flpos[cell] >= 0; }
   // ---- bad free cells (badFreeCells, hived_algorithm.go:78)
@@ -1825,6 +1845,7 @@ struct Core {
         int32_t* lower = sfl(level - 1);
         const int nl = s.sfl_len[level - 1];
         const int nc = d.p_nchild[c], c0 = d.p_child0[c];
+        if (nl + nc > d.fl_cap[cl(sflChain, level - 1)]) { panic(HIVED_ERR_CAPACITY); return false; }  // (duplicates: see fl_append)
         for (int j = lane; j < nc; j += HIVED_WARPSZ) lower[nl + j] = c0 + j;
         hv_warp_sync();
         ST(s.sfl_len[level - 1], nl + nc);
@@ -1875,6 +1896,7 @@ struct Core {
         // freeList[currentLevel] = append(splitList, freeList[currentLevel]...)
         int32_t* cur = sfl(currentLevel);
         int nc = s.sfl_len[currentLevel];
+        if (nc + ns > d.fl_cap[cl(sflChain, currentLevel)]) { panic(HIVED_ERR_CAPACITY); return false; }  // (duplicates: see fl_append)
         for (int i = nc - 1; i >= 0; i--) { int v = cur[i]; hv_warp_sync(); ST(cur[i + ns], v); }
         for (int i = 0; i < ns; i++) ST(cur[i], split[i]);
         ST(s.sfl_len[currentLevel], nc + ns);

@@ -56,7 +56,7 @@ struct GroupMemFld {  // indexed by g * 8 + m like the flat arrays it replaces
   Y(v_prio, S.NV, -2) Y(v_state, S.NV, 0) Y(v_healthy, S.NV, 1) Y(v_pcell, S.NV, -1)                   \
   Y(vcFree, S.nVCs * S.nChains * MAXL, 0) Y(allVCFree, S.nChains * MAXL, 0)                            \
   Y(totalLeft, S.nChains * MAXL, 0) Y(allVCDoomed, S.nChains * MAXL, 0)                                \
-  Y(fl_data, S.flTotal, -1) Y(fl_len, S.nChains * MAXL, 0) Y(bf_data, S.flTotal, -1)                   \
+  Y(fl_data, S.flTotal, -1) Y(fl_len, S.nChains * MAXL, 0) Y(fl_dup, S.nChains * MAXL, 0) Y(bf_data, S.flTotal, -1)                   \
   Y(bf_len, S.nChains * MAXL, 0) Y(dm_data, S.dmTotal, -1) Y(dm_len, S.nVCs * S.nChains * MAXL, 0)     \
   Y(cv, S.cvTotal, -1) Y(node_bad, S.nNodes, 0)                                                        \
   Y(g_hdr, (int64_t)(S.maxGroups + GHOST_GROUPS) * GROUP_HDR_WORDS, 0)                                                  \

@@ -438,7 +438,7 @@ struct Engine {
     v.push_back({dev.p_dmpos, NP}); v.push_back({dev.p_dmvc, NP});
     v.push_back({dev.vcFree, LV * dev.S.nVCs}); v.push_back({dev.allVCFree, LV}); v.push_back({dev.totalLeft, LV});
     v.push_back({dev.allVCDoomed, LV});
-    v.push_back({dev.fl_data, (size_t)dev.S.flTotal * 4}); v.push_back({dev.fl_len, LV});
+    v.push_back({dev.fl_data, (size_t)dev.S.flTotal * 4}); v.push_back({dev.fl_len, LV}); v.push_back({dev.fl_dup, LV});
     v.push_back({dev.bf_data, (size_t)dev.S.flTotal * 4}); v.push_back({dev.bf_len, LV});
     v.push_back({dev.dm_data, (size_t)dev.S.dmTotal * 4}); v.push_back({dev.dm_len, LV * dev.S.nVCs});
     return v;

@@ -25,6 +25,7 @@ namespace hived {
 constexpr int MAXL = 16;            // levels per chain are 1..MAXL-1
 constexpr int MAX_NODE_LEAVES = 64; // leaves below one cluster-view node
 constexpr int MAX_FANOUT = 64;      // children per cell
+constexpr int FL_DUP_SLACK = 16;    // duplicate entries a free-list segment can hold (see fl_cap)
 
 struct TopoError : std::runtime_error {
   int code;
@@ -479,9 +480,13 @@ inline FlatTopo buildTopo(const std::string& text) {
   for (int32_t c = 0; c < T.nChains; c++) {
     int32_t chainTotal = 0;
     for (int32_t l = 1; l < MAXL; l++) {
-      T.fl_base[c * MAXL + l] = T.flTotal; T.fl_cap[c * MAXL + l] = T.p_lvl_cnt[c * MAXL + l];
-      T.flTotal += T.p_lvl_cnt[c * MAXL + l]; chainTotal += T.p_lvl_cnt[c * MAXL + l];
-      if (T.p_lvl_cnt[c * MAXL + l] > T.maxLevelCount) T.maxLevelCount = T.p_lvl_cnt[c * MAXL + l];
+      // the reference's free list is a slice: releasing a preassigned cell that is already free appends it AGAIN
+      // (addCellToFreeList, hived_algorithm.go:1530-1565 — reachable once Filtering-phase binds have made its counters
+      // drift), so a segment has room for FL_DUP_SLACK duplicates beyond the cells of its level (hived_core.h fl_append)
+      const int32_t cap = T.p_lvl_cnt[c * MAXL + l] > 0 ? T.p_lvl_cnt[c * MAXL + l] + FL_DUP_SLACK : 0;
+      T.fl_base[c * MAXL + l] = T.flTotal; T.fl_cap[c * MAXL + l] = cap;
+      T.flTotal += cap; chainTotal += cap;
+      if (cap > T.maxLevelCount) T.maxLevelCount = cap;
     }
     if (chainTotal > T.maxChainFree) T.maxChainFree = chainTotal;
   }

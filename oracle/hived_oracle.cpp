@@ -541,8 +541,12 @@ void HivedAlgorithm::parseConfig(const std::string& specText) {
 HivedAlgorithm::HivedAlgorithm(const std::string& specText) { parseConfig(specText); }
 
 HivedAlgorithm::~HivedAlgorithm() {
-  for (auto& kv : affinityGroups) delete kv.second;
-  for (Group* g : deletedGroups) delete g;
+  // a group reached through a stale cell pointer can be deleted a second time by the reference's own flow (Go's GC does
+  // not care; Filtering-phase fuzz seed 1059): every group object is freed once
+  std::unordered_set<Group*> owned;
+  for (auto& kv : affinityGroups) owned.insert(kv.second);
+  for (Group* g : deletedGroups) owned.insert(g);
+  for (Group* g : owned) delete g;
   for (auto& kv : pods) delete kv.second;
 }
 

@@ -203,12 +203,15 @@ def test_api_fuzz_seeds_with_recreated_group(emu_lib, oracle_lib, seed):
     assert fuzz_api.run_seed(emu_lib, oracle_lib, seed, 300) is None
 
 
-@pytest.mark.parametrize("seed", [7, 12, 29])
+@pytest.mark.parametrize("seed", [7, 12, 29, 782, 1059])
 def test_api_fuzz_with_filtering_phase_calls(emu_lib, oracle_lib, seed, monkeypatch):
     """The same fuzz with 40 % of the Schedule calls in the Filtering phase (FUZZ_FILTERING=1): binds that land on
     Reserved cells make the reference's incremental used-leaf counters drift from its leaf priorities (modelled exactly:
     noteDelta), and seed 7 reaches a Reserved cell without a reserving group — the reference dereferences the nil
-    group when it cancels the overlapping preemptions (hived_algorithm.go:1116): a platform error on both sides."""
+    group when it cancels the overlapping preemptions (hived_algorithm.go:1116): a platform error on both sides.
+    Seed 782 releases a preassigned cell that is already free, again and again: the reference's free list (a slice)
+    holds the cell 16 times (hived_core.h fl_append: first-occurrence positions + a duplicate count per segment, bounded
+    by FL_DUP_SLACK); seed 1059 deletes a group twice through a stale cell pointer."""
     import fuzz_api
     monkeypatch.setenv("FUZZ_FILTERING", "1")
     assert fuzz_api.run_seed(emu_lib, oracle_lib, seed, 300) is None
