@@ -227,6 +227,16 @@ def test_cuda_api_fuzz_seeds(cuda_lib, oracle_lib, seed):
     assert fuzz_api.run_seed(cuda_lib, oracle_lib, seed, 300) is None
 
 
+@pytest.mark.parametrize("seed", [7, 782, 1059])
+def test_cuda_api_fuzz_with_filtering_phase_calls(cuda_lib, oracle_lib, seed, monkeypatch):
+    """The Filtering-phase form of the fuzz on the GPU: 7 = a Reserved cell without a reserving group (platform error on
+    both sides), 782 = a free-list segment holding one cell 16 times (hived_core.h fl_append), 1059 = a group deleted
+    twice through a stale cell pointer."""
+    import fuzz_api
+    monkeypatch.setenv("FUZZ_FILTERING", "1")
+    assert fuzz_api.run_seed(cuda_lib, oracle_lib, seed, 300) is None
+
+
 def test_contexts_of_several_threads_take_turns_on_one_device(cuda_lib, oracle_lib):
     """Three host threads, each driving ITS OWN context through the per-call path (API fuzz vs the oracle, every cell
     compared after every call): the contexts share the device's constant bank (one Dev loaded at a time,
