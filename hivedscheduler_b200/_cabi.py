@@ -55,7 +55,7 @@ class Event(C.Structure):
 
 class GroupInfo(C.Structure):
     _fields_ = [("state", C.c_int32), ("vc", C.c_int32), ("priority", C.c_int32), ("has_virtual", C.c_int32),
-                ("n_preempting_pods", C.c_int32), ("reserved", C.c_int32 * 3)]
+                ("n_preempting_pods", C.c_int32), ("referenced", C.c_int32), ("reserved", C.c_int32 * 2)]
 
 
 class GroupPlacement(C.Structure):

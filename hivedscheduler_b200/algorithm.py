@@ -497,7 +497,7 @@ class HivedAlgorithm:
         """The id of a group that no longer exists goes back to the interner (include/hived.h "Id lifetime")."""
         gi = _cabi.GroupInfo()
         self._lib.hived_get_group(self._ctx, gid, C.byref(gi))
-        if gi.state == _cabi.GROUP_NONE:
+        if gi.state == _cabi.GROUP_NONE and not gi.referenced:
             self._groups.release(name)
 
     def AddAllocatedPod(self, pod: Pod) -> None:  # hived_algorithm.go:247-270

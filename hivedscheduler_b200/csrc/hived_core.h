@@ -2034,6 +2034,15 @@ struct Core {
     return n;
   }
   HIVED_DEV void eraseGroup(int g) { ST(d.g_state[g], HIVED_GROUP_NONE); }
+  // delete(h.affinityGroups, g.name) for an object reached through a cell (cell.reservingOrReservedGroup): when the
+  // object is a ghost, whichever group carries its name NOW leaves the map as well — and lives on as a ghost itself
+  // while its own leaves name it (the shims keep name <-> id while a ghost of the id exists: hived.h "Id lifetime")
+  HIVED_DEV void eraseGroupByName(int g) {
+    if (g < d.S.maxGroups) { eraseGroup(g); return; }
+    const int origin = d.g_hdr[(int64_t)g * GROUP_HDR_WORDS + GH_ORIGIN] - 1;
+    eraseGroup(g);
+    if (origin >= 0 && d.g_state[origin] != HIVED_GROUP_NONE) { ghostify(origin); eraseGroup(origin); }
+  }
   // Object identity of an erased group.  The reference's cells point at *AlgoAffinityGroup objects (cell.usingGroup,
   // cell.reservingOrReservedGroup), its name map at whichever object carries the name now.  One path erases a group
   // from the map while its own leaves keep naming it: schedulePodFromExistingGroup treats every state but Allocated as
@@ -2057,7 +2066,11 @@ struct Core {
     if (gg < 0) { panic(HIVED_ERR_CAPACITY); return; }
     const int nl = groupLeaves(g), np = groupPods(g), npre = d.g_npre[g];
     hv_phase();
-    for (int w = lane; w < GROUP_HDR_WORDS; w += HIVED_WARPSZ) d.g_hdr[(int64_t)gg * GROUP_HDR_WORDS + w] = d.g_hdr[(int64_t)g * GROUP_HDR_WORDS + w];
+    // the name travels with the object: a ghost of a ghost keeps the first id
+    const int origin = g >= d.S.maxGroups ? d.g_hdr[(int64_t)g * GROUP_HDR_WORDS + GH_ORIGIN] : g + 1;
+    for (int w = lane; w < GROUP_HDR_WORDS; w += HIVED_WARPSZ)
+      d.g_hdr[(int64_t)gg * GROUP_HDR_WORDS + w] = w == GH_ORIGIN ? origin : d.g_hdr[(int64_t)g * GROUP_HDR_WORDS + w];
+    if (lane == 0 && origin > 0) d.g_hdr[(int64_t)(origin - 1) * GROUP_HDR_WORDS + GH_LINK] = gg + 1;
     for (int i = lane; i < nl; i += HIVED_WARPSZ) { gphys(gg)[i] = gphys(g)[i]; gvirt(gg)[i] = gvirt(g)[i]; }
     for (int i = lane; i < np; i += HIVED_WARPSZ) gpods(gg)[i] = gpods(g)[i];
     for (int i = lane; i < npre; i += HIVED_WARPSZ) gpre(gg)[i] = gpre(g)[i];
@@ -2258,6 +2271,11 @@ struct Core {
         setCellState(pLeaf, HIVED_CELL_RESERVED, ceil);
       }
     }
+    // A group that is itself PREEMPTING can be deleted here (DeleteAllocatedPod of a pod bound under an earlier
+    // incarnation of the name, hived_algorithm.go:272-296): its Reserved leaves keep naming the erased object
+    // (cell.reservingOrReservedGroup), and a later preemptor / allocation on them cancels "its" preemption
+    // (:731-742, :1001-1010) — the old object, not whoever carries the id by then (API fuzz seed 2385).
+    ghostify(g);
     eraseGroup(g);
   }
   // utils.go:267-283
@@ -2284,7 +2302,7 @@ struct Core {
       }
     }
     ghostify(g);  // (only a group that was not Preempting can still be named by its leaves here)
-    eraseGroup(g);
+    eraseGroupByName(g);
   }
   // hived_algorithm.go:1147-1163
   HIVED_DEV_NOINLINE void allocatePreemptingAffinityGroup(int g) {

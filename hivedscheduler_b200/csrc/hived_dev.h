@@ -15,11 +15,14 @@ namespace hived {
 
 // An affinity group's scalars live in ONE 128-byte record (a decision touches a group it has not seen for
 // a while: one L2 round trip instead of eight).  Word layout: 0 state, 1 vc, 2 priority, 3 flags,
-// 4 #members, 5 #preempting pods, 8..15 member leaf numbers, 16..23 member pod numbers.
+// 4 #members, 5 #preempting pods, 8..15 member leaf numbers, 16..23 member pod numbers, 24..27 the lean lane's unit
+// decomposition, 28 (ghost records) the id the ghost came from + 1, 29 (live records; survives re-creation) the ghost
+// slot + 1 that last took this id's object over.
 constexpr int GROUP_HDR_WORDS = 32;
 // Records [maxGroups, maxGroups + GHOST_GROUPS) of the group tables hold GHOSTS: a group that the reference erases from
 // its name map while cells still point at the object (cell.usingGroup), see Core::ghostify.  Never visible by id.
 constexpr int GHOST_GROUPS = 64;
+constexpr int GH_ORIGIN = 28, GH_LINK = 29;
 constexpr int DELTA_SLOTS = 4;          // (priority, difference) pairs per cell, see noteDelta
 constexpr int DELTA_EMPTY = -1000000;
 constexpr int BK_STRIDE = 33;  // buckets of a bucketed cluster view: used-leaf counts 0..32

@@ -768,7 +768,16 @@ int hived_get_group(hived_ctx* ctx, int32_t group, hived_group_info_t* out) {
   int32_t hdr[hived::GROUP_HDR_WORDS];
   hived::bk_d2h(hdr, e.dev.g_hdr + (size_t)group * hived::GROUP_HDR_WORDS, sizeof hdr);
   int32_t v[5] = {hdr[0], hdr[1], hdr[2], hdr[3], hdr[5]};
-  if (v[0] == HIVED_GROUP_NONE) return 0;
+  if (v[0] == HIVED_GROUP_NONE) {
+    // an erased object of this id that cells may still name (Core::ghostify): the shims keep the id (hived.h "Id lifetime")
+    const int32_t slot = hdr[hived::GH_LINK] - 1;
+    if (slot >= e.dev.S.maxGroups && slot < e.dev.S.maxGroups + hived::GHOST_GROUPS) {
+      int32_t gh[hived::GROUP_HDR_WORDS];
+      hived::bk_d2h(gh, e.dev.g_hdr + (size_t)slot * hived::GROUP_HDR_WORDS, sizeof gh);
+      if (gh[0] != HIVED_GROUP_NONE && gh[hived::GH_ORIGIN] == group + 1) out->referenced = 1;
+    }
+    return 0;
+  }
   out->state = v[0]; out->vc = v[1]; out->priority = v[2];
   out->has_virtual = (v[3] & hived::GF_HAS_VIRTUAL) ? 1 : 0;
   out->n_preempting_pods = v[0] == HIVED_GROUP_PREEMPTING ? v[4] : 0;

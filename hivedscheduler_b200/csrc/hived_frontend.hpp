@@ -80,7 +80,7 @@ struct hived_fe {
       groupRefs.erase(it);
       hived_group_info_t gi{};
       // the id goes back to the pool once the algorithm has forgotten the group (hived.h "Id lifetime")
-      if (p.spec.group >= 0 && (hived_get_group(ctx, p.spec.group, &gi) != 0 || gi.state == HIVED_GROUP_NONE))
+      if (p.spec.group >= 0 && (hived_get_group(ctx, p.spec.group, &gi) != 0 || (gi.state == HIVED_GROUP_NONE && !gi.referenced)))
         hived_ingest_release(ing, 0, p.group.data(), (int32_t)p.group.size());
     }
   }

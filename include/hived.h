@@ -33,8 +33,10 @@
  *   - virtual cell ids: for VC in id order: non-pinned chains in id order then pinned cells in id
  *     order; inside each: level 1..top, construction order (config.go:282-317).
  *   Group ids and pod ids are interned by the caller (dense, < the capacities in hived_options_t).
- *   Id lifetime: a group id may be handed to another group once hived_get_group reports HIVED_GROUP_NONE for it (after
- *   the DeleteAllocatedPod / DeleteUnallocatedPod that removed its last pod), a pod id once the pod has been deleted
+ *   Id lifetime: a group id may be handed to another group once hived_get_group reports HIVED_GROUP_NONE for it AND
+ *   `referenced` == 0 (after the DeleteAllocatedPod / DeleteUnallocatedPod that removed its last pod; `referenced` = cells
+ *   still point at the erased object, which the reference can reach and erase BY NAME later: the name keeps its id until
+ *   then, so that a re-created group of that name is the one that is hit — and no other), a pod id once the pod has been deleted
  *   AND hived_delete_allocated_pod_ex reported it as the removed occupant (see there);
  *   the shims recycle them that way (hivedscheduler_b200/algorithm.py, integration/pkg/algorithm/cuda_backend.go), so a
  *   long-running scheduler never meets HIVED_ERR_CAPACITY.  Batch callers (hived_process_events) number the gangs of
@@ -219,7 +221,8 @@ typedef struct hived_group_info {
   int32_t priority;
   int32_t has_virtual;  /* 0 after lazy preemption (virtualLeafCellPlacement == nil) */
   int32_t n_preempting_pods;
-  int32_t reserved[3];
+  int32_t referenced;   /* state == NONE only: 1 = an erased object of this id is still named by cells (keep the id) */
+  int32_t reserved[2];
 } hived_group_info_t;
 
 typedef struct hived_cell_status {

@@ -630,7 +630,8 @@ func (h *CudaHivedAlgorithm) releasePod(pod *core.Pod, pid C.int32_t) {
 func (h *CudaHivedAlgorithm) releaseGroupIfGone(name string, gid C.int32_t) {
 	var gi C.hived_group_info_t
 	C.hived_get_group(h.ctx, gid, &gi)
-	if gi.state == C.HIVED_GROUP_NONE {
+	// (referenced: cells still point at the erased object, which can be erased by name later — the name keeps its id)
+	if gi.state == C.HIVED_GROUP_NONE && gi.referenced == 0 {
 		h.groups.release(name)
 		delete(h.lazyInfo, name)
 	}

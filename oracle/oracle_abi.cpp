@@ -383,7 +383,16 @@ int hived_process_events(hived_ctx* ctx, const hived_event_t* events, int32_t n,
 int hived_get_group(hived_ctx* ctx, int32_t group, hived_group_info_t* out) {
   memset(out, 0, sizeof(*out));
   auto it = ctx->h->affinityGroups.find(groupName(group));
-  if (it == ctx->h->affinityGroups.end()) return 0;
+  if (it == ctx->h->affinityGroups.end()) {
+    // an erased object of this name that a cell still points at (the reference can erase it BY NAME later)
+    const std::string name = groupName(group);
+    for (Cell* c : ctx->h->physicalCells)
+      if ((c->usingGroup && c->usingGroup->name == name) || (c->reservingOrReservedGroup && c->reservingOrReservedGroup->name == name)) {
+        out->referenced = 1;
+        break;
+      }
+    return 0;
+  }
   Group* g = it->second;
   out->state = g->state;
   out->vc = -1;

@@ -191,14 +191,18 @@ def test_compiled_c4_player_equals_python_harness(emu_lib):
         assert (tm["calls"] < tm["events"]) == batch
 
 
-@pytest.mark.parametrize("seed", [16, 31, 160, 553, 775])
+@pytest.mark.parametrize("seed", [16, 31, 160, 553, 775, 2385])
 def test_api_fuzz_seeds_with_recreated_group(emu_lib, oracle_lib, seed):
     """tests/fuzz_api.py: random calls of the 14-method API, results + every cell + every view order compared after every
     call.  Seeds 16 and 31 erase a group that is being preempted while its leaves still name it and create a new group
     under the same name (hived_algorithm.go:671-707 -> :1114-1145): the old object lives on as a ghost record
     (Core::ghostify) — the victims of a later preemption are ITS pods.  160 / 553: nil dereferences of the reference
     (allocatePreassignedCell of a nil cell, lazy preemption of an unbound virtual leaf) are platform errors on both
-    sides.  775: a pod deleted through a slot that holds ANOTHER pod stays a possible victim (the shim keeps it)."""
+    sides.  775: a pod deleted through a slot that holds ANOTHER pod stays a possible victim (the shim keeps it).
+    2385: DeleteAllocatedPod of a pod bound under an earlier incarnation of a name deletes the PREEMPTING group that
+    carries the name now; its Reserved leaves keep naming the erased object, and a later Schedule that overlaps them
+    cancels "its" preemption (hived_algorithm.go:731-742): a ghost reached through p_resv, erased by name
+    (Core::eraseGroupByName); the shim keeps the id with the name while hived_get_group reports `referenced`."""
     import fuzz_api
     assert fuzz_api.run_seed(emu_lib, oracle_lib, seed, 300) is None
 
