@@ -1198,51 +1198,6 @@ struct Core {
     // free, same, higher: 9 bits each, biased by 128 (the reference's counters may be negative or exceed the leaf count)
     return ((free + 128) & 511) | (((same + 128) & 511) << 9) | (((higher + 128) & 511) << 18) | (healthy << 27) | (suggested << 28);
   }
-  // The same for VB nodes at once (non-anomalous views): every stage loads for all of them before anything is used, so
-  // a thread has VB independent chains of dependent loads in flight instead of one (the pass is latency-bound: 8 192
-  // nodes over 480 threads used to be 17 serial chains of 3 L2 round trips per thread).  cell[u] < 0 = no node.
-  static constexpr int VB = 4;
-  HIVED_DEV void viewNodeInfoBatch(const int (&cell)[VB], bool isVirtual, bool cross, int p, bool ignoreSuggested, int (&info)[VB]) const {
-    int leaf0[VB], nleaf[VB], hc[VB];  // hc: the physical cell whose health / node count (-1: none, healthy and suggested)
-    const int32_t* prio = isVirtual ? d.v_prio : d.p_prio;
-#pragma unroll
-    for (int u = 0; u < VB; u++) {
-      leaf0[u] = 0; nleaf[u] = 0; hc[u] = -1;
-      if (cell[u] < 0) continue;
-      if (isVirtual) { leaf0[u] = d.v_leaf0[cell[u]]; nleaf[u] = d.v_nleaf[cell[u]]; hc[u] = d.v_pcell[cell[u]]; }
-      else { leaf0[u] = d.p_leaf0[cell[u]]; nleaf[u] = d.p_nleaf[cell[u]]; hc[u] = cell[u]; }
-    }
-    int healthy[VB], node[VB];
-#pragma unroll
-    for (int u = 0; u < VB; u++) {
-      healthy[u] = 1; node[u] = -2;
-      if (hc[u] >= 0) { healthy[u] = d.p_healthy[hc[u]]; node[u] = d.p_node[hc[u]]; }
-    }
-    int suggested[VB];
-#pragma unroll
-    for (int u = 0; u < VB; u++) suggested[u] = (hc[u] < 0 || ignoreSuggested || node_suggested(node[u])) ? 1 : 0;
-    int same[VB], higher[VB], ge[VB], maxn = 0;
-#pragma unroll
-    for (int u = 0; u < VB; u++) { same[u] = higher[u] = ge[u] = 0; if (nleaf[u] > maxn) maxn = nleaf[u]; }
-    for (int j = 0; j < maxn; j++) {
-      int q[VB];
-#pragma unroll
-      for (int u = 0; u < VB; u++) q[u] = j < nleaf[u] ? prio[leaf0[u] + j] : OPP_PRIO - 1;
-#pragma unroll
-      for (int u = 0; u < VB; u++) {
-        if (q[u] < OPP_PRIO) continue;  // free leaf
-        if (q[u] == p) same[u]++;
-        else if (cross) same[u]++;
-        else if (q[u] > p) higher[u]++;
-        if (q[u] >= p) ge[u]++;
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < VB; u++) {
-      const int free = nleaf[u] - ge[u];
-      info[u] = ((free + 128) & 511) | (((same[u] + 128) & 511) << 9) | (((higher[u] + 128) & 511) << 18) | (healthy[u] << 27) | (suggested[u] << 28);
-    }
-  }
   HIVED_DEV static int infoFree(int w) { return (w & 511) - 128; }
   HIVED_DEV static int infoSame(int w) { return ((w >> 9) & 511) - 128; }
   HIVED_DEV static int infoHigher(int w) { return ((w >> 18) & 511) - 128; }
@@ -1299,50 +1254,28 @@ struct Core {
     int chunk = (n + W - 1) / W;
     chunk = (chunk + HIVED_WARPSZ - 1) / HIVED_WARPSZ * HIVED_WARPSZ;
     int lo = w * chunk, hi = lo + chunk < n ? lo + chunk : n;
-    // VB rows of 32 per trip: the rows' loads (index, info word, cell) are all issued before the first row is ranked —
-    // the rows themselves are still ranked one after the other, in order (the counters carry the order)
-    for (int base = lo; base < hi; base += HIVED_WARPSZ * VB) {
-      int b[VB];
-#pragma unroll
-      for (int u = 0; u < VB; u++) { const int i = base + u * HIVED_WARPSZ + lane; b[u] = i < hi ? in[i] : -1; }
-#pragma unroll
-      for (int u = 0; u < VB; u++) b[u] = b[u] >= 0 ? binOf(s.vw_info[b[u]]) : -1 - lane;  // inactive lanes get unique dummies
-#pragma unroll
-      for (int u = 0; u < VB; u++) {
-        if (base + u * HIVED_WARPSZ >= hi) break;
-        const int i = base + u * HIVED_WARPSZ + lane;
-        unsigned peers = hv_match(b[u]);
-        if (i < hi && (peers & hv_lanemask_lt()) == 0) smp()->cnt[b[u] * W + w] += hv_popc(peers);
-        hv_warp_sync();
-      }
+    for (int base = lo; base < hi; base += HIVED_WARPSZ) {
+      int i = base + lane;
+      int b = i < hi ? binOf(s.vw_info[in[i]]) : -1 - lane;  // inactive lanes get unique dummies
+      unsigned peers = hv_match(b);
+      if (i < hi && (peers & hv_lanemask_lt()) == 0) smp()->cnt[b * W + w] += hv_popc(peers);
+      hv_warp_sync();
     }
     hv_cta_sync();
     ctaExclusiveScan(nbins * W);
-    for (int base = lo; base < hi; base += HIVED_WARPSZ * VB) {
-      int src[VB], inf[VB], cellOf[VB], b[VB];
-#pragma unroll
-      for (int u = 0; u < VB; u++) { const int i = base + u * HIVED_WARPSZ + lane; src[u] = i < hi ? in[i] : -1; }
-#pragma unroll
-      for (int u = 0; u < VB; u++) {
-        inf[u] = src[u] >= 0 ? s.vw_info[src[u]] : 0;
-        cellOf[u] = (cvOut && src[u] >= 0) ? s.vw_cell[src[u]] : -1;
+    for (int base = lo; base < hi; base += HIVED_WARPSZ) {
+      int i = base + lane;
+      int b = i < hi ? binOf(s.vw_info[in[i]]) : -1 - lane;
+      unsigned peers = hv_match(b);
+      if (i < hi) {
+        int rank = smp()->cnt[b * W + w] + hv_popc(peers & hv_lanemask_lt());
+        int src = in[i];
+        out[rank] = src;
+        if (cvOut) { cvOut[rank] = s.vw_cell[src]; s.vw_sinfo[rank] = s.vw_info[src]; }
       }
-#pragma unroll
-      for (int u = 0; u < VB; u++) b[u] = src[u] >= 0 ? binOf(inf[u]) : -1 - lane;
-#pragma unroll
-      for (int u = 0; u < VB; u++) {
-        if (base + u * HIVED_WARPSZ >= hi) break;
-        const int i = base + u * HIVED_WARPSZ + lane;
-        unsigned peers = hv_match(b[u]);
-        if (i < hi) {
-          int rank = smp()->cnt[b[u] * W + w] + hv_popc(peers & hv_lanemask_lt());
-          out[rank] = src[u];
-          if (cvOut) { cvOut[rank] = cellOf[u]; s.vw_sinfo[rank] = inf[u]; }
-        }
-        hv_warp_sync();
-        if (i < hi && (peers & hv_lanemask_lt()) == 0) smp()->cnt[b[u] * W + w] += hv_popc(peers);
-        hv_warp_sync();
-      }
+      hv_warp_sync();
+      if (i < hi && (peers & hv_lanemask_lt()) == 0) smp()->cnt[b * W + w] += hv_popc(peers);
+      hv_warp_sync();
     }
     hv_cta_sync();
   }
@@ -1361,25 +1294,11 @@ struct Core {
     const bool anomalous = d.s_anom[sched] != 0;
     const int firstBins = cross ? 4 * (L + 1) : L + 1;
     for (int i = tid; i < firstBins * W; i += nth) smp()->cnt[i] = 0;
-    if (anomalous) {
-      for (int i = tid; i < n; i += nth) {
-        int cell = d.cv[off + i];
-        s.vw_cell[i] = cell;
-        s.vw_info[i] = viewNodeInfo(cell, isVirtual, cross, p, ignoreSuggested, anomalous);
-        s.vw_ordA[i] = i;
-      }
-    } else {
-      for (int i0 = tid; i0 < n; i0 += nth * VB) {
-        int cell[VB], info[VB];
-#pragma unroll
-        for (int u = 0; u < VB; u++) { const int i = i0 + u * nth; cell[u] = i < n ? d.cv[off + i] : -1; }
-        viewNodeInfoBatch(cell, isVirtual, cross, p, ignoreSuggested, info);
-#pragma unroll
-        for (int u = 0; u < VB; u++) {
-          const int i = i0 + u * nth;
-          if (i < n) { s.vw_cell[i] = cell[u]; s.vw_info[i] = info[u]; s.vw_ordA[i] = i; }
-        }
-      }
+    for (int i = tid; i < n; i += nth) {
+      int cell = d.cv[off + i];
+      s.vw_cell[i] = cell;
+      s.vw_info[i] = viewNodeInfo(cell, isVirtual, cross, p, ignoreSuggested, anomalous);
+      s.vw_ordA[i] = i;
     }
     hv_cta_sync();
     // 2. stable sort by (healthy desc, suggested desc, usedSame desc, usedHigher asc): LSD passes.  The last pass also
