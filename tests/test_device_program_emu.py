@@ -219,3 +219,30 @@ def test_api_fuzz_with_filtering_phase_calls(emu_lib, oracle_lib, seed, monkeypa
     import fuzz_api
     monkeypatch.setenv("FUZZ_FILTERING", "1")
     assert fuzz_api.run_seed(emu_lib, oracle_lib, seed, 300) is None
+
+
+def test_group_id_stays_with_its_name_while_an_erased_object_is_referenced(emu_lib, oracle_lib, monkeypatch):
+    """include/hived.h "Id lifetime": in API-fuzz seed 2385 a PREEMPTING group is deleted by DeleteAllocatedPod while its
+    Reserved leaves keep naming it — hived_get_group then reports NONE with `referenced` = 1 on both implementations, the
+    mirror keeps name <-> id (no other group can be handed that id), and the run stays divergence-free."""
+    import ctypes as C
+    import fuzz_api
+    from hivedscheduler_b200 import _cabi
+    from hivedscheduler_b200 import algorithm as alg
+    seen = {"emu": [], "oracle": []}
+    orig = alg.HivedAlgorithm._release_group_if_gone
+
+    def spy(self, name, gid):
+        gi = _cabi.GroupInfo()
+        self._lib.hived_get_group(self._ctx, gid, C.byref(gi))
+        side = "emu" if self._lib is emu_lib else "oracle"
+        if gi.state == _cabi.GROUP_NONE and gi.referenced:
+            seen[side].append((name, gid))
+        orig(self, name, gid)
+        if gi.state == _cabi.GROUP_NONE and gi.referenced:
+            assert self._groups.ids.get(name) == gid  # still interned
+
+    monkeypatch.setattr(alg.HivedAlgorithm, "_release_group_if_gone", spy)
+    assert fuzz_api.run_seed(emu_lib, oracle_lib, 2385, 300) is None
+    assert seen["oracle"], "the scenario no longer occurs in this seed"
+    assert set(seen["oracle"]) <= set(seen["emu"])  # the device's answer is the conservative one
