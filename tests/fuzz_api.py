@@ -68,15 +68,20 @@ def run_seed(lib_a, lib_b, seed: int, n_ops: int, fx=None, verbose=False):
         ra, rb = _call(lambda: op(hs[0], 0)), _call(lambda: op(hs[1], 1))
         return ra, rb
 
+    # the operation mix (defaults: the mix every committed seed number refers to).  FUZZ_MIX = "a,b,c": Schedule below a,
+    # DeleteAllocatedPod below b, DeleteUnallocatedPod below c, node flaps above; FUZZ_RENAME = share of the gangs that
+    # get one of six suffixed names (the rest re-use the spec's own name: more groups re-created under the same name)
+    t_sched, t_del, t_unalloc = (float(x) for x in os.environ.get("FUZZ_MIX", "0.55,0.78,0.85").split(","))
+    p_rename = float(os.environ.get("FUZZ_RENAME", "0.5"))
     try:
         for step in range(n_ops):
             r = rng.random()
             what = None
-            if r < 0.55 or not allocated:
+            if r < t_sched or not allocated:
                 name = rng.choice(spec_names)
                 spec = copy.deepcopy(fx["pss"][name])
                 # gangs get a fresh name now and then, so that both new and further pods of a group occur
-                if rng.random() < 0.5:
+                if rng.random() < p_rename:
                     spec["affinityGroup"]["name"] = "%s-%d" % (spec["affinityGroup"]["name"], rng.randrange(6))
                 serial += 1
                 pods = [alg.Pod(name="p%d" % serial, namespace="fz", uid="u%d" % serial, annotations={}) for _ in range(2)]
@@ -105,7 +110,7 @@ def run_seed(lib_a, lib_b, seed: int, n_ops: int, fx=None, verbose=False):
                     allocated.append(tuple(bound))
                 elif ra[0] == "ok" and ra[1][0] == "preempt" and phase == alg.PREEMPTING_PHASE:
                     preempting.append(tuple(pods))
-            elif r < 0.78:
+            elif r < t_del:
                 pair = allocated.pop(rng.randrange(len(allocated)))
                 what = "DeleteAllocatedPod(%s)" % pair[0].uid
                 ra, rb = both(lambda h, k: h.DeleteAllocatedPod(pair[k]))
@@ -113,7 +118,7 @@ def run_seed(lib_a, lib_b, seed: int, n_ops: int, fx=None, verbose=False):
                     return "seed %d op %d %s: %r != %r" % (seed, step, what, ra, rb)
                 if ra[0] == "platform":
                     return None
-            elif r < 0.85 and preempting:
+            elif r < t_unalloc and preempting:
                 pair = preempting.pop(rng.randrange(len(preempting)))
                 what = "DeleteUnallocatedPod(%s)" % pair[0].uid
                 ra, rb = both(lambda h, k: h.DeleteUnallocatedPod(pair[k]))
