@@ -42,9 +42,33 @@ def _norm(psr):
     return ("wait", psr.pod_wait_info["reason"])
 
 
+def synthetic_fixture():
+    """FUZZ_CLUSTER=synthetic: a small homogeneous 5-level forest in the shape of BASELINE's C3-C5 (GPU / HALF / NODE / RACK /
+    POD: 3 x 3 x 4 nodes x 8 GPUs) with three VCs that hold POD-, RACK- and NODE-level cells and leave two racks to
+    opportunistic pods, and 48 generated pod specs (1-2 members, 1-8 GPUs x 1-4 pods, priorities -1..5, typed and
+    untyped, lazy preemption on half of them) — the same random API calls on a tree whose cells split and merge over
+    three levels above the node."""
+    from hivedscheduler_b200 import config as cfgmod
+    levels = [("HALF", "B200", 4), ("NODE", "HALF", 2), ("RACK", "NODE", 4), ("POD", "RACK", 3)]
+    vcs = {"vcA": [("POD", 1), ("POD.RACK", 1)], "vcB": [("POD.RACK", 2), ("POD.RACK.NODE", 2)], "vcC": [("POD.RACK", 1)]}
+    cfg = cfgmod._synthetic(levels, 3, "NODE", vcs, "n%04d")
+    rng = random.Random(20240911)
+    pss = {}
+    for i in range(48):
+        members = [{"leafCellNumber": rng.choice([1, 2, 4, 8]), "podNumber": rng.choice([1, 1, 2, 3, 4])}]
+        if rng.random() < 0.3:
+            members.append({"leafCellNumber": rng.choice([1, 2, 4, 8]), "podNumber": rng.choice([1, 2])})
+        pss["spec%02d" % i] = {
+            "affinityGroup": {"members": members, "name": "sg%d" % i}, "gangReleaseEnable": False,
+            "ignoreK8sSuggestedNodes": rng.random() < 0.3, "lazyPreemptionEnable": rng.random() < 0.5,
+            "leafCellNumber": members[0]["leafCellNumber"], "leafCellType": "B200" if rng.random() < 0.7 else "",
+            "pinnedCellId": "", "priority": rng.choice([-1, -1, 0, 1, 1, 2, 5]), "virtualCluster": rng.choice(["vcA", "vcB", "vcC"])}
+    return {"design_config": cfg, "pss": pss}
+
+
 def run_seed(lib_a, lib_b, seed: int, n_ops: int, fx=None, verbose=False):
     """Returns None (no divergence) or a description of the first one."""
-    fx = fx or load_fixture()
+    fx = fx or (synthetic_fixture() if os.environ.get("FUZZ_CLUSTER") == "synthetic" else load_fixture())
     rng = random.Random(seed)
     cfg = new_config(copy.deepcopy(fx["design_config"]))
     hs = [alg.HivedAlgorithm(cfg, lib=lib, max_groups=1024, max_pods=4096, max_group_leaves=128, max_group_pods=16)

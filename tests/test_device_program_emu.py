@@ -246,3 +246,15 @@ def test_group_id_stays_with_its_name_while_an_erased_object_is_referenced(emu_l
     assert fuzz_api.run_seed(emu_lib, oracle_lib, 2385, 300) is None
     assert seen["oracle"], "the scenario no longer occurs in this seed"
     assert set(seen["oracle"]) <= set(seen["emu"])  # the device's answer is the conservative one
+
+
+@pytest.mark.parametrize("seed,filtering", [(3, False), (11, True)])
+def test_api_fuzz_on_the_synthetic_five_level_cluster(emu_lib, oracle_lib, seed, filtering, monkeypatch):
+    """tests/fuzz_api.py with FUZZ_CLUSTER=synthetic: the same random API calls on a small forest in the shape of
+    BASELINE's C3-C5 (GPU / HALF / NODE / RACK / POD, VCs with POD-, RACK- and NODE-level cells, generated pod specs with
+    1-2 members): buddy splits and merges over three levels above the node, preemption, bad nodes, opportunistic pods."""
+    import fuzz_api
+    monkeypatch.setenv("FUZZ_CLUSTER", "synthetic")
+    if filtering:
+        monkeypatch.setenv("FUZZ_FILTERING", "1")
+    assert fuzz_api.run_seed(emu_lib, oracle_lib, seed, 300) is None
