@@ -2475,7 +2475,11 @@ struct Core {
           if (leader && topLevel) sel = t;
         }
         if (leader && sel >= 0 && l > 1) scanned += d.p_nchild[sel];
-        if (hv_ballot(leader && sel < 0) || unusable) return false;
+        // below an unbound cell every child is unbound — unless an anomaly left a binding behind (a gang lazy-preempted
+        // on a bad node keeps its bindings, hived_algorithm.go:1332-1335; Filtering-phase binds): the sequential search
+        // would skip such a child, so the general path takes over (API fuzz on the synthetic cluster, seed 1087)
+        const bool staleBound = leader && !topLevel && sel >= 0 && d.p_vcell[sel] >= 0;
+        if (hv_ballot((leader && sel < 0) || staleBound) || unusable) return false;
         if (leader) {
           d.binding[va] = sel; d.vx_stamp[va] = epochNow; d.vx_of[va] = 0;
           if ((sib >> lane) <= 1u) d.vx_of[vpar] = d.vx_of[vpar] + hv_popc(sib);  // the last of the new siblings

@@ -248,6 +248,18 @@ def test_group_id_stays_with_its_name_while_an_erased_object_is_referenced(emu_l
     assert set(seen["oracle"]) <= set(seen["emu"])  # the device's answer is the conservative one
 
 
+def test_batched_mapping_leaves_a_cell_with_a_stale_binding_to_the_general_path(emu_lib, oracle_lib, monkeypatch):
+    """Synthetic-cluster fuzz seed 1087 (names always re-used, Filtering-phase calls): a leaf that kept its binding below
+    an UNBOUND cell (a gang lazy-preempted on a bad node keeps its bindings, hived_algorithm.go:1332-1335).  The
+    reference's mapping skips such a child — here: finds no usable leaf and waits — while the whole-placement mapping
+    (mapPlacementBatched) used to hand it out as "the j-th child" and answered with a preemption."""
+    import fuzz_api
+    monkeypatch.setenv("FUZZ_CLUSTER", "synthetic")
+    monkeypatch.setenv("FUZZ_RENAME", "0.0")
+    monkeypatch.setenv("FUZZ_FILTERING", "1")
+    assert fuzz_api.run_seed(emu_lib, oracle_lib, 1087, 300) is None
+
+
 @pytest.mark.parametrize("seed,filtering", [(3, False), (11, True)])
 def test_api_fuzz_on_the_synthetic_five_level_cluster(emu_lib, oracle_lib, seed, filtering, monkeypatch):
     """tests/fuzz_api.py with FUZZ_CLUSTER=synthetic: the same random API calls on a small forest in the shape of

@@ -239,6 +239,16 @@ def test_cuda_api_fuzz_with_filtering_phase_calls(cuda_lib, oracle_lib, seed, mo
     assert fuzz_api.run_seed(cuda_lib, oracle_lib, seed, 300) is None
 
 
+def test_cuda_api_fuzz_on_the_synthetic_cluster(cuda_lib, oracle_lib, monkeypatch):
+    """Synthetic-cluster fuzz seed 1087 on the GPU (a stale binding below an unbound cell: mapPlacementBatched hands the
+    placement to the general mapping, which finds no usable leaf like the reference)."""
+    import fuzz_api
+    monkeypatch.setenv("FUZZ_CLUSTER", "synthetic")
+    monkeypatch.setenv("FUZZ_RENAME", "0.0")
+    monkeypatch.setenv("FUZZ_FILTERING", "1")
+    assert fuzz_api.run_seed(cuda_lib, oracle_lib, 1087, 300) is None
+
+
 def test_contexts_of_several_threads_take_turns_on_one_device(cuda_lib, oracle_lib):
     """Three host threads, each driving ITS OWN context through the per-call path (API fuzz vs the oracle, every cell
     compared after every call): the contexts share the device's constant bank (one Dev loaded at a time,
